@@ -1,0 +1,117 @@
+"""Parity cases: one table that drives the golden generator, the oracle tests and the GPU parity tests.
+
+TEST INFRASTRUCTURE (see ``oracle/__init__.py``).  A case is ``(kind, cfg)``; inputs and weights are
+regenerated deterministically from seeds (``oracle/synth.py``), only reference OUTPUTS are stored in
+``tests/golden/``.  Shape classes follow SURVEY.md §8a: MCAN (Lq,Lk) ∈ {(30,30),(100,100),(100,30)},
+microbench (30,100), LoRRA h=1 with h·d_k ≠ D, masks (B,1,1,Lk) / (B,1,L,L) / (1,1,L,L) / None,
+a sample whose keys are ALL masked, ragged lengths not multiples of 8/16.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import restated as R
+from . import synth as S
+
+# ----------------------------------------------------------------------------- attention-level cases
+# name: (B, Lq, Lk, D, h, dk, dv, mask_kind, self_attention)
+ATT_CASES = {
+    "sa_text_30":       (2, 30, 30, 512, 8, 64, 64, "pad", True),
+    "sa_vision_100":    (2, 100, 100, 512, 8, 64, 64, "pad", True),
+    "guided_100x30":    (2, 100, 30, 512, 8, 64, 64, "pad", False),
+    "micro_30x100":     (3, 30, 100, 512, 8, 64, 64, "pad_allmasked", False),
+    "lorra_h1":         (2, 20, 37, 512, 1, 64, 64, "pad", False),
+    "dec_causal_13":    (2, 13, 13, 512, 8, 64, 64, "pad+causal", True),
+    "seq_only_17":      (2, 17, 17, 256, 4, 64, 64, "causal", True),
+    "nomask_ragged":    (1, 7, 45, 256, 4, 64, 64, "none", False),
+    "m4c_d96":          (2, 30, 182, 768, 8, 96, 96, "pad", False),
+    "long_600":         (1, 30, 600, 512, 8, 64, 64, "pad", False),
+}
+
+
+def att_spec(D, h, dk, dv, aoa=False, geometry_dg=None):
+    spec = []
+    if aoa:
+        spec += [("informative_attention.weight", (D, 2 * D)), ("informative_attention.bias", (D,)),
+                 ("gated_attention.weight", (D, 2 * D)), ("gated_attention.bias", (D,))]
+    spec += [("attention.fc_q.weight", (h * dk, D)), ("attention.fc_q.bias", (h * dk,)),
+             ("attention.fc_k.weight", (h * dk, D)), ("attention.fc_k.bias", (h * dk,)),
+             ("attention.fc_v.weight", (h * dv, D)), ("attention.fc_v.bias", (h * dv,)),
+             ("attention.fc_o.weight", (D, h * dv)), ("attention.fc_o.bias", (D,))]
+    if geometry_dg is not None:
+        for i in range(h):
+            spec += [(f"attention.fc_gs.{i}.weight", (1, geometry_dg)), (f"attention.fc_gs.{i}.bias", (1,))]
+    spec += [("layer_norm.weight", (D,)), ("layer_norm.bias", (D,))]
+    return spec
+
+
+def pwff_spec(D, d_ff):
+    return [("fc1.weight", (d_ff, D)), ("fc1.bias", (d_ff,)), ("fc2.weight", (D, d_ff)), ("fc2.bias", (D,)),
+            ("layer_norm.weight", (D,)), ("layer_norm.bias", (D,))]
+
+
+def att_inputs(name: str, seed: int = 11):
+    B, Lq, Lk, D, h, dk, dv, mkind, self_att = ATT_CASES[name]
+    g = S._gen(seed, name)
+    keys = S.padded_features(B, Lk, D, seed + 1, min_valid=max(1, Lk // 3), relu_like=False,
+                             all_pad_first=(mkind == "pad_allmasked"))
+    if self_att:
+        queries = keys
+    else:
+        queries = torch.randn((B, Lq, D), generator=g)
+    mask = None
+    if mkind in ("pad", "pad_allmasked"):
+        mask = R.padding_mask(keys, 0)
+    elif mkind == "causal":
+        mask = R.sequential_mask(Lk)
+    elif mkind == "pad+causal":
+        mask = R.self_attention_masks(R.padding_mask(keys, 0), R.sequential_mask(Lk))
+    return dict(queries=queries, keys=keys, values=keys, mask=mask, h=h, d_k=dk, d_v=dv, D=D)
+
+
+# ----------------------------------------------------------------------------- geometry cases  (B, N, D, h, trig)
+GEO_CASES = {
+    "geo_36": (2, 36, 512, 8, True),
+    "geo_100": (1, 100, 512, 8, True),
+    "geo_raw4": (2, 19, 256, 4, False),
+}
+
+
+def geo_inputs(name: str, seed: int = 23):
+    B, N, D, h, trig = GEO_CASES[name]
+    g = S._gen(seed, name)
+    x = torch.randn((B, N, D), generator=g)
+    return dict(x=x, boxes=S.boxes(B, N, seed), h=h, d_k=D // h, d_v=D // h, D=D,
+                d_g=(D // h if trig else 4), trig=trig)
+
+
+# ----------------------------------------------------------------------------- model-level cases
+MCAN_SMALL = dict(B=3, Lt=30, Nv=100, d_feature=256, d_model=128, h=4, layers=2, d_ff=256, vocab=200, answers=53)
+MCAN_FULL = dict(B=2, Lt=30, Nv=100, d_feature=2048, d_model=512, h=8, layers=6, d_ff=2048, vocab=4096, answers=353)
+
+M4C_SMALL = dict(B=3, Lt=7, Nobj=9, Nocr=5, d_obj=32, hidden=96, heads=4, mmt_layers=2, text_layers=2,
+                 vocab=60, T=6)
+
+
+def mcan_inputs(c, seed: int = 1):
+    return dict(region_features=S.padded_features(c["B"], c["Nv"], c["d_feature"], seed, min_valid=36),
+                question_tokens=S.padded_tokens(c["B"], c["Lt"], c["vocab"], seed, min_len=5))
+
+
+def m4c_inputs(c, seed: int = 5):
+    B = c["B"]
+    ocr_n = dict(min_valid=0)
+    f = S.padded_features
+    # one shared validity pattern for the three OCR feature streams (zero rows == padding, mmf_m4c.py:196-199)
+    det = f(B, c["Nocr"], 256, seed + 3, relu_like=False, all_pad_first=True, **ocr_n)
+    valid = (det.abs().sum(-1, keepdim=True) > 0).float()
+    g = S._gen(seed, "m4c")
+    return dict(
+        question_tokens=S.padded_tokens(B, c["Lt"], c["vocab"], seed, min_len=2),
+        region_features=f(B, c["Nobj"], c["d_obj"], seed + 1, min_valid=3),
+        region_boxes=S.boxes(B, c["Nobj"], seed + 2, scale=1.0),
+        ocr_det_features=det,
+        ocr_rec_features=torch.randn((B, c["Nocr"], 256), generator=g) * valid,
+        ocr_fasttext_features=torch.randn((B, c["Nocr"], 300), generator=g) * valid,
+        ocr_boxes=S.boxes(B, c["Nocr"], seed + 4, scale=1.0),
+    )
