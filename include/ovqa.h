@@ -1,0 +1,205 @@
+/*
+ * ovqa.h — C ABI of libovqa_b200.so: the B200 (sm_100a) kernels behind OpenViVQA's cross-modal
+ * attention hot path.
+ *
+ * The reference (hieunghia-pat/OpenViVQA) is pure Python/PyTorch and has no FFI of its own; the boundary a
+ * maintainer binds is therefore "one entry point per op site of the hot path" (SURVEY.md §2.1 table /
+ * §8a).  Each entry point cites the reference lines it replaces.  Conventions:
+ *   - plain pointers + sizes, no torch types; all pointers are DEVICE pointers unless stated otherwise;
+ *   - the CALLER owns every buffer (inputs, outputs, saved statistics, workspaces);
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); entry points never synchronise;
+ *   - return value: 0 on success, a negative OVQA_ERR_* otherwise (never throws, never falls back to CPU);
+ *   - dtype arguments are OVQA_F32 / OVQA_BF16 and name the STORAGE type; arithmetic is always fp32
+ *     accumulate (tcgen05 bf16xbf16->fp32 for the tensor-core GEMMs).
+ */
+#ifndef OVQA_H_
+#define OVQA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OVQA_F32  0
+#define OVQA_BF16 1
+
+#define OVQA_OK                 0
+#define OVQA_ERR_BAD_ARG       -1   /* null pointer, negative size, unsupported dtype            */
+#define OVQA_ERR_BAD_SHAPE     -2   /* shape outside the kernel's supported range                 */
+#define OVQA_ERR_ALIGNMENT     -3   /* pointer / leading dimension not aligned as required        */
+#define OVQA_ERR_CUDA          -4   /* a CUDA runtime/driver call failed (see ovqa_last_cuda_error) */
+#define OVQA_ERR_NO_DEVICE     -5   /* no sm_100 device / driver entry point unavailable          */
+
+/* epilogue flags for ovqa_gemm */
+#define OVQA_EPI_GELU        1      /* exact erf GELU (positionwise_feed_forward.py:24)           */
+#define OVQA_EPI_DGELU       2      /* multiply by GELU'(aux) (backward of the above)             */
+
+#define OVQA_OP_N 0                 /* operand stored with the reduction (K) dimension contiguous */
+#define OVQA_OP_T 1                 /* operand stored with its M/N dimension contiguous           */
+
+int         ovqa_version(void);
+const char* ovqa_error_string(int code);
+int         ovqa_last_cuda_error(void);           /* cudaError_t of the last failing call (thread local) */
+int         ovqa_device_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Dense contraction with fused epilogue.            C[m,n] = epi( sum_k A[m,k] * B[n,k] )
+ *   replaces: nn.Linear at attentions.py:49-51,58 (fc_q/fc_k/fc_v/fc_o), positionwise_feed_forward.py:24-25
+ *             (fc1+GELU, fc2), mmf_m4c.py:387-392 (OcrPtrNet query/key) and their autograd backward
+ *             (dgrad / wgrad).
+ *   A: a_op==OVQA_OP_N -> stored [m, k] (row stride lda);  OVQA_OP_T -> stored [k, m] (row stride lda)
+ *   B: b_op==OVQA_OP_N -> stored [n, k] (row stride ldb);  OVQA_OP_T -> stored [k, n] (row stride ldb)
+ *      (y = x W^T : N,N.   dx = dy W : A N, B T.   dW = dy^T x : A T, B T.)
+ *   ab_dtype: OVQA_BF16 runs on tcgen05/TMEM fed by TMA; OVQA_F32 runs the exact fp32 FFMA path
+ *             (the 1e-4 parity path).  c_dtype: storage of C (and of c2).
+ *   epilogue, in order:  v = acc*alpha + bias[n];  if aux_out: aux_out = v (pre-activation, c_dtype);
+ *             GELU / DGELU(aux_in);  dropout(p, seed, offset) if p>0;  v += residual[m,n] (fp32);
+ *             if beta!=0: v += beta*C_old (fp32 C only);  C = v;  if c2: c2 = bf16(v).
+ *   split_k>1 (wgrad): partial sums are atomically added into fp32 C, which the caller zero-fills (or
+ *             pre-loads); bias/epilogue flags are not allowed with split_k>1.
+ * ------------------------------------------------------------------------------------------------- */
+int ovqa_gemm(const void* A, const void* B, void* C,
+              int64_t m, int64_t n, int64_t k,
+              int64_t lda, int64_t ldb, int64_t ldc,
+              int a_op, int b_op, int ab_dtype, int c_dtype,
+              float alpha, float beta,
+              const float* bias, int epi_flags,
+              const void* aux_in, void* aux_out, int64_t ld_aux,
+              const float* residual, int64_t ld_res,
+              void* c2_bf16, int64_t ldc2,
+              float dropout_p, uint64_t seed, uint64_t offset,
+              int split_k, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Attention core.   out = softmax(q k^T * scale + mask [+ geometry log-bias]) v
+ *   replaces: ScaledDotProductAttention.forward attentions.py:53-57,
+ *             AugmentedGeometryScaledDotProductAttention.forward attentions.py:113-134 (+ models/utils.py
+ *             :102-162 box_relational_embedding, recomputed on the fly from boxes),
+ *             HF eager_attention_forward as called from mmf_m4c.py:349-351.
+ *   q [B, Lq, *] rows of stride ldq, head hd at column hd*dk;  k [B, Lk, *] (ldk);  v [B, Lk, *] (ldv) head at
+ *   hd*dv;  out [B, Lq, h*dv] (ldo).  Batch strides are Lq*ldq etc. (dense batches).
+ *   mask: additive fp32 (value -1e5 in the reference, models/utils.py:56) with element strides
+ *         (mask_sb, mask_sh, mask_sq) and unit stride over keys; any stride may be 0 (broadcast); NULL = none.
+ *         The add happens in fp32 BEFORE the row max is taken.
+ *   geometry (all NULL/0 for the plain core): boxes [B, N, 4] fp32 (x_min,y_min,x_max,y_max), requires
+ *         Lq==Lk==N; geo_w [h, d_g], geo_b [h]; d_g = 64-style trig embedding (geo_trig=1, d_g%8==0) or 4;
+ *         geo_freq [d_g/8] fp32 optional: the 1/1000^(k/(d_g/8)) table (models/utils.py:146-148) as the host
+ *         computed it (NULL -> computed in-kernel with powf).
+ *   lse  [B, h, Lq] fp32, optional: row log-sum-exp, saved for backward / for ovqa_sdpa_probs.
+ *   att  [B, h, Lq, Lk] fp32, optional: the probabilities (direct callers of the core consume them:
+ *         mmf_lorra.py:118-146).
+ * ------------------------------------------------------------------------------------------------- */
+int ovqa_sdpa_fwd(const void* q, const void* k, const void* v, void* out,
+                  int64_t B, int64_t h, int64_t Lq, int64_t Lk, int64_t dk, int64_t dv,
+                  int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                  const float* mask, int64_t mask_sb, int64_t mask_sh, int64_t mask_sq,
+                  const float* boxes, const float* geo_w, const float* geo_b, const float* geo_freq,
+                  int64_t d_g, int geo_trig,
+                  float scale, int dtype, float* lse, float* att, void* stream);
+
+/* Backward of the core (recomputes the probabilities from q,k,mask,lse):
+ *   dq, dk, dv have the layouts of q, k, v (lddq/lddk/lddv).  `delta` [B,h,Lq] fp32 is caller-provided
+ *   scratch (rowsum(dout*out)).  Geometry bias participates in the recomputation; its weight gradient
+ *   (geo_dw [h,d_g], geo_db [h], fp32, ACCUMULATED into) is produced when non-NULL. */
+int ovqa_sdpa_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout,
+                  void* dq, void* dk, void* dv,
+                  int64_t B, int64_t h, int64_t Lq, int64_t Lk, int64_t dk_, int64_t dv_,
+                  int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int64_t lddo,
+                  int64_t lddq, int64_t lddk, int64_t lddv,
+                  const float* mask, int64_t mask_sb, int64_t mask_sh, int64_t mask_sq,
+                  const float* boxes, const float* geo_w, const float* geo_b, const float* geo_freq,
+                  int64_t d_g, int geo_trig,
+                  float* geo_dw, float* geo_db,
+                  float scale, int dtype, const float* lse, float* delta, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * LayerNorm over the last dimension with optional fused residual add.
+ *   replaces: `self.layer_norm(queries + out)` attentions.py:331, positionwise_feed_forward.py:26,
+ *             encoders.py:113 (+ pos), HF BertSelfOutput/BertOutput LayerNorm (eps 1e-12).
+ *   y = LN(x [+ residual]) * gamma + beta [+ post_add];  x/residual/post_add fp32 [rows, D];
+ *   y_f32 and/or y_bf16 (either may be NULL);  mean/rstd [rows] fp32 optional (saved for backward);
+ *   sum_out fp32 optional: x+residual (the LN input, saved for backward when residual is fused).
+ * ------------------------------------------------------------------------------------------------- */
+int ovqa_layernorm_fwd(const float* x, const float* residual, const float* gamma, const float* beta,
+                       const float* post_add, int64_t post_add_rows,
+                       float* y_f32, void* y_bf16, float* sum_out, float* mean, float* rstd,
+                       int64_t rows, int64_t D, float eps, void* stream);
+
+/* dx = LN backward(dy; x, mean, rstd, gamma) [+ dx_add];  dgamma/dbeta are ACCUMULATED into (fp32 [D]).
+ * dx_bf16 optional second output (feeds the following bf16 dgrad/wgrad GEMMs), optionally with the
+ * forward dropout mask re-applied (dropout_p, seed, offset over the [rows, D] index space). */
+int ovqa_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
+                       const float* gamma, const float* dx_add,
+                       float* dx, void* dx_bf16, float* dgamma, float* dbeta,
+                       int64_t rows, int64_t D,
+                       float dropout_p, uint64_t seed, uint64_t offset, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Element-wise helpers of the path.
+ * ------------------------------------------------------------------------------------------------- */
+/* y(bf16) = x(fp32), n elements — staging of GEMM operands (weights once per optimiser step). */
+int ovqa_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream);
+int ovqa_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream);
+/* out[n] (+)= sum_m x[m, n]  — bias gradients.  x dtype f32/bf16, out fp32, accumulate!=0 adds. */
+int ovqa_colsum(const void* x, float* out, int64_t m, int64_t n, int64_t ldx, int dtype, int accumulate,
+                void* stream);
+/* y = dropout(x): y[i] = x[i] * keep(i)/(1-p) with the same counter-based mask as the GEMM/LN epilogues
+ * (element index i, seed, offset); x fp32, y fp32 or bf16 (out_dtype).  p == 0 is a plain cast/copy. */
+int ovqa_dropout_apply(const float* x, void* y, int64_t n, float p, uint64_t seed, uint64_t offset, int out_dtype,
+                       void* stream);
+/* y = a + b (fp32, n elements) */
+int ovqa_add_f32(const float* a, const float* b, float* y, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Box-geometry bias, materialised (only for callers that want it; the fused core recomputes it):
+ *   out[b,h,i,j] = log(max(relu(geo_w[h] . emb(box_i, box_j) + geo_b[h]), 1e-6))
+ *   replaces models/utils.py:102-162 + attentions.py:113-119,131-132.
+ * ------------------------------------------------------------------------------------------------- */
+int ovqa_box_geometry_bias(const float* boxes, const float* geo_w, const float* geo_b, const float* geo_freq,
+                           float* out, int64_t B, int64_t N, int64_t h, int64_t d_g, int geo_trig, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * M4C dynamic pointer network and greedy decode step.
+ * ------------------------------------------------------------------------------------------------- */
+/* scores[b,t,j] = (q[b,t,:] . k[b,j,:]) * scale + mask[b,j]   written into a row of width ld_scores at
+ * column col_offset (so the caller's (B,T,V+Locr) score tensor is filled in place, no torch.cat).
+ *   replaces OcrPtrNet.forward mmf_m4c.py:394-396 (+ the cat at :227) and DynamicPointerNetwork m4c.py:27-33
+ *   (mask_is_bool=1: uint8 mask, masked positions get -inf as in m4c.py:31). */
+int ovqa_ptr_scores(const void* q, const void* k, const void* mask, float* scores,
+                    int64_t B, int64_t T, int64_t L, int64_t d, int64_t ldq, int64_t ldk,
+                    int64_t ld_scores, int64_t col_offset, float scale, int dtype, int mask_is_bool,
+                    void* stream);
+
+/* PrevPredEmbeddings: out[b,t,:] = LN_src(table_row(prev_inds[b,t])) + LN_emb(pos_emb[t] + type_emb[is_ocr])
+ *   where table_row(i) = ans_emb[i] (i < V, LayerNorm ans_*) else ocr_emb[b, i-V] (LayerNorm ocr_*).
+ *   replaces mmf_m4c.py:416-459 without materialising the (B, V+Locr, D) table. fp32 in, fp32 out
+ *   (row stride ld_out so it can write straight into the joint (B, L, D) encoder input). */
+int ovqa_prev_pred_embed(const float* ans_emb, const float* ocr_emb, const int64_t* prev_inds,
+                         const float* pos_emb, const float* type_emb,
+                         const float* ans_g, const float* ans_b, const float* ocr_g, const float* ocr_b,
+                         const float* emb_g, const float* emb_b,
+                         float* out, int64_t B, int64_t T, int64_t V, int64_t Locr, int64_t D,
+                         int64_t ld_out, int64_t out_batch_stride, float eps, void* stream);
+
+/* One greedy step (mmf_m4c.py:247-256): argmax over the score row (first maximal index, as torch.argmax),
+ *   prev_inds[b,1:] = argmax[b,:-1];  last_ids[b] = (last_ids[b]==eos) ? eos : argmax[b,step];
+ *   *all_eos = 1 iff every last_ids[b]==eos (device flag; the host may poll it instead of syncing).
+ *   argmax_out [B,T] int64 (required scratch/output). */
+int ovqa_greedy_step(const float* scores, int64_t* prev_inds, int64_t* last_ids, int64_t* argmax_out,
+                     int32_t* all_eos, int64_t B, int64_t T, int64_t W, int64_t step, int64_t eos_idx,
+                     void* stream);
+
+/* Verification twin of ovqa_gemm's bf16 path on CUDA cores (same operand forms, bias/GELU epilogue): lets the
+ * GPU tests cross-check the tcgen05 kernel on device.  Not on the product path. */
+int ovqa_gemm_bf16_simt(const void* A, const void* B, void* C, int64_t m, int64_t n, int64_t k,
+                        int64_t lda, int64_t ldb, int64_t ldc, int a_op, int b_op, int c_dtype,
+                        float alpha, const float* bias, int epi_flags, void* stream);
+
+/* Diagnostics for tests: fill `out[0..n)` with the dropout keep-mask (1/0 as float) the epilogues use. */
+int ovqa_dropout_mask(float* out, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OVQA_H_ */

@@ -1,0 +1,98 @@
+"""ctypes binding of ``libovqa_b200.so`` (the C ABI declared in ``include/ovqa.h``).
+
+There is no CPU fallback: if the library is missing, or an entry point returns a non-zero code, this module
+raises.  PyTorch is only used by the callers for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libovqa_b200.so")
+
+F32, BF16 = 0, 1
+OP_N, OP_T = 0, 1
+EPI_GELU, EPI_DGELU = 1, 2
+
+_vp, _i64, _i32, _f32, _u64 = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_uint64
+
+# name -> argtypes (restype is int unless listed in _RESTYPES)
+_PROTOS = {
+    "ovqa_version": [],
+    "ovqa_error_string": [_i32],
+    "ovqa_last_cuda_error": [],
+    "ovqa_device_sm_count": [],
+    "ovqa_gemm": [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _f32, _f32, _vp, _i32,
+                  _vp, _vp, _i64, _vp, _i64, _vp, _i64, _f32, _u64, _u64, _i32, _vp],
+    "ovqa_gemm_bf16_simt": [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _f32, _vp, _i32, _vp],
+    "ovqa_sdpa_fwd": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
+                      _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _i32, _vp, _vp, _vp],
+    "ovqa_sdpa_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64,
+                      _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
+                      _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _f32, _i32, _vp, _vp, _vp],
+    "ovqa_layernorm_fwd": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, _vp],
+    "ovqa_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, _u64, _u64, _vp],
+    "ovqa_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
+    "ovqa_cast_bf16_to_f32": [_vp, _vp, _i64, _vp],
+    "ovqa_colsum": [_vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp],
+    "ovqa_add_f32": [_vp, _vp, _vp, _i64, _vp],
+    "ovqa_dropout_apply": [_vp, _vp, _i64, _f32, _u64, _u64, _i32, _vp],
+    "ovqa_box_geometry_bias": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp],
+    "ovqa_ptr_scores": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _i32, _i32, _vp],
+    "ovqa_prev_pred_embed": [_vp] * 12 + [_i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _vp],
+    "ovqa_greedy_step": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp],
+    "ovqa_dropout_mask": [_vp, _i64, _f32, _u64, _u64, _vp],
+}
+_RESTYPES = {"ovqa_error_string": C.c_char_p}
+
+_lib = None
+_lock = threading.Lock()
+
+#: launches of our kernels issued through this binding (bench.py reports it as ``gpu_launches``)
+launch_count = 0
+_KERNELS_PER_CALL = {"ovqa_sdpa_bwd": 3, "ovqa_greedy_step": 2}
+
+
+class OvqaError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the shared library (once).  Raises if it has not been built — never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise OvqaError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  openvivqa_b200 has no CPU / PyTorch fallback.")
+        l = C.CDLL(LIB_PATH)
+        for name, args in _PROTOS.items():
+            fn = getattr(l, name)
+            fn.argtypes = args
+            fn.restype = _RESTYPES.get(name, C.c_int)
+        _lib = l
+    return _lib
+
+
+def declared_symbols():
+    return list(_PROTOS)
+
+
+def check(code: int, what: str):
+    if code != 0:
+        l = lib()
+        msg = l.ovqa_error_string(code).decode()
+        extra = f" (cudaError {l.ovqa_last_cuda_error()})" if code == -4 else ""
+        raise OvqaError(f"{what}: {msg}{extra}")
+
+
+def call(name: str, *args):
+    global launch_count
+    check(getattr(lib(), name)(*args), name)
+    launch_count += _KERNELS_PER_CALL.get(name, 1)

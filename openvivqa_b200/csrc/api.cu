@@ -1,0 +1,131 @@
+// extern "C" entry points of libovqa_b200.so (see include/ovqa.h): argument validation + dispatch.
+#include "attention_simt.cuh"
+
+namespace ovqa {
+
+thread_local int g_last_cuda_error = 0;
+
+int sm_count() {
+    static int n = [] {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return kNumSMsB200;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return kNumSMsB200;
+        return v;
+    }();
+    return n;
+}
+
+template <typename T> int sdpa_fwd_simt_launch(const SdpaArgs&, cudaStream_t);
+template <typename T> int sdpa_bwd_simt_launch(const SdpaArgs&, const void*, void*, void*, void*, int64_t, int64_t, int64_t, int64_t, float*, float*, float*, cudaStream_t);
+int box_geometry_bias_launch(const GeoArg&, float*, int64_t, int64_t, int64_t, cudaStream_t);
+int sdpa_fwd_mma_bf16(const SdpaArgs&, cudaStream_t);   // attention_mma.cu
+bool sdpa_fwd_mma_supported(const SdpaArgs&);
+
+}  // namespace ovqa
+
+using namespace ovqa;
+
+extern "C" int ovqa_version(void) { return 100; }
+
+extern "C" const char* ovqa_error_string(int code) {
+    switch (code) {
+        case OVQA_OK: return "ok";
+        case OVQA_ERR_BAD_ARG: return "bad argument (null pointer, negative size or unsupported dtype/flag)";
+        case OVQA_ERR_BAD_SHAPE: return "shape outside the supported range of this kernel";
+        case OVQA_ERR_ALIGNMENT: return "pointer or leading dimension not aligned as required (16 bytes)";
+        case OVQA_ERR_CUDA: return "CUDA call failed (see ovqa_last_cuda_error)";
+        case OVQA_ERR_NO_DEVICE: return "no usable sm_100 device / driver entry point";
+        default: return "unknown error";
+    }
+}
+extern "C" int ovqa_last_cuda_error(void) { return g_last_cuda_error; }
+extern "C" int ovqa_device_sm_count(void) { return sm_count(); }
+
+extern "C" int ovqa_gemm(const void* A, const void* B, void* C, int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb,
+                         int64_t ldc, int a_op, int b_op, int ab_dtype, int c_dtype, float alpha, float beta, const float* bias,
+                         int epi_flags, const void* aux_in, void* aux_out, int64_t ld_aux, const float* residual, int64_t ld_res,
+                         void* c2_bf16, int64_t ldc2, float dropout_p, uint64_t seed, uint64_t offset, int split_k, void* stream) {
+    if (!A || !B || !C || m < 0 || n < 0 || k < 0) return OVQA_ERR_BAD_ARG;
+    if ((a_op != OVQA_OP_N && a_op != OVQA_OP_T) || (b_op != OVQA_OP_N && b_op != OVQA_OP_T)) return OVQA_ERR_BAD_ARG;
+    if ((ab_dtype != OVQA_F32 && ab_dtype != OVQA_BF16) || (c_dtype != OVQA_F32 && c_dtype != OVQA_BF16)) return OVQA_ERR_BAD_ARG;
+    if (dropout_p < 0.f || dropout_p >= 1.f) return OVQA_ERR_BAD_ARG;
+    if ((epi_flags & OVQA_EPI_DGELU) && !aux_in) return OVQA_ERR_BAD_ARG;
+    if (beta != 0.f && c_dtype != OVQA_F32) return OVQA_ERR_BAD_ARG;
+    if (split_k > 1 && (bias || epi_flags || aux_out || residual || c2_bf16 || dropout_p > 0.f || beta != 0.f)) return OVQA_ERR_BAD_ARG;
+    if (m == 0 || n == 0) return OVQA_OK;
+    // vectorised epilogue accesses: 16-byte alignment of every row start
+    const int64_t c_vec = c_dtype == OVQA_F32 ? 4 : 8;
+    if ((reinterpret_cast<uintptr_t>(C) & 15) || (n % 4 == 0 && ldc % c_vec != 0 && ldc % 4 != 0)) return OVQA_ERR_ALIGNMENT;
+    Epilogue e{alpha, beta, bias, epi_flags, aux_in, aux_out, ld_aux, residual, ld_res, c2_bf16, ldc2, dropout_p, seed, offset, c_dtype};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ab_dtype == OVQA_F32) return gemm_simt_f32((const float*)A, (const float*)B, C, m, n, k, lda, ldb, ldc, a_op, b_op, e, split_k, st);
+    // bf16: tensor cores.  Row pitches must allow TMA (16-byte multiples) and the vectorised epilogue.
+    const bool epi_aligned = (ldc % 4 == 0) && (!residual || ld_res % 4 == 0) && (!(aux_in || aux_out) || ld_aux % 4 == 0) &&
+                             (!c2_bf16 || ldc2 % 4 == 0) && (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0);
+    if (!epi_aligned) return OVQA_ERR_ALIGNMENT;
+    return gemm_tcgen05_bf16((const __nv_bfloat16*)A, (const __nv_bfloat16*)B, C, m, n, k, lda, ldb, ldc, a_op, b_op, e, split_k, st);
+}
+
+// Debug/verification twin of ovqa_gemm's bf16 path on CUDA cores (same operand forms and epilogue); used by
+// the GPU tests to cross-check the tcgen05 kernel element by element.  Not part of the product path.
+extern "C" int ovqa_gemm_bf16_simt(const void* A, const void* B, void* C, int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb,
+                                   int64_t ldc, int a_op, int b_op, int c_dtype, float alpha, const float* bias, int epi_flags,
+                                   void* stream) {
+    if (!A || !B || !C) return OVQA_ERR_BAD_ARG;
+    Epilogue e{alpha, 0.f, bias, epi_flags, nullptr, nullptr, 0, nullptr, 0, nullptr, 0, 0.f, 0, 0, c_dtype};
+    return gemm_simt_bf16((const __nv_bfloat16*)A, (const __nv_bfloat16*)B, C, m, n, k, lda, ldb, ldc, a_op, b_op, e, 1, (cudaStream_t)stream);
+}
+
+static int check_sdpa(const void* q, const void* k, const void* v, int64_t B, int64_t h, int64_t Lq, int64_t Lk, int64_t dk,
+                      int64_t dv, const float* boxes, const float* geo_w, const float* geo_b, int64_t d_g, int geo_trig, int dtype) {
+    if (!q || !k || !v || B < 0 || h <= 0 || Lq < 0 || Lk <= 0 || dk <= 0 || dv <= 0) return OVQA_ERR_BAD_ARG;
+    if (dtype != OVQA_F32 && dtype != OVQA_BF16) return OVQA_ERR_BAD_ARG;
+    if (dk > 128 || dv > 128) return OVQA_ERR_BAD_SHAPE;
+    if (boxes) {
+        if (!geo_w || !geo_b || Lq != Lk) return OVQA_ERR_BAD_ARG;     // attentions.py:116-118,132: self-attention over the boxed set
+        if (geo_trig ? (d_g % 8 != 0 || d_g <= 0) : d_g != 4) return OVQA_ERR_BAD_SHAPE;
+    }
+    return OVQA_OK;
+}
+
+extern "C" int ovqa_sdpa_fwd(const void* q, const void* k, const void* v, void* out, int64_t B, int64_t h, int64_t Lq, int64_t Lk,
+                             int64_t dk, int64_t dv, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, const float* mask,
+                             int64_t mask_sb, int64_t mask_sh, int64_t mask_sq, const float* boxes, const float* geo_w,
+                             const float* geo_b, const float* geo_freq, int64_t d_g, int geo_trig, float scale, int dtype,
+                             float* lse, float* att, void* stream) {
+    int rc = check_sdpa(q, k, v, B, h, Lq, Lk, dk, dv, boxes, geo_w, geo_b, d_g, geo_trig, dtype);
+    if (rc) return rc;
+    if (!out) return OVQA_ERR_BAD_ARG;
+    if (B == 0 || Lq == 0) return OVQA_OK;
+    SdpaArgs a{q, k, v, out, B, h, Lq, Lk, dk, dv, ldq, ldk, ldv, ldo, {mask, mask_sb, mask_sh, mask_sq},
+               {boxes, geo_w, geo_b, geo_freq, (int)d_g, geo_trig}, scale, lse, att};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == OVQA_F32) return sdpa_fwd_simt_launch<float>(a, st);
+    if (sdpa_fwd_mma_supported(a)) return sdpa_fwd_mma_bf16(a, st);
+    return sdpa_fwd_simt_launch<__nv_bfloat16>(a, st);
+}
+
+extern "C" int ovqa_sdpa_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout, void* dq, void* dk,
+                             void* dv, int64_t B, int64_t h, int64_t Lq, int64_t Lk, int64_t dk_, int64_t dv_, int64_t ldq,
+                             int64_t ldk, int64_t ldv, int64_t ldo, int64_t lddo, int64_t lddq, int64_t lddk, int64_t lddv,
+                             const float* mask, int64_t mask_sb, int64_t mask_sh, int64_t mask_sq, const float* boxes,
+                             const float* geo_w, const float* geo_b, const float* geo_freq, int64_t d_g, int geo_trig,
+                             float* geo_dw, float* geo_db, float scale, int dtype, const float* lse, float* delta, void* stream) {
+    int rc = check_sdpa(q, k, v, B, h, Lq, Lk, dk_, dv_, boxes, geo_w, geo_b, d_g, geo_trig, dtype);
+    if (rc) return rc;
+    if (!out || !dout || !dq || !dk || !dv || !lse || !delta) return OVQA_ERR_BAD_ARG;
+    if ((geo_dw == nullptr) != (geo_db == nullptr)) return OVQA_ERR_BAD_ARG;
+    if (B == 0 || Lq == 0) return OVQA_OK;
+    SdpaArgs a{q, k, v, const_cast<void*>(out), B, h, Lq, Lk, dk_, dv_, ldq, ldk, ldv, ldo, {mask, mask_sb, mask_sh, mask_sq},
+               {boxes, geo_w, geo_b, geo_freq, (int)d_g, geo_trig}, scale, const_cast<float*>(lse), nullptr};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == OVQA_F32) return sdpa_bwd_simt_launch<float>(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv, delta, geo_dw, geo_db, st);
+    return sdpa_bwd_simt_launch<__nv_bfloat16>(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv, delta, geo_dw, geo_db, st);
+}
+
+extern "C" int ovqa_box_geometry_bias(const float* boxes, const float* geo_w, const float* geo_b, const float* geo_freq, float* out,
+                                      int64_t B, int64_t N, int64_t h, int64_t d_g, int geo_trig, void* stream) {
+    if (!boxes || !geo_w || !geo_b || !out || B < 0 || N < 0 || h <= 0) return OVQA_ERR_BAD_ARG;
+    if (geo_trig ? (d_g % 8 != 0 || d_g <= 0) : d_g != 4) return OVQA_ERR_BAD_SHAPE;
+    return box_geometry_bias_launch({boxes, geo_w, geo_b, geo_freq, (int)d_g, geo_trig}, out, B, N, h, (cudaStream_t)stream);
+}

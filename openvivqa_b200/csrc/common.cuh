@@ -1,0 +1,139 @@
+// Shared device/host helpers for libovqa_b200 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ovqa.h"
+
+namespace ovqa {
+
+extern thread_local int g_last_cuda_error;
+
+inline int cuda_fail(cudaError_t e) {
+    g_last_cuda_error = (int)e;
+    return OVQA_ERR_CUDA;
+}
+#define OVQA_CUDA_OK(expr)                                    \
+    do {                                                      \
+        cudaError_t _e = (expr);                              \
+        if (_e != cudaSuccess) return ::ovqa::cuda_fail(_e);  \
+    } while (0)
+#define OVQA_LAUNCH_OK() OVQA_CUDA_OK(cudaPeekAtLastError())
+
+constexpr int kNumSMsB200 = 148;
+int sm_count();
+
+// ----------------------------------------------------------------------------- element access
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+    __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&u);
+    return __bfloat1622float2(t);
+}
+
+// ----------------------------------------------------------------------------- warp / block reductions
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ----------------------------------------------------------------------------- exact GELU (erf), F.gelu default
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float dgelu_erf(float x) {
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+    return cdf + x * pdf;
+}
+
+// ----------------------------------------------------------------------------- counter-based dropout RNG
+// Philox4x32-10 keyed by `seed`, counter = (offset + element_index/4); lane = element_index%4.
+// Stateless, so the backward pass regenerates the forward mask from (seed, offset) — no mask tensor.
+__device__ __forceinline__ uint4 philox4x32_10(uint64_t ctr, uint64_t key) {
+    uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0x243F6A88u, c3 = 0x85A308D3u;
+    uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+// keep-scale for element `idx`: 1/(1-p) if kept else 0.
+__device__ __forceinline__ float dropout_scale(uint64_t idx, float p, float inv_keep, uint64_t seed, uint64_t offset) {
+    const uint4 r = philox4x32_10(offset + (idx >> 2), seed);
+    const uint32_t lane = (uint32_t)(idx & 3);
+    const uint32_t u = lane == 0 ? r.x : lane == 1 ? r.y : lane == 2 ? r.z : r.w;
+    // uniform in [0,1): keep iff u >= p
+    return ((float)(u >> 8) * (1.0f / 16777216.0f) >= p) ? inv_keep : 0.0f;
+}
+// four consecutive elements starting at idx (idx % 4 == 0): one Philox call
+__device__ __forceinline__ float4 dropout_scale4(uint64_t idx, float p, float inv_keep, uint64_t seed, uint64_t offset) {
+    const uint4 r = philox4x32_10(offset + (idx >> 2), seed);
+    float4 o;
+    o.x = ((float)(r.x >> 8) * (1.0f / 16777216.0f) >= p) ? inv_keep : 0.0f;
+    o.y = ((float)(r.y >> 8) * (1.0f / 16777216.0f) >= p) ? inv_keep : 0.0f;
+    o.z = ((float)(r.z >> 8) * (1.0f / 16777216.0f) >= p) ? inv_keep : 0.0f;
+    o.w = ((float)(r.w >> 8) * (1.0f / 16777216.0f) >= p) ? inv_keep : 0.0f;
+    return o;
+}
+
+// ----------------------------------------------------------------------------- GEMM epilogue description
+struct Epilogue {
+    float alpha, beta;
+    const float* bias;
+    int flags;
+    const void* aux_in;   // c_dtype, ld_aux
+    void* aux_out;        // c_dtype, ld_aux
+    int64_t ld_aux;
+    const float* residual;
+    int64_t ld_res;
+    void* c2;             // bf16 copy
+    int64_t ldc2;
+    float dropout_p;
+    uint64_t seed, offset;
+    int c_dtype;
+};
+
+// Apply the epilogue to one accumulator value at (row, col); C addressing is left to the caller.
+template <typename TC>
+__device__ __forceinline__ float epilogue_value(const Epilogue& e, float acc, int64_t row, int64_t col, int64_t n_cols,
+                                                const TC* c_old_ptr) {
+    float v = acc * e.alpha;
+    if (e.bias) v += __ldg(e.bias + col);
+    if (e.aux_out) reinterpret_cast<TC*>(e.aux_out)[row * e.ld_aux + col] = from_f32<TC>(v);
+    if (e.flags & OVQA_EPI_GELU) v = gelu_erf(v);
+    if (e.flags & OVQA_EPI_DGELU) v *= dgelu_erf(to_f32<TC>(reinterpret_cast<const TC*>(e.aux_in)[row * e.ld_aux + col]));
+    if (e.dropout_p > 0.0f) v *= dropout_scale((uint64_t)(row * n_cols + col), e.dropout_p, 1.0f / (1.0f - e.dropout_p), e.seed, e.offset);
+    if (e.residual) v += __ldg(e.residual + row * e.ld_res + col);
+    if (e.beta != 0.0f && c_old_ptr) v += e.beta * to_f32<TC>(*c_old_ptr);
+    return v;
+}
+
+// internal entry points (implemented in the per-kernel .cu files)
+int gemm_simt_f32(const float* A, const float* B, void* C, int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb,
+                  int64_t ldc, int a_op, int b_op, const Epilogue& epi, int split_k, cudaStream_t st);
+int gemm_simt_bf16(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, int64_t m, int64_t n, int64_t k, int64_t lda,
+                   int64_t ldb, int64_t ldc, int a_op, int b_op, const Epilogue& epi, int split_k, cudaStream_t st);
+int gemm_tcgen05_bf16(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, int64_t m, int64_t n, int64_t k,
+                      int64_t lda, int64_t ldb, int64_t ldc, int a_op, int b_op, const Epilogue& epi, int split_k,
+                      cudaStream_t st);
+
+}  // namespace ovqa

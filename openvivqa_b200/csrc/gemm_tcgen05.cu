@@ -1,0 +1,434 @@
+// bf16 x bf16 -> fp32 GEMM on 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM), operands staged
+// in shared memory by TMA (cp.async.bulk.tensor, SWIZZLE_128B), persistent over output tiles with a
+// double-buffered TMEM accumulator so the epilogue of tile i overlaps the mainloop of tile i+1.
+//
+// Warp roles (192 threads, 1 CTA/SM):  warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator +
+// MMA issuer (one elected lane), warps 2..5 = epilogue (TMEM -> registers -> fused epilogue -> global).
+//
+// Operand forms (ovqa.h): OVQA_OP_N = reduction dim contiguous ("K-major" UMMA operand, one TMA box of
+// 64(k) x ROWS); OVQA_OP_T = M/N dim contiguous ("MN-major" UMMA operand, ROWS/64 TMA boxes of 64(mn) x 64(k)).
+// The latter lets dgrad (dy W) and wgrad (dy^T x) read the tensors where they lie, with no transposes.
+#include <cuda.h>
+#include <cstdio>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+
+namespace ovqa {
+
+namespace {
+
+constexpr int BM = 128;          // UMMA M (cta_group::1)
+constexpr int BK = 64;           // 64 bf16 = 128 B = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 192;
+constexpr int kAccStages = 2;
+
+template <int BN> struct Cfg {
+    static constexpr int kStages = BN == 256 ? 4 : 6;
+    static constexpr int kABytes = BM * BK * 2;
+    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kTmemCols = kAccStages * BN;  // 256 or 512: power of two
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// ----------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug (wrong tx byte count, missing arrive) traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {  // ~2 s at 1.9 GHz
+            printf("ovqa gemm_tcgen05: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout_type [61,64) (2 = SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+           (1ull << 46) | (2ull << 61);
+}
+// UMMA instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=BF16 [7,10)=1, b=BF16 [10,13)=1,
+// a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ----------------------------------------------------------------------------- kernel
+template <int BN, bool A_MN, bool B_MN, typename TC>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, TC* __restrict__ C,
+                    int64_t m, int64_t n, int64_t k, int64_t ldc, Epilogue epi, int split_k) {
+    using cfg = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + cfg::kStages * cfg::kABytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + cfg::kStages * cfg::kStageBytes);
+    uint64_t* full_bar = bars;                              // [kStages]   TMA -> MMA
+    uint64_t* empty_bar = bars + cfg::kStages;              // [kStages]   MMA -> TMA
+    uint64_t* tmem_full = bars + 2 * cfg::kStages;          // [2]         MMA -> epilogue
+    uint64_t* tmem_empty = tmem_full + kAccStages;          // [2]         epilogue -> MMA
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + kAccStages);
+
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int num_m_tiles = (int)((m + BM - 1) / BM), num_n_tiles = (int)((n + BN - 1) / BN);
+    const int num_k_blocks = (int)((k + BK - 1) / BK);
+    const int num_tiles = num_m_tiles * num_n_tiles * split_k;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
+        for (int i = 0; i < cfg::kStages; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
+        for (int i = 0; i < kAccStages; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"((uint32_t)cfg::kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    // tile -> (m tile, n tile, k split); n fastest so concurrently running CTAs share the A (activation) tile in L2
+    auto decode = [&](int tile, int& mt, int& nt, int& kb0, int& kb1) {
+        const int ks = tile % split_k;
+        const int t2 = tile / split_k;
+        nt = t2 % num_n_tiles;
+        mt = t2 / num_n_tiles;
+        const int base = num_k_blocks / split_k, rem = num_k_blocks % split_k;
+        kb0 = ks * base + min(ks, rem);
+        kb1 = kb0 + base + (ks < rem ? 1 : 0);
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int mt, nt, kb0, kb1;
+                decode(tile, mt, nt, kb0, kb1);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(empty_bar + stage, phase ^ 1);
+                    mbar_expect_tx(full_bar + stage, cfg::kStageBytes);
+                    uint8_t* sa = smem_a + stage * cfg::kABytes;
+                    uint8_t* sb = smem_b + stage * cfg::kBBytes;
+                    if constexpr (!A_MN) {
+                        tma_load_2d(sa, &tma_a, full_bar + stage, kb * BK, mt * BM);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &tma_a, full_bar + stage, mt * BM + j * 64, kb * BK);
+                    }
+                    if constexpr (!B_MN) {
+                        tma_load_2d(sb, &tma_b, full_bar + stage, kb * BK, nt * BN);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tma_b, full_bar + stage, nt * BN + j * 64, kb * BK);
+                    }
+                    if (++stage == cfg::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BM, BN, A_MN, B_MN);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int mt, nt, kb0, kb1;
+                decode(tile, mt, nt, kb0, kb1);
+                mbar_wait(tmem_empty + acc, acc_phase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(full_bar + stage, phase);
+                    tcgen05_fence_after();
+                    const uint32_t a_addr = smem_u32(smem_a + stage * cfg::kABytes);
+                    const uint32_t b_addr = smem_u32(smem_b + stage * cfg::kBBytes);
+#pragma unroll
+                    for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                        // K-major: 8-row groups are 1024 B apart (SBO), K step of 16 elems = +32 B inside the swizzled row.
+                        // MN-major: 64-elem MN blocks are 8192 B apart (LBO), 8-k-row groups 1024 B apart (SBO), K step = +2048 B.
+                        const uint64_t a_desc = A_MN ? make_smem_desc(a_addr + kk * 2048, 8192, 1024) : make_smem_desc(a_addr + kk * 32, 16, 1024);
+                        const uint64_t b_desc = B_MN ? make_smem_desc(b_addr + kk * 2048, 8192, 1024) : make_smem_desc(b_addr + kk * 32, 16, 1024);
+                        tcgen05_mma_bf16(d_tmem, a_desc, b_desc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+                    }
+                    tcgen05_commit(empty_bar + stage);  // frees the smem slot when these MMAs retire
+                    if (++stage == cfg::kStages) { stage = 0; phase ^= 1; }
+                }
+                tcgen05_commit(tmem_full + acc);        // accumulator ready for the epilogue
+                if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue warps 2..5
+        const int lane_group = warp % 4;                  // tcgen05.ld: warp w may touch TMEM lanes [32*(w%4), +32)
+        const int row_in_tile = lane_group * 32 + lane;   // accumulator row == TMEM lane (M=128, cta_group::1)
+        const bool vec_ok = (n % 4 == 0);
+        const float inv_keep = epi.dropout_p > 0.f ? 1.0f / (1.0f - epi.dropout_p) : 1.0f;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            int mt, nt, kb0, kb1;
+            decode(tile, mt, nt, kb0, kb1);
+            mbar_wait(tmem_full + acc, acc_phase);
+            tcgen05_fence_after();
+            const int64_t row = (int64_t)mt * BM + row_in_tile;
+            const uint32_t t_row = tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(t_row + (uint32_t)c0, r);
+                tmem_ld_wait();
+                const int64_t col0 = (int64_t)nt * BN + c0;
+                if (row < m && col0 < n) {
+                    if (split_k > 1) {
+                        if constexpr (sizeof(TC) == 4) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (col0 + j < n) atomicAdd(reinterpret_cast<float*>(C) + row * ldc + col0 + j, __uint_as_float(r[j]) * epi.alpha);
+                        }
+                    } else if (vec_ok && col0 + 32 <= n) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const int64_t col = col0 + j;
+                            float v[4] = {__uint_as_float(r[j]) * epi.alpha, __uint_as_float(r[j + 1]) * epi.alpha,
+                                          __uint_as_float(r[j + 2]) * epi.alpha, __uint_as_float(r[j + 3]) * epi.alpha};
+                            if (epi.bias) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col));
+                                v[0] += b4.x; v[1] += b4.y; v[2] += b4.z; v[3] += b4.w;
+                            }
+                            if (epi.aux_out) {
+                                TC* ap = reinterpret_cast<TC*>(epi.aux_out) + row * epi.ld_aux + col;
+                                if constexpr (sizeof(TC) == 4) *reinterpret_cast<float4*>(ap) = make_float4(v[0], v[1], v[2], v[3]);
+                                else *reinterpret_cast<uint2*>(ap) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+                            }
+                            if (epi.flags & OVQA_EPI_GELU) {
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) v[t] = gelu_erf(v[t]);
+                            }
+                            if (epi.flags & OVQA_EPI_DGELU) {
+                                const TC* ap = reinterpret_cast<const TC*>(epi.aux_in) + row * epi.ld_aux + col;
+                                float a[4];
+                                if constexpr (sizeof(TC) == 4) { const float4 t4 = *reinterpret_cast<const float4*>(ap); a[0] = t4.x; a[1] = t4.y; a[2] = t4.z; a[3] = t4.w; }
+                                else { const uint2 u = *reinterpret_cast<const uint2*>(ap); const float2 lo = unpack_bf16x2(u.x), hi = unpack_bf16x2(u.y); a[0] = lo.x; a[1] = lo.y; a[2] = hi.x; a[3] = hi.y; }
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) v[t] *= dgelu_erf(a[t]);
+                            }
+                            if (epi.dropout_p > 0.f) {
+                                const float4 s4 = dropout_scale4((uint64_t)(row * n + col), epi.dropout_p, inv_keep, epi.seed, epi.offset);
+                                v[0] *= s4.x; v[1] *= s4.y; v[2] *= s4.z; v[3] *= s4.w;
+                            }
+                            if (epi.residual) {
+                                const float4 r4 = __ldg(reinterpret_cast<const float4*>(epi.residual + row * epi.ld_res + col));
+                                v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
+                            }
+                            TC* cp = C + row * ldc + col;
+                            if constexpr (sizeof(TC) == 4) {
+                                if (epi.beta != 0.f) { const float4 o = *reinterpret_cast<const float4*>(cp); v[0] += epi.beta * o.x; v[1] += epi.beta * o.y; v[2] += epi.beta * o.z; v[3] += epi.beta * o.w; }
+                                *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+                            } else {
+                                *reinterpret_cast<uint2*>(cp) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+                            }
+                            if (epi.c2) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(epi.c2) + row * epi.ldc2 + col) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+                        }
+                    } else {
+                        for (int j = 0; j < 32; ++j) {
+                            const int64_t col = col0 + j;
+                            if (col >= n) break;
+                            TC* cp = C + row * ldc + col;
+                            const float v = epilogue_value<TC>(epi, __uint_as_float(r[j]), row, col, n, cp);
+                            *cp = from_f32<TC>(v);
+                            if (epi.c2) reinterpret_cast<__nv_bfloat16*>(epi.c2)[row * epi.ldc2 + col] = __float2bfloat16_rn(v);
+                        }
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty + acc);
+            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)cfg::kTmemCols) : "memory");
+    }
+}
+
+// ----------------------------------------------------------------------------- host: TMA descriptors
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode() {
+    static EncodeFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return reinterpret_cast<EncodeFn>(p);
+    }();
+    return fn;
+}
+
+struct MapKey {
+    const void* ptr; uint64_t inner, outer, ld; uint32_t box_inner, box_outer;
+    bool operator==(const MapKey& o) const { return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner && box_outer == o.box_outer; }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        size_t h = std::hash<const void*>()(k.ptr);
+        auto mix = [&](uint64_t v) { h ^= std::hash<uint64_t>()(v) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+        mix(k.inner); mix(k.outer); mix(k.ld); mix(((uint64_t)k.box_inner << 32) | k.box_outer);
+        return h;
+    }
+};
+
+// 2-D bf16 tensor [outer, inner] with row stride ld (elements); box [box_outer, box_inner]; SWIZZLE_128B; OOB -> 0.
+int make_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer) {
+    static std::mutex mu;
+    static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+    const MapKey key{ptr, inner, outer, ld, box_inner, box_outer};
+    {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) { *out = it->second; return OVQA_OK; }
+    }
+    EncodeFn enc = get_encode();
+    if (!enc) return OVQA_ERR_NO_DEVICE;
+    const cuuint64_t dims[2] = {inner, outer};
+    const cuuint64_t strides[1] = {ld * 2};
+    const cuuint32_t box[2] = {box_inner, box_outer};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { g_last_cuda_error = (int)r; return OVQA_ERR_CUDA; }
+    std::lock_guard<std::mutex> g(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache.emplace(key, *out);
+    return OVQA_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb,
+           int64_t ldc, const Epilogue& epi, int split_k, cudaStream_t st) {
+    using cfg = Cfg<BN>;
+    CUtensorMap ma, mb;
+    int rc;
+    // K-major: tensor [rows, k] box {64 k, ROWS};  MN-major: tensor [k, rows] box {64 rows, 64 k}
+    rc = A_MN ? make_map(&ma, A, (uint64_t)m, (uint64_t)k, (uint64_t)lda, 64, BK) : make_map(&ma, A, (uint64_t)k, (uint64_t)m, (uint64_t)lda, BK, BM);
+    if (rc) return rc;
+    rc = B_MN ? make_map(&mb, B, (uint64_t)n, (uint64_t)k, (uint64_t)ldb, 64, BK) : make_map(&mb, B, (uint64_t)k, (uint64_t)n, (uint64_t)ldb, BK, BN);
+    if (rc) return rc;
+    const int num_k_blocks = (int)((k + BK - 1) / BK);
+    if (split_k > num_k_blocks) split_k = num_k_blocks;
+    const int64_t tiles = ((m + BM - 1) / BM) * ((n + BN - 1) / BN) * split_k;
+    const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+    if (epi.c_dtype == OVQA_F32) {
+        auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, float>;
+        static bool attr_set = false;
+        if (!attr_set) { OVQA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::kSmemBytes)); attr_set = true; }
+        kern<<<grid, kThreads, cfg::kSmemBytes, st>>>(ma, mb, (float*)C, m, n, k, ldc, epi, split_k);
+    } else {
+        auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, __nv_bfloat16>;
+        static bool attr_set = false;
+        if (!attr_set) { OVQA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::kSmemBytes)); attr_set = true; }
+        kern<<<grid, kThreads, cfg::kSmemBytes, st>>>(ma, mb, (__nv_bfloat16*)C, m, n, k, ldc, epi, split_k);
+    }
+    OVQA_LAUNCH_OK();
+    return OVQA_OK;
+}
+
+}  // namespace
+
+int gemm_tcgen05_bf16(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, int64_t m, int64_t n, int64_t k, int64_t lda,
+                      int64_t ldb, int64_t ldc, int a_op, int b_op, const Epilogue& epi, int split_k, cudaStream_t st) {
+    if (m == 0 || n == 0) return OVQA_OK;
+    if (k <= 0) return OVQA_ERR_BAD_SHAPE;
+    // TMA: base 16-byte aligned, row pitch multiple of 16 bytes
+    if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) || (lda % 8) || (ldb % 8)) return OVQA_ERR_ALIGNMENT;
+    if (split_k < 1) split_k = 1;
+    if (split_k > 1 && epi.c_dtype != OVQA_F32) return OVQA_ERR_BAD_ARG;
+    const bool a_mn = a_op == OVQA_OP_T, b_mn = b_op == OVQA_OP_T;
+    // wide-N tiles when there are enough of them to fill the machine; BN=128 otherwise
+    const int64_t tiles256 = ((m + BM - 1) / BM) * ((n + 255) / 256) * split_k;
+    const bool wide = (n % 256 == 0 || n > 1024) && tiles256 >= 2 * sm_count();
+#define OVQA_DISPATCH(BN_)                                                                                                 \
+    do {                                                                                                                   \
+        if (!a_mn && !b_mn) return launch<BN_, false, false>(A, B, C, m, n, k, lda, ldb, ldc, epi, split_k, st);           \
+        if (!a_mn && b_mn) return launch<BN_, false, true>(A, B, C, m, n, k, lda, ldb, ldc, epi, split_k, st);             \
+        if (a_mn && b_mn) return launch<BN_, true, true>(A, B, C, m, n, k, lda, ldb, ldc, epi, split_k, st);               \
+        return launch<BN_, true, false>(A, B, C, m, n, k, lda, ldb, ldc, epi, split_k, st);                                \
+    } while (0)
+    if (wide) OVQA_DISPATCH(256);
+    OVQA_DISPATCH(128);
+#undef OVQA_DISPATCH
+}
+
+}  // namespace ovqa

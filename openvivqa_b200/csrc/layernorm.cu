@@ -1,0 +1,298 @@
+// Residual + LayerNorm (forward/backward) and the small element-wise helpers of the path.
+// HBM-bound: one warp per row, the row lives in registers (128-bit loads/stores), statistics by warp shuffle;
+// two-pass mean/variance in fp32 like ATen's LayerNorm.  Algorithmic bytes: fwd 2-3 x 4*D per row.
+#include "common.cuh"
+
+namespace ovqa {
+
+namespace {
+
+constexpr int kMaxVec = 8;  // float4 per lane -> D <= 1024
+constexpr int kRowsPerCta = 4;
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+__global__ void __launch_bounds__(kRowsPerCta * 32)
+layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ residual, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, const float* __restrict__ post_add, int64_t post_rows,
+                     float* __restrict__ y, __nv_bfloat16* __restrict__ y16, float* __restrict__ sum_out,
+                     float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t rows, int D, float eps) {
+    const int64_t row = (int64_t)blockIdx.x * kRowsPerCta + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
+    if (row >= rows) return;
+    const int nvec = D / 4;
+    float4 v[kMaxVec];
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < kMaxVec; ++t) {
+        const int c = lane + 32 * t;
+        if (c < nvec) {
+            v[t] = ld4(x + row * D + 4 * c);
+            if (residual) v[t] = add4(v[t], ld4(residual + row * D + 4 * c));
+            if (sum_out) *reinterpret_cast<float4*>(sum_out + row * D + 4 * c) = v[t];
+            s += (v[t].x + v[t].y) + (v[t].z + v[t].w);
+        }
+    }
+    const float mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int t = 0; t < kMaxVec; ++t) {
+        const int c = lane + 32 * t;
+        if (c < nvec) {
+            const float a = v[t].x - mean, b = v[t].y - mean, cc = v[t].z - mean, d = v[t].w - mean;
+            q += (a * a + b * b) + (cc * cc + d * d);
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+    if (lane == 0) { if (mean_out) mean_out[row] = mean; if (rstd_out) rstd_out[row] = rstd; }
+#pragma unroll
+    for (int t = 0; t < kMaxVec; ++t) {
+        const int c = lane + 32 * t;
+        if (c < nvec) {
+            const float4 g = ld4(gamma + 4 * c), bb = ld4(beta + 4 * c);
+            float4 o = make_float4((v[t].x - mean) * rstd * g.x + bb.x, (v[t].y - mean) * rstd * g.y + bb.y,
+                                   (v[t].z - mean) * rstd * g.z + bb.z, (v[t].w - mean) * rstd * g.w + bb.w);
+            if (post_add) o = add4(o, ld4(post_add + (row % post_rows) * D + 4 * c));
+            if (y) *reinterpret_cast<float4*>(y + row * D + 4 * c) = o;
+            if (y16) *reinterpret_cast<uint2*>(y16 + row * D + 4 * c) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kRowsPerCta * 32)
+layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dx_add,
+                     float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                     int64_t rows, int D, float p, float inv_keep, uint64_t seed, uint64_t offset) {
+    __shared__ float red[kRowsPerCta][32 * 4 + 1];
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int nvec = D / 4;
+    float4 g[kMaxVec], ag[kMaxVec], ab[kMaxVec];
+#pragma unroll
+    for (int t = 0; t < kMaxVec; ++t) {
+        const int c = lane + 32 * t;
+        g[t] = c < nvec ? ld4(gamma + 4 * c) : make_float4(0, 0, 0, 0);
+        ag[t] = make_float4(0, 0, 0, 0);
+        ab[t] = make_float4(0, 0, 0, 0);
+    }
+    for (int64_t row = (int64_t)blockIdx.x * kRowsPerCta + warp; row < rows; row += (int64_t)gridDim.x * kRowsPerCta) {
+        const float mu = mean[row], rs = rstd[row];
+        float4 xh[kMaxVec], d[kMaxVec];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int t = 0; t < kMaxVec; ++t) {
+            const int c = lane + 32 * t;
+            if (c < nvec) {
+                const float4 xv = ld4(x + row * D + 4 * c);
+                d[t] = ld4(dy + row * D + 4 * c);
+                xh[t] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+                ab[t] = add4(ab[t], d[t]);
+                ag[t] = add4(ag[t], make_float4(d[t].x * xh[t].x, d[t].y * xh[t].y, d[t].z * xh[t].z, d[t].w * xh[t].w));
+                d[t] = make_float4(d[t].x * g[t].x, d[t].y * g[t].y, d[t].z * g[t].z, d[t].w * g[t].w);  // dy * gamma
+                s1 += (d[t].x + d[t].y) + (d[t].z + d[t].w);
+                s2 += (d[t].x * xh[t].x + d[t].y * xh[t].y) + (d[t].z * xh[t].z + d[t].w * xh[t].w);
+            }
+        }
+        s1 = warp_sum(s1) / (float)D;
+        s2 = warp_sum(s2) / (float)D;
+#pragma unroll
+        for (int t = 0; t < kMaxVec; ++t) {
+            const int c = lane + 32 * t;
+            if (c < nvec) {
+                float4 o = make_float4(rs * (d[t].x - s1 - xh[t].x * s2), rs * (d[t].y - s1 - xh[t].y * s2),
+                                       rs * (d[t].z - s1 - xh[t].z * s2), rs * (d[t].w - s1 - xh[t].w * s2));
+                if (dx_add) o = add4(o, ld4(dx_add + row * D + 4 * c));
+                if (dx) *reinterpret_cast<float4*>(dx + row * D + 4 * c) = o;
+                if (dx16) {
+                    if (p > 0.f) {
+                        const float4 s4 = dropout_scale4((uint64_t)(row * D + 4 * c), p, inv_keep, seed, offset);
+                        o = make_float4(o.x * s4.x, o.y * s4.y, o.z * s4.z, o.w * s4.w);
+                    }
+                    *reinterpret_cast<uint2*>(dx16 + row * D + 4 * c) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+                }
+            }
+        }
+    }
+    // dgamma / dbeta: reduce the 4 warps through smem, then one atomicAdd per column per CTA
+    if (!dgamma && !dbeta) return;
+    for (int pass = 0; pass < 2; ++pass) {
+        float* dst = pass == 0 ? dgamma : dbeta;
+        if (!dst) continue;
+#pragma unroll
+        for (int t = 0; t < kMaxVec; ++t) {
+            const int c = lane + 32 * t;
+            const float4 a = pass == 0 ? ag[t] : ab[t];
+            __syncthreads();
+            red[warp][lane * 4 + 0] = a.x; red[warp][lane * 4 + 1] = a.y; red[warp][lane * 4 + 2] = a.z; red[warp][lane * 4 + 3] = a.w;
+            __syncthreads();
+            if (warp == 0 && c < nvec) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int w = 0; w < kRowsPerCta; ++w) s += red[w][lane * 4 + e];
+                    atomicAdd(dst + 4 * c + e, s);
+                }
+            }
+        }
+    }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 8;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+        if (i + 8 <= n) {
+            const float4 a = ld4(x + i), b = ld4(x + i + 4);
+            *reinterpret_cast<uint4*>(y + i) = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+        } else {
+            for (int64_t j = i; j < n; ++j) y[j] = __float2bfloat16_rn(x[j]);
+        }
+    }
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = __bfloat162float(x[i]);
+}
+__global__ void add_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+        if (i + 4 <= n) *reinterpret_cast<float4*>(y + i) = add4(ld4(a + i), ld4(b + i));
+        else for (int64_t j = i; j < n; ++j) y[j] = a[j] + b[j];
+    }
+}
+
+// out[c] += sum over a slab of rows; block (32 cols, 8 row lanes)
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ x, float* __restrict__ out, int64_t m, int64_t n, int64_t ldx, int64_t rows_per_block) {
+    __shared__ float red[8][33];
+    const int64_t col = (int64_t)blockIdx.x * 32 + threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(m, r0 + rows_per_block);
+    float s = 0.f;
+    if (col < n)
+        for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) s += to_f32<T>(x[r * ldx + col]);
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && col < n) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+        atomicAdd(out + col, t);
+    }
+}
+
+template <typename TO>
+__global__ void dropout_apply_kernel(const float* __restrict__ x, TO* __restrict__ y, int64_t n, float p, float inv_keep, uint64_t seed, uint64_t offset) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+        float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (p > 0.f) s4 = dropout_scale4((uint64_t)i, p, inv_keep, seed, offset);
+        const float sc[4] = {s4.x, s4.y, s4.z, s4.w};
+        for (int j = 0; j < 4 && i + j < n; ++j) y[i + j] = from_f32<TO>(x[i + j] * sc[j]);
+    }
+}
+
+__global__ void dropout_mask_kernel(float* out, int64_t n, float p, uint64_t seed, uint64_t offset) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = dropout_scale((uint64_t)i, p, 1.0f, seed, offset);
+}
+
+int grid_for(int64_t work_items, int threads) {
+    int64_t g = (work_items + threads - 1) / threads;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+}  // namespace ovqa
+
+using namespace ovqa;
+
+extern "C" int ovqa_layernorm_fwd(const float* x, const float* residual, const float* gamma, const float* beta,
+                                  const float* post_add, int64_t post_add_rows, float* y_f32, void* y_bf16, float* sum_out,
+                                  float* mean, float* rstd, int64_t rows, int64_t D, float eps, void* stream) {
+    if (!x || !gamma || !beta || rows < 0 || D <= 0) return OVQA_ERR_BAD_ARG;
+    if (D % 4 != 0 || D > kMaxVec * 128) return OVQA_ERR_BAD_SHAPE;
+    if (rows == 0) return OVQA_OK;
+    if (post_add && post_add_rows <= 0) return OVQA_ERR_BAD_ARG;
+    layernorm_fwd_kernel<<<(unsigned)((rows + kRowsPerCta - 1) / kRowsPerCta), kRowsPerCta * 32, 0, (cudaStream_t)stream>>>(
+        x, residual, gamma, beta, post_add, post_add ? post_add_rows : 1, y_f32, (__nv_bfloat16*)y_bf16, sum_out, mean, rstd, rows, (int)D, eps);
+    OVQA_LAUNCH_OK();
+    return OVQA_OK;
+}
+
+extern "C" int ovqa_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                                  const float* dx_add, float* dx, void* dx_bf16, float* dgamma, float* dbeta, int64_t rows,
+                                  int64_t D, float dropout_p, uint64_t seed, uint64_t offset, void* stream) {
+    if (!dy || !x || !mean || !rstd || !gamma || rows < 0 || D <= 0) return OVQA_ERR_BAD_ARG;
+    if (D % 4 != 0 || D > kMaxVec * 128) return OVQA_ERR_BAD_SHAPE;
+    if (dropout_p < 0.f || dropout_p >= 1.f) return OVQA_ERR_BAD_ARG;
+    if (rows == 0) return OVQA_OK;
+    int64_t g = (rows + kRowsPerCta - 1) / kRowsPerCta;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (g > cap) g = cap;
+    layernorm_bwd_kernel<<<(unsigned)g, kRowsPerCta * 32, 0, (cudaStream_t)stream>>>(
+        dy, x, mean, rstd, gamma, dx_add, dx, (__nv_bfloat16*)dx_bf16, dgamma, dbeta, rows, (int)D, dropout_p,
+        dropout_p > 0.f ? 1.0f / (1.0f - dropout_p) : 1.0f, seed, offset);
+    OVQA_LAUNCH_OK();
+    return OVQA_OK;
+}
+
+extern "C" int ovqa_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream) {
+    if (!x || !y || n < 0) return OVQA_ERR_BAD_ARG;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return OVQA_ERR_ALIGNMENT;
+    if (n == 0) return OVQA_OK;
+    cast_f32_bf16_kernel<<<grid_for((n + 7) / 8, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, n);
+    OVQA_LAUNCH_OK();
+    return OVQA_OK;
+}
+extern "C" int ovqa_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream) {
+    if (!x || !y || n < 0) return OVQA_ERR_BAD_ARG;
+    if (n == 0) return OVQA_OK;
+    cast_bf16_f32_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, y, n);
+    OVQA_LAUNCH_OK();
+    return OVQA_OK;
+}
+extern "C" int ovqa_add_f32(const float* a, const float* b, float* y, int64_t n, void* stream) {
+    if (!a || !b || !y || n < 0) return OVQA_ERR_BAD_ARG;
+    if ((reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return OVQA_ERR_ALIGNMENT;
+    if (n == 0) return OVQA_OK;
+    add_f32_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(a, b, y, n);
+    OVQA_LAUNCH_OK();
+    return OVQA_OK;
+}
+extern "C" int ovqa_colsum(const void* x, float* out, int64_t m, int64_t n, int64_t ldx, int dtype, int accumulate, void* stream) {
+    if (!x || !out || m < 0 || n <= 0) return OVQA_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!accumulate) OVQA_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * n, st));
+    if (m == 0) return OVQA_OK;
+    const int64_t col_blocks = (n + 31) / 32;
+    int64_t row_blocks = (int64_t)sm_count() * 4 / col_blocks;
+    if (row_blocks < 1) row_blocks = 1;
+    if (row_blocks > (m + 63) / 64) row_blocks = (m + 63) / 64;
+    const int64_t rpb = (m + row_blocks - 1) / row_blocks;
+    dim3 grid((unsigned)col_blocks, (unsigned)row_blocks), block(32, 8);
+    if (dtype == OVQA_F32) colsum_kernel<float><<<grid, block, 0, st>>>((const float*)x, out, m, n, ldx, rpb);
+    else if (dtype == OVQA_BF16) colsum_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, out, m, n, ldx, rpb);
+    else return OVQA_ERR_BAD_ARG;
+    OVQA_LAUNCH_OK();
+    return OVQA_OK;
+}
+extern "C" int ovqa_dropout_apply(const float* x, void* y, int64_t n, float p, uint64_t seed, uint64_t offset, int out_dtype, void* stream) {
+    if (!x || !y || n < 0 || p < 0.f || p >= 1.f) return OVQA_ERR_BAD_ARG;
+    if (n == 0) return OVQA_OK;
+    const float inv = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
+    if (out_dtype == OVQA_F32) dropout_apply_kernel<float><<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, (float*)y, n, p, inv, seed, offset);
+    else if (out_dtype == OVQA_BF16) dropout_apply_kernel<__nv_bfloat16><<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, n, p, inv, seed, offset);
+    else return OVQA_ERR_BAD_ARG;
+    OVQA_LAUNCH_OK();
+    return OVQA_OK;
+}
+extern "C" int ovqa_dropout_mask(float* out, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream) {
+    if (!out || n < 0) return OVQA_ERR_BAD_ARG;
+    if (n == 0) return OVQA_OK;
+    dropout_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, n, p, seed, offset);
+    OVQA_LAUNCH_OK();
+    return OVQA_OK;
+}

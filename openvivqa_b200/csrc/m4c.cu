@@ -1,0 +1,175 @@
+// M4C dynamic pointer network, previous-prediction embedding and the greedy decode step (HBM/latency-bound
+// integer+float glue of mmf_m4c.py:236-256, :379-396, :416-459), fused so that no (B, V+Locr, D) table,
+// torch.cat or per-step host sync is needed.
+#include "common.cuh"
+
+namespace ovqa {
+namespace {
+
+constexpr int kMaxVec = 8;
+
+// one warp per (b, t, j): scores[b, t, col_offset + j] = q[b,t,:].k[b,j,:] * scale + mask[b,j]
+template <typename T>
+__global__ void ptr_scores_kernel(const T* __restrict__ q, const T* __restrict__ k, const void* __restrict__ mask, float* __restrict__ scores,
+                                  int64_t B, int64_t Tn, int64_t L, int64_t d, int64_t ldq, int64_t ldk, int64_t ld_scores,
+                                  int64_t col_offset, float scale, int mask_is_bool) {
+    const int64_t w = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
+    if (w >= B * Tn * L) return;
+    const int64_t j = w % L, t = (w / L) % Tn, b = w / (L * Tn);
+    const T* qr = q + (b * Tn + t) * ldq;
+    const T* kr = k + (b * L + j) * ldk;
+    float s = 0.f;
+    for (int64_t c = lane; c < d; c += 32) s = fmaf(to_f32<T>(qr[c]), to_f32<T>(kr[c]), s);
+    s = warp_sum(s);
+    if (lane == 0) {
+        s *= scale;
+        if (mask) {
+            if (mask_is_bool) { if (reinterpret_cast<const uint8_t*>(mask)[b * L + j]) s = -INFINITY; }
+            else s += reinterpret_cast<const float*>(mask)[b * L + j];
+        }
+        scores[(b * Tn + t) * ld_scores + col_offset + j] = s;
+    }
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// LayerNorm of a register-resident row (float4 per lane), fp32 two-pass
+__device__ __forceinline__ void ln_row(float4 (&v)[kMaxVec], int nvec, int lane, int D, float eps, const float* g, const float* b) {
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < kMaxVec; ++t) if (lane + 32 * t < nvec) s += (v[t].x + v[t].y) + (v[t].z + v[t].w);
+    const float mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int t = 0; t < kMaxVec; ++t) if (lane + 32 * t < nvec) {
+        const float a = v[t].x - mean, bb = v[t].y - mean, c = v[t].z - mean, dd = v[t].w - mean;
+        q += (a * a + bb * bb) + (c * c + dd * dd);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+#pragma unroll
+    for (int t = 0; t < kMaxVec; ++t) {
+        const int c = lane + 32 * t;
+        if (c < nvec) {
+            const float4 gg = ld4(g + 4 * c), bb = ld4(b + 4 * c);
+            v[t] = make_float4((v[t].x - mean) * rstd * gg.x + bb.x, (v[t].y - mean) * rstd * gg.y + bb.y,
+                               (v[t].z - mean) * rstd * gg.z + bb.z, (v[t].w - mean) * rstd * gg.w + bb.w);
+        }
+    }
+}
+
+// one warp per (b, t)
+__global__ void prev_pred_embed_kernel(const float* __restrict__ ans_emb, const float* __restrict__ ocr_emb, const int64_t* __restrict__ prev_inds,
+                                       const float* __restrict__ pos_emb, const float* __restrict__ type_emb,
+                                       const float* ans_g, const float* ans_b, const float* ocr_g, const float* ocr_b,
+                                       const float* emb_g, const float* emb_b, float* __restrict__ out,
+                                       int64_t B, int64_t Tn, int64_t V, int64_t Locr, int D, int64_t ld_out, int64_t out_bs, float eps) {
+    const int64_t w = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
+    if (w >= B * Tn) return;
+    const int64_t t = w % Tn, b = w / Tn;
+    const int nvec = D / 4;
+    int64_t idx = prev_inds[b * Tn + t];
+    idx = idx < 0 ? 0 : (idx >= V + Locr ? V + Locr - 1 : idx);
+    const bool is_ocr = idx >= V;
+    const float* src = is_ocr ? ocr_emb + (b * Locr + (idx - V)) * D : ans_emb + idx * D;
+    float4 a[kMaxVec], e[kMaxVec];
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nvec) {
+            a[i] = ld4(src + 4 * c);
+            const float4 p = ld4(pos_emb + t * D + 4 * c), ty = ld4(type_emb + (is_ocr ? 1 : 0) * D + 4 * c);
+            e[i] = make_float4(p.x + ty.x, p.y + ty.y, p.z + ty.z, p.w + ty.w);
+        }
+    }
+    ln_row(a, nvec, lane, D, eps, is_ocr ? ocr_g : ans_g, is_ocr ? ocr_b : ans_b);
+    ln_row(e, nvec, lane, D, eps, emb_g, emb_b);
+    float* o = out + b * out_bs + t * ld_out;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nvec) *reinterpret_cast<float4*>(o + 4 * c) = make_float4(a[i].x + e[i].x, a[i].y + e[i].y, a[i].z + e[i].z, a[i].w + e[i].w);
+    }
+}
+
+// one warp per (b, t): first index of the row maximum (torch.argmax tie rule)
+__global__ void argmax_rows_kernel(const float* __restrict__ scores, int64_t* __restrict__ out, int64_t rows, int64_t W) {
+    const int64_t w = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
+    if (w >= rows) return;
+    const float* r = scores + w * W;
+    float best = -INFINITY;
+    int64_t bi = W;  // sentinel larger than any index
+    for (int64_t c = lane; c < W; c += 32) {
+        const float v = r[c];
+        if (bi == W || v > best) { best = v; bi = c; }  // c ascends per lane: strict > keeps the first maximum
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oi < W && (bi == W || ov > best || (ov == best && oi < bi))) { best = ov; bi = oi; }
+    }
+    if (lane == 0) out[w] = bi == W ? 0 : bi;
+}
+
+__global__ void greedy_update_kernel(const int64_t* __restrict__ argmax, int64_t* __restrict__ prev_inds, int64_t* __restrict__ last_ids,
+                                     int32_t* __restrict__ all_eos, int64_t B, int64_t Tn, int64_t step, int64_t eos) {
+    int ok = 1;
+    for (int64_t b = threadIdx.x; b < B; b += blockDim.x) {
+        for (int64_t t = 1; t < Tn; ++t) prev_inds[b * Tn + t] = argmax[b * Tn + t - 1];
+        int64_t l = last_ids[b];
+        if (l != eos) l = argmax[b * Tn + step];
+        last_ids[b] = l;
+        ok &= (l == eos);
+    }
+    ok = __syncthreads_and(ok);
+    if (threadIdx.x == 0 && all_eos) *all_eos = ok;
+}
+
+}  // namespace
+}  // namespace ovqa
+
+using namespace ovqa;
+
+extern "C" int ovqa_ptr_scores(const void* q, const void* k, const void* mask, float* scores, int64_t B, int64_t T, int64_t L,
+                               int64_t d, int64_t ldq, int64_t ldk, int64_t ld_scores, int64_t col_offset, float scale, int dtype,
+                               int mask_is_bool, void* stream) {
+    if (!q || !k || !scores || B < 0 || T < 0 || L < 0 || d <= 0) return OVQA_ERR_BAD_ARG;
+    const int64_t warps = B * T * L;
+    if (warps == 0) return OVQA_OK;
+    const unsigned grid = (unsigned)((warps + 7) / 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == OVQA_F32) ptr_scores_kernel<float><<<grid, 256, 0, st>>>((const float*)q, (const float*)k, mask, scores, B, T, L, d, ldq, ldk, ld_scores, col_offset, scale, mask_is_bool);
+    else if (dtype == OVQA_BF16) ptr_scores_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, mask, scores, B, T, L, d, ldq, ldk, ld_scores, col_offset, scale, mask_is_bool);
+    else return OVQA_ERR_BAD_ARG;
+    OVQA_LAUNCH_OK();
+    return OVQA_OK;
+}
+
+extern "C" int ovqa_prev_pred_embed(const float* ans_emb, const float* ocr_emb, const int64_t* prev_inds, const float* pos_emb,
+                                    const float* type_emb, const float* ans_g, const float* ans_b, const float* ocr_g,
+                                    const float* ocr_b, const float* emb_g, const float* emb_b, float* out, int64_t B, int64_t T,
+                                    int64_t V, int64_t Locr, int64_t D, int64_t ld_out, int64_t out_batch_stride, float eps,
+                                    void* stream) {
+    if (!ans_emb || !ocr_emb || !prev_inds || !pos_emb || !type_emb || !ans_g || !ans_b || !ocr_g || !ocr_b || !emb_g || !emb_b || !out) return OVQA_ERR_BAD_ARG;
+    if (B < 0 || T < 0 || V <= 0 || Locr < 0 || D <= 0) return OVQA_ERR_BAD_ARG;
+    if (D % 4 != 0 || D > kMaxVec * 128 || ld_out % 4 != 0 || out_batch_stride % 4 != 0) return OVQA_ERR_BAD_SHAPE;
+    if (B * T == 0) return OVQA_OK;
+    prev_pred_embed_kernel<<<(unsigned)((B * T + 3) / 4), 128, 0, (cudaStream_t)stream>>>(ans_emb, ocr_emb, prev_inds, pos_emb, type_emb, ans_g, ans_b, ocr_g, ocr_b, emb_g, emb_b, out, B, T, V, Locr, (int)D, ld_out, out_batch_stride, eps);
+    OVQA_LAUNCH_OK();
+    return OVQA_OK;
+}
+
+extern "C" int ovqa_greedy_step(const float* scores, int64_t* prev_inds, int64_t* last_ids, int64_t* argmax_out, int32_t* all_eos,
+                                int64_t B, int64_t T, int64_t W, int64_t step, int64_t eos_idx, void* stream) {
+    if (!scores || !prev_inds || !last_ids || !argmax_out || B < 0 || T <= 0 || W <= 0 || step < 0 || step >= T) return OVQA_ERR_BAD_ARG;
+    if (B == 0) return OVQA_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    argmax_rows_kernel<<<(unsigned)((B * T + 7) / 8), 256, 0, st>>>(scores, argmax_out, B * T, W);
+    OVQA_LAUNCH_OK();
+    greedy_update_kernel<<<1, 1024, 0, st>>>(argmax_out, prev_inds, last_ids, all_eos, B, T, step, eos_idx);
+    OVQA_LAUNCH_OK();
+    return OVQA_OK;
+}

@@ -1,0 +1,379 @@
+"""Autograd blocks of the hot path, built from the library calls in :mod:`openvivqa_b200.ops`.
+
+Two fused blocks mirror the reference modules one-to-one:
+
+* :func:`mha_block`  — ``MultiHeadAttention.forward`` (attentions.py:319-339): QKV projection(s) → attention core →
+  output projection with bias + dropout + residual fused in the GEMM epilogue → LayerNorm.
+* :func:`pwff_block` — ``PositionWiseFeedForward.forward`` (positionwise_feed_forward.py:23-27): fc1 + GELU(erf) +
+  dropout in one epilogue, fc2 + dropout + residual in another, → LayerNorm.
+
+Both have hand-written backward passes (dgrad/wgrad through the same GEMM kernel reading the saved tensors in
+place, LayerNorm/attention/GELU backward kernels, dropout masks regenerated from (seed, offset)).
+
+``mode`` is "fp32" (exact FFMA GEMMs, the 1e-4 parity path) or "bf16" (tcgen05 GEMMs with bf16 operands and fp32
+accumulation; residual stream, softmax, LayerNorm statistics and masks stay fp32).
+"""
+from __future__ import annotations
+
+import math
+import weakref
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import ops
+
+# ----------------------------------------------------------------------------- dropout counter-RNG stream
+class _DropoutStream:
+    """(seed, offset) provider for the stateless Philox masks; deterministic after torch.manual_seed()."""
+
+    def __init__(self):
+        self.offset = 0
+        self._seed_of = None
+        self.seed = 0
+
+    def next(self, numel: int):
+        s = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF
+        if s != self._seed_of:
+            self._seed_of, self.seed, self.offset = s, s ^ 0x5DEECE66D, 0
+        off = self.offset
+        self.offset += (numel + 3) // 4 + 1
+        return self.seed, off
+
+
+dropout_stream = _DropoutStream()
+
+
+# ----------------------------------------------------------------------------- operand staging caches
+class _WeightCache:
+    """bf16 (and concatenated) copies of parameters, refreshed when the parameter's version counter moves
+    (i.e. after each optimiser step).  Keeps fc_q/fc_k/fc_v as separately named parameters (state_dict
+    compatibility) while the kernels see one fused [3*h*d, D] operand."""
+
+    def __init__(self):
+        self._store = {}
+
+    def get(self, params: Sequence[torch.Tensor], dtype: torch.dtype) -> torch.Tensor:
+        key = tuple(id(p) for p in params) + (dtype,)
+        ver = tuple((p._version, p.data_ptr()) for p in params)
+        hit = self._store.get(key)
+        if hit is not None and hit[0] == ver and all(r() is p for r, p in zip(hit[2], params)):
+            return hit[1]
+        with torch.no_grad():
+            src = params[0].detach() if len(params) == 1 else torch.cat([p.detach() for p in params], dim=0)
+            src = src.contiguous()
+            val = ops.to_bf16(src) if dtype == torch.bfloat16 else src.float()
+        self._store[key] = (ver, val, [weakref.ref(p) for p in params])
+        if len(self._store) > 4096:
+            self._store = {k: v for k, v in self._store.items() if all(r() is not None for r in v[2])}
+        return val
+
+
+weights = _WeightCache()
+
+
+def _operand(x: torch.Tensor, mode: str) -> torch.Tensor:
+    """2-D GEMM operand of x (…,D) in the compute dtype; reuses the bf16 shadow a previous block attached."""
+    D = x.shape[-1]
+    if mode == "fp32":
+        return x.reshape(-1, D).float().contiguous() if x.dtype != torch.float32 or not x.is_contiguous() else x.reshape(-1, D)
+    sh = getattr(x, "_ovqa_bf16", None)
+    if sh is not None and sh[0] == x._version and sh[1].shape == x.shape:
+        return sh[1].reshape(-1, D)
+    if x.dtype == torch.bfloat16:
+        return x.reshape(-1, D).contiguous()
+    return ops.to_bf16(x.reshape(-1, D).float())
+
+
+def _attach_shadow(y: torch.Tensor, y16: Optional[torch.Tensor]):
+    if y16 is not None:
+        y._ovqa_bf16 = (y._version, y16)
+
+
+def _cdt(mode: str) -> torch.dtype:
+    return torch.float32 if mode == "fp32" else torch.bfloat16
+
+
+def _split_k(m_rows: int, n_out: int, n_in: int) -> int:
+    """wgrad: C is [n_out, n_in] (few tiles), reduction over m_rows is long -> split it to fill the SMs."""
+    tiles = ((n_out + 127) // 128) * ((n_in + 127) // 128)
+    want = max(1, (2 * 148) // max(tiles, 1))
+    return int(max(1, min(want, m_rows // 512 if m_rows >= 512 else 1)))
+
+
+def _wgrad(dy2: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
+    """dW[n_out, n_in] = dy2^T x2 (fp32), both operands read where they lie ("T","T")."""
+    sk = _split_k(dy2.shape[0], dy2.shape[1], x2.shape[1])
+    return ops.gemm(dy2, x2, a_op="T", b_op="T", out_dtype=torch.float32, split_k=sk)
+
+
+def _masked_operand(ds: torch.Tensor, ds16: Optional[torch.Tensor], mode: str, p: float, seed: int, off: int) -> torch.Tensor:
+    if mode == "bf16":
+        return ds16.reshape(-1, ds.shape[-1])
+    d2 = ds.reshape(-1, ds.shape[-1])
+    return d2 if p == 0.0 else ops.dropout_apply(d2, p, seed, off)
+
+
+# ----------------------------------------------------------------------------- generic Linear (AoA gate, pointer net, ...)
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, mode, out_dtype):
+        x2 = _operand(x, mode)
+        w_c = weights.get([w], _cdt(mode))
+        y = ops.gemm(x2, w_c, bias=weights.get([b], torch.float32) if b is not None else None, out_dtype=out_dtype)
+        ctx.save_for_backward(x2, w_c)
+        ctx.mode, ctx.has_b, ctx.xshape = mode, b is not None, x.shape
+        return y.view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w_c = ctx.saved_tensors
+        mode = ctx.mode
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        dyc = dy2.float().contiguous() if mode == "fp32" else ops.to_bf16(dy2.float() if dy2.dtype != torch.bfloat16 else dy2)
+        dx = ops.gemm(dyc, w_c, b_op="T", out_dtype=torch.float32).view(ctx.xshape) if ctx.needs_input_grad[0] else None
+        dw = _wgrad(dyc, x2) if ctx.needs_input_grad[1] else None
+        db = ops.colsum(dyc) if ctx.has_b and ctx.needs_input_grad[2] else None
+        return dx, dw, db, None, None
+
+
+def linear(x, w, b=None, mode="fp32", out_dtype=torch.float32):
+    """``F.linear`` through ovqa_gemm; compute dtype per ``mode``; output fp32 unless ``out_dtype`` says otherwise."""
+    return _LinearFn.apply(x, w, b, mode, out_dtype)
+
+
+# ----------------------------------------------------------------------------- fused MHA block
+class _MHAFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, queries, keys, values, mask, boxes, wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta, geo_w, geo_b, cfg):
+        mode, h, dk, dv = cfg["mode"], cfg["h"], cfg["d_k"], cfg["d_v"]
+        p = cfg["dropout"] if cfg["training"] else 0.0
+        cdt = _cdt(mode)
+        B, Lq, D = queries.shape
+        Lk = keys.shape[1]
+        self_att = (keys is queries) and (values is queries)
+        kv_same = values is keys
+        xq = _operand(queries, mode)
+        xk = xq if keys is queries else _operand(keys, mode)
+        xv = xk if kv_same else _operand(values, mode)
+        hk, hv = h * dk, h * dv
+        fb = lambda *bs: weights.get(list(bs), torch.float32)
+        if self_att:
+            qkv = ops.gemm(xq, weights.get([wq, wk, wv], cdt), bias=fb(bq, bk, bv), out_dtype=cdt).view(B, Lq, 2 * hk + hv)
+            q, k, v = qkv[..., :hk], qkv[..., hk:2 * hk], qkv[..., 2 * hk:]
+            proj = (qkv,)
+        elif kv_same:
+            qb = ops.gemm(xq, weights.get([wq], cdt), bias=fb(bq), out_dtype=cdt).view(B, Lq, hk)
+            kvb = ops.gemm(xk, weights.get([wk, wv], cdt), bias=fb(bk, bv), out_dtype=cdt).view(B, Lk, hk + hv)
+            q, k, v = qb, kvb[..., :hk], kvb[..., hk:]
+            proj = (qb, kvb)
+        else:
+            q = ops.gemm(xq, weights.get([wq], cdt), bias=fb(bq), out_dtype=cdt).view(B, Lq, hk)
+            k = ops.gemm(xk, weights.get([wk], cdt), bias=fb(bk), out_dtype=cdt).view(B, Lk, hk)
+            v = ops.gemm(xv, weights.get([wv], cdt), bias=fb(bv), out_dtype=cdt).view(B, Lk, hv)
+            proj = (q, k, v)
+        geo = ops.GeoParams(boxes, geo_w.detach(), geo_b.detach(), cfg["geo_trig"]) if boxes is not None else None
+        need_grad = any(ctx.needs_input_grad)
+        att_ctx, lse, _ = ops.sdpa_fwd(q, k, v, h=h, d_k=dk, d_v=dv, mask=mask, geo=geo, scale=cfg["scale"], need_lse=need_grad)
+        seed, off = dropout_stream.next(B * Lq * D) if p > 0.0 else (0, 0)
+        q_res = queries.reshape(-1, D)
+        q_res = q_res if (q_res.dtype == torch.float32 and q_res.is_contiguous()) else q_res.float().contiguous()
+        s = ops.gemm(att_ctx.view(B * Lq, hv), weights.get([wo], cdt), bias=fb(bo), out_dtype=torch.float32,
+                     dropout_p=p, seed=seed, offset=off, residual=q_res)
+        y, y16, _, mean, rstd = ops.layernorm_fwd(s, gamma.detach(), beta.detach(), eps=cfg["eps"], want_bf16=(mode == "bf16"),
+                                                  save_stats=need_grad)
+        y = y.view(B, Lq, D)
+        if need_grad:
+            ctx.save_for_backward(xq, xk, xv, mask, *proj, att_ctx, lse, s, mean, rstd, gamma, wq, wk, wv, wo,
+                                  boxes, geo_w, geo_b)
+            ctx.n_proj = len(proj)
+            ctx.cfg, ctx.p, ctx.seed, ctx.off = cfg, p, seed, off
+            ctx.flags = (self_att, kv_same)
+            ctx.shapes = (B, Lq, Lk, D)
+        y16 = y16.view(B, Lq, D) if y16 is not None else y.new_empty(0)
+        ctx.mark_non_differentiable(y16)
+        return y, y16
+
+    @staticmethod
+    def backward(ctx, dy, _dy16):
+        cfg = ctx.cfg
+        mode, h, dk, dv = cfg["mode"], cfg["h"], cfg["d_k"], cfg["d_v"]
+        cdt = _cdt(mode)
+        sv = ctx.saved_tensors
+        xq, xk, xv, mask = sv[:4]
+        proj = sv[4:4 + ctx.n_proj]
+        att_ctx, lse, s, mean, rstd, gamma, wq, wk, wv, wo, boxes, geo_w, geo_b = sv[4 + ctx.n_proj:]
+        self_att, kv_same = ctx.flags
+        B, Lq, Lk, D = ctx.shapes
+        hk, hv = h * dk, h * dv
+        p, seed, off = ctx.p, ctx.seed, ctx.off
+        # LayerNorm backward; the bf16 copy already carries the output-projection dropout mask
+        ds, ds16, dgamma, dbeta = ops.layernorm_bwd(dy.reshape(B * Lq, D), s, mean, rstd, gamma, want_bf16=(mode == "bf16"),
+                                                    dropout_p=p, seed=seed, offset=off)
+        d_o = _masked_operand(ds, ds16, mode, p, seed, off)                       # grad of the fc_o output
+        ctx2 = att_ctx.view(B * Lq, hv)
+        dwo = _wgrad(d_o, ctx2)
+        dbo = ops.colsum(d_o)
+        dctx = ops.gemm(d_o, weights.get([wo], cdt), b_op="T", out_dtype=cdt).view(B, Lq, hv)
+        geo = ops.GeoParams(boxes, geo_w.detach(), geo_b.detach(), cfg["geo_trig"]) if boxes is not None else None
+        gdw = torch.zeros_like(geo_w, dtype=torch.float32) if geo is not None else None
+        gdb = torch.zeros_like(geo_b, dtype=torch.float32) if geo is not None else None
+        if self_att:
+            (qkv,) = proj
+            dqkv = torch.empty_like(qkv)
+            q, k, v = qkv[..., :hk], qkv[..., hk:2 * hk], qkv[..., 2 * hk:]
+            dq, dk_, dv_ = dqkv[..., :hk], dqkv[..., hk:2 * hk], dqkv[..., 2 * hk:]
+        elif kv_same:
+            qb, kvb = proj
+            dqb, dkvb = torch.empty_like(qb), torch.empty_like(kvb)
+            q, k, v = qb, kvb[..., :hk], kvb[..., hk:]
+            dq, dk_, dv_ = dqb, dkvb[..., :hk], dkvb[..., hk:]
+        else:
+            q, k, v = proj
+            dq, dk_, dv_ = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        ops.sdpa_bwd(q, k, v, att_ctx, dctx, lse, dq, dk_, dv_, h=h, d_k=dk, d_v=dv, mask=mask, geo=geo, geo_dw=gdw,
+                     geo_db=gdb, scale=cfg["scale"])
+        dkeys = dvalues = None
+        if self_att:
+            d2 = dqkv.view(B * Lq, -1)
+            dW = _wgrad(d2, xq)
+            db = ops.colsum(d2)
+            dwq, dwk, dwv = dW[:hk], dW[hk:2 * hk], dW[2 * hk:]
+            dbq, dbk, dbv = db[:hk], db[hk:2 * hk], db[2 * hk:]
+            dqueries = ops.gemm(d2, weights.get([wq, wk, wv], cdt), b_op="T", out_dtype=torch.float32, residual=ds.view(B * Lq, D)).view(B, Lq, D)
+        else:
+            dq2 = dq.reshape(B * Lq, hk)
+            dwq, dbq = _wgrad(dq2, xq), ops.colsum(dq2)
+            dqueries = ops.gemm(dq2, weights.get([wq], cdt), b_op="T", out_dtype=torch.float32, residual=ds.view(B * Lq, D)).view(B, Lq, D)
+            if kv_same:
+                d2 = dkvb.view(B * Lk, -1)
+                dW, db = _wgrad(d2, xk), ops.colsum(d2)
+                dwk, dwv, dbk, dbv = dW[:hk], dW[hk:], db[:hk], db[hk:]
+                dkeys = ops.gemm(d2, weights.get([wk, wv], cdt), b_op="T", out_dtype=torch.float32).view(B, Lk, D)
+            else:
+                dk2, dv2 = dk_.reshape(B * Lk, hk), dv_.reshape(B * Lk, hv)
+                dwk, dbk = _wgrad(dk2, xk), ops.colsum(dk2)
+                dwv, dbv = _wgrad(dv2, xv), ops.colsum(dv2)
+                dkeys = ops.gemm(dk2, weights.get([wk], cdt), b_op="T", out_dtype=torch.float32).view(B, Lk, D)
+                dvalues = ops.gemm(dv2, weights.get([wv], cdt), b_op="T", out_dtype=torch.float32).view(B, Lk, D)
+        return (dqueries, dkeys, dvalues, None, None, dwq, dbq, dwk, dbk, dwv, dbv, dwo, dbo, dgamma, dbeta, gdw, gdb, None)
+
+
+def mha_block(queries, keys, values, mask, *, wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta, h, d_k, d_v, mode="fp32",
+              dropout=0.0, training=False, eps=1e-5, boxes=None, geo_w=None, geo_b=None, geo_trig=True, scale=None):
+    cfg = dict(mode=mode, h=h, d_k=d_k, d_v=d_v, dropout=float(dropout), training=bool(training), eps=float(eps),
+               geo_trig=bool(geo_trig), scale=(1.0 / math.sqrt(d_k)) if scale is None else float(scale))
+    y, y16 = _MHAFn.apply(queries, keys, values, mask, boxes, wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta, geo_w, geo_b, cfg)
+    _attach_shadow(y, y16 if mode == "bf16" else None)
+    return y
+
+
+# ----------------------------------------------------------------------------- fused PWFF block
+class _PWFFFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, gamma, beta, cfg):
+        mode = cfg["mode"]
+        p = cfg["dropout"] if cfg["training"] else 0.0
+        cdt = _cdt(mode)
+        D = x.shape[-1]
+        x2 = _operand(x, mode)
+        M, dff = x2.shape[0], w1.shape[0]
+        need_grad = any(ctx.needs_input_grad)
+        pre = torch.empty((M, dff), device=x.device, dtype=cdt) if need_grad else None
+        s1, o1 = dropout_stream.next(M * dff) if p > 0.0 else (0, 0)
+        hact = ops.gemm(x2, weights.get([w1], cdt), bias=weights.get([b1], torch.float32), out_dtype=cdt, gelu=True,
+                        aux_out=pre, dropout_p=p, seed=s1, offset=o1)
+        s2, o2 = dropout_stream.next(M * D) if p > 0.0 else (0, 0)
+        x_res = x.reshape(-1, D)
+        x_res = x_res if (x_res.dtype == torch.float32 and x_res.is_contiguous()) else x_res.float().contiguous()
+        s = ops.gemm(hact, weights.get([w2], cdt), bias=weights.get([b2], torch.float32), out_dtype=torch.float32,
+                     dropout_p=p, seed=s2, offset=o2, residual=x_res)
+        y, y16, _, mean, rstd = ops.layernorm_fwd(s, gamma.detach(), beta.detach(), eps=cfg["eps"], want_bf16=(mode == "bf16"),
+                                                  save_stats=need_grad)
+        if need_grad:
+            ctx.save_for_backward(x2, pre, hact, s, mean, rstd, gamma, w1, w2)
+            ctx.cfg, ctx.p, ctx.rng = cfg, p, (s1, o1, s2, o2)
+            ctx.xshape = x.shape
+        y16 = y16.view(x.shape) if y16 is not None else y.new_empty(0)
+        ctx.mark_non_differentiable(y16)
+        return y.view(x.shape), y16
+
+    @staticmethod
+    def backward(ctx, dy, _dy16):
+        x2, pre, hact, s, mean, rstd, gamma, w1, w2 = ctx.saved_tensors
+        mode, p = ctx.cfg["mode"], ctx.p
+        s1, o1, s2, o2 = ctx.rng
+        cdt = _cdt(mode)
+        D = x2.shape[1]
+        ds, ds16, dgamma, dbeta = ops.layernorm_bwd(dy.reshape(-1, D), s, mean, rstd, gamma, want_bf16=(mode == "bf16"),
+                                                    dropout_p=p, seed=s2, offset=o2)
+        d2 = _masked_operand(ds, ds16, mode, p, s2, o2)                             # grad of the fc2 output
+        dw2, db2 = _wgrad(d2, hact), ops.colsum(d2)
+        # grad of the fc1 pre-activation: (d2 W2) * dropout1 mask * gelu'(pre), all in the dgrad epilogue
+        dpre = ops.gemm(d2, weights.get([w2], cdt), b_op="T", out_dtype=cdt, dgelu_aux=pre, dropout_p=p, seed=s1, offset=o1)
+        dw1, db1 = _wgrad(dpre, x2), ops.colsum(dpre)
+        dx = ops.gemm(dpre, weights.get([w1], cdt), b_op="T", out_dtype=torch.float32, residual=ds.reshape(-1, D)).view(ctx.xshape)
+        return dx, dw1, db1, dw2, db2, dgamma, dbeta, None
+
+
+def pwff_block(x, *, w1, b1, w2, b2, gamma, beta, mode="fp32", dropout=0.0, training=False, eps=1e-5):
+    cfg = dict(mode=mode, dropout=float(dropout), training=bool(training), eps=float(eps))
+    y, y16 = _PWFFFn.apply(x, w1, b1, w2, b2, gamma, beta, cfg)
+    _attach_shadow(y, y16 if mode == "bf16" else None)
+    return y
+
+
+# ----------------------------------------------------------------------------- stand-alone pieces (direct core calls)
+class _SdpaFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, mask, cfg):
+        h, dk, dv = cfg["h"], cfg["d_k"], cfg["d_v"]
+        need_grad = any(ctx.needs_input_grad)
+        out, lse, att = ops.sdpa_fwd(q, k, v, h=h, d_k=dk, d_v=dv, mask=mask, geo=cfg.get("geo"), scale=cfg["scale"],
+                                     need_lse=need_grad, need_att=cfg["need_att"])
+        if need_grad:
+            ctx.save_for_backward(q, k, v, mask, out, lse)
+            ctx.cfg = cfg
+        if att is not None:
+            ctx.mark_non_differentiable(att)
+            return out, att
+        return out, torch.empty(0, device=q.device)
+
+    @staticmethod
+    def backward(ctx, dout, _datt):
+        q, k, v, mask, out, lse = ctx.saved_tensors
+        cfg = ctx.cfg
+        dq, dk_, dv_ = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        ops.sdpa_bwd(q, k, v, out, dout.contiguous(), lse, dq, dk_, dv_, h=cfg["h"], d_k=cfg["d_k"], d_v=cfg["d_v"],
+                     mask=mask, geo=cfg.get("geo"), scale=cfg["scale"])
+        return dq, dk_, dv_, None, None
+
+
+def sdpa(q, k, v, mask, *, h, d_k, d_v, scale=None, need_att=False, geo=None):
+    """Attention core on already projected (B,L,h*d) tensors (fp32 or bf16).  Returns (out, att|None).
+    Gradients flow to q,k,v (not through the returned probabilities, nor to the geometry weights: use
+    :func:`mha_block` for that)."""
+    cfg = dict(h=h, d_k=d_k, d_v=d_v, scale=(1.0 / math.sqrt(d_k)) if scale is None else float(scale), need_att=need_att, geo=geo)
+    out, att = _SdpaFn.apply(q.contiguous(), k.contiguous(), v.contiguous(), mask, cfg)
+    return out, (att if need_att else None)
+
+
+class _LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, post_add):
+        need_grad = any(ctx.needs_input_grad)
+        y, _, _, mean, rstd = ops.layernorm_fwd(x.float(), gamma.detach(), beta.detach(), eps=eps, post_add=post_add, save_stats=need_grad)
+        if need_grad:
+            ctx.save_for_backward(x, mean, rstd, gamma)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, rstd, gamma = ctx.saved_tensors
+        dx, _, dg, db = ops.layernorm_bwd(dy, x.float().contiguous(), mean, rstd, gamma)
+        return dx, dg, db, None, None
+
+
+def layer_norm(x, gamma, beta, eps=1e-5, post_add=None):
+    """``LN(x) [+ post_add]`` (e.g. the encoders' ``layer_norm(features) + pos_embedding``, encoders.py:113)."""
+    return _LayerNormFn.apply(x, gamma, beta, float(eps), post_add)

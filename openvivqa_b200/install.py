@@ -1,0 +1,72 @@
+"""Install the drop-ins into an importable OpenViVQA checkout.
+
+``builders.registry.Registry._do_register`` asserts on duplicate names (registry.py:43-47), so the registry's
+``_obj_map`` is overwritten directly; ``MultiHeadAttention`` / ``PositionWiseFeedForward`` are plain classes that
+``encoders.py:4-5``, ``decoders.py:5,7`` (and a few models) import by name, so those module attributes are rebound.
+Call after ``import builders`` (or after importing ``models.modules.*``) and before ``build_model``.
+"""
+from __future__ import annotations
+
+import importlib
+import sys
+
+from . import modules as M
+
+_saved = {}
+
+_REBIND = {
+    "MultiHeadAttention": ("models.modules.attentions", "models.modules.encoders", "models.modules.decoders",
+                           "models.modules.SCP"),
+    "PositionWiseFeedForward": ("models.modules.positionwise_feed_forward", "models.modules.encoders",
+                                "models.modules.decoders", "models.iterative_mcan"),
+    "OcrPtrNet": ("models.mmf_m4c",),
+}
+
+
+def _maybe(modname):
+    if modname in sys.modules:
+        return sys.modules[modname]
+    return None
+
+
+def install(compute_dtype: str | None = None, verbose: bool = False):
+    """Patch the already-imported reference modules.  Returns the dict of classes that were installed."""
+    if compute_dtype is not None:
+        M.set_compute_dtype(compute_dtype)
+    att_builder = _maybe("builders.attention_builder")
+    if att_builder is None:
+        att_builder = importlib.import_module("builders.attention_builder")
+    reg = att_builder.META_ATTENTION
+    for name in ("ScaledDotProductAttention", "AugmentedGeometryScaledDotProductAttention"):
+        _saved.setdefault(("registry", name), reg._obj_map.get(name))
+        reg._obj_map[name] = getattr(M, name)
+    # derive MHA from the reference's stateful base so containers.py's isinstance recursion still sees it
+    containers = _maybe("models.modules.containers")
+    base = containers.Module if containers is not None else M.StatefulModule
+    mha = M.make_multi_head_attention(base=base, builder=att_builder.build_attention)
+    classes = {"MultiHeadAttention": mha, "PositionWiseFeedForward": M.PositionWiseFeedForward, "OcrPtrNet": M.OcrPtrNet,
+               "ScaledDotProductAttention": M.ScaledDotProductAttention,
+               "AugmentedGeometryScaledDotProductAttention": M.AugmentedGeometryScaledDotProductAttention}
+    for name, mods in _REBIND.items():
+        for modname in mods:
+            mod = _maybe(modname)
+            if mod is not None and hasattr(mod, name):
+                _saved.setdefault((modname, name), getattr(mod, name))
+                setattr(mod, name, classes[name])
+                if verbose:
+                    print(f"openvivqa_b200: {modname}.{name} -> B200 drop-in")
+    return classes
+
+
+def uninstall():
+    """Undo :func:`install` (used by the tests that compare with/without the drop-ins in one process)."""
+    for (where, name), obj in list(_saved.items()):
+        if where == "registry":
+            reg = sys.modules["builders.attention_builder"].META_ATTENTION
+            if obj is None:
+                reg._obj_map.pop(name, None)
+            else:
+                reg._obj_map[name] = obj
+        else:
+            setattr(sys.modules[where], name, obj)
+    _saved.clear()

@@ -1,0 +1,355 @@
+"""Drop-in modules: same class names, ``__init__(config)`` keys, parameter names/shapes/initialisers and
+``forward`` signatures as the reference, computing through libovqa_b200.
+
+Reference classes mirrored (``/root/reference``):
+  * ``ScaledDotProductAttention``                      models/modules/attentions.py:10-60
+  * ``AugmentedGeometryScaledDotProductAttention``     models/modules/attentions.py:62-137
+  * ``MultiHeadAttention``                             models/modules/attentions.py:293-339
+  * ``PositionWiseFeedForward``                        models/modules/positionwise_feed_forward.py:5-27
+  * ``OcrPtrNet`` / ``DynamicPointerNetwork``          models/mmf_m4c.py:367-396 / models/m4c.py:19-33
+
+Compute dtype: ``"fp32"`` (parity path, default) or ``"bf16"`` (tcgen05 path); chosen by, in order, an optional
+config key ``COMPUTE_DTYPE``, :func:`set_compute_dtype`, env ``OVQA_COMPUTE_DTYPE``.  No new required config keys.
+"""
+from __future__ import annotations
+
+import copy
+import math
+import os
+from contextlib import contextmanager
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import functional as Fn
+from . import ops
+
+_default_mode = os.environ.get("OVQA_COMPUTE_DTYPE", "fp32")
+
+
+def set_compute_dtype(mode: str):
+    """Process-wide default compute dtype for modules built without a ``COMPUTE_DTYPE`` key: "fp32" or "bf16"."""
+    global _default_mode
+    if mode not in ("fp32", "bf16"):
+        raise ValueError("compute dtype must be 'fp32' or 'bf16'")
+    _default_mode = mode
+
+
+def get_compute_dtype() -> str:
+    return _default_mode
+
+
+def _mode_of(module) -> str:
+    return module.compute_dtype or _default_mode
+
+
+class StatefulModule(nn.Module):
+    """Minimal stand-in for the reference's ``containers.Module`` (models/modules/containers.py:4-70): buffers
+    registered as decode "states" that ``statefulness(batch_size)`` expands per batch and resets afterwards.
+    When installed into a reference checkout the drop-ins derive from the reference's own class instead, so its
+    ``isinstance(m, Module)`` recursion (containers.py:22-24) keeps working."""
+
+    def __init__(self):
+        super().__init__()
+        self._is_stateful = False
+        self._state_names = []
+        self._state_defaults = {}
+
+    def register_state(self, name, default):
+        self._state_names.append(name)
+        self._state_defaults[name] = None if default is None else default.clone().detach()
+        self.register_buffer(name, default)
+
+    def _children_stateful(self):
+        return [m for m in self.children() if isinstance(m, StatefulModule)]
+
+    def states(self):
+        for n in self._state_names:
+            yield self._buffers[n]
+        for m in self._children_stateful():
+            yield from m.states()
+
+    def apply_to_states(self, fn):
+        for n in self._state_names:
+            self._buffers[n] = fn(self._buffers[n])
+        for m in self._children_stateful():
+            m.apply_to_states(fn)
+
+    def enable_statefulness(self, batch_size):
+        for m in self._children_stateful():
+            m.enable_statefulness(batch_size)
+        for n in self._state_names:
+            d = self._state_defaults[n]
+            if d is None:
+                self._buffers[n] = None
+            else:
+                t = d.clone().detach().to(self._buffers[n].device).unsqueeze(0)
+                self._buffers[n] = t.expand([batch_size] + list(t.shape[1:])).contiguous()
+        self._is_stateful = True
+
+    def disable_statefulness(self):
+        for m in self._children_stateful():
+            m.disable_statefulness()
+        for n in self._state_names:
+            d = self._state_defaults[n]
+            self._buffers[n] = None if d is None else d.clone().detach().to(self._buffers[n].device)
+        self._is_stateful = False
+
+    @contextmanager
+    def statefulness(self, batch_size):
+        self.enable_statefulness(batch_size)
+        try:
+            yield
+        finally:
+            self.disable_statefulness()
+
+
+def _init_core_linears(m):
+    # attentions.py:36-44: Xavier-uniform q,k,v,o in that order, zero biases
+    for fc in (m.fc_q, m.fc_k, m.fc_v, m.fc_o):
+        nn.init.xavier_uniform_(fc.weight)
+    for fc in (m.fc_q, m.fc_k, m.fc_v, m.fc_o):
+        nn.init.constant_(fc.bias, 0)
+
+
+class ScaledDotProductAttention(nn.Module):
+    """attentions.py:10-60.  ``forward(queries, keys, values, attention_mask=None, **kwargs) -> (out, att)``;
+    ``att`` (B,h,Lq,Lk) is materialised here because direct callers consume it (mmf_lorra.py:118-146); the
+    ``MultiHeadAttention`` wrapper uses the fused block instead and never materialises it."""
+
+    def __init__(self, config):
+        super().__init__()
+        d_model, h, d_k, d_v = config.D_MODEL, config.HEAD, config.D_KEY, config.D_VALUE
+        self.fc_q = nn.Linear(d_model, h * d_k)
+        self.fc_k = nn.Linear(d_model, h * d_k)
+        self.fc_v = nn.Linear(d_model, h * d_v)
+        self.fc_o = nn.Linear(h * d_v, d_model)
+        self.d_model, self.d_k, self.d_v, self.h = d_model, d_k, d_v, h
+        self.compute_dtype = getattr(config, "COMPUTE_DTYPE", None)
+        self.init_weights()
+
+    def init_weights(self):
+        _init_core_linears(self)
+
+    def _geo(self, boxes):
+        return None
+
+    def forward(self, queries, keys, values, attention_mask=None, **kwargs):
+        mode = _mode_of(self)
+        odt = torch.float32 if mode == "fp32" else torch.bfloat16
+        q = Fn.linear(queries, self.fc_q.weight, self.fc_q.bias, mode, odt)
+        k = Fn.linear(keys, self.fc_k.weight, self.fc_k.bias, mode, odt)
+        v = Fn.linear(values, self.fc_v.weight, self.fc_v.bias, mode, odt)
+        ctx, att = Fn.sdpa(q, k, v, attention_mask, h=self.h, d_k=self.d_k, d_v=self.d_v, need_att=True,
+                           geo=self._geo(kwargs.get("boxes")))
+        out = Fn.linear(ctx, self.fc_o.weight, self.fc_o.bias, mode)
+        return out, att
+
+
+class AugmentedGeometryScaledDotProductAttention(ScaledDotProductAttention):
+    """attentions.py:62-137: the core with ``log(clamp(relu(fc_g_h(emb(boxes))), 1e-6))`` added to the scores.
+
+    Documented deviations (SURVEY.md finding 5): ``attention_mask`` is honoured (the reference crashes on it,
+    attentions.py:128-129) and ``boxes`` may also arrive as a keyword (so it works through ``MultiHeadAttention``)."""
+
+    def __init__(self, config):
+        nn.Module.__init__(self)
+        d_model, h, d_k, d_v = config.D_MODEL, config.HEAD, config.D_KEY, config.D_VALUE
+        self.trignometric_embedding = config.TRIGNOMETRIC_EMBEDDING
+        self.d_g = d_model // h if self.trignometric_embedding else 4
+        self.fc_q = nn.Linear(d_model, h * d_k)
+        self.fc_k = nn.Linear(d_model, h * d_k)
+        self.fc_v = nn.Linear(d_model, h * d_v)
+        self.fc_o = nn.Linear(h * d_v, d_model)
+        fc_g = nn.Linear(self.d_g, 1)
+        self.fc_gs = nn.ModuleList([copy.deepcopy(fc_g) for _ in range(h)])   # models/utils.py:40-42 clones()
+        self.d_model, self.d_k, self.d_v, self.h = d_model, d_k, d_v, h
+        self.compute_dtype = getattr(config, "COMPUTE_DTYPE", None)
+        self.init_weights()
+
+    def init_weights(self):
+        for fc in (self.fc_q, self.fc_k, self.fc_v, self.fc_o):
+            nn.init.xavier_uniform_(fc.weight)
+        for g in self.fc_gs:
+            nn.init.xavier_uniform_(g.weight)
+        for fc in (self.fc_q, self.fc_k, self.fc_v, self.fc_o):
+            nn.init.constant_(fc.bias, 0)
+        for g in self.fc_gs:
+            nn.init.constant_(g.bias, 0)
+
+    def geo_weights(self):
+        w = torch.cat([g.weight for g in self.fc_gs], dim=0)        # (h, d_g)
+        b = torch.cat([g.bias for g in self.fc_gs], dim=0)          # (h,)
+        return w, b
+
+    def _geo(self, boxes):
+        if boxes is None:
+            raise ValueError("AugmentedGeometryScaledDotProductAttention needs `boxes` (B,N,4)")
+        w, b = self.geo_weights()
+        return ops.GeoParams(boxes, w.detach(), b.detach(), self.trignometric_embedding)
+
+    def forward(self, queries, keys, values, boxes=None, attention_mask=None, **kwargs):
+        return super().forward(queries, keys, values, attention_mask, boxes=boxes)
+
+
+class AttentionRegistry:
+    """Name → class map with the reference's ``build_attention`` contract (builders/attention_builder.py:3-8,
+    builders/registry.py:42-48 incl. the duplicate-name assertion)."""
+
+    def __init__(self):
+        self._obj_map = {}
+
+    def register(self, obj=None):
+        def deco(c):
+            assert c.__name__ not in self._obj_map, f"An object named '{c.__name__}' was already registered!"
+            self._obj_map[c.__name__] = c
+            return c
+        return deco if obj is None else deco(obj)
+
+    def get(self, name):
+        if name not in self._obj_map:
+            raise KeyError(f"No object named '{name}' found in 'META_ATTENTION' registry!")
+        return self._obj_map[name]
+
+    def __contains__(self, name):
+        return name in self._obj_map
+
+
+META_ATTENTION = AttentionRegistry()
+META_ATTENTION.register(ScaledDotProductAttention)
+META_ATTENTION.register(AugmentedGeometryScaledDotProductAttention)
+
+
+def build_attention(config):
+    return META_ATTENTION.get(config.ARCHITECTURE)(config)
+
+
+def make_multi_head_attention(base=StatefulModule, builder=None):
+    """Class factory so that, inside a reference checkout, the drop-in derives from the reference's own
+    ``containers.Module`` and builds its core through the reference's registry."""
+    builder = builder or build_attention
+
+    class MultiHeadAttention(base):
+        """attentions.py:293-339: (stateful K/V concat) → core → dropout → LayerNorm(queries + out) → (AoA gate)."""
+
+        def __init__(self, config):
+            super().__init__()
+            d_model = config.D_MODEL
+            self.use_aoa = config.USE_AOA
+            if self.use_aoa:
+                self.informative_attention = nn.Linear(2 * d_model, d_model)
+                self.gated_attention = nn.Linear(2 * d_model, d_model)
+            self.attention = builder(config)
+            self.dropout = nn.Dropout(p=config.DROPOUT)
+            self.layer_norm = nn.LayerNorm(d_model)
+            self.can_be_stateful = config.CAN_BE_STATEFUL
+            if self.can_be_stateful:
+                self.register_state("running_keys", torch.zeros((0, d_model)))
+                self.register_state("running_values", torch.zeros((0, d_model)))
+            self.compute_dtype = getattr(config, "COMPUTE_DTYPE", None)
+
+        def forward(self, queries, keys, values, attention_mask, **kwargs):
+            core = self.attention
+            if not isinstance(core, ScaledDotProductAttention):
+                # a core we do not accelerate (memory / adaptive variants): reference composition, their own math
+                out, _ = core(queries, keys, values, attention_mask, **kwargs)
+                out = self.layer_norm(queries + self.dropout(out))
+            else:
+                if self.can_be_stateful and self._is_stateful:
+                    self.running_keys = torch.cat([self.running_keys, keys], 1)
+                    keys = self.running_keys
+                    self.running_values = torch.cat([self.running_values, values], 1)
+                    values = self.running_values
+                geo = isinstance(core, AugmentedGeometryScaledDotProductAttention)
+                boxes = kwargs.get("boxes") if geo else None
+                if geo and boxes is None:
+                    raise ValueError("geometry attention needs `boxes=` (B,N,4)")
+                gw, gb = core.geo_weights() if geo else (None, None)
+                mode = self.compute_dtype or core.compute_dtype or get_compute_dtype()
+                out = Fn.mha_block(queries, keys, values, attention_mask,
+                                   wq=core.fc_q.weight, bq=core.fc_q.bias, wk=core.fc_k.weight, bk=core.fc_k.bias,
+                                   wv=core.fc_v.weight, bv=core.fc_v.bias, wo=core.fc_o.weight, bo=core.fc_o.bias,
+                                   gamma=self.layer_norm.weight, beta=self.layer_norm.bias,
+                                   h=core.h, d_k=core.d_k, d_v=core.d_v, mode=mode, dropout=self.dropout.p,
+                                   training=self.training, eps=self.layer_norm.eps, boxes=boxes, geo_w=gw, geo_b=gb,
+                                   geo_trig=getattr(core, "trignometric_embedding", True))
+            if self.use_aoa:                                                     # attentions.py:333-337
+                mode = self.compute_dtype or get_compute_dtype()
+                aoa_in = torch.cat([queries, out], dim=-1)
+                i = Fn.linear(aoa_in, self.informative_attention.weight, self.informative_attention.bias, mode)
+                g = torch.sigmoid(Fn.linear(aoa_in, self.gated_attention.weight, self.gated_attention.bias, mode))
+                out = i * g
+            return out
+
+    return MultiHeadAttention
+
+
+MultiHeadAttention = make_multi_head_attention()
+
+
+class PositionWiseFeedForward(nn.Module):
+    """positionwise_feed_forward.py:5-27: ``LN(x + drop(fc2(drop(gelu(fc1 x)))))`` (erf GELU, eps 1e-5)."""
+
+    def __init__(self, config):
+        super().__init__()
+        d_model, d_ff, dropout = config.D_MODEL, config.D_FF, config.DROPOUT
+        self.fc1 = nn.Linear(d_model, d_ff)
+        self.fc2 = nn.Linear(d_ff, d_model)
+        self.dropout_1 = nn.Dropout(p=dropout)
+        self.dropout_2 = nn.Dropout(p=dropout)
+        self.layer_norm = nn.LayerNorm(d_model)
+        self.compute_dtype = getattr(config, "COMPUTE_DTYPE", None)
+
+    def forward(self, input):
+        return Fn.pwff_block(input, w1=self.fc1.weight, b1=self.fc1.bias, w2=self.fc2.weight, b2=self.fc2.bias,
+                             gamma=self.layer_norm.weight, beta=self.layer_norm.bias, mode=_mode_of(self),
+                             dropout=self.dropout_1.p, training=self.training, eps=self.layer_norm.eps)
+
+
+class OcrPtrNet(nn.Module):
+    """mmf_m4c.py:367-396: ``(Wq·dec + b)(Wk·ocr + b)ᵀ / √d_qk + mask``."""
+
+    def __init__(self, hidden_size, query_key_size=None):
+        super().__init__()
+        query_key_size = hidden_size if query_key_size is None else query_key_size
+        self.hidden_size, self.query_key_size = hidden_size, query_key_size
+        self.query = nn.Linear(hidden_size, query_key_size)
+        self.key = nn.Linear(hidden_size, query_key_size)
+        self.compute_dtype = None
+
+    def forward(self, query_inputs, key_inputs, attention_mask, scores_out=None, col_offset=0):
+        """``scores_out`` (B,T,W) fp32 + ``col_offset``: write the pointer scores straight into the joint score
+        tensor (replaces the ``torch.cat`` at mmf_m4c.py:227).  Inference-only fast path; returns (B,T,Locr)."""
+        mode = _mode_of(self)
+        squeeze = query_inputs.dim() == 2
+        if squeeze:
+            query_inputs = query_inputs.unsqueeze(1)
+        odt = torch.float32 if mode == "fp32" else torch.bfloat16
+        q = Fn.linear(query_inputs, self.query.weight, self.query.bias, mode, odt)
+        k = Fn.linear(key_inputs, self.key.weight, self.key.bias, mode, odt)
+        B, T, L = q.shape[0], q.shape[1], k.shape[1]
+        if scores_out is None:
+            scores_out, col_offset = torch.empty((B, T, L), device=q.device, dtype=torch.float32), 0
+        ops.ptr_scores(q.detach(), k.detach(), attention_mask, scores_out, col_offset, 1.0 / math.sqrt(self.query_key_size))
+        res = scores_out[..., col_offset:col_offset + L]
+        return res.squeeze(1) if squeeze else res
+
+
+class DynamicPointerNetwork(nn.Module):
+    """m4c.py:19-33 (author's variant): ``QKᵀ/√d_model`` with ``masked_fill(-inf)`` on a boolean key mask."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.d_model = config.D_MODEL
+        self.fc_q = nn.Linear(config.D_MODEL, config.D_MODEL)
+        self.fc_k = nn.Linear(config.D_MODEL, config.D_MODEL)
+        self.compute_dtype = getattr(config, "COMPUTE_DTYPE", None)
+
+    def forward(self, query_inputs, key_inputs, attention_mask):
+        mode = _mode_of(self)
+        odt = torch.float32 if mode == "fp32" else torch.bfloat16
+        q = Fn.linear(query_inputs, self.fc_q.weight, self.fc_q.bias, mode, odt)
+        k = Fn.linear(key_inputs, self.fc_k.weight, self.fc_k.bias, mode, odt)
+        scores = torch.empty((q.shape[0], q.shape[1], k.shape[1]), device=q.device, dtype=torch.float32)
+        return ops.ptr_scores(q.detach(), k.detach(), attention_mask, scores, 0, 1.0 / math.sqrt(self.d_model), mask_is_bool=True)

@@ -1,0 +1,326 @@
+"""Thin PyTorch-facing wrappers over the C ABI: shape/dtype/device validation, then one library call.
+
+Every function enqueues on ``torch.cuda.current_stream()`` and returns device tensors.  CPU tensors are an
+error (SURVEY.md §8b "Errors": no CPU fallback).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+_DT = {torch.float32: L.F32, torch.bfloat16: L.BF16}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise ValueError("openvivqa_b200 kernels need CUDA tensors (no CPU fallback); got a CPU tensor")
+
+
+def _rowmajor2d(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dim() != 2:
+        raise ValueError(f"{name}: expected a 2-D tensor, got {tuple(t.shape)}")
+    if t.stride(1) != 1 and t.shape[1] != 1:
+        t = t.contiguous()
+    return t
+
+
+def _ld(t: torch.Tensor) -> int:
+    return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, *, a_op: str = "N", b_op: str = "N", out: Optional[torch.Tensor] = None,
+         out_dtype: Optional[torch.dtype] = None, bias: Optional[torch.Tensor] = None, alpha: float = 1.0,
+         beta: float = 0.0, gelu: bool = False, dgelu_aux: Optional[torch.Tensor] = None,
+         aux_out: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+         c2: Optional[torch.Tensor] = None, dropout_p: float = 0.0, seed: int = 0, offset: int = 0,
+         split_k: int = 1) -> torch.Tensor:
+    """``C[m,n] = epilogue(sum_k A[m,k] B[n,k])`` — see ``ovqa_gemm`` in include/ovqa.h.
+
+    ``a_op``/``b_op``: "N" = operand stored [rows, k]; "T" = stored [k, rows]."""
+    _need_cuda(a, b, out, bias, dgelu_aux, aux_out, residual, c2)
+    a, b = _rowmajor2d(a, "a"), _rowmajor2d(b, "b")
+    if a.dtype != b.dtype or a.dtype not in _DT:
+        raise ValueError(f"gemm: operand dtypes must match and be fp32/bf16, got {a.dtype}, {b.dtype}")
+    m, k = (a.shape if a_op == "N" else (a.shape[1], a.shape[0]))
+    n, kb = (b.shape if b_op == "N" else (b.shape[1], b.shape[0]))
+    if k != kb:
+        raise ValueError(f"gemm: reduction sizes differ ({k} vs {kb})")
+    if out is None:
+        out = torch.empty((m, n), device=a.device, dtype=out_dtype or a.dtype) if split_k <= 1 and beta == 0.0 \
+            else torch.zeros((m, n), device=a.device, dtype=out_dtype or torch.float32)
+    if out.shape != (m, n) or out.dtype not in _DT or (out.stride(1) != 1 and n != 1):
+        raise ValueError("gemm: bad `out`")
+    if bias is not None and (bias.dtype != torch.float32 or bias.numel() != n or not bias.is_contiguous()):
+        raise ValueError("gemm: bias must be contiguous fp32 [n]")
+    for t, nm in ((residual, "residual"),):
+        if t is not None and (t.dtype != torch.float32 or t.shape != (m, n) or t.stride(1) != 1):
+            raise ValueError(f"gemm: {nm} must be fp32 [m,n] with unit column stride")
+    for t, nm in ((dgelu_aux, "dgelu_aux"), (aux_out, "aux_out")):
+        if t is not None and (t.dtype != out.dtype or t.shape != (m, n) or t.stride(1) != 1):
+            raise ValueError(f"gemm: {nm} must have out's dtype and shape")
+    if dgelu_aux is not None and aux_out is not None and _ld(dgelu_aux) != _ld(aux_out):
+        raise ValueError("gemm: aux_in/aux_out must share a leading dimension")
+    if c2 is not None and (c2.dtype != torch.bfloat16 or c2.shape != (m, n) or c2.stride(1) != 1):
+        raise ValueError("gemm: c2 must be bf16 [m,n]")
+    flags = (L.EPI_GELU if gelu else 0) | (L.EPI_DGELU if dgelu_aux is not None else 0)
+    aux = dgelu_aux if dgelu_aux is not None else aux_out
+    L.call("ovqa_gemm", _p(a), _p(b), _p(out), m, n, k, _ld(a), _ld(b), _ld(out),
+           L.OP_N if a_op == "N" else L.OP_T, L.OP_N if b_op == "N" else L.OP_T, _DT[a.dtype], _DT[out.dtype],
+           float(alpha), float(beta), _p(bias), flags, _p(dgelu_aux), _p(aux_out), _ld(aux) if aux is not None else 0,
+           _p(residual), _ld(residual) if residual is not None else 0, _p(c2), _ld(c2) if c2 is not None else 0,
+           float(dropout_p), int(seed), int(offset), int(split_k), _stream())
+    return out
+
+
+def gemm_bf16_simt(a, b, *, a_op="N", b_op="N", out_dtype=torch.float32, bias=None, alpha=1.0, gelu=False):
+    """CUDA-core twin of the tcgen05 path (tests only)."""
+    _need_cuda(a, b)
+    a, b = _rowmajor2d(a, "a"), _rowmajor2d(b, "b")
+    m, k = (a.shape if a_op == "N" else (a.shape[1], a.shape[0]))
+    n = b.shape[0] if b_op == "N" else b.shape[1]
+    out = torch.empty((m, n), device=a.device, dtype=out_dtype)
+    L.call("ovqa_gemm_bf16_simt", _p(a), _p(b), _p(out), m, n, k, _ld(a), _ld(b), _ld(out),
+           L.OP_N if a_op == "N" else L.OP_T, L.OP_N if b_op == "N" else L.OP_T, _DT[out_dtype], float(alpha), _p(bias),
+           L.EPI_GELU if gelu else 0, _stream())
+    return out
+
+
+def _mask_strides(mask: Optional[torch.Tensor], B: int, h: int, Lq: int, Lk: int):
+    """Additive fp32 mask broadcastable to (B,h,Lq,Lk) -> (tensor, sb, sh, sq) with unit key stride."""
+    if mask is None:
+        return None, 0, 0, 0
+    if mask.dtype != torch.float32:
+        mask = mask.float()
+    while mask.dim() < 4:
+        mask = mask.unsqueeze(0)
+    if mask.dim() != 4 or mask.shape[-1] != Lk:
+        raise ValueError(f"attention_mask {tuple(mask.shape)} is not broadcastable to (B,h,Lq,{Lk})")
+    for d, full in zip(range(3), (B, h, Lq)):
+        if mask.shape[d] not in (1, full):
+            raise ValueError(f"attention_mask {tuple(mask.shape)} is not broadcastable to ({B},{h},{Lq},{Lk})")
+    if mask.stride(-1) != 1 and Lk > 1:
+        mask = mask.contiguous()
+    st = [0 if mask.shape[d] == 1 else mask.stride(d) for d in range(3)]
+    return mask, st[0], st[1], st[2]
+
+
+class GeoParams:
+    """Box-geometry arguments of the fused core: boxes (B,N,4) fp32, w (h,d_g), b (h), freq table."""
+
+    def __init__(self, boxes, w, b, trig: bool):
+        self.boxes = boxes.float().contiguous()
+        self.w = w.float().contiguous()
+        self.b = b.float().contiguous()
+        self.trig = bool(trig)
+        self.d_g = self.w.shape[1]
+        if self.trig:
+            # models/utils.py:146-148, computed with the same torch ops so the table is bit-identical
+            fr = torch.arange(self.d_g / 8, device=self.boxes.device)
+            self.freq = (1.0 / torch.pow(1000, fr / (self.d_g / 8))).float().contiguous()
+        else:
+            self.freq = None
+
+
+def sdpa_fwd(q, k, v, *, h: int, d_k: int, d_v: int, mask=None, geo: Optional[GeoParams] = None,
+             scale: Optional[float] = None, need_lse: bool = False, need_att: bool = False, out=None):
+    """Attention core on projected tensors.  q:(B,Lq,>=h*d_k) k:(B,Lk,..) v:(B,Lk,..) — last-dim-contiguous views
+    (e.g. slices of a fused QKV buffer).  Returns (out (B,Lq,h*d_v), lse|None, att|None)."""
+    _need_cuda(q, k, v, mask)
+    if q.dtype not in _DT or k.dtype != q.dtype or v.dtype != q.dtype:
+        raise ValueError("sdpa: q,k,v must share a dtype in {fp32, bf16}")
+    B, Lq, Lk = q.shape[0], q.shape[1], k.shape[1]
+    for t, L_, nm in ((q, Lq, "q"), (k, Lk, "k"), (v, Lk, "v")):
+        if t.dim() != 3 or t.stride(2) != 1 or (t.shape[0] > 1 and t.stride(0) != L_ * t.stride(1)):
+            raise ValueError(f"sdpa: {nm} must be (B,L,*) with dense batches and unit last stride")
+    if out is None:
+        out = torch.empty((B, Lq, h * d_v), device=q.device, dtype=q.dtype)
+    lse = torch.empty((B, h, Lq), device=q.device, dtype=torch.float32) if need_lse else None
+    att = torch.empty((B, h, Lq, Lk), device=q.device, dtype=torch.float32) if need_att else None
+    mask, sb, sh, sq = _mask_strides(mask, B, h, Lq, Lk)
+    if scale is None:
+        scale = 1.0 / math.sqrt(d_k)
+    g = geo
+    L.call("ovqa_sdpa_fwd", _p(q), _p(k), _p(v), _p(out), B, h, Lq, Lk, d_k, d_v,
+           q.stride(1), k.stride(1), v.stride(1), out.stride(1), _p(mask), sb, sh, sq,
+           _p(g.boxes) if g else None, _p(g.w) if g else None, _p(g.b) if g else None,
+           _p(g.freq) if (g and g.freq is not None) else None, g.d_g if g else 0, int(g.trig) if g else 0,
+           float(scale), _DT[q.dtype], _p(lse), _p(att), _stream())
+    return out, lse, att
+
+
+def sdpa_bwd(q, k, v, out, dout, lse, dq, dk, dv, *, h: int, d_k: int, d_v: int, mask=None,
+             geo: Optional[GeoParams] = None, geo_dw=None, geo_db=None, scale: Optional[float] = None):
+    _need_cuda(q, k, v, out, dout, lse, dq, dk, dv)
+    B, Lq, Lk = q.shape[0], q.shape[1], k.shape[1]
+    mask, sb, sh, sq = _mask_strides(mask, B, h, Lq, Lk)
+    if dout.stride(2) != 1:
+        dout = dout.contiguous()
+    delta = torch.empty((B, h, Lq), device=q.device, dtype=torch.float32)
+    if scale is None:
+        scale = 1.0 / math.sqrt(d_k)
+    g = geo
+    L.call("ovqa_sdpa_bwd", _p(q), _p(k), _p(v), _p(out), _p(dout), _p(dq), _p(dk), _p(dv), B, h, Lq, Lk, d_k, d_v,
+           q.stride(1), k.stride(1), v.stride(1), out.stride(1), dout.stride(1), dq.stride(1), dk.stride(1), dv.stride(1),
+           _p(mask), sb, sh, sq,
+           _p(g.boxes) if g else None, _p(g.w) if g else None, _p(g.b) if g else None,
+           _p(g.freq) if (g and g.freq is not None) else None, g.d_g if g else 0, int(g.trig) if g else 0,
+           _p(geo_dw), _p(geo_db), float(scale), _DT[q.dtype], _p(lse), _p(delta), _stream())
+
+
+def layernorm_fwd(x, gamma, beta, *, residual=None, post_add=None, eps: float = 1e-5, want_f32: bool = True,
+                  want_bf16: bool = False, save_stats: bool = False, save_sum: bool = False):
+    """y = LN(x [+ residual]) [+ post_add];  returns (y_f32|None, y_bf16|None, sum|None, mean|None, rstd|None)."""
+    _need_cuda(x, gamma, beta, residual, post_add)
+    D = x.shape[-1]
+    x2 = x.reshape(-1, D)
+    if x2.dtype != torch.float32:
+        raise ValueError("layernorm: x must be fp32")
+    x2 = x2.contiguous()
+    rows = x2.shape[0]
+    r2 = None if residual is None else residual.reshape(-1, D).contiguous()
+    pa, pa_rows = None, 0
+    if post_add is not None:
+        pa = post_add.reshape(-1, D).contiguous().float()
+        pa_rows = pa.shape[0]
+        if rows % pa_rows != 0:
+            raise ValueError("layernorm: post_add rows must divide the row count")
+    y = torch.empty_like(x2) if want_f32 else None
+    y16 = torch.empty(x2.shape, device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    s = torch.empty_like(x2) if save_sum else None
+    mean = torch.empty((rows,), device=x.device, dtype=torch.float32) if save_stats else None
+    rstd = torch.empty((rows,), device=x.device, dtype=torch.float32) if save_stats else None
+    L.call("ovqa_layernorm_fwd", _p(x2), _p(r2), _p(gamma), _p(beta), _p(pa), pa_rows, _p(y), _p(y16), _p(s), _p(mean),
+           _p(rstd), rows, D, float(eps), _stream())
+    shp = x.shape
+    return (None if y is None else y.view(shp), None if y16 is None else y16.view(shp),
+            None if s is None else s.view(shp), mean, rstd)
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, *, dx_add=None, want_bf16: bool = False, dropout_p: float = 0.0,
+                  seed: int = 0, offset: int = 0, dgamma=None, dbeta=None):
+    _need_cuda(dy, x, mean, rstd, gamma)
+    D = x.shape[-1]
+    dy2, x2 = dy.reshape(-1, D).contiguous().float(), x.reshape(-1, D)
+    rows = x2.shape[0]
+    dx = torch.empty_like(x2)
+    dx16 = torch.empty(x2.shape, device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    if dgamma is None:
+        dgamma = torch.zeros((D,), device=x.device, dtype=torch.float32)
+    if dbeta is None:
+        dbeta = torch.zeros((D,), device=x.device, dtype=torch.float32)
+    L.call("ovqa_layernorm_bwd", _p(dy2), _p(x2), _p(mean), _p(rstd), _p(gamma),
+           None if dx_add is None else _p(dx_add.reshape(-1, D).contiguous()), _p(dx), _p(dx16), _p(dgamma), _p(dbeta),
+           rows, D, float(dropout_p), int(seed), int(offset), _stream())
+    return dx.view(x.shape), (None if dx16 is None else dx16.view(x.shape)), dgamma, dbeta
+
+
+def to_bf16(x: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x)
+    if x.dtype == torch.bfloat16:
+        return x
+    x = x.contiguous()
+    y = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    L.call("ovqa_cast_f32_to_bf16", _p(x), _p(y), x.numel(), _stream())
+    return y
+
+
+def to_f32(x: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x)
+    if x.dtype == torch.float32:
+        return x
+    x = x.contiguous()
+    y = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+    L.call("ovqa_cast_bf16_to_f32", _p(x), _p(y), x.numel(), _stream())
+    return y
+
+
+def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    _need_cuda(x)
+    x = _rowmajor2d(x, "x")
+    if out is None:
+        out = torch.empty((x.shape[1],), device=x.device, dtype=torch.float32)
+        accumulate = False
+    L.call("ovqa_colsum", _p(x), _p(out), x.shape[0], x.shape[1], _ld(x), _DT[x.dtype], int(accumulate), _stream())
+    return out
+
+
+def add(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    _need_cuda(a, b)
+    a, b = a.contiguous(), b.contiguous()
+    y = torch.empty_like(a)
+    L.call("ovqa_add_f32", _p(a), _p(b), _p(y), a.numel(), _stream())
+    return y
+
+
+def dropout_apply(x: torch.Tensor, p: float, seed: int, offset: int, out_dtype=torch.float32) -> torch.Tensor:
+    """y = dropout(x) with the library's counter-based mask over the flattened index space (p=0: cast)."""
+    _need_cuda(x)
+    x = x.contiguous()
+    y = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    L.call("ovqa_dropout_apply", _p(x), _p(y), x.numel(), float(p), int(seed), int(offset), _DT[out_dtype], _stream())
+    return y
+
+
+def dropout_keep_mask(n: int, p: float, seed: int, offset: int, device) -> torch.Tensor:
+    out = torch.empty((n,), device=device, dtype=torch.float32)
+    L.call("ovqa_dropout_mask", _p(out), n, float(p), int(seed), int(offset), _stream())
+    return out
+
+
+def box_geometry_bias(geo: GeoParams, h: int) -> torch.Tensor:
+    B, N = geo.boxes.shape[:2]
+    out = torch.empty((B, h, N, N), device=geo.boxes.device, dtype=torch.float32)
+    L.call("ovqa_box_geometry_bias", _p(geo.boxes), _p(geo.w), _p(geo.b), _p(geo.freq) if geo.freq is not None else None,
+           _p(out), B, N, h, geo.d_g, int(geo.trig), _stream())
+    return out
+
+
+def ptr_scores(q, k, mask, scores, col_offset: int, scale: float, mask_is_bool: bool = False):
+    """Writes ``scores[:, :, col_offset:col_offset+L]`` in place (scores: fp32 (B,T,W) contiguous)."""
+    _need_cuda(q, k, mask, scores)
+    B, T, d = q.shape
+    Lk = k.shape[1]
+    if q.stride(2) != 1 or k.stride(2) != 1 or not scores.is_contiguous() or scores.dtype != torch.float32:
+        raise ValueError("ptr_scores: bad layout")
+    if mask is not None:
+        mask = mask.reshape(B, Lk).contiguous()
+        mask = mask.to(torch.uint8) if mask_is_bool else mask.float()
+    L.call("ovqa_ptr_scores", _p(q), _p(k), _p(mask), _p(scores), B, T, Lk, d, q.stride(1), k.stride(1), scores.shape[-1],
+           col_offset, float(scale), _DT[q.dtype], int(mask_is_bool), _stream())
+    return scores
+
+
+def prev_pred_embed(ans_emb, ocr_emb, prev_inds, pos_emb, type_emb, ans_ln, ocr_ln, emb_ln, eps: float, out=None):
+    """ans_ln/ocr_ln/emb_ln: (gamma, beta) pairs.  out: fp32 view (B,T,D) with unit last stride (may be a slice of the
+    joint encoder input)."""
+    _need_cuda(ans_emb, ocr_emb, prev_inds)
+    B, T = prev_inds.shape
+    V, D = ans_emb.shape
+    Locr = ocr_emb.shape[1]
+    if out is None:
+        out = torch.empty((B, T, D), device=ans_emb.device, dtype=torch.float32)
+    L.call("ovqa_prev_pred_embed", _p(ans_emb.contiguous()), _p(ocr_emb.contiguous()), _p(prev_inds.contiguous()),
+           _p(pos_emb), _p(type_emb), _p(ans_ln[0]), _p(ans_ln[1]), _p(ocr_ln[0]), _p(ocr_ln[1]), _p(emb_ln[0]),
+           _p(emb_ln[1]), _p(out), B, T, V, Locr, D, out.stride(1), out.stride(0) if B > 1 else T * out.stride(1),
+           float(eps), _stream())
+    return out
+
+
+def greedy_step(scores, prev_inds, last_ids, argmax_out, all_eos, step: int, eos_idx: int):
+    _need_cuda(scores, prev_inds, last_ids, argmax_out, all_eos)
+    B, T, W = scores.shape
+    L.call("ovqa_greedy_step", _p(scores.contiguous()), _p(prev_inds), _p(last_ids), _p(argmax_out), _p(all_eos), B, T, W,
+           int(step), int(eos_idx), _stream())

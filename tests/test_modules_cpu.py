@@ -1,0 +1,97 @@
+"""CPU: host-side logic of the drop-ins — parameter names/shapes/initialisers, registry contract, install()."""
+import pytest
+import torch
+
+import openvivqa_b200 as ovqa
+from openvivqa_b200 import harness as H
+from oracle import cases as C
+from oracle import ref_loader as RL
+
+
+def _spec(m):
+    return [(k, tuple(v.shape)) for k, v in m.state_dict().items() if v.dtype.is_floating_point]
+
+
+def test_mha_and_pwff_state_dict_keys_match_the_reference_spec():
+    assert _spec(ovqa.MultiHeadAttention(H.attention_cfg())) == C.att_spec(512, 8, 64, 64)
+    assert _spec(ovqa.MultiHeadAttention(H.attention_cfg(use_aoa=True))) == C.att_spec(512, 8, 64, 64, aoa=True)
+    assert _spec(ovqa.MultiHeadAttention(H.attention_cfg(head=1, d_key=64, d_value=64))) == C.att_spec(512, 1, 64, 64)
+    geo = ovqa.MultiHeadAttention(H.attention_cfg(arch="AugmentedGeometryScaledDotProductAttention"))
+    assert _spec(geo) == C.att_spec(512, 8, 64, 64, geometry_dg=64)
+    assert _spec(ovqa.PositionWiseFeedForward(H.attention_cfg())) == C.pwff_spec(512, 2048)
+
+
+def test_model_state_dicts_match_reference_generated_specs(golden):
+    g = golden("mcan")
+    c = C.MCAN_SMALL
+    m = H.MCAN(H.mcan_cfg(c["d_model"], c["d_feature"], c["layers"], c["h"], c["d_ff"]), H.StubVocab(c["vocab"], c["answers"]))
+    assert _spec(m) == [tuple(x) for x in g["small"]["spec"]]
+    e = golden("encoders")
+    x = H.xmt_cfg("cross", 128, 256, 2, 4, 256)
+    assert _spec(H.CrossModalityEncoder(x.ENCODER)) == [tuple(t) for t in e["CrossModalityEncoder"]["spec"]]
+    x = H.xmt_cfg("co", 128, 256, 2, 4, 256)
+    assert _spec(H.CoAttentionEncoder(x.ENCODER)) == [tuple(t) for t in e["CoAttentionEncoder"]["spec"]]
+
+
+def test_initialisers_follow_the_reference():
+    torch.manual_seed(0)
+    m = ovqa.ScaledDotProductAttention(H.attention_cfg())
+    for fc in (m.fc_q, m.fc_k, m.fc_v, m.fc_o):
+        assert torch.count_nonzero(fc.bias) == 0                       # attentions.py:41-44
+        bound = (6.0 / (fc.weight.shape[0] + fc.weight.shape[1])) ** 0.5   # xavier_uniform_
+        assert fc.weight.abs().max() <= bound + 1e-6 and fc.weight.abs().max() > 0.9 * bound
+    mha = ovqa.MultiHeadAttention(H.attention_cfg())
+    assert mha.layer_norm.eps == 1e-5 and mha.dropout.p == 0.1
+
+
+def test_registry_contract():
+    assert "ScaledDotProductAttention" in ovqa.META_ATTENTION
+    core = ovqa.build_attention(H.attention_cfg())
+    assert isinstance(core, ovqa.ScaledDotProductAttention)
+    with pytest.raises(KeyError):
+        ovqa.META_ATTENTION.get("NoSuchAttention")
+    with pytest.raises(AssertionError):                                 # duplicate names assert (registry.py:43-47)
+        ovqa.META_ATTENTION.register(ovqa.ScaledDotProductAttention)
+
+
+def test_stateful_module_semantics():
+    m = ovqa.MultiHeadAttention(H.attention_cfg(stateful=True))
+    assert m.running_keys.shape == (0, 512)
+    with m.statefulness(3):
+        assert m._is_stateful and m.running_keys.shape == (3, 0, 512)
+    assert not m._is_stateful and m.running_keys.shape == (0, 512)
+
+
+def test_compute_dtype_selection():
+    assert ovqa.get_compute_dtype() in ("fp32", "bf16")
+    with pytest.raises(ValueError):
+        ovqa.set_compute_dtype("fp8")
+    m = ovqa.PositionWiseFeedForward(H.attention_cfg(compute_dtype="bf16"))
+    assert m.compute_dtype == "bf16"
+
+
+@pytest.mark.skipif(not RL.available(), reason="/root/reference not mounted")
+def test_install_into_the_reference_checkout_and_reference_state_dict_loads():
+    RL.load()
+    import models.modules.attentions as A
+    import models.modules.encoders as E
+    from builders.attention_builder import META_ATTENTION
+
+    ref_mha = A.MultiHeadAttention(RL.attention_cfg())
+    try:
+        ovqa.install()
+        assert META_ATTENTION.get("ScaledDotProductAttention") is ovqa.ScaledDotProductAttention
+        assert E.MultiHeadAttention.__module__.startswith("openvivqa_b200")
+        enc = E.Encoder(RL.NS(D_MODEL=512, LAYERS=1, SELF_ATTENTION=RL.attention_cfg()))   # the reference's own Encoder
+        mha = enc.layers[0].mhatt
+        assert type(mha).__module__.startswith("openvivqa_b200")
+        from models.modules.containers import Module
+        assert isinstance(mha, Module)                      # stateful recursion of the reference still sees it
+        assert isinstance(enc.layers[0].pwff, ovqa.PositionWiseFeedForward)
+        mha.load_state_dict(ref_mha.state_dict(), strict=True)      # reference checkpoints load unchanged
+        # memory / adaptive cores stay the reference's
+        assert META_ATTENTION.get("AdaptiveScaledDotProductAttention").__module__ == "models.modules.attentions"
+    finally:
+        ovqa.uninstall()
+    assert E.MultiHeadAttention is A.MultiHeadAttention
+    assert META_ATTENTION.get("ScaledDotProductAttention").__module__ == "models.modules.attentions"
