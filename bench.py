@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py — MCAN training-step throughput (VQA samples/sec) through the B200 hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload mcan_train]
+
+Workload (BASELINE.json configs[1]): MCAN, 30 question tokens, 100 regions x 2048-d, d_model 512, 8 heads,
+6 SA + 6 SGA layers, batch 256 per GPU, bf16 operands / fp32 accumulate, dropout 0.1 active, NLL loss, Adam —
+synthetic ViVQA-shaped data, random-init weights.  One process per GPU (torchrun for N>1), NCCL gradient
+all-reduce overlapped with backward, weak scaling.
+
+Prints ONE JSON line (rank 0).  `value` = device-resident whole-job samples/s; `e2e` = the same step fed from
+pinned HOST buffers every step (H2D copy of the next batch overlapped on a copy stream, D2H read of the loss);
+`roofline` = the dominant kernel (tcgen05 GEMM) timed live with CUDA events; `cpu_baseline` = the oracle port of
+the reference MCAN step timed on the host cores (bounded sample).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+WORKLOAD = dict(name="mcan_train", B=256, Lt=30, Nv=100, d_feature=2048, d_model=512, h=8, layers=6, d_ff=2048,
+                vocab=4096, answers=353, dropout=0.1)
+
+
+# ----------------------------------------------------------------------------------------------- helpers
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], bf16_tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 and len(r) >= 8] or [r for (_, r) in self.rows if len(r) >= 8]
+        if not rows:
+            return None
+        sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in rows for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=float(rows[0][2]) if rows[0][2].replace(".", "").isdigit() else None,
+                    reasons=reasons, samples=len(rows))
+
+
+def synth_batches(n, wl, seed=1):
+    """n distinct synthetic ViVQA-shaped batches in pinned host memory."""
+    g = torch.Generator().manual_seed(seed)
+    B, Nv, Lt = wl["B"], wl["Nv"], wl["Lt"]
+    out = []
+    for _ in range(n):
+        feats = torch.randn((B, Nv, wl["d_feature"]), generator=g).abs_()
+        nv = torch.randint(36, Nv + 1, (B,), generator=g)
+        feats[torch.arange(Nv).unsqueeze(0) >= nv.unsqueeze(1)] = 0.0
+        toks = torch.randint(4, wl["vocab"], (B, Lt), generator=g)
+        nt = torch.randint(5, Lt + 1, (B,), generator=g)
+        toks[torch.arange(Lt).unsqueeze(0) >= nt.unsqueeze(1)] = 0
+        ans = torch.randint(0, wl["answers"], (B,), generator=g)
+        out.append(tuple(t.pin_memory() if torch.cuda.is_available() else t for t in (feats, toks, ans)))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- reference / CPU arm
+def cpu_mcan_step_fn(wl, B, seed=0):
+    """The oracle port of the reference MCAN training step (fwd + NLL + bwd + Adam) on the host cores."""
+    from openvivqa_b200 import harness as H
+    from oracle import restated as R, synth as S
+
+    spec_model = H.MCAN(H.mcan_cfg(wl["d_model"], wl["d_feature"], wl["layers"], wl["h"], wl["d_ff"]), H.StubVocab(wl["vocab"], wl["answers"]))
+    params = S.synth_params([(k, tuple(v.shape)) for k, v in spec_model.state_dict().items()], seed)
+    params = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    opt = torch.optim.Adam(list(params.values()), lr=1e-4, betas=(0.9, 0.98))
+    feats, toks, ans = synth_batches(1, dict(wl, B=B))[0]
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        logp = R.mcan_forward(params, feats, toks, d_model=wl["d_model"], h=wl["h"], layers=wl["layers"], dropout=wl["dropout"], training=True)
+        loss = F.nll_loss(logp, ans)
+        loss.backward()
+        opt.step()
+        return loss.item()
+
+    return step
+
+
+def time_cpu(wl, B, steps, warmup):
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = cpu_mcan_step_fn(wl, B)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return B * steps / dt, dt / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOAD
+    B = 32
+    sps, per = time_cpu(wl, B, max(1, args.steps), max(1, min(args.warmup, 2)))
+    cores = torch.get_num_threads()
+    line = dict(metric="VQA samples/sec (MCAN train)", value=sps, unit="samples/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=per * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
+                config=dict(workload="mcan_train: MCAN 6SA+6SGA d512 h8, 30 tok, 100x2048 regions (BASELINE configs[1])",
+                            batch_per_step=B, note="reference CPU path = oracle port of the reference PyTorch step (fwd+NLL+bwd+Adam), all host threads"),
+                cpu_baseline=dict(value=sps, unit="samples/s", cores=cores, kind="port", sample=f"{args.steps} steps of batch {B} (of 256/GPU)"),
+                e2e=dict(value=sps, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+class GemmMeter:
+    """CUDA-event timing of every tcgen05 GEMM launch inside the timed region (events on the launching stream)."""
+
+    def __init__(self):
+        self.records, self.enabled = [], False
+
+    def install(self):
+        from openvivqa_b200 import ops
+        orig = ops.gemm
+        meter = self
+
+        def gemm(a, b, **kw):
+            if not meter.enabled or a.dtype != torch.bfloat16:
+                return orig(a, b, **kw)
+            m, k = a.shape if kw.get("a_op", "N") == "N" else (a.shape[1], a.shape[0])
+            n = b.shape[0] if kw.get("b_op", "N") == "N" else b.shape[1]
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = orig(a, b, **kw)
+            e1.record()
+            meter.records.append((e0, e1, 2.0 * m * n * k))
+            return out
+
+        ops.gemm = gemm
+
+    def summary(self):
+        if not self.records:
+            return None
+        ms = sum(e0.elapsed_time(e1) for e0, e1, _ in self.records)
+        fl = sum(f for _, _, f in self.records)
+        return dict(launches=len(self.records), total_ms=ms, flops=fl, tflops=fl / (ms * 1e-3) / 1e12, avg_us=ms * 1e3 / len(self.records))
+
+
+def run_ours(args):
+    import torch.distributed as dist
+
+    import openvivqa_b200 as ovqa
+    from openvivqa_b200 import _lib, harness as H
+
+    wl = WORKLOAD
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()                                   # fail loudly if the CUDA library is missing
+    ovqa.set_compute_dtype("bf16")
+    torch.manual_seed(0)
+    model = H.MCAN(H.mcan_cfg(wl["d_model"], wl["d_feature"], wl["layers"], wl["h"], wl["d_ff"], dropout=wl["dropout"], compute_dtype="bf16"),
+                   H.StubVocab(wl["vocab"], wl["answers"])).to(dev).train()
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True, bucket_cap_mb=25)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.9, 0.98), fused=True)
+    host = synth_batches(3, wl, seed=1 + rank)
+    dev_batches = [tuple(t.to(dev) for t in b) for b in host]
+    meter = GemmMeter()
+    meter.install()
+
+    def step(feats, toks, ans):
+        with torch.autocast("cuda", dtype=torch.bfloat16):      # library ops around the hot path (LSTM, embedding Linear, head)
+            logp = net(H.Batch(region_features=feats, question_tokens=toks))
+        loss = F.nll_loss(logp.float(), ans)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (`value`)
+    for i in range(args.warmup):
+        step(*dev_batches[i % len(dev_batches)])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count
+    meter.enabled = True
+    t_wall0 = time.time()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = step(*dev_batches[i % len(dev_batches)])
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    meter.enabled = False
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count - launches0
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    final_loss = loss.item()
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    value = wl["B"] * world * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end timing: pinned host buffers -> device every step (prefetch on a copy stream), loss read back
+    if args.no_e2e:
+        if rank == 0:
+            print(json.dumps(dict(metric="VQA samples/sec (MCAN train)", value=value, ms_per_step=ms / args.steps, gpu_launches=launches,
+                                  note="profiling run: no e2e / roofline / cpu legs")), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    copy_stream = torch.cuda.Stream()
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
+
+    def fetch(i):
+        with torch.cuda.stream(copy_stream):
+            b = tuple(t.to(dev, non_blocking=True) for t in host[i % len(host)])
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return b, ev
+
+    for i in range(2):
+        b, ev = fetch(i)
+        torch.cuda.current_stream().wait_event(ev)
+        step(*b)
+    barrier()
+    t0 = time.perf_counter()
+    nxt = fetch(0)
+    for i in range(args.steps):
+        b, ev = nxt
+        torch.cuda.current_stream().wait_event(ev)
+        if i + 1 < args.steps:
+            nxt = fetch(i + 1)
+        loss = step(*b)
+        for t in b:
+            t.record_stream(torch.cuda.current_stream())
+        _ = loss.item()                                  # D2H read of the step's result
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = t.item()
+    e2e = wl["B"] * world * args.steps / e2e_s
+
+    if rank == 0:
+        peaks = load_peaks()
+        gm = meter.summary()
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        roof = None
+        if gm:
+            peak = peaks["bf16_tflops_sustained"]
+            roof = dict(bound="tensor", kernel="gemm_tcgen05_kernel (all bf16 GEMM launches of the step)", achieved=gm["tflops"], peak=peak,
+                        unit="TFLOP/s", frac=gm["tflops"] / peak, traffic=traffic, peak_source=peaks["source"] + " (sustained cuBLAS bf16)",
+                        launches=gm["launches"], avg_launch_us=gm["avg_us"], share_of_step=gm["total_ms"] / ms)
+        cpu_sps, cpu_per = time_cpu(wl, 32, 2, 1) if args.gpus == 1 and not args.no_cpu_baseline else (None, None)
+        line = dict(metric="VQA samples/sec (MCAN train)", value=value, unit="samples/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+                    config=dict(workload="mcan_train: MCAN 6SA+6SGA d512 h8 dff2048, 30 tok, 100x2048 regions, batch 256/GPU, dropout 0.1, "
+                                         "NLL+Adam (BASELINE configs[1])", global_batch=wl["B"] * world, parallelism=f"dp{world}",
+                                l2="inputs larger than L2 (210 MB of features per step, 3 rotating batches)", final_loss=final_loss),
+                    e2e=dict(value=e2e, unit="samples/s", h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=4),
+                    gpu_launches=launches, roofline=roof, clocks=clocks)
+        if cpu_sps is not None:
+            line["cpu_baseline"] = dict(value=cpu_sps, unit="samples/s", cores=torch.get_num_threads(), kind="port",
+                                        sample="2 training steps (fwd+NLL+bwd+Adam) of batch 32 after 1 warm-up, oracle port on all host threads")
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs only)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

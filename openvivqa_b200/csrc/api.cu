@@ -1,4 +1,6 @@
 // extern "C" entry points of libovqa_b200.so (see include/ovqa.h): argument validation + dispatch.
+#include <cstdlib>
+
 #include "attention_simt.cuh"
 
 namespace ovqa {
@@ -63,6 +65,9 @@ extern "C" int ovqa_gemm(const void* A, const void* B, void* C, int64_t m, int64
     const bool epi_aligned = (ldc % 4 == 0) && (!residual || ld_res % 4 == 0) && (!(aux_in || aux_out) || ld_aux % 4 == 0) &&
                              (!c2_bf16 || ldc2 % 4 == 0) && (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0);
     if (!epi_aligned) return OVQA_ERR_ALIGNMENT;
+    // debugging aid only: OVQA_BF16_GEMM=simt routes bf16 GEMMs to the CUDA-core twin (to bisect a tensor-core bug)
+    static const bool force_simt = [] { const char* e = getenv("OVQA_BF16_GEMM"); return e && e[0] == 's'; }();
+    if (force_simt) return gemm_simt_bf16((const __nv_bfloat16*)A, (const __nv_bfloat16*)B, C, m, n, k, lda, ldb, ldc, a_op, b_op, e, split_k, st);
     return gemm_tcgen05_bf16((const __nv_bfloat16*)A, (const __nv_bfloat16*)B, C, m, n, k, lda, ldb, ldc, a_op, b_op, e, split_k, st);
 }
 

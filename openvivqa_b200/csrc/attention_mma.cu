@@ -1,6 +1,230 @@
-// placeholder until the tensor-core core lands (next commit)
+// Attention core on bf16 tensor-core tiles for the short-sequence regime (Lq ~ 30-182, Lk ~ 30-600):
+//   forward  : out = softmax(q k^T * scale + mask) v, flash-style over 64-key chunks staged in shared memory
+//   backward : dq kernel (CTA = query tile, streams keys) + dk/dv kernel (CTA = key tile, streams queries),
+//              probabilities recomputed from the saved row log-sum-exp.
+// One warp owns a 16-row MMA tile (mma.sync.m16n8k16 bf16 -> fp32); the softmax lives in registers with quad
+// shuffles; masks are added in fp32 before the running max (reference order).  The core is HBM-bound
+// (~23 FLOP/B at Lq=30, Lk=100): a 128-row tcgen05 tile would be 3/4 padding here, so the dense projections get
+// tcgen05 (gemm_tcgen05.cu) and the core gets warp-level tiles, as BASELINE.json's north_star prescribes.
 #include "attention_simt.cuh"
+
 namespace ovqa {
-bool sdpa_fwd_mma_supported(const SdpaArgs&) { return false; }
-int sdpa_fwd_mma_bf16(const SdpaArgs&, cudaStream_t) { return OVQA_ERR_BAD_SHAPE; }
+
+namespace {
+
+constexpr int KCH = 64;    // keys (or queries, in the dk/dv kernel) per streamed chunk
+constexpr int PAD = 8;     // bf16 elements of row padding: row pitch (D+8)*2 B -> conflict-free ldmatrix
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
 }
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+
+// Stage `rows` x D bf16 (global row pitch ld elements) into smem with pitch D+PAD; rows >= valid are zero-filled.
+template <int D>
+__device__ __forceinline__ void stage_rows(__nv_bfloat16* dst, const __nv_bfloat16* src, int64_t ld, int rows, int valid, int tid, int nthreads) {
+    constexpr int CPR = D / 8;  // 16-byte chunks per row
+    for (int i = tid; i < rows * CPR; i += nthreads) {
+        const int r = i / CPR, c = i % CPR;
+        __nv_bfloat16* d = dst + r * (D + PAD) + c * 8;
+        if (r < valid) cp_async16(d, src + (int64_t)r * ld + c * 8);
+        else *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
+    }
+}
+
+// A-operand fragments of a 16 x D row-major smem tile (pitch D+PAD), rows [row0, row0+16)
+template <int D>
+__device__ __forceinline__ void load_a_frags(uint32_t (&a)[D / 16][4], const __nv_bfloat16* tile, int row0, int lane) {
+    const int r = row0 + (lane % 8) + 8 * ((lane / 8) % 2), c = 8 * (lane / 16);
+#pragma unroll
+    for (int ks = 0; ks < D / 16; ++ks) ldsm_x4(smem_u32(tile + r * (D + PAD) + ks * 16 + c), a[ks][0], a[ks][1], a[ks][2], a[ks][3]);
+}
+
+// acc[nt] (16 x 8 each, nt over 64 "column" rows of `rows_tile`) += A(16 x D) . rows_tile^T      (S = Q K^T form)
+template <int D>
+__device__ __forceinline__ void mma_a_rowsT(float (&acc)[KCH / 8][4], const uint32_t (&a)[D / 16][4], const __nv_bfloat16* rows_tile, int lane) {
+    const int rr = (lane % 8) + 8 * (lane / 16), cc = 8 * ((lane / 8) % 2);
+#pragma unroll
+    for (int np = 0; np < KCH / 16; ++np) {
+#pragma unroll
+        for (int ks = 0; ks < D / 16; ++ks) {
+            uint32_t b0, b1, b2, b3;
+            ldsm_x4(smem_u32(rows_tile + (np * 16 + rr) * (D + PAD) + ks * 16 + cc), b0, b1, b2, b3);
+            mma_bf16(acc[2 * np], a[ks], b0, b1);
+            mma_bf16(acc[2 * np + 1], a[ks], b2, b3);
+        }
+    }
+}
+
+// out[nt] (16 x 8 each, nt over D columns) += P(16 x 64, from accumulator-layout registers) . rows_tile(64 x D)
+template <int D>
+__device__ __forceinline__ void mma_p_rows(float (&out)[D / 8][4], const float (&p)[KCH / 8][4], const __nv_bfloat16* rows_tile, int lane) {
+    const int rr = (lane % 8) + 8 * ((lane / 8) % 2), cc = 8 * (lane / 16);
+#pragma unroll
+    for (int ks = 0; ks < KCH / 16; ++ks) {
+        uint32_t a[4];
+        a[0] = pack_bf16x2(p[2 * ks][0], p[2 * ks][1]);
+        a[1] = pack_bf16x2(p[2 * ks][2], p[2 * ks][3]);
+        a[2] = pack_bf16x2(p[2 * ks + 1][0], p[2 * ks + 1][1]);
+        a[3] = pack_bf16x2(p[2 * ks + 1][2], p[2 * ks + 1][3]);
+#pragma unroll
+        for (int np = 0; np < D / 16; ++np) {
+            uint32_t b0, b1, b2, b3;
+            ldsm_x4_t(smem_u32(rows_tile + (ks * 16 + rr) * (D + PAD) + np * 16 + cc), b0, b1, b2, b3);
+            mma_bf16(out[2 * np], a, b0, b1);
+            mma_bf16(out[2 * np + 1], a, b2, b3);
+        }
+    }
+}
+
+__device__ __forceinline__ float quad_max(float v) { v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1)); return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2)); }
+__device__ __forceinline__ float quad_sum(float v) { v += __shfl_xor_sync(0xffffffffu, v, 1); return v + __shfl_xor_sync(0xffffffffu, v, 2); }
+
+// ------------------------------------------------------------------------------------------------ forward
+template <int D, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32) sdpa_fwd_mma_kernel(SdpaArgs a) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);          // [NWARPS*16][D+PAD]
+    __nv_bfloat16* sK = sQ + NWARPS * 16 * (D + PAD);                       // [KCH][D+PAD]
+    __nv_bfloat16* sV = sK + KCH * (D + PAD);                               // [KCH][D+PAD]
+    const int b = blockIdx.z, hd = blockIdx.y, q0 = blockIdx.x * NWARPS * 16;
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, g = lane / 4, t = lane % 4;
+    const int Lq = (int)a.Lq, Lk = (int)a.Lk;
+    const __nv_bfloat16* Q = reinterpret_cast<const __nv_bfloat16*>(a.q) + ((int64_t)b * Lq + q0) * a.ldq + (int64_t)hd * D;
+    const __nv_bfloat16* K = reinterpret_cast<const __nv_bfloat16*>(a.k) + (int64_t)b * Lk * a.ldk + (int64_t)hd * D;
+    const __nv_bfloat16* V = reinterpret_cast<const __nv_bfloat16*>(a.v) + (int64_t)b * Lk * a.ldv + (int64_t)hd * D;
+
+    stage_rows<D>(sQ, Q, a.ldq, NWARPS * 16, min(NWARPS * 16, Lq - q0), threadIdx.x, NWARPS * 32);
+    cp_async_wait_all();
+    __syncthreads();
+    uint32_t qa[D / 16][4];
+    load_a_frags<D>(qa, sQ, warp * 16, lane);
+
+    const int row_lo = q0 + warp * 16 + g, row_hi = row_lo + 8;      // the two query rows this thread holds
+    const float* mrow_lo = nullptr;
+    const float* mrow_hi = nullptr;
+    if (a.mask.ptr) {
+        const float* mb = a.mask.ptr + (int64_t)b * a.mask.sb + (int64_t)hd * a.mask.sh;
+        mrow_lo = mb + (int64_t)min(row_lo, Lq - 1) * a.mask.sq;
+        mrow_hi = mb + (int64_t)min(row_hi, Lq - 1) * a.mask.sq;
+    }
+    float o[D / 8][4];
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
+
+    for (int k0 = 0; k0 < Lk; k0 += KCH) {
+        const int nk = min(KCH, Lk - k0);
+        __syncthreads();                                   // previous chunk fully consumed
+        stage_rows<D>(sK, K + (int64_t)k0 * a.ldk, a.ldk, KCH, nk, threadIdx.x, NWARPS * 32);
+        stage_rows<D>(sV, V + (int64_t)k0 * a.ldv, a.ldv, KCH, nk, threadIdx.x, NWARPS * 32);
+        cp_async_wait_all();
+        __syncthreads();
+        float s[KCH / 8][4];
+#pragma unroll
+        for (int i = 0; i < KCH / 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+        mma_a_rowsT<D>(s, qa, sK, lane);
+        // scale, additive mask (fp32, before the max), key-range predicate
+        float cmax_lo = -INFINITY, cmax_hi = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < KCH / 8; ++nt) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int j = k0 + nt * 8 + 2 * t + e;
+                float v_lo = s[nt][e] * a.scale, v_hi = s[nt][2 + e] * a.scale;
+                if (j < Lk) {
+                    if (mrow_lo) { v_lo += __ldg(mrow_lo + j); v_hi += __ldg(mrow_hi + j); }
+                } else { v_lo = -INFINITY; v_hi = -INFINITY; }
+                s[nt][e] = v_lo; s[nt][2 + e] = v_hi;
+                cmax_lo = fmaxf(cmax_lo, v_lo); cmax_hi = fmaxf(cmax_hi, v_hi);
+            }
+        }
+        const float mn_lo = fmaxf(m_lo, quad_max(cmax_lo)), mn_hi = fmaxf(m_hi, quad_max(cmax_hi));
+        const float corr_lo = __expf(m_lo - mn_lo), corr_hi = __expf(m_hi - mn_hi);   // exp(-inf) = 0 on the first chunk
+        m_lo = mn_lo; m_hi = mn_hi;
+        float sum_lo = 0.f, sum_hi = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < KCH / 8; ++nt) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const float p_lo = __expf(s[nt][e] - m_lo), p_hi = __expf(s[nt][2 + e] - m_hi);
+                s[nt][e] = p_lo; s[nt][2 + e] = p_hi;
+                sum_lo += p_lo; sum_hi += p_hi;
+            }
+        }
+        l_lo = l_lo * corr_lo + quad_sum(sum_lo);
+        l_hi = l_hi * corr_hi + quad_sum(sum_hi);
+#pragma unroll
+        for (int i = 0; i < D / 8; ++i) { o[i][0] *= corr_lo; o[i][1] *= corr_lo; o[i][2] *= corr_hi; o[i][3] *= corr_hi; }
+        mma_p_rows<D>(o, s, sV, lane);
+    }
+    const float inv_lo = 1.f / l_lo, inv_hi = 1.f / l_hi;
+    __nv_bfloat16* O = reinterpret_cast<__nv_bfloat16*>(a.out) + (int64_t)b * Lq * a.ldo + (int64_t)hd * D;
+#pragma unroll
+    for (int nt = 0; nt < D / 8; ++nt) {
+        const int c = nt * 8 + 2 * t;
+        if (row_lo < Lq) *reinterpret_cast<uint32_t*>(O + (int64_t)row_lo * a.ldo + c) = pack_bf16x2(o[nt][0] * inv_lo, o[nt][1] * inv_lo);
+        if (row_hi < Lq) *reinterpret_cast<uint32_t*>(O + (int64_t)row_hi * a.ldo + c) = pack_bf16x2(o[nt][2] * inv_hi, o[nt][3] * inv_hi);
+    }
+    if (a.lse && t == 0) {
+        float* lse = a.lse + ((int64_t)b * a.h + hd) * Lq;
+        if (row_lo < Lq) lse[row_lo] = m_lo + logf(l_lo);
+        if (row_hi < Lq) lse[row_hi] = m_hi + logf(l_hi);
+    }
+}
+
+template <int D>
+int launch_fwd(const SdpaArgs& a, cudaStream_t st) {
+    const int Lq = (int)a.Lq;
+    // warps per CTA: cover Lq with as few CTAs as make sense (16 rows per warp), at most 8 warps
+    const int tiles = (Lq + 15) / 16;
+    auto go = [&](auto kern, int nw) -> int {
+        const size_t smem = sizeof(__nv_bfloat16) * (size_t)(nw * 16 + 2 * KCH) * (D + PAD);
+        if (smem > 48 * 1024) OVQA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((unsigned)((Lq + nw * 16 - 1) / (nw * 16)), (unsigned)a.h, (unsigned)a.B);
+        kern<<<grid, nw * 32, smem, st>>>(a);
+        OVQA_LAUNCH_OK();
+        return OVQA_OK;
+    };
+    if (tiles <= 2) return go(sdpa_fwd_mma_kernel<D, 2>, 2);
+    if (tiles <= 4) return go(sdpa_fwd_mma_kernel<D, 4>, 4);
+    if (tiles == 7 || tiles == 13 || tiles == 14) return go(sdpa_fwd_mma_kernel<D, 7>, 7);   // 100 or 200-224 rows: no empty warps
+    if (tiles % 6 == 0 || tiles == 11 || tiles == 12) return go(sdpa_fwd_mma_kernel<D, 6>, 6);      // 182 rows -> 12 tiles
+    return go(sdpa_fwd_mma_kernel<D, 8>, 8);
+}
+
+}  // namespace
+
+bool sdpa_fwd_mma_supported(const SdpaArgs& a) {
+    if (a.geo.boxes || a.att) return false;                     // geometry / materialised probabilities: fp32-math kernel
+    if (a.dk != a.dv || !(a.dk == 32 || a.dk == 64 || a.dk == 96 || a.dk == 128)) return false;
+    // 16-byte cp.async rows and 4-byte output stores
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (!al16(a.q) || !al16(a.k) || !al16(a.v) || (a.ldq % 8) || (a.ldk % 8) || (a.ldv % 8) || (a.ldo % 2)) return false;
+    if (reinterpret_cast<uintptr_t>(a.out) & 3) return false;
+    return true;
+}
+
+int sdpa_fwd_mma_bf16(const SdpaArgs& a, cudaStream_t st) {
+    switch ((int)a.dk) {
+        case 32: return launch_fwd<32>(a, st);
+        case 64: return launch_fwd<64>(a, st);
+        case 96: return launch_fwd<96>(a, st);
+        case 128: return launch_fwd<128>(a, st);
+    }
+    return OVQA_ERR_BAD_SHAPE;
+}
+
+}  // namespace ovqa

@@ -1,3 +1,3 @@
 from .config import NS, StubVocab, attention_cfg, mcan_cfg, xmt_cfg  # noqa: F401
 from .models import (Batch, CoAttentionEncoder, CrossModalTransformer, CrossModalityEncoder, Encoder,  # noqa: F401
-                     GuidedAttentionEncoder, MCAN)
+                     GuidedAttentionEncoder, MCAN, strict_fp32_library_math)

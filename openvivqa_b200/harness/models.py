@@ -300,6 +300,13 @@ class CrossModalTransformer(_ClassifierBase):
         return self._pool_and_classify(vision_features, text_features)
 
 
+def strict_fp32_library_math():
+    """fp32 parity runs: keep the library ops AROUND the hot path (cuDNN LSTM, cuBLAS embedding Linear) out of
+    TF32 so that the 1e-4 budget is spent on our kernels only."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
 class Batch(dict):
     """Attribute-style batch (stand-in for utils/instance.py InstanceList)."""
 

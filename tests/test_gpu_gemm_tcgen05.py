@@ -1,0 +1,74 @@
+"""GPU: the tcgen05/TMEM/TMA GEMM against its CUDA-core twin and an fp64 reference, every operand form, both tile
+widths, fused epilogues, split-K."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from openvivqa_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def _mk(m, n, k, a_op, b_op, dev, seed=0):
+    g = torch.Generator().manual_seed(seed + m + 3 * n + 7 * k)
+    A, B = torch.randn((m, k), generator=g), torch.randn((n, k), generator=g)
+    a = (A if a_op == "N" else A.t().contiguous()).to(dev).bfloat16()
+    b = (B if b_op == "N" else B.t().contiguous()).to(dev).bfloat16()
+    ref = (A.bfloat16().double() @ B.bfloat16().double().t()).float()
+    return a, b, ref
+
+
+@pytest.mark.parametrize("a_op,b_op", [("N", "N"), ("N", "T"), ("T", "T"), ("T", "N")])
+@pytest.mark.parametrize("m,n,k", [(128, 128, 64), (300, 200, 328), (1000, 512, 512), (257, 1024, 2048), (40000, 2048, 512)])
+def test_forms_and_shapes(dev, a_op, b_op, m, n, k):
+    if a_op == "T":
+        m = (m + 7) // 8 * 8       # TMA: the contiguous dimension's pitch must be a multiple of 16 bytes
+    if b_op == "T":
+        n = (n + 7) // 8 * 8
+    a, b, ref = _mk(m, n, k, a_op, b_op, dev)
+    out = ops.gemm(a, b, a_op=a_op, b_op=b_op, out_dtype=torch.float32)
+    err = (out.cpu() - ref).abs().max().item()
+    assert err <= 1e-3 * ref.abs().max().item(), (a_op, b_op, m, n, k, err)
+    twin = ops.gemm_bf16_simt(a, b, a_op=a_op, b_op=b_op)
+    assert (out - twin).abs().max().item() <= 1e-3 * ref.abs().max().item()
+
+
+def test_fused_epilogues(dev):
+    m, n, k = 700, 768, 512
+    a, b, ref = _mk(m, n, k, "N", "N", dev)
+    g = torch.Generator().manual_seed(1)
+    bias, res = torch.randn(n, generator=g), torch.randn((m, n), generator=g)
+    pre = torch.empty((m, n), device=dev, dtype=torch.bfloat16)
+    out = ops.gemm(a, b, bias=bias.to(dev), gelu=True, aux_out=pre, out_dtype=torch.bfloat16)
+    want = F.gelu(ref + bias)
+    assert (out.float().cpu() - want).abs().max() <= 2e-2 * want.abs().max()
+    assert (pre.float().cpu() - (ref + bias)).abs().max() <= 2e-2 * ref.abs().max()
+    c2 = torch.empty((m, n), device=dev, dtype=torch.bfloat16)
+    out = ops.gemm(a, b, bias=bias.to(dev), residual=res.to(dev), out_dtype=torch.float32, c2=c2)
+    want = ref + bias + res
+    assert (out.cpu() - want).abs().max() <= 1e-3 * want.abs().max()
+    assert (c2.float().cpu() - want).abs().max() <= 2e-2 * want.abs().max()
+    # dgelu epilogue and dropout mask are the same functions as on the fp32 path
+    keep = ops.dropout_keep_mask(m * n, 0.1, 9, 5, dev).view(m, n)
+    out = ops.gemm(a, b, out_dtype=torch.float32, dropout_p=0.1, seed=9, offset=5)
+    assert (out.cpu() - ref * keep.cpu() / 0.9).abs().max() <= 1e-3 * ref.abs().max()
+
+
+@pytest.mark.parametrize("split_k", [2, 7, 37])
+def test_split_k_wgrad(dev, split_k):
+    m, n, k = 512, 768, 9000
+    a, b, ref = _mk(m, n, k, "T", "T", dev)
+    out = ops.gemm(a, b, a_op="T", b_op="T", out_dtype=torch.float32, split_k=split_k)
+    assert (out.cpu() - ref).abs().max() <= 2e-3 * ref.abs().max()
+
+
+def test_rejects_unaligned_operands(dev):
+    from openvivqa_b200._lib import OvqaError
+    a = torch.randn((64, 36), device=dev).bfloat16()      # K=36 -> row pitch 72 B, not a multiple of 16
+    with pytest.raises(OvqaError):
+        ops.gemm(a, a)
