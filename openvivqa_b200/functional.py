@@ -20,6 +20,7 @@ import weakref
 from typing import List, Optional, Sequence
 
 import torch
+from torch.optim.optimizer import register_optimizer_step_post_hook
 
 from . import ops
 
@@ -46,16 +47,25 @@ dropout_stream = _DropoutStream()
 
 # ----------------------------------------------------------------------------- operand staging caches
 class _WeightCache:
-    """bf16 (and concatenated) copies of parameters, refreshed when the parameter's version counter moves
-    (i.e. after each optimiser step).  Keeps fc_q/fc_k/fc_v as separately named parameters (state_dict
-    compatibility) while the kernels see one fused [3*h*d, D] operand."""
+    """bf16 (and concatenated) copies of parameters.  Keeps fc_q/fc_k/fc_v as separately named parameters
+    (state_dict compatibility) while the kernels see one fused [3*h*d, D] operand.
+
+    A copy is refreshed when (a) a parameter's version counter moves (``copy_``, ``load_state_dict``, foreach
+    optimisers) or (b) ANY ``torch.optim`` optimiser has stepped since it was made: fused optimisers
+    (``Adam(fused=True)``) update parameters without bumping ``_version``, so a process-wide optimiser-step
+    post-hook advances ``epoch`` instead.  Code that writes parameters behind both mechanisms (raw
+    ``torch._foreach_*`` on ``.data``) must call :func:`invalidate_weight_cache`."""
 
     def __init__(self):
         self._store = {}
+        self.epoch = 0
+
+    def invalidate(self):
+        self.epoch += 1
 
     def get(self, params: Sequence[torch.Tensor], dtype: torch.dtype) -> torch.Tensor:
         key = tuple(id(p) for p in params) + (dtype,)
-        ver = tuple((p._version, p.data_ptr()) for p in params)
+        ver = (self.epoch,) + tuple((p._version, p.data_ptr()) for p in params)
         hit = self._store.get(key)
         if hit is not None and hit[0] == ver and all(r() is p for r, p in zip(hit[2], params)):
             return hit[1]
@@ -70,6 +80,12 @@ class _WeightCache:
 
 
 weights = _WeightCache()
+register_optimizer_step_post_hook(lambda *_a, **_k: weights.invalidate())
+
+
+def invalidate_weight_cache():
+    """Force the staged bf16 / fused operand copies to be rebuilt at their next use."""
+    weights.invalidate()
 
 
 def _operand(x: torch.Tensor, mode: str) -> torch.Tensor:

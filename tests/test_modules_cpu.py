@@ -95,3 +95,21 @@ def test_install_into_the_reference_checkout_and_reference_state_dict_loads():
         ovqa.uninstall()
     assert E.MultiHeadAttention is A.MultiHeadAttention
     assert META_ATTENTION.get("ScaledDotProductAttention").__module__ == "models.modules.attentions"
+
+
+def test_weight_cache_refreshes_after_fused_optimizer_step():
+    """``Adam(fused=True)`` updates parameters WITHOUT bumping ``Tensor._version``; the staged (concatenated) operand
+    copies must still be rebuilt after every optimiser step (process-wide optimiser post-hook)."""
+    from openvivqa_b200 import functional as Fn
+
+    a, b = torch.nn.Parameter(torch.randn(4, 8)), torch.nn.Parameter(torch.randn(4, 8))
+    w0 = Fn.weights.get([a, b], torch.float32)
+    assert Fn.weights.get([a, b], torch.float32) is w0                  # cached
+    opt = torch.optim.Adam([a, b], lr=0.1, fused=True)
+    a.grad, b.grad = torch.ones_like(a), torch.ones_like(b)
+    opt.step()
+    w1 = Fn.weights.get([a, b], torch.float32)
+    assert w1 is not w0 and torch.equal(w1, torch.cat([a.detach(), b.detach()]))
+    with torch.no_grad():
+        a.mul_(2.0)                                                      # version-bump path
+    assert torch.equal(Fn.weights.get([a, b], torch.float32), torch.cat([a.detach(), b.detach()]))
