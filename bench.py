@@ -233,7 +233,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    launches0 = _lib.launch_count
+    launches0 = _lib.launch_count()
     meter.enabled = True
     t_wall0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -245,7 +245,7 @@ def run_ours(args):
     t_wall1 = time.time()
     meter.enabled = False
     ms = e0.elapsed_time(e1)
-    launches = _lib.launch_count - launches0
+    launches = _lib.launch_count() - launches0
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     final_loss = loss.item()
     if world > 1:

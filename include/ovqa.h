@@ -42,6 +42,7 @@ int         ovqa_version(void);
 const char* ovqa_error_string(int code);
 int         ovqa_last_cuda_error(void);           /* cudaError_t of the last failing call (thread local) */
 int         ovqa_device_sm_count(void);
+uint64_t    ovqa_launch_count(void);              /* kernels launched by this library so far (process wide) */
 
 /* ---------------------------------------------------------------------------------------------------
  * Dense contraction with fused epilogue.            C[m,n] = epi( sum_k A[m,k] * B[n,k] )

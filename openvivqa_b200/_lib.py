@@ -24,6 +24,7 @@ _PROTOS = {
     "ovqa_error_string": [_i32],
     "ovqa_last_cuda_error": [],
     "ovqa_device_sm_count": [],
+    "ovqa_launch_count": [],
     "ovqa_gemm": [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _f32, _f32, _vp, _i32,
                   _vp, _vp, _i64, _vp, _i64, _vp, _i64, _f32, _u64, _u64, _i32, _vp],
     "ovqa_gemm_bf16_simt": [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _f32, _vp, _i32, _vp],
@@ -45,14 +46,16 @@ _PROTOS = {
     "ovqa_greedy_step": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp],
     "ovqa_dropout_mask": [_vp, _i64, _f32, _u64, _u64, _vp],
 }
-_RESTYPES = {"ovqa_error_string": C.c_char_p}
+_RESTYPES = {"ovqa_error_string": C.c_char_p, "ovqa_launch_count": C.c_uint64}
 
 _lib = None
 _lock = threading.Lock()
 
-#: launches of our kernels issued through this binding (bench.py reports it as ``gpu_launches``)
-launch_count = 0
-_KERNELS_PER_CALL = {"ovqa_sdpa_bwd": 3, "ovqa_greedy_step": 2}
+
+def launch_count() -> int:
+    """Kernels launched by the library so far, counted inside the library at each launch site
+    (bench.py reports the difference over the timed region as ``gpu_launches``)."""
+    return int(lib().ovqa_launch_count())
 
 
 class OvqaError(RuntimeError):
@@ -93,6 +96,4 @@ def check(code: int, what: str):
 
 
 def call(name: str, *args):
-    global launch_count
     check(getattr(lib(), name)(*args), name)
-    launch_count += _KERNELS_PER_CALL.get(name, 1)

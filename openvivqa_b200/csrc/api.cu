@@ -6,6 +6,7 @@
 namespace ovqa {
 
 thread_local int g_last_cuda_error = 0;
+unsigned long long g_launch_count = 0;
 
 int sm_count() {
     static int n = [] {
@@ -22,6 +23,8 @@ template <typename T> int sdpa_bwd_simt_launch(const SdpaArgs&, const void*, voi
 int box_geometry_bias_launch(const GeoArg&, float*, int64_t, int64_t, int64_t, cudaStream_t);
 int sdpa_fwd_mma_bf16(const SdpaArgs&, cudaStream_t);   // attention_mma.cu
 bool sdpa_fwd_mma_supported(const SdpaArgs&);
+int sdpa_bwd_mma_bf16(const SdpaArgs&, const void*, void*, void*, void*, int64_t, int64_t, int64_t, int64_t, cudaStream_t);
+bool sdpa_bwd_mma_supported(const SdpaArgs&, const void*, const void*, const void*, const void*, int64_t, int64_t, int64_t, int64_t);
 
 }  // namespace ovqa
 
@@ -42,6 +45,7 @@ extern "C" const char* ovqa_error_string(int code) {
 }
 extern "C" int ovqa_last_cuda_error(void) { return g_last_cuda_error; }
 extern "C" int ovqa_device_sm_count(void) { return sm_count(); }
+extern "C" uint64_t ovqa_launch_count(void) { return __atomic_load_n(&g_launch_count, __ATOMIC_RELAXED); }
 
 extern "C" int ovqa_gemm(const void* A, const void* B, void* C, int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb,
                          int64_t ldc, int a_op, int b_op, int ab_dtype, int c_dtype, float alpha, float beta, const float* bias,
@@ -118,12 +122,17 @@ extern "C" int ovqa_sdpa_bwd(const void* q, const void* k, const void* v, const 
                              float* geo_dw, float* geo_db, float scale, int dtype, const float* lse, float* delta, void* stream) {
     int rc = check_sdpa(q, k, v, B, h, Lq, Lk, dk_, dv_, boxes, geo_w, geo_b, d_g, geo_trig, dtype);
     if (rc) return rc;
-    if (!out || !dout || !dq || !dk || !dv || !lse || !delta) return OVQA_ERR_BAD_ARG;
+    if (!out || !dout || !dq || !dk || !dv || !lse) return OVQA_ERR_BAD_ARG;
     if ((geo_dw == nullptr) != (geo_db == nullptr)) return OVQA_ERR_BAD_ARG;
     if (B == 0 || Lq == 0) return OVQA_OK;
     SdpaArgs a{q, k, v, const_cast<void*>(out), B, h, Lq, Lk, dk_, dv_, ldq, ldk, ldv, ldo, {mask, mask_sb, mask_sh, mask_sq},
                {boxes, geo_w, geo_b, geo_freq, (int)d_g, geo_trig}, scale, const_cast<float*>(lse), nullptr};
     cudaStream_t st = (cudaStream_t)stream;
+    // debugging aid only: OVQA_SDPA_BWD=simt keeps the bf16 backward on the CUDA-core kernels
+    static const bool force_simt = [] { const char* e = getenv("OVQA_SDPA_BWD"); return e && e[0] == 's'; }();
+    if (dtype == OVQA_BF16 && !force_simt && sdpa_bwd_mma_supported(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv))
+        return sdpa_bwd_mma_bf16(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv, st);
+    if (!delta) return OVQA_ERR_BAD_ARG;
     if (dtype == OVQA_F32) return sdpa_bwd_simt_launch<float>(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv, delta, geo_dw, geo_db, st);
     return sdpa_bwd_simt_launch<__nv_bfloat16>(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv, delta, geo_dw, geo_db, st);
 }

@@ -52,12 +52,12 @@ __device__ __forceinline__ void load_a_frags(uint32_t (&a)[D / 16][4], const __n
     for (int ks = 0; ks < D / 16; ++ks) ldsm_x4(smem_u32(tile + r * (D + PAD) + ks * 16 + c), a[ks][0], a[ks][1], a[ks][2], a[ks][3]);
 }
 
-// acc[nt] (16 x 8 each, nt over 64 "column" rows of `rows_tile`) += A(16 x D) . rows_tile^T      (S = Q K^T form)
-template <int D>
-__device__ __forceinline__ void mma_a_rowsT(float (&acc)[KCH / 8][4], const uint32_t (&a)[D / 16][4], const __nv_bfloat16* rows_tile, int lane) {
+// acc[nt] (16 x 8 each, nt over CH "column" rows of `rows_tile`) += A(16 x D) . rows_tile^T      (S = Q K^T form)
+template <int D, int CH = KCH>
+__device__ __forceinline__ void mma_a_rowsT(float (&acc)[CH / 8][4], const uint32_t (&a)[D / 16][4], const __nv_bfloat16* rows_tile, int lane) {
     const int rr = (lane % 8) + 8 * (lane / 16), cc = 8 * ((lane / 8) % 2);
 #pragma unroll
-    for (int np = 0; np < KCH / 16; ++np) {
+    for (int np = 0; np < CH / 16; ++np) {
 #pragma unroll
         for (int ks = 0; ks < D / 16; ++ks) {
             uint32_t b0, b1, b2, b3;
@@ -68,12 +68,12 @@ __device__ __forceinline__ void mma_a_rowsT(float (&acc)[KCH / 8][4], const uint
     }
 }
 
-// out[nt] (16 x 8 each, nt over D columns) += P(16 x 64, from accumulator-layout registers) . rows_tile(64 x D)
-template <int D>
-__device__ __forceinline__ void mma_p_rows(float (&out)[D / 8][4], const float (&p)[KCH / 8][4], const __nv_bfloat16* rows_tile, int lane) {
+// out[nt] (16 x 8 each, nt over D columns) += P(16 x CH, from accumulator-layout registers) . rows_tile(CH x D)
+template <int D, int CH = KCH>
+__device__ __forceinline__ void mma_p_rows(float (&out)[D / 8][4], const float (&p)[CH / 8][4], const __nv_bfloat16* rows_tile, int lane) {
     const int rr = (lane % 8) + 8 * ((lane / 8) % 2), cc = 8 * (lane / 16);
 #pragma unroll
-    for (int ks = 0; ks < KCH / 16; ++ks) {
+    for (int ks = 0; ks < CH / 16; ++ks) {
         uint32_t a[4];
         a[0] = pack_bf16x2(p[2 * ks][0], p[2 * ks][1]);
         a[1] = pack_bf16x2(p[2 * ks][2], p[2 * ks][3]);
@@ -185,6 +185,197 @@ __global__ void __launch_bounds__(NWARPS * 32) sdpa_fwd_mma_kernel(SdpaArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ backward
+// One CTA per (batch, head): Q, dO (Lq rows) and K, V (Lk rows) of the head are staged ONCE in shared memory
+// (zero-padded to multiples of BCH rows), delta_i = dO_i . O_i and lse_i go to shared memory too, and then the
+// warps pull independent work items with no further block synchronisation:
+//   query-tile item (16 query rows):  S = Q K^T, P = exp(S*scale + mask - lse), dP = dO V^T, dS = P (dP - delta),
+//                                     dQ = scale * dS K                       (registers -> global)
+//   key-tile item   (16 key rows)  :  S^T = K Q^T, P^T, dP^T = V dO^T, dS^T,  dV = P^T dO,  dK = scale * dS^T Q
+// Computing S^T directly (instead of transposing P) keeps every product in the "A from registers, B rows from
+// smem" form of the forward, so the same two MMA helpers serve all seven contractions.
+constexpr int BCH = 32;    // rows of the streamed operand per inner step
+
+struct SdpaBwdMmaArgs {
+    SdpaArgs f;
+    const void* dout;
+    void *dq, *dk, *dv;
+    int64_t lddo, lddq, lddk, lddv;
+};
+
+template <int D, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32) sdpa_bwd_mma_kernel(SdpaBwdMmaArgs a) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    constexpr int P = D + PAD;
+    const SdpaArgs& f = a.f;
+    const int Lq = (int)f.Lq, Lk = (int)f.Lk;
+    const int Lqp = (Lq + BCH - 1) / BCH * BCH, Lkp = (Lk + BCH - 1) / BCH * BCH;
+    __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);      // [Lqp][P]
+    __nv_bfloat16* sdO = sQ + Lqp * P;                                    // [Lqp][P]
+    __nv_bfloat16* sK = sdO + Lqp * P;                                    // [Lkp][P]
+    __nv_bfloat16* sV = sK + Lkp * P;                                     // [Lkp][P]
+    float* sLse = reinterpret_cast<float*>(sV + Lkp * P);                 // [Lqp]
+    float* sDelta = sLse + Lqp;                                           // [Lqp]
+    const int b = blockIdx.y, hd = blockIdx.x;
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, g = lane / 4, t = lane % 4;
+    const __nv_bfloat16* Q = reinterpret_cast<const __nv_bfloat16*>(f.q) + (int64_t)b * Lq * f.ldq + (int64_t)hd * D;
+    const __nv_bfloat16* K = reinterpret_cast<const __nv_bfloat16*>(f.k) + (int64_t)b * Lk * f.ldk + (int64_t)hd * D;
+    const __nv_bfloat16* V = reinterpret_cast<const __nv_bfloat16*>(f.v) + (int64_t)b * Lk * f.ldv + (int64_t)hd * D;
+    const __nv_bfloat16* O = reinterpret_cast<const __nv_bfloat16*>(f.out) + (int64_t)b * Lq * f.ldo + (int64_t)hd * D;
+    const __nv_bfloat16* dO = reinterpret_cast<const __nv_bfloat16*>(a.dout) + (int64_t)b * Lq * a.lddo + (int64_t)hd * D;
+
+    stage_rows<D>(sQ, Q, f.ldq, Lqp, Lq, threadIdx.x, NWARPS * 32);
+    stage_rows<D>(sdO, dO, a.lddo, Lqp, Lq, threadIdx.x, NWARPS * 32);
+    stage_rows<D>(sK, K, f.ldk, Lkp, Lk, threadIdx.x, NWARPS * 32);
+    stage_rows<D>(sV, V, f.ldv, Lkp, Lk, threadIdx.x, NWARPS * 32);
+    // lse (+inf on padded rows: their probabilities vanish) while the copies fly
+    const float* lse_g = f.lse + ((int64_t)b * f.h + hd) * Lq;
+    for (int i = threadIdx.x; i < Lqp; i += NWARPS * 32) sLse[i] = i < Lq ? __ldg(lse_g + i) : INFINITY;
+    cp_async_wait_all();
+    __syncthreads();
+    // delta_i = sum_d dO[i,d] * O[i,d]  (warp per row; O straight from global, coalesced)
+    for (int i = warp; i < Lqp; i += NWARPS) {
+        float s = 0.f;
+        if (i < Lq)
+            for (int d = 2 * lane; d < D; d += 64) {
+                const float2 o2 = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(O + (int64_t)i * f.ldo + d));
+                const float2 d2 = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(sdO + i * P + d));
+                s = fmaf(o2.x, d2.x, fmaf(o2.y, d2.y, s));
+            }
+        s = warp_sum(s);
+        if (lane == 0) sDelta[i] = s;
+    }
+    __syncthreads();
+
+    const float* mbase = f.mask.ptr ? f.mask.ptr + (int64_t)b * f.mask.sb + (int64_t)hd * f.mask.sh : nullptr;
+    const int nqt = Lqp / 16, nkt = Lkp / 16;
+    // heavier key-tile items first (4 contractions each), then the query tiles
+    for (int item = warp; item < nqt + nkt; item += NWARPS) {
+        if (item >= nkt) {
+            // ------------------------------------------------ query-tile item
+            const int r0 = (item - nkt) * 16;
+            if (r0 >= Lq) continue;
+            uint32_t qa[D / 16][4], da[D / 16][4];
+            load_a_frags<D>(qa, sQ, r0, lane);
+            load_a_frags<D>(da, sdO, r0, lane);
+            const int i_lo = r0 + g, i_hi = i_lo + 8;
+            const float lse_lo = sLse[i_lo], lse_hi = sLse[i_hi], dl_lo = sDelta[i_lo], dl_hi = sDelta[i_hi];
+            const float* mrow_lo = mbase ? mbase + (int64_t)min(i_lo, Lq - 1) * f.mask.sq : nullptr;
+            const float* mrow_hi = mbase ? mbase + (int64_t)min(i_hi, Lq - 1) * f.mask.sq : nullptr;
+            float acc[D / 8][4];
+#pragma unroll
+            for (int i = 0; i < D / 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+            for (int k0 = 0; k0 < Lkp; k0 += BCH) {
+                float s[BCH / 8][4], dp[BCH / 8][4];
+#pragma unroll
+                for (int i = 0; i < BCH / 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f; }
+                mma_a_rowsT<D, BCH>(s, qa, sK + k0 * P, lane);
+                mma_a_rowsT<D, BCH>(dp, da, sV + k0 * P, lane);
+#pragma unroll
+                for (int nt = 0; nt < BCH / 8; ++nt) {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int j = k0 + nt * 8 + 2 * t + e;
+                        float p_lo = 0.f, p_hi = 0.f;
+                        if (j < Lk) {
+                            float v_lo = s[nt][e] * f.scale, v_hi = s[nt][2 + e] * f.scale;
+                            if (mrow_lo) { v_lo += __ldg(mrow_lo + j); v_hi += __ldg(mrow_hi + j); }
+                            p_lo = __expf(v_lo - lse_lo); p_hi = __expf(v_hi - lse_hi);
+                        }
+                        s[nt][e] = p_lo * (dp[nt][e] - dl_lo);
+                        s[nt][2 + e] = p_hi * (dp[nt][2 + e] - dl_hi);
+                    }
+                }
+                mma_p_rows<D, BCH>(acc, s, sK + k0 * P, lane);
+            }
+            __nv_bfloat16* dQ = reinterpret_cast<__nv_bfloat16*>(a.dq) + (int64_t)b * Lq * a.lddq + (int64_t)hd * D;
+#pragma unroll
+            for (int nt = 0; nt < D / 8; ++nt) {
+                const int c = nt * 8 + 2 * t;
+                if (i_lo < Lq) *reinterpret_cast<uint32_t*>(dQ + (int64_t)i_lo * a.lddq + c) = pack_bf16x2(acc[nt][0] * f.scale, acc[nt][1] * f.scale);
+                if (i_hi < Lq) *reinterpret_cast<uint32_t*>(dQ + (int64_t)i_hi * a.lddq + c) = pack_bf16x2(acc[nt][2] * f.scale, acc[nt][3] * f.scale);
+            }
+        } else {
+            // ------------------------------------------------ key-tile item (everything transposed: rows = keys)
+            const int j0 = item * 16;
+            if (j0 >= Lk) continue;
+            uint32_t ka[D / 16][4], va[D / 16][4];
+            load_a_frags<D>(ka, sK, j0, lane);
+            load_a_frags<D>(va, sV, j0, lane);
+            const int j_lo = j0 + g, j_hi = j_lo + 8;
+            const bool ok_lo = j_lo < Lk, ok_hi = j_hi < Lk;
+            const float* mcol_lo = mbase ? mbase + min(j_lo, Lk - 1) : nullptr;   // + i * sq
+            const float* mcol_hi = mbase ? mbase + min(j_hi, Lk - 1) : nullptr;
+            const bool row_bcast = f.mask.sq == 0;
+            const float m0_lo = (mbase && row_bcast) ? __ldg(mcol_lo) : 0.f, m0_hi = (mbase && row_bcast) ? __ldg(mcol_hi) : 0.f;
+            float acck[D / 8][4], accv[D / 8][4];
+#pragma unroll
+            for (int i = 0; i < D / 8; ++i) { acck[i][0] = acck[i][1] = acck[i][2] = acck[i][3] = 0.f; accv[i][0] = accv[i][1] = accv[i][2] = accv[i][3] = 0.f; }
+            for (int i0 = 0; i0 < Lqp; i0 += BCH) {
+                float st[BCH / 8][4], dpt[BCH / 8][4];
+#pragma unroll
+                for (int i = 0; i < BCH / 8; ++i) { st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f; dpt[i][0] = dpt[i][1] = dpt[i][2] = dpt[i][3] = 0.f; }
+                mma_a_rowsT<D, BCH>(st, ka, sQ + i0 * P, lane);
+                mma_a_rowsT<D, BCH>(dpt, va, sdO + i0 * P, lane);
+#pragma unroll
+                for (int nt = 0; nt < BCH / 8; ++nt) {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int i = i0 + nt * 8 + 2 * t + e;           // query index (column of the transposed tile)
+                        const float lse_i = sLse[i], dl_i = sDelta[i];   // +inf on padded queries -> p = 0
+                        float v_lo = st[nt][e] * f.scale, v_hi = st[nt][2 + e] * f.scale;
+                        if (mbase) {
+                            if (row_bcast) { v_lo += m0_lo; v_hi += m0_hi; }
+                            else { const int64_t off = (int64_t)min(i, Lq - 1) * f.mask.sq; v_lo += __ldg(mcol_lo + off); v_hi += __ldg(mcol_hi + off); }
+                        }
+                        const float p_lo = ok_lo ? __expf(v_lo - lse_i) : 0.f, p_hi = ok_hi ? __expf(v_hi - lse_i) : 0.f;
+                        st[nt][e] = p_lo; st[nt][2 + e] = p_hi;
+                        dpt[nt][e] = p_lo * (dpt[nt][e] - dl_i);
+                        dpt[nt][2 + e] = p_hi * (dpt[nt][2 + e] - dl_i);
+                    }
+                }
+                mma_p_rows<D, BCH>(accv, st, sdO + i0 * P, lane);
+                mma_p_rows<D, BCH>(acck, dpt, sQ + i0 * P, lane);
+            }
+            __nv_bfloat16* dK = reinterpret_cast<__nv_bfloat16*>(a.dk) + (int64_t)b * Lk * a.lddk + (int64_t)hd * D;
+            __nv_bfloat16* dV = reinterpret_cast<__nv_bfloat16*>(a.dv) + (int64_t)b * Lk * a.lddv + (int64_t)hd * D;
+#pragma unroll
+            for (int nt = 0; nt < D / 8; ++nt) {
+                const int c = nt * 8 + 2 * t;
+                if (ok_lo) {
+                    *reinterpret_cast<uint32_t*>(dK + (int64_t)j_lo * a.lddk + c) = pack_bf16x2(acck[nt][0] * f.scale, acck[nt][1] * f.scale);
+                    *reinterpret_cast<uint32_t*>(dV + (int64_t)j_lo * a.lddv + c) = pack_bf16x2(accv[nt][0], accv[nt][1]);
+                }
+                if (ok_hi) {
+                    *reinterpret_cast<uint32_t*>(dK + (int64_t)j_hi * a.lddk + c) = pack_bf16x2(acck[nt][2] * f.scale, acck[nt][3] * f.scale);
+                    *reinterpret_cast<uint32_t*>(dV + (int64_t)j_hi * a.lddv + c) = pack_bf16x2(accv[nt][2], accv[nt][3]);
+                }
+            }
+        }
+    }
+}
+
+size_t bwd_smem_bytes(int D, int64_t Lq, int64_t Lk) {
+    const int64_t Lqp = (Lq + BCH - 1) / BCH * BCH, Lkp = (Lk + BCH - 1) / BCH * BCH;
+    return (size_t)(2 * (Lqp + Lkp) * (D + PAD)) * sizeof(__nv_bfloat16) + (size_t)(2 * Lqp) * sizeof(float);
+}
+
+template <int D>
+int launch_bwd(const SdpaBwdMmaArgs& a, cudaStream_t st) {
+    const size_t smem = bwd_smem_bytes(D, a.f.Lq, a.f.Lk);
+    const int items = (int)((a.f.Lq + 15) / 16 + (a.f.Lk + 15) / 16);
+    auto go = [&](auto kern, int nw) -> int {
+        if (smem > 48 * 1024) OVQA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((unsigned)a.f.h, (unsigned)a.f.B);
+        kern<<<grid, nw * 32, smem, st>>>(a);
+        OVQA_LAUNCH_OK();
+        return OVQA_OK;
+    };
+    if (items <= 4) return go(sdpa_bwd_mma_kernel<D, 4>, 4);
+    if (items % 7 == 0 || items == 13) return go(sdpa_bwd_mma_kernel<D, 7>, 7);    // 100 x 100 -> 14 items
+    return go(sdpa_bwd_mma_kernel<D, 8>, 8);
+}
+
 template <int D>
 int launch_fwd(const SdpaArgs& a, cudaStream_t st) {
     const int Lq = (int)a.Lq;
@@ -223,6 +414,28 @@ int sdpa_fwd_mma_bf16(const SdpaArgs& a, cudaStream_t st) {
         case 64: return launch_fwd<64>(a, st);
         case 96: return launch_fwd<96>(a, st);
         case 128: return launch_fwd<128>(a, st);
+    }
+    return OVQA_ERR_BAD_SHAPE;
+}
+
+bool sdpa_bwd_mma_supported(const SdpaArgs& a, const void* dout, const void* dq, const void* dk, const void* dv, int64_t lddo,
+                            int64_t lddq, int64_t lddk, int64_t lddv) {
+    if (a.geo.boxes) return false;                              // geometry: fp32-math kernels (also produce the fc_g gradients)
+    if (a.dk != a.dv || !(a.dk == 32 || a.dk == 64 || a.dk == 96)) return false;
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    auto al4 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3) == 0; };
+    if (!al16(a.q) || !al16(a.k) || !al16(a.v) || !al16(dout) || (a.ldq % 8) || (a.ldk % 8) || (a.ldv % 8) || (lddo % 8)) return false;
+    if (!al4(a.out) || !al4(dq) || !al4(dk) || !al4(dv) || (a.ldo % 2) || (lddq % 2) || (lddk % 2) || (lddv % 2)) return false;
+    return bwd_smem_bytes((int)a.dk, a.Lq, a.Lk) <= 200 * 1024;
+}
+
+int sdpa_bwd_mma_bf16(const SdpaArgs& f, const void* dout, void* dq, void* dk, void* dv, int64_t lddo, int64_t lddq, int64_t lddk,
+                      int64_t lddv, cudaStream_t st) {
+    SdpaBwdMmaArgs a{f, dout, dq, dk, dv, lddo, lddq, lddk, lddv};
+    switch ((int)f.dk) {
+        case 32: return launch_bwd<32>(a, st);
+        case 64: return launch_bwd<64>(a, st);
+        case 96: return launch_bwd<96>(a, st);
     }
     return OVQA_ERR_BAD_SHAPE;
 }

@@ -19,7 +19,13 @@ inline int cuda_fail(cudaError_t e) {
         cudaError_t _e = (expr);                              \
         if (_e != cudaSuccess) return ::ovqa::cuda_fail(_e);  \
     } while (0)
-#define OVQA_LAUNCH_OK() OVQA_CUDA_OK(cudaPeekAtLastError())
+// every kernel launch of the library goes through this check; it also feeds ovqa_launch_count()
+extern unsigned long long g_launch_count;
+#define OVQA_LAUNCH_OK()                                      \
+    do {                                                      \
+        __atomic_fetch_add(&::ovqa::g_launch_count, 1ull, __ATOMIC_RELAXED); \
+        OVQA_CUDA_OK(cudaPeekAtLastError());                  \
+    } while (0)
 
 constexpr int kNumSMsB200 = 148;
 int sm_count();

@@ -1,0 +1,157 @@
+#!/usr/bin/env python
+"""Kernel-level timings on the GPU box (CUDA events, L2 flushed between iterations), each against its roofline:
+
+    python tools/microbench.py [gemm] [sdpa] [ln] [mha] > gpurun_out/microbench.jsonl
+
+* gemm : ovqa_gemm (tcgen05) on the MCAN/M4C training shapes (fwd, dgrad, wgrad forms) next to torch.matmul (cuBLAS)
+* sdpa : attention core forward/backward at the §8a shape classes -> GB/s of algorithmic bytes
+* ln   : LayerNorm forward/backward -> GB/s
+* mha  : BASELINE configs[4] sweep — fused MHA block (eval) B x Lq=30 x Lk, D 512/768 vs roofline
+"""
+import json
+import math
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import openvivqa_b200 as ovqa  # noqa: E402
+from openvivqa_b200 import harness as H, ops  # noqa: E402
+
+dev = torch.device("cuda:0")
+PEAKS = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json"))) if os.path.exists(
+    os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else dict(hbm_gbs=6650.0, bf16_tflops=1590.0)
+_flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+
+def timeit(fn, iters=20, warmup=3, flush=True):
+    for _ in range(warmup):
+        fn()
+    ts = []
+    for _ in range(iters):
+        if flush:
+            _flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2]        # median, microseconds
+
+
+def emit(**kw):
+    print(json.dumps(kw), flush=True)
+
+
+def bench_gemm():
+    B = 256
+    shapes = [  # (tag, m, n, k, a_op, b_op, out dtype)
+        ("qkv_self_vision  NN bf16", B * 100, 1536, 512, "N", "N", torch.bfloat16),
+        ("fc1_vision       NN bf16", B * 100, 2048, 512, "N", "N", torch.bfloat16),
+        ("fc2_vision       NN f32 ", B * 100, 512, 2048, "N", "N", torch.float32),
+        ("fc_o_vision      NN f32 ", B * 100, 512, 512, "N", "N", torch.float32),
+        ("qkv_self_text    NN bf16", B * 30, 1536, 512, "N", "N", torch.bfloat16),
+        ("dgrad fc2 (dpre) NT bf16", B * 100, 2048, 512, "N", "T", torch.bfloat16),
+        ("dgrad fc1 (dx)   NT f32 ", B * 100, 512, 2048, "N", "T", torch.float32),
+        ("dgrad qkv (dx)   NT f32 ", B * 100, 512, 1536, "N", "T", torch.float32),
+        ("wgrad fc1        TT f32 ", 2048, 512, B * 100, "T", "T", torch.float32),
+        ("wgrad fc2        TT f32 ", 512, 2048, B * 100, "T", "T", torch.float32),
+        ("wgrad qkv        TT f32 ", 1536, 512, B * 100, "T", "T", torch.float32),
+        ("wgrad fc_o       TT f32 ", 512, 512, B * 100, "T", "T", torch.float32),
+        ("m4c mmt qkv      NN bf16", 64 * 182, 2304, 768, "N", "N", torch.bfloat16),
+        ("m4c mmt ffn1     NN bf16", 64 * 182, 3072, 768, "N", "N", torch.bfloat16),
+        ("square 8192      NN bf16", 8192, 8192, 8192, "N", "N", torch.bfloat16),
+        ("square 4096      NN bf16", 4096, 4096, 4096, "N", "N", torch.bfloat16),
+    ]
+    from openvivqa_b200 import functional as Fn
+    for tag, m, n, k, ao, bo, odt in shapes:
+        a = torch.randn((m, k) if ao == "N" else (k, m), device=dev).bfloat16()
+        b = torch.randn((n, k) if bo == "N" else (k, n), device=dev).bfloat16()
+        sk = Fn._split_k(k, m, n) if ao == "T" else 1
+        out = torch.zeros((m, n), device=dev, dtype=odt)
+        t_ours = timeit(lambda: ops.gemm(a, b, a_op=ao, b_op=bo, out=out, split_k=sk))
+        am = a if ao == "N" else a.t()
+        bm = b.t() if bo == "N" else b
+        ref_out = torch.empty((m, n), device=dev, dtype=torch.bfloat16)
+        t_ref = timeit(lambda: torch.matmul(am, bm, out=ref_out))
+        fl = 2.0 * m * n * k
+        emit(kind="gemm", tag=tag, m=m, n=n, k=k, split_k=sk, us=t_ours, tflops=fl / t_ours / 1e6, cublas_us=t_ref,
+             cublas_tflops=fl / t_ref / 1e6, frac_of_peak=fl / t_ours / 1e6 / PEAKS["bf16_tflops"])
+
+
+def bench_sdpa():
+    for (B, h, Lq, Lk, d) in [(256, 8, 100, 100, 64), (256, 8, 30, 30, 64), (256, 8, 100, 30, 64), (256, 8, 30, 100, 64),
+                              (1024, 8, 30, 100, 64), (256, 8, 30, 600, 64), (64, 8, 182, 182, 96), (4096, 8, 30, 100, 64)]:
+        fused = Lq == Lk
+        if fused:
+            buf = torch.randn((B, Lq, 3 * h * d), device=dev).bfloat16()
+            q, k, v = buf[..., :h * d], buf[..., h * d:2 * h * d], buf[..., 2 * h * d:]
+            dbuf = torch.empty_like(buf)
+            dq, dk, dv = dbuf[..., :h * d], dbuf[..., h * d:2 * h * d], dbuf[..., 2 * h * d:]
+        else:
+            q = torch.randn((B, Lq, h * d), device=dev).bfloat16()
+            kv = torch.randn((B, Lk, 2 * h * d), device=dev).bfloat16()
+            k, v = kv[..., :h * d], kv[..., h * d:]
+            dq, dkv = torch.empty_like(q), torch.empty_like(kv)
+            dk, dv = dkv[..., :h * d], dkv[..., h * d:]
+        mask = torch.zeros((B, 1, 1, Lk), device=dev)
+        mask[:, :, :, int(Lk * 0.8):] = -10e4
+        out = torch.empty((B, Lq, h * d), device=dev, dtype=torch.bfloat16)
+        dout = torch.randn((B, Lq, h * d), device=dev).bfloat16()
+        lse = ops.sdpa_fwd(q, k, v, h=h, d_k=d, d_v=d, mask=mask, need_lse=True, out=out)[1]
+        t_f = timeit(lambda: ops.sdpa_fwd(q, k, v, h=h, d_k=d, d_v=d, mask=mask, need_lse=True, out=out))
+        t_b = timeit(lambda: ops.sdpa_bwd(q, k, v, out, dout, lse, dq, dk, dv, h=h, d_k=d, d_v=d, mask=mask))
+        e = 2
+        y_f = B * (e * h * d * (2 * Lq + 2 * Lk) + 4 * Lk + 4 * h * Lq)                    # q,k,v in; out, lse out; mask
+        y_b = B * (e * h * d * (3 * Lq + 2 * Lk) + e * h * d * (Lq + 2 * Lk) + 4 * Lk + 4 * h * Lq)   # q,k,v,o,do in; dq,dk,dv out
+        fl = 4.0 * B * h * Lq * Lk * d
+        emit(kind="sdpa", B=B, h=h, Lq=Lq, Lk=Lk, d=d, fwd_us=t_f, fwd_gbs=y_f / t_f / 1e3, fwd_frac_hbm=y_f / t_f / 1e3 / PEAKS["hbm_gbs"],
+             fwd_tflops=fl / t_f / 1e6, bwd_us=t_b, bwd_gbs=y_b / t_b / 1e3, bwd_frac_hbm=y_b / t_b / 1e3 / PEAKS["hbm_gbs"],
+             bwd_tflops=2.5 * fl / t_b / 1e6)
+
+
+def bench_ln():
+    for rows, D in [(25600, 512), (7680, 512), (11648, 768)]:
+        x = torch.randn((rows, D), device=dev)
+        g, b = torch.randn(D, device=dev), torch.randn(D, device=dev)
+        y, y16, _, mean, rstd = ops.layernorm_fwd(x, g, b, want_bf16=True, save_stats=True)
+        t_f = timeit(lambda: ops.layernorm_fwd(x, g, b, want_bf16=True, save_stats=True))
+        dy = torch.randn_like(x)
+        t_b = timeit(lambda: ops.layernorm_bwd(dy, x, mean, rstd, g, want_bf16=True))
+        y_f, y_b = rows * D * (4 + 4 + 2), rows * D * (4 + 4 + 4 + 2)
+        emit(kind="layernorm", rows=rows, D=D, fwd_us=t_f, fwd_gbs=y_f / t_f / 1e3, fwd_frac_hbm=y_f / t_f / 1e3 / PEAKS["hbm_gbs"],
+             bwd_us=t_b, bwd_gbs=y_b / t_b / 1e3, bwd_frac_hbm=y_b / t_b / 1e3 / PEAKS["hbm_gbs"])
+
+
+def bench_mha():
+    """BASELINE configs[4]: fused MHA block, eval, k=v!=q, padding mask with 20% trailing keys masked."""
+    ovqa.set_compute_dtype("bf16")
+    for D, dk in [(512, 64), (768, 96)]:
+        m = ovqa.MultiHeadAttention(H.attention_cfg(D, 8, dk, dk, dropout=0.0, compute_dtype="bf16")).to(dev).eval()
+        for Lk in (100, 250, 400, 600):
+            for B in (16, 64, 256, 1024, 4096):
+                if B * Lk * D * 4 > 6e9:
+                    continue
+                Lq = 30
+                q = torch.randn((B, Lq, D), device=dev)
+                kv = torch.randn((B, Lk, D), device=dev)
+                mask = torch.zeros((B, 1, 1, Lk), device=dev)
+                mask[:, :, :, int(Lk * 0.8):] = -10e4
+                with torch.no_grad():
+                    t = timeit(lambda: m(q, kv, kv, mask), iters=10, warmup=2)
+                F_mha = 4.0 * D * D * (Lq + Lk) + 4.0 * Lq * Lk * D
+                Y_mha = 4 * D * (Lq + Lk + Lq) + 4 * Lk            # fp32 activations in/out as the module sees them
+                t_roof = max(B * F_mha / (PEAKS["bf16_tflops"] * 1e12), B * Y_mha / (PEAKS["hbm_gbs"] * 1e9)) * 1e6
+                emit(kind="mha_block", D=D, B=B, Lq=Lq, Lk=Lk, us=t, samples_per_s=B / t * 1e6, tflops=B * F_mha / t / 1e6,
+                     roofline_us=t_roof, frac_of_roofline=t_roof / t)
+    ovqa.set_compute_dtype("fp32")
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["gemm", "sdpa", "ln", "mha"]
+    emit(kind="meta", gpu=torch.cuda.get_device_name(0), peaks=PEAKS)
+    for w in which:
+        {"gemm": bench_gemm, "sdpa": bench_sdpa, "ln": bench_ln, "mha": bench_mha}[w]()
