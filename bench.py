@@ -187,7 +187,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     import openvivqa_b200 as ovqa
-    from openvivqa_b200 import _lib, harness as H
+    from openvivqa_b200 import _lib, functional as Fn, harness as H
 
     wl = WORKLOAD
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -206,14 +206,19 @@ def run_ours(args):
     net = model
     if world > 1:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True, bucket_cap_mb=25)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.9, 0.98), fused=True)
+    use_graph = not args.no_graph and (world == 1 or os.environ.get("OVQA_DDP_GRAPH") == "1")
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.9, 0.98), fused=True, capturable=use_graph)
     host = synth_batches(3, wl, seed=1 + rank)
     dev_batches = [tuple(t.to(dev) for t in b) for b in host]
+    static = tuple(torch.empty_like(t) for t in dev_batches[0])           # the step's input buffers (graph-stable addresses)
     meter = GemmMeter()
     meter.install()
 
-    def step(feats, toks, ans):
-        with torch.autocast("cuda", dtype=torch.bfloat16):      # library ops around the hot path (LSTM, embedding Linear, head)
+    def step_body():
+        """One training step on the static input buffers: fwd + NLL + bwd + Adam.  Capturable."""
+        Fn.dropout_stream.advance_on_device(dev)                          # fresh dropout masks every replay (device-side offset)
+        feats, toks, ans = static
+        with torch.autocast("cuda", dtype=torch.bfloat16):              # library ops around the hot path (LSTM, embedding Linear, head)
             logp = net(H.Batch(region_features=feats, question_tokens=toks))
         loss = F.nll_loss(logp.float(), ans)
         opt.zero_grad(set_to_none=True)
@@ -221,31 +226,75 @@ def run_ours(args):
         opt.step()
         return loss
 
+    def load(batch, non_blocking=False):
+        for dst, src in zip(static, batch):
+            dst.copy_(src, non_blocking=non_blocking)
+
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- eager warm-up (also what a CUDA graph capture needs), with the GEMM meter on for the roofline numbers
+    n_eager = max(3, args.warmup)
+    for i in range(n_eager):
+        if i == n_eager - 2:
+            barrier()
+            meter.enabled = True
+            e_m0, e_m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e_m0.record()
+        load(dev_batches[i % len(dev_batches)])
+        step_body()
+    e_m1.record()
+    barrier()
+    meter.enabled = False
+    eager_ms_per_step = e_m0.elapsed_time(e_m1) / 2.0
+
+    # ---- capture the whole step into one CUDA graph (launch-bound otherwise: ~1.4k kernels per step)
+    graph, graph_launches, graph_err = None, None, None
+    if use_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                load(dev_batches[0])
+                step_body()                                                # allocator / cuDNN / NCCL warm-up on the capture stream
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            l0 = _lib.launch_count()
+            with torch.cuda.graph(graph):
+                static_loss = step_body()
+            graph_launches = _lib.launch_count() - l0                      # our kernel nodes per replay
+        except Exception as e:  # noqa: BLE001
+            graph, graph_err = None, repr(e)[:200]
+            torch.cuda.synchronize()
+
+    def step(batch, non_blocking=False):
+        load(batch, non_blocking)
+        if graph is not None:
+            graph.replay()
+            return static_loss
+        return step_body()
+
     # ---- device-resident timing (`value`)
     for i in range(args.warmup):
-        step(*dev_batches[i % len(dev_batches)])
+        step(dev_batches[i % len(dev_batches)])
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches0 = _lib.launch_count()
-    meter.enabled = True
     t_wall0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        loss = step(*dev_batches[i % len(dev_batches)])
+        loss = step(dev_batches[i % len(dev_batches)])
     e1.record()
     barrier()
     t_wall1 = time.time()
-    meter.enabled = False
     ms = e0.elapsed_time(e1)
-    launches = _lib.launch_count() - launches0
+    launches = (_lib.launch_count() - launches0) if graph is None else graph_launches * args.steps
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     final_loss = loss.item()
     if world > 1:
@@ -258,16 +307,19 @@ def run_ours(args):
     if args.no_e2e:
         if rank == 0:
             print(json.dumps(dict(metric="VQA samples/sec (MCAN train)", value=value, ms_per_step=ms / args.steps, gpu_launches=launches,
-                                  note="profiling run: no e2e / roofline / cpu legs")), flush=True)
+                                  cuda_graph=graph is not None, note="profiling run: no e2e / roofline / cpu legs")), flush=True)
         if world > 1:
             dist.destroy_process_group()
         return
     copy_stream = torch.cuda.Stream()
     h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
+    staging = [tuple(torch.empty_like(t) for t in static) for _ in range(2)]   # double-buffered device landing zone
 
     def fetch(i):
         with torch.cuda.stream(copy_stream):
-            b = tuple(t.to(dev, non_blocking=True) for t in host[i % len(host)])
+            b = staging[i % 2]
+            for dst, src in zip(b, host[i % len(host)]):
+                dst.copy_(src, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
         return b, ev
@@ -275,18 +327,27 @@ def run_ours(args):
     for i in range(2):
         b, ev = fetch(i)
         torch.cuda.current_stream().wait_event(ev)
-        step(*b)
+        step(b)
     barrier()
     t0 = time.perf_counter()
     nxt = fetch(0)
+    prev_freed = None
     for i in range(args.steps):
         b, ev = nxt
         torch.cuda.current_stream().wait_event(ev)
+        load(b)                                          # landing zone -> the step's static input buffers (compute stream)
+        freed = torch.cuda.Event()
+        freed.record()
+        if graph is not None:
+            graph.replay()
+            loss = static_loss
+        else:
+            loss = step_body()
         if i + 1 < args.steps:
-            nxt = fetch(i + 1)
-        loss = step(*b)
-        for t in b:
-            t.record_stream(torch.cuda.current_stream())
+            if prev_freed is not None:                   # landing zone (i+1)%2 was last read by step i-1's load
+                copy_stream.wait_event(prev_freed)
+            nxt = fetch(i + 1)                           # H2D of the next batch overlaps this step
+        prev_freed = freed
         _ = loss.item()                                  # D2H read of the step's result
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -306,15 +367,18 @@ def run_ours(args):
         roof = None
         if gm:
             peak = peaks["bf16_tflops_sustained"]
-            roof = dict(bound="tensor", kernel="gemm_tcgen05_kernel (all bf16 GEMM launches of the step)", achieved=gm["tflops"], peak=peak,
+            roof = dict(bound="tensor", kernel="gemm_tcgen05_kernel (all bf16 GEMM launches of a step)", achieved=gm["tflops"], peak=peak,
                         unit="TFLOP/s", frac=gm["tflops"] / peak, traffic=traffic, peak_source=peaks["source"] + " (sustained cuBLAS bf16)",
-                        launches=gm["launches"], avg_launch_us=gm["avg_us"], share_of_step=gm["total_ms"] / ms)
+                        launches=gm["launches"], avg_launch_us=gm["avg_us"], share_of_step=(gm["total_ms"] / 2.0) / (ms / args.steps),
+                        how="CUDA events around every GEMM launch during 2 eager (un-graphed) steps of the same workload in this process; "
+                            "the timed region replays those launches from a CUDA graph, where events cannot be interleaved")
         cpu_sps, cpu_per = time_cpu(wl, 32, 2, 1) if args.gpus == 1 and not args.no_cpu_baseline else (None, None)
         line = dict(metric="VQA samples/sec (MCAN train)", value=value, unit="samples/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
                     config=dict(workload="mcan_train: MCAN 6SA+6SGA d512 h8 dff2048, 30 tok, 100x2048 regions, batch 256/GPU, dropout 0.1, "
                                          "NLL+Adam (BASELINE configs[1])", global_batch=wl["B"] * world, parallelism=f"dp{world}",
-                                l2="inputs larger than L2 (210 MB of features per step, 3 rotating batches)", final_loss=final_loss),
+                                l2="inputs larger than L2 (210 MB of features per step, 3 rotating batches)", final_loss=final_loss,
+                                cuda_graph=graph is not None, cuda_graph_error=graph_err, eager_ms_per_step=eager_ms_per_step),
                     e2e=dict(value=e2e, unit="samples/s", h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=4),
                     gpu_launches=launches, roofline=roof, clocks=clocks)
         if cpu_sps is not None:
@@ -333,6 +397,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs only)")
+    ap.add_argument("--no-graph", action="store_true", help="do not capture the step into a CUDA graph (eager launches)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

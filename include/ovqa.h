@@ -55,10 +55,14 @@ uint64_t    ovqa_launch_count(void);              /* kernels launched by this li
  *   ab_dtype: OVQA_BF16 runs on tcgen05/TMEM fed by TMA; OVQA_F32 runs the exact fp32 FFMA path
  *             (the 1e-4 parity path).  c_dtype: storage of C (and of c2).
  *   epilogue, in order:  v = acc*alpha + bias[n];  if aux_out: aux_out = v (pre-activation, c_dtype);
- *             GELU / DGELU(aux_in);  dropout(p, seed, offset) if p>0;  v += residual[m,n] (fp32);
+ *             GELU / DGELU(aux_in);  dropout(p, seed, offset [+ *offset_base]) if p>0;  v += residual[m,n] (fp32);
  *             if beta!=0: v += beta*C_old (fp32 C only);  C = v;  if c2: c2 = bf16(v).
+ *   offset_base: optional DEVICE pointer to a u64 added to `offset` inside the kernel.  A host that replays a captured
+ *             CUDA graph advances that word on the device between replays (ovqa_advance_u64), so every replay draws
+ *             fresh dropout masks although the launch parameters are frozen in the graph.
  *   split_k>1 (wgrad): partial sums are atomically added into fp32 C, which the caller zero-fills (or
- *             pre-loads); bias/epilogue flags are not allowed with split_k>1.
+ *             pre-loads); bias/epilogue flags are not allowed with split_k != 1.  split_k == 0: the library
+ *             picks the split (and tile width) that fills the SMs; C must be zero-filled as for split_k>1.
  * ------------------------------------------------------------------------------------------------- */
 int ovqa_gemm(const void* A, const void* B, void* C,
               int64_t m, int64_t n, int64_t k,
@@ -69,7 +73,7 @@ int ovqa_gemm(const void* A, const void* B, void* C,
               const void* aux_in, void* aux_out, int64_t ld_aux,
               const float* residual, int64_t ld_res,
               void* c2_bf16, int64_t ldc2,
-              float dropout_p, uint64_t seed, uint64_t offset,
+              float dropout_p, uint64_t seed, uint64_t offset, const uint64_t* offset_base,
               int split_k, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
@@ -134,7 +138,7 @@ int ovqa_layernorm_bwd(const float* dy, const float* x, const float* mean, const
                        const float* gamma, const float* dx_add,
                        float* dx, void* dx_bf16, float* dgamma, float* dbeta,
                        int64_t rows, int64_t D,
-                       float dropout_p, uint64_t seed, uint64_t offset, void* stream);
+                       float dropout_p, uint64_t seed, uint64_t offset, const uint64_t* offset_base, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Element-wise helpers of the path.
@@ -147,8 +151,10 @@ int ovqa_colsum(const void* x, float* out, int64_t m, int64_t n, int64_t ldx, in
                 void* stream);
 /* y = dropout(x): y[i] = x[i] * keep(i)/(1-p) with the same counter-based mask as the GEMM/LN epilogues
  * (element index i, seed, offset); x fp32, y fp32 or bf16 (out_dtype).  p == 0 is a plain cast/copy. */
-int ovqa_dropout_apply(const float* x, void* y, int64_t n, float p, uint64_t seed, uint64_t offset, int out_dtype,
-                       void* stream);
+int ovqa_dropout_apply(const float* x, void* y, int64_t n, float p, uint64_t seed, uint64_t offset,
+                       const uint64_t* offset_base, int out_dtype, void* stream);
+/* *word += delta on the device (one thread): advances the dropout offset base between CUDA-graph replays. */
+int ovqa_advance_u64(uint64_t* word, uint64_t delta, void* stream);
 /* y = a + b (fp32, n elements) */
 int ovqa_add_f32(const float* a, const float* b, float* y, int64_t n, void* stream);
 
@@ -198,7 +204,8 @@ int ovqa_gemm_bf16_simt(const void* A, const void* B, void* C, int64_t m, int64_
                         float alpha, const float* bias, int epi_flags, void* stream);
 
 /* Diagnostics for tests: fill `out[0..n)` with the dropout keep-mask (1/0 as float) the epilogues use. */
-int ovqa_dropout_mask(float* out, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
+int ovqa_dropout_mask(float* out, int64_t n, float p, uint64_t seed, uint64_t offset, const uint64_t* offset_base,
+                      void* stream);
 
 #ifdef __cplusplus
 }

@@ -26,7 +26,7 @@ _PROTOS = {
     "ovqa_device_sm_count": [],
     "ovqa_launch_count": [],
     "ovqa_gemm": [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _f32, _f32, _vp, _i32,
-                  _vp, _vp, _i64, _vp, _i64, _vp, _i64, _f32, _u64, _u64, _i32, _vp],
+                  _vp, _vp, _i64, _vp, _i64, _vp, _i64, _f32, _u64, _u64, _vp, _i32, _vp],
     "ovqa_gemm_bf16_simt": [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _f32, _vp, _i32, _vp],
     "ovqa_sdpa_fwd": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
                       _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _i32, _vp, _vp, _vp],
@@ -34,17 +34,18 @@ _PROTOS = {
                       _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
                       _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _f32, _i32, _vp, _vp, _vp],
     "ovqa_layernorm_fwd": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, _vp],
-    "ovqa_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, _u64, _u64, _vp],
+    "ovqa_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, _u64, _u64, _vp, _vp],
     "ovqa_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
     "ovqa_cast_bf16_to_f32": [_vp, _vp, _i64, _vp],
     "ovqa_colsum": [_vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp],
     "ovqa_add_f32": [_vp, _vp, _vp, _i64, _vp],
-    "ovqa_dropout_apply": [_vp, _vp, _i64, _f32, _u64, _u64, _i32, _vp],
+    "ovqa_dropout_apply": [_vp, _vp, _i64, _f32, _u64, _u64, _vp, _i32, _vp],
+    "ovqa_advance_u64": [_vp, _u64, _vp],
     "ovqa_box_geometry_bias": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp],
     "ovqa_ptr_scores": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _i32, _i32, _vp],
     "ovqa_prev_pred_embed": [_vp] * 12 + [_i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _vp],
     "ovqa_greedy_step": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp],
-    "ovqa_dropout_mask": [_vp, _i64, _f32, _u64, _u64, _vp],
+    "ovqa_dropout_mask": [_vp, _i64, _f32, _u64, _u64, _vp, _vp],
 }
 _RESTYPES = {"ovqa_error_string": C.c_char_p, "ovqa_launch_count": C.c_uint64}
 

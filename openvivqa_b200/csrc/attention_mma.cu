@@ -93,20 +93,37 @@ __device__ __forceinline__ float quad_max(float v) { v = fmaxf(v, __shfl_xor_syn
 __device__ __forceinline__ float quad_sum(float v) { v += __shfl_xor_sync(0xffffffffu, v, 1); return v + __shfl_xor_sync(0xffffffffu, v, 2); }
 
 // ------------------------------------------------------------------------------------------------ forward
-template <int D, int NWARPS>
+// FULL = the head's whole K and V (Lk rows padded to 64) fit next to the Q tile: everything is requested at once with
+// cp.async, ONE wait + barrier, and the chunk loop then runs with no further synchronisation (one DRAM round trip
+// per CTA instead of one per chunk — these CTAs are latency-bound, not bandwidth-bound).  Otherwise K/V stream
+// through one 64-row chunk buffer.  When the mask is a per-key row (stride over queries == 0: padding masks) or
+// absent it is staged as one float row with -inf beyond Lk, so the key-range predicate disappears as well.
+template <int D, int NWARPS, bool FULL>
 __global__ void __launch_bounds__(NWARPS * 32) sdpa_fwd_mma_kernel(SdpaArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);          // [NWARPS*16][D+PAD]
-    __nv_bfloat16* sK = sQ + NWARPS * 16 * (D + PAD);                       // [KCH][D+PAD]
-    __nv_bfloat16* sV = sK + KCH * (D + PAD);                               // [KCH][D+PAD]
+    constexpr int P = D + PAD;
+    const int Lq = (int)a.Lq, Lk = (int)a.Lk;
+    const int Lkp = (Lk + KCH - 1) / KCH * KCH;
+    const int kv_rows = FULL ? Lkp : KCH;
+    __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);          // [NWARPS*16][P]
+    __nv_bfloat16* sK = sQ + NWARPS * 16 * P;                               // [kv_rows][P]
+    __nv_bfloat16* sV = sK + kv_rows * P;                                   // [kv_rows][P]
+    float* sMask = reinterpret_cast<float*>(sV + kv_rows * P);              // [Lkp]
     const int b = blockIdx.z, hd = blockIdx.y, q0 = blockIdx.x * NWARPS * 16;
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, g = lane / 4, t = lane % 4;
-    const int Lq = (int)a.Lq, Lk = (int)a.Lk;
     const __nv_bfloat16* Q = reinterpret_cast<const __nv_bfloat16*>(a.q) + ((int64_t)b * Lq + q0) * a.ldq + (int64_t)hd * D;
     const __nv_bfloat16* K = reinterpret_cast<const __nv_bfloat16*>(a.k) + (int64_t)b * Lk * a.ldk + (int64_t)hd * D;
     const __nv_bfloat16* V = reinterpret_cast<const __nv_bfloat16*>(a.v) + (int64_t)b * Lk * a.ldv + (int64_t)hd * D;
 
     stage_rows<D>(sQ, Q, a.ldq, NWARPS * 16, min(NWARPS * 16, Lq - q0), threadIdx.x, NWARPS * 32);
+    if constexpr (FULL) {
+        stage_rows<D>(sK, K, a.ldk, Lkp, Lk, threadIdx.x, NWARPS * 32);
+        stage_rows<D>(sV, V, a.ldv, Lkp, Lk, threadIdx.x, NWARPS * 32);
+    }
+    const float* mbase = a.mask.ptr ? a.mask.ptr + (int64_t)b * a.mask.sb + (int64_t)hd * a.mask.sh : nullptr;
+    const bool row_mask = mbase == nullptr || a.mask.sq == 0;               // one mask row serves every query
+    if (row_mask)
+        for (int j = threadIdx.x; j < Lkp; j += NWARPS * 32) sMask[j] = j < Lk ? (mbase ? __ldg(mbase + j) : 0.f) : -INFINITY;
     cp_async_wait_all();
     __syncthreads();
     uint32_t qa[D / 16][4];
@@ -115,10 +132,9 @@ __global__ void __launch_bounds__(NWARPS * 32) sdpa_fwd_mma_kernel(SdpaArgs a) {
     const int row_lo = q0 + warp * 16 + g, row_hi = row_lo + 8;      // the two query rows this thread holds
     const float* mrow_lo = nullptr;
     const float* mrow_hi = nullptr;
-    if (a.mask.ptr) {
-        const float* mb = a.mask.ptr + (int64_t)b * a.mask.sb + (int64_t)hd * a.mask.sh;
-        mrow_lo = mb + (int64_t)min(row_lo, Lq - 1) * a.mask.sq;
-        mrow_hi = mb + (int64_t)min(row_hi, Lq - 1) * a.mask.sq;
+    if (!row_mask) {
+        mrow_lo = mbase + (int64_t)min(row_lo, Lq - 1) * a.mask.sq;
+        mrow_hi = mbase + (int64_t)min(row_hi, Lq - 1) * a.mask.sq;
     }
     float o[D / 8][4];
 #pragma unroll
@@ -126,27 +142,43 @@ __global__ void __launch_bounds__(NWARPS * 32) sdpa_fwd_mma_kernel(SdpaArgs a) {
     float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
 
     for (int k0 = 0; k0 < Lk; k0 += KCH) {
-        const int nk = min(KCH, Lk - k0);
-        __syncthreads();                                   // previous chunk fully consumed
-        stage_rows<D>(sK, K + (int64_t)k0 * a.ldk, a.ldk, KCH, nk, threadIdx.x, NWARPS * 32);
-        stage_rows<D>(sV, V + (int64_t)k0 * a.ldv, a.ldv, KCH, nk, threadIdx.x, NWARPS * 32);
-        cp_async_wait_all();
-        __syncthreads();
+        const __nv_bfloat16* kc = sK;
+        const __nv_bfloat16* vc = sV;
+        if constexpr (FULL) {
+            kc = sK + k0 * P;
+            vc = sV + k0 * P;
+        } else {
+            const int nk = min(KCH, Lk - k0);
+            __syncthreads();                               // previous chunk fully consumed
+            stage_rows<D>(sK, K + (int64_t)k0 * a.ldk, a.ldk, KCH, nk, threadIdx.x, NWARPS * 32);
+            stage_rows<D>(sV, V + (int64_t)k0 * a.ldv, a.ldv, KCH, nk, threadIdx.x, NWARPS * 32);
+            cp_async_wait_all();
+            __syncthreads();
+        }
         float s[KCH / 8][4];
 #pragma unroll
         for (int i = 0; i < KCH / 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
-        mma_a_rowsT<D>(s, qa, sK, lane);
+        mma_a_rowsT<D>(s, qa, kc, lane);
         // scale, additive mask (fp32, before the max), key-range predicate
         float cmax_lo = -INFINITY, cmax_hi = -INFINITY;
 #pragma unroll
         for (int nt = 0; nt < KCH / 8; ++nt) {
+            const int j0 = k0 + nt * 8 + 2 * t;
+            float mk_lo[2], mk_hi[2];
+            if (row_mask) {
+                const float2 m2 = *reinterpret_cast<const float2*>(sMask + j0);
+                mk_lo[0] = mk_hi[0] = m2.x; mk_lo[1] = mk_hi[1] = m2.y;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const bool in = j0 + e < Lk;
+                    mk_lo[e] = in ? __ldg(mrow_lo + j0 + e) : -INFINITY;
+                    mk_hi[e] = in ? __ldg(mrow_hi + j0 + e) : -INFINITY;
+                }
+            }
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int j = k0 + nt * 8 + 2 * t + e;
-                float v_lo = s[nt][e] * a.scale, v_hi = s[nt][2 + e] * a.scale;
-                if (j < Lk) {
-                    if (mrow_lo) { v_lo += __ldg(mrow_lo + j); v_hi += __ldg(mrow_hi + j); }
-                } else { v_lo = -INFINITY; v_hi = -INFINITY; }
+                const float v_lo = fmaf(s[nt][e], a.scale, mk_lo[e]), v_hi = fmaf(s[nt][2 + e], a.scale, mk_hi[e]);
                 s[nt][e] = v_lo; s[nt][2 + e] = v_hi;
                 cmax_lo = fmaxf(cmax_lo, v_lo); cmax_hi = fmaxf(cmax_hi, v_hi);
             }
@@ -168,7 +200,7 @@ __global__ void __launch_bounds__(NWARPS * 32) sdpa_fwd_mma_kernel(SdpaArgs a) {
         l_hi = l_hi * corr_hi + quad_sum(sum_hi);
 #pragma unroll
         for (int i = 0; i < D / 8; ++i) { o[i][0] *= corr_lo; o[i][1] *= corr_lo; o[i][2] *= corr_hi; o[i][3] *= corr_hi; }
-        mma_p_rows<D>(o, s, sV, lane);
+        mma_p_rows<D>(o, s, vc, lane);
     }
     const float inv_lo = 1.f / l_lo, inv_hi = 1.f / l_hi;
     __nv_bfloat16* O = reinterpret_cast<__nv_bfloat16*>(a.out) + (int64_t)b * Lq * a.ldo + (int64_t)hd * D;
@@ -203,8 +235,11 @@ struct SdpaBwdMmaArgs {
     int64_t lddo, lddq, lddk, lddv;
 };
 
-template <int D, int NWARPS>
-__global__ void __launch_bounds__(NWARPS * 32) sdpa_bwd_mma_kernel(SdpaBwdMmaArgs a) {
+// Register budget: the register file is per SM sub-partition (16K), so 12 resident warps (3 per sub-partition) may use
+// up to 170 registers each: 6-warp CTAs x 2 or 4-warp CTAs x 3 (MINB) for d <= 64.  A-operand fragments are re-read
+// from shared memory inside the chunk loops (ldmatrix is cheap) instead of living in registers across them.
+template <int D, int NWARPS, int MINB>
+__global__ void __launch_bounds__(NWARPS * 32, MINB) sdpa_bwd_mma_kernel(SdpaBwdMmaArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     constexpr int P = D + PAD;
     const SdpaArgs& f = a.f;
@@ -214,8 +249,10 @@ __global__ void __launch_bounds__(NWARPS * 32) sdpa_bwd_mma_kernel(SdpaBwdMmaArg
     __nv_bfloat16* sdO = sQ + Lqp * P;                                    // [Lqp][P]
     __nv_bfloat16* sK = sdO + Lqp * P;                                    // [Lkp][P]
     __nv_bfloat16* sV = sK + Lkp * P;                                     // [Lkp][P]
-    float* sLse = reinterpret_cast<float*>(sV + Lkp * P);                 // [Lqp]
+    __nv_bfloat16* sO = sV + Lkp * P;                                     // [Lqp][P]  (only until delta is known)
+    float* sLse = reinterpret_cast<float*>(sO + Lqp * P);                 // [Lqp]
     float* sDelta = sLse + Lqp;                                           // [Lqp]
+    float* sMask = sDelta + Lqp;                                          // [Lkp]    per-key mask row (when broadcast over queries)
     const int b = blockIdx.y, hd = blockIdx.x;
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, g = lane / 4, t = lane % 4;
     const __nv_bfloat16* Q = reinterpret_cast<const __nv_bfloat16*>(f.q) + (int64_t)b * Lq * f.ldq + (int64_t)hd * D;
@@ -228,26 +265,36 @@ __global__ void __launch_bounds__(NWARPS * 32) sdpa_bwd_mma_kernel(SdpaBwdMmaArg
     stage_rows<D>(sdO, dO, a.lddo, Lqp, Lq, threadIdx.x, NWARPS * 32);
     stage_rows<D>(sK, K, f.ldk, Lkp, Lk, threadIdx.x, NWARPS * 32);
     stage_rows<D>(sV, V, f.ldv, Lkp, Lk, threadIdx.x, NWARPS * 32);
-    // lse (+inf on padded rows: their probabilities vanish) while the copies fly
+    stage_rows<D>(sO, O, f.ldo, Lqp, Lq, threadIdx.x, NWARPS * 32);
+    // lse (+inf on padded rows: their probabilities vanish) and the mask row while the copies fly
     const float* lse_g = f.lse + ((int64_t)b * f.h + hd) * Lq;
     for (int i = threadIdx.x; i < Lqp; i += NWARPS * 32) sLse[i] = i < Lq ? __ldg(lse_g + i) : INFINITY;
+    const float* mbase = f.mask.ptr ? f.mask.ptr + (int64_t)b * f.mask.sb + (int64_t)hd * f.mask.sh : nullptr;
+    const bool row_bcast = mbase == nullptr || f.mask.sq == 0;
+    if (row_bcast)
+        for (int j = threadIdx.x; j < Lkp; j += NWARPS * 32) sMask[j] = (mbase && j < Lk) ? __ldg(mbase + j) : 0.f;
     cp_async_wait_all();
     __syncthreads();
-    // delta_i = sum_d dO[i,d] * O[i,d]  (warp per row; O straight from global, coalesced)
-    for (int i = warp; i < Lqp; i += NWARPS) {
+    // delta_i = sum_d dO[i,d] * O[i,d]: 8 lanes per row, each one 16-byte piece at a time, all operands already in smem
+    for (int i0 = 0; i0 < Lqp; i0 += NWARPS * 4) {                       // block-uniform trip count (full-warp shuffles below)
+        const int i = i0 + threadIdx.x / 8;
         float s = 0.f;
-        if (i < Lq)
-            for (int d = 2 * lane; d < D; d += 64) {
-                const float2 o2 = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(O + (int64_t)i * f.ldo + d));
-                const float2 d2 = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(sdO + i * P + d));
+        for (int c = threadIdx.x % 8; i < Lqp && c < D / 8; c += 8) {
+            const uint4 o4 = *reinterpret_cast<const uint4*>(sO + i * P + c * 8), d4 = *reinterpret_cast<const uint4*>(sdO + i * P + c * 8);
+            const uint32_t ow[4] = {o4.x, o4.y, o4.z, o4.w}, dw[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 o2 = unpack_bf16x2(ow[e]), d2 = unpack_bf16x2(dw[e]);
                 s = fmaf(o2.x, d2.x, fmaf(o2.y, d2.y, s));
             }
-        s = warp_sum(s);
-        if (lane == 0) sDelta[i] = s;
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (threadIdx.x % 8 == 0 && i < Lqp) sDelta[i] = s;
     }
     __syncthreads();
 
-    const float* mbase = f.mask.ptr ? f.mask.ptr + (int64_t)b * f.mask.sb + (int64_t)hd * f.mask.sh : nullptr;
     const int nqt = Lqp / 16, nkt = Lkp / 16;
     // heavier key-tile items first (4 contractions each), then the query tiles
     for (int item = warp; item < nqt + nkt; item += NWARPS) {
@@ -255,13 +302,10 @@ __global__ void __launch_bounds__(NWARPS * 32) sdpa_bwd_mma_kernel(SdpaBwdMmaArg
             // ------------------------------------------------ query-tile item
             const int r0 = (item - nkt) * 16;
             if (r0 >= Lq) continue;
-            uint32_t qa[D / 16][4], da[D / 16][4];
-            load_a_frags<D>(qa, sQ, r0, lane);
-            load_a_frags<D>(da, sdO, r0, lane);
             const int i_lo = r0 + g, i_hi = i_lo + 8;
             const float lse_lo = sLse[i_lo], lse_hi = sLse[i_hi], dl_lo = sDelta[i_lo], dl_hi = sDelta[i_hi];
-            const float* mrow_lo = mbase ? mbase + (int64_t)min(i_lo, Lq - 1) * f.mask.sq : nullptr;
-            const float* mrow_hi = mbase ? mbase + (int64_t)min(i_hi, Lq - 1) * f.mask.sq : nullptr;
+            const float* mrow_lo = !row_bcast ? mbase + (int64_t)min(i_lo, Lq - 1) * f.mask.sq : nullptr;
+            const float* mrow_hi = !row_bcast ? mbase + (int64_t)min(i_hi, Lq - 1) * f.mask.sq : nullptr;
             float acc[D / 8][4];
 #pragma unroll
             for (int i = 0; i < D / 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
@@ -269,8 +313,13 @@ __global__ void __launch_bounds__(NWARPS * 32) sdpa_bwd_mma_kernel(SdpaBwdMmaArg
                 float s[BCH / 8][4], dp[BCH / 8][4];
 #pragma unroll
                 for (int i = 0; i < BCH / 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f; }
-                mma_a_rowsT<D, BCH>(s, qa, sK + k0 * P, lane);
-                mma_a_rowsT<D, BCH>(dp, da, sV + k0 * P, lane);
+                {
+                    uint32_t fa[D / 16][4];
+                    load_a_frags<D>(fa, sQ, r0, lane);
+                    mma_a_rowsT<D, BCH>(s, fa, sK + k0 * P, lane);
+                    load_a_frags<D>(fa, sdO, r0, lane);
+                    mma_a_rowsT<D, BCH>(dp, fa, sV + k0 * P, lane);
+                }
 #pragma unroll
                 for (int nt = 0; nt < BCH / 8; ++nt) {
 #pragma unroll
@@ -280,6 +329,7 @@ __global__ void __launch_bounds__(NWARPS * 32) sdpa_bwd_mma_kernel(SdpaBwdMmaArg
                         if (j < Lk) {
                             float v_lo = s[nt][e] * f.scale, v_hi = s[nt][2 + e] * f.scale;
                             if (mrow_lo) { v_lo += __ldg(mrow_lo + j); v_hi += __ldg(mrow_hi + j); }
+                            else { const float mk = sMask[j]; v_lo += mk; v_hi += mk; }
                             p_lo = __expf(v_lo - lse_lo); p_hi = __expf(v_hi - lse_hi);
                         }
                         s[nt][e] = p_lo * (dp[nt][e] - dl_lo);
@@ -299,15 +349,11 @@ __global__ void __launch_bounds__(NWARPS * 32) sdpa_bwd_mma_kernel(SdpaBwdMmaArg
             // ------------------------------------------------ key-tile item (everything transposed: rows = keys)
             const int j0 = item * 16;
             if (j0 >= Lk) continue;
-            uint32_t ka[D / 16][4], va[D / 16][4];
-            load_a_frags<D>(ka, sK, j0, lane);
-            load_a_frags<D>(va, sV, j0, lane);
             const int j_lo = j0 + g, j_hi = j_lo + 8;
             const bool ok_lo = j_lo < Lk, ok_hi = j_hi < Lk;
             const float* mcol_lo = mbase ? mbase + min(j_lo, Lk - 1) : nullptr;   // + i * sq
             const float* mcol_hi = mbase ? mbase + min(j_hi, Lk - 1) : nullptr;
-            const bool row_bcast = f.mask.sq == 0;
-            const float m0_lo = (mbase && row_bcast) ? __ldg(mcol_lo) : 0.f, m0_hi = (mbase && row_bcast) ? __ldg(mcol_hi) : 0.f;
+            const float m0_lo = row_bcast ? sMask[j_lo] : 0.f, m0_hi = row_bcast ? sMask[j_hi] : 0.f;
             float acck[D / 8][4], accv[D / 8][4];
 #pragma unroll
             for (int i = 0; i < D / 8; ++i) { acck[i][0] = acck[i][1] = acck[i][2] = acck[i][3] = 0.f; accv[i][0] = accv[i][1] = accv[i][2] = accv[i][3] = 0.f; }
@@ -315,8 +361,13 @@ __global__ void __launch_bounds__(NWARPS * 32) sdpa_bwd_mma_kernel(SdpaBwdMmaArg
                 float st[BCH / 8][4], dpt[BCH / 8][4];
 #pragma unroll
                 for (int i = 0; i < BCH / 8; ++i) { st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f; dpt[i][0] = dpt[i][1] = dpt[i][2] = dpt[i][3] = 0.f; }
-                mma_a_rowsT<D, BCH>(st, ka, sQ + i0 * P, lane);
-                mma_a_rowsT<D, BCH>(dpt, va, sdO + i0 * P, lane);
+                {
+                    uint32_t fa[D / 16][4];
+                    load_a_frags<D>(fa, sK, j0, lane);
+                    mma_a_rowsT<D, BCH>(st, fa, sQ + i0 * P, lane);
+                    load_a_frags<D>(fa, sV, j0, lane);
+                    mma_a_rowsT<D, BCH>(dpt, fa, sdO + i0 * P, lane);
+                }
 #pragma unroll
                 for (int nt = 0; nt < BCH / 8; ++nt) {
 #pragma unroll
@@ -324,9 +375,9 @@ __global__ void __launch_bounds__(NWARPS * 32) sdpa_bwd_mma_kernel(SdpaBwdMmaArg
                         const int i = i0 + nt * 8 + 2 * t + e;           // query index (column of the transposed tile)
                         const float lse_i = sLse[i], dl_i = sDelta[i];   // +inf on padded queries -> p = 0
                         float v_lo = st[nt][e] * f.scale, v_hi = st[nt][2 + e] * f.scale;
-                        if (mbase) {
-                            if (row_bcast) { v_lo += m0_lo; v_hi += m0_hi; }
-                            else { const int64_t off = (int64_t)min(i, Lq - 1) * f.mask.sq; v_lo += __ldg(mcol_lo + off); v_hi += __ldg(mcol_hi + off); }
+                        if (row_bcast) { v_lo += m0_lo; v_hi += m0_hi; }
+                        else {
+                            { const int64_t off = (int64_t)min(i, Lq - 1) * f.mask.sq; v_lo += __ldg(mcol_lo + off); v_hi += __ldg(mcol_hi + off); }
                         }
                         const float p_lo = ok_lo ? __expf(v_lo - lse_i) : 0.f, p_hi = ok_hi ? __expf(v_hi - lse_i) : 0.f;
                         st[nt][e] = p_lo; st[nt][2 + e] = p_hi;
@@ -357,7 +408,7 @@ __global__ void __launch_bounds__(NWARPS * 32) sdpa_bwd_mma_kernel(SdpaBwdMmaArg
 
 size_t bwd_smem_bytes(int D, int64_t Lq, int64_t Lk) {
     const int64_t Lqp = (Lq + BCH - 1) / BCH * BCH, Lkp = (Lk + BCH - 1) / BCH * BCH;
-    return (size_t)(2 * (Lqp + Lkp) * (D + PAD)) * sizeof(__nv_bfloat16) + (size_t)(2 * Lqp) * sizeof(float);
+    return (size_t)((3 * Lqp + 2 * Lkp) * (D + PAD)) * sizeof(__nv_bfloat16) + (size_t)(2 * Lqp + Lkp) * sizeof(float);
 }
 
 template <int D>
@@ -371,29 +422,43 @@ int launch_bwd(const SdpaBwdMmaArgs& a, cudaStream_t st) {
         OVQA_LAUNCH_OK();
         return OVQA_OK;
     };
-    if (items <= 4) return go(sdpa_bwd_mma_kernel<D, 4>, 4);
-    if (items % 7 == 0 || items == 13) return go(sdpa_bwd_mma_kernel<D, 7>, 7);    // 100 x 100 -> 14 items
-    return go(sdpa_bwd_mma_kernel<D, 8>, 8);
+    if constexpr (D <= 64) {
+        if (items <= 4) return go(sdpa_bwd_mma_kernel<D, 4, 3>, 4);
+        return go(sdpa_bwd_mma_kernel<D, 6, 2>, 6);
+    } else {
+        if (items <= 4) return go(sdpa_bwd_mma_kernel<D, 4, 1>, 4);
+        return go(sdpa_bwd_mma_kernel<D, 8, 1>, 8);
+    }
 }
 
 template <int D>
 int launch_fwd(const SdpaArgs& a, cudaStream_t st) {
     const int Lq = (int)a.Lq;
+    const int64_t Lkp = (a.Lk + KCH - 1) / KCH * KCH;
     // warps per CTA: cover Lq with as few CTAs as make sense (16 rows per warp), at most 8 warps
     const int tiles = (Lq + 15) / 16;
-    auto go = [&](auto kern, int nw) -> int {
-        const size_t smem = sizeof(__nv_bfloat16) * (size_t)(nw * 16 + 2 * KCH) * (D + PAD);
-        if (smem > 48 * 1024) OVQA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto go = [&](auto kern_full, auto kern_chunk, int nw) -> int {
+        const size_t smem_full = sizeof(__nv_bfloat16) * (size_t)(nw * 16 + 2 * Lkp) * (D + PAD) + sizeof(float) * Lkp;
+        const bool full = smem_full <= 100 * 1024;                      // keeps >= 2 CTAs per SM resident
+        const size_t smem = full ? smem_full : sizeof(__nv_bfloat16) * (size_t)(nw * 16 + 2 * KCH) * (D + PAD) + sizeof(float) * Lkp;
         dim3 grid((unsigned)((Lq + nw * 16 - 1) / (nw * 16)), (unsigned)a.h, (unsigned)a.B);
-        kern<<<grid, nw * 32, smem, st>>>(a);
+        if (full) {
+            if (smem > 48 * 1024) OVQA_CUDA_OK(cudaFuncSetAttribute(kern_full, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern_full<<<grid, nw * 32, smem, st>>>(a);
+        } else {
+            if (smem > 48 * 1024) OVQA_CUDA_OK(cudaFuncSetAttribute(kern_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern_chunk<<<grid, nw * 32, smem, st>>>(a);
+        }
         OVQA_LAUNCH_OK();
         return OVQA_OK;
     };
-    if (tiles <= 2) return go(sdpa_fwd_mma_kernel<D, 2>, 2);
-    if (tiles <= 4) return go(sdpa_fwd_mma_kernel<D, 4>, 4);
-    if (tiles == 7 || tiles == 13 || tiles == 14) return go(sdpa_fwd_mma_kernel<D, 7>, 7);   // 100 or 200-224 rows: no empty warps
-    if (tiles % 6 == 0 || tiles == 11 || tiles == 12) return go(sdpa_fwd_mma_kernel<D, 6>, 6);      // 182 rows -> 12 tiles
-    return go(sdpa_fwd_mma_kernel<D, 8>, 8);
+#define OVQA_FWD(NW) go(sdpa_fwd_mma_kernel<D, NW, true>, sdpa_fwd_mma_kernel<D, NW, false>, NW)
+    if (tiles <= 2) return OVQA_FWD(2);
+    if (tiles <= 4) return OVQA_FWD(4);
+    if (tiles == 7 || tiles == 13 || tiles == 14) return OVQA_FWD(7);   // 100 or 200-224 rows: no empty warps
+    if (tiles % 6 == 0 || tiles == 11 || tiles == 12) return OVQA_FWD(6);      // 182 rows -> 12 tiles
+    return OVQA_FWD(8);
+#undef OVQA_FWD
 }
 
 }  // namespace

@@ -67,9 +67,29 @@ __device__ __forceinline__ float dgelu_erf(float x) {
     return cdf + x * pdf;
 }
 
+// Standard normal CDF Phi(x) = 0.5 (1 + erf(x / sqrt 2)) for the tensor-core GEMM epilogues, where GELU runs in the
+// shadow of the MMA pipe and instruction count matters: Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7 on erf, i.e.
+// fp32-rounding level), evaluated on the erfc side so the negative tail has no 1+erf cancellation.
+__device__ __forceinline__ float normal_cdf_fast(float x) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float h = 0.5f * poly * t * __expf(-z * z);     // 0.5 erfc(|x|/sqrt 2)
+    return x < 0.0f ? h : 1.0f - h;
+}
+__device__ __forceinline__ float gelu_fast(float x) { return x * normal_cdf_fast(x); }
+__device__ __forceinline__ float dgelu_fast(float x) {
+    return fmaf(x * 0.39894228040143267794f, __expf(-0.5f * x * x), normal_cdf_fast(x));
+}
+
 // ----------------------------------------------------------------------------- counter-based dropout RNG
-// Philox4x32-10 keyed by `seed`, counter = (offset + element_index/4); lane = element_index%4.
-// Stateless, so the backward pass regenerates the forward mask from (seed, offset) — no mask tensor.
+// Philox4x32-10 keyed by `seed`; one call serves EIGHT consecutive elements: counter = offset + element_index/8,
+// element (index % 8) takes the 16-bit field (index % 8) of the 128 random bits and is kept iff field >= round(p * 65536)
+// (drop probability quantised to 1/65536).  Stateless, so the backward pass regenerates the forward mask from
+// (seed, offset) — no mask tensor is ever stored.
 __device__ __forceinline__ uint4 philox4x32_10(uint64_t ctr, uint64_t key) {
     uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0x243F6A88u, c3 = 0x85A308D3u;
     uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
@@ -82,22 +102,38 @@ __device__ __forceinline__ uint4 philox4x32_10(uint64_t ctr, uint64_t key) {
     }
     return make_uint4(c0, c1, c2, c3);
 }
+__device__ __forceinline__ uint32_t dropout_threshold(float p) { return (uint32_t)(p * 65536.0f + 0.5f); }
+__device__ __forceinline__ uint32_t philox_field16(const uint4& r, uint32_t lane8) {
+    const uint32_t w = lane8 < 2 ? r.x : lane8 < 4 ? r.y : lane8 < 6 ? r.z : r.w;
+    return (lane8 & 1) ? (w >> 16) : (w & 0xFFFFu);
+}
 // keep-scale for element `idx`: 1/(1-p) if kept else 0.
 __device__ __forceinline__ float dropout_scale(uint64_t idx, float p, float inv_keep, uint64_t seed, uint64_t offset) {
-    const uint4 r = philox4x32_10(offset + (idx >> 2), seed);
-    const uint32_t lane = (uint32_t)(idx & 3);
-    const uint32_t u = lane == 0 ? r.x : lane == 1 ? r.y : lane == 2 ? r.z : r.w;
-    // uniform in [0,1): keep iff u >= p
-    return ((float)(u >> 8) * (1.0f / 16777216.0f) >= p) ? inv_keep : 0.0f;
+    const uint4 r = philox4x32_10(offset + (idx >> 3), seed);
+    return philox_field16(r, (uint32_t)(idx & 7)) >= dropout_threshold(p) ? inv_keep : 0.0f;
 }
-// four consecutive elements starting at idx (idx % 4 == 0): one Philox call
+// eight consecutive elements starting at idx (idx % 8 == 0): one Philox call
+__device__ __forceinline__ void dropout_scale8(float (&o)[8], uint64_t idx, float p, float inv_keep, uint64_t seed, uint64_t offset) {
+    const uint4 r = philox4x32_10(offset + (idx >> 3), seed);
+    const uint32_t thr = dropout_threshold(p);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        o[2 * i] = (w[i] & 0xFFFFu) >= thr ? inv_keep : 0.0f;
+        o[2 * i + 1] = (w[i] >> 16) >= thr ? inv_keep : 0.0f;
+    }
+}
+// four consecutive elements starting at idx (idx % 4 == 0): the matching half of the group's Philox call
 __device__ __forceinline__ float4 dropout_scale4(uint64_t idx, float p, float inv_keep, uint64_t seed, uint64_t offset) {
-    const uint4 r = philox4x32_10(offset + (idx >> 2), seed);
+    const uint4 r = philox4x32_10(offset + (idx >> 3), seed);
+    const uint32_t thr = dropout_threshold(p);
+    const bool hi = (idx & 4) != 0;
+    const uint32_t w0 = hi ? r.z : r.x, w1 = hi ? r.w : r.y;
     float4 o;
-    o.x = ((float)(r.x >> 8) * (1.0f / 16777216.0f) >= p) ? inv_keep : 0.0f;
-    o.y = ((float)(r.y >> 8) * (1.0f / 16777216.0f) >= p) ? inv_keep : 0.0f;
-    o.z = ((float)(r.z >> 8) * (1.0f / 16777216.0f) >= p) ? inv_keep : 0.0f;
-    o.w = ((float)(r.w >> 8) * (1.0f / 16777216.0f) >= p) ? inv_keep : 0.0f;
+    o.x = (w0 & 0xFFFFu) >= thr ? inv_keep : 0.0f;
+    o.y = (w0 >> 16) >= thr ? inv_keep : 0.0f;
+    o.z = (w1 & 0xFFFFu) >= thr ? inv_keep : 0.0f;
+    o.w = (w1 >> 16) >= thr ? inv_keep : 0.0f;
     return o;
 }
 
@@ -115,8 +151,10 @@ struct Epilogue {
     int64_t ldc2;
     float dropout_p;
     uint64_t seed, offset;
+    const uint64_t* offset_base;   // device word added to `offset` (CUDA-graph replays), or NULL
     int c_dtype;
 };
+__device__ __forceinline__ uint64_t effective_offset(uint64_t offset, const uint64_t* base) { return base ? offset + __ldg(base) : offset; }
 
 // Apply the epilogue to one accumulator value at (row, col); C addressing is left to the caller.
 template <typename TC>
@@ -127,7 +165,7 @@ __device__ __forceinline__ float epilogue_value(const Epilogue& e, float acc, in
     if (e.aux_out) reinterpret_cast<TC*>(e.aux_out)[row * e.ld_aux + col] = from_f32<TC>(v);
     if (e.flags & OVQA_EPI_GELU) v = gelu_erf(v);
     if (e.flags & OVQA_EPI_DGELU) v *= dgelu_erf(to_f32<TC>(reinterpret_cast<const TC*>(e.aux_in)[row * e.ld_aux + col]));
-    if (e.dropout_p > 0.0f) v *= dropout_scale((uint64_t)(row * n_cols + col), e.dropout_p, 1.0f / (1.0f - e.dropout_p), e.seed, e.offset);
+    if (e.dropout_p > 0.0f) v *= dropout_scale((uint64_t)(row * n_cols + col), e.dropout_p, 1.0f / (1.0f - e.dropout_p), e.seed, effective_offset(e.offset, e.offset_base));
     if (e.residual) v += __ldg(e.residual + row * e.ld_res + col);
     if (e.beta != 0.0f && c_old_ptr) v += e.beta * to_f32<TC>(*c_old_ptr);
     return v;

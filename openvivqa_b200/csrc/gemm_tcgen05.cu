@@ -2,8 +2,14 @@
 // in shared memory by TMA (cp.async.bulk.tensor, SWIZZLE_128B), persistent over output tiles with a
 // double-buffered TMEM accumulator so the epilogue of tile i overlaps the mainloop of tile i+1.
 //
-// Warp roles (192 threads, 1 CTA/SM):  warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator +
-// MMA issuer (one elected lane), warps 2..5 = epilogue (TMEM -> registers -> fused epilogue -> global).
+// Warp roles (320 threads, 1 CTA/SM):  warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator +
+// MMA issuer (one elected lane), warps 2..9 = epilogue: two warps per TMEM lane quadrant, each owning every other
+// 32-column chunk.  A chunk goes TMEM -> registers (row per lane) -> XOR-swizzled shared-memory scratch -> registers
+// (8 consecutive columns per lane, 4 lanes per row), so every global access of the fused epilogue (bias, saved
+// pre-activation, residual, C, bf16 copy, split-K reductions) is a coalesced 16-byte vector covering whole 128-byte
+// row segments, one Philox call serves a lane's 8 elements, and address arithmetic is amortised over 8 outputs.
+// With K = 512 the mainloop of a 128x256 tile is only ~4k cycles: the epilogue (GELU + dropout in fc1) runs in
+// its shadow on the other TMEM buffer and must not be the longer of the two.
 //
 // Operand forms (ovqa.h): OVQA_OP_N = reduction dim contiguous ("K-major" UMMA operand, one TMA box of
 // 64(k) x ROWS); OVQA_OP_T = M/N dim contiguous ("MN-major" UMMA operand, ROWS/64 TMA boxes of 64(mn) x 64(k)).
@@ -23,8 +29,10 @@ namespace {
 constexpr int BM = 128;          // UMMA M (cta_group::1)
 constexpr int BK = 64;           // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr int kAccStages = 2;
+constexpr int kScratchBytes = kEpiWarps * 32 * 32 * 4;   // one 32x32 fp32 chunk per epilogue warp
 
 template <int BN> struct Cfg {
     static constexpr int kStages = BN == 256 ? 4 : 6;
@@ -32,7 +40,7 @@ template <int BN> struct Cfg {
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kTmemCols = kAccStages * BN;  // 256 or 512: power of two
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kScratchBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 // ----------------------------------------------------------------------------- PTX wrappers
@@ -125,7 +133,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + cfg::kStages * cfg::kABytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + cfg::kStages * cfg::kStageBytes);
+    float4* scratch = reinterpret_cast<float4*>(smem + cfg::kStages * cfg::kStageBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + cfg::kStages * cfg::kStageBytes + kScratchBytes);
     uint64_t* full_bar = bars;                              // [kStages]   TMA -> MMA
     uint64_t* empty_bar = bars + cfg::kStages;              // [kStages]   MMA -> TMA
     uint64_t* tmem_full = bars + 2 * cfg::kStages;          // [2]         MMA -> epilogue
@@ -141,7 +150,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
         for (int i = 0; i < cfg::kStages; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
-        for (int i = 0; i < kAccStages; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, 4); }
+        for (int i = 0; i < kAccStages; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -224,11 +233,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue warps 2..5
-        const int lane_group = warp % 4;                  // tcgen05.ld: warp w may touch TMEM lanes [32*(w%4), +32)
-        const int row_in_tile = lane_group * 32 + lane;   // accumulator row == TMEM lane (M=128, cta_group::1)
-        const bool vec_ok = (n % 4 == 0);
+        // ------------------------------------------------------------------ epilogue warps 2..9
+        const int quad = warp % 4;                        // tcgen05.ld: warp w may touch TMEM lanes [32*(w%4), +32)
+        const int half = (warp - 2) / 4;                  // which 32-column chunks of the tile this warp owns
+        float4* sc = scratch + (warp - 2) * 256;          // 32 rows x 8 granules of 16 B, granule index XOR (row & 7)
+        const int rr = lane / 4, c8 = lane % 4;           // read-back mapping: row rr (+8 per pass), columns [8*c8, +8)
         const float inv_keep = epi.dropout_p > 0.f ? 1.0f / (1.0f - epi.dropout_p) : 1.0f;
+        const uint64_t rng_offset = epi.dropout_p > 0.f ? effective_offset(epi.offset, epi.offset_base) : 0;
+        // 16-byte vector accesses need every touched row start aligned: checked once
+        constexpr int kCVec = sizeof(TC) == 4 ? 4 : 8;
+        auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+        const bool vec_ok = (ldc % kCVec == 0) && al16(C) && (!epi.residual || (epi.ld_res % 4 == 0 && al16(epi.residual))) &&
+                            (!(epi.aux_in || epi.aux_out) || (epi.ld_aux % kCVec == 0 && al16(epi.aux_in) && al16(epi.aux_out))) &&
+                            (!epi.c2 || (epi.ldc2 % 8 == 0 && al16(epi.c2))) && (epi.dropout_p <= 0.f || n % 8 == 0);
+        const bool bias_vec = al16(epi.bias);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -236,76 +254,119 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             decode(tile, mt, nt, kb0, kb1);
             mbar_wait(tmem_full + acc, acc_phase);
             tcgen05_fence_after();
-            const int64_t row = (int64_t)mt * BM + row_in_tile;
-            const uint32_t t_row = tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)(acc * BN);
+            const int64_t row0 = (int64_t)mt * BM + quad * 32;
+            const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = half * 32; c0 < BN; c0 += 64) {
+                const int64_t col0 = (int64_t)nt * BN + c0;
+                if (col0 >= n) break;                                     // warp-uniform
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(t_row + (uint32_t)c0, r);
                 tmem_ld_wait();
-                const int64_t col0 = (int64_t)nt * BN + c0;
-                if (row < m && col0 < n) {
-                    if (split_k > 1) {
-                        if constexpr (sizeof(TC) == 4) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (col0 + j < n) atomicAdd(reinterpret_cast<float*>(C) + row * ldc + col0 + j, __uint_as_float(r[j]) * epi.alpha);
-                        }
-                    } else if (vec_ok && col0 + 32 <= n) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const int64_t col = col0 + j;
-                            float v[4] = {__uint_as_float(r[j]) * epi.alpha, __uint_as_float(r[j + 1]) * epi.alpha,
-                                          __uint_as_float(r[j + 2]) * epi.alpha, __uint_as_float(r[j + 3]) * epi.alpha};
-                            if (epi.bias) {
-                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col));
-                                v[0] += b4.x; v[1] += b4.y; v[2] += b4.z; v[3] += b4.w;
-                            }
-                            if (epi.aux_out) {
-                                TC* ap = reinterpret_cast<TC*>(epi.aux_out) + row * epi.ld_aux + col;
-                                if constexpr (sizeof(TC) == 4) *reinterpret_cast<float4*>(ap) = make_float4(v[0], v[1], v[2], v[3]);
-                                else *reinterpret_cast<uint2*>(ap) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
-                            }
-                            if (epi.flags & OVQA_EPI_GELU) {
-#pragma unroll
-                                for (int t = 0; t < 4; ++t) v[t] = gelu_erf(v[t]);
-                            }
-                            if (epi.flags & OVQA_EPI_DGELU) {
-                                const TC* ap = reinterpret_cast<const TC*>(epi.aux_in) + row * epi.ld_aux + col;
-                                float a[4];
-                                if constexpr (sizeof(TC) == 4) { const float4 t4 = *reinterpret_cast<const float4*>(ap); a[0] = t4.x; a[1] = t4.y; a[2] = t4.z; a[3] = t4.w; }
-                                else { const uint2 u = *reinterpret_cast<const uint2*>(ap); const float2 lo = unpack_bf16x2(u.x), hi = unpack_bf16x2(u.y); a[0] = lo.x; a[1] = lo.y; a[2] = hi.x; a[3] = hi.y; }
-#pragma unroll
-                                for (int t = 0; t < 4; ++t) v[t] *= dgelu_erf(a[t]);
-                            }
-                            if (epi.dropout_p > 0.f) {
-                                const float4 s4 = dropout_scale4((uint64_t)(row * n + col), epi.dropout_p, inv_keep, epi.seed, epi.offset);
-                                v[0] *= s4.x; v[1] *= s4.y; v[2] *= s4.z; v[3] *= s4.w;
-                            }
-                            if (epi.residual) {
-                                const float4 r4 = __ldg(reinterpret_cast<const float4*>(epi.residual + row * epi.ld_res + col));
-                                v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
-                            }
-                            TC* cp = C + row * ldc + col;
-                            if constexpr (sizeof(TC) == 4) {
-                                if (epi.beta != 0.f) { const float4 o = *reinterpret_cast<const float4*>(cp); v[0] += epi.beta * o.x; v[1] += epi.beta * o.y; v[2] += epi.beta * o.z; v[3] += epi.beta * o.w; }
-                                *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
-                            } else {
-                                *reinterpret_cast<uint2*>(cp) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
-                            }
-                            if (epi.c2) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(epi.c2) + row * epi.ldc2 + col) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
-                        }
+                for (int g = 0; g < 8; ++g)
+                    sc[lane * 8 + (g ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]),
+                                                                  __uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3]));
+                __syncwarp();
+                const int64_t col = col0 + c8 * 8;
+                float bias8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (epi.bias && split_k == 1) {
+                    if (bias_vec && col + 8 <= n) {
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(epi.bias + col)), b1 = __ldg(reinterpret_cast<const float4*>(epi.bias + col + 4));
+                        bias8[0] = b0.x; bias8[1] = b0.y; bias8[2] = b0.z; bias8[3] = b0.w; bias8[4] = b1.x; bias8[5] = b1.y; bias8[6] = b1.z; bias8[7] = b1.w;
                     } else {
-                        for (int j = 0; j < 32; ++j) {
-                            const int64_t col = col0 + j;
-                            if (col >= n) break;
-                            TC* cp = C + row * ldc + col;
-                            const float v = epilogue_value<TC>(epi, __uint_as_float(r[j]), row, col, n, cp);
-                            *cp = from_f32<TC>(v);
-                            if (epi.c2) reinterpret_cast<__nv_bfloat16*>(epi.c2)[row * epi.ldc2 + col] = __float2bfloat16_rn(v);
-                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) if (col + j < n) bias8[j] = __ldg(epi.bias + col + j);
                     }
                 }
+#pragma unroll
+                for (int pass = 0; pass < 4; ++pass) {
+                    const int rl = pass * 8 + rr;
+                    const int64_t row = row0 + rl;
+                    const float4 lo = sc[rl * 8 + ((2 * c8) ^ (rl & 7))], hi = sc[rl * 8 + ((2 * c8 + 1) ^ (rl & 7))];
+                    if (row >= m || col >= n) continue;
+                    float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+                    if (split_k > 1) {
+                        if constexpr (sizeof(TC) == 4) {
+                            float* cp = reinterpret_cast<float*>(C) + row * ldc + col;
+                            if (vec_ok && col + 8 <= n) {
+                                atomicAdd(reinterpret_cast<float4*>(cp), make_float4(v[0] * epi.alpha, v[1] * epi.alpha, v[2] * epi.alpha, v[3] * epi.alpha));
+                                atomicAdd(reinterpret_cast<float4*>(cp + 4), make_float4(v[4] * epi.alpha, v[5] * epi.alpha, v[6] * epi.alpha, v[7] * epi.alpha));
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) if (col + j < n) atomicAdd(cp + j, v[j] * epi.alpha);
+                            }
+                        }
+                        continue;
+                    }
+                    if (!(vec_ok && col + 8 <= n)) {                      // ragged tail / unaligned pitches: scalar path
+#pragma unroll 1
+                        for (int j = 0; j < 8; ++j) {
+                            if (col + j >= n) break;
+                            TC* cp = C + row * ldc + col + j;
+                            const float o = epilogue_value<TC>(epi, v[j], row, col + j, n, cp);
+                            *cp = from_f32<TC>(o);
+                            if (epi.c2) reinterpret_cast<__nv_bfloat16*>(epi.c2)[row * epi.ldc2 + col + j] = __float2bfloat16_rn(o);
+                        }
+                        continue;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], epi.alpha, bias8[j]);
+                    if (epi.aux_out) {
+                        TC* ap = reinterpret_cast<TC*>(epi.aux_out) + row * epi.ld_aux + col;
+                        if constexpr (sizeof(TC) == 4) {
+                            *reinterpret_cast<float4*>(ap) = make_float4(v[0], v[1], v[2], v[3]);
+                            *reinterpret_cast<float4*>(ap + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                        } else {
+                            *reinterpret_cast<uint4*>(ap) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                        }
+                    }
+                    if (epi.flags & OVQA_EPI_GELU) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = gelu_fast(v[j]);
+                    }
+                    if (epi.flags & OVQA_EPI_DGELU) {
+                        const TC* ap = reinterpret_cast<const TC*>(epi.aux_in) + row * epi.ld_aux + col;
+                        float a[8];
+                        if constexpr (sizeof(TC) == 4) {
+                            const float4 a0 = *reinterpret_cast<const float4*>(ap), a1 = *reinterpret_cast<const float4*>(ap + 4);
+                            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+                        } else {
+                            const uint4 u = *reinterpret_cast<const uint4*>(ap);
+                            const float2 p0 = unpack_bf16x2(u.x), p1 = unpack_bf16x2(u.y), p2 = unpack_bf16x2(u.z), p3 = unpack_bf16x2(u.w);
+                            a[0] = p0.x; a[1] = p0.y; a[2] = p1.x; a[3] = p1.y; a[4] = p2.x; a[5] = p2.y; a[6] = p3.x; a[7] = p3.y;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] *= dgelu_fast(a[j]);
+                    }
+                    if (epi.dropout_p > 0.f) {
+                        float ds[8];
+                        dropout_scale8(ds, (uint64_t)(row * n + col), epi.dropout_p, inv_keep, epi.seed, rng_offset);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] *= ds[j];
+                    }
+                    if (epi.residual) {
+                        const float* rp = epi.residual + row * epi.ld_res + col;
+                        const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp)), r1 = __ldg(reinterpret_cast<const float4*>(rp + 4));
+                        v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+                    }
+                    TC* cp = C + row * ldc + col;
+                    if constexpr (sizeof(TC) == 4) {
+                        if (epi.beta != 0.f) {
+                            const float4 o0 = *reinterpret_cast<const float4*>(cp), o1 = *reinterpret_cast<const float4*>(cp + 4);
+                            v[0] = fmaf(epi.beta, o0.x, v[0]); v[1] = fmaf(epi.beta, o0.y, v[1]); v[2] = fmaf(epi.beta, o0.z, v[2]); v[3] = fmaf(epi.beta, o0.w, v[3]);
+                            v[4] = fmaf(epi.beta, o1.x, v[4]); v[5] = fmaf(epi.beta, o1.y, v[5]); v[6] = fmaf(epi.beta, o1.z, v[6]); v[7] = fmaf(epi.beta, o1.w, v[7]);
+                        }
+                        *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+                        *reinterpret_cast<float4*>(cp + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                    } else {
+                        *reinterpret_cast<uint4*>(cp) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                    }
+                    if (epi.c2)
+                        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(epi.c2) + row * epi.ldc2 + col) =
+                            make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                }
+                __syncwarp();                                             // scratch is rewritten by the next chunk
             }
             tcgen05_fence_before();
             __syncwarp();
@@ -413,12 +474,25 @@ int gemm_tcgen05_bf16(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, i
     if (k <= 0) return OVQA_ERR_BAD_SHAPE;
     // TMA: base 16-byte aligned, row pitch multiple of 16 bytes
     if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) || (lda % 8) || (ldb % 8)) return OVQA_ERR_ALIGNMENT;
-    if (split_k < 1) split_k = 1;
-    if (split_k > 1 && epi.c_dtype != OVQA_F32) return OVQA_ERR_BAD_ARG;
     const bool a_mn = a_op == OVQA_OP_T, b_mn = b_op == OVQA_OP_T;
-    // wide-N tiles when there are enough of them to fill the machine; BN=128 otherwise
-    const int64_t tiles256 = ((m + BM - 1) / BM) * ((n + 255) / 256) * split_k;
-    const bool wide = (n % 256 == 0 || n > 1024) && tiles256 >= 2 * sm_count();
+    bool wide;
+    if (split_k <= 0) {
+        // auto (long reductions, i.e. wgrad): 256-wide tiles halve the operand bytes pulled from L2 per flop (the
+        // 128x128 tile needs 128 B/clk/SM of L2->smem at full MMA rate), then split K until ~2 waves of work units
+        // exist, keeping at least 8 k-blocks per unit.  C must have been zero-filled by the caller.
+        if (epi.c_dtype != OVQA_F32) return OVQA_ERR_BAD_ARG;
+        wide = n >= 256;
+        const int64_t tiles = ((m + BM - 1) / BM) * ((n + (wide ? 255 : 127)) / (wide ? 256 : 128));
+        const int64_t kblocks = (k + BK - 1) / BK;
+        int64_t want = (2 * (int64_t)sm_count() + tiles / 2) / tiles;
+        if (want > kblocks / 8) want = kblocks / 8;
+        split_k = (int)(want < 1 ? 1 : want);
+    } else {
+        if (split_k > 1 && epi.c_dtype != OVQA_F32) return OVQA_ERR_BAD_ARG;
+        // wide-N tiles when there are enough of them to fill the machine; BN=128 otherwise
+        const int64_t tiles256 = ((m + BM - 1) / BM) * ((n + 255) / 256) * split_k;
+        wide = (n % 256 == 0 || n > 1024) && tiles256 >= 2 * sm_count();
+    }
 #define OVQA_DISPATCH(BN_)                                                                                                 \
     do {                                                                                                                   \
         if (!a_mn && !b_mn) return launch<BN_, false, false>(A, B, C, m, n, k, lda, ldb, ldc, epi, split_k, st);           \

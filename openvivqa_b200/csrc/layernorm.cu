@@ -13,6 +13,8 @@ constexpr int kRowsPerCta = 4;
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
+// NV = float4 vectors per lane (D <= 128*NV): sized at compile time so the row really lives in registers
+template <int NV>
 __global__ void __launch_bounds__(kRowsPerCta * 32)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ residual, const float* __restrict__ gamma,
                      const float* __restrict__ beta, const float* __restrict__ post_add, int64_t post_rows,
@@ -22,10 +24,10 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ resi
     const int lane = threadIdx.x % 32;
     if (row >= rows) return;
     const int nvec = D / 4;
-    float4 v[kMaxVec];
+    float4 v[NV];
     float s = 0.f;
 #pragma unroll
-    for (int t = 0; t < kMaxVec; ++t) {
+    for (int t = 0; t < NV; ++t) {
         const int c = lane + 32 * t;
         if (c < nvec) {
             v[t] = ld4(x + row * D + 4 * c);
@@ -37,7 +39,7 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ resi
     const float mean = warp_sum(s) / (float)D;
     float q = 0.f;
 #pragma unroll
-    for (int t = 0; t < kMaxVec; ++t) {
+    for (int t = 0; t < NV; ++t) {
         const int c = lane + 32 * t;
         if (c < nvec) {
             const float a = v[t].x - mean, b = v[t].y - mean, cc = v[t].z - mean, d = v[t].w - mean;
@@ -47,7 +49,7 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ resi
     const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
     if (lane == 0) { if (mean_out) mean_out[row] = mean; if (rstd_out) rstd_out[row] = rstd; }
 #pragma unroll
-    for (int t = 0; t < kMaxVec; ++t) {
+    for (int t = 0; t < NV; ++t) {
         const int c = lane + 32 * t;
         if (c < nvec) {
             const float4 g = ld4(gamma + 4 * c), bb = ld4(beta + 4 * c);
@@ -60,17 +62,19 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ resi
     }
 }
 
+template <int NV>
 __global__ void __launch_bounds__(kRowsPerCta * 32)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
                      const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dx_add,
                      float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                     int64_t rows, int D, float p, float inv_keep, uint64_t seed, uint64_t offset) {
+                     int64_t rows, int D, float p, float inv_keep, uint64_t seed, uint64_t offset_, const uint64_t* offset_base) {
     __shared__ float red[kRowsPerCta][32 * 4 + 1];
+    const uint64_t offset = p > 0.f ? effective_offset(offset_, offset_base) : 0;
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int nvec = D / 4;
-    float4 g[kMaxVec], ag[kMaxVec], ab[kMaxVec];
+    float4 g[NV], ag[NV], ab[NV];
 #pragma unroll
-    for (int t = 0; t < kMaxVec; ++t) {
+    for (int t = 0; t < NV; ++t) {
         const int c = lane + 32 * t;
         g[t] = c < nvec ? ld4(gamma + 4 * c) : make_float4(0, 0, 0, 0);
         ag[t] = make_float4(0, 0, 0, 0);
@@ -78,10 +82,10 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
     }
     for (int64_t row = (int64_t)blockIdx.x * kRowsPerCta + warp; row < rows; row += (int64_t)gridDim.x * kRowsPerCta) {
         const float mu = mean[row], rs = rstd[row];
-        float4 xh[kMaxVec], d[kMaxVec];
+        float4 xh[NV], d[NV];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int t = 0; t < kMaxVec; ++t) {
+        for (int t = 0; t < NV; ++t) {
             const int c = lane + 32 * t;
             if (c < nvec) {
                 const float4 xv = ld4(x + row * D + 4 * c);
@@ -97,7 +101,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
         s1 = warp_sum(s1) / (float)D;
         s2 = warp_sum(s2) / (float)D;
 #pragma unroll
-        for (int t = 0; t < kMaxVec; ++t) {
+        for (int t = 0; t < NV; ++t) {
             const int c = lane + 32 * t;
             if (c < nvec) {
                 float4 o = make_float4(rs * (d[t].x - s1 - xh[t].x * s2), rs * (d[t].y - s1 - xh[t].y * s2),
@@ -120,7 +124,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
         float* dst = pass == 0 ? dgamma : dbeta;
         if (!dst) continue;
 #pragma unroll
-        for (int t = 0; t < kMaxVec; ++t) {
+        for (int t = 0; t < NV; ++t) {
             const int c = lane + 32 * t;
             const float4 a = pass == 0 ? ag[t] : ab[t];
             __syncthreads();
@@ -182,7 +186,9 @@ __global__ void colsum_kernel(const T* __restrict__ x, float* __restrict__ out, 
 }
 
 template <typename TO>
-__global__ void dropout_apply_kernel(const float* __restrict__ x, TO* __restrict__ y, int64_t n, float p, float inv_keep, uint64_t seed, uint64_t offset) {
+__global__ void dropout_apply_kernel(const float* __restrict__ x, TO* __restrict__ y, int64_t n, float p, float inv_keep, uint64_t seed, uint64_t offset_,
+                                     const uint64_t* offset_base) {
+    const uint64_t offset = p > 0.f ? effective_offset(offset_, offset_base) : 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
     for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
         float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f);
@@ -192,10 +198,11 @@ __global__ void dropout_apply_kernel(const float* __restrict__ x, TO* __restrict
     }
 }
 
-__global__ void dropout_mask_kernel(float* out, int64_t n, float p, uint64_t seed, uint64_t offset) {
+__global__ void dropout_mask_kernel(float* out, int64_t n, float p, uint64_t seed, uint64_t offset, const uint64_t* offset_base) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = dropout_scale((uint64_t)i, p, 1.0f, seed, offset);
+    if (i < n) out[i] = dropout_scale((uint64_t)i, p, 1.0f, seed, effective_offset(offset, offset_base));
 }
+__global__ void advance_u64_kernel(uint64_t* word, uint64_t delta) { *word += delta; }
 
 int grid_for(int64_t work_items, int threads) {
     int64_t g = (work_items + threads - 1) / threads;
@@ -209,6 +216,9 @@ int grid_for(int64_t work_items, int threads) {
 
 using namespace ovqa;
 
+// kernel instantiation whose per-lane register row (NV float4) just covers D
+#define OVQA_LN_DISPATCH(K) (nv <= 1 ? K<1> : nv <= 2 ? K<2> : nv <= 3 ? K<3> : nv <= 4 ? K<4> : nv <= 6 ? K<6> : K<8>)
+
 extern "C" int ovqa_layernorm_fwd(const float* x, const float* residual, const float* gamma, const float* beta,
                                   const float* post_add, int64_t post_add_rows, float* y_f32, void* y_bf16, float* sum_out,
                                   float* mean, float* rstd, int64_t rows, int64_t D, float eps, void* stream) {
@@ -216,7 +226,8 @@ extern "C" int ovqa_layernorm_fwd(const float* x, const float* residual, const f
     if (D % 4 != 0 || D > kMaxVec * 128) return OVQA_ERR_BAD_SHAPE;
     if (rows == 0) return OVQA_OK;
     if (post_add && post_add_rows <= 0) return OVQA_ERR_BAD_ARG;
-    layernorm_fwd_kernel<<<(unsigned)((rows + kRowsPerCta - 1) / kRowsPerCta), kRowsPerCta * 32, 0, (cudaStream_t)stream>>>(
+    const int nv = (int)((D + 127) / 128);
+    OVQA_LN_DISPATCH(layernorm_fwd_kernel)<<<(unsigned)((rows + kRowsPerCta - 1) / kRowsPerCta), kRowsPerCta * 32, 0, (cudaStream_t)stream>>>(
         x, residual, gamma, beta, post_add, post_add ? post_add_rows : 1, y_f32, (__nv_bfloat16*)y_bf16, sum_out, mean, rstd, rows, (int)D, eps);
     OVQA_LAUNCH_OK();
     return OVQA_OK;
@@ -224,7 +235,7 @@ extern "C" int ovqa_layernorm_fwd(const float* x, const float* residual, const f
 
 extern "C" int ovqa_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                                   const float* dx_add, float* dx, void* dx_bf16, float* dgamma, float* dbeta, int64_t rows,
-                                  int64_t D, float dropout_p, uint64_t seed, uint64_t offset, void* stream) {
+                                  int64_t D, float dropout_p, uint64_t seed, uint64_t offset, const uint64_t* offset_base, void* stream) {
     if (!dy || !x || !mean || !rstd || !gamma || rows < 0 || D <= 0) return OVQA_ERR_BAD_ARG;
     if (D % 4 != 0 || D > kMaxVec * 128) return OVQA_ERR_BAD_SHAPE;
     if (dropout_p < 0.f || dropout_p >= 1.f) return OVQA_ERR_BAD_ARG;
@@ -232,9 +243,10 @@ extern "C" int ovqa_layernorm_bwd(const float* dy, const float* x, const float* 
     int64_t g = (rows + kRowsPerCta - 1) / kRowsPerCta;
     const int64_t cap = (int64_t)sm_count() * 8;
     if (g > cap) g = cap;
-    layernorm_bwd_kernel<<<(unsigned)g, kRowsPerCta * 32, 0, (cudaStream_t)stream>>>(
+    const int nv = (int)((D + 127) / 128);
+    OVQA_LN_DISPATCH(layernorm_bwd_kernel)<<<(unsigned)g, kRowsPerCta * 32, 0, (cudaStream_t)stream>>>(
         dy, x, mean, rstd, gamma, dx_add, dx, (__nv_bfloat16*)dx_bf16, dgamma, dbeta, rows, (int)D, dropout_p,
-        dropout_p > 0.f ? 1.0f / (1.0f - dropout_p) : 1.0f, seed, offset);
+        dropout_p > 0.f ? 1.0f / (1.0f - dropout_p) : 1.0f, seed, offset, offset_base);
     OVQA_LAUNCH_OK();
     return OVQA_OK;
 }
@@ -279,20 +291,27 @@ extern "C" int ovqa_colsum(const void* x, float* out, int64_t m, int64_t n, int6
     OVQA_LAUNCH_OK();
     return OVQA_OK;
 }
-extern "C" int ovqa_dropout_apply(const float* x, void* y, int64_t n, float p, uint64_t seed, uint64_t offset, int out_dtype, void* stream) {
+extern "C" int ovqa_dropout_apply(const float* x, void* y, int64_t n, float p, uint64_t seed, uint64_t offset, const uint64_t* offset_base,
+                                  int out_dtype, void* stream) {
     if (!x || !y || n < 0 || p < 0.f || p >= 1.f) return OVQA_ERR_BAD_ARG;
     if (n == 0) return OVQA_OK;
     const float inv = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
-    if (out_dtype == OVQA_F32) dropout_apply_kernel<float><<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, (float*)y, n, p, inv, seed, offset);
-    else if (out_dtype == OVQA_BF16) dropout_apply_kernel<__nv_bfloat16><<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, n, p, inv, seed, offset);
+    if (out_dtype == OVQA_F32) dropout_apply_kernel<float><<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, (float*)y, n, p, inv, seed, offset, offset_base);
+    else if (out_dtype == OVQA_BF16) dropout_apply_kernel<__nv_bfloat16><<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, n, p, inv, seed, offset, offset_base);
     else return OVQA_ERR_BAD_ARG;
     OVQA_LAUNCH_OK();
     return OVQA_OK;
 }
-extern "C" int ovqa_dropout_mask(float* out, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream) {
+extern "C" int ovqa_advance_u64(uint64_t* word, uint64_t delta, void* stream) {
+    if (!word) return OVQA_ERR_BAD_ARG;
+    advance_u64_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(word, delta);
+    OVQA_LAUNCH_OK();
+    return OVQA_OK;
+}
+extern "C" int ovqa_dropout_mask(float* out, int64_t n, float p, uint64_t seed, uint64_t offset, const uint64_t* offset_base, void* stream) {
     if (!out || n < 0) return OVQA_ERR_BAD_ARG;
     if (n == 0) return OVQA_OK;
-    dropout_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, n, p, seed, offset);
+    dropout_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, n, p, seed, offset, offset_base);
     OVQA_LAUNCH_OK();
     return OVQA_OK;
 }

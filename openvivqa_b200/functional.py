@@ -32,6 +32,21 @@ class _DropoutStream:
         self.offset = 0
         self._seed_of = None
         self.seed = 0
+        self._base = {}
+
+    def base(self, device) -> torch.Tensor:
+        """Device word added to every offset inside the kernels (``offset_base`` of the C ABI).  Zero unless a
+        CUDA-graph user advances it between replays with :meth:`advance_on_device` — the launch parameters
+        (seed, offset) are frozen inside a captured graph, this word is what makes each replay draw new masks."""
+        key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+        t = self._base.get(key)
+        if t is None:
+            t = self._base[key] = torch.zeros((1,), dtype=torch.int64, device=device)
+        return t
+
+    def advance_on_device(self, device, delta: int = 1 << 32):
+        """Enqueue ``base += delta`` (capturable).  ``delta`` must exceed the offsets one step consumes."""
+        ops.advance_u64(self.base(device), delta)
 
     def next(self, numel: int):
         s = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF
@@ -110,24 +125,17 @@ def _cdt(mode: str) -> torch.dtype:
     return torch.float32 if mode == "fp32" else torch.bfloat16
 
 
-def _split_k(m_rows: int, n_out: int, n_in: int) -> int:
-    """wgrad: C is [n_out, n_in] (few tiles), reduction over m_rows is long -> split it to fill the SMs."""
-    tiles = ((n_out + 127) // 128) * ((n_in + 127) // 128)
-    want = max(1, (2 * 148) // max(tiles, 1))
-    return int(max(1, min(want, m_rows // 512 if m_rows >= 512 else 1)))
-
-
 def _wgrad(dy2: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
-    """dW[n_out, n_in] = dy2^T x2 (fp32), both operands read where they lie ("T","T")."""
-    sk = _split_k(dy2.shape[0], dy2.shape[1], x2.shape[1])
-    return ops.gemm(dy2, x2, a_op="T", b_op="T", out_dtype=torch.float32, split_k=sk)
+    """dW[n_out, n_in] = dy2^T x2 (fp32), both operands read where they lie ("T","T").  C has few tiles and the
+    reduction over B*L rows is long: ``split_k=0`` lets the library split it to fill the SMs."""
+    return ops.gemm(dy2, x2, a_op="T", b_op="T", out_dtype=torch.float32, split_k=0)
 
 
-def _masked_operand(ds: torch.Tensor, ds16: Optional[torch.Tensor], mode: str, p: float, seed: int, off: int) -> torch.Tensor:
+def _masked_operand(ds: torch.Tensor, ds16: Optional[torch.Tensor], mode: str, p: float, seed: int, off: int, rng_base=None) -> torch.Tensor:
     if mode == "bf16":
         return ds16.reshape(-1, ds.shape[-1])
     d2 = ds.reshape(-1, ds.shape[-1])
-    return d2 if p == 0.0 else ops.dropout_apply(d2, p, seed, off)
+    return d2 if p == 0.0 else ops.dropout_apply(d2, p, seed, off, offset_base=rng_base)
 
 
 # ----------------------------------------------------------------------------- generic Linear (AoA gate, pointer net, ...)
@@ -192,10 +200,11 @@ class _MHAFn(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad)
         att_ctx, lse, _ = ops.sdpa_fwd(q, k, v, h=h, d_k=dk, d_v=dv, mask=mask, geo=geo, scale=cfg["scale"], need_lse=need_grad)
         seed, off = dropout_stream.next(B * Lq * D) if p > 0.0 else (0, 0)
+        rng_base = dropout_stream.base(queries.device) if p > 0.0 else None
         q_res = queries.reshape(-1, D)
         q_res = q_res if (q_res.dtype == torch.float32 and q_res.is_contiguous()) else q_res.float().contiguous()
         s = ops.gemm(att_ctx.view(B * Lq, hv), weights.get([wo], cdt), bias=fb(bo), out_dtype=torch.float32,
-                     dropout_p=p, seed=seed, offset=off, residual=q_res)
+                     dropout_p=p, seed=seed, offset=off, offset_base=rng_base, residual=q_res)
         y, y16, _, mean, rstd = ops.layernorm_fwd(s, gamma.detach(), beta.detach(), eps=cfg["eps"], want_bf16=(mode == "bf16"),
                                                   save_stats=need_grad)
         y = y.view(B, Lq, D)
@@ -203,7 +212,7 @@ class _MHAFn(torch.autograd.Function):
             ctx.save_for_backward(xq, xk, xv, mask, *proj, att_ctx, lse, s, mean, rstd, gamma, wq, wk, wv, wo,
                                   boxes, geo_w, geo_b)
             ctx.n_proj = len(proj)
-            ctx.cfg, ctx.p, ctx.seed, ctx.off = cfg, p, seed, off
+            ctx.cfg, ctx.p, ctx.seed, ctx.off, ctx.rng_base = cfg, p, seed, off, rng_base
             ctx.flags = (self_att, kv_same)
             ctx.shapes = (B, Lq, Lk, D)
         y16 = y16.view(B, Lq, D) if y16 is not None else y.new_empty(0)
@@ -222,11 +231,11 @@ class _MHAFn(torch.autograd.Function):
         self_att, kv_same = ctx.flags
         B, Lq, Lk, D = ctx.shapes
         hk, hv = h * dk, h * dv
-        p, seed, off = ctx.p, ctx.seed, ctx.off
+        p, seed, off, rng_base = ctx.p, ctx.seed, ctx.off, ctx.rng_base
         # LayerNorm backward; the bf16 copy already carries the output-projection dropout mask
         ds, ds16, dgamma, dbeta = ops.layernorm_bwd(dy.reshape(B * Lq, D), s, mean, rstd, gamma, want_bf16=(mode == "bf16"),
-                                                    dropout_p=p, seed=seed, offset=off)
-        d_o = _masked_operand(ds, ds16, mode, p, seed, off)                       # grad of the fc_o output
+                                                    dropout_p=p, seed=seed, offset=off, offset_base=rng_base)
+        d_o = _masked_operand(ds, ds16, mode, p, seed, off, rng_base)             # grad of the fc_o output
         ctx2 = att_ctx.view(B * Lq, hv)
         dwo = _wgrad(d_o, ctx2)
         dbo = ops.colsum(d_o)
@@ -297,18 +306,19 @@ class _PWFFFn(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad)
         pre = torch.empty((M, dff), device=x.device, dtype=cdt) if need_grad else None
         s1, o1 = dropout_stream.next(M * dff) if p > 0.0 else (0, 0)
+        rng_base = dropout_stream.base(x.device) if p > 0.0 else None
         hact = ops.gemm(x2, weights.get([w1], cdt), bias=weights.get([b1], torch.float32), out_dtype=cdt, gelu=True,
-                        aux_out=pre, dropout_p=p, seed=s1, offset=o1)
+                        aux_out=pre, dropout_p=p, seed=s1, offset=o1, offset_base=rng_base)
         s2, o2 = dropout_stream.next(M * D) if p > 0.0 else (0, 0)
         x_res = x.reshape(-1, D)
         x_res = x_res if (x_res.dtype == torch.float32 and x_res.is_contiguous()) else x_res.float().contiguous()
         s = ops.gemm(hact, weights.get([w2], cdt), bias=weights.get([b2], torch.float32), out_dtype=torch.float32,
-                     dropout_p=p, seed=s2, offset=o2, residual=x_res)
+                     dropout_p=p, seed=s2, offset=o2, offset_base=rng_base, residual=x_res)
         y, y16, _, mean, rstd = ops.layernorm_fwd(s, gamma.detach(), beta.detach(), eps=cfg["eps"], want_bf16=(mode == "bf16"),
                                                   save_stats=need_grad)
         if need_grad:
             ctx.save_for_backward(x2, pre, hact, s, mean, rstd, gamma, w1, w2)
-            ctx.cfg, ctx.p, ctx.rng = cfg, p, (s1, o1, s2, o2)
+            ctx.cfg, ctx.p, ctx.rng, ctx.rng_base = cfg, p, (s1, o1, s2, o2), rng_base
             ctx.xshape = x.shape
         y16 = y16.view(x.shape) if y16 is not None else y.new_empty(0)
         ctx.mark_non_differentiable(y16)
@@ -319,14 +329,15 @@ class _PWFFFn(torch.autograd.Function):
         x2, pre, hact, s, mean, rstd, gamma, w1, w2 = ctx.saved_tensors
         mode, p = ctx.cfg["mode"], ctx.p
         s1, o1, s2, o2 = ctx.rng
+        rng_base = ctx.rng_base
         cdt = _cdt(mode)
         D = x2.shape[1]
         ds, ds16, dgamma, dbeta = ops.layernorm_bwd(dy.reshape(-1, D), s, mean, rstd, gamma, want_bf16=(mode == "bf16"),
-                                                    dropout_p=p, seed=s2, offset=o2)
-        d2 = _masked_operand(ds, ds16, mode, p, s2, o2)                             # grad of the fc2 output
+                                                    dropout_p=p, seed=s2, offset=o2, offset_base=rng_base)
+        d2 = _masked_operand(ds, ds16, mode, p, s2, o2, rng_base)                   # grad of the fc2 output
         dw2, db2 = _wgrad(d2, hact), ops.colsum(d2)
         # grad of the fc1 pre-activation: (d2 W2) * dropout1 mask * gelu'(pre), all in the dgrad epilogue
-        dpre = ops.gemm(d2, weights.get([w2], cdt), b_op="T", out_dtype=cdt, dgelu_aux=pre, dropout_p=p, seed=s1, offset=o1)
+        dpre = ops.gemm(d2, weights.get([w2], cdt), b_op="T", out_dtype=cdt, dgelu_aux=pre, dropout_p=p, seed=s1, offset=o1, offset_base=rng_base)
         dw1, db1 = _wgrad(dpre, x2), ops.colsum(dpre)
         dx = ops.gemm(dpre, weights.get([w1], cdt), b_op="T", out_dtype=torch.float32, residual=ds.reshape(-1, D)).view(ctx.xshape)
         return dx, dw1, db1, dw2, db2, dgamma, dbeta, None

@@ -62,3 +62,16 @@ def xmt_cfg(kind="cross", d_model=512, d_feature=2048, layers=2, head=8, d_ff=20
              LANGUAGE_SELF_ATTENTION=att())
     return NS(ARCHITECTURE="CrossModalityTransformer", NAME="xmt", DEVICE="cuda", D_MODEL=d_model, ENCODER=enc,
               USE_BOXES=geometry, **_embeddings(d_model, d_feature, dropout))
+
+
+def m4c_cfg(hidden=768, heads=8, mmt_layers=4, text_layers=3, d_obj=1024, d_ocr=812, ptr_qk=None, compute_dtype=None):
+    """configs/mmf_m4c.yaml:64-100 structure with BASELINE config 3's numbers (768 hidden, 8 heads -> d_head 96,
+    4 MMT layers, 3 TextBert layers, random init: ``LOAD_PRETRAINED False``)."""
+    c = NS(ARCHITECTURE="MMF_M4C", NAME="mmf_m4c", DEVICE="cuda",
+           MMT=NS(HIDDEN_SIZE=hidden, NUM_HIDDEN_LAYERS=mmt_layers, NUM_ATTENTION_HEADS=heads),
+           TEXT_BERT=NS(HIDDEN_SIZE=hidden, NUM_HIDDEN_LAYERS=text_layers, LOAD_PRETRAINED=False, PRETRAINED_NAME=None),
+           OBJECT_EMBEDDING=NS(D_FEATURE=d_obj, DROPOUT=0.1), OCR_EMBEDDING=NS(D_FEATURE=d_ocr, DROPOUT=0.1),
+           OCR_PTR_NET=NS(HIDDEN_SIZE=hidden, QUERY_KEY_SIZE=hidden if ptr_qk is None else ptr_qk))
+    if compute_dtype is not None:
+        c.COMPUTE_DTYPE = compute_dtype
+    return c

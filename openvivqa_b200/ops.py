@@ -46,7 +46,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_op: str = "N", b_op: str = "N", 
          beta: float = 0.0, gelu: bool = False, dgelu_aux: Optional[torch.Tensor] = None,
          aux_out: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          c2: Optional[torch.Tensor] = None, dropout_p: float = 0.0, seed: int = 0, offset: int = 0,
-         split_k: int = 1) -> torch.Tensor:
+         offset_base: Optional[torch.Tensor] = None, split_k: int = 1) -> torch.Tensor:
     """``C[m,n] = epilogue(sum_k A[m,k] B[n,k])`` — see ``ovqa_gemm`` in include/ovqa.h.
 
     ``a_op``/``b_op``: "N" = operand stored [rows, k]; "T" = stored [k, rows]."""
@@ -59,7 +59,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_op: str = "N", b_op: str = "N", 
     if k != kb:
         raise ValueError(f"gemm: reduction sizes differ ({k} vs {kb})")
     if out is None:
-        out = torch.empty((m, n), device=a.device, dtype=out_dtype or a.dtype) if split_k <= 1 and beta == 0.0 \
+        out = torch.empty((m, n), device=a.device, dtype=out_dtype or a.dtype) if split_k == 1 and beta == 0.0 \
             else torch.zeros((m, n), device=a.device, dtype=out_dtype or torch.float32)
     if out.shape != (m, n) or out.dtype not in _DT or (out.stride(1) != 1 and n != 1):
         raise ValueError("gemm: bad `out`")
@@ -81,7 +81,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_op: str = "N", b_op: str = "N", 
            L.OP_N if a_op == "N" else L.OP_T, L.OP_N if b_op == "N" else L.OP_T, _DT[a.dtype], _DT[out.dtype],
            float(alpha), float(beta), _p(bias), flags, _p(dgelu_aux), _p(aux_out), _ld(aux) if aux is not None else 0,
            _p(residual), _ld(residual) if residual is not None else 0, _p(c2), _ld(c2) if c2 is not None else 0,
-           float(dropout_p), int(seed), int(offset), int(split_k), _stream())
+           float(dropout_p), int(seed), int(offset), _p(offset_base), int(split_k), _stream())
     return out
 
 
@@ -210,7 +210,7 @@ def layernorm_fwd(x, gamma, beta, *, residual=None, post_add=None, eps: float = 
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, *, dx_add=None, want_bf16: bool = False, dropout_p: float = 0.0,
-                  seed: int = 0, offset: int = 0, dgamma=None, dbeta=None):
+                  seed: int = 0, offset: int = 0, offset_base=None, dgamma=None, dbeta=None):
     _need_cuda(dy, x, mean, rstd, gamma)
     D = x.shape[-1]
     dy2, x2 = dy.reshape(-1, D).contiguous().float(), x.reshape(-1, D)
@@ -223,7 +223,7 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, *, dx_add=None, want_bf16: bool = Fa
         dbeta = torch.zeros((D,), device=x.device, dtype=torch.float32)
     L.call("ovqa_layernorm_bwd", _p(dy2), _p(x2), _p(mean), _p(rstd), _p(gamma),
            None if dx_add is None else _p(dx_add.reshape(-1, D).contiguous()), _p(dx), _p(dx16), _p(dgamma), _p(dbeta),
-           rows, D, float(dropout_p), int(seed), int(offset), _stream())
+           rows, D, float(dropout_p), int(seed), int(offset), _p(offset_base), _stream())
     return dx.view(x.shape), (None if dx16 is None else dx16.view(x.shape)), dgamma, dbeta
 
 
@@ -265,19 +265,25 @@ def add(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return y
 
 
-def dropout_apply(x: torch.Tensor, p: float, seed: int, offset: int, out_dtype=torch.float32) -> torch.Tensor:
+def dropout_apply(x: torch.Tensor, p: float, seed: int, offset: int, out_dtype=torch.float32, offset_base=None) -> torch.Tensor:
     """y = dropout(x) with the library's counter-based mask over the flattened index space (p=0: cast)."""
     _need_cuda(x)
     x = x.contiguous()
     y = torch.empty(x.shape, device=x.device, dtype=out_dtype)
-    L.call("ovqa_dropout_apply", _p(x), _p(y), x.numel(), float(p), int(seed), int(offset), _DT[out_dtype], _stream())
+    L.call("ovqa_dropout_apply", _p(x), _p(y), x.numel(), float(p), int(seed), int(offset), _p(offset_base), _DT[out_dtype], _stream())
     return y
 
 
-def dropout_keep_mask(n: int, p: float, seed: int, offset: int, device) -> torch.Tensor:
+def dropout_keep_mask(n: int, p: float, seed: int, offset: int, device, offset_base=None) -> torch.Tensor:
     out = torch.empty((n,), device=device, dtype=torch.float32)
-    L.call("ovqa_dropout_mask", _p(out), n, float(p), int(seed), int(offset), _stream())
+    L.call("ovqa_dropout_mask", _p(out), n, float(p), int(seed), int(offset), _p(offset_base), _stream())
     return out
+
+
+def advance_u64(word: torch.Tensor, delta: int):
+    """``word[0] += delta`` on the device (word: int64 tensor of one element; the library treats it as u64)."""
+    _need_cuda(word)
+    L.call("ovqa_advance_u64", _p(word), int(delta), _stream())
 
 
 def box_geometry_bias(geo: GeoParams, h: int) -> torch.Tensor:

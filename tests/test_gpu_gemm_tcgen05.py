@@ -59,7 +59,7 @@ def test_fused_epilogues(dev):
     assert (out.cpu() - ref * keep.cpu() / 0.9).abs().max() <= 1e-3 * ref.abs().max()
 
 
-@pytest.mark.parametrize("split_k", [2, 7, 37])
+@pytest.mark.parametrize("split_k", [0, 2, 7, 37])
 def test_split_k_wgrad(dev, split_k):
     m, n, k = 512, 768, 9000
     a, b, ref = _mk(m, n, k, "T", "T", dev)
@@ -72,3 +72,39 @@ def test_rejects_unaligned_operands(dev):
     a = torch.randn((64, 36), device=dev).bfloat16()      # K=36 -> row pitch 72 B, not a multiple of 16
     with pytest.raises(OvqaError):
         ops.gemm(a, a)
+
+
+@pytest.mark.parametrize("n,odt", [(520, torch.float32), (520, torch.bfloat16), (516, torch.float32), (250, torch.bfloat16), (2048, torch.bfloat16)])
+def test_epilogue_vector_and_ragged_paths(dev, n, odt):
+    """The transposed 8-wide epilogue: full tiles, a tile with a ragged 8-column tail (n % 8 != 0), rows not a multiple
+    of 128, with bias + GELU + residual + bf16 copy in one pass, against the CUDA-core twin."""
+    m, k = 300, 192
+    a, b, ref = _mk(m, n, k, "N", "N", dev)
+    bias = torch.randn(n, device=dev)
+    res = torch.randn((m, n), device=dev)
+    pre = torch.empty((m, n), device=dev, dtype=odt)
+    c2 = torch.empty((m, n), device=dev, dtype=torch.bfloat16) if n % 8 == 0 else None
+    out = ops.gemm(a, b, out_dtype=odt, bias=bias, gelu=True, aux_out=pre, residual=res, c2=c2)
+    want_pre = ref.to(dev) + bias
+    want = torch.nn.functional.gelu(want_pre) + res
+    tol = 2e-2 if odt == torch.bfloat16 else 2e-3
+    assert (pre.float() - want_pre).abs().max() <= tol * want_pre.abs().max()
+    assert (out.float() - want).abs().max() <= tol * want.abs().max()
+    if c2 is not None:
+        assert (c2.float() - want).abs().max() <= 2e-2 * want.abs().max()
+    # backward-style epilogue: multiply by GELU'(saved pre-activation)
+    d = ops.gemm(a, b, out_dtype=odt, dgelu_aux=pre)
+    xs = pre.float().requires_grad_(True)
+    torch.nn.functional.gelu(xs).sum().backward()
+    want_d = ref.to(dev) * xs.grad
+    assert (d.float() - want_d).abs().max() <= tol * want_d.abs().max()
+
+
+def test_fast_gelu_matches_erf_gelu(dev):
+    """normal_cdf_fast (Abramowitz-Stegun 7.1.26) vs the exact erf GELU over the whole useful range."""
+    x = torch.linspace(-12, 12, 128 * 256, device=dev).view(128, 256)
+    eye = torch.eye(256, device=dev).bfloat16()
+    xb = x.bfloat16()
+    out = ops.gemm(xb, eye, out_dtype=torch.float32, gelu=True)           # y = gelu(x_bf16 * I)
+    want = torch.nn.functional.gelu(xb.float())
+    assert (out - want).abs().max().item() <= 1e-6

@@ -384,6 +384,42 @@ def test_dropout_mask_is_consistent_between_kernels(dev):
     assert abs_err(y16, (x * keep / (1 - p)).bfloat16()) == 0.0
     # a different offset gives a different mask
     assert (ops.dropout_keep_mask(m * n, p, seed, off + 10000, dev).view(m, n) != keep).any()
+    # device-side offset base (CUDA-graph replays): offset + *base is what the kernels use, in every kernel family
+    base = torch.tensor([10000], dtype=torch.int64, device=dev)
+    keep2 = ops.dropout_keep_mask(m * n, p, seed, off + 10000, dev).view(m, n)
+    assert torch.equal(ops.dropout_keep_mask(m * n, p, seed, off, dev, offset_base=base).view(m, n), keep2)
+    assert rel_err(ops.gemm(A, Bm, dropout_p=p, seed=seed, offset=off, offset_base=base), plain * keep2 / (1 - p)) < 1e-6
+    assert rel_err(ops.gemm(A.bfloat16(), Bm.bfloat16(), out_dtype=torch.float32, dropout_p=p, seed=seed, offset=off, offset_base=base),
+                   ops.gemm(A.bfloat16(), Bm.bfloat16(), out_dtype=torch.float32) * keep2 / (1 - p)) < 1e-6
+    assert rel_err(ops.dropout_apply(x, p, seed, off, offset_base=base), x * keep2 / (1 - p)) < 1e-6
+    ops.advance_u64(base, 5)
+    assert base.item() == 10005
+
+
+def test_cuda_graph_replays_draw_fresh_dropout_masks(dev):
+    """A captured training step freezes (seed, offset) in its launch parameters; advancing the device-side offset base
+    inside the graph makes every replay use new masks, and backward still matches its own forward."""
+    torch.manual_seed(0)
+    m = ovqa.MultiHeadAttention(H.attention_cfg(128, 4, dropout=0.5, compute_dtype="bf16")).to(dev).train()
+    x = torch.randn((4, 9, 128), device=dev)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            m(x, x, x, None).square().sum().backward()
+    torch.cuda.current_stream().wait_stream(side)
+    m.zero_grad(set_to_none=True)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        Fn.dropout_stream.advance_on_device(dev)
+        y = m(x, x, x, None)
+        y.square().sum().backward()
+    outs = []
+    for _ in range(3):
+        g.replay()
+        outs.append(y.clone())
+    torch.cuda.synchronize()
+    assert not torch.equal(outs[0], outs[1]) and not torch.equal(outs[1], outs[2])
 
 
 @pytest.mark.parametrize("block", ["mha", "pwff"])

@@ -113,3 +113,10 @@ def test_weight_cache_refreshes_after_fused_optimizer_step():
     with torch.no_grad():
         a.mul_(2.0)                                                      # version-bump path
     assert torch.equal(Fn.weights.get([a, b], torch.float32), torch.cat([a.detach(), b.detach()]))
+
+
+def test_m4c_mirror_state_dict_matches_reference_generated_spec(golden):
+    c = C.M4C_SMALL
+    m = H.MMF_M4C(H.m4c_cfg(c["hidden"], c["heads"], c["mmt_layers"], c["text_layers"], c["d_obj"]),
+                  H.StubVocab(c["vocab"], max_answer_length=c["T"]))
+    assert _spec(m) == [tuple(t) for t in golden("m4c")["spec"]]

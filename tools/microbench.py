@@ -70,7 +70,7 @@ def bench_gemm():
     for tag, m, n, k, ao, bo, odt in shapes:
         a = torch.randn((m, k) if ao == "N" else (k, m), device=dev).bfloat16()
         b = torch.randn((n, k) if bo == "N" else (k, n), device=dev).bfloat16()
-        sk = Fn._split_k(k, m, n) if ao == "T" else 1
+        sk = 0 if ao == "T" else 1      # 0: library picks split + tile width
         out = torch.zeros((m, n), device=dev, dtype=odt)
         t_ours = timeit(lambda: ops.gemm(a, b, a_op=ao, b_op=bo, out=out, split_k=sk))
         am = a if ao == "N" else a.t()
