@@ -123,8 +123,48 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool 
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// ----------------------------------------------------------------------------- epilogue pieces
+enum { EPI_PLAIN = 0, EPI_FULL = 1, EPI_SPLITK = 2 };   // alpha/bias only | every fused feature | fp32 atomic accumulation
+
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void lds128(uint32_t addr, float& a, float& b, float& c, float& d) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(addr) : "memory");
+}
+template <typename TC> __device__ __forceinline__ void store8(TC* p, const float (&v)[8]);
+template <> __device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+template <typename TC> __device__ __forceinline__ void load8(const TC* p, float (&v)[8]);
+template <> __device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    const float2 p0 = unpack_bf16x2(u.x), p1 = unpack_bf16x2(u.y), p2 = unpack_bf16x2(u.z), p3 = unpack_bf16x2(u.w);
+    v[0] = p0.x; v[1] = p0.y; v[2] = p1.x; v[3] = p1.y; v[4] = p2.x; v[5] = p2.y; v[6] = p3.x; v[7] = p3.y;
+}
+// slow path for ragged column tails / pitches that do not allow 16-byte vectors: one element, every feature
+template <typename TC>
+__device__ __noinline__ void epilogue_scalar(const Epilogue& epi, float acc, int64_t row, int64_t col, int64_t n, TC* C, int64_t ldc, int split_k) {
+    TC* cp = C + row * ldc + col;
+    if (split_k > 1) {
+        if constexpr (sizeof(TC) == 4) atomicAdd(reinterpret_cast<float*>(cp), acc * epi.alpha);
+        return;
+    }
+    const float o = epilogue_value<TC>(epi, acc, row, col, n, cp);
+    *cp = from_f32<TC>(o);
+    if (epi.c2) reinterpret_cast<__nv_bfloat16*>(epi.c2)[row * epi.ldc2 + col] = __float2bfloat16_rn(o);
+}
+
 // ----------------------------------------------------------------------------- kernel
-template <int BN, bool A_MN, bool B_MN, typename TC>
+template <int BN, bool A_MN, bool B_MN, typename TC, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, TC* __restrict__ C,
                     int64_t m, int64_t n, int64_t k, int64_t ldc, Epilogue epi, int split_k) {
@@ -236,17 +276,32 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         // ------------------------------------------------------------------ epilogue warps 2..9
         const int quad = warp % 4;                        // tcgen05.ld: warp w may touch TMEM lanes [32*(w%4), +32)
         const int half = (warp - 2) / 4;                  // which 32-column chunks of the tile this warp owns
-        float4* sc = scratch + (warp - 2) * 256;          // 32 rows x 8 granules of 16 B, granule index XOR (row & 7)
         const int rr = lane / 4, c8 = lane % 4;           // read-back mapping: row rr (+8 per pass), columns [8*c8, +8)
-        const float inv_keep = epi.dropout_p > 0.f ? 1.0f / (1.0f - epi.dropout_p) : 1.0f;
-        const uint64_t rng_offset = epi.dropout_p > 0.f ? effective_offset(epi.offset, epi.offset_base) : 0;
-        // 16-byte vector accesses need every touched row start aligned: checked once
-        constexpr int kCVec = sizeof(TC) == 4 ? 4 : 8;
+        // scratch: 32 rows x 8 granules of 16 B per warp, granule index XOR (row & 7)  (conflict-free both ways)
+        const uint32_t sc = smem_u32(scratch) + (uint32_t)(warp - 2) * 4096u;
+        const uint32_t st_row = sc + (uint32_t)lane * 128u, st_x = (uint32_t)(lane & 7);
+        const uint32_t ld_lo = sc + (uint32_t)rr * 128u + (uint32_t)(((2 * c8) ^ rr) << 4), ld_hi = sc + (uint32_t)rr * 128u + (uint32_t)(((2 * c8 + 1) ^ rr) << 4);
+        const float alpha = epi.alpha;
+        const float* __restrict__ bias = (MODE == EPI_SPLITK) ? nullptr : epi.bias;
         auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-        const bool vec_ok = (ldc % kCVec == 0) && al16(C) && (!epi.residual || (epi.ld_res % 4 == 0 && al16(epi.residual))) &&
-                            (!(epi.aux_in || epi.aux_out) || (epi.ld_aux % kCVec == 0 && al16(epi.aux_in) && al16(epi.aux_out))) &&
-                            (!epi.c2 || (epi.ldc2 % 8 == 0 && al16(epi.c2))) && (epi.dropout_p <= 0.f || n % 8 == 0);
-        const bool bias_vec = al16(epi.bias);
+        constexpr int kCVec = sizeof(TC) == 4 ? 4 : 8;
+        // 16-byte vector accesses need every touched row start aligned: checked once
+        const bool vec_ok = (ldc % kCVec == 0) && al16(C) && al16(bias) &&
+                            (MODE != EPI_FULL ||
+                             ((!epi.residual || (epi.ld_res % 4 == 0 && al16(epi.residual))) &&
+                              (!(epi.aux_in || epi.aux_out) || (epi.ld_aux % kCVec == 0 && al16(epi.aux_in) && al16(epi.aux_out))) &&
+                              (!epi.c2 || (epi.ldc2 % 8 == 0 && al16(epi.c2))) && (epi.dropout_p <= 0.f || n % 8 == 0)));
+        // FULL-mode features, hoisted (warp-uniform)
+        const bool f_gelu = MODE == EPI_FULL && (epi.flags & OVQA_EPI_GELU), f_dgelu = MODE == EPI_FULL && (epi.flags & OVQA_EPI_DGELU);
+        const bool f_drop = MODE == EPI_FULL && epi.dropout_p > 0.f;
+        const float* __restrict__ residual = MODE == EPI_FULL ? epi.residual : nullptr;
+        const TC* __restrict__ aux_in = MODE == EPI_FULL ? reinterpret_cast<const TC*>(epi.aux_in) : nullptr;
+        TC* __restrict__ aux_out = MODE == EPI_FULL ? reinterpret_cast<TC*>(epi.aux_out) : nullptr;
+        __nv_bfloat16* __restrict__ c2 = MODE == EPI_FULL ? reinterpret_cast<__nv_bfloat16*>(epi.c2) : nullptr;
+        const float beta = MODE == EPI_FULL ? epi.beta : 0.f;
+        const float drop_p = epi.dropout_p, inv_keep = f_drop ? 1.0f / (1.0f - epi.dropout_p) : 1.0f;
+        const uint64_t seed = epi.seed, rng_offset = f_drop ? effective_offset(epi.offset, epi.offset_base) : 0;
+        const int64_t ld_res = epi.ld_res, ld_aux = epi.ld_aux, ldc2 = epi.ldc2;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -254,119 +309,137 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             decode(tile, mt, nt, kb0, kb1);
             mbar_wait(tmem_full + acc, acc_phase);
             tcgen05_fence_after();
-            const int64_t row0 = (int64_t)mt * BM + quad * 32;
+            const int64_t row_base = (int64_t)mt * BM + quad * 32 + rr;          // + 8 * pass
             const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
             for (int c0 = half * 32; c0 < BN; c0 += 64) {
                 const int64_t col0 = (int64_t)nt * BN + c0;
                 if (col0 >= n) break;                                     // warp-uniform
+                const int64_t col = col0 + c8 * 8;
+                const bool fast = vec_ok && (col0 + 32 <= n);             // warp-uniform: whole chunk on the vector path
+                // operands that do not depend on the accumulator are requested first: their latency hides behind the
+                // TMEM read and the shared-memory transposition
+                float pre[4][8], b8[8];                                   // pre: residual rows, else the saved pre-activation (DGELU)
+                if (fast) {
+                    if (bias) load8<float>(bias + col, b8);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) b8[j] = 0.f;
+                    }
+                    if constexpr (MODE == EPI_FULL) {
+                        if (residual) {
+#pragma unroll
+                            for (int p = 0; p < 4; ++p)
+                                if (row_base + 8 * p < m) load8<float>(residual + (row_base + 8 * p) * ld_res + col, pre[p]);
+                        } else if (f_dgelu) {
+#pragma unroll
+                            for (int p = 0; p < 4; ++p)
+                                if (row_base + 8 * p < m) load8<TC>(aux_in + (row_base + 8 * p) * ld_aux + col, pre[p]);
+                        }
+                    }
+                }
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(t_row + (uint32_t)c0, r);
                 tmem_ld_wait();
 #pragma unroll
                 for (int g = 0; g < 8; ++g)
-                    sc[lane * 8 + (g ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]),
-                                                                  __uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3]));
+                    sts128(st_row + (((uint32_t)g ^ st_x) << 4), __uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
+                           __uint_as_float(r[4 * g + 3]));
                 __syncwarp();
-                const int64_t col = col0 + c8 * 8;
-                float bias8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                if (epi.bias && split_k == 1) {
-                    if (bias_vec && col + 8 <= n) {
-                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(epi.bias + col)), b1 = __ldg(reinterpret_cast<const float4*>(epi.bias + col + 4));
-                        bias8[0] = b0.x; bias8[1] = b0.y; bias8[2] = b0.z; bias8[3] = b0.w; bias8[4] = b1.x; bias8[5] = b1.y; bias8[6] = b1.z; bias8[7] = b1.w;
-                    } else {
+                float v[4][8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) if (col + j < n) bias8[j] = __ldg(epi.bias + col + j);
-                    }
-                }
-#pragma unroll
-                for (int pass = 0; pass < 4; ++pass) {
-                    const int rl = pass * 8 + rr;
-                    const int64_t row = row0 + rl;
-                    const float4 lo = sc[rl * 8 + ((2 * c8) ^ (rl & 7))], hi = sc[rl * 8 + ((2 * c8 + 1) ^ (rl & 7))];
-                    if (row >= m || col >= n) continue;
-                    float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-                    if (split_k > 1) {
-                        if constexpr (sizeof(TC) == 4) {
-                            float* cp = reinterpret_cast<float*>(C) + row * ldc + col;
-                            if (vec_ok && col + 8 <= n) {
-                                atomicAdd(reinterpret_cast<float4*>(cp), make_float4(v[0] * epi.alpha, v[1] * epi.alpha, v[2] * epi.alpha, v[3] * epi.alpha));
-                                atomicAdd(reinterpret_cast<float4*>(cp + 4), make_float4(v[4] * epi.alpha, v[5] * epi.alpha, v[6] * epi.alpha, v[7] * epi.alpha));
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) if (col + j < n) atomicAdd(cp + j, v[j] * epi.alpha);
-                            }
-                        }
-                        continue;
-                    }
-                    if (!(vec_ok && col + 8 <= n)) {                      // ragged tail / unaligned pitches: scalar path
-#pragma unroll 1
-                        for (int j = 0; j < 8; ++j) {
-                            if (col + j >= n) break;
-                            TC* cp = C + row * ldc + col + j;
-                            const float o = epilogue_value<TC>(epi, v[j], row, col + j, n, cp);
-                            *cp = from_f32<TC>(o);
-                            if (epi.c2) reinterpret_cast<__nv_bfloat16*>(epi.c2)[row * epi.ldc2 + col + j] = __float2bfloat16_rn(o);
-                        }
-                        continue;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], epi.alpha, bias8[j]);
-                    if (epi.aux_out) {
-                        TC* ap = reinterpret_cast<TC*>(epi.aux_out) + row * epi.ld_aux + col;
-                        if constexpr (sizeof(TC) == 4) {
-                            *reinterpret_cast<float4*>(ap) = make_float4(v[0], v[1], v[2], v[3]);
-                            *reinterpret_cast<float4*>(ap + 4) = make_float4(v[4], v[5], v[6], v[7]);
-                        } else {
-                            *reinterpret_cast<uint4*>(ap) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-                        }
-                    }
-                    if (epi.flags & OVQA_EPI_GELU) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = gelu_fast(v[j]);
-                    }
-                    if (epi.flags & OVQA_EPI_DGELU) {
-                        const TC* ap = reinterpret_cast<const TC*>(epi.aux_in) + row * epi.ld_aux + col;
-                        float a[8];
-                        if constexpr (sizeof(TC) == 4) {
-                            const float4 a0 = *reinterpret_cast<const float4*>(ap), a1 = *reinterpret_cast<const float4*>(ap + 4);
-                            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
-                        } else {
-                            const uint4 u = *reinterpret_cast<const uint4*>(ap);
-                            const float2 p0 = unpack_bf16x2(u.x), p1 = unpack_bf16x2(u.y), p2 = unpack_bf16x2(u.z), p3 = unpack_bf16x2(u.w);
-                            a[0] = p0.x; a[1] = p0.y; a[2] = p1.x; a[3] = p1.y; a[4] = p2.x; a[5] = p2.y; a[6] = p3.x; a[7] = p3.y;
-                        }
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] *= dgelu_fast(a[j]);
-                    }
-                    if (epi.dropout_p > 0.f) {
-                        float ds[8];
-                        dropout_scale8(ds, (uint64_t)(row * n + col), epi.dropout_p, inv_keep, epi.seed, rng_offset);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] *= ds[j];
-                    }
-                    if (epi.residual) {
-                        const float* rp = epi.residual + row * epi.ld_res + col;
-                        const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp)), r1 = __ldg(reinterpret_cast<const float4*>(rp + 4));
-                        v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
-                    }
-                    TC* cp = C + row * ldc + col;
-                    if constexpr (sizeof(TC) == 4) {
-                        if (epi.beta != 0.f) {
-                            const float4 o0 = *reinterpret_cast<const float4*>(cp), o1 = *reinterpret_cast<const float4*>(cp + 4);
-                            v[0] = fmaf(epi.beta, o0.x, v[0]); v[1] = fmaf(epi.beta, o0.y, v[1]); v[2] = fmaf(epi.beta, o0.z, v[2]); v[3] = fmaf(epi.beta, o0.w, v[3]);
-                            v[4] = fmaf(epi.beta, o1.x, v[4]); v[5] = fmaf(epi.beta, o1.y, v[5]); v[6] = fmaf(epi.beta, o1.z, v[6]); v[7] = fmaf(epi.beta, o1.w, v[7]);
-                        }
-                        *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
-                        *reinterpret_cast<float4*>(cp + 4) = make_float4(v[4], v[5], v[6], v[7]);
-                    } else {
-                        *reinterpret_cast<uint4*>(cp) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-                    }
-                    if (epi.c2)
-                        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(epi.c2) + row * epi.ldc2 + col) =
-                            make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                for (int p = 0; p < 4; ++p) {
+                    lds128(ld_lo + p * 1024, v[p][0], v[p][1], v[p][2], v[p][3]);
+                    lds128(ld_hi + p * 1024, v[p][4], v[p][5], v[p][6], v[p][7]);
                 }
                 __syncwarp();                                             // scratch is rewritten by the next chunk
+                if (!fast) {                                              // ragged tail / unaligned pitches
+#pragma unroll
+                    for (int p = 0; p < 4; ++p)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (row_base + 8 * p < m && col + j < n) epilogue_scalar<TC>(epi, v[p][j], row_base + 8 * p, col + j, n, C, ldc, split_k);
+                    continue;
+                }
+                if constexpr (MODE == EPI_SPLITK) {
+                    if constexpr (sizeof(TC) == 4) {
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) {
+                            if (row_base + 8 * p >= m) continue;
+                            float* cp = reinterpret_cast<float*>(C) + (row_base + 8 * p) * ldc + col;
+                            atomicAdd(reinterpret_cast<float4*>(cp), make_float4(v[p][0] * alpha, v[p][1] * alpha, v[p][2] * alpha, v[p][3] * alpha));
+                            atomicAdd(reinterpret_cast<float4*>(cp + 4), make_float4(v[p][4] * alpha, v[p][5] * alpha, v[p][6] * alpha, v[p][7] * alpha));
+                        }
+                    }
+                    continue;
+                }
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[p][j] = fmaf(v[p][j], alpha, b8[j]);
+                if constexpr (MODE == EPI_FULL) {
+                    if (aux_out) {
+#pragma unroll
+                        for (int p = 0; p < 4; ++p)
+                            if (row_base + 8 * p < m) store8<TC>(aux_out + (row_base + 8 * p) * ld_aux + col, v[p]);
+                    }
+                    if (f_gelu) {
+#pragma unroll
+                        for (int p = 0; p < 4; ++p)
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[p][j] = gelu_fast(v[p][j]);
+                    }
+                    if (f_dgelu) {
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) {
+                            if (residual) {                               // (never together on the path) not prefetched: load now
+                                if (row_base + 8 * p < m) load8<TC>(aux_in + (row_base + 8 * p) * ld_aux + col, b8);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[p][j] *= dgelu_fast(b8[j]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[p][j] *= dgelu_fast(pre[p][j]);
+                            }
+                        }
+                    }
+                    if (f_drop) {
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) {
+                            float ds[8];
+                            dropout_scale8(ds, (uint64_t)((row_base + 8 * p) * n + col), drop_p, inv_keep, seed, rng_offset);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[p][j] *= ds[j];
+                        }
+                    }
+                    if (residual) {
+#pragma unroll
+                        for (int p = 0; p < 4; ++p)
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[p][j] += pre[p][j];
+                    }
+                    if constexpr (sizeof(TC) == 4) {
+                        if (beta != 0.f) {
+#pragma unroll
+                            for (int p = 0; p < 4; ++p) {
+                                if (row_base + 8 * p >= m) continue;
+                                float o[8];
+                                load8<float>(reinterpret_cast<const float*>(C) + (row_base + 8 * p) * ldc + col, o);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[p][j] = fmaf(beta, o[j], v[p][j]);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+                    if (row_base + 8 * p < m) store8<TC>(C + (row_base + 8 * p) * ldc + col, v[p]);
+                if constexpr (MODE == EPI_FULL) {
+                    if (c2) {
+#pragma unroll
+                        for (int p = 0; p < 4; ++p)
+                            if (row_base + 8 * p < m) store8<__nv_bfloat16>(c2 + (row_base + 8 * p) * ldc2 + col, v[p]);
+                    }
+                }
             }
             tcgen05_fence_before();
             __syncwarp();
@@ -451,17 +524,24 @@ int launch(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, int64_t m, i
     if (split_k > num_k_blocks) split_k = num_k_blocks;
     const int64_t tiles = ((m + BM - 1) / BM) * ((n + BN - 1) / BN) * split_k;
     const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+    const bool full = epi.flags || epi.aux_in || epi.aux_out || epi.residual || epi.c2 || epi.dropout_p > 0.f || epi.beta != 0.f;
+    const int mode = split_k > 1 ? EPI_SPLITK : full ? EPI_FULL : EPI_PLAIN;
+#define OVQA_GO(TC_, MODE_)                                                                                                     \
+    do {                                                                                                                       \
+        auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, TC_, MODE_>;                                                            \
+        static bool attr_set = false;                                                                                          \
+        if (!attr_set) { OVQA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::kSmemBytes)); attr_set = true; } \
+        kern<<<grid, kThreads, cfg::kSmemBytes, st>>>(ma, mb, (TC_*)C, m, n, k, ldc, epi, split_k);                            \
+    } while (0)
     if (epi.c_dtype == OVQA_F32) {
-        auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, float>;
-        static bool attr_set = false;
-        if (!attr_set) { OVQA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::kSmemBytes)); attr_set = true; }
-        kern<<<grid, kThreads, cfg::kSmemBytes, st>>>(ma, mb, (float*)C, m, n, k, ldc, epi, split_k);
+        if (mode == EPI_SPLITK) OVQA_GO(float, EPI_SPLITK);
+        else if (mode == EPI_FULL) OVQA_GO(float, EPI_FULL);
+        else OVQA_GO(float, EPI_PLAIN);
     } else {
-        auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, __nv_bfloat16>;
-        static bool attr_set = false;
-        if (!attr_set) { OVQA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::kSmemBytes)); attr_set = true; }
-        kern<<<grid, kThreads, cfg::kSmemBytes, st>>>(ma, mb, (__nv_bfloat16*)C, m, n, k, ldc, epi, split_k);
+        if (mode == EPI_FULL) OVQA_GO(__nv_bfloat16, EPI_FULL);
+        else OVQA_GO(__nv_bfloat16, EPI_PLAIN);
     }
+#undef OVQA_GO
     OVQA_LAUNCH_OK();
     return OVQA_OK;
 }
