@@ -155,10 +155,14 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------------------------- our arm
 class GemmMeter:
-    """CUDA-event timing of every tcgen05 GEMM launch inside the timed region (events on the launching stream)."""
+    """CUDA-event timing of every tcgen05 GEMM launch of a step (events recorded on the launching stream).
+
+    ``external=True`` makes the events graph-capturable: inside a ``torch.cuda.graph`` capture each ``record()`` becomes an
+    event-record NODE, so replaying the instrumented graph times every GEMM exactly where it runs in the step, back to back
+    with its neighbours (eager events would also measure the host's launch gaps)."""
 
     def __init__(self):
-        self.records, self.enabled = [], False
+        self.records, self.enabled, self.external = [], False, False
 
     def install(self):
         from openvivqa_b200 import ops
@@ -170,21 +174,70 @@ class GemmMeter:
                 return orig(a, b, **kw)
             m, k = a.shape if kw.get("a_op", "N") == "N" else (a.shape[1], a.shape[0])
             n = b.shape[0] if kw.get("b_op", "N") == "N" else b.shape[1]
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0 = torch.cuda.Event(enable_timing=True, external=meter.external)
+            e1 = torch.cuda.Event(enable_timing=True, external=meter.external)
             e0.record()
             out = orig(a, b, **kw)
             e1.record()
-            meter.records.append((e0, e1, 2.0 * m * n * k))
+            epi = "+".join(t for t, on in (("bias", kw.get("bias") is not None), ("gelu", kw.get("gelu")), ("dgelu", kw.get("dgelu_aux") is not None),
+                                           ("save", kw.get("aux_out") is not None), ("drop", kw.get("dropout_p", 0.0) > 0), ("res", kw.get("residual") is not None),
+                                           ("splitk", kw.get("split_k", 1) != 1)) if on) or "plain"
+            tag = f"{kw.get('a_op', 'N')}{kw.get('b_op', 'N')} m={m} n={n} k={k} {epi} -> {str(out.dtype).replace('torch.', '')}"
+            meter.records.append((e0, e1, 2.0 * m * n * k, tag))
             return out
 
         ops.gemm = gemm
 
-    def summary(self):
+    def summary(self, steps=1):
         if not self.records:
             return None
-        ms = sum(e0.elapsed_time(e1) for e0, e1, _ in self.records)
-        fl = sum(f for _, _, f in self.records)
-        return dict(launches=len(self.records), total_ms=ms, flops=fl, tflops=fl / (ms * 1e-3) / 1e12, avg_us=ms * 1e3 / len(self.records))
+        per = {}
+        ms = fl = 0.0
+        for e0, e1, f, tag in self.records:
+            t = e0.elapsed_time(e1)
+            ms += t
+            fl += f
+            c = per.setdefault(tag, [0, 0.0, 0.0])
+            c[0] += 1; c[1] += t; c[2] += f
+        table = sorted(({"gemm": k, "launches": v[0], "ms": v[1], "tflops": v[2] / (v[1] * 1e-3) / 1e12} for k, v in per.items()), key=lambda r: -r["ms"])
+        return dict(launches=len(self.records), total_ms=ms, flops=fl, tflops=fl / (ms * 1e-3) / 1e12, avg_us=ms * 1e3 / len(self.records),
+                    steps=steps, table=table)
+
+
+def meter_step(meter, body, use_graph, prepare=None):
+    """Run ``body`` once more with an event pair around every GEMM launch; returns (ms of the instrumented step, how).
+    With graphs: a second, instrumented capture (event-record nodes), replayed twice; otherwise eager events."""
+    meter.enabled = True
+    try:
+        if not use_graph:
+            raise RuntimeError("graphs disabled")
+        meter.external = True
+        g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g2):
+            body()
+        torch.cuda.synchronize()
+        e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g2.replay()
+        e_a.record()
+        g2.replay()
+        e_b.record()
+        torch.cuda.synchronize()
+        ms, how = e_a.elapsed_time(e_b), ("event-record nodes around every GEMM launch inside a second, instrumented CUDA-graph capture of the same "
+                                          "step, replayed after the timed region (per-launch times of the last replay)")
+    except Exception as e:  # noqa: BLE001
+        meter.records, meter.external = [], False
+        torch.cuda.synchronize()
+        if prepare is not None:
+            prepare()
+        e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e_a.record()
+        body()
+        e_b.record()
+        torch.cuda.synchronize()
+        ms, how = e_a.elapsed_time(e_b), ("CUDA events around every GEMM launch during 1 eager step after the timed region (host launch gaps "
+                                          f"included; graph metering unavailable: {repr(e)[:80]})")
+    meter.enabled = False
+    return ms, how
 
 
 def run_ours(args):
@@ -207,8 +260,14 @@ def run_ours(args):
     torch.manual_seed(0)
     model = H.MCAN(H.mcan_cfg(wl["d_model"], wl["d_feature"], wl["layers"], wl["h"], wl["d_ff"], dropout=wl["dropout"], compute_dtype="bf16"),
                    H.StubVocab(wl["vocab"], wl["answers"])).to(dev).train()
+    use_graph = not args.no_graph and (world == 1 or os.environ.get("OVQA_DDP_GRAPH", "1") == "1")
+    if world > 1 and use_graph:
+        # capturing DDP's bucketed NCCL all-reduce: build DDP and warm up (>= 11 iterations: bucket rebuild, logging) on a side stream
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
+        side0 = torch.cuda.Stream()
+        side0.wait_stream(torch.cuda.current_stream())
+        torch.cuda.set_stream(side0)
     net = D.data_parallel(model, device_ids=[local], bucket_cap_mb=25)   # NCCL gradient all-reduce overlapped with backward (no-op at N=1)
-    use_graph = not args.no_graph and (world == 1 or os.environ.get("OVQA_DDP_GRAPH") == "1")
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.9, 0.98), fused=True, capturable=use_graph)
     host = synth_batches(3, wl, seed=1 + rank)
     dev_batches = [tuple(t.to(dev) for t in b) for b in host]
@@ -237,19 +296,17 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- eager warm-up (also what a CUDA graph capture needs), with the GEMM meter on for the roofline numbers
-    n_eager = max(3, args.warmup)
+    # ---- eager warm-up (also what a CUDA graph capture needs); the last 2 steps are timed as the eager reference
+    n_eager = max(3, args.warmup) if not (world > 1 and use_graph) else max(11, args.warmup)
     for i in range(n_eager):
         if i == n_eager - 2:
             barrier()
-            meter.enabled = True
             e_m0, e_m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e_m0.record()
         load(dev_batches[i % len(dev_batches)])
         step_body()
     e_m1.record()
     barrier()
-    meter.enabled = False
     eager_ms_per_step = e_m0.elapsed_time(e_m1) / 2.0
 
     # ---- capture the whole step into one CUDA graph (launch-bound otherwise: ~1.4k kernels per step)
@@ -359,6 +416,9 @@ def run_ours(args):
         e2e_s = t.item()
     e2e = wl["B"] * world * args.steps / e2e_s
 
+    # ---- roofline leg (kept out of the timed regions above)
+    meter_ms_per_step, meter_how = meter_step(meter, step_body, graph is not None, lambda: load(dev_batches[0]))
+
     if rank == 0:
         peaks = load_peaks()
         gm = meter.summary()
@@ -371,9 +431,8 @@ def run_ours(args):
             peak = peaks["bf16_tflops_sustained"]
             roof = dict(bound="tensor", kernel="gemm_tcgen05_kernel (all bf16 GEMM launches of a step)", achieved=gm["tflops"], peak=peak,
                         unit="TFLOP/s", frac=gm["tflops"] / peak, traffic=traffic, peak_source=peaks["source"] + " (sustained cuBLAS bf16)",
-                        launches=gm["launches"], avg_launch_us=gm["avg_us"], share_of_step=(gm["total_ms"] / 2.0) / (ms / args.steps),
-                        how="CUDA events around every GEMM launch during 2 eager (un-graphed) steps of the same workload in this process; "
-                            "the timed region replays those launches from a CUDA graph, where events cannot be interleaved")
+                        launches=gm["launches"], avg_launch_us=gm["avg_us"], share_of_step=gm["total_ms"] / meter_ms_per_step,
+                        instrumented_ms_per_step=meter_ms_per_step, how=meter_how, by_gemm=gm["table"][:12])
         cpu_sps, cpu_per = time_cpu(wl, 32, 2, 1) if args.gpus == 1 and not args.no_cpu_baseline else (None, None)
         line = dict(metric="VQA samples/sec (MCAN train)", value=value, unit="samples/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
@@ -506,14 +565,12 @@ def run_m4c(args):
     for i in range(3):
         if i == 1:
             barrier()
-            meter.enabled = True
             e_m0, e_m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e_m0.record()
         load(dev_batches[i % 3])
         decode_body()
     e_m1.record()
     barrier()
-    meter.enabled = False
     eager_ms = e_m0.elapsed_time(e_m1) / 2.0
     graph, graph_launches, graph_err = None, None, None
     if not args.no_graph:
@@ -576,6 +633,7 @@ def run_m4c(args):
         t = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = t.item()
+    meter_ms, meter_how = meter_step(meter, decode_body, graph is not None)
     if rank == 0:
         peaks = load_peaks()
         gm = meter.summary()
@@ -584,8 +642,8 @@ def run_m4c(args):
             peak = peaks["bf16_tflops_sustained"]
             roof = dict(bound="tensor", kernel="gemm_tcgen05_kernel (all bf16 GEMM launches of a decode)", achieved=gm["tflops"], peak=peak, unit="TFLOP/s",
                         frac=gm["tflops"] / peak, traffic=None, peak_source=peaks["source"] + " (sustained cuBLAS bf16)", launches=gm["launches"],
-                        avg_launch_us=gm["avg_us"], share_of_step=(gm["total_ms"] / 2.0) / (ms / args.steps),
-                        how="CUDA events around every GEMM launch during 2 eager decodes in this process (the timed region replays a CUDA graph)")
+                        avg_launch_us=gm["avg_us"], share_of_step=gm["total_ms"] / meter_ms, instrumented_ms_per_step=meter_ms, how=meter_how,
+                        by_gemm=gm["table"][:10])
         line = dict(metric=metric, value=value, unit="samples/s", n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps,
                     higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
                     config=dict(workload=m4c_workload_name(c, B), global_batch=B * world, parallelism=f"dp{world} (batch partition, no collective)",

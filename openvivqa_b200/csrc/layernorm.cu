@@ -240,8 +240,10 @@ extern "C" int ovqa_layernorm_bwd(const float* dy, const float* x, const float* 
     if (D % 4 != 0 || D > kMaxVec * 128) return OVQA_ERR_BAD_SHAPE;
     if (dropout_p < 0.f || dropout_p >= 1.f) return OVQA_ERR_BAD_ARG;
     if (rows == 0) return OVQA_OK;
+    // persistent: as many CTAs as stay resident (register-limited to ~3 per SM); every CTA ends with one atomicAdd per
+    // column into dgamma/dbeta, so fewer, longer-lived CTAs also mean fewer same-address atomics
     int64_t g = (rows + kRowsPerCta - 1) / kRowsPerCta;
-    const int64_t cap = (int64_t)sm_count() * 8;
+    const int64_t cap = (int64_t)sm_count() * 3;
     if (g > cap) g = cap;
     const int nv = (int)((D + 127) / 128);
     OVQA_LN_DISPATCH(layernorm_bwd_kernel)<<<(unsigned)g, kRowsPerCta * 32, 0, (cudaStream_t)stream>>>(

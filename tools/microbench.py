@@ -150,8 +150,34 @@ def bench_mha():
     ovqa.set_compute_dtype("fp32")
 
 
+def bench_gemm_epilogues():
+    """The fused epilogues of the training step at the vision-branch shapes (B*L = 25600)."""
+    M, D, F_ = 25600, 512, 2048
+    x16 = torch.randn((M, D), device=dev).bfloat16()
+    h16 = torch.randn((M, F_), device=dev).bfloat16()
+    w1, w2 = torch.randn((F_, D), device=dev).bfloat16(), torch.randn((D, F_), device=dev).bfloat16()
+    wqkv, wo = torch.randn((3 * D, D), device=dev).bfloat16(), torch.randn((D, D), device=dev).bfloat16()
+    b1, b2, bqkv = torch.randn(F_, device=dev), torch.randn(D, device=dev), torch.randn(3 * D, device=dev)
+    res = torch.randn((M, D), device=dev)
+    pre = torch.empty((M, F_), device=dev, dtype=torch.bfloat16)
+    o_h, o_s, o_qkv = torch.empty((M, F_), device=dev, dtype=torch.bfloat16), torch.empty((M, D), device=dev), torch.empty((M, 3 * D), device=dev, dtype=torch.bfloat16)
+    d2 = torch.randn((M, D), device=dev).bfloat16()
+    cases = [
+        ("qkv: bias -> bf16", 2.0 * M * 3 * D * D, lambda: ops.gemm(x16, wqkv, bias=bqkv, out=o_qkv)),
+        ("fc1: bias+save pre+GELU+dropout -> bf16", 2.0 * M * F_ * D, lambda: ops.gemm(x16, w1, bias=b1, out=o_h, gelu=True, aux_out=pre, dropout_p=0.1, seed=1, offset=0)),
+        ("fc1 eval: bias+GELU -> bf16", 2.0 * M * F_ * D, lambda: ops.gemm(x16, w1, bias=b1, out=o_h, gelu=True)),
+        ("fc2: bias+dropout+residual -> f32", 2.0 * M * F_ * D, lambda: ops.gemm(h16, w2, bias=b2, out=o_s, dropout_p=0.1, seed=1, offset=0, residual=res)),
+        ("fc_o: bias+dropout+residual -> f32", 2.0 * M * D * D, lambda: ops.gemm(x16, wo, bias=b2, out=o_s, dropout_p=0.1, seed=1, offset=0, residual=res)),
+        ("dpre: dgrad fc2 * GELU'(pre) * dropout -> bf16", 2.0 * M * F_ * D, lambda: ops.gemm(d2, w2, b_op="T", out=o_h, dgelu_aux=pre, dropout_p=0.1, seed=1, offset=0)),
+        ("dx: dgrad fc1 + residual -> f32", 2.0 * M * F_ * D, lambda: ops.gemm(h16, w1, b_op="T", out=o_s, residual=res)),
+    ]
+    for tag, fl, fn in cases:
+        t = timeit(fn)
+        emit(kind="gemm_epilogue", tag=tag, us=t, tflops=fl / t / 1e6, frac_of_peak=fl / t / 1e6 / PEAKS["bf16_tflops"])
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["gemm", "sdpa", "ln", "mha"]
+    which = sys.argv[1:] or ["gemm", "epi", "sdpa", "ln", "mha"]
     emit(kind="meta", gpu=torch.cuda.get_device_name(0), peaks=PEAKS)
     for w in which:
-        {"gemm": bench_gemm, "sdpa": bench_sdpa, "ln": bench_ln, "mha": bench_mha}[w]()
+        {"gemm": bench_gemm, "epi": bench_gemm_epilogues, "sdpa": bench_sdpa, "ln": bench_ln, "mha": bench_mha}[w]()
