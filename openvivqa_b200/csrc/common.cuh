@@ -69,20 +69,27 @@ __device__ __forceinline__ float dgelu_erf(float x) {
 
 // Standard normal CDF Phi(x) = 0.5 (1 + erf(x / sqrt 2)) for the tensor-core GEMM epilogues, where GELU runs in the
 // shadow of the MMA pipe and instruction count matters: Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7 on erf, i.e.
-// fp32-rounding level), evaluated on the erfc side so the negative tail has no 1+erf cancellation.
-__device__ __forceinline__ float normal_cdf_fast(float x) {
+// fp32-rounding level), evaluated on the erfc side so the negative tail has no 1+erf cancellation.  Exactly two
+// MUFU operations per element (rcp.approx, ex2.approx — the IEEE-rounded intrinsics compile to call sequences), and
+// GELU' reuses the same exponential: exp(-z^2) with z = x/sqrt 2 IS the Gaussian kernel exp(-x^2/2).
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float normal_cdf_fast(float x, float& gauss) {
     const float z = fabsf(x) * 0.70710678118654752440f;
-    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
+    gauss = ex2_approx(x * x * -0.72134752044448170368f);           // exp(-x^2/2) = 2^(-x^2 / (2 ln 2))
     float poly = fmaf(1.061405429f, t, -1.453152027f);
     poly = fmaf(poly, t, 1.421413741f);
     poly = fmaf(poly, t, -0.284496736f);
     poly = fmaf(poly, t, 0.254829592f);
-    const float h = 0.5f * poly * t * __expf(-z * z);     // 0.5 erfc(|x|/sqrt 2)
+    const float h = 0.5f * poly * t * gauss;               // 0.5 erfc(|x|/sqrt 2)
     return x < 0.0f ? h : 1.0f - h;
 }
-__device__ __forceinline__ float gelu_fast(float x) { return x * normal_cdf_fast(x); }
+__device__ __forceinline__ float gelu_fast(float x) { float g; return x * normal_cdf_fast(x, g); }
 __device__ __forceinline__ float dgelu_fast(float x) {
-    return fmaf(x * 0.39894228040143267794f, __expf(-0.5f * x * x), normal_cdf_fast(x));
+    float g;
+    const float cdf = normal_cdf_fast(x, g);
+    return fmaf(x * 0.39894228040143267794f, g, cdf);
 }
 
 // ----------------------------------------------------------------------------- counter-based dropout RNG

@@ -197,7 +197,7 @@ class _MHAFn(torch.autograd.Function):
             v = ops.gemm(xv, weights.get([wv], cdt), bias=fb(bv), out_dtype=cdt).view(B, Lk, hv)
             proj = (q, k, v)
         geo = ops.GeoParams(boxes, geo_w.detach(), geo_b.detach(), cfg["geo_trig"]) if boxes is not None else None
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = cfg["grad"] and any(ctx.needs_input_grad)     # (grad mode is always off INSIDE forward: flag taken outside)
         att_ctx, lse, _ = ops.sdpa_fwd(q, k, v, h=h, d_k=dk, d_v=dv, mask=mask, geo=geo, scale=cfg["scale"], need_lse=need_grad)
         seed, off = dropout_stream.next(B * Lq * D) if p > 0.0 else (0, 0)
         rng_base = dropout_stream.base(queries.device) if p > 0.0 else None
@@ -286,7 +286,7 @@ class _MHAFn(torch.autograd.Function):
 
 def mha_block(queries, keys, values, mask, *, wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta, h, d_k, d_v, mode="fp32",
               dropout=0.0, training=False, eps=1e-5, boxes=None, geo_w=None, geo_b=None, geo_trig=True, scale=None):
-    cfg = dict(mode=mode, h=h, d_k=d_k, d_v=d_v, dropout=float(dropout), training=bool(training), eps=float(eps),
+    cfg = dict(grad=torch.is_grad_enabled(), mode=mode, h=h, d_k=d_k, d_v=d_v, dropout=float(dropout), training=bool(training), eps=float(eps),
                geo_trig=bool(geo_trig), scale=(1.0 / math.sqrt(d_k)) if scale is None else float(scale))
     y, y16 = _MHAFn.apply(queries, keys, values, mask, boxes, wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta, geo_w, geo_b, cfg)
     _attach_shadow(y, y16 if mode == "bf16" else None)
@@ -303,7 +303,7 @@ class _PWFFFn(torch.autograd.Function):
         D = x.shape[-1]
         x2 = _operand(x, mode)
         M, dff = x2.shape[0], w1.shape[0]
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = cfg["grad"] and any(ctx.needs_input_grad)
         pre = torch.empty((M, dff), device=x.device, dtype=cdt) if need_grad else None
         s1, o1 = dropout_stream.next(M * dff) if p > 0.0 else (0, 0)
         rng_base = dropout_stream.base(x.device) if p > 0.0 else None
@@ -344,7 +344,7 @@ class _PWFFFn(torch.autograd.Function):
 
 
 def pwff_block(x, *, w1, b1, w2, b2, gamma, beta, mode="fp32", dropout=0.0, training=False, eps=1e-5):
-    cfg = dict(mode=mode, dropout=float(dropout), training=bool(training), eps=float(eps))
+    cfg = dict(grad=torch.is_grad_enabled(), mode=mode, dropout=float(dropout), training=bool(training), eps=float(eps))
     y, y16 = _PWFFFn.apply(x, w1, b1, w2, b2, gamma, beta, cfg)
     _attach_shadow(y, y16 if mode == "bf16" else None)
     return y
@@ -355,7 +355,7 @@ class _SdpaFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, mask, cfg):
         h, dk, dv = cfg["h"], cfg["d_k"], cfg["d_v"]
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = cfg["grad"] and any(ctx.needs_input_grad)
         out, lse, att = ops.sdpa_fwd(q, k, v, h=h, d_k=dk, d_v=dv, mask=mask, geo=cfg.get("geo"), scale=cfg["scale"],
                                      need_lse=need_grad, need_att=cfg["need_att"])
         if need_grad:
@@ -380,15 +380,16 @@ def sdpa(q, k, v, mask, *, h, d_k, d_v, scale=None, need_att=False, geo=None):
     """Attention core on already projected (B,L,h*d) tensors (fp32 or bf16).  Returns (out, att|None).
     Gradients flow to q,k,v (not through the returned probabilities, nor to the geometry weights: use
     :func:`mha_block` for that)."""
-    cfg = dict(h=h, d_k=d_k, d_v=d_v, scale=(1.0 / math.sqrt(d_k)) if scale is None else float(scale), need_att=need_att, geo=geo)
+    cfg = dict(grad=torch.is_grad_enabled(), h=h, d_k=d_k, d_v=d_v, scale=(1.0 / math.sqrt(d_k)) if scale is None else float(scale), need_att=need_att,
+               geo=geo)
     out, att = _SdpaFn.apply(q.contiguous(), k.contiguous(), v.contiguous(), mask, cfg)
     return out, (att if need_att else None)
 
 
 class _LayerNormFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, eps, post_add):
-        need_grad = any(ctx.needs_input_grad)
+    def forward(ctx, x, gamma, beta, eps, post_add, grad_on):
+        need_grad = grad_on and any(ctx.needs_input_grad)
         y, _, _, mean, rstd = ops.layernorm_fwd(x.float(), gamma.detach(), beta.detach(), eps=eps, post_add=post_add, save_stats=need_grad)
         if need_grad:
             ctx.save_for_backward(x, mean, rstd, gamma)
@@ -398,9 +399,9 @@ class _LayerNormFn(torch.autograd.Function):
     def backward(ctx, dy):
         x, mean, rstd, gamma = ctx.saved_tensors
         dx, _, dg, db = ops.layernorm_bwd(dy, x.float().contiguous(), mean, rstd, gamma)
-        return dx, dg, db, None, None
+        return dx, dg, db, None, None, None
 
 
 def layer_norm(x, gamma, beta, eps=1e-5, post_add=None):
     """``LN(x) [+ post_add]`` (e.g. the encoders' ``layer_norm(features) + pos_embedding``, encoders.py:113)."""
-    return _LayerNormFn.apply(x, gamma, beta, float(eps), post_add)
+    return _LayerNormFn.apply(x, gamma, beta, float(eps), post_add, torch.is_grad_enabled())
