@@ -179,7 +179,7 @@ class GemmMeter:
             e0.record()
             out = orig(a, b, **kw)
             e1.record()
-            epi = "+".join(t for t, on in (("bias", kw.get("bias") is not None), ("gelu", kw.get("gelu")), ("dgelu", kw.get("dgelu_aux") is not None),
+            epi = "+".join(t for t, on in (("bias", kw.get("bias") is not None), ("gelu", kw.get("gelu")), ("dgelu", kw.get("dgelu_aux") is not None), ("mulaux", kw.get("mul_aux") is not None),
                                            ("save", kw.get("aux_out") is not None), ("drop", kw.get("dropout_p", 0.0) > 0), ("res", kw.get("residual") is not None),
                                            ("splitk", kw.get("split_k", 1) != 1)) if on) or "plain"
             tag = f"{kw.get('a_op', 'N')}{kw.get('b_op', 'N')} m={m} n={n} k={k} {epi} -> {str(out.dtype).replace('torch.', '')}"

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libovqa_b200.so")
 
 F32, BF16 = 0, 1
 OP_N, OP_T = 0, 1
-EPI_GELU, EPI_DGELU = 1, 2
+EPI_GELU, EPI_DGELU, EPI_SAVE_DGELU, EPI_MUL_AUX = 1, 2, 4, 8
 
 _vp, _i64, _i32, _f32, _u64 = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_uint64
 

@@ -56,7 +56,8 @@ extern "C" int ovqa_gemm(const void* A, const void* B, void* C, int64_t m, int64
     if ((a_op != OVQA_OP_N && a_op != OVQA_OP_T) || (b_op != OVQA_OP_N && b_op != OVQA_OP_T)) return OVQA_ERR_BAD_ARG;
     if ((ab_dtype != OVQA_F32 && ab_dtype != OVQA_BF16) || (c_dtype != OVQA_F32 && c_dtype != OVQA_BF16)) return OVQA_ERR_BAD_ARG;
     if (dropout_p < 0.f || dropout_p >= 1.f) return OVQA_ERR_BAD_ARG;
-    if ((epi_flags & OVQA_EPI_DGELU) && !aux_in) return OVQA_ERR_BAD_ARG;
+    if ((epi_flags & (OVQA_EPI_DGELU | OVQA_EPI_MUL_AUX)) && !aux_in) return OVQA_ERR_BAD_ARG;
+    if ((epi_flags & OVQA_EPI_SAVE_DGELU) && !((epi_flags & OVQA_EPI_GELU) && aux_out)) return OVQA_ERR_BAD_ARG;
     if (beta != 0.f && c_dtype != OVQA_F32) return OVQA_ERR_BAD_ARG;
     if (split_k != 1 && (bias || epi_flags || aux_out || residual || c2_bf16 || dropout_p > 0.f || beta != 0.f)) return OVQA_ERR_BAD_ARG;
     if (m == 0 || n == 0) return OVQA_OK;

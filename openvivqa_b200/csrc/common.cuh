@@ -86,6 +86,13 @@ __device__ __forceinline__ float normal_cdf_fast(float x, float& gauss) {
     return x < 0.0f ? h : 1.0f - h;
 }
 __device__ __forceinline__ float gelu_fast(float x) { float g; return x * normal_cdf_fast(x, g); }
+// GELU(x) and GELU'(x) from one CDF / exponential evaluation (the forward pass saves GELU' for backward)
+__device__ __forceinline__ float gelu_and_grad_fast(float x, float& grad) {
+    float g;
+    const float cdf = normal_cdf_fast(x, g);
+    grad = fmaf(x * 0.39894228040143267794f, g, cdf);
+    return x * cdf;
+}
 __device__ __forceinline__ float dgelu_fast(float x) {
     float g;
     const float cdf = normal_cdf_fast(x, g);
@@ -169,9 +176,10 @@ __device__ __forceinline__ float epilogue_value(const Epilogue& e, float acc, in
                                                 const TC* c_old_ptr) {
     float v = acc * e.alpha;
     if (e.bias) v += __ldg(e.bias + col);
-    if (e.aux_out) reinterpret_cast<TC*>(e.aux_out)[row * e.ld_aux + col] = from_f32<TC>(v);
+    if (e.aux_out) reinterpret_cast<TC*>(e.aux_out)[row * e.ld_aux + col] = from_f32<TC>((e.flags & OVQA_EPI_SAVE_DGELU) ? dgelu_erf(v) : v);
     if (e.flags & OVQA_EPI_GELU) v = gelu_erf(v);
     if (e.flags & OVQA_EPI_DGELU) v *= dgelu_erf(to_f32<TC>(reinterpret_cast<const TC*>(e.aux_in)[row * e.ld_aux + col]));
+    if (e.flags & OVQA_EPI_MUL_AUX) v *= to_f32<TC>(reinterpret_cast<const TC*>(e.aux_in)[row * e.ld_aux + col]);
     if (e.dropout_p > 0.0f) v *= dropout_scale((uint64_t)(row * n_cols + col), e.dropout_p, 1.0f / (1.0f - e.dropout_p), e.seed, effective_offset(e.offset, e.offset_base));
     if (e.residual) v += __ldg(e.residual + row * e.ld_res + col);
     if (e.beta != 0.0f && c_old_ptr) v += e.beta * to_f32<TC>(*c_old_ptr);

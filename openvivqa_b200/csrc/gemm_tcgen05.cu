@@ -293,6 +293,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                               (!epi.c2 || (epi.ldc2 % 8 == 0 && al16(epi.c2))) && (epi.dropout_p <= 0.f || n % 8 == 0)));
         // FULL-mode features, hoisted (warp-uniform)
         const bool f_gelu = MODE == EPI_FULL && (epi.flags & OVQA_EPI_GELU), f_dgelu = MODE == EPI_FULL && (epi.flags & OVQA_EPI_DGELU);
+        const bool f_save_d = MODE == EPI_FULL && (epi.flags & OVQA_EPI_SAVE_DGELU) && (epi.flags & OVQA_EPI_GELU) && epi.aux_out;
+        const bool f_mul_aux = MODE == EPI_FULL && (epi.flags & OVQA_EPI_MUL_AUX);
         const bool f_drop = MODE == EPI_FULL && epi.dropout_p > 0.f;
         const float* __restrict__ residual = MODE == EPI_FULL ? epi.residual : nullptr;
         const TC* __restrict__ aux_in = MODE == EPI_FULL ? reinterpret_cast<const TC*>(epi.aux_in) : nullptr;
@@ -331,7 +333,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 #pragma unroll
                             for (int p = 0; p < 4; ++p)
                                 if (row_base + 8 * p < m) load8<float>(residual + (row_base + 8 * p) * ld_res + col, pre[p]);
-                        } else if (f_dgelu) {
+                        } else if (f_dgelu || f_mul_aux) {
 #pragma unroll
                             for (int p = 0; p < 4; ++p)
                                 if (row_base + 8 * p < m) load8<TC>(aux_in + (row_base + 8 * p) * ld_aux + col, pre[p]);
@@ -378,24 +380,37 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[p][j] = fmaf(v[p][j], alpha, b8[j]);
                 if constexpr (MODE == EPI_FULL) {
-                    if (aux_out) {
+                    if (f_save_d) {                                       // y = GELU(v), aux_out = GELU'(v): one CDF + one exponential for both
 #pragma unroll
-                        for (int p = 0; p < 4; ++p)
-                            if (row_base + 8 * p < m) store8<TC>(aux_out + (row_base + 8 * p) * ld_aux + col, v[p]);
+                        for (int p = 0; p < 4; ++p) {
+                            float d[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[p][j] = gelu_and_grad_fast(v[p][j], d[j]);
+                            if (row_base + 8 * p < m) store8<TC>(aux_out + (row_base + 8 * p) * ld_aux + col, d);
+                        }
+                    } else {
+                        if (aux_out) {
+#pragma unroll
+                            for (int p = 0; p < 4; ++p)
+                                if (row_base + 8 * p < m) store8<TC>(aux_out + (row_base + 8 * p) * ld_aux + col, v[p]);
+                        }
+                        if (f_gelu) {
+#pragma unroll
+                            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[p][j] = gelu_fast(v[p][j]);
+                        }
                     }
-                    if (f_gelu) {
-#pragma unroll
-                        for (int p = 0; p < 4; ++p)
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) v[p][j] = gelu_fast(v[p][j]);
-                    }
-                    if (f_dgelu) {
+                    if (f_dgelu || f_mul_aux) {
 #pragma unroll
                         for (int p = 0; p < 4; ++p) {
                             if (residual) {                               // (never together on the path) not prefetched: load now
                                 if (row_base + 8 * p < m) load8<TC>(aux_in + (row_base + 8 * p) * ld_aux + col, b8);
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) v[p][j] *= dgelu_fast(b8[j]);
+                                for (int j = 0; j < 8; ++j) v[p][j] *= f_mul_aux ? b8[j] : dgelu_fast(b8[j]);
+                            } else if (f_mul_aux) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[p][j] *= pre[p][j];
                             } else {
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) v[p][j] *= dgelu_fast(pre[p][j]);

@@ -46,10 +46,17 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_op: str = "N", b_op: str = "N", 
          beta: float = 0.0, gelu: bool = False, dgelu_aux: Optional[torch.Tensor] = None,
          aux_out: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          c2: Optional[torch.Tensor] = None, dropout_p: float = 0.0, seed: int = 0, offset: int = 0,
-         offset_base: Optional[torch.Tensor] = None, split_k: int = 1) -> torch.Tensor:
+         offset_base: Optional[torch.Tensor] = None, split_k: int = 1, save_dgelu: bool = False,
+         mul_aux: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``C[m,n] = epilogue(sum_k A[m,k] B[n,k])`` — see ``ovqa_gemm`` in include/ovqa.h.
 
-    ``a_op``/``b_op``: "N" = operand stored [rows, k]; "T" = stored [k, rows]."""
+    ``a_op``/``b_op``: "N" = operand stored [rows, k]; "T" = stored [k, rows].
+    ``save_dgelu`` (with ``gelu`` + ``aux_out``): ``aux_out`` receives GELU'(pre-activation); a later GEMM multiplies by it
+    with ``mul_aux=`` (no transcendental in the backward epilogue)."""
+    if mul_aux is not None:
+        if dgelu_aux is not None:
+            raise ValueError("gemm: dgelu_aux and mul_aux are exclusive")
+        dgelu_aux = mul_aux
     _need_cuda(a, b, out, bias, dgelu_aux, aux_out, residual, c2)
     a, b = _rowmajor2d(a, "a"), _rowmajor2d(b, "b")
     if a.dtype != b.dtype or a.dtype not in _DT:
@@ -75,7 +82,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_op: str = "N", b_op: str = "N", 
         raise ValueError("gemm: aux_in/aux_out must share a leading dimension")
     if c2 is not None and (c2.dtype != torch.bfloat16 or c2.shape != (m, n) or c2.stride(1) != 1):
         raise ValueError("gemm: c2 must be bf16 [m,n]")
-    flags = (L.EPI_GELU if gelu else 0) | (L.EPI_DGELU if dgelu_aux is not None else 0)
+    flags = (L.EPI_GELU if gelu else 0) | ((L.EPI_MUL_AUX if mul_aux is not None else L.EPI_DGELU) if dgelu_aux is not None else 0) | \
+        (L.EPI_SAVE_DGELU if save_dgelu else 0)
     aux = dgelu_aux if dgelu_aux is not None else aux_out
     L.call("ovqa_gemm", _p(a), _p(b), _p(out), m, n, k, _ld(a), _ld(b), _ld(out),
            L.OP_N if a_op == "N" else L.OP_T, L.OP_N if b_op == "N" else L.OP_T, _DT[a.dtype], _DT[out.dtype],

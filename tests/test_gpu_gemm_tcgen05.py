@@ -98,6 +98,16 @@ def test_epilogue_vector_and_ragged_paths(dev, n, odt):
     torch.nn.functional.gelu(xs).sum().backward()
     want_d = ref.to(dev) * xs.grad
     assert (d.float() - want_d).abs().max() <= tol * want_d.abs().max()
+    # the training pair: forward saves GELU'(pre) itself, backward multiplies by it
+    dsave = torch.empty((m, n), device=dev, dtype=odt)
+    out2 = ops.gemm(a, b, out_dtype=odt, bias=bias, gelu=True, aux_out=dsave, save_dgelu=True, residual=res)
+    assert torch.equal(out2, out)
+    xs2 = want_pre.clone().requires_grad_(True)
+    torch.nn.functional.gelu(xs2).sum().backward()
+    assert (dsave.float() - xs2.grad).abs().max() <= (1e-2 if odt == torch.bfloat16 else 1e-5)
+    d2 = ops.gemm(a, b, out_dtype=odt, mul_aux=dsave)
+    want_d2 = ref.to(dev) * dsave.float()
+    assert (d2.float() - want_d2).abs().max() <= tol * want_d2.abs().max()
 
 
 def test_fast_gelu_matches_erf_gelu(dev):

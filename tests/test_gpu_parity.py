@@ -109,6 +109,15 @@ def test_gemm_fp32_epilogue(dev):
     F.gelu(x).backward(dy @ W)
     out2 = ops.gemm(dy.to(dev), W.to(dev), b_op="T", dgelu_aux=pre2.to(dev))
     assert rel_err(out2, x.grad) < 1e-5
+    # the training pair: forward saves GELU'(pre) in aux_out, backward multiplies by the saved tensor
+    dsave = torch.empty((m, n), device=dev)
+    out_s = ops.gemm(A.to(dev), B.to(dev), bias=bias.to(dev), gelu=True, aux_out=dsave, save_dgelu=True, residual=res.to(dev))
+    xp = pre.clone().requires_grad_(True)
+    F.gelu(xp).sum().backward()
+    assert torch.equal(out_s, out) and rel_err(dsave, xp.grad) < 1e-5
+    gsave = torch.randn((m, 40), generator=g)
+    out_m = ops.gemm(dy.to(dev), W.to(dev), b_op="T", mul_aux=gsave.to(dev))
+    assert rel_err(out_m, (dy @ W) * gsave) < 1e-5
     # split-k accumulates into fp32
     out3 = ops.gemm(A.t().contiguous().to(dev), B.t().contiguous().to(dev), a_op="T", b_op="T", split_k=3)
     assert rel_err(out3, A @ B.t()) < 1e-5
