@@ -136,10 +136,12 @@ int ovqa_layernorm_fwd(const float* x, const float* residual, const float* gamma
 
 /* dx = LN backward(dy; x, mean, rstd, gamma) [+ dx_add];  dgamma/dbeta are ACCUMULATED into (fp32 [D]).
  * dx_bf16 optional second output (feeds the following bf16 dgrad/wgrad GEMMs), optionally with the
- * forward dropout mask re-applied (dropout_p, seed, offset over the [rows, D] index space). */
+ * forward dropout mask re-applied (dropout_p, seed, offset over the [rows, D] index space).
+ * dbias optional (fp32 [D], ACCUMULATED into): column sums of the masked dx, i.e. the bias gradient of the
+ * GEMM whose output fed this LayerNorm (fc_o / fc2) — saves a separate pass over dx. */
 int ovqa_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
                        const float* gamma, const float* dx_add,
-                       float* dx, void* dx_bf16, float* dgamma, float* dbeta,
+                       float* dx, void* dx_bf16, float* dgamma, float* dbeta, float* dbias,
                        int64_t rows, int64_t D,
                        float dropout_p, uint64_t seed, uint64_t offset, const uint64_t* offset_base, void* stream);
 

@@ -34,7 +34,7 @@ _PROTOS = {
                       _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
                       _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _f32, _i32, _vp, _vp, _vp],
     "ovqa_layernorm_fwd": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, _vp],
-    "ovqa_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, _u64, _u64, _vp, _vp],
+    "ovqa_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, _u64, _u64, _vp, _vp],
     "ovqa_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
     "ovqa_cast_bf16_to_f32": [_vp, _vp, _i64, _vp],
     "ovqa_colsum": [_vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp],

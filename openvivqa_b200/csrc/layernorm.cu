@@ -67,18 +67,20 @@ __global__ void __launch_bounds__(kRowsPerCta * 32)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
                      const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dx_add,
                      float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                     int64_t rows, int D, float p, float inv_keep, uint64_t seed, uint64_t offset_, const uint64_t* offset_base) {
+                     float* __restrict__ dbias, int64_t rows, int D, float p, float inv_keep, uint64_t seed, uint64_t offset_,
+                     const uint64_t* offset_base) {
     __shared__ float red[kRowsPerCta][32 * 4 + 1];
     const uint64_t offset = p > 0.f ? effective_offset(offset_, offset_base) : 0;
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int nvec = D / 4;
-    float4 g[NV], ag[NV], ab[NV];
+    float4 g[NV], ag[NV], ab[NV], ad[NV];      // gamma; column sums for dgamma, dbeta and (masked dx) the preceding GEMM's bias grad
 #pragma unroll
     for (int t = 0; t < NV; ++t) {
         const int c = lane + 32 * t;
         g[t] = c < nvec ? ld4(gamma + 4 * c) : make_float4(0, 0, 0, 0);
         ag[t] = make_float4(0, 0, 0, 0);
         ab[t] = make_float4(0, 0, 0, 0);
+        ad[t] = make_float4(0, 0, 0, 0);
     }
     for (int64_t row = (int64_t)blockIdx.x * kRowsPerCta + warp; row < rows; row += (int64_t)gridDim.x * kRowsPerCta) {
         const float mu = mean[row], rs = rstd[row];
@@ -108,25 +110,26 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
                                        rs * (d[t].z - s1 - xh[t].z * s2), rs * (d[t].w - s1 - xh[t].w * s2));
                 if (dx_add) o = add4(o, ld4(dx_add + row * D + 4 * c));
                 if (dx) *reinterpret_cast<float4*>(dx + row * D + 4 * c) = o;
-                if (dx16) {
+                if (dx16 || dbias) {
                     if (p > 0.f) {
                         const float4 s4 = dropout_scale4((uint64_t)(row * D + 4 * c), p, inv_keep, seed, offset);
                         o = make_float4(o.x * s4.x, o.y * s4.y, o.z * s4.z, o.w * s4.w);
                     }
-                    *reinterpret_cast<uint2*>(dx16 + row * D + 4 * c) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+                    if (dx16) *reinterpret_cast<uint2*>(dx16 + row * D + 4 * c) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+                    if (dbias) ad[t] = add4(ad[t], o);
                 }
             }
         }
     }
-    // dgamma / dbeta: reduce the 4 warps through smem, then one atomicAdd per column per CTA
-    if (!dgamma && !dbeta) return;
-    for (int pass = 0; pass < 2; ++pass) {
-        float* dst = pass == 0 ? dgamma : dbeta;
+    // dgamma / dbeta / dbias: reduce the 4 warps through smem, then one atomicAdd per column per CTA
+    if (!dgamma && !dbeta && !dbias) return;
+    for (int pass = 0; pass < 3; ++pass) {
+        float* dst = pass == 0 ? dgamma : pass == 1 ? dbeta : dbias;
         if (!dst) continue;
 #pragma unroll
         for (int t = 0; t < NV; ++t) {
             const int c = lane + 32 * t;
-            const float4 a = pass == 0 ? ag[t] : ab[t];
+            const float4 a = pass == 0 ? ag[t] : pass == 1 ? ab[t] : ad[t];
             __syncthreads();
             red[warp][lane * 4 + 0] = a.x; red[warp][lane * 4 + 1] = a.y; red[warp][lane * 4 + 2] = a.z; red[warp][lane * 4 + 3] = a.w;
             __syncthreads();
@@ -234,8 +237,9 @@ extern "C" int ovqa_layernorm_fwd(const float* x, const float* residual, const f
 }
 
 extern "C" int ovqa_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
-                                  const float* dx_add, float* dx, void* dx_bf16, float* dgamma, float* dbeta, int64_t rows,
-                                  int64_t D, float dropout_p, uint64_t seed, uint64_t offset, const uint64_t* offset_base, void* stream) {
+                                  const float* dx_add, float* dx, void* dx_bf16, float* dgamma, float* dbeta, float* dbias,
+                                  int64_t rows, int64_t D, float dropout_p, uint64_t seed, uint64_t offset, const uint64_t* offset_base,
+                                  void* stream) {
     if (!dy || !x || !mean || !rstd || !gamma || rows < 0 || D <= 0) return OVQA_ERR_BAD_ARG;
     if (D % 4 != 0 || D > kMaxVec * 128) return OVQA_ERR_BAD_SHAPE;
     if (dropout_p < 0.f || dropout_p >= 1.f) return OVQA_ERR_BAD_ARG;
@@ -247,7 +251,7 @@ extern "C" int ovqa_layernorm_bwd(const float* dy, const float* x, const float* 
     if (g > cap) g = cap;
     const int nv = (int)((D + 127) / 128);
     OVQA_LN_DISPATCH(layernorm_bwd_kernel)<<<(unsigned)g, kRowsPerCta * 32, 0, (cudaStream_t)stream>>>(
-        dy, x, mean, rstd, gamma, dx_add, dx, (__nv_bfloat16*)dx_bf16, dgamma, dbeta, rows, (int)D, dropout_p,
+        dy, x, mean, rstd, gamma, dx_add, dx, (__nv_bfloat16*)dx_bf16, dgamma, dbeta, dbias, rows, (int)D, dropout_p,
         dropout_p > 0.f ? 1.0f / (1.0f - dropout_p) : 1.0f, seed, offset, offset_base);
     OVQA_LAUNCH_OK();
     return OVQA_OK;

@@ -233,12 +233,11 @@ class _MHAFn(torch.autograd.Function):
         hk, hv = h * dk, h * dv
         p, seed, off, rng_base = ctx.p, ctx.seed, ctx.off, ctx.rng_base
         # LayerNorm backward; the bf16 copy already carries the output-projection dropout mask
-        ds, ds16, dgamma, dbeta = ops.layernorm_bwd(dy.reshape(B * Lq, D), s, mean, rstd, gamma, want_bf16=(mode == "bf16"),
-                                                    dropout_p=p, seed=seed, offset=off, offset_base=rng_base)
-        d_o = _masked_operand(ds, ds16, mode, p, seed, off, rng_base)             # grad of the fc_o output
+        ds, ds16, dgamma, dbeta, dbo = ops.layernorm_bwd(dy.reshape(B * Lq, D), s, mean, rstd, gamma, want_bf16=(mode == "bf16"),
+                                                         dropout_p=p, seed=seed, offset=off, offset_base=rng_base, want_dbias=True)
+        d_o = _masked_operand(ds, ds16, mode, p, seed, off, rng_base)             # grad of the fc_o output (its column sums: dbo)
         ctx2 = att_ctx.view(B * Lq, hv)
         dwo = _wgrad(d_o, ctx2)
-        dbo = ops.colsum(d_o)
         dctx = ops.gemm(d_o, weights.get([wo], cdt), b_op="T", out_dtype=cdt).view(B, Lq, hv)
         geo = ops.GeoParams(boxes, geo_w.detach(), geo_b.detach(), cfg["geo_trig"]) if boxes is not None else None
         gdw = torch.zeros_like(geo_w, dtype=torch.float32) if geo is not None else None
@@ -332,10 +331,10 @@ class _PWFFFn(torch.autograd.Function):
         rng_base = ctx.rng_base
         cdt = _cdt(mode)
         D = x2.shape[1]
-        ds, ds16, dgamma, dbeta = ops.layernorm_bwd(dy.reshape(-1, D), s, mean, rstd, gamma, want_bf16=(mode == "bf16"),
-                                                    dropout_p=p, seed=s2, offset=o2, offset_base=rng_base)
-        d2 = _masked_operand(ds, ds16, mode, p, s2, o2, rng_base)                   # grad of the fc2 output
-        dw2, db2 = _wgrad(d2, hact), ops.colsum(d2)
+        ds, ds16, dgamma, dbeta, db2 = ops.layernorm_bwd(dy.reshape(-1, D), s, mean, rstd, gamma, want_bf16=(mode == "bf16"),
+                                                         dropout_p=p, seed=s2, offset=o2, offset_base=rng_base, want_dbias=True)
+        d2 = _masked_operand(ds, ds16, mode, p, s2, o2, rng_base)                   # grad of the fc2 output (its column sums: db2)
+        dw2 = _wgrad(d2, hact)
         # grad of the fc1 pre-activation: (d2 W2) * dropout1 mask * gelu'(pre) — the forward saved gelu' itself, so the dgrad
         # epilogue is a plain multiply
         dpre = ops.gemm(d2, weights.get([w2], cdt), b_op="T", out_dtype=cdt, mul_aux=pre, dropout_p=p, seed=s1, offset=o1, offset_base=rng_base)

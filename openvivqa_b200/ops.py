@@ -218,21 +218,31 @@ def layernorm_fwd(x, gamma, beta, *, residual=None, post_add=None, eps: float = 
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, *, dx_add=None, want_bf16: bool = False, dropout_p: float = 0.0,
-                  seed: int = 0, offset: int = 0, offset_base=None, dgamma=None, dbeta=None):
+                  seed: int = 0, offset: int = 0, offset_base=None, dgamma=None, dbeta=None, want_dbias: bool = False):
+    """Returns (dx, dx_bf16|None, dgamma, dbeta[, dbias]).  ``want_dbias``: also the column sums of the (dropout-masked) dx —
+    the bias gradient of the GEMM that produced this LayerNorm's input."""
     _need_cuda(dy, x, mean, rstd, gamma)
     D = x.shape[-1]
     dy2, x2 = dy.reshape(-1, D).contiguous().float(), x.reshape(-1, D)
     rows = x2.shape[0]
     dx = torch.empty_like(x2)
     dx16 = torch.empty(x2.shape, device=x.device, dtype=torch.bfloat16) if want_bf16 else None
-    if dgamma is None:
-        dgamma = torch.zeros((D,), device=x.device, dtype=torch.float32)
-    if dbeta is None:
-        dbeta = torch.zeros((D,), device=x.device, dtype=torch.float32)
+    dbias = None
+    if dgamma is None and dbeta is None:
+        acc = torch.zeros((3 if want_dbias else 2, D), device=x.device, dtype=torch.float32)     # one fill for all accumulators
+        dgamma, dbeta = acc[0], acc[1]
+        dbias = acc[2] if want_dbias else None
+    else:
+        if dgamma is None:
+            dgamma = torch.zeros((D,), device=x.device, dtype=torch.float32)
+        if dbeta is None:
+            dbeta = torch.zeros((D,), device=x.device, dtype=torch.float32)
+        dbias = torch.zeros((D,), device=x.device, dtype=torch.float32) if want_dbias else None
     L.call("ovqa_layernorm_bwd", _p(dy2), _p(x2), _p(mean), _p(rstd), _p(gamma),
-           None if dx_add is None else _p(dx_add.reshape(-1, D).contiguous()), _p(dx), _p(dx16), _p(dgamma), _p(dbeta),
+           None if dx_add is None else _p(dx_add.reshape(-1, D).contiguous()), _p(dx), _p(dx16), _p(dgamma), _p(dbeta), _p(dbias),
            rows, D, float(dropout_p), int(seed), int(offset), _p(offset_base), _stream())
-    return dx.view(x.shape), (None if dx16 is None else dx16.view(x.shape)), dgamma, dbeta
+    out = (dx.view(x.shape), (None if dx16 is None else dx16.view(x.shape)), dgamma, dbeta)
+    return out + (dbias,) if want_dbias else out
 
 
 def to_bf16(x: torch.Tensor) -> torch.Tensor:

@@ -483,6 +483,14 @@ def test_layernorm_fwd_bwd(dev, D):
     assert rel_err(y, ref) < 1e-5 and abs_err(y16, ref.detach().bfloat16()) <= 0.04 and rel_err(s, x + r) < 1e-6
     dx, _, dg, db = ops.layernorm_bwd(dy.to(dev), s, mean, rstd, gamma.to(dev))
     assert rel_err(dx, xs.grad) < 1e-4 and rel_err(dg, gm.grad) < 1e-4 and rel_err(db, bt.grad) < 1e-4
+    # fused bias gradient of the producing GEMM: column sums of the dropout-masked dx (and the bf16 copy carries the same mask)
+    p, seed, off = 0.25, 77, 1000
+    keep = ops.dropout_keep_mask(37 * D, p, seed, off, dev).view(37, D)
+    dx2, dx16, dg2, db2, dbias = ops.layernorm_bwd(dy.to(dev), s, mean, rstd, gamma.to(dev), want_bf16=True, dropout_p=p, seed=seed, offset=off,
+                                                   want_dbias=True)
+    masked = dx.to(dev) * keep / (1 - p)
+    assert torch.equal(dx2, dx) and rel_err(dg2, dg) < 1e-6 and rel_err(db2, db) < 1e-6
+    assert rel_err(dbias, masked.sum(0)) < 1e-4 and abs_err(dx16, masked.bfloat16()) <= 0.02 * masked.abs().max().item()
     # eps of the BERT layers
     y2, *_ = ops.layernorm_fwd(x.to(dev), gamma.to(dev), beta.to(dev), eps=1e-12)
     assert rel_err(y2, F.layer_norm(x, (D,), gamma, beta, 1e-12)) < 1e-5
