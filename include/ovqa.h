@@ -160,6 +160,16 @@ int ovqa_dropout_apply(const float* x, void* y, int64_t n, float p, uint64_t see
                        const uint64_t* offset_base, int out_dtype, void* stream);
 /* *word += delta on the device (one thread): advances the dropout offset base between CUDA-graph replays. */
 int ovqa_advance_u64(uint64_t* word, uint64_t delta, void* stream);
+/* Many contiguous fp32 -> {fp32, bf16} copies in ONE launch: the once-per-optimiser-step staging of the GEMM operands
+ * (bf16 weight copies, row-concatenated [Wq;Wk;Wv] / [bq;bk;bv]).  `descs` is a DEVICE array of n_desc descriptors. */
+typedef struct {
+    const float* src;       /* device, fp32, n elements                        */
+    void*        dst;       /* device, dst_dtype, n elements (may be an offset into a larger buffer) */
+    int64_t      n;
+    int32_t      dst_dtype; /* OVQA_F32 | OVQA_BF16 */
+    int32_t      reserved;
+} ovqa_stage_desc;
+int ovqa_stage_many(const ovqa_stage_desc* descs, int64_t n_desc, void* stream);
 /* y = a + b (fp32, n elements) */
 int ovqa_add_f32(const float* a, const float* b, float* y, int64_t n, void* stream);
 

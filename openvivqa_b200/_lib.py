@@ -41,6 +41,7 @@ _PROTOS = {
     "ovqa_add_f32": [_vp, _vp, _vp, _i64, _vp],
     "ovqa_dropout_apply": [_vp, _vp, _i64, _f32, _u64, _u64, _vp, _i32, _vp],
     "ovqa_advance_u64": [_vp, _u64, _vp],
+    "ovqa_stage_many": [_vp, _i64, _vp],
     "ovqa_box_geometry_bias": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp],
     "ovqa_ptr_scores": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _i32, _i32, _vp],
     "ovqa_prev_pred_embed": [_vp] * 12 + [_i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _vp],

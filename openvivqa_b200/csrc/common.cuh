@@ -100,15 +100,16 @@ __device__ __forceinline__ float dgelu_fast(float x) {
 }
 
 // ----------------------------------------------------------------------------- counter-based dropout RNG
-// Philox4x32-10 keyed by `seed`; one call serves EIGHT consecutive elements: counter = offset + element_index/8,
+// Philox4x32-7 (the round count the Random123 authors give as the minimum passing BigCrush; the mask only has to be
+// uncorrelated, and the generator runs inside GEMM epilogues) keyed by `seed`; one call serves EIGHT consecutive elements: counter = offset + element_index/8,
 // element (index % 8) takes the 16-bit field (index % 8) of the 128 random bits and is kept iff field >= round(p * 65536)
 // (drop probability quantised to 1/65536).  Stateless, so the backward pass regenerates the forward mask from
 // (seed, offset) — no mask tensor is ever stored.
-__device__ __forceinline__ uint4 philox4x32_10(uint64_t ctr, uint64_t key) {
+__device__ __forceinline__ uint4 philox4x32(uint64_t ctr, uint64_t key) {
     uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0x243F6A88u, c3 = 0x85A308D3u;
     uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < 7; ++r) {
         const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
         c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
@@ -123,12 +124,12 @@ __device__ __forceinline__ uint32_t philox_field16(const uint4& r, uint32_t lane
 }
 // keep-scale for element `idx`: 1/(1-p) if kept else 0.
 __device__ __forceinline__ float dropout_scale(uint64_t idx, float p, float inv_keep, uint64_t seed, uint64_t offset) {
-    const uint4 r = philox4x32_10(offset + (idx >> 3), seed);
+    const uint4 r = philox4x32(offset + (idx >> 3), seed);
     return philox_field16(r, (uint32_t)(idx & 7)) >= dropout_threshold(p) ? inv_keep : 0.0f;
 }
 // eight consecutive elements starting at idx (idx % 8 == 0): one Philox call
 __device__ __forceinline__ void dropout_scale8(float (&o)[8], uint64_t idx, float p, float inv_keep, uint64_t seed, uint64_t offset) {
-    const uint4 r = philox4x32_10(offset + (idx >> 3), seed);
+    const uint4 r = philox4x32(offset + (idx >> 3), seed);
     const uint32_t thr = dropout_threshold(p);
     const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
@@ -139,7 +140,7 @@ __device__ __forceinline__ void dropout_scale8(float (&o)[8], uint64_t idx, floa
 }
 // four consecutive elements starting at idx (idx % 4 == 0): the matching half of the group's Philox call
 __device__ __forceinline__ float4 dropout_scale4(uint64_t idx, float p, float inv_keep, uint64_t seed, uint64_t offset) {
-    const uint4 r = philox4x32_10(offset + (idx >> 3), seed);
+    const uint4 r = philox4x32(offset + (idx >> 3), seed);
     const uint32_t thr = dropout_threshold(p);
     const bool hi = (idx & 4) != 0;
     const uint32_t w0 = hi ? r.z : r.x, w1 = hi ? r.w : r.y;

@@ -2,9 +2,9 @@
 // in shared memory by TMA (cp.async.bulk.tensor, SWIZZLE_128B), persistent over output tiles with a
 // double-buffered TMEM accumulator so the epilogue of tile i overlaps the mainloop of tile i+1.
 //
-// Warp roles (320 threads, 1 CTA/SM):  warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator +
-// MMA issuer (one elected lane), warps 2..9 = epilogue: two warps per TMEM lane quadrant, each owning every other
-// 32-column chunk.  A chunk goes TMEM -> registers (row per lane) -> XOR-swizzled shared-memory scratch -> registers
+// Warp roles (576 threads, 1 CTA/SM):  warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator +
+// MMA issuer (one elected lane), warps 2..17 = epilogue: four warps per TMEM lane quadrant, each owning every fourth
+// 32-column chunk (the fused epilogues are latency/issue bound: 16 warps hide what 8 could not — profiles/r01d).  A chunk goes TMEM -> registers (row per lane) -> XOR-swizzled shared-memory scratch -> registers
 // (8 consecutive columns per lane, 4 lanes per row), so every global access of the fused epilogue (bias, saved
 // pre-activation, residual, C, bf16 copy, split-K reductions) is a coalesced 16-byte vector covering whole 128-byte
 // row segments, one Philox call serves a lane's 8 elements, and address arithmetic is amortised over 8 outputs.
@@ -29,13 +29,15 @@ namespace {
 constexpr int BM = 128;          // UMMA M (cta_group::1)
 constexpr int BK = 64;           // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;
 constexpr int kThreads = 64 + kEpiWarps * 32;
+constexpr int kRegBoundThreads = 640;   // __launch_bounds__ figure: 65536/640 -> <= 96 registers per thread, which is what 5 warps per SM
+                                        // sub-partition (18 warps over 4 partitions) can actually be given
 constexpr int kAccStages = 2;
 constexpr int kScratchBytes = kEpiWarps * 32 * 32 * 4;   // one 32x32 fp32 chunk per epilogue warp
 
 template <int BN> struct Cfg {
-    static constexpr int kStages = BN == 256 ? 4 : 6;
+    static constexpr int kStages = BN == 256 ? 3 : 5;
     static constexpr int kABytes = BM * BK * 2;
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
@@ -165,7 +167,7 @@ __device__ __noinline__ void epilogue_scalar(const Epilogue& epi, float acc, int
 
 // ----------------------------------------------------------------------------- kernel
 template <int BN, bool A_MN, bool B_MN, typename TC, int MODE>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kRegBoundThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, TC* __restrict__ C,
                     int64_t m, int64_t n, int64_t k, int64_t ldc, Epilogue epi, int split_k) {
     using cfg = Cfg<BN>;
@@ -273,9 +275,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue warps 2..9
+        // ------------------------------------------------------------------ epilogue warps 2..17
         const int quad = warp % 4;                        // tcgen05.ld: warp w may touch TMEM lanes [32*(w%4), +32)
-        const int half = (warp - 2) / 4;                  // which 32-column chunks of the tile this warp owns
+        const int slot = (warp - 2) / 4;                  // which 32-column chunks of the tile this warp owns: slot, slot+4, ...
         const int rr = lane / 4, c8 = lane % 4;           // read-back mapping: row rr (+8 per pass), columns [8*c8, +8)
         // scratch: 32 rows x 8 granules of 16 B per warp, granule index XOR (row & 7)  (conflict-free both ways)
         const uint32_t sc = smem_u32(scratch) + (uint32_t)(warp - 2) * 4096u;
@@ -314,147 +316,105 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             const int64_t row_base = (int64_t)mt * BM + quad * 32 + rr;          // + 8 * pass
             const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-            for (int c0 = half * 32; c0 < BN; c0 += 64) {
+            for (int c0 = slot * 32; c0 < BN; c0 += 128) {
                 const int64_t col0 = (int64_t)nt * BN + c0;
                 if (col0 >= n) break;                                     // warp-uniform
                 const int64_t col = col0 + c8 * 8;
                 const bool fast = vec_ok && (col0 + 32 <= n);             // warp-uniform: whole chunk on the vector path
-                // operands that do not depend on the accumulator are requested first: their latency hides behind the
-                // TMEM read and the shared-memory transposition
-                float pre[4][8], b8[8];                                   // pre: residual rows, else the saved pre-activation (DGELU)
-                if (fast) {
-                    if (bias) load8<float>(bias + col, b8);
-                    else {
+                float b8[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) b8[j] = 0.f;
-                    }
-                    if constexpr (MODE == EPI_FULL) {
-                        if (residual) {
+                for (int j = 0; j < 8; ++j) b8[j] = 0.f;
+                if (fast && bias) load8<float>(bias + col, b8);
+                {   // TMEM -> registers (row per lane) -> swizzled scratch
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(t_row + (uint32_t)c0, r);
+                    tmem_ld_wait();
 #pragma unroll
-                            for (int p = 0; p < 4; ++p)
-                                if (row_base + 8 * p < m) load8<float>(residual + (row_base + 8 * p) * ld_res + col, pre[p]);
-                        } else if (f_dgelu || f_mul_aux) {
-#pragma unroll
-                            for (int p = 0; p < 4; ++p)
-                                if (row_base + 8 * p < m) load8<TC>(aux_in + (row_base + 8 * p) * ld_aux + col, pre[p]);
-                        }
-                    }
+                    for (int g = 0; g < 8; ++g)
+                        sts128(st_row + (((uint32_t)g ^ st_x) << 4), __uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
+                               __uint_as_float(r[4 * g + 3]));
                 }
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(t_row + (uint32_t)c0, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int g = 0; g < 8; ++g)
-                    sts128(st_row + (((uint32_t)g ^ st_x) << 4), __uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
-                           __uint_as_float(r[4 * g + 3]));
                 __syncwarp();
-                float v[4][8];
+                // four passes of 8 rows: each lane finishes 8 consecutive columns of one row per pass, every feature applied to
+                // those 8 values before the next pass (small live state: 16 epilogue warps share the register file)
 #pragma unroll
                 for (int p = 0; p < 4; ++p) {
-                    lds128(ld_lo + p * 1024, v[p][0], v[p][1], v[p][2], v[p][3]);
-                    lds128(ld_hi + p * 1024, v[p][4], v[p][5], v[p][6], v[p][7]);
-                }
-                __syncwarp();                                             // scratch is rewritten by the next chunk
-                if (!fast) {                                              // ragged tail / unaligned pitches
-#pragma unroll
-                    for (int p = 0; p < 4; ++p)
+                    const int64_t row = row_base + 8 * p;
+                    const bool row_ok = row < m;
+                    float pre[8];                                         // residual row, else the saved GELU' / pre-activation
+                    if constexpr (MODE == EPI_FULL) {
+                        if (fast && row_ok) {
+                            if (residual) load8<float>(residual + row * ld_res + col, pre);
+                            else if (f_dgelu || f_mul_aux) load8<TC>(aux_in + row * ld_aux + col, pre);
+                        }
+                    }
+                    float v[8];
+                    lds128(ld_lo + p * 1024, v[0], v[1], v[2], v[3]);
+                    lds128(ld_hi + p * 1024, v[4], v[5], v[6], v[7]);
+                    if (!fast) {                                          // ragged tail / unaligned pitches
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
-                            if (row_base + 8 * p < m && col + j < n) epilogue_scalar<TC>(epi, v[p][j], row_base + 8 * p, col + j, n, C, ldc, split_k);
-                    continue;
-                }
-                if constexpr (MODE == EPI_SPLITK) {
-                    if constexpr (sizeof(TC) == 4) {
-#pragma unroll
-                        for (int p = 0; p < 4; ++p) {
-                            if (row_base + 8 * p >= m) continue;
-                            float* cp = reinterpret_cast<float*>(C) + (row_base + 8 * p) * ldc + col;
-                            atomicAdd(reinterpret_cast<float4*>(cp), make_float4(v[p][0] * alpha, v[p][1] * alpha, v[p][2] * alpha, v[p][3] * alpha));
-                            atomicAdd(reinterpret_cast<float4*>(cp + 4), make_float4(v[p][4] * alpha, v[p][5] * alpha, v[p][6] * alpha, v[p][7] * alpha));
-                        }
+                            if (row_ok && col + j < n) epilogue_scalar<TC>(epi, v[j], row, col + j, n, C, ldc, split_k);
+                        continue;
                     }
-                    continue;
-                }
+                    if (!row_ok) continue;
+                    if constexpr (MODE == EPI_SPLITK) {
+                        if constexpr (sizeof(TC) == 4) {
+                            float* cp = reinterpret_cast<float*>(C) + row * ldc + col;
+                            atomicAdd(reinterpret_cast<float4*>(cp), make_float4(v[0] * alpha, v[1] * alpha, v[2] * alpha, v[3] * alpha));
+                            atomicAdd(reinterpret_cast<float4*>(cp + 4), make_float4(v[4] * alpha, v[5] * alpha, v[6] * alpha, v[7] * alpha));
+                        }
+                        continue;
+                    }
 #pragma unroll
-                for (int p = 0; p < 4; ++p)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) v[p][j] = fmaf(v[p][j], alpha, b8[j]);
-                if constexpr (MODE == EPI_FULL) {
-                    if (f_save_d) {                                       // y = GELU(v), aux_out = GELU'(v): one CDF + one exponential for both
-#pragma unroll
-                        for (int p = 0; p < 4; ++p) {
+                    for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], alpha, b8[j]);
+                    if constexpr (MODE == EPI_FULL) {
+                        if (f_save_d) {                                   // y = GELU(v), aux_out = GELU'(v): one CDF + one exponential for both
                             float d[8];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) v[p][j] = gelu_and_grad_fast(v[p][j], d[j]);
-                            if (row_base + 8 * p < m) store8<TC>(aux_out + (row_base + 8 * p) * ld_aux + col, d);
-                        }
-                    } else {
-                        if (aux_out) {
+                            for (int j = 0; j < 8; ++j) v[j] = gelu_and_grad_fast(v[j], d[j]);
+                            store8<TC>(aux_out + row * ld_aux + col, d);
+                        } else {
+                            if (aux_out) store8<TC>(aux_out + row * ld_aux + col, v);
+                            if (f_gelu) {
 #pragma unroll
-                            for (int p = 0; p < 4; ++p)
-                                if (row_base + 8 * p < m) store8<TC>(aux_out + (row_base + 8 * p) * ld_aux + col, v[p]);
-                        }
-                        if (f_gelu) {
-#pragma unroll
-                            for (int p = 0; p < 4; ++p)
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) v[p][j] = gelu_fast(v[p][j]);
-                        }
-                    }
-                    if (f_dgelu || f_mul_aux) {
-#pragma unroll
-                        for (int p = 0; p < 4; ++p) {
-                            if (residual) {                               // (never together on the path) not prefetched: load now
-                                if (row_base + 8 * p < m) load8<TC>(aux_in + (row_base + 8 * p) * ld_aux + col, b8);
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) v[p][j] *= f_mul_aux ? b8[j] : dgelu_fast(b8[j]);
-                            } else if (f_mul_aux) {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) v[p][j] *= pre[p][j];
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) v[p][j] *= dgelu_fast(pre[p][j]);
+                                for (int j = 0; j < 8; ++j) v[j] = gelu_fast(v[j]);
                             }
                         }
-                    }
-                    if (f_drop) {
+                        if (f_dgelu || f_mul_aux) {
+                            if (residual) load8<TC>(aux_in + row * ld_aux + col, b8 /*scratch: bias already applied*/);
 #pragma unroll
-                        for (int p = 0; p < 4; ++p) {
+                            for (int j = 0; j < 8; ++j) {
+                                const float a = residual ? b8[j] : pre[j];
+                                v[j] *= f_mul_aux ? a : dgelu_fast(a);
+                            }
+                            if (residual && bias) load8<float>(bias + col, b8);   // (never together on the path) restore for the next pass
+                        }
+                        if (f_drop) {
                             float ds[8];
-                            dropout_scale8(ds, (uint64_t)((row_base + 8 * p) * n + col), drop_p, inv_keep, seed, rng_offset);
+                            dropout_scale8(ds, (uint64_t)(row * n + col), drop_p, inv_keep, seed, rng_offset);
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) v[p][j] *= ds[j];
+                            for (int j = 0; j < 8; ++j) v[j] *= ds[j];
                         }
-                    }
-                    if (residual) {
+                        if (residual) {
 #pragma unroll
-                        for (int p = 0; p < 4; ++p)
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) v[p][j] += pre[p][j];
-                    }
-                    if constexpr (sizeof(TC) == 4) {
-                        if (beta != 0.f) {
-#pragma unroll
-                            for (int p = 0; p < 4; ++p) {
-                                if (row_base + 8 * p >= m) continue;
+                            for (int j = 0; j < 8; ++j) v[j] += pre[j];
+                        }
+                        if constexpr (sizeof(TC) == 4) {
+                            if (beta != 0.f) {
                                 float o[8];
-                                load8<float>(reinterpret_cast<const float*>(C) + (row_base + 8 * p) * ldc + col, o);
+                                load8<float>(reinterpret_cast<const float*>(C) + row * ldc + col, o);
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) v[p][j] = fmaf(beta, o[j], v[p][j]);
+                                for (int j = 0; j < 8; ++j) v[j] = fmaf(beta, o[j], v[j]);
                             }
                         }
                     }
-                }
-#pragma unroll
-                for (int p = 0; p < 4; ++p)
-                    if (row_base + 8 * p < m) store8<TC>(C + (row_base + 8 * p) * ldc + col, v[p]);
-                if constexpr (MODE == EPI_FULL) {
-                    if (c2) {
-#pragma unroll
-                        for (int p = 0; p < 4; ++p)
-                            if (row_base + 8 * p < m) store8<__nv_bfloat16>(c2 + (row_base + 8 * p) * ldc2 + col, v[p]);
+                    store8<TC>(C + row * ldc + col, v);
+                    if constexpr (MODE == EPI_FULL) {
+                        if (c2) store8<__nv_bfloat16>(c2 + row * ldc2 + col, v);
                     }
                 }
+                __syncwarp();                                             // scratch is rewritten by the next chunk
             }
             tcgen05_fence_before();
             __syncwarp();

@@ -62,6 +62,14 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ resi
     }
 }
 
+// Backward.  One warp per row, persistent over rows.  The row's x and dy are brought in by cp.async into a per-warp
+// double buffer in shared memory, the NEXT row's copies being issued before the current row is reduced: two rows of loads
+// in flight per warp without holding them in registers (the kernel is DRAM-latency bound: ~150 registers allowed only 12
+// warps per SM and one row in flight each; profiles/r01d: 36 % of HBM peak, 80 % of stall samples on long_scoreboard).
+__device__ __forceinline__ void ln_cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
 template <int NV>
 __global__ void __launch_bounds__(kRowsPerCta * 32)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
@@ -69,35 +77,51 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
                      float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16, float* __restrict__ dgamma, float* __restrict__ dbeta,
                      float* __restrict__ dbias, int64_t rows, int D, float p, float inv_keep, uint64_t seed, uint64_t offset_,
                      const uint64_t* offset_base) {
-    __shared__ float red[kRowsPerCta][32 * 4 + 1];
+    extern __shared__ __align__(16) float ln_smem[];       // [kRowsPerCta][2 stages][2 (x, dy)][NV*128]; reused for the final reduction
+    constexpr int W = NV * 128;
     const uint64_t offset = p > 0.f ? effective_offset(offset_, offset_base) : 0;
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int nvec = D / 4;
-    float4 g[NV], ag[NV], ab[NV], ad[NV];      // gamma; column sums for dgamma, dbeta and (masked dx) the preceding GEMM's bias grad
+    float* wbuf = ln_smem + (size_t)warp * 4 * W;
+    float4 ag[NV], ab[NV], ad[NV];      // column sums for dgamma, dbeta and (masked dx) the producing GEMM's bias gradient
 #pragma unroll
-    for (int t = 0; t < NV; ++t) {
-        const int c = lane + 32 * t;
-        g[t] = c < nvec ? ld4(gamma + 4 * c) : make_float4(0, 0, 0, 0);
-        ag[t] = make_float4(0, 0, 0, 0);
-        ab[t] = make_float4(0, 0, 0, 0);
-        ad[t] = make_float4(0, 0, 0, 0);
-    }
-    for (int64_t row = (int64_t)blockIdx.x * kRowsPerCta + warp; row < rows; row += (int64_t)gridDim.x * kRowsPerCta) {
-        const float mu = mean[row], rs = rstd[row];
-        float4 xh[NV], d[NV];
+    for (int t = 0; t < NV; ++t) ag[t] = ab[t] = ad[t] = make_float4(0, 0, 0, 0);
+    const int64_t stride = (int64_t)gridDim.x * kRowsPerCta;
+    auto prefetch = [&](int64_t row, int stage) {
+        float* bx = wbuf + stage * 2 * W;
+#pragma unroll
+        for (int t = 0; t < NV; ++t) {
+            const int c = lane + 32 * t;
+            if (c < nvec) {
+                ln_cp_async16(bx + 4 * c, x + row * D + 4 * c);
+                ln_cp_async16(bx + W + 4 * c, dy + row * D + 4 * c);
+            }
+        }
+    };
+    int64_t row = (int64_t)blockIdx.x * kRowsPerCta + warp;
+    if (row < rows) prefetch(row, 0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int it = 0; row < rows; row += stride, ++it) {
+        const int stage = it & 1;
+        const int64_t next = row + stride;
+        if (next < rows) prefetch(next, stage ^ 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const float mu = __ldg(mean + row), rs = __ldg(rstd + row);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");          // everything but the newest group: this row has landed
+        __syncwarp();
+        const float* bx = wbuf + stage * 2 * W;
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int t = 0; t < NV; ++t) {
             const int c = lane + 32 * t;
             if (c < nvec) {
-                const float4 xv = ld4(x + row * D + 4 * c);
-                d[t] = ld4(dy + row * D + 4 * c);
-                xh[t] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-                ab[t] = add4(ab[t], d[t]);
-                ag[t] = add4(ag[t], make_float4(d[t].x * xh[t].x, d[t].y * xh[t].y, d[t].z * xh[t].z, d[t].w * xh[t].w));
-                d[t] = make_float4(d[t].x * g[t].x, d[t].y * g[t].y, d[t].z * g[t].z, d[t].w * g[t].w);  // dy * gamma
-                s1 += (d[t].x + d[t].y) + (d[t].z + d[t].w);
-                s2 += (d[t].x * xh[t].x + d[t].y * xh[t].y) + (d[t].z * xh[t].z + d[t].w * xh[t].w);
+                const float4 xv = ld4(bx + 4 * c), d = ld4(bx + W + 4 * c), g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+                const float4 xh = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+                ab[t] = add4(ab[t], d);
+                ag[t] = add4(ag[t], make_float4(d.x * xh.x, d.y * xh.y, d.z * xh.z, d.w * xh.w));
+                const float4 dg = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);  // dy * gamma
+                s1 += (dg.x + dg.y) + (dg.z + dg.w);
+                s2 += (dg.x * xh.x + dg.y * xh.y) + (dg.z * xh.z + dg.w * xh.w);
             }
         }
         s1 = warp_sum(s1) / (float)D;
@@ -106,8 +130,10 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
         for (int t = 0; t < NV; ++t) {
             const int c = lane + 32 * t;
             if (c < nvec) {
-                float4 o = make_float4(rs * (d[t].x - s1 - xh[t].x * s2), rs * (d[t].y - s1 - xh[t].y * s2),
-                                       rs * (d[t].z - s1 - xh[t].z * s2), rs * (d[t].w - s1 - xh[t].w * s2));
+                const float4 xv = ld4(bx + 4 * c), d = ld4(bx + W + 4 * c), g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+                const float4 xh = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+                float4 o = make_float4(rs * (d.x * g.x - s1 - xh.x * s2), rs * (d.y * g.y - s1 - xh.y * s2),
+                                       rs * (d.z * g.z - s1 - xh.z * s2), rs * (d.w * g.w - s1 - xh.w * s2));
                 if (dx_add) o = add4(o, ld4(dx_add + row * D + 4 * c));
                 if (dx) *reinterpret_cast<float4*>(dx + row * D + 4 * c) = o;
                 if (dx16 || dbias) {
@@ -120,9 +146,12 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
                 }
             }
         }
+        __syncwarp();                                                 // this stage is overwritten by the prefetch of iteration it+1
     }
-    // dgamma / dbeta / dbias: reduce the 4 warps through smem, then one atomicAdd per column per CTA
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    // dgamma / dbeta / dbias: reduce the warps through smem (the staging buffers are free now), one atomicAdd per column per CTA
     if (!dgamma && !dbeta && !dbias) return;
+    float(*red)[32 * 4 + 1] = reinterpret_cast<float(*)[32 * 4 + 1]>(ln_smem);
     for (int pass = 0; pass < 3; ++pass) {
         float* dst = pass == 0 ? dgamma : pass == 1 ? dbeta : dbias;
         if (!dst) continue;
@@ -207,6 +236,32 @@ __global__ void dropout_mask_kernel(float* out, int64_t n, float p, uint64_t see
 }
 __global__ void advance_u64_kernel(uint64_t* word, uint64_t delta) { *word += delta; }
 
+// many (src fp32 -> dst fp32|bf16) contiguous copies in one launch: blockIdx.y = descriptor, blockIdx.x strides over it
+__global__ void stage_many_kernel(const ovqa_stage_desc* __restrict__ descs) {
+    const ovqa_stage_desc d = descs[blockIdx.y];
+    const float* __restrict__ x = d.src;
+    const int64_t n = d.n;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 8;
+    const bool vec = ((reinterpret_cast<uintptr_t>(d.src) | reinterpret_cast<uintptr_t>(d.dst)) & 15) == 0;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+        if (vec && i + 8 <= n) {
+            const float4 a = ld4(x + i), b = ld4(x + i + 4);
+            if (d.dst_dtype == OVQA_BF16) {
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(d.dst) + i) =
+                    make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+            } else {
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(d.dst) + i) = a;
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(d.dst) + i + 4) = b;
+            }
+        } else {
+            for (int64_t j = i; j < n && j < i + 8; ++j) {
+                if (d.dst_dtype == OVQA_BF16) reinterpret_cast<__nv_bfloat16*>(d.dst)[j] = __float2bfloat16_rn(x[j]);
+                else reinterpret_cast<float*>(d.dst)[j] = x[j];
+            }
+        }
+    }
+}
+
 int grid_for(int64_t work_items, int threads) {
     int64_t g = (work_items + threads - 1) / threads;
     const int64_t cap = (int64_t)sm_count() * 16;
@@ -244,13 +299,19 @@ extern "C" int ovqa_layernorm_bwd(const float* dy, const float* x, const float* 
     if (D % 4 != 0 || D > kMaxVec * 128) return OVQA_ERR_BAD_SHAPE;
     if (dropout_p < 0.f || dropout_p >= 1.f) return OVQA_ERR_BAD_ARG;
     if (rows == 0) return OVQA_OK;
-    // persistent: as many CTAs as stay resident (register-limited to ~3 per SM); every CTA ends with one atomicAdd per
-    // column into dgamma/dbeta, so fewer, longer-lived CTAs also mean fewer same-address atomics
-    int64_t g = (rows + kRowsPerCta - 1) / kRowsPerCta;
-    const int64_t cap = (int64_t)sm_count() * 3;
-    if (g > cap) g = cap;
+    // persistent: as many CTAs as stay resident; every CTA ends with one atomicAdd per column into dgamma/dbeta/dbias, so
+    // fewer, longer-lived CTAs also mean fewer same-address atomics
     const int nv = (int)((D + 127) / 128);
-    OVQA_LN_DISPATCH(layernorm_bwd_kernel)<<<(unsigned)g, kRowsPerCta * 32, 0, (cudaStream_t)stream>>>(
+    const size_t smem = (size_t)kRowsPerCta * 4 * nv * 128 * sizeof(float);      // >= the [kRowsPerCta][129] reduction scratch
+    auto kern = OVQA_LN_DISPATCH(layernorm_bwd_kernel);
+    if (smem > 48 * 1024) OVQA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    OVQA_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRowsPerCta * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    int64_t g = (rows + kRowsPerCta - 1) / kRowsPerCta;
+    const int64_t cap = (int64_t)sm_count() * per_sm;
+    if (g > cap) g = cap;
+    kern<<<(unsigned)g, kRowsPerCta * 32, smem, (cudaStream_t)stream>>>(
         dy, x, mean, rstd, gamma, dx_add, dx, (__nv_bfloat16*)dx_bf16, dgamma, dbeta, dbias, rows, (int)D, dropout_p,
         dropout_p > 0.f ? 1.0f / (1.0f - dropout_p) : 1.0f, seed, offset, offset_base);
     OVQA_LAUNCH_OK();
@@ -311,6 +372,14 @@ extern "C" int ovqa_dropout_apply(const float* x, void* y, int64_t n, float p, u
 extern "C" int ovqa_advance_u64(uint64_t* word, uint64_t delta, void* stream) {
     if (!word) return OVQA_ERR_BAD_ARG;
     advance_u64_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(word, delta);
+    OVQA_LAUNCH_OK();
+    return OVQA_OK;
+}
+extern "C" int ovqa_stage_many(const ovqa_stage_desc* descs, int64_t n_desc, void* stream) {
+    if (n_desc < 0 || (n_desc > 0 && !descs)) return OVQA_ERR_BAD_ARG;
+    if (n_desc == 0) return OVQA_OK;
+    if (n_desc > 65535) return OVQA_ERR_BAD_SHAPE;
+    stage_many_kernel<<<dim3(32, (unsigned)n_desc), 256, 0, (cudaStream_t)stream>>>(descs);
     OVQA_LAUNCH_OK();
     return OVQA_OK;
 }

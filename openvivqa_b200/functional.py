@@ -61,37 +61,97 @@ dropout_stream = _DropoutStream()
 
 
 # ----------------------------------------------------------------------------- operand staging caches
+class _Entry:
+    __slots__ = ("refs", "dtype", "dst", "ver", "epoch", "staged")
+
+
 class _WeightCache:
     """bf16 (and concatenated) copies of parameters.  Keeps fc_q/fc_k/fc_v as separately named parameters
     (state_dict compatibility) while the kernels see one fused [3*h*d, D] operand.
 
-    A copy is refreshed when (a) a parameter's version counter moves (``copy_``, ``load_state_dict``, foreach
+    A copy is refreshed when (a) a parameter's version counter or storage moves (``copy_``, ``load_state_dict``, foreach
     optimisers) or (b) ANY ``torch.optim`` optimiser has stepped since it was made: fused optimisers
     (``Adam(fused=True)``) update parameters without bumping ``_version``, so a process-wide optimiser-step
     post-hook advances ``epoch`` instead.  Code that writes parameters behind both mechanisms (raw
-    ``torch._foreach_*`` on ``.data``) must call :func:`invalidate_weight_cache`."""
+    ``torch._foreach_*`` on ``.data``) must call :func:`invalidate_weight_cache`.
+
+    Case (b) — once per training step — re-stages EVERY registered copy of the device with one ``ovqa_stage_many``
+    launch (a descriptor table of (src, dst, n, dtype) kept on the device) instead of a cat + cast per operand; the
+    copies keep their addresses, so a captured CUDA graph replays that one node."""
 
     def __init__(self):
         self._store = {}
         self.epoch = 0
+        self._tables = {}            # device -> {"dirty": bool, "host": pinned int64 (n,4), "dev": int64 (n,4), "n": int}
 
     def invalidate(self):
         self.epoch += 1
 
+    @staticmethod
+    def _versions(params):
+        return tuple((p._version, p.data_ptr()) for p in params)
+
     def get(self, params: Sequence[torch.Tensor], dtype: torch.dtype) -> torch.Tensor:
         key = tuple(id(p) for p in params) + (dtype,)
-        ver = (self.epoch,) + tuple((p._version, p.data_ptr()) for p in params)
-        hit = self._store.get(key)
-        if hit is not None and hit[0] == ver and all(r() is p for r, p in zip(hit[2], params)):
-            return hit[1]
+        e = self._store.get(key)
+        if e is not None and all(r() is p for r, p in zip(e.refs, params)):
+            if e.ver == self._versions(params):
+                if e.epoch == self.epoch:
+                    return e.dst
+                if e.staged:
+                    self._restage_all(e.dst.device)
+                    return e.dst
+        return self._refresh(key, params, dtype)
+
+    def _refresh(self, key, params, dtype):
+        """(Re)build one copy the simple way: first use, or a parameter was rewritten / re-allocated."""
         with torch.no_grad():
             src = params[0].detach() if len(params) == 1 else torch.cat([p.detach() for p in params], dim=0)
             src = src.contiguous()
             val = ops.to_bf16(src) if dtype == torch.bfloat16 else src.float()
-        self._store[key] = (ver, val, [weakref.ref(p) for p in params])
+        e = self._store.get(key)
+        direct = len(params) == 1 and val.data_ptr() == params[0].data_ptr()       # fp32 view of the parameter itself: nothing staged
+        if e is not None and not direct and e.staged and e.dst.shape == val.shape and e.dst.dtype == val.dtype and e.dst.device == val.device:
+            e.dst.copy_(val)                                                         # keep the staged address (descriptor table, graphs)
+        else:
+            e = _Entry()
+            e.dst = val
+            e.staged = (not direct) and val.is_cuda and all(p.is_contiguous() and p.dtype == torch.float32 for p in params)
+            self._store[key] = e
+        e.refs, e.dtype, e.ver, e.epoch = [weakref.ref(p) for p in params], dtype, self._versions(params), self.epoch
+        if e.staged:
+            self._tables.setdefault(val.device, {})["dirty"] = True                  # new entry or new source addresses
         if len(self._store) > 4096:
-            self._store = {k: v for k, v in self._store.items() if all(r() is not None for r in v[2])}
-        return val
+            self._prune()
+        return e.dst
+
+    def _prune(self):
+        dead = [k for k, v in self._store.items() if any(r() is None for r in v.refs)]
+        for k in dead:
+            e = self._store.pop(k)
+            if e.staged:
+                self._tables.setdefault(e.dst.device, {})["dirty"] = True
+
+    def _restage_all(self, device):
+        """One launch refreshes every staged copy on ``device`` from the current parameter values."""
+        t = self._tables.setdefault(device, {"dirty": True})
+        if any(r() is None for e in self._store.values() if e.staged and e.dst.device == device for r in e.refs):
+            self._prune()
+        entries = [e for e in self._store.values() if e.staged and e.dst.device == device]
+        if t.get("dirty", True):
+            rows = []
+            for e in entries:
+                off, esz = 0, e.dst.element_size()
+                for r in e.refs:
+                    p = r()
+                    rows.append((p.data_ptr(), e.dst.data_ptr() + off * esz, p.numel(), 1 if e.dst.dtype == torch.bfloat16 else 0))
+                    off += p.numel()
+            host = torch.tensor(rows, dtype=torch.int64).reshape(-1, 4).pin_memory()
+            t.update(host=host, dev=host.to(device, non_blocking=True), n=len(rows), dirty=False)   # host kept alive (async copy, graphs)
+        if t["n"]:
+            ops.stage_many(t["dev"], t["n"])
+        for e in entries:
+            e.epoch, e.ver = self.epoch, self._versions([r() for r in e.refs])
 
 
 weights = _WeightCache()
@@ -170,6 +230,7 @@ def linear(x, w, b=None, mode="fp32", out_dtype=torch.float32):
 class _MHAFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, queries, keys, values, mask, boxes, wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta, geo_w, geo_b, cfg):
+        ctx.set_materialize_grads(False)      # no zero-filled "gradient" tensor for the bf16 shadow output
         mode, h, dk, dv = cfg["mode"], cfg["h"], cfg["d_k"], cfg["d_v"]
         p = cfg["dropout"] if cfg["training"] else 0.0
         cdt = _cdt(mode)
@@ -221,6 +282,8 @@ class _MHAFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy, _dy16):
+        if dy is None:
+            return (None,) * 18
         cfg = ctx.cfg
         mode, h, dk, dv = cfg["mode"], cfg["h"], cfg["d_k"], cfg["d_v"]
         cdt = _cdt(mode)
@@ -296,6 +359,7 @@ def mha_block(queries, keys, values, mask, *, wq, bq, wk, bk, wv, bv, wo, bo, ga
 class _PWFFFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2, gamma, beta, cfg):
+        ctx.set_materialize_grads(False)
         mode = cfg["mode"]
         p = cfg["dropout"] if cfg["training"] else 0.0
         cdt = _cdt(mode)
@@ -325,6 +389,8 @@ class _PWFFFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy, _dy16):
+        if dy is None:
+            return (None,) * 8
         x2, pre, hact, s, mean, rstd, gamma, w1, w2 = ctx.saved_tensors
         mode, p = ctx.cfg["mode"], ctx.p
         s1, o1, s2, o2 = ctx.rng
@@ -354,6 +420,7 @@ def pwff_block(x, *, w1, b1, w2, b2, gamma, beta, mode="fp32", dropout=0.0, trai
 class _SdpaFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, mask, cfg):
+        ctx.set_materialize_grads(False)
         h, dk, dv = cfg["h"], cfg["d_k"], cfg["d_v"]
         need_grad = cfg["grad"] and any(ctx.needs_input_grad)
         out, lse, att = ops.sdpa_fwd(q, k, v, h=h, d_k=dk, d_v=dv, mask=mask, geo=cfg.get("geo"), scale=cfg["scale"],
@@ -368,6 +435,8 @@ class _SdpaFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout, _datt):
+        if dout is None:
+            return (None,) * 5
         q, k, v, mask, out, lse = ctx.saved_tensors
         cfg = ctx.cfg
         dq, dk_, dv_ = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)

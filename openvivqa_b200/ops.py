@@ -298,6 +298,15 @@ def dropout_keep_mask(n: int, p: float, seed: int, offset: int, device, offset_b
     return out
 
 
+def stage_many(table: torch.Tensor, n_desc: int):
+    """One launch for ``n_desc`` fp32 -> {fp32, bf16} copies; ``table`` is a device int64 tensor (n_desc, 4) laid out as
+    ``ovqa_stage_desc`` {src ptr, dst ptr, n, dst_dtype | reserved<<32}."""
+    _need_cuda(table)
+    if table.dtype != torch.int64 or not table.is_contiguous() or table.numel() < 4 * n_desc:
+        raise ValueError("stage_many: table must be a contiguous int64 tensor of shape (n_desc, 4)")
+    L.call("ovqa_stage_many", _p(table), int(n_desc), _stream())
+
+
 def advance_u64(word: torch.Tensor, delta: int):
     """``word[0] += delta`` on the device (word: int64 tensor of one element; the library treats it as u64)."""
     _need_cuda(word)
