@@ -155,14 +155,18 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------------------------- our arm
 class GemmMeter:
-    """CUDA-event timing of every tcgen05 GEMM launch of a step (events recorded on the launching stream).
+    """CUDA-event timing of every library launch of a step (events recorded on the launching stream): the tcgen05 GEMMs
+    (flops per launch) and the attention / LayerNorm / reduction kernels (algorithmic bytes per launch).
 
     ``external=True`` makes the events graph-capturable: inside a ``torch.cuda.graph`` capture each ``record()`` becomes an
-    event-record NODE, so replaying the instrumented graph times every GEMM exactly where it runs in the step, back to back
+    event-record NODE, so replaying the instrumented graph times every kernel exactly where it runs in the step, back to back
     with its neighbours (eager events would also measure the host's launch gaps)."""
 
     def __init__(self):
-        self.records, self.enabled, self.external = [], False, False
+        self.records, self.other, self.enabled, self.external = [], [], False, False
+
+    def _pair(self):
+        return (torch.cuda.Event(enable_timing=True, external=self.external), torch.cuda.Event(enable_timing=True, external=self.external))
 
     def install(self):
         from openvivqa_b200 import ops
@@ -174,8 +178,7 @@ class GemmMeter:
                 return orig(a, b, **kw)
             m, k = a.shape if kw.get("a_op", "N") == "N" else (a.shape[1], a.shape[0])
             n = b.shape[0] if kw.get("b_op", "N") == "N" else b.shape[1]
-            e0 = torch.cuda.Event(enable_timing=True, external=meter.external)
-            e1 = torch.cuda.Event(enable_timing=True, external=meter.external)
+            e0, e1 = meter._pair()
             e0.record()
             out = orig(a, b, **kw)
             e1.record()
@@ -187,6 +190,59 @@ class GemmMeter:
             return out
 
         ops.gemm = gemm
+
+        def nbytes(*ts):
+            return float(sum(t.numel() * t.element_size() for t in ts if t is not None))
+
+        # algorithmic HBM bytes of the memory-bound kernels: every operand once, every result once
+        def y_sdpa_fwd(a, kw, out):
+            q, k, v = a[:3]
+            h, dk, dv = kw["h"], kw["d_k"], kw["d_v"]
+            B, Lq, Lk, e = q.shape[0], q.shape[1], k.shape[1], q.element_size()
+            return e * B * h * (Lq * dk + Lk * dk + Lk * dv + Lq * dv) + 4.0 * B * Lk + 4.0 * B * h * Lq, f"sdpa_fwd B={B} Lq={Lq} Lk={Lk} h={h} d={dk}"
+
+        def y_sdpa_bwd(a, kw, out):
+            q, k, v = a[:3]
+            h, dk, dv = kw["h"], kw["d_k"], kw["d_v"]
+            B, Lq, Lk, e = q.shape[0], q.shape[1], k.shape[1], q.element_size()
+            return e * B * h * (2 * Lq * dk + 2 * Lk * dk + 2 * Lk * dv + 3 * Lq * dv) + 4.0 * B * Lk + 4.0 * B * h * Lq, f"sdpa_bwd B={B} Lq={Lq} Lk={Lk} h={h} d={dk}"
+
+        def y_ln_fwd(a, kw, out):
+            x = a[0]
+            return x.numel() * (4.0 + 4.0 + (2.0 if kw.get("want_bf16") else 0.0) + (4.0 if kw.get("residual") is not None else 0.0)), f"layernorm_fwd rows={x.numel() // x.shape[-1]} D={x.shape[-1]}"
+
+        def y_ln_bwd(a, kw, out):
+            x = a[1]
+            return x.numel() * (4.0 + 4.0 + 4.0 + (2.0 if kw.get("want_bf16") else 0.0)), f"layernorm_bwd rows={x.numel() // x.shape[-1]} D={x.shape[-1]}"
+
+        def y_in(name):
+            return lambda a, kw, out: (nbytes(a[0]), f"{name} {tuple(a[0].shape)} {str(a[0].dtype).replace('torch.', '')}")
+
+        def y_io(name):
+            return lambda a, kw, out: (nbytes(a[0]) + nbytes(out if torch.is_tensor(out) else None), f"{name} {tuple(a[0].shape)}")
+
+        table = dict(sdpa_fwd=y_sdpa_fwd, sdpa_bwd=y_sdpa_bwd, layernorm_fwd=y_ln_fwd, layernorm_bwd=y_ln_bwd, colsum=y_in("colsum"),
+                     to_bf16=y_io("to_bf16"), to_f32=y_io("to_f32"), add=y_io("add"), dropout_apply=y_io("dropout_apply"))
+        for name, fn_bytes in table.items():
+            if not hasattr(ops, name):
+                continue
+
+            def wrap(orig_fn, fn_bytes, name):
+                def w(*a, **kw):
+                    if not meter.enabled:
+                        return orig_fn(*a, **kw)
+                    e0, e1 = meter._pair()
+                    e0.record()
+                    out = orig_fn(*a, **kw)
+                    e1.record()
+                    try:
+                        y, tag = fn_bytes(a, kw, out)
+                    except Exception:  # noqa: BLE001
+                        y, tag = 0.0, name
+                    meter.other.append((e0, e1, y, name, tag))
+                    return out
+                return w
+            setattr(ops, name, wrap(getattr(ops, name), fn_bytes, name))
 
     def summary(self, steps=1):
         if not self.records:
@@ -202,6 +258,31 @@ class GemmMeter:
         table = sorted(({"gemm": k, "launches": v[0], "ms": v[1], "tflops": v[2] / (v[1] * 1e-3) / 1e12} for k, v in per.items()), key=lambda r: -r["ms"])
         return dict(launches=len(self.records), total_ms=ms, flops=fl, tflops=fl / (ms * 1e-3) / 1e12, avg_us=ms * 1e3 / len(self.records),
                     steps=steps, table=table)
+
+    def summary_other(self, hbm_gbs):
+        """Per-kernel table of the memory-bound library launches: ms, algorithmic GB/s, fraction of the measured HBM peak."""
+        per, ops_ = {}, {}
+        for e0, e1, y, name, tag in self.other:
+            t = e0.elapsed_time(e1)
+            c = per.setdefault(tag, [0, 0.0, 0.0]); c[0] += 1; c[1] += t; c[2] += y
+            o = ops_.setdefault(name, [0, 0.0, 0.0]); o[0] += 1; o[1] += t; o[2] += y
+        row = lambda k, v: {"kernel": k, "launches": v[0], "ms": round(v[1], 4), "gbs": round(v[2] / (v[1] * 1e-3) / 1e9, 1) if v[1] > 0 else None,
+                            "frac_hbm": round(v[2] / (v[1] * 1e-3) / 1e9 / hbm_gbs, 4) if v[1] > 0 else None}
+        return (sorted((row(k, v) for k, v in per.items()), key=lambda r: -r["ms"]), {k: row(k, v) for k, v in ops_.items()})
+
+
+def finish(world):
+    """End of a multi-rank run.  Communicator teardown with captured NCCL all-reduce graphs still alive was seen to hang
+    (gpurun_out/bench_n2.err, round 1): every rank synchronises, meets at a barrier and leaves without running it."""
+    if world <= 1:
+        return
+    import torch.distributed as dist
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def meter_step(meter, body, use_graph, prepare=None):
@@ -225,7 +306,7 @@ def meter_step(meter, body, use_graph, prepare=None):
         ms, how = e_a.elapsed_time(e_b), ("event-record nodes around every GEMM launch inside a second, instrumented CUDA-graph capture of the same "
                                           "step, replayed after the timed region (per-launch times of the last replay)")
     except Exception as e:  # noqa: BLE001
-        meter.records, meter.external = [], False
+        meter.records, meter.other, meter.external = [], [], False
         torch.cuda.synchronize()
         if prepare is not None:
             prepare()
@@ -367,8 +448,7 @@ def run_ours(args):
         if rank == 0:
             print(json.dumps(dict(metric="VQA samples/sec (MCAN train)", value=value, ms_per_step=ms / args.steps, gpu_launches=launches,
                                   cuda_graph=graph is not None, note="profiling run: no e2e / roofline / cpu legs")), flush=True)
-        if world > 1:
-            dist.destroy_process_group()
+        finish(world)
         return
     copy_stream = torch.cuda.Stream()
     h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
@@ -433,6 +513,16 @@ def run_ours(args):
                         unit="TFLOP/s", frac=gm["tflops"] / peak, traffic=traffic, peak_source=peaks["source"] + " (sustained cuBLAS bf16)",
                         launches=gm["launches"], avg_launch_us=gm["avg_us"], share_of_step=gm["total_ms"] / meter_ms_per_step,
                         instrumented_ms_per_step=meter_ms_per_step, how=meter_how, by_gemm=gm["table"][:12])
+        by_kernel, by_op = meter.summary_other(peaks["hbm_gbs"])
+        att = None
+        if "sdpa_fwd" in by_op and "sdpa_bwd" in by_op:
+            a_ms = by_op["sdpa_fwd"]["ms"] + by_op["sdpa_bwd"]["ms"]
+            a_y = (by_op["sdpa_fwd"]["gbs"] * by_op["sdpa_fwd"]["ms"] + by_op["sdpa_bwd"]["gbs"] * by_op["sdpa_bwd"]["ms"]) * 1e6   # bytes
+            att = dict(bound="hbm", kernel="sdpa_fwd_mma_kernel + sdpa_bwd_mma_kernel (attention core, all launches of a step)",
+                       achieved=a_y / (a_ms * 1e-3) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s", frac=a_y / (a_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                       traffic=None, share_of_step=a_ms / meter_ms_per_step, launches=by_op["sdpa_fwd"]["launches"] + by_op["sdpa_bwd"]["launches"],
+                       how="same instrumented graph replay as `roofline`; algorithmic bytes = q,k,v,out(,dout,dq,dk,dv),lse,mask once each")
+        lib_ms = (gm["total_ms"] if gm else 0.0) + sum(v["ms"] for v in by_op.values())
         cpu_sps, cpu_per = time_cpu(wl, 32, 2, 1) if args.gpus == 1 and not args.no_cpu_baseline else (None, None)
         line = dict(metric="VQA samples/sec (MCAN train)", value=value, unit="samples/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
@@ -441,13 +531,17 @@ def run_ours(args):
                                 l2="inputs larger than L2 (210 MB of features per step, 3 rotating batches)", final_loss=final_loss,
                                 cuda_graph=graph is not None, cuda_graph_error=graph_err, eager_ms_per_step=eager_ms_per_step),
                     e2e=dict(value=e2e, unit="samples/s", h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=4),
-                    gpu_launches=launches, roofline=roof, clocks=clocks)
+                    gpu_launches=launches, roofline=roof, roofline_attention=att,
+                    step_breakdown=dict(instrumented_ms_per_step=meter_ms_per_step, gemm_ms=gm["total_ms"] if gm else None, by_op=by_op,
+                                        library_ms=lib_ms, other_ms=meter_ms_per_step - lib_ms,
+                                        other="torch-native kernels around the path (cuDNN LSTM, embedding, fused Adam, zero-fills, loss) + gaps",
+                                        by_kernel=by_kernel[:14]),
+                    clocks=clocks)
         if cpu_sps is not None:
             line["cpu_baseline"] = dict(value=cpu_sps, unit="samples/s", cores=torch.get_num_threads(), kind="port",
                                         sample="2 training steps (fwd+NLL+bwd+Adam) of batch 32 after 1 warm-up, oracle port on all host threads")
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish(world)
 
 
 # ----------------------------------------------------------------------------------------------- M4C decode (configs[2])
@@ -656,8 +750,7 @@ def run_m4c(args):
             line["cpu_baseline"] = dict(value=cs, unit="samples/s", cores=torch.get_num_threads(), kind="port",
                                         sample="1 greedy decode (12 steps) of batch 4 after 1 warm-up, oracle port on all host threads")
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish(world)
 
 
 def main():

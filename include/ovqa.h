@@ -34,8 +34,8 @@ extern "C" {
 /* epilogue flags for ovqa_gemm */
 #define OVQA_EPI_GELU        1      /* exact erf GELU (positionwise_feed_forward.py:24)           */
 #define OVQA_EPI_DGELU       2      /* multiply by GELU'(aux) (backward of the above)             */
-#define OVQA_EPI_SAVE_DGELU  4      /* with GELU + aux_out: aux_out receives GELU'(v), not v      */
-#define OVQA_EPI_MUL_AUX     8      /* multiply by aux (a GELU' saved by the forward pass)        */
+#define OVQA_EPI_SAVE_DGELU  4      /* with GELU + aux_out: aux_out receives GELU'(v) x dropout scale */
+#define OVQA_EPI_MUL_AUX     8      /* multiply by aux (the derivative saved by the forward pass) */
 
 #define OVQA_OP_N 0                 /* operand stored with the reduction (K) dimension contiguous */
 #define OVQA_OP_T 1                 /* operand stored with its M/N dimension contiguous           */
@@ -56,8 +56,9 @@ uint64_t    ovqa_launch_count(void);              /* kernels launched by this li
  *      (y = x W^T : N,N.   dx = dy W : A N, B T.   dW = dy^T x : A T, B T.)
  *   ab_dtype: OVQA_BF16 runs on tcgen05/TMEM fed by TMA; OVQA_F32 runs the exact fp32 FFMA path
  *             (the 1e-4 parity path).  c_dtype: storage of C (and of c2).
- *   epilogue, in order:  v = acc*alpha + bias[n];  if aux_out: aux_out = v (pre-activation, c_dtype) — or GELU'(v)
- *             with OVQA_EPI_SAVE_DGELU, which lets the backward GEMM use the transcendental-free OVQA_EPI_MUL_AUX;
+ *   epilogue, in order:  v = acc*alpha + bias[n];  if aux_out: aux_out = v (pre-activation, c_dtype) — or, with
+ *             OVQA_EPI_SAVE_DGELU, d(dropout(GELU(v)))/dv = GELU'(v) * s, s = this element's dropout scale (0 or 1/(1-p); 1 if
+ *             p == 0), which lets the backward GEMM use OVQA_EPI_MUL_AUX alone (no transcendental, no RNG);
  *             GELU / DGELU(aux_in) / MUL_AUX(aux_in);  dropout(p, seed, offset [+ *offset_base]) if p>0;  v += residual[m,n] (fp32);
  *             if beta!=0: v += beta*C_old (fp32 C only);  C = v;  if c2: c2 = bf16(v).
  *   offset_base: optional DEVICE pointer to a u64 added to `offset` inside the kernel.  A host that replays a captured

@@ -110,6 +110,15 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* r) 
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14), LBO>>4 [16,30),
@@ -127,6 +136,12 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool 
 
 // ----------------------------------------------------------------------------- epilogue pieces
 enum { EPI_PLAIN = 0, EPI_FULL = 1, EPI_SPLITK = 2 };   // alpha/bias only | every fused feature | fp32 atomic accumulation
+// EPI_FULL comes in two flavours.  FEAT == F_RUNTIME tests the Epilogue fields at run time (any combination; the compiler
+// keeps every feature's state live and serialises the per-element math: profiles/r01d, 45 instructions per element at an
+// IPC of 0.09 per warp).  FEAT >= 0 is a compile-time feature set for the combinations the attention / feed-forward blocks
+// actually launch: no feature tests, the operands a pass needs are requested before the accumulator is read, and the eight
+// elements of a pass are independent instruction streams.
+enum : int { F_RUNTIME = -1, F_BIAS = 1, F_GELU = 2, F_SAVE_D = 4, F_MULAUX = 8, F_DROP = 16, F_RES = 32 };
 
 __device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -166,7 +181,7 @@ __device__ __noinline__ void epilogue_scalar(const Epilogue& epi, float acc, int
 }
 
 // ----------------------------------------------------------------------------- kernel
-template <int BN, bool A_MN, bool B_MN, typename TC, int MODE>
+template <int BN, bool A_MN, bool B_MN, typename TC, int MODE, int FEAT>
 __global__ void __launch_bounds__(kRegBoundThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, TC* __restrict__ C,
                     int64_t m, int64_t n, int64_t k, int64_t ldc, Epilogue epi, int split_k) {
@@ -305,6 +320,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         const float beta = MODE == EPI_FULL ? epi.beta : 0.f;
         const float drop_p = epi.dropout_p, inv_keep = f_drop ? 1.0f / (1.0f - epi.dropout_p) : 1.0f;
         const uint64_t seed = epi.seed, rng_offset = f_drop ? effective_offset(epi.offset, epi.offset_base) : 0;
+        const uint32_t thr_hi = dropout_threshold_hi(drop_p);
         const int64_t ld_res = epi.ld_res, ld_aux = epi.ld_aux, ldc2 = epi.ldc2;
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -321,6 +337,101 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                 if (col0 >= n) break;                                     // warp-uniform
                 const int64_t col = col0 + c8 * 8;
                 const bool fast = vec_ok && (col0 + 32 <= n);             // warp-uniform: whole chunk on the vector path
+                if constexpr (MODE == EPI_FULL && FEAT >= 0) {
+                    if (fast) {                                           // warp-uniform
+                        constexpr bool kBias = FEAT & F_BIAS, kGelu = FEAT & F_GELU, kSave = FEAT & F_SAVE_D, kMul = FEAT & F_MULAUX,
+                                       kDrop = FEAT & F_DROP, kRes = FEAT & F_RES;
+                        static_assert(!(kMul && kRes) && !(kSave && !kGelu), "unsupported specialised epilogue");
+                        const float k_out = kDrop ? inv_keep : 1.0f;      // dropout keep-scale, folded into the constants below
+                        const float a_s = (kGelu ? 1.0f : k_out) * alpha;
+                        float b8[8];
+                        if constexpr (kBias) {
+                            load8<float>(bias + col, b8);
+                            if constexpr (kDrop && !kGelu) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) b8[j] *= k_out;
+                            }
+                        }
+                        // operands of the four passes, requested before the accumulator is touched (rows beyond m: clamped, unused)
+                        uint4 in_lo[4], in_hi[4];
+                        if constexpr (kMul || kRes) {
+#pragma unroll
+                            for (int p = 0; p < 4; ++p) {
+                                const int64_t row = min(row_base + 8 * p, m - 1);
+                                if constexpr (kRes) {
+                                    const uint4* rp = reinterpret_cast<const uint4*>(residual + row * ld_res + col);
+                                    in_lo[p] = __ldg(rp); in_hi[p] = __ldg(rp + 1);
+                                } else {
+                                    static_assert(!kMul || sizeof(TC) == 2, "MUL_AUX specialisation is bf16");
+                                    in_lo[p] = __ldg(reinterpret_cast<const uint4*>(aux_in + row * ld_aux + col));
+                                }
+                            }
+                        }
+                        if constexpr (kRes) {                             // 32 residual registers are in flight: stage the chunk in two halves
+#pragma unroll
+                            for (int hlf = 0; hlf < 2; ++hlf) {
+                                uint32_t r[16];
+                                tmem_ld_32x32b_x16(t_row + (uint32_t)(c0 + 16 * hlf), r);
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int g = 0; g < 4; ++g)
+                                    sts128(st_row + (((uint32_t)(4 * hlf + g) ^ st_x) << 4), __uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]),
+                                           __uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3]));
+                            }
+                        } else {
+                            uint32_t r[32];
+                            tmem_ld_32x32b_x32(t_row + (uint32_t)c0, r);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int g = 0; g < 8; ++g)
+                                sts128(st_row + (((uint32_t)g ^ st_x) << 4), __uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]),
+                                       __uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3]));
+                        }
+                        __syncwarp();
+                        const GeluK gk(k_out);
+                        const uint64_t ctr0 = rng_offset + (uint64_t)((row_base * n + col) >> 3);   // n % 8 == 0 (vec_ok): + n per pass
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) {
+                            const int64_t row = row_base + 8 * p;
+                            float v[8], g[8];
+                            lds128(ld_lo + p * 1024, v[0], v[1], v[2], v[3]);
+                            lds128(ld_hi + p * 1024, v[4], v[5], v[6], v[7]);
+                            bool keep[8];
+                            if constexpr (kDrop) dropout_keep8(keep, philox4x32(ctr0 + (uint64_t)p * (uint64_t)n, seed), thr_hi);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                v[j] = kBias ? fmaf(v[j], a_s, b8[j]) : v[j] * a_s;
+                                if constexpr (kGelu) v[j] = kSave ? gelu_and_grad_tanhfit(v[j], gk, g[j]) : gelu_tanhfit(v[j], gk);
+                            }
+                            if constexpr (kMul) {
+                                const uint32_t w[4] = {in_lo[p].x, in_lo[p].y, in_lo[p].z, in_lo[p].w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float2 a = unpack_bf16x2(w[j]);
+                                    v[2 * j] *= a.x; v[2 * j + 1] *= a.y;
+                                }
+                            }
+                            if constexpr (kDrop) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    v[j] = keep[j] ? v[j] : 0.0f;
+                                    if constexpr (kSave) g[j] = keep[j] ? g[j] : 0.0f;
+                                }
+                            }
+                            if constexpr (kRes) {
+                                const uint32_t w[8] = {in_lo[p].x, in_lo[p].y, in_lo[p].z, in_lo[p].w, in_hi[p].x, in_hi[p].y, in_hi[p].z, in_hi[p].w};
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[j] += __uint_as_float(w[j]);
+                            }
+                            if (row < m) {
+                                store8<TC>(C + row * ldc + col, v);
+                                if constexpr (kSave) store8<TC>(aux_out + row * ld_aux + col, g);
+                            }
+                        }
+                        __syncwarp();
+                        continue;
+                    }
+                }
                 float b8[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) b8[j] = 0.f;
@@ -369,10 +480,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], alpha, b8[j]);
                     if constexpr (MODE == EPI_FULL) {
-                        if (f_save_d) {                                   // y = GELU(v), aux_out = GELU'(v): one CDF + one exponential for both
+                        float ds[8];
+                        if (f_drop) dropout_scale8(ds, (uint64_t)(row * n + col), drop_p, inv_keep, seed, rng_offset);
+                        if (f_save_d) {                                   // y = GELU(v), aux_out = GELU'(v) [x dropout scale]: one CDF + one exponential for both
                             float d[8];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) v[j] = gelu_and_grad_fast(v[j], d[j]);
+                            for (int j = 0; j < 8; ++j) {
+                                v[j] = gelu_and_grad_fast(v[j], d[j]);
+                                if (f_drop) d[j] *= ds[j];
+                            }
                             store8<TC>(aux_out + row * ld_aux + col, d);
                         } else {
                             if (aux_out) store8<TC>(aux_out + row * ld_aux + col, v);
@@ -391,8 +507,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                             if (residual && bias) load8<float>(bias + col, b8);   // (never together on the path) restore for the next pass
                         }
                         if (f_drop) {
-                            float ds[8];
-                            dropout_scale8(ds, (uint64_t)(row * n + col), drop_p, inv_keep, seed, rng_offset);
 #pragma unroll
                             for (int j = 0; j < 8; ++j) v[j] *= ds[j];
                         }
@@ -501,20 +615,35 @@ int launch(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, int64_t m, i
     const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
     const bool full = epi.flags || epi.aux_in || epi.aux_out || epi.residual || epi.c2 || epi.dropout_p > 0.f || epi.beta != 0.f;
     const int mode = split_k > 1 ? EPI_SPLITK : full ? EPI_FULL : EPI_PLAIN;
-#define OVQA_GO(TC_, MODE_)                                                                                                     \
+    // compile-time feature set of this launch, if it is one of the specialised combinations (else F_RUNTIME)
+    int feat = F_RUNTIME;
+    if (mode == EPI_FULL && !epi.c2 && epi.beta == 0.f && !(epi.flags & OVQA_EPI_DGELU) && !(epi.aux_out && !(epi.flags & OVQA_EPI_SAVE_DGELU))) {
+        feat = (epi.bias ? F_BIAS : 0) | ((epi.flags & OVQA_EPI_GELU) ? F_GELU : 0) | ((epi.flags & OVQA_EPI_SAVE_DGELU) ? F_SAVE_D : 0) |
+               ((epi.flags & OVQA_EPI_MUL_AUX) ? F_MULAUX : 0) | (epi.dropout_p > 0.f ? F_DROP : 0) | (epi.residual ? F_RES : 0);
+    }
+#define OVQA_GO(TC_, MODE_, FEAT_)                                                                                              \
     do {                                                                                                                       \
-        auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, TC_, MODE_>;                                                            \
+        auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, TC_, MODE_, FEAT_>;                                                     \
         static bool attr_set = false;                                                                                          \
         if (!attr_set) { OVQA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::kSmemBytes)); attr_set = true; } \
         kern<<<grid, kThreads, cfg::kSmemBytes, st>>>(ma, mb, (TC_*)C, m, n, k, ldc, epi, split_k);                            \
     } while (0)
+    // the specialised sets exist for the operand forms that launch them: forward y = x W^T is (N,N), dgrad dx = dy W is (N,T)
+    constexpr bool kFwd = !A_MN && !B_MN, kDgrad = !A_MN && B_MN;
     if (epi.c_dtype == OVQA_F32) {
-        if (mode == EPI_SPLITK) OVQA_GO(float, EPI_SPLITK);
-        else if (mode == EPI_FULL) OVQA_GO(float, EPI_FULL);
-        else OVQA_GO(float, EPI_PLAIN);
+        if (mode == EPI_SPLITK) OVQA_GO(float, EPI_SPLITK, F_RUNTIME);
+        else if (mode == EPI_PLAIN) OVQA_GO(float, EPI_PLAIN, F_RUNTIME);
+        else if (kFwd && feat == (F_BIAS | F_DROP | F_RES)) OVQA_GO(float, EPI_FULL, (kFwd ? F_BIAS | F_DROP | F_RES : F_RUNTIME));     // fc_o / fc2, training
+        else if (kFwd && feat == (F_BIAS | F_RES)) OVQA_GO(float, EPI_FULL, (kFwd ? F_BIAS | F_RES : F_RUNTIME));                       // fc_o / fc2, eval
+        else if (kDgrad && feat == F_RES) OVQA_GO(float, EPI_FULL, (kDgrad ? F_RES : F_RUNTIME));                                       // dx = dy W + other branch's gradient
+        else OVQA_GO(float, EPI_FULL, F_RUNTIME);
     } else {
-        if (mode == EPI_FULL) OVQA_GO(__nv_bfloat16, EPI_FULL);
-        else OVQA_GO(__nv_bfloat16, EPI_PLAIN);
+        if (mode == EPI_PLAIN) OVQA_GO(__nv_bfloat16, EPI_PLAIN, F_RUNTIME);
+        else if (kFwd && feat == (F_BIAS | F_GELU | F_SAVE_D | F_DROP)) OVQA_GO(__nv_bfloat16, EPI_FULL, (kFwd ? F_BIAS | F_GELU | F_SAVE_D | F_DROP : F_RUNTIME));   // fc1, training
+        else if (kFwd && feat == (F_BIAS | F_GELU | F_SAVE_D)) OVQA_GO(__nv_bfloat16, EPI_FULL, (kFwd ? F_BIAS | F_GELU | F_SAVE_D : F_RUNTIME));                     // fc1, training, p = 0
+        else if (kFwd && feat == (F_BIAS | F_GELU)) OVQA_GO(__nv_bfloat16, EPI_FULL, (kFwd ? F_BIAS | F_GELU : F_RUNTIME));                                           // fc1, eval
+        else if (kDgrad && feat == F_MULAUX) OVQA_GO(__nv_bfloat16, EPI_FULL, (kDgrad ? F_MULAUX : F_RUNTIME));                                                       // dpre = (dy W2) * saved derivative
+        else OVQA_GO(__nv_bfloat16, EPI_FULL, F_RUNTIME);
     }
 #undef OVQA_GO
     OVQA_LAUNCH_OK();

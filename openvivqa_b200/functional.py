@@ -371,7 +371,7 @@ class _PWFFFn(torch.autograd.Function):
         s1, o1 = dropout_stream.next(M * dff) if p > 0.0 else (0, 0)
         rng_base = dropout_stream.base(x.device) if p > 0.0 else None
         hact = ops.gemm(x2, weights.get([w1], cdt), bias=weights.get([b1], torch.float32), out_dtype=cdt, gelu=True,
-                        aux_out=pre, save_dgelu=need_grad, dropout_p=p, seed=s1, offset=o1, offset_base=rng_base)   # pre := GELU'(fc1 x)
+                        aux_out=pre, save_dgelu=need_grad, dropout_p=p, seed=s1, offset=o1, offset_base=rng_base)   # pre := GELU'(fc1 x) * dropout scale
         s2, o2 = dropout_stream.next(M * D) if p > 0.0 else (0, 0)
         x_res = x.reshape(-1, D)
         x_res = x_res if (x_res.dtype == torch.float32 and x_res.is_contiguous()) else x_res.float().contiguous()
@@ -401,9 +401,9 @@ class _PWFFFn(torch.autograd.Function):
                                                          dropout_p=p, seed=s2, offset=o2, offset_base=rng_base, want_dbias=True)
         d2 = _masked_operand(ds, ds16, mode, p, s2, o2, rng_base)                   # grad of the fc2 output (its column sums: db2)
         dw2 = _wgrad(d2, hact)
-        # grad of the fc1 pre-activation: (d2 W2) * dropout1 mask * gelu'(pre) — the forward saved gelu' itself, so the dgrad
-        # epilogue is a plain multiply
-        dpre = ops.gemm(d2, weights.get([w2], cdt), b_op="T", out_dtype=cdt, mul_aux=pre, dropout_p=p, seed=s1, offset=o1, offset_base=rng_base)
+        # grad of the fc1 pre-activation: (d2 W2) * [dropout1 scale * gelu'(pre)] — the forward saved that product (the derivative
+        # of its whole fused activation), so the dgrad epilogue is one multiply: no transcendental, no RNG
+        dpre = ops.gemm(d2, weights.get([w2], cdt), b_op="T", out_dtype=cdt, mul_aux=pre)
         dw1, db1 = _wgrad(dpre, x2), ops.colsum(dpre)
         dx = ops.gemm(dpre, weights.get([w1], cdt), b_op="T", out_dtype=torch.float32, residual=ds.reshape(-1, D)).view(ctx.xshape)
         return dx, dw1, db1, dw2, db2, dgamma, dbeta, None

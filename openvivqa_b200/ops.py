@@ -51,8 +51,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_op: str = "N", b_op: str = "N", 
     """``C[m,n] = epilogue(sum_k A[m,k] B[n,k])`` — see ``ovqa_gemm`` in include/ovqa.h.
 
     ``a_op``/``b_op``: "N" = operand stored [rows, k]; "T" = stored [k, rows].
-    ``save_dgelu`` (with ``gelu`` + ``aux_out``): ``aux_out`` receives GELU'(pre-activation); a later GEMM multiplies by it
-    with ``mul_aux=`` (no transcendental in the backward epilogue)."""
+    ``save_dgelu`` (with ``gelu`` + ``aux_out``): ``aux_out`` receives the derivative of the whole fused activation,
+    GELU'(pre-activation) times the element's dropout scale (0 or 1/(1-p); 1 without dropout); the backward GEMM multiplies
+    by it with ``mul_aux=`` — no transcendental and no RNG in the backward epilogue."""
     if mul_aux is not None:
         if dgelu_aux is not None:
             raise ValueError("gemm: dgelu_aux and mul_aux are exclusive")

@@ -118,3 +118,66 @@ def test_fast_gelu_matches_erf_gelu(dev):
     out = ops.gemm(xb, eye, out_dtype=torch.float32, gelu=True)           # y = gelu(x_bf16 * I)
     want = torch.nn.functional.gelu(xb.float())
     assert (out - want).abs().max().item() <= 1e-6
+
+
+@pytest.mark.parametrize("m,n,k", [(300, 512, 192), (1000, 2048, 512), (257, 768, 2048)])
+def test_specialised_epilogues(dev, m, n, k):
+    """The compile-time feature sets of gemm_tcgen05.cu (fc1 train / eval, dpre, fc_o / fc2 train / eval, dx + residual)
+    against torch: erf GELU (the tanh-fit epilogue must stay within bf16 rounding of it), the same Philox keep mask as every
+    other kernel, and the saved derivative = GELU' x dropout scale."""
+    a, b, ref = _mk(m, n, k, "N", "N", dev)
+    ref = ref.to(dev)
+    g = torch.Generator().manual_seed(2)
+    bias, res = torch.randn(n, generator=g).to(dev), torch.randn((m, n), generator=g).to(dev)
+    pre = ref + bias
+    p, seed, off = 0.1, 11, 3
+    keep = ops.dropout_keep_mask(m * n, p, seed, off, dev).view(m, n).float()
+    assert 0.88 < keep.mean().item() < 0.92
+    xs = pre.clone().requires_grad_(True)
+    F.gelu(xs).sum().backward()
+    dgelu, gelu = xs.grad, F.gelu(pre)
+    tol = 2e-2
+    # fc1, training: bias + GELU + dropout -> bf16, saved derivative
+    dsave = torch.empty((m, n), device=dev, dtype=torch.bfloat16)
+    y = ops.gemm(a, b, bias=bias, gelu=True, aux_out=dsave, save_dgelu=True, dropout_p=p, seed=seed, offset=off, out_dtype=torch.bfloat16)
+    assert (y.float() - gelu * keep / (1 - p)).abs().max() <= tol * gelu.abs().max()
+    assert (dsave.float() - dgelu * keep / (1 - p)).abs().max() <= tol
+    assert (y[keep == 0] == 0).all() and (dsave[keep == 0] == 0).all()
+    # fc1, training with p = 0, and eval
+    y0 = ops.gemm(a, b, bias=bias, gelu=True, aux_out=dsave, save_dgelu=True, out_dtype=torch.bfloat16)
+    y1 = ops.gemm(a, b, bias=bias, gelu=True, out_dtype=torch.bfloat16)
+    assert torch.equal(y0, y1)
+    assert (y1.float() - gelu).abs().max() <= tol * gelu.abs().max()
+    assert (y1.float() - gelu).abs().max() <= 3e-3 * torch.maximum(gelu.abs(), torch.ones_like(gelu)).max()
+    assert (dsave.float() - dgelu).abs().max() <= 1e-2
+    # dpre = (dy W2) * saved derivative  (N,T operand form, bf16 out)
+    bt = b.t().contiguous()                                   # stored [k, n]: the "T" form of the same B
+    d = ops.gemm(a, bt, b_op="T", out_dtype=torch.bfloat16, mul_aux=dsave)
+    want = ref * dsave.float()
+    assert (d.float() - want).abs().max() <= tol * want.abs().max()
+    # fc_o / fc2: bias + dropout + residual -> fp32 (training), bias + residual (eval)
+    s = ops.gemm(a, b, bias=bias, dropout_p=p, seed=seed, offset=off, residual=res, out_dtype=torch.float32)
+    want = pre * keep / (1 - p) + res
+    assert (s - want).abs().max() <= 1e-3 * want.abs().max()
+    s = ops.gemm(a, b, bias=bias, residual=res, out_dtype=torch.float32)
+    assert (s - (pre + res)).abs().max() <= 1e-3 * (pre + res).abs().max()
+    # dx = dy W + the other branch's gradient  (N,T form, fp32 out)
+    s = ops.gemm(a, bt, b_op="T", residual=res, out_dtype=torch.float32)
+    assert (s - (ref + res)).abs().max() <= 1e-3 * (ref + res).abs().max()
+
+
+def test_tanhfit_gelu_matches_erf_gelu(dev):
+    """The specialised bf16 epilogue's GELU (tanh form fitted to the erf definition, tanh.approx) against F.gelu on a
+    dense grid: error well below the bf16 rounding of the result."""
+    x = torch.linspace(-12, 12, 128 * 256, device=dev).view(128, 256)
+    eye = torch.eye(256, device=dev).bfloat16()
+    xb = x.bfloat16()
+    zero = torch.zeros(256, device=dev)
+    dsave = torch.empty((128, 256), device=dev, dtype=torch.bfloat16)
+    out = ops.gemm(xb, eye, bias=zero, out_dtype=torch.bfloat16, gelu=True, aux_out=dsave, save_dgelu=True)
+    xs = xb.float().requires_grad_(True)
+    want = F.gelu(xs)
+    want.sum().backward()
+    err = (out.float() - want.detach()).abs()
+    assert (err <= 2.0 ** -8 * want.detach().abs() + 1.5e-3).all(), err.max().item()
+    assert (dsave.float() - xs.grad).abs().max().item() <= 6e-3

@@ -170,7 +170,7 @@ def bench_gemm_epilogues():
         ("fc_o: bias+dropout+residual -> f32", 2.0 * M * D * D, lambda: ops.gemm(x16, wo, bias=b2, out=o_s, dropout_p=0.1, seed=1, offset=0, residual=res)),
         ("fc1 train: bias+GELU+save GELU'+dropout -> bf16", 2.0 * M * F_ * D, lambda: ops.gemm(x16, w1, bias=b1, out=o_h, gelu=True, aux_out=pre, save_dgelu=True, dropout_p=0.1, seed=1, offset=0)),
         ("dpre: dgrad fc2 * GELU'(pre) * dropout -> bf16", 2.0 * M * F_ * D, lambda: ops.gemm(d2, w2, b_op="T", out=o_h, dgelu_aux=pre, dropout_p=0.1, seed=1, offset=0)),
-        ("dpre: dgrad fc2 * saved GELU' * dropout -> bf16", 2.0 * M * F_ * D, lambda: ops.gemm(d2, w2, b_op="T", out=o_h, mul_aux=pre, dropout_p=0.1, seed=1, offset=0)),
+        ("dpre: dgrad fc2 * saved derivative -> bf16", 2.0 * M * F_ * D, lambda: ops.gemm(d2, w2, b_op="T", out=o_h, mul_aux=pre)),
         ("dx: dgrad fc1 + residual -> f32", 2.0 * M * F_ * D, lambda: ops.gemm(h16, w1, b_op="T", out=o_s, residual=res)),
     ]
     for tag, fl, fn in cases:
