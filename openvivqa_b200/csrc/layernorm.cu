@@ -9,6 +9,9 @@ namespace {
 
 constexpr int kMaxVec = 8;  // float4 per lane -> D <= 1024
 constexpr int kRowsPerCta = 4;
+constexpr int kBwdWarps = 8;  // backward: warps per CTA.  Every CTA ends with one atomic per column vector into dgamma/dbeta/dbias, and
+                              // same-address atomics serialise in L2: with 4-warp CTAs (1036 of them) and scalar atomics that tail cost
+                              // ~40 us regardless of the row count (profiles/r01e: 47 us for 7680 rows, 62 us for 25600)
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
@@ -71,13 +74,13 @@ __device__ __forceinline__ void ln_cp_async16(void* dst, const void* src) {
 }
 
 template <int NV>
-__global__ void __launch_bounds__(kRowsPerCta * 32)
+__global__ void __launch_bounds__(kBwdWarps * 32, 2)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
                      const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dx_add,
                      float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16, float* __restrict__ dgamma, float* __restrict__ dbeta,
                      float* __restrict__ dbias, int64_t rows, int D, float p, float inv_keep, uint64_t seed, uint64_t offset_,
                      const uint64_t* offset_base) {
-    extern __shared__ __align__(16) float ln_smem[];       // [kRowsPerCta][2 stages][2 (x, dy)][NV*128]; reused for the final reduction
+    extern __shared__ __align__(16) float ln_smem[];       // [kBwdWarps][2 stages][2 (x, dy)][NV*128]; reused for the final reduction
     constexpr int W = NV * 128;
     const uint64_t offset = p > 0.f ? effective_offset(offset_, offset_base) : 0;
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -86,7 +89,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
     float4 ag[NV], ab[NV], ad[NV];      // column sums for dgamma, dbeta and (masked dx) the producing GEMM's bias gradient
 #pragma unroll
     for (int t = 0; t < NV; ++t) ag[t] = ab[t] = ad[t] = make_float4(0, 0, 0, 0);
-    const int64_t stride = (int64_t)gridDim.x * kRowsPerCta;
+    const int64_t stride = (int64_t)gridDim.x * kBwdWarps;
     auto prefetch = [&](int64_t row, int stage) {
         float* bx = wbuf + stage * 2 * W;
 #pragma unroll
@@ -98,7 +101,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
             }
         }
     };
-    int64_t row = (int64_t)blockIdx.x * kRowsPerCta + warp;
+    int64_t row = (int64_t)blockIdx.x * kBwdWarps + warp;
     if (row < rows) prefetch(row, 0);
     asm volatile("cp.async.commit_group;" ::: "memory");
     for (int it = 0; row < rows; row += stride, ++it) {
@@ -149,27 +152,26 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
         __syncwarp();                                                 // this stage is overwritten by the prefetch of iteration it+1
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    // dgamma / dbeta / dbias: reduce the warps through smem (the staging buffers are free now), one atomicAdd per column per CTA
+    // dgamma / dbeta / dbias: reduce the warps through smem (the staging buffers are free now), then ONE 16-byte vector
+    // atomic per 4 columns per CTA
     if (!dgamma && !dbeta && !dbias) return;
-    float(*red)[32 * 4 + 1] = reinterpret_cast<float(*)[32 * 4 + 1]>(ln_smem);
+    float4* red = reinterpret_cast<float4*>(ln_smem);                 // [kBwdWarps][NV*32] float4
     for (int pass = 0; pass < 3; ++pass) {
         float* dst = pass == 0 ? dgamma : pass == 1 ? dbeta : dbias;
         if (!dst) continue;
+        __syncthreads();                                              // staging buffers / previous pass fully consumed
 #pragma unroll
-        for (int t = 0; t < NV; ++t) {
-            const int c = lane + 32 * t;
-            const float4 a = pass == 0 ? ag[t] : pass == 1 ? ab[t] : ad[t];
-            __syncthreads();
-            red[warp][lane * 4 + 0] = a.x; red[warp][lane * 4 + 1] = a.y; red[warp][lane * 4 + 2] = a.z; red[warp][lane * 4 + 3] = a.w;
-            __syncthreads();
-            if (warp == 0 && c < nvec) {
+        for (int t = 0; t < NV; ++t) red[warp * (NV * 32) + lane + 32 * t] = pass == 0 ? ag[t] : pass == 1 ? ab[t] : ad[t];
+        __syncthreads();
+        const bool vec = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+        for (int c = threadIdx.x; c < nvec; c += kBwdWarps * 32) {
+            float4 sum = red[c];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    float s = 0.f;
-#pragma unroll
-                    for (int w = 0; w < kRowsPerCta; ++w) s += red[w][lane * 4 + e];
-                    atomicAdd(dst + 4 * c + e, s);
-                }
+            for (int w = 1; w < kBwdWarps; ++w) sum = add4(sum, red[w * (NV * 32) + c]);
+            if (vec) {
+                atomicAdd(reinterpret_cast<float4*>(dst) + c, sum);
+            } else {
+                atomicAdd(dst + 4 * c, sum.x); atomicAdd(dst + 4 * c + 1, sum.y); atomicAdd(dst + 4 * c + 2, sum.z); atomicAdd(dst + 4 * c + 3, sum.w);
             }
         }
     }
@@ -214,6 +216,58 @@ __global__ void colsum_kernel(const T* __restrict__ x, float* __restrict__ out, 
 #pragma unroll
         for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
         atomicAdd(out + col, t);
+    }
+}
+
+// Vector form (n % 8 == 0, 16-byte aligned rows): a lane owns 8 consecutive columns (one 16-byte load of bf16, two of fp32), a
+// warp 256 columns of a row (512 contiguous bytes), the 8 warps of a CTA take rows r, r+8, ... of the CTA's slab four at a time
+// (four independent loads in flight per lane); warps are reduced through shared memory, then one 16-byte atomic per 4 columns.
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ x, float* __restrict__ out, int64_t m, int64_t n, int64_t ldx,
+                                                         int64_t rows_per_block) {
+    __shared__ float4 red[8][64];
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int64_t col = (int64_t)blockIdx.x * 256 + lane * 8;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(m, r0 + rows_per_block);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    auto load8v = [&](int64_t r, float (&v)[8]) {
+        if constexpr (sizeof(T) == 2) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + r * ldx + col));
+            const float2 p0 = unpack_bf16x2(u.x), p1 = unpack_bf16x2(u.y), p2 = unpack_bf16x2(u.z), p3 = unpack_bf16x2(u.w);
+            v[0] = p0.x; v[1] = p0.y; v[2] = p1.x; v[3] = p1.y; v[4] = p2.x; v[5] = p2.y; v[6] = p3.x; v[7] = p3.y;
+        } else {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(x + r * ldx + col)), b = __ldg(reinterpret_cast<const float4*>(x + r * ldx + col) + 1);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        }
+    };
+    if (col < n) {
+        int64_t r = r0 + warp;
+        for (; r + 24 < r1; r += 32) {
+            float v0[8], v1[8], v2[8], v3[8];
+            load8v(r, v0); load8v(r + 8, v1); load8v(r + 16, v2); load8v(r + 24, v3);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += (v0[j] + v1[j]) + (v2[j] + v3[j]);
+        }
+        for (; r < r1; r += 8) {
+            float v0[8];
+            load8v(r, v0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += v0[j];
+        }
+    }
+    red[warp][2 * lane] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    red[warp][2 * lane + 1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        const int64_t c4 = (int64_t)blockIdx.x * 256 + threadIdx.x * 4;
+        if (c4 < n) {
+            float4 sum = red[0][threadIdx.x];
+#pragma unroll
+            for (int w = 1; w < 8; ++w) sum = add4(sum, red[w][threadIdx.x]);
+            atomicAdd(reinterpret_cast<float4*>(out + c4), sum);
+        }
     }
 }
 
@@ -299,19 +353,18 @@ extern "C" int ovqa_layernorm_bwd(const float* dy, const float* x, const float* 
     if (D % 4 != 0 || D > kMaxVec * 128) return OVQA_ERR_BAD_SHAPE;
     if (dropout_p < 0.f || dropout_p >= 1.f) return OVQA_ERR_BAD_ARG;
     if (rows == 0) return OVQA_OK;
-    // persistent: as many CTAs as stay resident; every CTA ends with one atomicAdd per column into dgamma/dbeta/dbias, so
-    // fewer, longer-lived CTAs also mean fewer same-address atomics
+    // persistent: as many CTAs as stay resident (two rows of cp.async per warp in flight), never more than the rows need
     const int nv = (int)((D + 127) / 128);
-    const size_t smem = (size_t)kRowsPerCta * 4 * nv * 128 * sizeof(float);      // >= the [kRowsPerCta][129] reduction scratch
+    const size_t smem = (size_t)kBwdWarps * 4 * nv * 128 * sizeof(float);        // >= the [kBwdWarps][nv*32] float4 reduction scratch
     auto kern = OVQA_LN_DISPATCH(layernorm_bwd_kernel);
     if (smem > 48 * 1024) OVQA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    OVQA_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRowsPerCta * 32, smem));
+    OVQA_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBwdWarps * 32, smem));
     if (per_sm < 1) per_sm = 1;
-    int64_t g = (rows + kRowsPerCta - 1) / kRowsPerCta;
+    int64_t g = (rows + kBwdWarps - 1) / kBwdWarps;
     const int64_t cap = (int64_t)sm_count() * per_sm;
     if (g > cap) g = cap;
-    kern<<<(unsigned)g, kRowsPerCta * 32, smem, (cudaStream_t)stream>>>(
+    kern<<<(unsigned)g, kBwdWarps * 32, smem, (cudaStream_t)stream>>>(
         dy, x, mean, rstd, gamma, dx_add, dx, (__nv_bfloat16*)dx_bf16, dgamma, dbeta, dbias, rows, (int)D, dropout_p,
         dropout_p > 0.f ? 1.0f / (1.0f - dropout_p) : 1.0f, seed, offset, offset_base);
     OVQA_LAUNCH_OK();
@@ -346,6 +399,20 @@ extern "C" int ovqa_colsum(const void* x, float* out, int64_t m, int64_t n, int6
     cudaStream_t st = (cudaStream_t)stream;
     if (!accumulate) OVQA_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * n, st));
     if (m == 0) return OVQA_OK;
+    const int esz = dtype == OVQA_F32 ? 4 : 2;
+    if ((dtype == OVQA_F32 || dtype == OVQA_BF16) && n % 8 == 0 && (ldx * esz) % 16 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        const int64_t cb = (n + 255) / 256;
+        int64_t rb = ((int64_t)sm_count() * 6 + cb - 1) / cb;              // ~6 CTAs of 8 warps per SM
+        if (rb > (m + 63) / 64) rb = (m + 63) / 64;
+        if (rb < 1) rb = 1;
+        const int64_t rpb_v = ((m + rb - 1) / rb + 7) / 8 * 8;
+        dim3 grid_v((unsigned)cb, (unsigned)((m + rpb_v - 1) / rpb_v));
+        if (dtype == OVQA_F32) colsum_vec_kernel<float><<<grid_v, 256, 0, st>>>((const float*)x, out, m, n, ldx, rpb_v);
+        else colsum_vec_kernel<__nv_bfloat16><<<grid_v, 256, 0, st>>>((const __nv_bfloat16*)x, out, m, n, ldx, rpb_v);
+        OVQA_LAUNCH_OK();
+        return OVQA_OK;
+    }
     const int64_t col_blocks = (n + 31) / 32;
     int64_t row_blocks = (int64_t)sm_count() * 4 / col_blocks;
     if (row_blocks < 1) row_blocks = 1;

@@ -496,6 +496,37 @@ def test_layernorm_fwd_bwd(dev, D):
     assert rel_err(y2, F.layer_norm(x, (D,), gamma, beta, 1e-12)) < 1e-5
 
 
+def test_layernorm_bwd_many_rows_persistent(dev):
+    """Enough rows that every warp of the persistent backward loops (cp.async double buffer) and many CTAs meet in the
+    column-sum atomics."""
+    rows, D = 9001, 512
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn((rows, D), generator=g) * 2 + 0.5).to(dev)
+    gamma, beta, dy = torch.randn(D, generator=g).to(dev), torch.randn(D, generator=g).to(dev), torch.randn((rows, D), generator=g).to(dev)
+    xs, gm, bt = x.clone().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    F.layer_norm(xs, (D,), gm, bt, 1e-5).backward(dy)
+    _, _, _, mean, rstd = ops.layernorm_fwd(x, gamma, beta, save_stats=True)
+    dx, dx16, dg, db, dbias = ops.layernorm_bwd(dy, x, mean, rstd, gamma, want_bf16=True, want_dbias=True)
+    assert rel_err(dx, xs.grad) < 1e-4 and rel_err(dg, gm.grad) < 1e-4 and rel_err(db, bt.grad) < 1e-4
+    assert rel_err(dbias, xs.grad.sum(0)) < 1e-3 and abs_err(dx16, xs.grad.bfloat16()) <= 0.02 * xs.grad.abs().max().item()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("m,n", [(1, 8), (37, 96), (5000, 1536), (25600, 512), (333, 100)])
+def test_colsum(dev, dtype, m, n):
+    g = torch.Generator().manual_seed(m + n)
+    x = torch.randn((m, n), generator=g).to(dev).to(dtype)
+    want = x.double().sum(0)
+    tol = 1e-5 * (x.double().abs().sum(0).max().item() + 1.0)
+    out = ops.colsum(x)
+    assert (out.double() - want).abs().max().item() <= tol
+    out2 = ops.colsum(x, out=out.clone(), accumulate=True)
+    assert (out2.double() - 2 * want).abs().max().item() <= 2 * tol
+    if n % 16 == 0:                                   # a column slice of a wider buffer (row pitch != n), as the fused QKV gradients are
+        xs = x[:, n // 2:]
+        assert (ops.colsum(xs).double() - want[n // 2:]).abs().max().item() <= tol
+
+
 # ------------------------------------------------------------------------------------------------ M4C kernels
 def test_m4c_pointer_prev_pred_and_greedy_kernels(dev, golden):
     c = C.M4C_SMALL
