@@ -23,6 +23,10 @@ template <typename T> int sdpa_bwd_simt_launch(const SdpaArgs&, const void*, voi
 int box_geometry_bias_launch(const GeoArg&, float*, int64_t, int64_t, int64_t, cudaStream_t);
 int sdpa_fwd_mma_bf16(const SdpaArgs&, cudaStream_t);   // attention_mma.cu
 bool sdpa_fwd_mma_supported(const SdpaArgs&);
+int sdpa_fwd_tc5_bf16(const SdpaArgs&, cudaStream_t);   // attention_tc5.cu (tcgen05 / TMEM / TMA: head dim 64, Lq, Lk <= 128, per-key mask)
+bool sdpa_fwd_tc5_supported(const SdpaArgs&);
+int sdpa_bwd_tc5_bf16(const SdpaArgs&, const void*, void*, void*, void*, int64_t, int64_t, int64_t, int64_t, cudaStream_t);
+bool sdpa_bwd_tc5_supported(const SdpaArgs&, const void*, const void*, const void*, const void*, int64_t, int64_t, int64_t, int64_t);
 int sdpa_bwd_mma_bf16(const SdpaArgs&, const void*, void*, void*, void*, int64_t, int64_t, int64_t, int64_t, cudaStream_t);
 bool sdpa_bwd_mma_supported(const SdpaArgs&, const void*, const void*, const void*, const void*, int64_t, int64_t, int64_t, int64_t);
 
@@ -107,6 +111,7 @@ extern "C" int ovqa_sdpa_fwd(const void* q, const void* k, const void* v, void* 
                {boxes, geo_w, geo_b, geo_freq, (int)d_g, geo_trig}, scale, lse, att};
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == OVQA_F32) return sdpa_fwd_simt_launch<float>(a, st);
+    if (sdpa_fwd_tc5_supported(a)) return sdpa_fwd_tc5_bf16(a, st);
     if (sdpa_fwd_mma_supported(a)) return sdpa_fwd_mma_bf16(a, st);
     return sdpa_fwd_simt_launch<__nv_bfloat16>(a, st);
 }
@@ -127,6 +132,8 @@ extern "C" int ovqa_sdpa_bwd(const void* q, const void* k, const void* v, const 
     cudaStream_t st = (cudaStream_t)stream;
     // debugging aid only: OVQA_SDPA_BWD=simt keeps the bf16 backward on the CUDA-core kernels
     static const bool force_simt = [] { const char* e = getenv("OVQA_SDPA_BWD"); return e && e[0] == 's'; }();
+    if (dtype == OVQA_BF16 && !force_simt && sdpa_bwd_tc5_supported(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv))
+        return sdpa_bwd_tc5_bf16(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv, st);
     if (dtype == OVQA_BF16 && !force_simt && sdpa_bwd_mma_supported(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv))
         return sdpa_bwd_mma_bf16(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv, st);
     if (!delta) return OVQA_ERR_BAD_ARG;

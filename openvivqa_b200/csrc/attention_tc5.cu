@@ -1,0 +1,572 @@
+// Attention core on 5th-gen tensor cores for the MCAN shape class: head dim 64, Lq <= 128, Lk <= 128, padding (per-key) mask.
+//
+// One head of one sample is ONE 128-row UMMA tile: S = Q K^T is 4 tcgen05.mma instructions (128 x Lk16 x 16 each) into TMEM,
+// the softmax runs with one THREAD per query row (tcgen05.ld gives lane = row, so max / sum need no shuffles), P goes back to
+// shared memory as the K-major A operand of O = P V (Lk16/16 more instructions), and O is read from TMEM, normalised and stored.
+// Against the mma.sync kernel (attention_mma.cu) this removes the ldmatrix / fragment traffic and ~3/4 of the issued
+// instructions (profiles/r01e: the warp-tile kernel is issue-bound at ~27 % of the HBM roofline), and it makes the core a
+// persistent, TMA-fed pipeline:
+//   warp 0      TMA producer: Q, K, V tiles of item i+1, i+2 while item i is computed (3 load stages, SWIZZLE_128B)
+//   warp 1      MMA issuer (one thread): S(i+1) is issued before waiting for P(i), so the tensor pipe never waits on softmax
+//   warps 2-5   softmax group 0 (items 0, 2, 4, ...)      } two groups ping-pong on their own TMEM columns and P buffer: one
+//   warps 6-9   softmax group 1 (items 1, 3, 5, ...)      } group's TMEM / MUFU latencies hide behind the other's arithmetic
+// Work item = (sample, head); CTAs are persistent over items (grid = min(B*h, #SM)).
+// Rows of the K / V tiles beyond Lk belong to the next sample (or are TMA zero fill): their P columns are exactly 0 (the
+// staged mask row is -inf there), so they contribute nothing.
+#include "attention_simt.cuh"
+#include "tcgen05.cuh"
+
+namespace ovqa {
+
+namespace {
+
+using namespace tc5;
+
+constexpr int kD = 64;                    // head dim (one SWIZZLE_128B row of bf16)
+constexpr int kLoadStages = 3;
+constexpr int kTileBytes = 128 * 128;     // 128 rows x 128 B
+constexpr int kStageBytes = 3 * kTileBytes;            // Q, K, V
+constexpr int kPBytes = 2 * kTileBytes;                // P: two 64-key blocks of 128 rows x 128 B
+constexpr int kFwdThreads = 64 + 2 * 128;
+constexpr int kFwdSmem = kLoadStages * kStageBytes + 2 * kPBytes + 2 * 128 * 4 /*mask rows*/ + 256 /*barriers*/ + 1024 /*align*/;
+constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+
+struct Tc5FwdArgs {
+    SdpaArgs a;
+    int nk16;               // Lk rounded up to 16 (N of the S MMA, K extent of the PV MMA, rows of the K / V TMA boxes)
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void lds128f(uint32_t addr, float& a, float& b, float& c, float& d) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(addr));
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(kFwdThreads, 1)
+sdpa_fwd_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                    const __grid_constant__ CUtensorMap map_v, Tc5FwdArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* s_load = smem;                                          // [kLoadStages][Q | K | V]
+    uint8_t* s_p = smem + kLoadStages * kStageBytes;                 // [2 groups][2 key blocks][128][128 B]
+    float* s_mask = reinterpret_cast<float*>(s_p + 2 * kPBytes);     // [2 groups][128]  (mask * log2 e; -inf beyond Lk)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_mask + 2 * 128);
+    uint64_t* load_full = bars;                     // [kLoadStages]  TMA -> MMA
+    uint64_t* load_empty = load_full + kLoadStages; // [kLoadStages]  MMA -> TMA
+    uint64_t* s_full = load_empty + kLoadStages;    // [2]            MMA -> softmax group (S ready)
+    uint64_t* p_full = s_full + 2;                  // [2]            softmax group -> MMA (P in smem), 128 arrivals
+    uint64_t* o_full = p_full + 2;                  // [2]            MMA -> softmax group (O ready)
+    uint64_t* acc_empty = o_full + 2;               // [2]            softmax group -> MMA (S/O columns and P buffer free), 128 arrivals
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const SdpaArgs& a = args.a;
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int Lq = (int)a.Lq, Lk = (int)a.Lk, H = (int)a.h, nk16 = args.nk16;
+    const int n_items = (int)a.B * H;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_k)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_v)) : "memory");
+        for (int i = 0; i < kLoadStages; ++i) { mbar_init(load_full + i, 1); mbar_init(load_empty + i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(s_full + i, 1); mbar_init(p_full + i, 128); mbar_init(o_full + i, 1); mbar_init(acc_empty + i, 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // TMEM columns: group g owns [g*192, g*192+128) for S and [g*192+128, g*192+192) for O
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)(Lq + 2 * nk16) * 128u;
+            int it = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const int ls = it % kLoadStages;
+                const uint32_t par = (uint32_t)(it / kLoadStages) & 1u;
+                const int b = item / H, hd = item % H;
+                mbar_wait(load_empty + ls, par ^ 1u);
+                mbar_expect_tx(load_full + ls, bytes);
+                uint8_t* st = s_load + ls * kStageBytes;
+                tma_load_2d(st, &map_q, load_full + ls, hd * kD, b * Lq);
+                tma_load_2d(st + kTileBytes, &map_k, load_full + ls, hd * kD, b * Lk);
+                tma_load_2d(st + 2 * kTileBytes, &map_v, load_full + ls, hd * kD, b * Lk);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc_s = make_idesc(128, nk16, false, false);
+            const uint32_t idesc_o = make_idesc(128, kD, false, true);
+            const int my_items = n_items > (int)blockIdx.x ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+            auto issue_s = [&](int it) {
+                const int ls = it % kLoadStages, g = it & 1;
+                mbar_wait(load_full + ls, (uint32_t)(it / kLoadStages) & 1u);
+                mbar_wait(acc_empty + g, ((uint32_t)(it >> 1) & 1u) ^ 1u);
+                tcgen05_fence_after();
+                const uint32_t q_addr = smem_u32(s_load + ls * kStageBytes), k_addr = q_addr + kTileBytes;
+                const uint32_t d_s = tmem_base + (uint32_t)(g * 192);
+#pragma unroll
+                for (int kk = 0; kk < kD / 16; ++kk)
+                    tcgen05_mma_bf16(d_s, make_smem_desc(q_addr + kk * 32, 16, 1024), make_smem_desc(k_addr + kk * 32, 16, 1024), idesc_s, kk > 0 ? 1u : 0u);
+                tcgen05_commit(s_full + g);
+            };
+            auto issue_pv = [&](int it) {
+                const int ls = it % kLoadStages, g = it & 1;
+                mbar_wait(p_full + g, (uint32_t)(it >> 1) & 1u);
+                tcgen05_fence_after();
+                const uint32_t v_addr = smem_u32(s_load + ls * kStageBytes + 2 * kTileBytes);
+                const uint32_t p_addr = smem_u32(s_p + g * kPBytes);
+                const uint32_t d_o = tmem_base + (uint32_t)(g * 192 + 128);
+                for (int ks = 0; ks < nk16 / 16; ++ks)
+                    tcgen05_mma_bf16(d_o, make_smem_desc(p_addr + (ks >> 2) * kTileBytes + (ks & 3) * 32, 16, 1024),
+                                     make_smem_desc(v_addr + ks * 2048, 8192, 1024), idesc_o, ks > 0 ? 1u : 0u);
+                tcgen05_commit(o_full + g);
+                tcgen05_commit(load_empty + ls);     // Q, K, V of this stage are no longer read
+            };
+            if (my_items > 0) issue_s(0);
+            for (int it = 0; it < my_items; ++it) {
+                if (it + 1 < my_items) issue_s(it + 1);
+                issue_pv(it);
+            }
+        }
+    } else {
+        const int g = (warp - 2) / 4;                 // softmax group
+        const int quad = warp % 4;                    // TMEM lane quadrant this warp may access
+        const int row = quad * 32 + lane;             // query row of this thread
+        const int tid_g = (warp - 2) % 4 * 32 + lane; // 0..127 inside the group
+        float* mrow = s_mask + g * 128;
+        const uint32_t mrow_u32 = smem_u32(mrow);
+        const uint32_t p_row = smem_u32(s_p + g * kPBytes) + (uint32_t)row * 128u, p_x = (uint32_t)(row & 7);
+        const uint32_t t_s = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * 192);
+        const uint32_t t_o = t_s + 128u;
+        const float sc2 = a.scale * kLog2e;
+        const int nch32 = (nk16 + 31) / 32;
+        int u = 0;
+        for (int item = blockIdx.x + g * gridDim.x; item < n_items; item += 2 * gridDim.x, ++u) {
+            const int b = item / H, hd = item % H;
+            const uint32_t par = (uint32_t)u & 1u;
+            // per-key mask row of this (sample, head), pre-multiplied by log2 e; -inf beyond Lk
+            named_bar_sync(1 + g, 128);               // the previous item's readers are done
+            {
+                float mv = -INFINITY;
+                if (tid_g < Lk) mv = a.mask.ptr ? __ldg(a.mask.ptr + (int64_t)b * a.mask.sb + (int64_t)hd * a.mask.sh + tid_g) * kLog2e : 0.0f;
+                mrow[tid_g] = mv;
+            }
+            named_bar_sync(1 + g, 128);
+            mbar_wait(s_full + g, par);
+            tcgen05_fence_after();
+            // Two passes over the S row in TMEM (row max, then exponentials), 32 columns at a time, the next chunk's tcgen05.ld
+            // in flight while the current one is processed: ~70 live registers instead of the whole 128-column row (10 warps
+            // per CTA leave 168 registers per thread; the one-pass version spilled).
+            auto load_chunk = [&](uint32_t (&r)[32], int c32) {        // columns [32 c32, +32) of S, zero beyond nk16
+                if (32 * c32 + 32 <= nk16) {
+                    tmem_ld_32x32b_x32(t_s + (uint32_t)(32 * c32), r);
+                } else {
+                    tmem_ld_32x32b_x16(t_s + (uint32_t)(32 * c32), r);
+#pragma unroll
+                    for (int j = 16; j < 32; ++j) r[j] = 0u;
+                }
+            };
+            auto scaled = [&](const uint32_t (&r)[32], int c32, float (&v)[32]) {   // v = S * scale * log2e + mask
+#pragma unroll
+                for (int q4 = 0; q4 < 8; ++q4) {
+                    float m0, m1, m2, m3;
+                    lds128f(mrow_u32 + (uint32_t)(32 * c32 + 4 * q4) * 4u, m0, m1, m2, m3);
+                    v[4 * q4] = fmaf(__uint_as_float(r[4 * q4]), sc2, m0);
+                    v[4 * q4 + 1] = fmaf(__uint_as_float(r[4 * q4 + 1]), sc2, m1);
+                    v[4 * q4 + 2] = fmaf(__uint_as_float(r[4 * q4 + 2]), sc2, m2);
+                    v[4 * q4 + 3] = fmaf(__uint_as_float(r[4 * q4 + 3]), sc2, m3);
+                }
+            };
+            uint32_t ra[32], rb[32];
+            float mx = -INFINITY;
+            load_chunk(ra, 0);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (c < nch32) {
+                    tmem_ld_wait();
+                    if (c + 1 < nch32) load_chunk((c & 1) ? ra : rb, c + 1);
+                    float v[32];
+                    scaled((c & 1) ? rb : ra, c, v);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) mx = fmaxf(fmaxf(mx, fmaxf(v[j], v[j + 1])), fmaxf(v[j + 2], v[j + 3]));
+                }
+            }
+            float l = 0.f;
+            const bool live = row < Lq;
+            load_chunk(ra, 0);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (c < nch32) {
+                    tmem_ld_wait();
+                    if (c + 1 < nch32) load_chunk((c & 1) ? ra : rb, c + 1);
+                    float v[32];
+                    scaled((c & 1) ? rb : ra, c, v);
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float p0 = ex2_approx(v[2 * j] - mx), p1 = ex2_approx(v[2 * j + 1] - mx);
+                        l += p0 + p1;
+                        pk[j] = live ? pack_bf16x2(p0, p1) : 0u;
+                    }
+                    // keys [32 c, +32) = 16-byte chunks 4c .. 4c+3 of the row; chunk i of key block i/8 sits at (i%8) ^ (row%8)
+                    const uint32_t blk = p_row + (uint32_t)(c >> 1) * kTileBytes;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        sts128u(blk + ((((uint32_t)(4 * c + i) & 7u) ^ p_x) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+                }
+            }
+            fence_proxy_async_smem();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            mbar_arrive(p_full + g);
+            mbar_wait(o_full + g, par);
+            tcgen05_fence_after();
+            uint32_t o[kD];
+            tmem_ld_32x32b_x32(t_o, o);
+            tmem_ld_32x32b_x32(t_o + 32u, o + 32);
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            mbar_arrive(acc_empty + g);               // S / O columns and the P buffer may be overwritten by item u+1 of this group
+            if (live) {
+                const float inv = 1.0f / l;
+                __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.out) + ((int64_t)b * Lq + row) * a.ldo + (int64_t)hd * kD;
+#pragma unroll
+                for (int c = 0; c < kD / 8; ++c) {
+                    uint4 w;
+                    w.x = pack_bf16x2(__uint_as_float(o[8 * c]) * inv, __uint_as_float(o[8 * c + 1]) * inv);
+                    w.y = pack_bf16x2(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv);
+                    w.z = pack_bf16x2(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv);
+                    w.w = pack_bf16x2(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv);
+                    *reinterpret_cast<uint4*>(op + 8 * c) = w;
+                }
+                if (a.lse) a.lse[((int64_t)b * H + hd) * Lq + row] = fmaf(mx, kLn2, __logf(l));
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------ backward
+// Per item (sample, head):   S = Q K^T,  dP = dO V^T                          (tcgen05, accumulators in TMEM)
+//   phase A, one thread per query row:  P = exp(S*scale + mask - lse),  delta = sum_j P dP  (== dO . O, so O is never read),
+//                                       dS = P (dP - delta);  P and dS go to shared memory as bf16 [query][key] tiles
+//   dV = P^T dO,  dK = dS^T Q,  dQ = dS K    — the SAME two tiles serve as MN-major A operands (transposed use) and as a
+//                                       K-major A operand: no transposition pass anywhere
+//   phase B, one thread per output row: TMEM -> bf16 -> global (dK, dQ scaled by 1/sqrt(d) here, in fp32)
+// warp 0 = TMA producer (Q, dO, K, V; 2 stages), warp 1 = MMA issuer, warps 2-5 = phase A, warps 6-9 = phase B, so the
+// element-wise work of item i+1 overlaps the output drain of item i and the loads of item i+2.  S(i+1) / dP(i+1) are issued
+// BEFORE dV/dK/dQ(i): phase A never waits for the three long products.
+constexpr int kBwdStages = 2;
+constexpr int kBwdStageBytes = 4 * kTileBytes;         // Q, dO, K, V
+constexpr int kBwdThreads = 64 + 2 * 128;
+constexpr int kBwdSmem = kBwdStages * kBwdStageBytes + 2 * kPBytes /*P, dS*/ + 128 * 4 /*mask row*/ + 256 /*barriers*/ + 1024 /*align*/;
+
+struct Tc5BwdArgs {
+    SdpaArgs a;
+    void *dq, *dk, *dv;
+    int64_t lddq, lddk, lddv;
+    int nk16, nq16;
+};
+
+__device__ __forceinline__ void store_row64(__nv_bfloat16* dst, const uint32_t (&r)[kD], float mul) {
+#pragma unroll
+    for (int c = 0; c < kD / 8; ++c) {
+        uint4 w;
+        w.x = pack_bf16x2(__uint_as_float(r[8 * c]) * mul, __uint_as_float(r[8 * c + 1]) * mul);
+        w.y = pack_bf16x2(__uint_as_float(r[8 * c + 2]) * mul, __uint_as_float(r[8 * c + 3]) * mul);
+        w.z = pack_bf16x2(__uint_as_float(r[8 * c + 4]) * mul, __uint_as_float(r[8 * c + 5]) * mul);
+        w.w = pack_bf16x2(__uint_as_float(r[8 * c + 6]) * mul, __uint_as_float(r[8 * c + 7]) * mul);
+        *reinterpret_cast<uint4*>(dst + 8 * c) = w;
+    }
+}
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
+sdpa_bwd_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
+                    const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v, Tc5BwdArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* s_load = smem;                                          // [kBwdStages][Q | dO | K | V]
+    uint8_t* s_p = smem + kBwdStages * kBwdStageBytes;               // P  [2 key blocks][128 queries][128 B]
+    uint8_t* s_ds = s_p + kPBytes;                                   // dS, same layout
+    float* s_mask = reinterpret_cast<float*>(s_ds + kPBytes);        // [128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_mask + 128);
+    uint64_t* load_full = bars;                     // [2]  TMA -> MMA (and phase A)
+    uint64_t* load_empty = load_full + kBwdStages;  // [2]  MMA -> TMA
+    uint64_t* sdp_full = load_empty + kBwdStages;   // MMA -> phase A: S and dP ready
+    uint64_t* pds_full = sdp_full + 1;              // phase A -> MMA: P and dS in smem, S / dP columns free   (128 arrivals)
+    uint64_t* out_full = pds_full + 1;              // MMA -> phase B (dV, dK, dQ ready) and -> phase A (P / dS tiles no longer read)
+    uint64_t* out_free = out_full + 1;              // phase B -> MMA: dV / dK / dQ columns drained             (128 arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(out_free + 1);
+
+    const SdpaArgs& a = args.a;
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int Lq = (int)a.Lq, Lk = (int)a.Lk, H = (int)a.h, nk16 = args.nk16, nq16 = args.nq16;
+    const int n_items = (int)a.B * H;
+    const int my_items = n_items > (int)blockIdx.x ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_do)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_k)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_v)) : "memory");
+        for (int i = 0; i < kBwdStages; ++i) { mbar_init(load_full + i, 1); mbar_init(load_empty + i, 1); }
+        mbar_init(sdp_full, 1); mbar_init(pds_full, 128); mbar_init(out_full, 1); mbar_init(out_free, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    constexpr uint32_t kColS = 0, kColDP = 128, kColDV = 256, kColDK = 320, kColDQ = 384;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)(2 * nq16 + 2 * nk16) * 128u;
+            for (int it = 0; it < my_items; ++it) {
+                const int item = blockIdx.x + it * gridDim.x;
+                const int ls = it % kBwdStages;
+                const int b = item / H, hd = item % H;
+                mbar_wait(load_empty + ls, ((uint32_t)(it / kBwdStages) & 1u) ^ 1u);
+                mbar_expect_tx(load_full + ls, bytes);
+                uint8_t* st = s_load + ls * kBwdStageBytes;
+                tma_load_2d(st, &map_q, load_full + ls, hd * kD, b * Lq);
+                tma_load_2d(st + kTileBytes, &map_do, load_full + ls, hd * kD, b * Lq);
+                tma_load_2d(st + 2 * kTileBytes, &map_k, load_full + ls, hd * kD, b * Lk);
+                tma_load_2d(st + 3 * kTileBytes, &map_v, load_full + ls, hd * kD, b * Lk);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc_s = make_idesc(128, nk16, false, false);      // S, dP: A, B K-major
+            const uint32_t idesc_t = make_idesc(128, kD, true, true);          // dV, dK: A = tile^T (MN-major), B MN-major
+            const uint32_t idesc_q = make_idesc(128, kD, false, true);         // dQ: A K-major, B MN-major
+            auto issue_sdp = [&](int it) {
+                const int ls = it % kBwdStages;
+                mbar_wait(load_full + ls, (uint32_t)(it / kBwdStages) & 1u);
+                tcgen05_fence_after();
+                const uint32_t q_addr = smem_u32(s_load + ls * kBwdStageBytes), do_addr = q_addr + kTileBytes, k_addr = q_addr + 2 * kTileBytes,
+                               v_addr = q_addr + 3 * kTileBytes;
+#pragma unroll
+                for (int kk = 0; kk < kD / 16; ++kk)
+                    tcgen05_mma_bf16(tmem_base + kColS, make_smem_desc(q_addr + kk * 32, 16, 1024), make_smem_desc(k_addr + kk * 32, 16, 1024), idesc_s, kk > 0 ? 1u : 0u);
+#pragma unroll
+                for (int kk = 0; kk < kD / 16; ++kk)
+                    tcgen05_mma_bf16(tmem_base + kColDP, make_smem_desc(do_addr + kk * 32, 16, 1024), make_smem_desc(v_addr + kk * 32, 16, 1024), idesc_s, kk > 0 ? 1u : 0u);
+                tcgen05_commit(sdp_full);
+            };
+            if (my_items > 0) issue_sdp(0);
+            for (int it = 0; it < my_items; ++it) {
+                const int ls = it % kBwdStages;
+                const uint32_t par = (uint32_t)it & 1u;
+                mbar_wait(pds_full, par);                 // P(it), dS(it) written; S / dP columns consumed
+                if (it + 1 < my_items) issue_sdp(it + 1);
+                mbar_wait(out_free, par ^ 1u);            // dV / dK / dQ of item it-1 drained
+                tcgen05_fence_after();
+                const uint32_t q_addr = smem_u32(s_load + ls * kBwdStageBytes), do_addr = q_addr + kTileBytes, k_addr = q_addr + 2 * kTileBytes;
+                const uint32_t p_addr = smem_u32(s_p), ds_addr = smem_u32(s_ds);
+                // dV[key, d] = sum_q P[q, key] dO[q, d]: A = P^T (MN-major: 64-key blocks kTileBytes apart, 16 queries = 2048 B), B = dO (MN-major)
+                for (int ks = 0; ks < nq16 / 16; ++ks)
+                    tcgen05_mma_bf16(tmem_base + kColDV, make_smem_desc(p_addr + ks * 2048, kTileBytes, 1024), make_smem_desc(do_addr + ks * 2048, 8192, 1024), idesc_t, ks > 0 ? 1u : 0u);
+                for (int ks = 0; ks < nq16 / 16; ++ks)
+                    tcgen05_mma_bf16(tmem_base + kColDK, make_smem_desc(ds_addr + ks * 2048, kTileBytes, 1024), make_smem_desc(q_addr + ks * 2048, 8192, 1024), idesc_t, ks > 0 ? 1u : 0u);
+                // dQ[q, d] = sum_key dS[q, key] K[key, d]: A = dS (K-major), B = K (MN-major)
+                for (int ks = 0; ks < nk16 / 16; ++ks)
+                    tcgen05_mma_bf16(tmem_base + kColDQ, make_smem_desc(ds_addr + (ks >> 2) * kTileBytes + (ks & 3) * 32, 16, 1024),
+                                     make_smem_desc(k_addr + ks * 2048, 8192, 1024), idesc_q, ks > 0 ? 1u : 0u);
+                tcgen05_commit(out_full);
+                tcgen05_commit(load_empty + ls);
+            }
+        }
+    } else if (warp < 6) {
+        // ---------------------------------------------------------------- phase A: one thread per query row
+        const int quad = warp % 4, row = quad * 32 + lane, tid_g = (warp - 2) * 32 + lane;
+        const uint32_t mrow_u32 = smem_u32(s_mask);
+        const uint32_t t_s = tmem_base + ((uint32_t)(quad * 32) << 16) + kColS, t_dp = tmem_base + ((uint32_t)(quad * 32) << 16) + kColDP;
+        const uint32_t p_row = smem_u32(s_p) + (uint32_t)row * 128u, ds_row = smem_u32(s_ds) + (uint32_t)row * 128u, p_x = (uint32_t)(row & 7);
+        const float sc2 = a.scale * kLog2e;
+        const int nch = nk16 / 16;
+        const bool live = row < Lq;
+        for (int it = 0; it < my_items; ++it) {
+            const int item = blockIdx.x + it * gridDim.x;
+            const int b = item / H, hd = item % H;
+            const uint32_t par = (uint32_t)it & 1u;
+            named_bar_sync(1, 128);
+            {
+                float mv = -INFINITY;
+                if (tid_g < Lk) mv = a.mask.ptr ? __ldg(a.mask.ptr + (int64_t)b * a.mask.sb + (int64_t)hd * a.mask.sh + tid_g) * kLog2e : 0.0f;
+                s_mask[tid_g] = mv;
+            }
+            const float lse2 = live ? __ldg(a.lse + ((int64_t)b * H + hd) * Lq + row) * kLog2e : 0.0f;
+            named_bar_sync(1, 128);
+            mbar_wait(sdp_full, par);
+            tcgen05_fence_after();
+            auto probs = [&](const uint32_t (&rs)[16], int ch, float (&pv)[16]) {       // P for keys [16 ch, +16)
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    float m0, m1, m2, m3;
+                    lds128f(mrow_u32 + (uint32_t)(16 * ch + 4 * q4) * 4u, m0, m1, m2, m3);
+                    pv[4 * q4] = ex2_approx(fmaf(__uint_as_float(rs[4 * q4]), sc2, m0) - lse2);
+                    pv[4 * q4 + 1] = ex2_approx(fmaf(__uint_as_float(rs[4 * q4 + 1]), sc2, m1) - lse2);
+                    pv[4 * q4 + 2] = ex2_approx(fmaf(__uint_as_float(rs[4 * q4 + 2]), sc2, m2) - lse2);
+                    pv[4 * q4 + 3] = ex2_approx(fmaf(__uint_as_float(rs[4 * q4 + 3]), sc2, m3) - lse2);
+                }
+            };
+            uint32_t sa[16], da[16], sb[16], db[16];
+            // pass 1: delta = sum_j P_j dP_j
+            float delta = 0.f;
+            tmem_ld_32x32b_x16(t_s, sa); tmem_ld_32x32b_x16(t_dp, da);
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+                if (ch < nch) {
+                    tmem_ld_wait();
+                    if (ch + 1 < nch) {
+                        tmem_ld_32x32b_x16(t_s + (uint32_t)(16 * (ch + 1)), (ch & 1) ? sa : sb);
+                        tmem_ld_32x32b_x16(t_dp + (uint32_t)(16 * (ch + 1)), (ch & 1) ? da : db);
+                    }
+                    float pv[16];
+                    probs((ch & 1) ? sb : sa, ch, pv);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) delta = fmaf(pv[j], __uint_as_float(((ch & 1) ? db : da)[j]), delta);
+                }
+            }
+            // the P / dS tiles are still being read by dV/dK/dQ of the previous item until out_full(it-1) fires
+            if (it > 0) mbar_wait(out_full, par ^ 1u);
+            // pass 2: P and dS = P (dP - delta) -> shared memory (bf16, [query][key], SWIZZLE_128B rows)
+            tmem_ld_32x32b_x16(t_s, sa); tmem_ld_32x32b_x16(t_dp, da);
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+                if (ch < nch) {
+                    tmem_ld_wait();
+                    if (ch + 1 < nch) {
+                        tmem_ld_32x32b_x16(t_s + (uint32_t)(16 * (ch + 1)), (ch & 1) ? sa : sb);
+                        tmem_ld_32x32b_x16(t_dp + (uint32_t)(16 * (ch + 1)), (ch & 1) ? da : db);
+                    }
+                    float pv[16];
+                    probs((ch & 1) ? sb : sa, ch, pv);
+                    uint32_t pp[8], pd[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float d0 = pv[2 * j] * (__uint_as_float(((ch & 1) ? db : da)[2 * j]) - delta);
+                        const float d1 = pv[2 * j + 1] * (__uint_as_float(((ch & 1) ? db : da)[2 * j + 1]) - delta);
+                        pp[j] = live ? pack_bf16x2(pv[2 * j], pv[2 * j + 1]) : 0u;
+                        pd[j] = live ? pack_bf16x2(d0, d1) : 0u;
+                    }
+                    const uint32_t off = (uint32_t)(ch >> 2) * kTileBytes;
+                    const uint32_t c0 = ((((uint32_t)(2 * ch)) & 7u) ^ p_x) << 4, c1 = ((((uint32_t)(2 * ch + 1)) & 7u) ^ p_x) << 4;
+                    sts128u(p_row + off + c0, pp[0], pp[1], pp[2], pp[3]);
+                    sts128u(p_row + off + c1, pp[4], pp[5], pp[6], pp[7]);
+                    sts128u(ds_row + off + c0, pd[0], pd[1], pd[2], pd[3]);
+                    sts128u(ds_row + off + c1, pd[4], pd[5], pd[6], pd[7]);
+                }
+            }
+            fence_proxy_async_smem();
+            tcgen05_fence_before();
+            mbar_arrive(pds_full);
+        }
+    } else {
+        // ---------------------------------------------------------------- phase B: one thread per output row (key for dV, dK; query for dQ)
+        const int quad = warp % 4, row = quad * 32 + lane;
+        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
+        for (int it = 0; it < my_items; ++it) {
+            const int item = blockIdx.x + it * gridDim.x;
+            const int b = item / H, hd = item % H;
+            mbar_wait(out_full, (uint32_t)it & 1u);
+            tcgen05_fence_after();
+            uint32_t r0[kD], r1[kD];
+            tmem_ld_32x32b_x32(t_row + kColDV, r0); tmem_ld_32x32b_x32(t_row + kColDV + 32u, r0 + 32);
+            tmem_ld_32x32b_x32(t_row + kColDK, r1); tmem_ld_32x32b_x32(t_row + kColDK + 32u, r1 + 32);
+            tmem_ld_wait();
+            if (row < Lk) {
+                store_row64(reinterpret_cast<__nv_bfloat16*>(args.dv) + ((int64_t)b * Lk + row) * args.lddv + (int64_t)hd * kD, r0, 1.0f);
+                store_row64(reinterpret_cast<__nv_bfloat16*>(args.dk) + ((int64_t)b * Lk + row) * args.lddk + (int64_t)hd * kD, r1, a.scale);
+            }
+            tmem_ld_32x32b_x32(t_row + kColDQ, r0); tmem_ld_32x32b_x32(t_row + kColDQ + 32u, r0 + 32);
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            mbar_arrive(out_free);
+            if (row < Lq) store_row64(reinterpret_cast<__nv_bfloat16*>(args.dq) + ((int64_t)b * Lq + row) * args.lddq + (int64_t)hd * kD, r0, a.scale);
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+}  // namespace
+
+bool sdpa_fwd_tc5_supported(const SdpaArgs& a) {
+    static const bool off = [] { const char* e = getenv("OVQA_SDPA_TC5"); return e && e[0] == '0'; }();
+    if (off) return false;
+    if (a.geo.boxes || a.att) return false;
+    if (a.dk != kD || a.dv != kD || a.Lq > 128 || a.Lk > 128 || a.Lq < 1 || a.Lk < 1) return false;
+    if (a.mask.ptr && a.mask.sq != 0) return false;                           // per-key (padding) masks only
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (!al16(a.q) || !al16(a.k) || !al16(a.v) || !al16(a.out) || (a.ldq % 8) || (a.ldk % 8) || (a.ldv % 8) || (a.ldo % 8)) return false;
+    return a.B * a.h >= 1;
+}
+
+int sdpa_fwd_tc5_bf16(const SdpaArgs& a, cudaStream_t st) {
+    Tc5FwdArgs args{a, (int)((a.Lk + 15) / 16 * 16)};
+    CUtensorMap mq, mk, mv;
+    int rc;
+    const uint64_t cols = (uint64_t)a.h * kD;
+    if ((rc = make_tma_map_bf16(&mq, a.q, cols, (uint64_t)(a.B * a.Lq), (uint64_t)a.ldq, kD, (uint32_t)a.Lq))) return rc;
+    if ((rc = make_tma_map_bf16(&mk, a.k, cols, (uint64_t)(a.B * a.Lk), (uint64_t)a.ldk, kD, (uint32_t)args.nk16))) return rc;
+    if ((rc = make_tma_map_bf16(&mv, a.v, cols, (uint64_t)(a.B * a.Lk), (uint64_t)a.ldv, kD, (uint32_t)args.nk16))) return rc;
+    static bool attr_set = false;
+    if (!attr_set) { OVQA_CUDA_OK(cudaFuncSetAttribute(sdpa_fwd_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem)); attr_set = true; }
+    const int64_t items = a.B * a.h;
+    const int grid = (int)(items < sm_count() ? items : sm_count());
+    sdpa_fwd_tc5_kernel<<<grid, kFwdThreads, kFwdSmem, st>>>(mq, mk, mv, args);
+    OVQA_LAUNCH_OK();
+    return OVQA_OK;
+}
+
+bool sdpa_bwd_tc5_supported(const SdpaArgs& a, const void* dout, const void* dq, const void* dk, const void* dv, int64_t lddo, int64_t lddq,
+                            int64_t lddk, int64_t lddv) {
+    static const bool off = [] { const char* e = getenv("OVQA_SDPA_TC5_BWD"); return e && e[0] == '0'; }();
+    if (off || !sdpa_fwd_tc5_supported(a) || !a.lse) return false;
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    return al16(dout) && al16(dq) && al16(dk) && al16(dv) && lddo % 8 == 0 && lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0;
+}
+
+int sdpa_bwd_tc5_bf16(const SdpaArgs& a, const void* dout, void* dq, void* dk, void* dv, int64_t lddo, int64_t lddq, int64_t lddk,
+                      int64_t lddv, cudaStream_t st) {
+    Tc5BwdArgs args{a, dq, dk, dv, lddq, lddk, lddv, (int)((a.Lk + 15) / 16 * 16), (int)((a.Lq + 15) / 16 * 16)};
+    CUtensorMap mq, mdo, mk, mv;
+    int rc;
+    const uint64_t cols = (uint64_t)a.h * kD;
+    if ((rc = make_tma_map_bf16(&mq, a.q, cols, (uint64_t)(a.B * a.Lq), (uint64_t)a.ldq, kD, (uint32_t)args.nq16))) return rc;
+    if ((rc = make_tma_map_bf16(&mdo, dout, cols, (uint64_t)(a.B * a.Lq), (uint64_t)lddo, kD, (uint32_t)args.nq16))) return rc;
+    if ((rc = make_tma_map_bf16(&mk, a.k, cols, (uint64_t)(a.B * a.Lk), (uint64_t)a.ldk, kD, (uint32_t)args.nk16))) return rc;
+    if ((rc = make_tma_map_bf16(&mv, a.v, cols, (uint64_t)(a.B * a.Lk), (uint64_t)a.ldv, kD, (uint32_t)args.nk16))) return rc;
+    static bool attr_set = false;
+    if (!attr_set) { OVQA_CUDA_OK(cudaFuncSetAttribute(sdpa_bwd_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem)); attr_set = true; }
+    const int64_t items = a.B * a.h;
+    const int grid = (int)(items < sm_count() ? items : sm_count());
+    sdpa_bwd_tc5_kernel<<<grid, kBwdThreads, kBwdSmem, st>>>(mq, mdo, mk, mv, args);
+    OVQA_LAUNCH_OK();
+    return OVQA_OK;
+}
+
+}  // namespace ovqa
