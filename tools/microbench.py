@@ -82,6 +82,20 @@ def bench_gemm():
              cublas_tflops=fl / t_ref / 1e6, frac_of_peak=fl / t_ours / 1e6 / PEAKS["bf16_tflops"])
 
 
+def bench_wgrad_split():
+    """Split-K sweep for the weight-gradient GEMMs (dW = dy^T x, k = B*L rows): atomics per output element grow with the
+    split, SM occupancy with the number of work units."""
+    B = 256
+    for tag, m, n, k in [("wgrad fc_o 512x512", 512, 512, B * 100), ("wgrad qkv 1536x512", 1536, 512, B * 100), ("wgrad fc1 2048x512", 2048, 512, B * 100),
+                         ("wgrad fc2 512x2048", 512, 2048, B * 100), ("wgrad fc_o text 512x512", 512, 512, B * 30), ("wgrad fc1 text", 2048, 512, B * 30)]:
+        a = torch.randn((k, m), device=dev).bfloat16()
+        b = torch.randn((k, n), device=dev).bfloat16()
+        out = torch.zeros((m, n), device=dev, dtype=torch.float32)
+        for sk in (0, 1, 2, 3, 4, 6, 9, 12, 18, 24, 37):
+            t = timeit(lambda: ops.gemm(a, b, a_op="T", b_op="T", out=out, split_k=sk), iters=10)
+            emit(kind="wgrad_split", tag=tag, m=m, n=n, k=k, split_k=sk, us=t, tflops=2.0 * m * n * k / t / 1e6)
+
+
 def bench_sdpa():
     for (B, h, Lq, Lk, d) in [(256, 8, 100, 100, 64), (256, 8, 30, 30, 64), (256, 8, 100, 30, 64), (256, 8, 30, 100, 64),
                               (1024, 8, 30, 100, 64), (256, 8, 30, 600, 64), (64, 8, 182, 182, 96), (4096, 8, 30, 100, 64)]:
@@ -182,4 +196,4 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "epi", "sdpa", "ln", "mha"]
     emit(kind="meta", gpu=torch.cuda.get_device_name(0), peaks=PEAKS)
     for w in which:
-        {"gemm": bench_gemm, "epi": bench_gemm_epilogues, "sdpa": bench_sdpa, "ln": bench_ln, "mha": bench_mha}[w]()
+        {"gemm": bench_gemm, "wgrad": bench_wgrad_split, "epi": bench_gemm_epilogues, "sdpa": bench_sdpa, "ln": bench_ln, "mha": bench_mha}[w]()
