@@ -64,6 +64,9 @@ uint64_t    ovqa_launch_count(void);              /* kernels launched by this li
  *   offset_base: optional DEVICE pointer to a u64 added to `offset` inside the kernel.  A host that replays a captured
  *             CUDA graph advances that word on the device between replays (ovqa_advance_u64), so every replay draws
  *             fresh dropout masks although the launch parameters are frozen in the graph.
+ *   colsum_out: optional fp32 [n], += the column sums of the final C (atomically; the caller zero-fills).  When C is the
+ *             gradient of a Linear's output this IS that Linear's bias gradient: the backward pass needs no separate
+ *             reduction over the B*L rows (autograd of nn.Linear's bias at attentions.py:49-51, positionwise_feed_forward.py:24).
  *   split_k>1 (wgrad): partial sums are atomically added into fp32 C, which the caller zero-fills (or
  *             pre-loads); bias/epilogue flags are not allowed with split_k != 1.  split_k == 0: the library
  *             picks the split (and tile width) that fills the SMs; C must be zero-filled as for split_k>1.
@@ -78,6 +81,7 @@ int ovqa_gemm(const void* A, const void* B, void* C,
               const float* residual, int64_t ld_res,
               void* c2_bf16, int64_t ldc2,
               float dropout_p, uint64_t seed, uint64_t offset, const uint64_t* offset_base,
+              float* colsum_out,
               int split_k, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------

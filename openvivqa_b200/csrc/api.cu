@@ -54,8 +54,8 @@ extern "C" uint64_t ovqa_launch_count(void) { return __atomic_load_n(&g_launch_c
 extern "C" int ovqa_gemm(const void* A, const void* B, void* C, int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb,
                          int64_t ldc, int a_op, int b_op, int ab_dtype, int c_dtype, float alpha, float beta, const float* bias,
                          int epi_flags, const void* aux_in, void* aux_out, int64_t ld_aux, const float* residual, int64_t ld_res,
-                         void* c2_bf16, int64_t ldc2, float dropout_p, uint64_t seed, uint64_t offset, const uint64_t* offset_base, int split_k,
-                         void* stream) {
+                         void* c2_bf16, int64_t ldc2, float dropout_p, uint64_t seed, uint64_t offset, const uint64_t* offset_base,
+                         float* colsum_out, int split_k, void* stream) {
     if (!A || !B || !C || m < 0 || n < 0 || k < 0) return OVQA_ERR_BAD_ARG;
     if ((a_op != OVQA_OP_N && a_op != OVQA_OP_T) || (b_op != OVQA_OP_N && b_op != OVQA_OP_T)) return OVQA_ERR_BAD_ARG;
     if ((ab_dtype != OVQA_F32 && ab_dtype != OVQA_BF16) || (c_dtype != OVQA_F32 && c_dtype != OVQA_BF16)) return OVQA_ERR_BAD_ARG;
@@ -63,9 +63,9 @@ extern "C" int ovqa_gemm(const void* A, const void* B, void* C, int64_t m, int64
     if ((epi_flags & (OVQA_EPI_DGELU | OVQA_EPI_MUL_AUX)) && !aux_in) return OVQA_ERR_BAD_ARG;
     if ((epi_flags & OVQA_EPI_SAVE_DGELU) && !((epi_flags & OVQA_EPI_GELU) && aux_out)) return OVQA_ERR_BAD_ARG;
     if (beta != 0.f && c_dtype != OVQA_F32) return OVQA_ERR_BAD_ARG;
-    if (split_k != 1 && (bias || epi_flags || aux_out || residual || c2_bf16 || dropout_p > 0.f || beta != 0.f)) return OVQA_ERR_BAD_ARG;
+    if (split_k != 1 && (bias || epi_flags || aux_out || residual || c2_bf16 || dropout_p > 0.f || beta != 0.f || colsum_out)) return OVQA_ERR_BAD_ARG;
     if (m == 0 || n == 0) return OVQA_OK;
-    Epilogue e{alpha, beta, bias, epi_flags, aux_in, aux_out, ld_aux, residual, ld_res, c2_bf16, ldc2, dropout_p, seed, offset, offset_base, c_dtype};
+    Epilogue e{alpha, beta, bias, epi_flags, aux_in, aux_out, ld_aux, residual, ld_res, c2_bf16, ldc2, dropout_p, seed, offset, offset_base, c_dtype, colsum_out};
     cudaStream_t st = (cudaStream_t)stream;
     if (ab_dtype == OVQA_F32) return gemm_simt_f32((const float*)A, (const float*)B, C, m, n, k, lda, ldb, ldc, a_op, b_op, e, split_k, st);
     // bf16: tensor cores.  Operand pitches must allow TMA (checked there); the epilogue picks 16-byte vector accesses
@@ -82,7 +82,7 @@ extern "C" int ovqa_gemm_bf16_simt(const void* A, const void* B, void* C, int64_
                                    int64_t ldc, int a_op, int b_op, int c_dtype, float alpha, const float* bias, int epi_flags,
                                    void* stream) {
     if (!A || !B || !C) return OVQA_ERR_BAD_ARG;
-    Epilogue e{alpha, 0.f, bias, epi_flags, nullptr, nullptr, 0, nullptr, 0, nullptr, 0, 0.f, 0, 0, nullptr, c_dtype};
+    Epilogue e{alpha, 0.f, bias, epi_flags, nullptr, nullptr, 0, nullptr, 0, nullptr, 0, 0.f, 0, 0, nullptr, c_dtype, nullptr};
     return gemm_simt_bf16((const __nv_bfloat16*)A, (const __nv_bfloat16*)B, C, m, n, k, lda, ldb, ldc, a_op, b_op, e, 1, (cudaStream_t)stream);
 }
 

@@ -514,15 +514,26 @@ sdpa_bwd_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 
 }  // namespace
 
-bool sdpa_fwd_tc5_supported(const SdpaArgs& a) {
-    static const bool off = [] { const char* e = getenv("OVQA_SDPA_TC5"); return e && e[0] == '0'; }();
-    if (off) return false;
+// OVQA_SDPA_TC5 / OVQA_SDPA_TC5_BWD: "0" = never, "1" = whenever the shape is supported, unset = where it is the faster core
+// (profiles/r01f: a 128-row tile that is 3/4 padding loses to the 16-row warp tiles of attention_mma.cu).  Read per call.
+static int tc5_mode(const char* name) {
+    const char* e = getenv(name);
+    return !e ? -1 : e[0] == '0' ? 0 : 1;
+}
+
+static bool tc5_shape_ok(const SdpaArgs& a) {
     if (a.geo.boxes || a.att) return false;
     if (a.dk != kD || a.dv != kD || a.Lq > 128 || a.Lk > 128 || a.Lq < 1 || a.Lk < 1) return false;
     if (a.mask.ptr && a.mask.sq != 0) return false;                           // per-key (padding) masks only
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     if (!al16(a.q) || !al16(a.k) || !al16(a.v) || !al16(a.out) || (a.ldq % 8) || (a.ldk % 8) || (a.ldv % 8) || (a.ldo % 8)) return false;
     return a.B * a.h >= 1;
+}
+
+bool sdpa_fwd_tc5_supported(const SdpaArgs& a) {
+    const int mode = tc5_mode("OVQA_SDPA_TC5");
+    if (mode == 0 || !tc5_shape_ok(a)) return false;
+    return mode == 1 || a.Lq > 48;
 }
 
 int sdpa_fwd_tc5_bf16(const SdpaArgs& a, cudaStream_t st) {
@@ -544,8 +555,9 @@ int sdpa_fwd_tc5_bf16(const SdpaArgs& a, cudaStream_t st) {
 
 bool sdpa_bwd_tc5_supported(const SdpaArgs& a, const void* dout, const void* dq, const void* dk, const void* dv, int64_t lddo, int64_t lddq,
                             int64_t lddk, int64_t lddv) {
-    static const bool off = [] { const char* e = getenv("OVQA_SDPA_TC5_BWD"); return e && e[0] == '0'; }();
-    if (off || !sdpa_fwd_tc5_supported(a) || !a.lse) return false;
+    const int mode = tc5_mode("OVQA_SDPA_TC5_BWD");
+    if (mode == 0 || !tc5_shape_ok(a) || !a.lse) return false;
+    if (mode != 1 && a.Lq <= 48 && a.Lk <= 48) return false;
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     return al16(dout) && al16(dq) && al16(dk) && al16(dv) && lddo % 8 == 0 && lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0;
 }

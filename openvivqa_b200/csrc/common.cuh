@@ -202,6 +202,7 @@ struct Epilogue {
     uint64_t seed, offset;
     const uint64_t* offset_base;   // device word added to `offset` (CUDA-graph replays), or NULL
     int c_dtype;
+    float* colsum;                 // fp32 [n] += column sums of the final C (the bias gradient of the layer that consumes dC), or NULL
 };
 __device__ __forceinline__ uint64_t effective_offset(uint64_t offset, const uint64_t* base) { return base ? offset + __ldg(base) : offset; }
 
@@ -219,6 +220,7 @@ __device__ __forceinline__ float epilogue_value(const Epilogue& e, float acc, in
     v *= ds;
     if (e.residual) v += __ldg(e.residual + row * e.ld_res + col);
     if (e.beta != 0.0f && c_old_ptr) v += e.beta * to_f32<TC>(*c_old_ptr);
+    if (e.colsum) atomicAdd(e.colsum + col, v);
     return v;
 }
 

@@ -51,7 +51,7 @@ enum { EPI_PLAIN = 0, EPI_FULL = 1, EPI_SPLITK = 2 };   // alpha/bias only | eve
 // IPC of 0.09 per warp).  FEAT >= 0 is a compile-time feature set for the combinations the attention / feed-forward blocks
 // actually launch: no feature tests, the operands a pass needs are requested before the accumulator is read, and the eight
 // elements of a pass are independent instruction streams.
-enum : int { F_RUNTIME = -1, F_BIAS = 1, F_GELU = 2, F_SAVE_D = 4, F_MULAUX = 8, F_DROP = 16, F_RES = 32 };
+enum : int { F_RUNTIME = -1, F_BIAS = 1, F_GELU = 2, F_SAVE_D = 4, F_MULAUX = 8, F_DROP = 16, F_RES = 32, F_COLSUM = 64 };
 
 __device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -76,6 +76,22 @@ template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bflo
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
     const float2 p0 = unpack_bf16x2(u.x), p1 = unpack_bf16x2(u.y), p2 = unpack_bf16x2(u.z), p3 = unpack_bf16x2(u.w);
     v[0] = p0.x; v[1] = p0.y; v[2] = p1.x; v[3] = p1.y; v[4] = p2.x; v[5] = p2.y; v[6] = p3.x; v[7] = p3.y;
+}
+// Column sums of a 32 x 32 chunk: every lane holds partial sums of its 8 columns over the rows it finished (rows rr, rr+8, ...);
+// the 8 lanes with the same column group (lane % 4) are combined by shuffles, lanes 0..3 add the chunk's 32 sums to colsum[].
+__device__ __forceinline__ void colsum_flush(float* __restrict__ colsum, int64_t col, const float (&cs)[8], int lane) {
+    float t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        t[j] = cs[j];
+        t[j] += __shfl_xor_sync(0xffffffffu, t[j], 4);
+        t[j] += __shfl_xor_sync(0xffffffffu, t[j], 8);
+        t[j] += __shfl_xor_sync(0xffffffffu, t[j], 16);
+    }
+    if (lane < 4) {
+        atomicAdd(reinterpret_cast<float4*>(colsum + col), make_float4(t[0], t[1], t[2], t[3]));
+        atomicAdd(reinterpret_cast<float4*>(colsum + col + 4), make_float4(t[4], t[5], t[6], t[7]));
+    }
 }
 // slow path for ragged column tails / pitches that do not allow 16-byte vectors: one element, every feature
 template <typename TC>
@@ -217,7 +233,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                             (MODE != EPI_FULL ||
                              ((!epi.residual || (epi.ld_res % 4 == 0 && al16(epi.residual))) &&
                               (!(epi.aux_in || epi.aux_out) || (epi.ld_aux % kCVec == 0 && al16(epi.aux_in) && al16(epi.aux_out))) &&
-                              (!epi.c2 || (epi.ldc2 % 8 == 0 && al16(epi.c2))) && (epi.dropout_p <= 0.f || n % 8 == 0)));
+                              (!epi.c2 || (epi.ldc2 % 8 == 0 && al16(epi.c2))) && (epi.dropout_p <= 0.f || n % 8 == 0) && al16(epi.colsum)));
         // FULL-mode features, hoisted (warp-uniform)
         const bool f_gelu = MODE == EPI_FULL && (epi.flags & OVQA_EPI_GELU), f_dgelu = MODE == EPI_FULL && (epi.flags & OVQA_EPI_DGELU);
         const bool f_save_d = MODE == EPI_FULL && (epi.flags & OVQA_EPI_SAVE_DGELU) && (epi.flags & OVQA_EPI_GELU) && epi.aux_out;
@@ -228,6 +244,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         TC* __restrict__ aux_out = MODE == EPI_FULL ? reinterpret_cast<TC*>(epi.aux_out) : nullptr;
         __nv_bfloat16* __restrict__ c2 = MODE == EPI_FULL ? reinterpret_cast<__nv_bfloat16*>(epi.c2) : nullptr;
         const float beta = MODE == EPI_FULL ? epi.beta : 0.f;
+        float* __restrict__ colsum = (MODE == EPI_FULL && (FEAT < 0 || (FEAT & F_COLSUM))) ? epi.colsum : nullptr;
         const float drop_p = epi.dropout_p, inv_keep = f_drop ? 1.0f / (1.0f - epi.dropout_p) : 1.0f;
         const uint64_t seed = epi.seed, rng_offset = f_drop ? effective_offset(epi.offset, epi.offset_base) : 0;
         const uint32_t thr_hi = dropout_threshold_hi(drop_p);
@@ -250,7 +267,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                 if constexpr (MODE == EPI_FULL && FEAT >= 0) {
                     if (fast) {                                           // warp-uniform
                         constexpr bool kBias = FEAT & F_BIAS, kGelu = FEAT & F_GELU, kSave = FEAT & F_SAVE_D, kMul = FEAT & F_MULAUX,
-                                       kDrop = FEAT & F_DROP, kRes = FEAT & F_RES;
+                                       kDrop = FEAT & F_DROP, kRes = FEAT & F_RES, kColsum = FEAT & F_COLSUM;
                         static_assert(!(kMul && kRes) && !(kSave && !kGelu), "unsupported specialised epilogue");
                         const float k_out = kDrop ? inv_keep : 1.0f;      // dropout keep-scale, folded into the constants below
                         const float a_s = (kGelu ? 1.0f : k_out) * alpha;
@@ -299,6 +316,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                         }
                         __syncwarp();
                         const GeluK gk(k_out);
+                        float cs[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) cs[j] = 0.f;
                         const uint64_t ctr0 = rng_offset + (uint64_t)((row_base * n + col) >> 3);   // n % 8 == 0 (vec_ok): + n per pass
 #pragma unroll
                         for (int p = 0; p < 4; ++p) {
@@ -336,15 +356,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                             if (row < m) {
                                 store8<TC>(C + row * ldc + col, v);
                                 if constexpr (kSave) store8<TC>(aux_out + row * ld_aux + col, g);
+                                if constexpr (kColsum) {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) cs[j] += v[j];
+                                }
                             }
                         }
+                        if constexpr (kColsum) colsum_flush(colsum, col, cs, lane);
                         __syncwarp();
                         continue;
                     }
                 }
-                float b8[8];
+                float b8[8], cs[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) b8[j] = 0.f;
+                for (int j = 0; j < 8; ++j) b8[j] = cs[j] = 0.f;
                 if (fast && bias) load8<float>(bias + col, b8);
                 {   // TMEM -> registers (row per lane) -> swizzled scratch
                     uint32_t r[32];
@@ -436,7 +461,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                     store8<TC>(C + row * ldc + col, v);
                     if constexpr (MODE == EPI_FULL) {
                         if (c2) store8<__nv_bfloat16>(c2 + row * ldc2 + col, v);
+                        if (colsum) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) cs[j] += v[j];
+                        }
                     }
+                }
+                if constexpr (MODE == EPI_FULL) {
+                    if (colsum && fast) colsum_flush(colsum, col, cs, lane);      // (the scalar path adds element by element)
                 }
                 __syncwarp();                                             // scratch is rewritten by the next chunk
             }
@@ -531,13 +563,14 @@ int launch(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, int64_t m, i
     if (split_k > num_k_blocks) split_k = num_k_blocks;
     const int64_t tiles = ((m + BM - 1) / BM) * ((n + BN - 1) / BN) * split_k;
     const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-    const bool full = epi.flags || epi.aux_in || epi.aux_out || epi.residual || epi.c2 || epi.dropout_p > 0.f || epi.beta != 0.f;
+    const bool full = epi.flags || epi.aux_in || epi.aux_out || epi.residual || epi.c2 || epi.dropout_p > 0.f || epi.beta != 0.f || epi.colsum;
     const int mode = split_k > 1 ? EPI_SPLITK : full ? EPI_FULL : EPI_PLAIN;
     // compile-time feature set of this launch, if it is one of the specialised combinations (else F_RUNTIME)
     int feat = F_RUNTIME;
     if (mode == EPI_FULL && !epi.c2 && epi.beta == 0.f && !(epi.flags & OVQA_EPI_DGELU) && !(epi.aux_out && !(epi.flags & OVQA_EPI_SAVE_DGELU))) {
         feat = (epi.bias ? F_BIAS : 0) | ((epi.flags & OVQA_EPI_GELU) ? F_GELU : 0) | ((epi.flags & OVQA_EPI_SAVE_DGELU) ? F_SAVE_D : 0) |
-               ((epi.flags & OVQA_EPI_MUL_AUX) ? F_MULAUX : 0) | (epi.dropout_p > 0.f ? F_DROP : 0) | (epi.residual ? F_RES : 0);
+               ((epi.flags & OVQA_EPI_MUL_AUX) ? F_MULAUX : 0) | (epi.dropout_p > 0.f ? F_DROP : 0) | (epi.residual ? F_RES : 0) |
+               (epi.colsum ? F_COLSUM : 0);
     }
 #define OVQA_GO(TC_, MODE_, FEAT_)                                                                                              \
     do {                                                                                                                       \
@@ -561,6 +594,8 @@ int launch(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, int64_t m, i
         else if (kFwd && feat == (F_BIAS | F_GELU | F_SAVE_D)) OVQA_GO(__nv_bfloat16, EPI_FULL, (kFwd ? F_BIAS | F_GELU | F_SAVE_D : F_RUNTIME));                     // fc1, training, p = 0
         else if (kFwd && feat == (F_BIAS | F_GELU)) OVQA_GO(__nv_bfloat16, EPI_FULL, (kFwd ? F_BIAS | F_GELU : F_RUNTIME));                                           // fc1, eval
         else if (kDgrad && feat == F_MULAUX) OVQA_GO(__nv_bfloat16, EPI_FULL, (kDgrad ? F_MULAUX : F_RUNTIME));                                                       // dpre = (dy W2) * saved derivative
+        else if (kDgrad && feat == (F_MULAUX | F_COLSUM)) OVQA_GO(__nv_bfloat16, EPI_FULL, (kDgrad ? F_MULAUX | F_COLSUM : F_RUNTIME));                               // ... + fc1 bias gradient
+        else if (kDgrad && feat == F_COLSUM) OVQA_GO(__nv_bfloat16, EPI_FULL, (kDgrad ? F_COLSUM : F_RUNTIME));                                                       // dctx = dy Wo + value-bias gradient
         else OVQA_GO(__nv_bfloat16, EPI_FULL, F_RUNTIME);
     }
 #undef OVQA_GO

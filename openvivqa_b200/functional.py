@@ -301,7 +301,11 @@ class _MHAFn(torch.autograd.Function):
         d_o = _masked_operand(ds, ds16, mode, p, seed, off, rng_base)             # grad of the fc_o output (its column sums: dbo)
         ctx2 = att_ctx.view(B * Lq, hv)
         dwo = _wgrad(d_o, ctx2)
-        dctx = ops.gemm(d_o, weights.get([wo], cdt), b_op="T", out_dtype=cdt).view(B, Lq, hv)
+        # projection bias gradients without a pass over dq/dk/dv:  d(bv) = sum_rows dV = sum_rows dctx  (softmax rows sum to 1), taken in
+        # the epilogue of the GEMM that produces dctx;  d(bk) == 0 analytically (softmax is shift invariant);  d(bq) = column sums of dq.
+        dbias = torch.zeros((2 * hk + hv,), device=dy.device, dtype=torch.float32)
+        dbq, dbk, dbv = dbias[:hk], dbias[hk:2 * hk], dbias[2 * hk:]
+        dctx = ops.gemm(d_o, weights.get([wo], cdt), b_op="T", out_dtype=cdt, colsum=dbv).view(B, Lq, hv)
         geo = ops.GeoParams(boxes, geo_w.detach(), geo_b.detach(), cfg["geo_trig"]) if boxes is not None else None
         gdw = torch.zeros_like(geo_w, dtype=torch.float32) if geo is not None else None
         gdb = torch.zeros_like(geo_b, dtype=torch.float32) if geo is not None else None
@@ -324,23 +328,22 @@ class _MHAFn(torch.autograd.Function):
         if self_att:
             d2 = dqkv.view(B * Lq, -1)
             dW = _wgrad(d2, xq)
-            db = ops.colsum(d2)
+            ops.colsum(d2[:, :hk], out=dbq, accumulate=True)
             dwq, dwk, dwv = dW[:hk], dW[hk:2 * hk], dW[2 * hk:]
-            dbq, dbk, dbv = db[:hk], db[hk:2 * hk], db[2 * hk:]
             dqueries = ops.gemm(d2, weights.get([wq, wk, wv], cdt), b_op="T", out_dtype=torch.float32, residual=ds.view(B * Lq, D)).view(B, Lq, D)
         else:
             dq2 = dq.reshape(B * Lq, hk)
-            dwq, dbq = _wgrad(dq2, xq), ops.colsum(dq2)
+            dwq = _wgrad(dq2, xq)
+            ops.colsum(dq2, out=dbq, accumulate=True)
             dqueries = ops.gemm(dq2, weights.get([wq], cdt), b_op="T", out_dtype=torch.float32, residual=ds.view(B * Lq, D)).view(B, Lq, D)
             if kv_same:
                 d2 = dkvb.view(B * Lk, -1)
-                dW, db = _wgrad(d2, xk), ops.colsum(d2)
-                dwk, dwv, dbk, dbv = dW[:hk], dW[hk:], db[:hk], db[hk:]
+                dW = _wgrad(d2, xk)
+                dwk, dwv = dW[:hk], dW[hk:]
                 dkeys = ops.gemm(d2, weights.get([wk, wv], cdt), b_op="T", out_dtype=torch.float32).view(B, Lk, D)
             else:
                 dk2, dv2 = dk_.reshape(B * Lk, hk), dv_.reshape(B * Lk, hv)
-                dwk, dbk = _wgrad(dk2, xk), ops.colsum(dk2)
-                dwv, dbv = _wgrad(dv2, xv), ops.colsum(dv2)
+                dwk, dwv = _wgrad(dk2, xk), _wgrad(dv2, xv)
                 dkeys = ops.gemm(dk2, weights.get([wk], cdt), b_op="T", out_dtype=torch.float32).view(B, Lk, D)
                 dvalues = ops.gemm(dv2, weights.get([wv], cdt), b_op="T", out_dtype=torch.float32).view(B, Lk, D)
         return (dqueries, dkeys, dvalues, None, None, dwq, dbq, dwk, dbk, dwv, dbv, dwo, dbo, dgamma, dbeta, gdw, gdb, None)
@@ -403,8 +406,9 @@ class _PWFFFn(torch.autograd.Function):
         dw2 = _wgrad(d2, hact)
         # grad of the fc1 pre-activation: (d2 W2) * [dropout1 scale * gelu'(pre)] — the forward saved that product (the derivative
         # of its whole fused activation), so the dgrad epilogue is one multiply: no transcendental, no RNG
-        dpre = ops.gemm(d2, weights.get([w2], cdt), b_op="T", out_dtype=cdt, mul_aux=pre)
-        dw1, db1 = _wgrad(dpre, x2), ops.colsum(dpre)
+        db1 = torch.zeros((w1.shape[0],), device=dy.device, dtype=torch.float32)
+        dpre = ops.gemm(d2, weights.get([w2], cdt), b_op="T", out_dtype=cdt, mul_aux=pre, colsum=db1)     # + fc1 bias gradient (column sums)
+        dw1 = _wgrad(dpre, x2)
         dx = ops.gemm(dpre, weights.get([w1], cdt), b_op="T", out_dtype=torch.float32, residual=ds.reshape(-1, D)).view(ctx.xshape)
         return dx, dw1, db1, dw2, db2, dgamma, dbeta, None
 

@@ -47,18 +47,20 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_op: str = "N", b_op: str = "N", 
          aux_out: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          c2: Optional[torch.Tensor] = None, dropout_p: float = 0.0, seed: int = 0, offset: int = 0,
          offset_base: Optional[torch.Tensor] = None, split_k: int = 1, save_dgelu: bool = False,
-         mul_aux: Optional[torch.Tensor] = None) -> torch.Tensor:
+         mul_aux: Optional[torch.Tensor] = None, colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``C[m,n] = epilogue(sum_k A[m,k] B[n,k])`` — see ``ovqa_gemm`` in include/ovqa.h.
 
     ``a_op``/``b_op``: "N" = operand stored [rows, k]; "T" = stored [k, rows].
     ``save_dgelu`` (with ``gelu`` + ``aux_out``): ``aux_out`` receives the derivative of the whole fused activation,
     GELU'(pre-activation) times the element's dropout scale (0 or 1/(1-p); 1 without dropout); the backward GEMM multiplies
-    by it with ``mul_aux=`` — no transcendental and no RNG in the backward epilogue."""
+    by it with ``mul_aux=`` — no transcendental and no RNG in the backward epilogue.
+    ``colsum``: fp32 [n], += the column sums of the result (zero-filled by the caller): the bias gradient when the result is the
+    gradient of a Linear's output, at no extra pass over the rows."""
     if mul_aux is not None:
         if dgelu_aux is not None:
             raise ValueError("gemm: dgelu_aux and mul_aux are exclusive")
         dgelu_aux = mul_aux
-    _need_cuda(a, b, out, bias, dgelu_aux, aux_out, residual, c2)
+    _need_cuda(a, b, out, bias, dgelu_aux, aux_out, residual, c2, colsum)
     a, b = _rowmajor2d(a, "a"), _rowmajor2d(b, "b")
     if a.dtype != b.dtype or a.dtype not in _DT:
         raise ValueError(f"gemm: operand dtypes must match and be fp32/bf16, got {a.dtype}, {b.dtype}")
@@ -83,6 +85,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_op: str = "N", b_op: str = "N", 
         raise ValueError("gemm: aux_in/aux_out must share a leading dimension")
     if c2 is not None and (c2.dtype != torch.bfloat16 or c2.shape != (m, n) or c2.stride(1) != 1):
         raise ValueError("gemm: c2 must be bf16 [m,n]")
+    if colsum is not None and (colsum.dtype != torch.float32 or colsum.numel() != n or not colsum.is_contiguous()):
+        raise ValueError("gemm: colsum must be contiguous fp32 [n]")
     flags = (L.EPI_GELU if gelu else 0) | ((L.EPI_MUL_AUX if mul_aux is not None else L.EPI_DGELU) if dgelu_aux is not None else 0) | \
         (L.EPI_SAVE_DGELU if save_dgelu else 0)
     aux = dgelu_aux if dgelu_aux is not None else aux_out
@@ -90,7 +94,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_op: str = "N", b_op: str = "N", 
            L.OP_N if a_op == "N" else L.OP_T, L.OP_N if b_op == "N" else L.OP_T, _DT[a.dtype], _DT[out.dtype],
            float(alpha), float(beta), _p(bias), flags, _p(dgelu_aux), _p(aux_out), _ld(aux) if aux is not None else 0,
            _p(residual), _ld(residual) if residual is not None else 0, _p(c2), _ld(c2) if c2 is not None else 0,
-           float(dropout_p), int(seed), int(offset), _p(offset_base), int(split_k), _stream())
+           float(dropout_p), int(seed), int(offset), _p(offset_base), _p(colsum), int(split_k), _stream())
     return out
 
 

@@ -53,7 +53,7 @@ def test_bad_arguments_return_codes_not_crashes(built_lib):
     l = built_lib.lib()
     # null pointers / bad dtype are rejected before any CUDA call
     assert l.ovqa_gemm(None, None, None, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 1.0, 0.0, None, 0, None, None, 0, None, 0, None, 0,
-                       0.0, 0, 0, None, 1, None) == -1
+                       0.0, 0, 0, None, None, 1, None) == -1
     assert l.ovqa_layernorm_fwd(None, None, None, None, None, 0, None, None, None, None, None, 4, 512, 1e-5, None) == -1
     with pytest.raises(built_lib.OvqaError):
         built_lib.check(-2, "x")

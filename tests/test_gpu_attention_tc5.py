@@ -29,7 +29,9 @@ def _ref(q, k, v, mask, h, d):
 
 @pytest.mark.parametrize("masked", [False, True])
 @pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
-def test_tc5_core_forward_backward(shape, masked):
+def test_tc5_core_forward_backward(shape, masked, monkeypatch):
+    monkeypatch.setenv("OVQA_SDPA_TC5", "1")            # also the shapes the dispatcher would give to the warp-tile core
+    monkeypatch.setenv("OVQA_SDPA_TC5_BWD", "1")
     B, h, Lq, Lk = shape
     d = 64
     dev = torch.device("cuda:0")

@@ -155,6 +155,20 @@ def test_specialised_epilogues(dev, m, n, k):
     d = ops.gemm(a, bt, b_op="T", out_dtype=torch.bfloat16, mul_aux=dsave)
     want = ref * dsave.float()
     assert (d.float() - want).abs().max() <= tol * want.abs().max()
+    # the same with the fused column sums (bias gradient of the consuming layer), and the plain dgrad with column sums
+    cs = torch.zeros(n, device=dev)
+    d_cs = ops.gemm(a, bt, b_op="T", out_dtype=torch.bfloat16, mul_aux=dsave, colsum=cs)
+    assert torch.equal(d_cs, d)
+    assert (cs - want.sum(0)).abs().max() <= 2e-3 * want.abs().sum(0).max()
+    cs = torch.zeros(n, device=dev)
+    plain = ops.gemm(a, bt, b_op="T", out_dtype=torch.bfloat16, colsum=cs)
+    assert (plain.float() - ref).abs().max() <= tol * ref.abs().max()
+    assert (cs - ref.sum(0)).abs().max() <= 2e-3 * ref.abs().sum(0).max()
+    cs = torch.zeros(n, device=dev)                            # run-time feature path (fp32 out, bias + column sums), accumulating twice
+    for _ in range(2):
+        s32 = ops.gemm(a, b, bias=bias, out_dtype=torch.float32, colsum=cs)
+    assert (cs - 2 * pre.sum(0)).abs().max() <= 2e-3 * pre.abs().sum(0).max()
+    assert (s32 - pre).abs().max() <= 1e-3 * pre.abs().max()
     # fc_o / fc2: bias + dropout + residual -> fp32 (training), bias + residual (eval)
     s = ops.gemm(a, b, bias=bias, dropout_p=p, seed=seed, offset=off, residual=res, out_dtype=torch.float32)
     want = pre * keep / (1 - p) + res
