@@ -35,10 +35,14 @@ constexpr int kRegBoundThreads = 640;   // __launch_bounds__ figure: 65536/640 -
 constexpr int kAccStages = 2;
 constexpr int kScratchBytes = kEpiWarps * 32 * 32 * 4;   // one 32x32 fp32 chunk per epilogue warp
 
-template <int BN> struct Cfg {
-    static constexpr int kStages = BN == 256 ? 3 : 5;
+// CTAS = 1: one CTA per 128 x BN tile.  CTAS = 2: a CTA pair (cluster of 2, cta_group::2) per 256 x BN tile — each CTA stages its
+// own 128 rows of A and HALF of B (the MMA reads the other half from the peer's shared memory): 32 KB instead of 48 KB of L2 -> smem
+// traffic per SM and k-block at BN = 256, and room for 5 pipeline stages instead of 3 (profiles/r01d: the single-CTA 128 x 256 tile
+// is bound by the L2 -> SM path, not by the tensor pipe).
+template <int BN, int CTAS> struct Cfg {
+    static constexpr int kStages = CTAS == 2 ? 5 : (BN == 256 ? 3 : 5);
     static constexpr int kABytes = BM * BK * 2;
-    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kBBytes = (BN / CTAS) * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kTmemCols = kAccStages * BN;  // 256 or 512: power of two
     static constexpr int kSmemBytes = kStages * kStageBytes + kScratchBytes + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -107,11 +111,11 @@ __device__ __noinline__ void epilogue_scalar(const Epilogue& epi, float acc, int
 }
 
 // ----------------------------------------------------------------------------- kernel
-template <int BN, bool A_MN, bool B_MN, typename TC, int MODE, int FEAT>
+template <int BN, bool A_MN, bool B_MN, typename TC, int MODE, int FEAT, int CTAS>
 __global__ void __launch_bounds__(kRegBoundThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, TC* __restrict__ C,
                     int64_t m, int64_t n, int64_t k, int64_t ldc, Epilogue epi, int split_k) {
-    using cfg = Cfg<BN>;
+    using cfg = Cfg<BN, CTAS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
@@ -125,23 +129,32 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + kAccStages);
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    const int num_m_tiles = (int)((m + BM - 1) / BM), num_n_tiles = (int)((n + BN - 1) / BN);
+    constexpr int TM = BM * CTAS;                            // rows of a work tile (a CTA pair shares one 256-row tile)
+    const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;
+    const int num_m_tiles = (int)((m + TM - 1) / TM), num_n_tiles = (int)((n + BN - 1) / BN);
     const int num_k_blocks = (int)((k + BK - 1) / BK);
     const int num_tiles = num_m_tiles * num_n_tiles * split_k;
+    const int tile0 = (int)blockIdx.x / CTAS, tile_step = (int)gridDim.x / CTAS;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
-        for (int i = 0; i < cfg::kStages; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
-        for (int i = 0; i < kAccStages; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, kEpiWarps); }
+        // full: the leader's own arrive.expect_tx (+ the peer's remote arrive); tmem_empty: the epilogue warps of every CTA of the pair
+        for (int i = 0; i < cfg::kStages; ++i) { mbar_init(full_bar + i, CTAS); mbar_init(empty_bar + i, 1); }
+        for (int i = 0; i < kAccStages; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, kEpiWarps * CTAS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"((uint32_t)cfg::kTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (CTAS == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"((uint32_t)cfg::kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"((uint32_t)cfg::kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
 
@@ -160,36 +173,46 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < num_tiles; tile += tile_step) {
                 int mt, nt, kb0, kb1;
                 decode(tile, mt, nt, kb0, kb1);
+                const int a_row = mt * TM + (int)cta_rank * BM, b_row = nt * BN + (int)cta_rank * (BN / CTAS);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty_bar + stage, phase ^ 1);
-                    mbar_expect_tx(full_bar + stage, cfg::kStageBytes);
+                    uint64_t* fb = full_bar + stage;
+                    if constexpr (CTAS == 2) {
+                        if (cta_rank == 0) mbar_expect_tx(fb, 2 * cfg::kStageBytes);           // both CTAs' bytes land on the leader's barrier
+                        else mbar_arrive_cluster(mapa_u32(smem_u32(fb), 0));
+                    } else {
+                        mbar_expect_tx(fb, cfg::kStageBytes);
+                    }
+                    auto load = [&](void* dst, const CUtensorMap* map, int c0, int c1) {
+                        if constexpr (CTAS == 2) tma_load_2d_2sm(dst, map, fb, c0, c1); else tma_load_2d(dst, map, fb, c0, c1);
+                    };
                     uint8_t* sa = smem_a + stage * cfg::kABytes;
                     uint8_t* sb = smem_b + stage * cfg::kBBytes;
                     if constexpr (!A_MN) {
-                        tma_load_2d(sa, &tma_a, full_bar + stage, kb * BK, mt * BM);
+                        load(sa, &tma_a, kb * BK, a_row);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &tma_a, full_bar + stage, mt * BM + j * 64, kb * BK);
+                        for (int j = 0; j < BM / 64; ++j) load(sa + j * 8192, &tma_a, a_row + j * 64, kb * BK);
                     }
                     if constexpr (!B_MN) {
-                        tma_load_2d(sb, &tma_b, full_bar + stage, kb * BK, nt * BN);
+                        load(sb, &tma_b, kb * BK, b_row);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tma_b, full_bar + stage, nt * BN + j * 64, kb * BK);
+                        for (int j = 0; j < BN / CTAS / 64; ++j) load(sb + j * 8192, &tma_b, b_row + j * 64, kb * BK);
                     }
                     if (++stage == cfg::kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BM, BN, A_MN, B_MN);
+        if (lane == 0 && cta_rank == 0) {
+            constexpr uint32_t idesc = make_idesc(TM, BN, A_MN, B_MN);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < num_tiles; tile += tile_step) {
                 int mt, nt, kb0, kb1;
                 decode(tile, mt, nt, kb0, kb1);
                 mbar_wait(tmem_empty + acc, acc_phase ^ 1);
@@ -206,12 +229,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                         // MN-major: 64-elem MN blocks are 8192 B apart (LBO), 8-k-row groups 1024 B apart (SBO), K step = +2048 B.
                         const uint64_t a_desc = A_MN ? make_smem_desc(a_addr + kk * 2048, 8192, 1024) : make_smem_desc(a_addr + kk * 32, 16, 1024);
                         const uint64_t b_desc = B_MN ? make_smem_desc(b_addr + kk * 2048, 8192, 1024) : make_smem_desc(b_addr + kk * 32, 16, 1024);
-                        tcgen05_mma_bf16(d_tmem, a_desc, b_desc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+                        if constexpr (CTAS == 2) tcgen05_mma_bf16_2sm(d_tmem, a_desc, b_desc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+                        else tcgen05_mma_bf16(d_tmem, a_desc, b_desc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
                     }
-                    tcgen05_commit(empty_bar + stage);  // frees the smem slot when these MMAs retire
+                    // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+                    if constexpr (CTAS == 2) tcgen05_commit_2sm(empty_bar + stage); else tcgen05_commit(empty_bar + stage);
                     if (++stage == cfg::kStages) { stage = 0; phase ^= 1; }
                 }
-                tcgen05_commit(tmem_full + acc);        // accumulator ready for the epilogue
+                // accumulator ready for the epilogue warps (of both CTAs)
+                if constexpr (CTAS == 2) tcgen05_commit_2sm(tmem_full + acc); else tcgen05_commit(tmem_full + acc);
                 if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -251,12 +277,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         const int64_t ld_res = epi.ld_res, ld_aux = epi.ld_aux, ldc2 = epi.ldc2;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < num_tiles; tile += tile_step) {
             int mt, nt, kb0, kb1;
             decode(tile, mt, nt, kb0, kb1);
             mbar_wait(tmem_full + acc, acc_phase);
             tcgen05_fence_after();
-            const int64_t row_base = (int64_t)mt * BM + quad * 32 + rr;          // + 8 * pass
+            const int64_t row_base = (int64_t)mt * TM + (int64_t)cta_rank * BM + quad * 32 + rr;          // + 8 * pass
             const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
             for (int c0 = slot * 32; c0 < BN; c0 += 128) {
@@ -474,15 +500,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             }
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty + acc);
+            if (lane == 0) {                                              // the MMA issuer (leader CTA) waits for every epilogue warp of the pair
+                if (CTAS == 2 && cta_rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(tmem_empty + acc), 0));
+                else mbar_arrive(tmem_empty + acc);
+            }
             if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
         }
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();       // (pair: nobody leaves while the peer may still touch its smem / TMEM)
     if (warp == 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)cfg::kTmemCols) : "memory");
+        if constexpr (CTAS == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)cfg::kTmemCols) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)cfg::kTmemCols) : "memory");
     }
 }
 
@@ -548,21 +578,22 @@ inline int make_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t 
     return tc5::make_tma_map_bf16(out, ptr, inner, outer, ld, box_inner, box_outer);
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int CTAS>
 int launch(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb,
            int64_t ldc, const Epilogue& epi, int split_k, cudaStream_t st) {
-    using cfg = Cfg<BN>;
+    using cfg = Cfg<BN, CTAS>;
     CUtensorMap ma, mb;
     int rc;
-    // K-major: tensor [rows, k] box {64 k, ROWS};  MN-major: tensor [k, rows] box {64 rows, 64 k}
+    // K-major: tensor [rows, k] box {64 k, ROWS};  MN-major: tensor [k, rows] box {64 rows, 64 k}.  A CTA of a pair loads half of B's rows.
     rc = A_MN ? make_map(&ma, A, (uint64_t)m, (uint64_t)k, (uint64_t)lda, 64, BK) : make_map(&ma, A, (uint64_t)k, (uint64_t)m, (uint64_t)lda, BK, BM);
     if (rc) return rc;
-    rc = B_MN ? make_map(&mb, B, (uint64_t)n, (uint64_t)k, (uint64_t)ldb, 64, BK) : make_map(&mb, B, (uint64_t)k, (uint64_t)n, (uint64_t)ldb, BK, BN);
+    rc = B_MN ? make_map(&mb, B, (uint64_t)n, (uint64_t)k, (uint64_t)ldb, 64, BK) : make_map(&mb, B, (uint64_t)k, (uint64_t)n, (uint64_t)ldb, BK, BN / CTAS);
     if (rc) return rc;
     const int num_k_blocks = (int)((k + BK - 1) / BK);
     if (split_k > num_k_blocks) split_k = num_k_blocks;
-    const int64_t tiles = ((m + BM - 1) / BM) * ((n + BN - 1) / BN) * split_k;
-    const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+    const int64_t tiles = ((m + BM * CTAS - 1) / (BM * CTAS)) * ((n + BN - 1) / BN) * split_k;
+    const int64_t units = sm_count() / CTAS;
+    const int grid = (int)(tiles < units ? tiles : units) * CTAS;
     const bool full = epi.flags || epi.aux_in || epi.aux_out || epi.residual || epi.c2 || epi.dropout_p > 0.f || epi.beta != 0.f || epi.colsum;
     const int mode = split_k > 1 ? EPI_SPLITK : full ? EPI_FULL : EPI_PLAIN;
     // compile-time feature set of this launch, if it is one of the specialised combinations (else F_RUNTIME)
@@ -574,10 +605,20 @@ int launch(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, int64_t m, i
     }
 #define OVQA_GO(TC_, MODE_, FEAT_)                                                                                              \
     do {                                                                                                                       \
-        auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, TC_, MODE_, FEAT_>;                                                     \
+        auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, TC_, MODE_, FEAT_, CTAS>;                                               \
         static bool attr_set = false;                                                                                          \
         if (!attr_set) { OVQA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::kSmemBytes)); attr_set = true; } \
-        kern<<<grid, kThreads, cfg::kSmemBytes, st>>>(ma, mb, (TC_*)C, m, n, k, ldc, epi, split_k);                            \
+        if constexpr (CTAS == 1) {                                                                                             \
+            kern<<<grid, kThreads, cfg::kSmemBytes, st>>>(ma, mb, (TC_*)C, m, n, k, ldc, epi, split_k);                        \
+        } else {                                                                                                               \
+            cudaLaunchConfig_t lc{};                                                                                           \
+            lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(kThreads); lc.dynamicSmemBytes = cfg::kSmemBytes; lc.stream = st; \
+            cudaLaunchAttribute at[1];                                                                                         \
+            at[0].id = cudaLaunchAttributeClusterDimension;                                                                    \
+            at[0].val.clusterDim.x = CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;                             \
+            lc.attrs = at; lc.numAttrs = 1;                                                                                    \
+            OVQA_CUDA_OK(cudaLaunchKernelEx(&lc, kern, ma, mb, (TC_*)C, m, n, k, ldc, epi, split_k));                          \
+        }                                                                                                                      \
     } while (0)
     // the specialised sets exist for the operand forms that launch them: forward y = x W^T is (N,N), dgrad dx = dy W is (N,T)
     constexpr bool kFwd = !A_MN && !B_MN, kDgrad = !A_MN && B_MN;
@@ -612,6 +653,9 @@ int gemm_tcgen05_bf16(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, i
     // TMA: base 16-byte aligned, row pitch multiple of 16 bytes
     if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) || (lda % 8) || (ldb % 8)) return OVQA_ERR_ALIGNMENT;
     const bool a_mn = a_op == OVQA_OP_T, b_mn = b_op == OVQA_OP_T;
+    // CTA pairs (cta_group::2) for the 256-wide tile whenever a 256-row tile makes sense; OVQA_GEMM_2CTA=0 keeps single CTAs
+    const char* env2 = getenv("OVQA_GEMM_2CTA");
+    const bool allow_pair = !(env2 && env2[0] == '0') && m >= 256 && sm_count() % 2 == 0;
     bool wide;
     if (split_k <= 0) {
         // auto (long reductions, i.e. wgrad): 256-wide tiles halve the operand bytes pulled from L2 per flop (the
@@ -619,9 +663,11 @@ int gemm_tcgen05_bf16(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, i
         // exist, keeping at least 8 k-blocks per unit.  C must have been zero-filled by the caller.
         if (epi.c_dtype != OVQA_F32) return OVQA_ERR_BAD_ARG;
         wide = n >= 256;
-        const int64_t tiles = ((m + BM - 1) / BM) * ((n + (wide ? 255 : 127)) / (wide ? 256 : 128));
+        const bool pair = wide && allow_pair;
+        const int64_t tm = pair ? 2 * BM : BM, units = pair ? sm_count() / 2 : sm_count();
+        const int64_t tiles = ((m + tm - 1) / tm) * ((n + (wide ? 255 : 127)) / (wide ? 256 : 128));
         const int64_t kblocks = (k + BK - 1) / BK;
-        int64_t want = (2 * (int64_t)sm_count() + tiles / 2) / tiles;
+        int64_t want = (2 * units + tiles / 2) / tiles;
         if (want > kblocks / 8) want = kblocks / 8;
         split_k = (int)(want < 1 ? 1 : want);
     } else {
@@ -630,15 +676,16 @@ int gemm_tcgen05_bf16(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, i
         const int64_t tiles256 = ((m + BM - 1) / BM) * ((n + 255) / 256) * split_k;
         wide = (n % 256 == 0 || n > 1024) && tiles256 >= 2 * sm_count();
     }
-#define OVQA_DISPATCH(BN_)                                                                                                 \
+#define OVQA_DISPATCH(BN_, CTAS_)                                                                                          \
     do {                                                                                                                   \
-        if (!a_mn && !b_mn) return launch<BN_, false, false>(A, B, C, m, n, k, lda, ldb, ldc, epi, split_k, st);           \
-        if (!a_mn && b_mn) return launch<BN_, false, true>(A, B, C, m, n, k, lda, ldb, ldc, epi, split_k, st);             \
-        if (a_mn && b_mn) return launch<BN_, true, true>(A, B, C, m, n, k, lda, ldb, ldc, epi, split_k, st);               \
-        return launch<BN_, true, false>(A, B, C, m, n, k, lda, ldb, ldc, epi, split_k, st);                                \
+        if (!a_mn && !b_mn) return launch<BN_, false, false, CTAS_>(A, B, C, m, n, k, lda, ldb, ldc, epi, split_k, st);    \
+        if (!a_mn && b_mn) return launch<BN_, false, true, CTAS_>(A, B, C, m, n, k, lda, ldb, ldc, epi, split_k, st);      \
+        if (a_mn && b_mn) return launch<BN_, true, true, CTAS_>(A, B, C, m, n, k, lda, ldb, ldc, epi, split_k, st);        \
+        return launch<BN_, true, false, CTAS_>(A, B, C, m, n, k, lda, ldb, ldc, epi, split_k, st);                         \
     } while (0)
-    if (wide) OVQA_DISPATCH(256);
-    OVQA_DISPATCH(128);
+    if (wide && allow_pair) OVQA_DISPATCH(256, 2);
+    if (wide) OVQA_DISPATCH(256, 1);
+    OVQA_DISPATCH(128, 1);
 #undef OVQA_DISPATCH
 }
 

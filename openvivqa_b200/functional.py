@@ -301,11 +301,13 @@ class _MHAFn(torch.autograd.Function):
         d_o = _masked_operand(ds, ds16, mode, p, seed, off, rng_base)             # grad of the fc_o output (its column sums: dbo)
         ctx2 = att_ctx.view(B * Lq, hv)
         dwo = _wgrad(d_o, ctx2)
-        # projection bias gradients without a pass over dq/dk/dv:  d(bv) = sum_rows dV = sum_rows dctx  (softmax rows sum to 1), taken in
-        # the epilogue of the GEMM that produces dctx;  d(bk) == 0 analytically (softmax is shift invariant);  d(bq) = column sums of dq.
-        dbias = torch.zeros((2 * hk + hv,), device=dy.device, dtype=torch.float32)
-        dbq, dbk, dbv = dbias[:hk], dbias[hk:2 * hk], dbias[2 * hk:]
-        dctx = ops.gemm(d_o, weights.get([wo], cdt), b_op="T", out_dtype=cdt, colsum=dbv).view(B, Lq, hv)
+        # projection bias gradients without a pass over dq/dk/dv:  d(bv) = sum_rows dV = sum_rows dctx (softmax rows sum to 1)
+        # = (sum_rows d_o) Wo = dbo Wo, a 512-vector times the fp32 master weight;  d(bk) == 0 analytically (softmax is shift
+        # invariant);  d(bq) = column sums of dq.
+        dbias = torch.zeros((2 * hk,), device=dy.device, dtype=torch.float32)
+        dbq, dbk = dbias[:hk], dbias[hk:]
+        dbv = torch.mv(wo.detach().float().t(), dbo)
+        dctx = ops.gemm(d_o, weights.get([wo], cdt), b_op="T", out_dtype=cdt).view(B, Lq, hv)
         geo = ops.GeoParams(boxes, geo_w.detach(), geo_b.detach(), cfg["geo_trig"]) if boxes is not None else None
         gdw = torch.zeros_like(geo_w, dtype=torch.float32) if geo is not None else None
         gdb = torch.zeros_like(geo_b, dtype=torch.float32) if geo is not None else None

@@ -195,3 +195,36 @@ def test_tanhfit_gelu_matches_erf_gelu(dev):
     err = (out.float() - want.detach()).abs()
     assert (err <= 2.0 ** -8 * want.detach().abs() + 1.5e-3).all(), err.max().item()
     assert (dsave.float() - xs.grad).abs().max().item() <= 6e-3
+
+
+@pytest.mark.parametrize("a_op,b_op", [("N", "N"), ("N", "T"), ("T", "T"), ("T", "N")])
+@pytest.mark.parametrize("m,n,k", [(40000, 512, 512), (20008, 768, 256), (38000 + 77, 256, 1024), (40000, 2048, 512)])
+def test_cta_pair_matches_single_cta(dev, monkeypatch, a_op, b_op, m, n, k):
+    """cta_group::2 (a CTA pair per 256-row tile, B split across the pair) against the single-CTA kernel: same K order, so
+    the results must be bit-identical, ragged last pair tiles included."""
+    if a_op == "T":
+        m = (m + 7) // 8 * 8
+    a, b, ref = _mk(m, n, k, a_op, b_op, dev)
+    bias = torch.randn(n, device=dev)
+    res = torch.randn((m, n), device=dev)
+    outs = {}
+    for pair in ("0", "1"):
+        monkeypatch.setenv("OVQA_GEMM_2CTA", pair)
+        o1 = ops.gemm(a, b, a_op=a_op, b_op=b_op, out_dtype=torch.float32)
+        o2 = ops.gemm(a, b, a_op=a_op, b_op=b_op, out_dtype=torch.bfloat16, bias=bias)
+        o3 = ops.gemm(a, b, a_op=a_op, b_op=b_op, out_dtype=torch.float32, bias=bias, residual=res, dropout_p=0.1, seed=3, offset=7)
+        torch.cuda.synchronize()
+        outs[pair] = (o1, o2, o3)
+    assert (outs["1"][0].cpu() - ref).abs().max() <= 1e-3 * ref.abs().max()
+    for x, y in zip(outs["0"], outs["1"]):
+        assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("split_k", [0, 3, 11])
+def test_cta_pair_split_k(dev, monkeypatch, split_k):
+    m, n, k = 1536, 512, 20000
+    a, b, ref = _mk(m, n, k, "T", "T", dev)
+    for pair in ("0", "1"):
+        monkeypatch.setenv("OVQA_GEMM_2CTA", pair)
+        out = ops.gemm(a, b, a_op="T", b_op="T", out_dtype=torch.float32, split_k=split_k)
+        assert (out.cpu() - ref).abs().max() <= 2e-3 * ref.abs().max(), pair
