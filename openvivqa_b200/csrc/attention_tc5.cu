@@ -150,16 +150,19 @@ sdpa_fwd_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         const float sc2 = a.scale * kLog2e;
         const int nch32 = (nk16 + 31) / 32;
         int u = 0;
+        // mask value of key `tid_g` for an item (raw; -inf beyond Lk): fetched one item ahead so its DRAM latency is off the critical path
+        auto mask_of = [&](int item) -> float {
+            if (tid_g >= Lk || item >= n_items) return -INFINITY;
+            return a.mask.ptr ? __ldg(a.mask.ptr + (int64_t)(item / H) * a.mask.sb + (int64_t)(item % H) * a.mask.sh + tid_g) : 0.0f;
+        };
+        float mv_next = mask_of(blockIdx.x + g * gridDim.x);
         for (int item = blockIdx.x + g * gridDim.x; item < n_items; item += 2 * gridDim.x, ++u) {
             const int b = item / H, hd = item % H;
             const uint32_t par = (uint32_t)u & 1u;
             // per-key mask row of this (sample, head), pre-multiplied by log2 e; -inf beyond Lk
             named_bar_sync(1 + g, 128);               // the previous item's readers are done
-            {
-                float mv = -INFINITY;
-                if (tid_g < Lk) mv = a.mask.ptr ? __ldg(a.mask.ptr + (int64_t)b * a.mask.sb + (int64_t)hd * a.mask.sh + tid_g) * kLog2e : 0.0f;
-                mrow[tid_g] = mv;
-            }
+            mrow[tid_g] = mv_next * kLog2e;
+            mv_next = mask_of(item + 2 * gridDim.x);
             named_bar_sync(1 + g, 128);
             mbar_wait(s_full + g, par);
             tcgen05_fence_after();
@@ -403,17 +406,20 @@ sdpa_bwd_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         const float sc2 = a.scale * kLog2e;
         const int nch = nk16 / 16;
         const bool live = row < Lq;
+        auto mask_of = [&](int item) -> float {          // fetched one item ahead (as lse): off the critical path
+            if (tid_g >= Lk || item >= n_items) return -INFINITY;
+            return a.mask.ptr ? __ldg(a.mask.ptr + (int64_t)(item / H) * a.mask.sb + (int64_t)(item % H) * a.mask.sh + tid_g) : 0.0f;
+        };
+        auto lse_of = [&](int item) -> float { return (live && item < n_items) ? __ldg(a.lse + (int64_t)item * Lq + row) : 0.0f; };
+        float mv_next = mask_of(blockIdx.x), lse_next = lse_of(blockIdx.x);
         for (int it = 0; it < my_items; ++it) {
             const int item = blockIdx.x + it * gridDim.x;
-            const int b = item / H, hd = item % H;
             const uint32_t par = (uint32_t)it & 1u;
             named_bar_sync(1, 128);
-            {
-                float mv = -INFINITY;
-                if (tid_g < Lk) mv = a.mask.ptr ? __ldg(a.mask.ptr + (int64_t)b * a.mask.sb + (int64_t)hd * a.mask.sh + tid_g) * kLog2e : 0.0f;
-                s_mask[tid_g] = mv;
-            }
-            const float lse2 = live ? __ldg(a.lse + ((int64_t)b * H + hd) * Lq + row) * kLog2e : 0.0f;
+            s_mask[tid_g] = mv_next * kLog2e;
+            const float lse2 = lse_next * kLog2e;
+            mv_next = mask_of(item + gridDim.x);
+            lse_next = lse_of(item + gridDim.x);
             named_bar_sync(1, 128);
             mbar_wait(sdp_full, par);
             tcgen05_fence_after();

@@ -617,6 +617,17 @@ int launch(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, int64_t m, i
             at[0].id = cudaLaunchAttributeClusterDimension;                                                                    \
             at[0].val.clusterDim.x = CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;                             \
             lc.attrs = at; lc.numAttrs = 1;                                                                                    \
+            /* persistent kernel: never more clusters than can be co-resident (GPCs with an odd SM count cannot pair them all) */ \
+            static int max_clusters = -1;                                                                                      \
+            if (max_clusters < 0) {                                                                                            \
+                int nc = 0;                                                                                                    \
+                lc.gridDim = dim3((unsigned)(sm_count() / CTAS * CTAS));                                                       \
+                if (cudaOccupancyMaxActiveClusters(&nc, kern, &lc) != cudaSuccess || nc < 1) { (void)cudaGetLastError(); nc = sm_count() / CTAS; } \
+                max_clusters = nc;                                                                                             \
+                if (getenv("OVQA_DEBUG")) fprintf(stderr, "ovqa gemm pair kernel: %d co-resident clusters of %d\n", nc, CTAS);  \
+            }                                                                                                                  \
+            const int clusters = grid / CTAS < max_clusters ? grid / CTAS : max_clusters;                                      \
+            lc.gridDim = dim3((unsigned)(clusters * CTAS));                                                                    \
             OVQA_CUDA_OK(cudaLaunchKernelEx(&lc, kern, ma, mb, (TC_*)C, m, n, k, ldc, epi, split_k));                          \
         }                                                                                                                      \
     } while (0)

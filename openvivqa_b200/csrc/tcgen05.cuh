@@ -113,8 +113,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) 
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
     return r;
 }
+// Remote arrive on a barrier of another CTA of the cluster.  Default (.release at .cta scope) semantics on purpose: with
+// .release.cluster the compiler emits MEMBAR.ALL.GPU + ERRBAR in front of every arrive, which throttled the peer's TMA producer to one
+// k-block per ~1500 cycles (profiles/r01h).  Nothing written by generic-proxy stores is handed over by these arrives: the operand
+// bytes are tracked by the barrier's tx-count, TMEM reads are ordered by tcgen05.fence::before_thread_sync.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;     // shared::cluster address of the same offset in the pair's even (leader) CTA
 __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, uint64_t* leader_bar, int c0, int c1) {
