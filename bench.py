@@ -84,6 +84,10 @@ class ClockSampler:
                     reasons=reasons, samples=len(rows))
 
 
+MCAN_WORKLOAD_NAME = ("mcan_train: MCAN 6SA+6SGA d512 h8 dff2048, 30 tok, 100x2048 regions, batch 256/GPU, dropout 0.1, "
+                      "NLL+Adam (BASELINE configs[1])")
+
+
 def synth_batches(n, wl, seed=1):
     """n distinct synthetic ViVQA-shaped batches in pinned host memory."""
     g = torch.Generator().manual_seed(seed)
@@ -146,8 +150,9 @@ def run_reference(args):
     cores = torch.get_num_threads()
     line = dict(metric="VQA samples/sec (MCAN train)", value=sps, unit="samples/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=per * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
-                config=dict(workload="mcan_train: MCAN 6SA+6SGA d512 h8, 30 tok, 100x2048 regions (BASELINE configs[1])",
-                            batch_per_step=B, note="reference CPU path = oracle port of the reference PyTorch step (fwd+NLL+bwd+Adam), all host threads"),
+                config=dict(workload=MCAN_WORKLOAD_NAME, global_batch=256 * max(1, args.gpus), parallelism=f"dp{max(1, args.gpus)}",
+                            batch_per_step=B, note="reference CPU path = oracle port of the reference PyTorch step (fwd+NLL+bwd+Adam) on all host threads; "
+                                                   "each timed step is a bounded sample (batch 32) of the 256/GPU workload"),
                 cpu_baseline=dict(value=sps, unit="samples/s", cores=cores, kind="port", sample=f"{args.steps} steps of batch {B} (of 256/GPU)"),
                 e2e=dict(value=sps, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
@@ -526,8 +531,7 @@ def run_ours(args):
         cpu_sps, cpu_per = time_cpu(wl, 32, 2, 1) if args.gpus == 1 and not args.no_cpu_baseline else (None, None)
         line = dict(metric="VQA samples/sec (MCAN train)", value=value, unit="samples/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
-                    config=dict(workload="mcan_train: MCAN 6SA+6SGA d512 h8 dff2048, 30 tok, 100x2048 regions, batch 256/GPU, dropout 0.1, "
-                                         "NLL+Adam (BASELINE configs[1])", global_batch=wl["B"] * world, parallelism=f"dp{world}",
+                    config=dict(workload=MCAN_WORKLOAD_NAME, global_batch=wl["B"] * world, parallelism=f"dp{world}",
                                 l2="inputs larger than L2 (210 MB of features per step, 3 rotating batches)", final_loss=final_loss,
                                 cuda_graph=graph is not None, cuda_graph_error=graph_err, eager_ms_per_step=eager_ms_per_step),
                     e2e=dict(value=e2e, unit="samples/s", h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=4),

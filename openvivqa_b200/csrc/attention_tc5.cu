@@ -6,11 +6,14 @@
 // Against the mma.sync kernel (attention_mma.cu) this removes the ldmatrix / fragment traffic and ~3/4 of the issued
 // instructions (profiles/r01e: the warp-tile kernel is issue-bound at ~27 % of the HBM roofline), and it makes the core a
 // persistent, TMA-fed pipeline:
-//   warp 0      TMA producer: Q, K, V tiles of item i+1, i+2 while item i is computed (3 load stages, SWIZZLE_128B)
+//   warp 0      TMA producer: Q, K, V tiles (SWIZZLE_128B), one stage per softmax group
 //   warp 1      MMA issuer (one thread): S(i+1) is issued before waiting for P(i), so the tensor pipe never waits on softmax
 //   warps 2-5   softmax group 0 (items 0, 2, 4, ...)      } two groups ping-pong on their own TMEM columns and P buffer: one
 //   warps 6-9   softmax group 1 (items 1, 3, 5, ...)      } group's TMEM / MUFU latencies hide behind the other's arithmetic
-// Work item = (sample, head); CTAs are persistent over items (grid = min(B*h, #SM)).
+// Two such CTAs are resident per SM (96 KB of shared memory, 256 TMEM columns, <= 100 registers each): four items in flight per
+// SM hide each other's load, MMA-commit and TMEM round-trip latencies (profiles/r01g: one CTA per SM was latency-bound at 37 % of HBM).
+// P overwrites the stage's Q | K tiles (dead once S is complete), O overwrites S in TMEM (dead once P is written).
+// Work item = (sample, head); CTAs are persistent over items (grid = min(B*h, 2 #SM)).
 // Rows of the K / V tiles beyond Lk belong to the next sample (or are TMA zero fill): their P columns are exactly 0 (the
 // staged mask row is -inf there), so they contribute nothing.
 #include "attention_simt.cuh"
@@ -23,12 +26,13 @@ namespace {
 using namespace tc5;
 
 constexpr int kD = 64;                    // head dim (one SWIZZLE_128B row of bf16)
-constexpr int kLoadStages = 3;
+constexpr int kLoadStages = 2;            // one per softmax group: item i lives in stage i % 2 and is processed by group i % 2
 constexpr int kTileBytes = 128 * 128;     // 128 rows x 128 B
 constexpr int kStageBytes = 3 * kTileBytes;            // Q, K, V
-constexpr int kPBytes = 2 * kTileBytes;                // P: two 64-key blocks of 128 rows x 128 B
+constexpr int kPBytes = 2 * kTileBytes;                // P: two 64-key blocks of 128 rows x 128 B (forward: aliased onto the stage's dead Q | K tiles)
 constexpr int kFwdThreads = 64 + 2 * 128;
-constexpr int kFwdSmem = kLoadStages * kStageBytes + 2 * kPBytes + 2 * 128 * 4 /*mask rows*/ + 256 /*barriers*/ + 1024 /*align*/;
+constexpr int kFwdSmem = kLoadStages * kStageBytes + 2 * 128 * 4 /*mask rows*/ + 256 /*barriers*/ + 1024 /*align*/;   // 2 CTAs per SM
+constexpr int kFwdTmemCols = 256;         // group g: S in [128 g, +128), O aliased onto the first 64 of them (S is dead once P is written)
 constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
 
 struct Tc5FwdArgs {
@@ -45,14 +49,13 @@ __device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, u
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-__global__ void __launch_bounds__(kFwdThreads, 1)
+__global__ void __launch_bounds__(kFwdThreads, 2)
 sdpa_fwd_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, Tc5FwdArgs args) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* s_load = smem;                                          // [kLoadStages][Q | K | V]
-    uint8_t* s_p = smem + kLoadStages * kStageBytes;                 // [2 groups][2 key blocks][128][128 B]
-    float* s_mask = reinterpret_cast<float*>(s_p + 2 * kPBytes);     // [2 groups][128]  (mask * log2 e; -inf beyond Lk)
+    uint8_t* s_load = smem;                                          // [kLoadStages][Q | K | V];  P of the stage's item overwrites Q | K
+    float* s_mask = reinterpret_cast<float*>(smem + kLoadStages * kStageBytes);   // [2 groups][128]  (mask * log2 e; -inf beyond Lk)
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_mask + 2 * 128);
     uint64_t* load_full = bars;                     // [kLoadStages]  TMA -> MMA
     uint64_t* load_empty = load_full + kLoadStages; // [kLoadStages]  MMA -> TMA
@@ -76,14 +79,13 @@ sdpa_fwd_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)kFwdTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // TMEM columns: group g owns [g*192, g*192+128) for S and [g*192+128, g*192+192) for O
 
     if (warp == 0) {
         if (lane == 0) {
@@ -112,7 +114,7 @@ sdpa_fwd_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 mbar_wait(acc_empty + g, ((uint32_t)(it >> 1) & 1u) ^ 1u);
                 tcgen05_fence_after();
                 const uint32_t q_addr = smem_u32(s_load + ls * kStageBytes), k_addr = q_addr + kTileBytes;
-                const uint32_t d_s = tmem_base + (uint32_t)(g * 192);
+                const uint32_t d_s = tmem_base + (uint32_t)(g * 128);
 #pragma unroll
                 for (int kk = 0; kk < kD / 16; ++kk)
                     tcgen05_mma_bf16(d_s, make_smem_desc(q_addr + kk * 32, 16, 1024), make_smem_desc(k_addr + kk * 32, 16, 1024), idesc_s, kk > 0 ? 1u : 0u);
@@ -122,9 +124,8 @@ sdpa_fwd_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 const int ls = it % kLoadStages, g = it & 1;
                 mbar_wait(p_full + g, (uint32_t)(it >> 1) & 1u);
                 tcgen05_fence_after();
-                const uint32_t v_addr = smem_u32(s_load + ls * kStageBytes + 2 * kTileBytes);
-                const uint32_t p_addr = smem_u32(s_p + g * kPBytes);
-                const uint32_t d_o = tmem_base + (uint32_t)(g * 192 + 128);
+                const uint32_t p_addr = smem_u32(s_load + ls * kStageBytes), v_addr = p_addr + 2 * kTileBytes;
+                const uint32_t d_o = tmem_base + (uint32_t)(g * 128);
                 for (int ks = 0; ks < nk16 / 16; ++ks)
                     tcgen05_mma_bf16(d_o, make_smem_desc(p_addr + (ks >> 2) * kTileBytes + (ks & 3) * 32, 16, 1024),
                                      make_smem_desc(v_addr + ks * 2048, 8192, 1024), idesc_o, ks > 0 ? 1u : 0u);
@@ -144,11 +145,11 @@ sdpa_fwd_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         const int tid_g = (warp - 2) % 4 * 32 + lane; // 0..127 inside the group
         float* mrow = s_mask + g * 128;
         const uint32_t mrow_u32 = smem_u32(mrow);
-        const uint32_t p_row = smem_u32(s_p + g * kPBytes) + (uint32_t)row * 128u, p_x = (uint32_t)(row & 7);
-        const uint32_t t_s = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * 192);
-        const uint32_t t_o = t_s + 128u;
+        const uint32_t p_row = smem_u32(s_load + g * kStageBytes) + (uint32_t)row * 128u, p_x = (uint32_t)(row & 7);   // stage g == group g
+        const uint32_t t_s = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * 128);
+        const uint32_t t_o = t_s;
         const float sc2 = a.scale * kLog2e;
-        const int nch32 = (nk16 + 31) / 32;
+        const int nch = nk16 / 16;
         int u = 0;
         // mask value of key `tid_g` for an item (raw; -inf beyond Lk): fetched one item ahead so its DRAM latency is off the critical path
         auto mask_of = [&](int item) -> float {
@@ -166,65 +167,55 @@ sdpa_fwd_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             named_bar_sync(1 + g, 128);
             mbar_wait(s_full + g, par);
             tcgen05_fence_after();
-            // Two passes over the S row in TMEM (row max, then exponentials), 32 columns at a time, the next chunk's tcgen05.ld
-            // in flight while the current one is processed: ~70 live registers instead of the whole 128-column row (10 warps
-            // per CTA leave 168 registers per thread; the one-pass version spilled).
-            auto load_chunk = [&](uint32_t (&r)[32], int c32) {        // columns [32 c32, +32) of S, zero beyond nk16
-                if (32 * c32 + 32 <= nk16) {
-                    tmem_ld_32x32b_x32(t_s + (uint32_t)(32 * c32), r);
-                } else {
-                    tmem_ld_32x32b_x16(t_s + (uint32_t)(32 * c32), r);
+            // Two passes over the S row in TMEM (row max, then exponentials), 16 columns at a time, the next chunk's tcgen05.ld in
+            // flight while the current one is processed: ~60 live registers (two resident CTAs leave 100 per thread).
+            auto scaled = [&](const uint32_t (&r)[16], int ch, float (&v)[16]) {   // v = S * scale * log2e + mask
 #pragma unroll
-                    for (int j = 16; j < 32; ++j) r[j] = 0u;
-                }
-            };
-            auto scaled = [&](const uint32_t (&r)[32], int c32, float (&v)[32]) {   // v = S * scale * log2e + mask
-#pragma unroll
-                for (int q4 = 0; q4 < 8; ++q4) {
+                for (int q4 = 0; q4 < 4; ++q4) {
                     float m0, m1, m2, m3;
-                    lds128f(mrow_u32 + (uint32_t)(32 * c32 + 4 * q4) * 4u, m0, m1, m2, m3);
+                    lds128f(mrow_u32 + (uint32_t)(16 * ch + 4 * q4) * 4u, m0, m1, m2, m3);
                     v[4 * q4] = fmaf(__uint_as_float(r[4 * q4]), sc2, m0);
                     v[4 * q4 + 1] = fmaf(__uint_as_float(r[4 * q4 + 1]), sc2, m1);
                     v[4 * q4 + 2] = fmaf(__uint_as_float(r[4 * q4 + 2]), sc2, m2);
                     v[4 * q4 + 3] = fmaf(__uint_as_float(r[4 * q4 + 3]), sc2, m3);
                 }
             };
-            uint32_t ra[32], rb[32];
+            uint32_t ra[16], rb[16];
             float mx = -INFINITY;
-            load_chunk(ra, 0);
+            tmem_ld_32x32b_x16(t_s, ra);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if (c < nch32) {
+            for (int c = 0; c < 8; ++c) {
+                if (c < nch) {
                     tmem_ld_wait();
-                    if (c + 1 < nch32) load_chunk((c & 1) ? ra : rb, c + 1);
-                    float v[32];
+                    if (c + 1 < nch) tmem_ld_32x32b_x16(t_s + (uint32_t)(16 * (c + 1)), (c & 1) ? ra : rb);
+                    float v[16];
                     scaled((c & 1) ? rb : ra, c, v);
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) mx = fmaxf(fmaxf(mx, fmaxf(v[j], v[j + 1])), fmaxf(v[j + 2], v[j + 3]));
+                    for (int j = 0; j < 16; j += 4) mx = fmaxf(fmaxf(mx, fmaxf(v[j], v[j + 1])), fmaxf(v[j + 2], v[j + 3]));
                 }
             }
             float l = 0.f;
             const bool live = row < Lq;
-            load_chunk(ra, 0);
+            tmem_ld_32x32b_x16(t_s, ra);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if (c < nch32) {
+            for (int c = 0; c < 8; ++c) {
+                if (c < nch) {
                     tmem_ld_wait();
-                    if (c + 1 < nch32) load_chunk((c & 1) ? ra : rb, c + 1);
-                    float v[32];
+                    if (c + 1 < nch) tmem_ld_32x32b_x16(t_s + (uint32_t)(16 * (c + 1)), (c & 1) ? ra : rb);
+                    float v[16];
                     scaled((c & 1) ? rb : ra, c, v);
-                    uint32_t pk[16];
+                    uint32_t pk[8];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
+                    for (int j = 0; j < 8; ++j) {
                         const float p0 = ex2_approx(v[2 * j] - mx), p1 = ex2_approx(v[2 * j + 1] - mx);
                         l += p0 + p1;
                         pk[j] = live ? pack_bf16x2(p0, p1) : 0u;
                     }
-                    // keys [32 c, +32) = 16-byte chunks 4c .. 4c+3 of the row; chunk i of key block i/8 sits at (i%8) ^ (row%8)
-                    const uint32_t blk = p_row + (uint32_t)(c >> 1) * kTileBytes;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        sts128u(blk + ((((uint32_t)(4 * c + i) & 7u) ^ p_x) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+                    // keys [16 c, +16) = 16-byte chunks 2c, 2c+1 of the row; chunk i of key block i/8 sits at (i%8) ^ (row%8).
+                    // (this overwrites the Q | K tiles of the stage: S = Q K^T is complete, nobody reads them any more)
+                    const uint32_t blk = p_row + (uint32_t)(c >> 2) * kTileBytes;
+                    sts128u(blk + ((((uint32_t)(2 * c) & 7u) ^ p_x) << 4), pk[0], pk[1], pk[2], pk[3]);
+                    sts128u(blk + ((((uint32_t)(2 * c + 1) & 7u) ^ p_x) << 4), pk[4], pk[5], pk[6], pk[7]);
                 }
             }
             fence_proxy_async_smem();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -257,25 +248,29 @@ sdpa_fwd_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kFwdTmemCols) : "memory");
     }
 }
 
 
 // ------------------------------------------------------------------------------------------------ backward
 // Per item (sample, head):   S = Q K^T,  dP = dO V^T                          (tcgen05, accumulators in TMEM)
-//   phase A, one thread per query row:  P = exp(S*scale + mask - lse),  delta = sum_j P dP  (== dO . O, so O is never read),
-//                                       dS = P (dP - delta);  P and dS go to shared memory as bf16 [query][key] tiles
+//   phase A, two threads per query row (alternate 16-key chunks; the element-wise chain is the critical path of an item):
+//                                       P = exp(S*scale + mask - lse),  delta = sum_j P dP  (== dO . O, so O is never read; the two
+//                                       partial sums meet in shared memory),  dS = P (dP - delta);  P and dS go to shared memory as
+//                                       bf16 [query][key] tiles
 //   dV = P^T dO,  dK = dS^T Q,  dQ = dS K    — the SAME two tiles serve as MN-major A operands (transposed use) and as a
 //                                       K-major A operand: no transposition pass anywhere
 //   phase B, one thread per output row: TMEM -> bf16 -> global (dK, dQ scaled by 1/sqrt(d) here, in fp32)
-// warp 0 = TMA producer (Q, dO, K, V; 2 stages), warp 1 = MMA issuer, warps 2-5 = phase A, warps 6-9 = phase B, so the
+// warp 0 = TMA producer (Q, dO, K, V; 2 stages), warp 1 = MMA issuer, warps 2-9 = phase A, warps 10-13 = phase B, so the
 // element-wise work of item i+1 overlaps the output drain of item i and the loads of item i+2.  S(i+1) / dP(i+1) are issued
 // BEFORE dV/dK/dQ(i): phase A never waits for the three long products.
 constexpr int kBwdStages = 2;
 constexpr int kBwdStageBytes = 4 * kTileBytes;         // Q, dO, K, V
-constexpr int kBwdThreads = 64 + 2 * 128;
-constexpr int kBwdSmem = kBwdStages * kBwdStageBytes + 2 * kPBytes /*P, dS*/ + 128 * 4 /*mask row*/ + 256 /*barriers*/ + 1024 /*align*/;
+constexpr int kBwdAThreads = 256;                      // phase A: TWO threads per query row, each owning every other 16-key chunk
+constexpr int kBwdThreads = 64 + kBwdAThreads + 128;
+constexpr int kBwdSmem = kBwdStages * kBwdStageBytes + 2 * kPBytes /*P, dS*/ + 128 * 4 /*mask row*/ + 2 * 2 * 128 * 4 /*delta partials*/ +
+                         256 /*barriers*/ + 1024 /*align*/;
 
 struct Tc5BwdArgs {
     SdpaArgs a;
@@ -305,11 +300,12 @@ sdpa_bwd_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     uint8_t* s_p = smem + kBwdStages * kBwdStageBytes;               // P  [2 key blocks][128 queries][128 B]
     uint8_t* s_ds = s_p + kPBytes;                                   // dS, same layout
     float* s_mask = reinterpret_cast<float*>(s_ds + kPBytes);        // [128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_mask + 128);
+    float* s_delta = s_mask + 128;                                   // [2 item parities][2 halves][128]  partial sums of P dP
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_delta + 2 * 2 * 128);
     uint64_t* load_full = bars;                     // [2]  TMA -> MMA (and phase A)
     uint64_t* load_empty = load_full + kBwdStages;  // [2]  MMA -> TMA
     uint64_t* sdp_full = load_empty + kBwdStages;   // MMA -> phase A: S and dP ready
-    uint64_t* pds_full = sdp_full + 1;              // phase A -> MMA: P and dS in smem, S / dP columns free   (128 arrivals)
+    uint64_t* pds_full = sdp_full + 1;              // phase A -> MMA: P and dS in smem, S / dP columns free   (256 arrivals)
     uint64_t* out_full = pds_full + 1;              // MMA -> phase B (dV, dK, dQ ready) and -> phase A (P / dS tiles no longer read)
     uint64_t* out_free = out_full + 1;              // phase B -> MMA: dV / dK / dQ columns drained             (128 arrivals)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(out_free + 1);
@@ -326,7 +322,7 @@ sdpa_bwd_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_k)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_v)) : "memory");
         for (int i = 0; i < kBwdStages; ++i) { mbar_init(load_full + i, 1); mbar_init(load_empty + i, 1); }
-        mbar_init(sdp_full, 1); mbar_init(pds_full, 128); mbar_init(out_full, 1); mbar_init(out_free, 128);
+        mbar_init(sdp_full, 1); mbar_init(pds_full, kBwdAThreads); mbar_init(out_full, 1); mbar_init(out_free, 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -397,14 +393,15 @@ sdpa_bwd_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 tcgen05_commit(load_empty + ls);
             }
         }
-    } else if (warp < 6) {
-        // ---------------------------------------------------------------- phase A: one thread per query row
-        const int quad = warp % 4, row = quad * 32 + lane, tid_g = (warp - 2) * 32 + lane;
+    } else if (warp < 2 + kBwdAThreads / 32) {
+        // ---------------------------------------------------------------- phase A: two threads per query row
+        const int quad = warp % 4, row = quad * 32 + lane, half = (warp - 2) / 4, tid_g = (warp - 2) * 32 + lane;
         const uint32_t mrow_u32 = smem_u32(s_mask);
         const uint32_t t_s = tmem_base + ((uint32_t)(quad * 32) << 16) + kColS, t_dp = tmem_base + ((uint32_t)(quad * 32) << 16) + kColDP;
         const uint32_t p_row = smem_u32(s_p) + (uint32_t)row * 128u, ds_row = smem_u32(s_ds) + (uint32_t)row * 128u, p_x = (uint32_t)(row & 7);
         const float sc2 = a.scale * kLog2e;
         const int nch = nk16 / 16;
+        const int n_mine = (nch - half + 1) / 2;         // this thread's chunks: half, half + 2, ...
         const bool live = row < Lq;
         auto mask_of = [&](int item) -> float {          // fetched one item ahead (as lse): off the critical path
             if (tid_g >= Lk || item >= n_items) return -INFINITY;
@@ -415,12 +412,12 @@ sdpa_bwd_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         for (int it = 0; it < my_items; ++it) {
             const int item = blockIdx.x + it * gridDim.x;
             const uint32_t par = (uint32_t)it & 1u;
-            named_bar_sync(1, 128);
-            s_mask[tid_g] = mv_next * kLog2e;
+            named_bar_sync(1, kBwdAThreads);
+            if (tid_g < 128) s_mask[tid_g] = mv_next * kLog2e;
             const float lse2 = lse_next * kLog2e;
             mv_next = mask_of(item + gridDim.x);
             lse_next = lse_of(item + gridDim.x);
-            named_bar_sync(1, 128);
+            named_bar_sync(1, kBwdAThreads);
             mbar_wait(sdp_full, par);
             tcgen05_fence_after();
             auto probs = [&](const uint32_t (&rs)[16], int ch, float (&pv)[16]) {       // P for keys [16 ch, +16)
@@ -434,43 +431,48 @@ sdpa_bwd_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                     pv[4 * q4 + 3] = ex2_approx(fmaf(__uint_as_float(rs[4 * q4 + 3]), sc2, m3) - lse2);
                 }
             };
+            auto load_pair = [&](uint32_t (&rs)[16], uint32_t (&rd)[16], int ch) {
+                tmem_ld_32x32b_x16(t_s + (uint32_t)(16 * ch), rs);
+                tmem_ld_32x32b_x16(t_dp + (uint32_t)(16 * ch), rd);
+            };
             uint32_t sa[16], da[16], sb[16], db[16];
-            // pass 1: delta = sum_j P_j dP_j
+            // pass 1: delta = sum_j P_j dP_j  (this thread's chunks; the other half's partial sum arrives through shared memory)
             float delta = 0.f;
-            tmem_ld_32x32b_x16(t_s, sa); tmem_ld_32x32b_x16(t_dp, da);
+            if (n_mine > 0) load_pair(sa, da, half);
 #pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {
-                if (ch < nch) {
+            for (int kq = 0; kq < 4; ++kq) {
+                if (kq < n_mine) {
+                    const int ch = half + 2 * kq;
                     tmem_ld_wait();
-                    if (ch + 1 < nch) {
-                        tmem_ld_32x32b_x16(t_s + (uint32_t)(16 * (ch + 1)), (ch & 1) ? sa : sb);
-                        tmem_ld_32x32b_x16(t_dp + (uint32_t)(16 * (ch + 1)), (ch & 1) ? da : db);
-                    }
+                    if (kq + 1 < n_mine) load_pair((kq & 1) ? sa : sb, (kq & 1) ? da : db, ch + 2);
                     float pv[16];
-                    probs((ch & 1) ? sb : sa, ch, pv);
+                    probs((kq & 1) ? sb : sa, ch, pv);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) delta = fmaf(pv[j], __uint_as_float(((ch & 1) ? db : da)[j]), delta);
+                    for (int j = 0; j < 16; ++j) delta = fmaf(pv[j], __uint_as_float(((kq & 1) ? db : da)[j]), delta);
                 }
             }
+            float* dpart = s_delta + (it & 1) * 256;
+            dpart[half * 128 + row] = delta;
+            // start re-reading while the partial sums cross
+            if (n_mine > 0) load_pair(sa, da, half);
+            named_bar_sync(2, kBwdAThreads);
+            delta += dpart[(half ^ 1) * 128 + row];
             // the P / dS tiles are still being read by dV/dK/dQ of the previous item until out_full(it-1) fires
             if (it > 0) mbar_wait(out_full, par ^ 1u);
             // pass 2: P and dS = P (dP - delta) -> shared memory (bf16, [query][key], SWIZZLE_128B rows)
-            tmem_ld_32x32b_x16(t_s, sa); tmem_ld_32x32b_x16(t_dp, da);
 #pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {
-                if (ch < nch) {
+            for (int kq = 0; kq < 4; ++kq) {
+                if (kq < n_mine) {
+                    const int ch = half + 2 * kq;
                     tmem_ld_wait();
-                    if (ch + 1 < nch) {
-                        tmem_ld_32x32b_x16(t_s + (uint32_t)(16 * (ch + 1)), (ch & 1) ? sa : sb);
-                        tmem_ld_32x32b_x16(t_dp + (uint32_t)(16 * (ch + 1)), (ch & 1) ? da : db);
-                    }
+                    if (kq + 1 < n_mine) load_pair((kq & 1) ? sa : sb, (kq & 1) ? da : db, ch + 2);
                     float pv[16];
-                    probs((ch & 1) ? sb : sa, ch, pv);
+                    probs((kq & 1) ? sb : sa, ch, pv);
                     uint32_t pp[8], pd[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const float d0 = pv[2 * j] * (__uint_as_float(((ch & 1) ? db : da)[2 * j]) - delta);
-                        const float d1 = pv[2 * j + 1] * (__uint_as_float(((ch & 1) ? db : da)[2 * j + 1]) - delta);
+                        const float d0 = pv[2 * j] * (__uint_as_float(((kq & 1) ? db : da)[2 * j]) - delta);
+                        const float d1 = pv[2 * j + 1] * (__uint_as_float(((kq & 1) ? db : da)[2 * j + 1]) - delta);
                         pp[j] = live ? pack_bf16x2(pv[2 * j], pv[2 * j + 1]) : 0u;
                         pd[j] = live ? pack_bf16x2(d0, d1) : 0u;
                     }
@@ -495,14 +497,13 @@ sdpa_bwd_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             const int b = item / H, hd = item % H;
             mbar_wait(out_full, (uint32_t)it & 1u);
             tcgen05_fence_after();
-            uint32_t r0[kD], r1[kD];
+            uint32_t r0[kD];
             tmem_ld_32x32b_x32(t_row + kColDV, r0); tmem_ld_32x32b_x32(t_row + kColDV + 32u, r0 + 32);
-            tmem_ld_32x32b_x32(t_row + kColDK, r1); tmem_ld_32x32b_x32(t_row + kColDK + 32u, r1 + 32);
             tmem_ld_wait();
-            if (row < Lk) {
-                store_row64(reinterpret_cast<__nv_bfloat16*>(args.dv) + ((int64_t)b * Lk + row) * args.lddv + (int64_t)hd * kD, r0, 1.0f);
-                store_row64(reinterpret_cast<__nv_bfloat16*>(args.dk) + ((int64_t)b * Lk + row) * args.lddk + (int64_t)hd * kD, r1, a.scale);
-            }
+            if (row < Lk) store_row64(reinterpret_cast<__nv_bfloat16*>(args.dv) + ((int64_t)b * Lk + row) * args.lddv + (int64_t)hd * kD, r0, 1.0f);
+            tmem_ld_32x32b_x32(t_row + kColDK, r0); tmem_ld_32x32b_x32(t_row + kColDK + 32u, r0 + 32);
+            tmem_ld_wait();
+            if (row < Lk) store_row64(reinterpret_cast<__nv_bfloat16*>(args.dk) + ((int64_t)b * Lk + row) * args.lddk + (int64_t)hd * kD, r0, a.scale);
             tmem_ld_32x32b_x32(t_row + kColDQ, r0); tmem_ld_32x32b_x32(t_row + kColDQ + 32u, r0 + 32);
             tmem_ld_wait();
             tcgen05_fence_before();
@@ -553,7 +554,8 @@ int sdpa_fwd_tc5_bf16(const SdpaArgs& a, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) { OVQA_CUDA_OK(cudaFuncSetAttribute(sdpa_fwd_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem)); attr_set = true; }
     const int64_t items = a.B * a.h;
-    const int grid = (int)(items < sm_count() ? items : sm_count());
+    const int64_t slots = 2 * (int64_t)sm_count();            // two CTAs per SM
+    const int grid = (int)(items < slots ? items : slots);
     sdpa_fwd_tc5_kernel<<<grid, kFwdThreads, kFwdSmem, st>>>(mq, mk, mv, args);
     OVQA_LAUNCH_OK();
     return OVQA_OK;

@@ -185,10 +185,22 @@ def _cdt(mode: str) -> torch.dtype:
     return torch.float32 if mode == "fp32" else torch.bfloat16
 
 
-def _wgrad(dy2: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
+def _wgrad(dy2: torch.Tensor, x2: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """dW[n_out, n_in] = dy2^T x2 (fp32), both operands read where they lie ("T","T").  C has few tiles and the
-    reduction over B*L rows is long: ``split_k=0`` lets the library split it to fill the SMs."""
-    return ops.gemm(dy2, x2, a_op="T", b_op="T", out_dtype=torch.float32, split_k=0)
+    reduction over B*L rows is long: ``split_k=0`` lets the library split it to fill the SMs.  ``out``: zero-filled fp32 [n_out, n_in]."""
+    return ops.gemm(dy2, x2, a_op="T", b_op="T", out=out, out_dtype=torch.float32, split_k=0)
+
+
+def _zero_slab(device, *shapes):
+    """fp32 zero-filled tensors of the given shapes carved from ONE allocation (one fill kernel instead of one per
+    accumulator: every split-K weight gradient and every column-sum accumulator of a block's backward pass starts from zero)."""
+    sizes = [(math.prod(sh) + 3) // 4 * 4 for sh in shapes]                 # 16-byte aligned starts (vector atomics)
+    slab = torch.zeros((sum(sizes),), device=device, dtype=torch.float32)
+    out, o = [], 0
+    for sh, n in zip(shapes, sizes):
+        out.append(slab[o:o + math.prod(sh)].view(sh))
+        o += n
+    return out
 
 
 def _masked_operand(ds: torch.Tensor, ds16: Optional[torch.Tensor], mode: str, p: float, seed: int, off: int, rng_base=None) -> torch.Tensor:
@@ -295,16 +307,23 @@ class _MHAFn(torch.autograd.Function):
         B, Lq, Lk, D = ctx.shapes
         hk, hv = h * dk, h * dv
         p, seed, off, rng_base = ctx.p, ctx.seed, ctx.off, ctx.rng_base
+        # every accumulator of this backward pass (split-K weight gradients, column sums) comes from one zero-filled slab
+        if self_att:
+            w_shapes = [(2 * hk + hv, D)]
+        elif kv_same:
+            w_shapes = [(hk, D), (hk + hv, D)]
+        else:
+            w_shapes = [(hk, D), (hk, D), (hv, D)]
+        dgamma, dbeta, dbo, dbias, dwo, *dWs = _zero_slab(dy.device, (D,), (D,), (D,), (2 * hk,), (D, hv), *w_shapes)
         # LayerNorm backward; the bf16 copy already carries the output-projection dropout mask
-        ds, ds16, dgamma, dbeta, dbo = ops.layernorm_bwd(dy.reshape(B * Lq, D), s, mean, rstd, gamma, want_bf16=(mode == "bf16"),
-                                                         dropout_p=p, seed=seed, offset=off, offset_base=rng_base, want_dbias=True)
+        ds, ds16, *_ = ops.layernorm_bwd(dy.reshape(B * Lq, D), s, mean, rstd, gamma, want_bf16=(mode == "bf16"), dropout_p=p, seed=seed,
+                                         offset=off, offset_base=rng_base, dgamma=dgamma, dbeta=dbeta, want_dbias=True, dbias=dbo)
         d_o = _masked_operand(ds, ds16, mode, p, seed, off, rng_base)             # grad of the fc_o output (its column sums: dbo)
         ctx2 = att_ctx.view(B * Lq, hv)
-        dwo = _wgrad(d_o, ctx2)
+        _wgrad(d_o, ctx2, out=dwo)
         # projection bias gradients without a pass over dq/dk/dv:  d(bv) = sum_rows dV = sum_rows dctx (softmax rows sum to 1)
         # = (sum_rows d_o) Wo = dbo Wo, a 512-vector times the fp32 master weight;  d(bk) == 0 analytically (softmax is shift
         # invariant);  d(bq) = column sums of dq.
-        dbias = torch.zeros((2 * hk,), device=dy.device, dtype=torch.float32)
         dbq, dbk = dbias[:hk], dbias[hk:]
         dbv = torch.mv(wo.detach().float().t(), dbo)
         dctx = ops.gemm(d_o, weights.get([wo], cdt), b_op="T", out_dtype=cdt).view(B, Lq, hv)
@@ -329,23 +348,23 @@ class _MHAFn(torch.autograd.Function):
         dkeys = dvalues = None
         if self_att:
             d2 = dqkv.view(B * Lq, -1)
-            dW = _wgrad(d2, xq)
+            dW = _wgrad(d2, xq, out=dWs[0])
             ops.colsum(d2[:, :hk], out=dbq, accumulate=True)
             dwq, dwk, dwv = dW[:hk], dW[hk:2 * hk], dW[2 * hk:]
             dqueries = ops.gemm(d2, weights.get([wq, wk, wv], cdt), b_op="T", out_dtype=torch.float32, residual=ds.view(B * Lq, D)).view(B, Lq, D)
         else:
             dq2 = dq.reshape(B * Lq, hk)
-            dwq = _wgrad(dq2, xq)
+            dwq = _wgrad(dq2, xq, out=dWs[0])
             ops.colsum(dq2, out=dbq, accumulate=True)
             dqueries = ops.gemm(dq2, weights.get([wq], cdt), b_op="T", out_dtype=torch.float32, residual=ds.view(B * Lq, D)).view(B, Lq, D)
             if kv_same:
                 d2 = dkvb.view(B * Lk, -1)
-                dW = _wgrad(d2, xk)
+                dW = _wgrad(d2, xk, out=dWs[1])
                 dwk, dwv = dW[:hk], dW[hk:]
                 dkeys = ops.gemm(d2, weights.get([wk, wv], cdt), b_op="T", out_dtype=torch.float32).view(B, Lk, D)
             else:
                 dk2, dv2 = dk_.reshape(B * Lk, hk), dv_.reshape(B * Lk, hv)
-                dwk, dwv = _wgrad(dk2, xk), _wgrad(dv2, xv)
+                dwk, dwv = _wgrad(dk2, xk, out=dWs[1]), _wgrad(dv2, xv, out=dWs[2])
                 dkeys = ops.gemm(dk2, weights.get([wk], cdt), b_op="T", out_dtype=torch.float32).view(B, Lk, D)
                 dvalues = ops.gemm(dv2, weights.get([wv], cdt), b_op="T", out_dtype=torch.float32).view(B, Lk, D)
         return (dqueries, dkeys, dvalues, None, None, dwq, dbq, dwk, dbk, dwv, dbv, dwo, dbo, dgamma, dbeta, gdw, gdb, None)
@@ -402,15 +421,16 @@ class _PWFFFn(torch.autograd.Function):
         rng_base = ctx.rng_base
         cdt = _cdt(mode)
         D = x2.shape[1]
-        ds, ds16, dgamma, dbeta, db2 = ops.layernorm_bwd(dy.reshape(-1, D), s, mean, rstd, gamma, want_bf16=(mode == "bf16"),
-                                                         dropout_p=p, seed=s2, offset=o2, offset_base=rng_base, want_dbias=True)
+        dff = w1.shape[0]
+        dgamma, dbeta, db2, db1, dw2, dw1 = _zero_slab(dy.device, (D,), (D,), (D,), (dff,), (D, dff), (dff, D))     # one fill for every accumulator
+        ds, ds16, *_ = ops.layernorm_bwd(dy.reshape(-1, D), s, mean, rstd, gamma, want_bf16=(mode == "bf16"), dropout_p=p, seed=s2,
+                                         offset=o2, offset_base=rng_base, dgamma=dgamma, dbeta=dbeta, want_dbias=True, dbias=db2)
         d2 = _masked_operand(ds, ds16, mode, p, s2, o2, rng_base)                   # grad of the fc2 output (its column sums: db2)
-        dw2 = _wgrad(d2, hact)
+        _wgrad(d2, hact, out=dw2)
         # grad of the fc1 pre-activation: (d2 W2) * [dropout1 scale * gelu'(pre)] — the forward saved that product (the derivative
         # of its whole fused activation), so the dgrad epilogue is one multiply: no transcendental, no RNG
-        db1 = torch.zeros((w1.shape[0],), device=dy.device, dtype=torch.float32)
         dpre = ops.gemm(d2, weights.get([w2], cdt), b_op="T", out_dtype=cdt, mul_aux=pre, colsum=db1)     # + fc1 bias gradient (column sums)
-        dw1 = _wgrad(dpre, x2)
+        _wgrad(dpre, x2, out=dw1)
         dx = ops.gemm(dpre, weights.get([w1], cdt), b_op="T", out_dtype=torch.float32, residual=ds.reshape(-1, D)).view(ctx.xshape)
         return dx, dw1, db1, dw2, db2, dgamma, dbeta, None
 

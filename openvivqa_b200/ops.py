@@ -223,15 +223,17 @@ def layernorm_fwd(x, gamma, beta, *, residual=None, post_add=None, eps: float = 
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, *, dx_add=None, want_bf16: bool = False, dropout_p: float = 0.0,
-                  seed: int = 0, offset: int = 0, offset_base=None, dgamma=None, dbeta=None, want_dbias: bool = False):
+                  seed: int = 0, offset: int = 0, offset_base=None, dgamma=None, dbeta=None, want_dbias: bool = False, dbias=None):
     """Returns (dx, dx_bf16|None, dgamma, dbeta[, dbias]).  ``want_dbias``: also the column sums of the (dropout-masked) dx —
-    the bias gradient of the GEMM that produced this LayerNorm's input."""
+    the bias gradient of the GEMM that produced this LayerNorm's input.  ``dgamma`` / ``dbeta`` / ``dbias``, when given, are
+    ZERO-FILLED fp32 [D] accumulators owned by the caller (e.g. views of one slab zeroed by a single fill)."""
     _need_cuda(dy, x, mean, rstd, gamma)
     D = x.shape[-1]
     dy2, x2 = dy.reshape(-1, D).contiguous().float(), x.reshape(-1, D)
     rows = x2.shape[0]
     dx = torch.empty_like(x2)
     dx16 = torch.empty(x2.shape, device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    dbias_given = dbias
     dbias = None
     if dgamma is None and dbeta is None:
         acc = torch.zeros((3 if want_dbias else 2, D), device=x.device, dtype=torch.float32)     # one fill for all accumulators
@@ -242,7 +244,7 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, *, dx_add=None, want_bf16: bool = Fa
             dgamma = torch.zeros((D,), device=x.device, dtype=torch.float32)
         if dbeta is None:
             dbeta = torch.zeros((D,), device=x.device, dtype=torch.float32)
-        dbias = torch.zeros((D,), device=x.device, dtype=torch.float32) if want_dbias else None
+        dbias = (dbias_given if dbias_given is not None else torch.zeros((D,), device=x.device, dtype=torch.float32)) if want_dbias else None
     L.call("ovqa_layernorm_bwd", _p(dy2), _p(x2), _p(mean), _p(rstd), _p(gamma),
            None if dx_add is None else _p(dx_add.reshape(-1, D).contiguous()), _p(dx), _p(dx16), _p(dgamma), _p(dbeta), _p(dbias),
            rows, D, float(dropout_p), int(seed), int(offset), _p(offset_base), _stream())
