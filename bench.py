@@ -210,7 +210,8 @@ class GemmMeter:
             q, k, v = a[:3]
             h, dk, dv = kw["h"], kw["d_k"], kw["d_v"]
             B, Lq, Lk, e = q.shape[0], q.shape[1], k.shape[1], q.element_size()
-            return e * B * h * (2 * Lq * dk + 2 * Lk * dk + 2 * Lk * dv + 3 * Lq * dv) + 4.0 * B * Lk + 4.0 * B * h * Lq, f"sdpa_bwd B={B} Lq={Lq} Lk={Lk} h={h} d={dk}"
+            # q, k, v, o, do read; dq, dk, dv written (the tensor-memory core does not even read o)
+            return e * B * h * (2 * Lq * dk + 2 * Lk * dk + 2 * Lk * dv + 2 * Lq * dv) + 4.0 * B * Lk + 4.0 * B * h * Lq, f"sdpa_bwd B={B} Lq={Lq} Lk={Lk} h={h} d={dk}"
 
         def y_ln_fwd(a, kw, out):
             x = a[0]
@@ -227,7 +228,10 @@ class GemmMeter:
             return lambda a, kw, out: (nbytes(a[0]) + nbytes(out if torch.is_tensor(out) else None), f"{name} {tuple(a[0].shape)}")
 
         table = dict(sdpa_fwd=y_sdpa_fwd, sdpa_bwd=y_sdpa_bwd, layernorm_fwd=y_ln_fwd, layernorm_bwd=y_ln_bwd, colsum=y_in("colsum"),
-                     to_bf16=y_io("to_bf16"), to_f32=y_io("to_f32"), add=y_io("add"), dropout_apply=y_io("dropout_apply"))
+                     to_bf16=y_io("to_bf16"), to_f32=y_io("to_f32"), add=y_io("add"), dropout_apply=y_io("dropout_apply"),
+                     ptr_scores=lambda a, kw, out: (nbytes(a[0], a[1]) + 4.0 * a[0].shape[0] * a[0].shape[1] * a[1].shape[1], "ptr_scores"),
+                     prev_pred_embed=lambda a, kw, out: (nbytes(out if torch.is_tensor(out) else None) * 2, "prev_pred_embed"),
+                     greedy_step=lambda a, kw, out: (nbytes(a[0]), "greedy_step"))
         for name, fn_bytes in table.items():
             if not hasattr(ops, name):
                 continue
@@ -523,7 +527,7 @@ def run_ours(args):
         if "sdpa_fwd" in by_op and "sdpa_bwd" in by_op:
             a_ms = by_op["sdpa_fwd"]["ms"] + by_op["sdpa_bwd"]["ms"]
             a_y = (by_op["sdpa_fwd"]["gbs"] * by_op["sdpa_fwd"]["ms"] + by_op["sdpa_bwd"]["gbs"] * by_op["sdpa_bwd"]["ms"]) * 1e6   # bytes
-            att = dict(bound="hbm", kernel="sdpa_fwd_mma_kernel + sdpa_bwd_mma_kernel (attention core, all launches of a step)",
+            att = dict(bound="hbm", kernel="sdpa_fwd_tc5_kernel + sdpa_bwd_tc5_kernel (+ sdpa_*_mma_kernel for the 30-token heads): attention core, all launches of a step",
                        achieved=a_y / (a_ms * 1e-3) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s", frac=a_y / (a_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                        traffic=None, share_of_step=a_ms / meter_ms_per_step, launches=by_op["sdpa_fwd"]["launches"] + by_op["sdpa_bwd"]["launches"],
                        how="same instrumented graph replay as `roofline`; algorithmic bytes = q,k,v,out(,dout,dq,dk,dv),lse,mask once each")
@@ -749,6 +753,10 @@ def run_m4c(args):
                                 eager_ms_per_step=eager_ms, hoisted="TextBert + input encodings run once per batch (loop-invariant); last MMT layer computes only the OCR+decoder rows"),
                     e2e=dict(value=B * world * args.steps / e2e_s, unit="samples/s", h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=B * c["T"] * 8),
                     gpu_launches=launches, roofline=roof, clocks=clocks)
+        by_kernel, by_op = meter.summary_other(peaks["hbm_gbs"])
+        lib_ms = (gm["total_ms"] if gm else 0.0) + sum(v["ms"] for v in by_op.values())
+        line["step_breakdown"] = dict(instrumented_ms_per_step=meter_ms, gemm_ms=gm["total_ms"] if gm else None, by_op=by_op, library_ms=lib_ms,
+                                      other_ms=meter_ms - lib_ms, by_kernel=by_kernel[:10])
         if args.gpus == 1 and not args.no_cpu_baseline:
             cs, _ = time_cpu_m4c(c, 4, 1, 1)
             line["cpu_baseline"] = dict(value=cs, unit="samples/s", cores=torch.get_num_threads(), kind="port",

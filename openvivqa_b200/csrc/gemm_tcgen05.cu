@@ -63,26 +63,48 @@ __device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c,
 __device__ __forceinline__ void lds128(uint32_t addr, float& a, float& b, float& c, float& d) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(addr) : "memory");
 }
-template <typename TC> __device__ __forceinline__ void store8(TC* p, const float (&v)[8]);
-template <> __device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) {
+// A lane's 8 values of a chunk row are columns [col, col+4) and [col+HI, col+HI+4).  bf16 results: HI = 4 (8 consecutive columns, one
+// 16-byte access).  fp32 results: HI = 16 — the four lanes of a row then cover 64 CONTIGUOUS bytes per access (two whole sectors);
+// with 8 consecutive fp32 columns per lane every 16-byte access was half a sector at a 32-byte stride, i.e. twice the L2
+// transactions for C, the residual and the split-K atomics.
+template <typename TC, int HI> __device__ __forceinline__ void store8(TC* p, const float (&v)[8]);
+template <> __device__ __forceinline__ void store8<float, 4>(float* p, const float (&v)[8]) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
     *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
 }
-template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
+template <> __device__ __forceinline__ void store8<float, 16>(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 16) = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <> __device__ __forceinline__ void store8<__nv_bfloat16, 4>(__nv_bfloat16* p, const float (&v)[8]) {
     *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
 }
-template <typename TC> __device__ __forceinline__ void load8(const TC* p, float (&v)[8]);
-template <> __device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
+template <> __device__ __forceinline__ void store8<__nv_bfloat16, 16>(__nv_bfloat16* p, const float (&v)[8]) {
+    *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+    *reinterpret_cast<uint2*>(p + 16) = make_uint2(pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+template <typename TC, int HI> __device__ __forceinline__ void load8(const TC* p, float (&v)[8]);
+template <> __device__ __forceinline__ void load8<float, 4>(const float* p, float (&v)[8]) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
-template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+template <> __device__ __forceinline__ void load8<float, 16>(const float* p, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 16));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <> __device__ __forceinline__ void load8<__nv_bfloat16, 4>(const __nv_bfloat16* p, float (&v)[8]) {
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
     const float2 p0 = unpack_bf16x2(u.x), p1 = unpack_bf16x2(u.y), p2 = unpack_bf16x2(u.z), p3 = unpack_bf16x2(u.w);
     v[0] = p0.x; v[1] = p0.y; v[2] = p1.x; v[3] = p1.y; v[4] = p2.x; v[5] = p2.y; v[6] = p3.x; v[7] = p3.y;
 }
+template <> __device__ __forceinline__ void load8<__nv_bfloat16, 16>(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint2 a = __ldg(reinterpret_cast<const uint2*>(p)), b = __ldg(reinterpret_cast<const uint2*>(p + 16));
+    const float2 p0 = unpack_bf16x2(a.x), p1 = unpack_bf16x2(a.y), p2 = unpack_bf16x2(b.x), p3 = unpack_bf16x2(b.y);
+    v[0] = p0.x; v[1] = p0.y; v[2] = p1.x; v[3] = p1.y; v[4] = p2.x; v[5] = p2.y; v[6] = p3.x; v[7] = p3.y;
+}
 // Column sums of a 32 x 32 chunk: every lane holds partial sums of its 8 columns over the rows it finished (rows rr, rr+8, ...);
 // the 8 lanes with the same column group (lane % 4) are combined by shuffles, lanes 0..3 add the chunk's 32 sums to colsum[].
+template <int HI>
 __device__ __forceinline__ void colsum_flush(float* __restrict__ colsum, int64_t col, const float (&cs)[8], int lane) {
     float t[8];
 #pragma unroll
@@ -94,7 +116,7 @@ __device__ __forceinline__ void colsum_flush(float* __restrict__ colsum, int64_t
     }
     if (lane < 4) {
         atomicAdd(reinterpret_cast<float4*>(colsum + col), make_float4(t[0], t[1], t[2], t[3]));
-        atomicAdd(reinterpret_cast<float4*>(colsum + col + 4), make_float4(t[4], t[5], t[6], t[7]));
+        atomicAdd(reinterpret_cast<float4*>(colsum + col + HI), make_float4(t[4], t[5], t[6], t[7]));
     }
 }
 // slow path for ragged column tails / pitches that do not allow 16-byte vectors: one element, every feature
@@ -245,11 +267,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         // ------------------------------------------------------------------ epilogue warps 2..17
         const int quad = warp % 4;                        // tcgen05.ld: warp w may touch TMEM lanes [32*(w%4), +32)
         const int slot = (warp - 2) / 4;                  // which 32-column chunks of the tile this warp owns: slot, slot+4, ...
-        const int rr = lane / 4, c8 = lane % 4;           // read-back mapping: row rr (+8 per pass), columns [8*c8, +8)
+        const int rr = lane / 4, c8 = lane % 4;           // read-back mapping: row rr (+8 per pass); bf16 C: columns [8 c8, +8); fp32 C: [4 c8, +4) and [16 + 4 c8, +4)
+        constexpr bool kSplit = sizeof(TC) == 4;
+        constexpr int HI = kSplit ? 16 : 4;               // column distance between a lane's two groups of four
         // scratch: 32 rows x 8 granules of 16 B per warp, granule index XOR (row & 7)  (conflict-free both ways)
         const uint32_t sc = smem_u32(scratch) + (uint32_t)(warp - 2) * 4096u;
         const uint32_t st_row = sc + (uint32_t)lane * 128u, st_x = (uint32_t)(lane & 7);
-        const uint32_t ld_lo = sc + (uint32_t)rr * 128u + (uint32_t)(((2 * c8) ^ rr) << 4), ld_hi = sc + (uint32_t)rr * 128u + (uint32_t)(((2 * c8 + 1) ^ rr) << 4);
+        const uint32_t g_lo = kSplit ? (uint32_t)c8 : (uint32_t)(2 * c8), g_hi = kSplit ? (uint32_t)(4 + c8) : (uint32_t)(2 * c8 + 1);   // 16-byte granules of the row
+        const uint32_t ld_lo = sc + (uint32_t)rr * 128u + ((g_lo ^ (uint32_t)rr) << 4), ld_hi = sc + (uint32_t)rr * 128u + ((g_hi ^ (uint32_t)rr) << 4);
         const float alpha = epi.alpha;
         const float* __restrict__ bias = (MODE == EPI_SPLITK) ? nullptr : epi.bias;
         auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
@@ -280,6 +305,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         for (int tile = tile0; tile < num_tiles; tile += tile_step) {
             int mt, nt, kb0, kb1;
             decode(tile, mt, nt, kb0, kb1);
+            if constexpr (MODE == EPI_FULL && FEAT >= 0 && (FEAT & (F_RES | F_MULAUX)) != 0) {
+                // Pull the NEXT tile's epilogue operand (residual rows / saved derivative) into L2 now: its loads are the
+                // latency that bounds these K = 512 epilogues, and an L2 hit is ~3x closer than DRAM.  128 rows x BN columns.
+                const int nxt = tile + tile_step;
+                if (nxt < num_tiles) {
+                    int mt2, nt2, ka, kb_;
+                    decode(nxt, mt2, nt2, ka, kb_);
+                    constexpr int kElt = (FEAT & F_RES) ? 4 : (int)sizeof(TC);
+                    constexpr int kLinesPerRow = BN * kElt / 128;
+                    const char* base = (FEAT & F_RES) ? reinterpret_cast<const char*>(residual) : reinterpret_cast<const char*>(aux_in);
+                    const int64_t ld_b = ((FEAT & F_RES) ? ld_res : ld_aux) * kElt;
+                    for (int idx = (warp - 2) * 32 + lane; idx < BM * kLinesPerRow; idx += kEpiWarps * 32) {
+                        const int64_t r = (int64_t)mt2 * TM + (int64_t)cta_rank * BM + idx / kLinesPerRow;
+                        const int64_t cbyte = ((int64_t)nt2 * BN) * kElt + (idx % kLinesPerRow) * 128;
+                        if (r < m && cbyte < n * kElt) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + r * ld_b + cbyte));
+                    }
+                }
+            }
             mbar_wait(tmem_full + acc, acc_phase);
             tcgen05_fence_after();
             const int64_t row_base = (int64_t)mt * TM + (int64_t)cta_rank * BM + quad * 32 + rr;          // + 8 * pass
@@ -288,7 +331,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             for (int c0 = slot * 32; c0 < BN; c0 += 128) {
                 const int64_t col0 = (int64_t)nt * BN + c0;
                 if (col0 >= n) break;                                     // warp-uniform
-                const int64_t col = col0 + c8 * 8;
+                const int64_t col = col0 + (kSplit ? c8 * 4 : c8 * 8);
                 const bool fast = vec_ok && (col0 + 32 <= n);             // warp-uniform: whole chunk on the vector path
                 if constexpr (MODE == EPI_FULL && FEAT >= 0) {
                     if (fast) {                                           // warp-uniform
@@ -299,7 +342,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                         const float a_s = (kGelu ? 1.0f : k_out) * alpha;
                         float b8[8];
                         if constexpr (kBias) {
-                            load8<float>(bias + col, b8);
+                            load8<float, HI>(bias + col, b8);
                             if constexpr (kDrop && !kGelu) {
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) b8[j] *= k_out;
@@ -312,8 +355,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                             for (int p = 0; p < 4; ++p) {
                                 const int64_t row = min(row_base + 8 * p, m - 1);
                                 if constexpr (kRes) {
-                                    const uint4* rp = reinterpret_cast<const uint4*>(residual + row * ld_res + col);
-                                    in_lo[p] = __ldg(rp); in_hi[p] = __ldg(rp + 1);
+                                    const float* rp = residual + row * ld_res + col;
+                                    in_lo[p] = __ldg(reinterpret_cast<const uint4*>(rp)); in_hi[p] = __ldg(reinterpret_cast<const uint4*>(rp + HI));
                                 } else {
                                     static_assert(!kMul || sizeof(TC) == 2, "MUL_AUX specialisation is bf16");
                                     in_lo[p] = __ldg(reinterpret_cast<const uint4*>(aux_in + row * ld_aux + col));
@@ -345,7 +388,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                         float cs[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) cs[j] = 0.f;
-                        const uint64_t ctr0 = rng_offset + (uint64_t)((row_base * n + col) >> 3);   // n % 8 == 0 (vec_ok): + n per pass
+                        // Philox group (8 consecutive elements) counters; n % 8 == 0 (vec_ok): + n per pass of 8 rows.  bf16 C: the lane's 8
+                        // columns ARE one group.  fp32 C: the lane holds half of two groups (g and g + 2); even lanes draw group g, odd lanes
+                        // group g + 2, and the pair swaps the halves it does not need — still one Philox call per lane and pass.
+                        const uint64_t ctr0 = rng_offset + (uint64_t)((row_base * n + col0) >> 3) +
+                                              (uint64_t)(kSplit ? ((c8 & 1) ? 2 + c8 / 2 : c8 / 2) : c8);
 #pragma unroll
                         for (int p = 0; p < 4; ++p) {
                             const int64_t row = row_base + 8 * p;
@@ -353,7 +400,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                             lds128(ld_lo + p * 1024, v[0], v[1], v[2], v[3]);
                             lds128(ld_hi + p * 1024, v[4], v[5], v[6], v[7]);
                             bool keep[8];
-                            if constexpr (kDrop) dropout_keep8(keep, philox4x32(ctr0 + (uint64_t)p * (uint64_t)n, seed), thr_hi);
+                            if constexpr (kDrop) {
+                                uint4 r = philox4x32(ctr0 + (uint64_t)p * (uint64_t)n, seed);
+                                if constexpr (kSplit) {
+                                    const bool odd = c8 & 1;
+                                    const uint32_t s0 = odd ? r.x : r.z, s1 = odd ? r.y : r.w;          // the half the partner needs
+                                    const uint32_t q0 = __shfl_xor_sync(0xffffffffu, s0, 1), q1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+                                    // columns [col, +4): fields of group g (even lane: own x,y; odd lane: partner's z,w);  [col+16, +4): group g + 2
+                                    r = odd ? make_uint4(q0, q1, r.z, r.w) : make_uint4(r.x, r.y, q0, q1);
+                                }
+                                dropout_keep8(keep, r, thr_hi);
+                            }
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 v[j] = kBias ? fmaf(v[j], a_s, b8[j]) : v[j] * a_s;
@@ -380,15 +437,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                                 for (int j = 0; j < 8; ++j) v[j] += __uint_as_float(w[j]);
                             }
                             if (row < m) {
-                                store8<TC>(C + row * ldc + col, v);
-                                if constexpr (kSave) store8<TC>(aux_out + row * ld_aux + col, g);
+                                store8<TC, HI>(C + row * ldc + col, v);
+                                if constexpr (kSave) store8<TC, HI>(aux_out + row * ld_aux + col, g);
                                 if constexpr (kColsum) {
 #pragma unroll
                                     for (int j = 0; j < 8; ++j) cs[j] += v[j];
                                 }
                             }
                         }
-                        if constexpr (kColsum) colsum_flush(colsum, col, cs, lane);
+                        if constexpr (kColsum) colsum_flush<HI>(colsum, col, cs, lane);
                         __syncwarp();
                         continue;
                     }
@@ -396,7 +453,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                 float b8[8], cs[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) b8[j] = cs[j] = 0.f;
-                if (fast && bias) load8<float>(bias + col, b8);
+                if (fast && bias) load8<float, HI>(bias + col, b8);
                 {   // TMEM -> registers (row per lane) -> swizzled scratch
                     uint32_t r[32];
                     tmem_ld_32x32b_x32(t_row + (uint32_t)c0, r);
@@ -416,8 +473,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                     float pre[8];                                         // residual row, else the saved GELU' / pre-activation
                     if constexpr (MODE == EPI_FULL) {
                         if (fast && row_ok) {
-                            if (residual) load8<float>(residual + row * ld_res + col, pre);
-                            else if (f_dgelu || f_mul_aux) load8<TC>(aux_in + row * ld_aux + col, pre);
+                            if (residual) load8<float, HI>(residual + row * ld_res + col, pre);
+                            else if (f_dgelu || f_mul_aux) load8<TC, HI>(aux_in + row * ld_aux + col, pre);
                         }
                     }
                     float v[8];
@@ -426,7 +483,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                     if (!fast) {                                          // ragged tail / unaligned pitches
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
-                            if (row_ok && col + j < n) epilogue_scalar<TC>(epi, v[j], row, col + j, n, C, ldc, split_k);
+                        {
+                            const int64_t cj = col + (j < 4 ? j : HI + j - 4);
+                            if (row_ok && cj < n) epilogue_scalar<TC>(epi, v[j], row, cj, n, C, ldc, split_k);
+                        }
                         continue;
                     }
                     if (!row_ok) continue;
@@ -434,7 +494,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                         if constexpr (sizeof(TC) == 4) {
                             float* cp = reinterpret_cast<float*>(C) + row * ldc + col;
                             atomicAdd(reinterpret_cast<float4*>(cp), make_float4(v[0] * alpha, v[1] * alpha, v[2] * alpha, v[3] * alpha));
-                            atomicAdd(reinterpret_cast<float4*>(cp + 4), make_float4(v[4] * alpha, v[5] * alpha, v[6] * alpha, v[7] * alpha));
+                            atomicAdd(reinterpret_cast<float4*>(cp + HI), make_float4(v[4] * alpha, v[5] * alpha, v[6] * alpha, v[7] * alpha));
                         }
                         continue;
                     }
@@ -442,7 +502,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                     for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], alpha, b8[j]);
                     if constexpr (MODE == EPI_FULL) {
                         float ds[8];
-                        if (f_drop) dropout_scale8(ds, (uint64_t)(row * n + col), drop_p, inv_keep, seed, rng_offset);
+                        if (f_drop) {
+                            if constexpr (kSplit) {               // two groups of four columns: the matching halves of two Philox calls
+                                const float4 d0 = dropout_scale4((uint64_t)(row * n + col), drop_p, inv_keep, seed, rng_offset);
+                                const float4 d1 = dropout_scale4((uint64_t)(row * n + col + HI), drop_p, inv_keep, seed, rng_offset);
+                                ds[0] = d0.x; ds[1] = d0.y; ds[2] = d0.z; ds[3] = d0.w; ds[4] = d1.x; ds[5] = d1.y; ds[6] = d1.z; ds[7] = d1.w;
+                            } else {
+                                dropout_scale8(ds, (uint64_t)(row * n + col), drop_p, inv_keep, seed, rng_offset);
+                            }
+                        }
                         if (f_save_d) {                                   // y = GELU(v), aux_out = GELU'(v) [x dropout scale]: one CDF + one exponential for both
                             float d[8];
 #pragma unroll
@@ -450,22 +518,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                                 v[j] = gelu_and_grad_fast(v[j], d[j]);
                                 if (f_drop) d[j] *= ds[j];
                             }
-                            store8<TC>(aux_out + row * ld_aux + col, d);
+                            store8<TC, HI>(aux_out + row * ld_aux + col, d);
                         } else {
-                            if (aux_out) store8<TC>(aux_out + row * ld_aux + col, v);
+                            if (aux_out) store8<TC, HI>(aux_out + row * ld_aux + col, v);
                             if (f_gelu) {
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) v[j] = gelu_fast(v[j]);
                             }
                         }
                         if (f_dgelu || f_mul_aux) {
-                            if (residual) load8<TC>(aux_in + row * ld_aux + col, b8 /*scratch: bias already applied*/);
+                            if (residual) load8<TC, HI>(aux_in + row * ld_aux + col, b8 /*scratch: bias already applied*/);
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const float a = residual ? b8[j] : pre[j];
                                 v[j] *= f_mul_aux ? a : dgelu_fast(a);
                             }
-                            if (residual && bias) load8<float>(bias + col, b8);   // (never together on the path) restore for the next pass
+                            if (residual && bias) load8<float, HI>(bias + col, b8);   // (never together on the path) restore for the next pass
                         }
                         if (f_drop) {
 #pragma unroll
@@ -478,15 +546,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                         if constexpr (sizeof(TC) == 4) {
                             if (beta != 0.f) {
                                 float o[8];
-                                load8<float>(reinterpret_cast<const float*>(C) + row * ldc + col, o);
+                                load8<float, HI>(reinterpret_cast<const float*>(C) + row * ldc + col, o);
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) v[j] = fmaf(beta, o[j], v[j]);
                             }
                         }
                     }
-                    store8<TC>(C + row * ldc + col, v);
+                    store8<TC, HI>(C + row * ldc + col, v);
                     if constexpr (MODE == EPI_FULL) {
-                        if (c2) store8<__nv_bfloat16>(c2 + row * ldc2 + col, v);
+                        if (c2) store8<__nv_bfloat16, HI>(c2 + row * ldc2 + col, v);
                         if (colsum) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) cs[j] += v[j];
@@ -494,7 +562,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                     }
                 }
                 if constexpr (MODE == EPI_FULL) {
-                    if (colsum && fast) colsum_flush(colsum, col, cs, lane);      // (the scalar path adds element by element)
+                    if (colsum && fast) colsum_flush<HI>(colsum, col, cs, lane);      // (the scalar path adds element by element)
                 }
                 __syncwarp();                                             // scratch is rewritten by the next chunk
             }
