@@ -25,6 +25,8 @@ int sdpa_fwd_mma_bf16(const SdpaArgs&, cudaStream_t);   // attention_mma.cu
 bool sdpa_fwd_mma_supported(const SdpaArgs&);
 int sdpa_fwd_tc5_bf16(const SdpaArgs&, cudaStream_t);   // attention_tc5.cu (tcgen05 / TMEM / TMA: head dim 64, Lq, Lk <= 128, per-key mask)
 bool sdpa_fwd_tc5_supported(const SdpaArgs&);
+int sdpa_fwd_tc5w_bf16(const SdpaArgs&, cudaStream_t);  // attention_tc5.cu, wide heads (d = 96 / 128), any Lq, Lk <= 256
+bool sdpa_fwd_tc5w_supported(const SdpaArgs&);
 int sdpa_bwd_tc5_bf16(const SdpaArgs&, const void*, void*, void*, void*, int64_t, int64_t, int64_t, int64_t, cudaStream_t);
 bool sdpa_bwd_tc5_supported(const SdpaArgs&, const void*, const void*, const void*, const void*, int64_t, int64_t, int64_t, int64_t);
 int sdpa_bwd_mma_bf16(const SdpaArgs&, const void*, void*, void*, void*, int64_t, int64_t, int64_t, int64_t, cudaStream_t);
@@ -112,6 +114,7 @@ extern "C" int ovqa_sdpa_fwd(const void* q, const void* k, const void* v, void* 
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == OVQA_F32) return sdpa_fwd_simt_launch<float>(a, st);
     if (sdpa_fwd_tc5_supported(a)) return sdpa_fwd_tc5_bf16(a, st);
+    if (sdpa_fwd_tc5w_supported(a)) return sdpa_fwd_tc5w_bf16(a, st);
     if (sdpa_fwd_mma_supported(a)) return sdpa_fwd_mma_bf16(a, st);
     return sdpa_fwd_simt_launch<__nv_bfloat16>(a, st);
 }

@@ -253,6 +253,238 @@ sdpa_fwd_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 }
 
 
+// ------------------------------------------------------------------------------------------------ forward, wide heads / long rows
+// Head dim 64 + TW (TW = 32: M4C's 96-wide heads, TW = 64: 128), Lq of any length as 128-row tiles (work item = sample, head, row tile),
+// Lk <= 256.  Same pipeline as above with ONE CTA per SM and two load stages (a stage is up to 96 KB here): producer warp, MMA warp, two
+// softmax groups.  A head is two column blocks: 64 columns as SWIZZLE_128B rows and a TW-column tail block as SWIZZLE_64B rows (32
+// columns) or a second SWIZZLE_128B block (64), so nothing is padded in shared memory:  S = Q K^T is 4 + TW/16 MMAs,  O = P V is one MMA per
+// 16 keys into columns [0,64) plus one into [64, 64+TW) (the tail block of V is its own MN-major operand).
+struct Tc5WideArgs {
+    SdpaArgs a;
+    int nk16, q_rows, n_mt;      // keys rounded to 16; rows of the Q box; row tiles per (sample, head)
+};
+constexpr int kWideThreads = 64 + 2 * 128;
+
+template <int TW>
+__global__ void __launch_bounds__(kWideThreads, 1)
+sdpa_fwd_tc5w_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_constant__ CUtensorMap map_q1,
+                     const __grid_constant__ CUtensorMap map_k0, const __grid_constant__ CUtensorMap map_k1,
+                     const __grid_constant__ CUtensorMap map_v0, const __grid_constant__ CUtensorMap map_v1, Tc5WideArgs args) {
+    constexpr int D = 64 + TW;
+    constexpr int kRowB = TW == 64 ? 128 : 64;           // bytes of a tail-block row
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const SdpaArgs& a = args.a;
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int Lq = (int)a.Lq, Lk = (int)a.Lk, H = (int)a.h, nk16 = args.nk16, n_mt = args.n_mt;
+    // stage: Q0 [128 x 128 B] | Q1 [128 x kRowB] | K0 [nk16 x 128] | K1 [nk16 x kRowB] | V0 | V1;  P (nk16/64 blocks of 128 x 128 B) overwrites Q | K
+    const uint32_t q1_off = kTileBytes, k0_off = q1_off + 128 * kRowB, k1_off = k0_off + (uint32_t)nk16 * 128u,
+                   v0_off = k1_off + (uint32_t)nk16 * kRowB, v1_off = v0_off + (uint32_t)nk16 * 128u, stage_bytes = v1_off + (uint32_t)nk16 * kRowB;
+    uint8_t* s_load = smem;
+    float* s_mask = reinterpret_cast<float*>(smem + 2 * stage_bytes);     // [2 groups][256]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_mask + 2 * 256);
+    uint64_t* load_full = bars;          // [2]
+    uint64_t* load_empty = bars + 2;     // [2]
+    uint64_t* s_full = bars + 4;         // [2]
+    uint64_t* p_full = bars + 6;         // [2]  128 arrivals
+    uint64_t* o_full = bars + 8;         // [2]
+    uint64_t* acc_empty = bars + 10;     // [2]  128 arrivals
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    const int n_items = (int)a.B * H * n_mt;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(load_full + i, 1); mbar_init(load_empty + i, 1); mbar_init(s_full + i, 1); mbar_init(p_full + i, 128);
+            mbar_init(o_full + i, 1); mbar_init(acc_empty + i, 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;           // group g: S in columns [256 g, +nk16), O aliased onto [256 g, +D)
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)(args.q_rows + 2 * nk16) * (128u + kRowB);
+            int it = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const int ls = it & 1;
+                const int mt = item % n_mt, bh = item / n_mt, b = bh / H, hd = bh % H;
+                mbar_wait(load_empty + ls, (((uint32_t)(it >> 1)) & 1u) ^ 1u);
+                mbar_expect_tx(load_full + ls, bytes);
+                uint8_t* st = s_load + ls * stage_bytes;
+                const int qrow = b * Lq + mt * 128, krow = b * Lk, c0 = hd * D, c1 = hd * D + 64;
+                tma_load_2d(st, &map_q0, load_full + ls, c0, qrow);
+                tma_load_2d(st + q1_off, &map_q1, load_full + ls, c1, qrow);
+                tma_load_2d(st + k0_off, &map_k0, load_full + ls, c0, krow);
+                tma_load_2d(st + k1_off, &map_k1, load_full + ls, c1, krow);
+                tma_load_2d(st + v0_off, &map_v0, load_full + ls, c0, krow);
+                tma_load_2d(st + v1_off, &map_v1, load_full + ls, c1, krow);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc_s = make_idesc(128, nk16, false, false);
+            const uint32_t idesc_o0 = make_idesc(128, 64, false, true), idesc_o1 = make_idesc(128, TW, false, true);
+            const int my_items = n_items > (int)blockIdx.x ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+            auto tail_desc_k = [&](uint32_t addr, int t) {           // K-major tail block, k-step t (16 columns)
+                return TW == 64 ? make_smem_desc(addr + t * 32, 16, 1024) : make_smem_desc_sw64(addr + t * 32, 16, 512);
+            };
+            auto issue_s = [&](int it) {
+                const int ls = it & 1, g = it & 1;
+                mbar_wait(load_full + ls, (uint32_t)(it >> 1) & 1u);
+                mbar_wait(acc_empty + g, ((uint32_t)(it >> 1) & 1u) ^ 1u);
+                tcgen05_fence_after();
+                const uint32_t st = smem_u32(s_load + ls * stage_bytes);
+                const uint32_t d_s = tmem_base + (uint32_t)(g * 256);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    tcgen05_mma_bf16(d_s, make_smem_desc(st + kk * 32, 16, 1024), make_smem_desc(st + k0_off + kk * 32, 16, 1024), idesc_s, kk > 0 ? 1u : 0u);
+#pragma unroll
+                for (int t = 0; t < TW / 16; ++t)
+                    tcgen05_mma_bf16(d_s, tail_desc_k(st + q1_off, t), tail_desc_k(st + k1_off, t), idesc_s, 1u);
+                tcgen05_commit(s_full + g);
+            };
+            auto issue_pv = [&](int it) {
+                const int ls = it & 1, g = it & 1;
+                mbar_wait(p_full + g, (uint32_t)(it >> 1) & 1u);
+                tcgen05_fence_after();
+                const uint32_t st = smem_u32(s_load + ls * stage_bytes);
+                const uint32_t d_o = tmem_base + (uint32_t)(g * 256);
+                for (int ks = 0; ks < nk16 / 16; ++ks) {
+                    const uint64_t p_desc = make_smem_desc(st + (ks >> 2) * kTileBytes + (ks & 3) * 32, 16, 1024);
+                    tcgen05_mma_bf16(d_o, p_desc, make_smem_desc(st + v0_off + ks * 2048, 8192, 1024), idesc_o0, ks > 0 ? 1u : 0u);
+                    // tail block of V: MN-major rows of kRowB bytes (16 keys = 16 rows)
+                    const uint64_t v1 = TW == 64 ? make_smem_desc(st + v1_off + ks * 2048, 8192, 1024) : make_smem_desc_sw64(st + v1_off + ks * 1024, 4096, 512);
+                    tcgen05_mma_bf16(d_o + 64u, p_desc, v1, idesc_o1, ks > 0 ? 1u : 0u);
+                }
+                tcgen05_commit(o_full + g);
+                tcgen05_commit(load_empty + ls);
+            };
+            if (my_items > 0) issue_s(0);
+            for (int it = 0; it < my_items; ++it) {
+                if (it + 1 < my_items) issue_s(it + 1);
+                issue_pv(it);
+            }
+        }
+    } else {
+        const int g = (warp - 2) / 4, quad = warp % 4, row = quad * 32 + lane, tid_g = (warp - 2) % 4 * 32 + lane;
+        float* mrow = s_mask + g * 256;
+        const uint32_t mrow_u32 = smem_u32(mrow);
+        const uint32_t p_row = smem_u32(s_load + g * stage_bytes) + (uint32_t)row * 128u, p_x = (uint32_t)(row & 7);   // stage g == group g
+        const uint32_t t_s = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * 256);
+        const float sc2 = a.scale * kLog2e;
+        const int nch = nk16 / 16;
+        auto mask_of = [&](int item, int key) -> float {
+            if (key >= Lk || item >= n_items) return -INFINITY;
+            const int bh = item / n_mt;
+            return a.mask.ptr ? __ldg(a.mask.ptr + (int64_t)(bh / H) * a.mask.sb + (int64_t)(bh % H) * a.mask.sh + key) : 0.0f;
+        };
+        const int first = blockIdx.x + g * gridDim.x;
+        float mv0 = mask_of(first, tid_g), mv1 = mask_of(first, tid_g + 128);
+        int u = 0;
+        for (int item = first; item < n_items; item += 2 * gridDim.x, ++u) {
+            const int mt = item % n_mt, bh = item / n_mt, b = bh / H, hd = bh % H;
+            const uint32_t par = (uint32_t)u & 1u;
+            named_bar_sync(1 + g, 128);
+            mrow[tid_g] = mv0 * kLog2e;
+            mrow[tid_g + 128] = mv1 * kLog2e;
+            mv0 = mask_of(item + 2 * gridDim.x, tid_g);
+            mv1 = mask_of(item + 2 * gridDim.x, tid_g + 128);
+            named_bar_sync(1 + g, 128);
+            mbar_wait(s_full + g, par);
+            tcgen05_fence_after();
+            auto scaled = [&](const uint32_t (&r)[16], int ch, float (&v)[16]) {
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    float m0, m1, m2, m3;
+                    lds128f(mrow_u32 + (uint32_t)(16 * ch + 4 * q4) * 4u, m0, m1, m2, m3);
+                    v[4 * q4] = fmaf(__uint_as_float(r[4 * q4]), sc2, m0);
+                    v[4 * q4 + 1] = fmaf(__uint_as_float(r[4 * q4 + 1]), sc2, m1);
+                    v[4 * q4 + 2] = fmaf(__uint_as_float(r[4 * q4 + 2]), sc2, m2);
+                    v[4 * q4 + 3] = fmaf(__uint_as_float(r[4 * q4 + 3]), sc2, m3);
+                }
+            };
+            uint32_t ra[16], rb[16];
+            float mx = -INFINITY;
+            tmem_ld_32x32b_x16(t_s, ra);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                if (c < nch) {
+                    tmem_ld_wait();
+                    if (c + 1 < nch) tmem_ld_32x32b_x16(t_s + (uint32_t)(16 * (c + 1)), (c & 1) ? ra : rb);
+                    float v[16];
+                    scaled((c & 1) ? rb : ra, c, v);
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) mx = fmaxf(fmaxf(mx, fmaxf(v[j], v[j + 1])), fmaxf(v[j + 2], v[j + 3]));
+                }
+            }
+            float l = 0.f;
+            const int qi = mt * 128 + row;
+            const bool live = qi < Lq;
+            tmem_ld_32x32b_x16(t_s, ra);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                if (c < nch) {
+                    tmem_ld_wait();
+                    if (c + 1 < nch) tmem_ld_32x32b_x16(t_s + (uint32_t)(16 * (c + 1)), (c & 1) ? ra : rb);
+                    float v[16];
+                    scaled((c & 1) ? rb : ra, c, v);
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float p0 = ex2_approx(v[2 * j] - mx), p1 = ex2_approx(v[2 * j + 1] - mx);
+                        l += p0 + p1;
+                        pk[j] = live ? pack_bf16x2(p0, p1) : 0u;
+                    }
+                    const uint32_t blk = p_row + (uint32_t)(c >> 2) * kTileBytes;
+                    sts128u(blk + ((((uint32_t)(2 * c) & 7u) ^ p_x) << 4), pk[0], pk[1], pk[2], pk[3]);
+                    sts128u(blk + ((((uint32_t)(2 * c + 1) & 7u) ^ p_x) << 4), pk[4], pk[5], pk[6], pk[7]);
+                }
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(p_full + g);
+            mbar_wait(o_full + g, par);
+            tcgen05_fence_after();
+            const float inv = 1.0f / l;
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.out) + ((int64_t)b * Lq + qi) * a.ldo + (int64_t)hd * D;
+#pragma unroll
+            for (int c32 = 0; c32 < D / 32; ++c32) {
+                uint32_t o[32];
+                tmem_ld_32x32b_x32(t_s + (uint32_t)(32 * c32), o);
+                tmem_ld_wait();
+                if (c32 == D / 32 - 1) {
+                    tcgen05_fence_before();
+                    mbar_arrive(acc_empty + g);
+                }
+                if (live) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint4 w;
+                        w.x = pack_bf16x2(__uint_as_float(o[8 * c]) * inv, __uint_as_float(o[8 * c + 1]) * inv);
+                        w.y = pack_bf16x2(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv);
+                        w.z = pack_bf16x2(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv);
+                        w.w = pack_bf16x2(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv);
+                        *reinterpret_cast<uint4*>(op + 32 * c32 + 8 * c) = w;
+                    }
+                }
+            }
+            if (live && a.lse) a.lse[((int64_t)b * H + hd) * Lq + qi] = fmaf(mx, kLn2, __logf(l));
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ backward
 // Per item (sample, head):   S = Q K^T,  dP = dO V^T                          (tcgen05, accumulators in TMEM)
 //   phase A, two threads per query row (alternate 16-key chunks; the element-wise chain is the critical path of an item):
@@ -560,6 +792,49 @@ int sdpa_fwd_tc5_bf16(const SdpaArgs& a, cudaStream_t st) {
     OVQA_LAUNCH_OK();
     return OVQA_OK;
 }
+
+// wide heads (d = 96 / 128) and rows longer than one tile: sdpa_fwd_tc5w_kernel
+static size_t tc5w_stage_bytes(int tw, int nk16) { const int rowb = tw == 64 ? 128 : 64; return (size_t)(128 + 2 * nk16) * (128 + rowb); }
+static size_t tc5w_smem_bytes(int tw, int nk16) { return 2 * tc5w_stage_bytes(tw, nk16) + 2 * 256 * 4 + 256 + 1024; }
+
+bool sdpa_fwd_tc5w_supported(const SdpaArgs& a) {
+    const int mode = tc5_mode("OVQA_SDPA_TC5");
+    if (mode == 0 || a.geo.boxes || a.att) return false;
+    if (a.dk != a.dv || !(a.dk == 96 || a.dk == 128) || a.Lq < 1 || a.Lk < 1 || a.Lk > 256) return false;
+    if (a.mask.ptr && a.mask.sq != 0) return false;
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (!al16(a.q) || !al16(a.k) || !al16(a.v) || !al16(a.out) || (a.ldq % 8) || (a.ldk % 8) || (a.ldv % 8) || (a.ldo % 8)) return false;
+    const int tw = (int)a.dk - 64, nk16 = (int)((a.Lk + 15) / 16 * 16), rowb = tw == 64 ? 128 : 64;
+    if (tc5w_smem_bytes(tw, nk16) > 227 * 1024) return false;
+    // P (nk16/64 blocks of 128 x 128 B) must fit into the stage's Q | K tiles it overwrites
+    if ((size_t)((nk16 + 63) / 64) * kTileBytes > (size_t)(128 + nk16) * (128 + rowb)) return false;
+    return mode == 1 || a.Lq > 48;
+}
+
+template <int TW>
+static int launch_tc5w(const SdpaArgs& a, cudaStream_t st) {
+    const int D = 64 + TW;
+    Tc5WideArgs args{a, (int)((a.Lk + 15) / 16 * 16), (int)(a.Lq < 128 ? a.Lq : 128), (int)((a.Lq + 127) / 128)};
+    CUtensorMap m[6];
+    const void* ptr[3] = {a.q, a.k, a.v};
+    const int64_t ld[3] = {a.ldq, a.ldk, a.ldv}, rows[3] = {a.B * a.Lq, a.B * a.Lk, a.B * a.Lk};
+    const uint32_t box_rows[3] = {(uint32_t)args.q_rows, (uint32_t)args.nk16, (uint32_t)args.nk16};
+    const uint64_t cols = (uint64_t)a.h * D;
+    for (int i = 0; i < 3; ++i) {
+        int rc;
+        if ((rc = make_tma_map_bf16(&m[2 * i], ptr[i], cols, (uint64_t)rows[i], (uint64_t)ld[i], 64, box_rows[i], 128))) return rc;
+        if ((rc = make_tma_map_bf16(&m[2 * i + 1], ptr[i], cols, (uint64_t)rows[i], (uint64_t)ld[i], TW, box_rows[i], TW == 64 ? 128 : 64))) return rc;
+    }
+    const int smem = (int)tc5w_smem_bytes(TW, args.nk16);
+    OVQA_CUDA_OK(cudaFuncSetAttribute(sdpa_fwd_tc5w_kernel<TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int64_t items = a.B * a.h * args.n_mt;
+    const int grid = (int)(items < sm_count() ? items : sm_count());
+    sdpa_fwd_tc5w_kernel<TW><<<grid, kWideThreads, smem, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], args);
+    OVQA_LAUNCH_OK();
+    return OVQA_OK;
+}
+
+int sdpa_fwd_tc5w_bf16(const SdpaArgs& a, cudaStream_t st) { return a.dk == 96 ? launch_tc5w<32>(a, st) : launch_tc5w<64>(a, st); }
 
 bool sdpa_bwd_tc5_supported(const SdpaArgs& a, const void* dout, const void* dq, const void* dk, const void* dv, int64_t lddo, int64_t lddq,
                             int64_t lddk, int64_t lddv) {

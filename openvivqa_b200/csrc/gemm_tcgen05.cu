@@ -600,14 +600,16 @@ EncodeFn get_encode() {
 }
 
 struct MapKey {
-    const void* ptr; uint64_t inner, outer, ld; uint32_t box_inner, box_outer;
-    bool operator==(const MapKey& o) const { return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner && box_outer == o.box_outer; }
+    const void* ptr; uint64_t inner, outer, ld; uint32_t box_inner, box_outer; int swz;
+    bool operator==(const MapKey& o) const {
+        return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner && box_outer == o.box_outer && swz == o.swz;
+    }
 };
 struct MapKeyHash {
     size_t operator()(const MapKey& k) const {
         size_t h = std::hash<const void*>()(k.ptr);
         auto mix = [&](uint64_t v) { h ^= std::hash<uint64_t>()(v) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
-        mix(k.inner); mix(k.outer); mix(k.ld); mix(((uint64_t)k.box_inner << 32) | k.box_outer);
+        mix(k.inner); mix(k.outer); mix(k.ld); mix(((uint64_t)k.box_inner << 32) | k.box_outer); mix((uint64_t)k.swz);
         return h;
     }
 };
@@ -615,10 +617,11 @@ struct MapKeyHash {
 }  // namespace
 
 // 2-D bf16 tensor [outer, inner] with row stride ld (elements); box [box_outer, box_inner]; SWIZZLE_128B; OOB -> 0.
-int tc5::make_tma_map_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer) {
+int tc5::make_tma_map_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer,
+                           int swizzle_bytes) {
     static std::mutex mu;
     static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-    const MapKey key{ptr, inner, outer, ld, box_inner, box_outer};
+    const MapKey key{ptr, inner, outer, ld, box_inner, box_outer, swizzle_bytes};
     {
         std::lock_guard<std::mutex> g(mu);
         auto it = cache.find(key);
@@ -631,7 +634,8 @@ int tc5::make_tma_map_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, ui
     const cuuint32_t box[2] = {box_inner, box_outer};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { g_last_cuda_error = (int)r; return OVQA_ERR_CUDA; }
     std::lock_guard<std::mutex> g(mu);
@@ -643,7 +647,7 @@ int tc5::make_tma_map_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, ui
 namespace {
 
 inline int make_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer) {
-    return tc5::make_tma_map_bf16(out, ptr, inner, outer, ld, box_inner, box_outer);
+    return tc5::make_tma_map_bf16(out, ptr, inner, outer, ld, box_inner, box_outer, 128);
 }
 
 template <int BN, bool A_MN, bool B_MN, int CTAS>

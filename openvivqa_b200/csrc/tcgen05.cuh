@@ -91,6 +91,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
            (1ull << 46) | (2ull << 61);
 }
+// SWIZZLE_64B variant (layout_type 4): 64-byte rows (32 bf16), 8-row groups 512 B apart — the 32-column tail block of a 96-wide head
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+           (1ull << 46) | (4ull << 61);
+}
 // UMMA instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=BF16 [7,10)=1, b=BF16 [10,13)=1,
 // a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29).
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn) {
@@ -142,7 +147,9 @@ __device__ __forceinline__ void tcgen05_mma_bf16_2sm(uint32_t d_tmem, uint64_t a
 
 // ----------------------------------------------------------------------------- host: TMA descriptors (gemm_tcgen05.cu)
 // 2-D bf16 tensor [outer, inner] with row stride ld (elements); box [box_outer, box_inner]; SWIZZLE_128B; OOB -> 0.  Cached.
-int make_tma_map_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer);
+// swizzle_bytes: 128 (default) or 64.
+int make_tma_map_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer,
+                      int swizzle_bytes = 128);
 
 }  // namespace tc5
 }  // namespace ovqa

@@ -181,6 +181,8 @@ class MMF_M4C(nn.Module):
         self.ocr_ptr_net = OcrPtrNet(config.OCR_PTR_NET.HIDDEN_SIZE, config.OCR_PTR_NET.QUERY_KEY_SIZE)
         self.classifier = nn.Linear(d, len(vocab))
         self.compute_dtype = getattr(config, "COMPUTE_DTYPE", None)
+        self.ocr_ptr_net.compute_dtype = self.compute_dtype          # the pointer network follows the model's compute dtype (it fell back
+                                                                     # to the global default: two fp32 CUDA-core GEMMs per decode step, 20 % of the decode)
         self.prune_last_layer = True
 
     # ------------------------------------------------------------------ step-invariant part (once per batch)
@@ -188,8 +190,14 @@ class MMF_M4C(nn.Module):
         return self.compute_dtype or get_compute_dtype()
 
     def _lin_ln(self, lin, ln, x, mode, post_add=None):
-        # small-K projections (bbox: K=4) are not TMA-able in bf16 (row pitch 8 B): keep those on the fp32 path
-        m = mode if x.shape[-1] % 8 == 0 else "fp32"
+        # bf16 operands need a 16-byte row pitch (TMA): the 4-wide box projections stay on the fp32 path, wider inputs whose
+        # width is not a multiple of 8 (OCR features: 256 + 256 + 300 = 812) are zero-padded to one (once per batch)
+        K = x.shape[-1]
+        if mode != "fp32" and K % 8 != 0 and K >= 64:
+            pad = 8 - K % 8
+            y = Fn.linear(F.pad(x, (0, pad)), F.pad(lin.weight, (0, pad)), lin.bias, mode)
+            return Fn.layer_norm(y, ln.weight, ln.bias, ln.eps, post_add=post_add)
+        m = mode if K % 8 == 0 else "fp32"
         y = Fn.linear(x, lin.weight, lin.bias, m)
         return Fn.layer_norm(y, ln.weight, ln.bias, ln.eps, post_add=post_add)
 

@@ -12,7 +12,9 @@ pytestmark = pytest.mark.gpu
 
 SHAPES = [  # (B, h, Lq, Lk)
     (256, 8, 100, 100), (64, 8, 128, 128), (130, 8, 100, 30), (300, 2, 30, 100), (77, 8, 30, 30), (9, 8, 1, 1), (5, 3, 17, 16), (5, 3, 16, 17),
-    (3, 8, 113, 127), (2, 1, 128, 1)]
+    (3, 8, 113, 127), (2, 1, 128, 1),
+    # wide heads / rows longer than one 128-row tile (sdpa_fwd_tc5w_kernel: M4C's 96-wide heads over 182 positions, 128-wide heads)
+    (128, 8, 182, 182, 96), (16, 8, 62, 182, 96), (5, 2, 100, 256, 96), (3, 4, 300, 200, 128), (2, 3, 17, 33, 128), (40, 8, 182, 182, 96)]
 
 
 def _ref(q, k, v, mask, h, d):
@@ -32,10 +34,10 @@ def _ref(q, k, v, mask, h, d):
 def test_tc5_core_forward_backward(shape, masked, monkeypatch):
     monkeypatch.setenv("OVQA_SDPA_TC5", "1")            # also the shapes the dispatcher would give to the warp-tile core
     monkeypatch.setenv("OVQA_SDPA_TC5_BWD", "1")
-    B, h, Lq, Lk = shape
+    B, h, Lq, Lk = shape[:4]
+    d = shape[4] if len(shape) > 4 else 64
     if masked and Lk == 1:
         pytest.skip("single fully-masked key: the exact gradients are 0 and only the -1e5 rounding noise of exp(s - lse) is left")
-    d = 64
     dev = torch.device("cuda:0")
     torch.backends.cuda.matmul.allow_tf32 = False
     g = torch.Generator(device="cpu").manual_seed(B * 1000 + Lq * 10 + Lk)
