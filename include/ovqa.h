@@ -111,6 +111,17 @@ int ovqa_sdpa_fwd(const void* q, const void* k, const void* v, void* out,
                   int64_t d_g, int geo_trig,
                   float scale, int dtype, float* lse, float* att, void* stream);
 
+/* Same core under M4C's prefix-LM mask (MMT.forward, mmf_m4c.py:310-343: (B,1,L,L) = per-key padding row repeated over the queries, with
+ * the last T x T block — the decoder steps — replaced by a causal pattern) WITHOUT materialising / reading the dense mask:
+ *   key_mask [B, Lk] additive fp32 row (batch stride key_mask_sb), causal_tail = T, causal_value = the additive value above the diagonal of
+ *   the tail block (queries Lq-T.., keys Lk-T..).  bf16, head dim 96 or 128, Lk <= 256 (the tensor-memory kernel); returns
+ *   OVQA_ERR_BAD_SHAPE for anything else: the caller then passes the dense mask to ovqa_sdpa_fwd. */
+int ovqa_sdpa_fwd_prefix_lm(const void* q, const void* k, const void* v, void* out,
+                            int64_t B, int64_t h, int64_t Lq, int64_t Lk, int64_t dk, int64_t dv,
+                            int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                            const float* key_mask, int64_t key_mask_sb, int64_t causal_tail, float causal_value,
+                            float scale, int dtype, float* lse, void* stream);
+
 /* Backward of the core (recomputes the probabilities from q,k,mask,lse):
  *   dq, dk, dv have the layouts of q, k, v (lddq/lddk/lddv).  `delta` [B,h,Lq] fp32 is caller-provided
  *   scratch (rowsum(dout*out)).  Geometry bias participates in the recomputation; its weight gradient

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(HERE, "libovqa_b200.so")
 F32, BF16 = 0, 1
 OP_N, OP_T = 0, 1
 EPI_GELU, EPI_DGELU, EPI_SAVE_DGELU, EPI_MUL_AUX = 1, 2, 4, 8
+ERR_BAD_SHAPE = -2
 
 _vp, _i64, _i32, _f32, _u64 = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_uint64
 
@@ -28,6 +29,8 @@ _PROTOS = {
     "ovqa_gemm": [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _f32, _f32, _vp, _i32,
                   _vp, _vp, _i64, _vp, _i64, _vp, _i64, _f32, _u64, _u64, _vp, _vp, _i32, _vp],
     "ovqa_gemm_bf16_simt": [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _f32, _vp, _i32, _vp],
+    "ovqa_sdpa_fwd_prefix_lm": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _f32, _f32, _i32,
+                                _vp, _vp],
     "ovqa_sdpa_fwd": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
                       _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _i32, _vp, _vp, _vp],
     "ovqa_sdpa_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64,

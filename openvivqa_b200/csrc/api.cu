@@ -119,6 +119,23 @@ extern "C" int ovqa_sdpa_fwd(const void* q, const void* k, const void* v, void* 
     return sdpa_fwd_simt_launch<__nv_bfloat16>(a, st);
 }
 
+// Attention core under M4C's prefix-LM mask (mmf_m4c.py:310-343: every query sees the unpadded keys; the last `causal_tail` positions —
+// the decoder steps — see each other causally) WITHOUT the dense (B,1,L,L) tensor: a per-key additive row + the tail length.  Tensor-memory
+// kernel only (bf16, d = 96 / 128, Lk <= 256); OVQA_ERR_BAD_SHAPE tells the caller to pass the dense mask to ovqa_sdpa_fwd instead.
+extern "C" int ovqa_sdpa_fwd_prefix_lm(const void* q, const void* k, const void* v, void* out, int64_t B, int64_t h, int64_t Lq, int64_t Lk,
+                                       int64_t dk, int64_t dv, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, const float* key_mask,
+                                       int64_t key_mask_sb, int64_t causal_tail, float causal_value, float scale, int dtype, float* lse,
+                                       void* stream) {
+    int rc = check_sdpa(q, k, v, B, h, Lq, Lk, dk, dv, nullptr, nullptr, nullptr, 0, 0, dtype);
+    if (rc) return rc;
+    if (!out || causal_tail < 0 || causal_tail > Lq || causal_tail > Lk) return OVQA_ERR_BAD_ARG;
+    if (B == 0 || Lq == 0) return OVQA_OK;
+    SdpaArgs a{q, k, v, out, B, h, Lq, Lk, dk, dv, ldq, ldk, ldv, ldo, {key_mask, key_mask_sb, 0, 0, causal_tail, causal_value},
+               {nullptr, nullptr, nullptr, nullptr, 0, 0}, scale, lse, nullptr};
+    if (dtype != OVQA_BF16 || !sdpa_fwd_tc5w_supported(a)) return OVQA_ERR_BAD_SHAPE;
+    return sdpa_fwd_tc5w_bf16(a, (cudaStream_t)stream);
+}
+
 extern "C" int ovqa_sdpa_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout, void* dq, void* dk,
                              void* dv, int64_t B, int64_t h, int64_t Lq, int64_t Lk, int64_t dk_, int64_t dv_, int64_t ldq,
                              int64_t ldk, int64_t ldv, int64_t ldo, int64_t lddo, int64_t lddq, int64_t lddk, int64_t lddv,

@@ -7,6 +7,10 @@ namespace ovqa {
 struct MaskArg {
     const float* ptr;
     int64_t sb, sh, sq;  // element strides over batch / head / query row (0 = broadcast); keys are unit stride
+    // prefix-LM structure (ovqa_sdpa_fwd_prefix_lm): on top of a per-key row, the last `causal_tail` queries x keys form a causal block
+    // whose entries above the diagonal get `causal_value` added
+    int64_t causal_tail;
+    float causal_value;
 };
 
 struct GeoArg {

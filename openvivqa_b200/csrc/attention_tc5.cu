@@ -380,6 +380,8 @@ sdpa_fwd_tc5w_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_co
         const uint32_t t_s = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * 256);
         const float sc2 = a.scale * kLog2e;
         const int nch = nk16 / 16;
+        const int ctail = (int)a.mask.causal_tail;
+        const float cval2 = a.mask.causal_value * kLog2e;
         auto mask_of = [&](int item, int key) -> float {
             if (key >= Lk || item >= n_items) return -INFINITY;
             const int bh = item / n_mt;
@@ -399,6 +401,9 @@ sdpa_fwd_tc5w_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_co
             named_bar_sync(1 + g, 128);
             mbar_wait(s_full + g, par);
             tcgen05_fence_after();
+            // prefix-LM tail: keys beyond `kmax` are in this query's causal future (kmax = INT_MAX for rows outside the tail)
+            const int qi_ = mt * 128 + row;
+            const int kmax = (ctail > 0 && qi_ >= Lq - ctail) ? (Lk - ctail) + (qi_ - (Lq - ctail)) : 0x7fffffff;
             auto scaled = [&](const uint32_t (&r)[16], int ch, float (&v)[16]) {
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) {
@@ -408,6 +413,10 @@ sdpa_fwd_tc5w_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_co
                     v[4 * q4 + 1] = fmaf(__uint_as_float(r[4 * q4 + 1]), sc2, m1);
                     v[4 * q4 + 2] = fmaf(__uint_as_float(r[4 * q4 + 2]), sc2, m2);
                     v[4 * q4 + 3] = fmaf(__uint_as_float(r[4 * q4 + 3]), sc2, m3);
+                }
+                if (16 * ch + 15 >= Lk - ctail && ctail > 0) {          // (warp-uniform) the chunk reaches into the causal block
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += (16 * ch + j > kmax) ? cval2 : 0.0f;
                 }
             };
             uint32_t ra[16], rb[16];
@@ -761,7 +770,7 @@ static int tc5_mode(const char* name) {
 }
 
 static bool tc5_shape_ok(const SdpaArgs& a) {
-    if (a.geo.boxes || a.att) return false;
+    if (a.geo.boxes || a.att || a.mask.causal_tail > 0) return false;
     if (a.dk != kD || a.dv != kD || a.Lq > 128 || a.Lk > 128 || a.Lq < 1 || a.Lk < 1) return false;
     if (a.mask.ptr && a.mask.sq != 0) return false;                           // per-key (padding) masks only
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };

@@ -32,6 +32,50 @@ __global__ void ptr_scores_kernel(const T* __restrict__ q, const T* __restrict__
     }
 }
 
+// Vector form for the decode step (bf16, d % 8 == 0, 16-byte aligned rows, T <= 16): one warp per KEY row (b, j).  The key row is read
+// once with 16-byte loads and stays in registers while the T query rows of the sample (L1/L2 resident) are dotted against it; the
+// scalar kernel above spent one warp and 2-byte loads on every (b, t, j) — 41 us for 128 x 12 x 50 scores of 768 elements.
+constexpr int kPtrMaxT = 16;
+__global__ void __launch_bounds__(256) ptr_scores_vec_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+                                                             const void* __restrict__ mask, float* __restrict__ scores, int64_t B, int Tn,
+                                                             int64_t L, int d, int64_t ldq, int64_t ldk, int64_t ld_scores, int64_t col_offset,
+                                                             float scale, int mask_is_bool) {
+    const int64_t w = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
+    if (w >= B * L) return;
+    const int64_t j = w % L, b = w / L;
+    const uint4* kr = reinterpret_cast<const uint4*>(k + (b * L + j) * ldk);
+    const int nv = d / 8;                                     // 16-byte vectors per row; lane owns vectors lane, lane + 32, ...
+    float acc[kPtrMaxT];
+#pragma unroll
+    for (int t = 0; t < kPtrMaxT; ++t) acc[t] = 0.f;
+    for (int c = lane; c < nv; c += 32) {
+        const uint4 kv = __ldg(kr + c);
+        const float2 k0 = unpack_bf16x2(kv.x), k1 = unpack_bf16x2(kv.y), k2 = unpack_bf16x2(kv.z), k3 = unpack_bf16x2(kv.w);
+#pragma unroll
+        for (int t = 0; t < kPtrMaxT; ++t) {
+            if (t < Tn) {
+                const uint4 qv = __ldg(reinterpret_cast<const uint4*>(q + (b * Tn + t) * ldq) + c);
+                const float2 q0 = unpack_bf16x2(qv.x), q1 = unpack_bf16x2(qv.y), q2 = unpack_bf16x2(qv.z), q3 = unpack_bf16x2(qv.w);
+                acc[t] += (q0.x * k0.x + q0.y * k0.y) + (q1.x * k1.x + q1.y * k1.y) + (q2.x * k2.x + q2.y * k2.y) + (q3.x * k3.x + q3.y * k3.y);
+            }
+        }
+    }
+    float add = 0.f;
+    bool kill = false;
+    if (mask) {
+        if (mask_is_bool) kill = reinterpret_cast<const uint8_t*>(mask)[b * L + j] != 0;
+        else add = reinterpret_cast<const float*>(mask)[b * L + j];
+    }
+#pragma unroll
+    for (int t = 0; t < kPtrMaxT; ++t) {
+        if (t < Tn) {
+            const float s = warp_sum(acc[t]);
+            if (lane == 0) scores[(b * Tn + t) * ld_scores + col_offset + j] = kill ? -INFINITY : s * scale + add;
+        }
+    }
+}
+
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
 // LayerNorm of a register-resident row (float4 per lane), fp32 two-pass
@@ -141,6 +185,12 @@ extern "C" int ovqa_ptr_scores(const void* q, const void* k, const void* mask, f
     if (warps == 0) return OVQA_OK;
     const unsigned grid = (unsigned)((warps + 7) / 8);
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == OVQA_BF16 && T <= kPtrMaxT && d % 8 == 0 && ldq % 8 == 0 && ldk % 8 == 0 && ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k)) & 15) == 0) {
+        ptr_scores_vec_kernel<<<(unsigned)((B * L + 7) / 8), 256, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, mask, scores, B, (int)T, L,
+                                                                          (int)d, ldq, ldk, ld_scores, col_offset, scale, mask_is_bool);
+        OVQA_LAUNCH_OK();
+        return OVQA_OK;
+    }
     if (dtype == OVQA_F32) ptr_scores_kernel<float><<<grid, 256, 0, st>>>((const float*)q, (const float*)k, mask, scores, B, T, L, d, ldq, ldk, ld_scores, col_offset, scale, mask_is_bool);
     else if (dtype == OVQA_BF16) ptr_scores_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, mask, scores, B, T, L, d, ldq, ldk, ld_scores, col_offset, scale, mask_is_bool);
     else return OVQA_ERR_BAD_ARG;

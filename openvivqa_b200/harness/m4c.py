@@ -31,7 +31,7 @@ from torch import nn
 from .. import functional as Fn
 from .. import ops
 from ..modules import OcrPtrNet, get_compute_dtype
-from .models import generate_padding_mask, generate_sequential_mask
+from .models import MASK_VALUE, generate_padding_mask, generate_sequential_mask
 
 
 class _BertSelf(nn.Module):
@@ -81,6 +81,9 @@ class BertLayer(nn.Module):
         if q_rows is not None:
             xq = x[:, q_rows].contiguous()
             mq = mask[:, :, q_rows] if (mask is not None and mask.shape[2] > 1) else mask
+            hint = getattr(mask, "_ovqa_prefix_lm", None)
+            if hint is not None and mq is not mask and q_rows.stop in (None, mask.shape[2]) and mq.shape[2] >= hint[1]:
+                mq._ovqa_prefix_lm = hint                     # the row slice still ends with the causal tail
         att = Fn.mha_block(xq, x, x, mq, wq=s.query.weight, bq=s.query.bias, wk=s.key.weight, bk=s.key.bias,
                            wv=s.value.weight, bv=s.value.bias, wo=a.output.dense.weight, bo=a.output.dense.bias,
                            gamma=a.output.LayerNorm.weight, beta=a.output.LayerNorm.bias, h=self.heads, d_k=self.d_head,
@@ -225,7 +228,11 @@ class MMF_M4C(nn.Module):
         L = am.shape[-1]
         ext = am.repeat(1, 1, L, 1)
         ext[:, :, -T:, -T:] = generate_sequential_mask(T, dev)
-        return ext.contiguous()
+        ext = ext.contiguous()
+        # structure hint for the attention core: the dense tensor is a per-key row plus a causal T x T tail, which the
+        # tensor-memory kernel evaluates without reading (B, L, L) floats per launch (ops.sdpa_fwd; dense mask otherwise)
+        ext._ovqa_prefix_lm = (am.contiguous(), T, float(MASK_VALUE))
+        return ext
 
     # ------------------------------------------------------------------ decode
     class State:

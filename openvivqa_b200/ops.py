@@ -162,9 +162,20 @@ def sdpa_fwd(q, k, v, *, h: int, d_k: int, d_v: int, mask=None, geo: Optional[Ge
         out = torch.empty((B, Lq, h * d_v), device=q.device, dtype=q.dtype)
     lse = torch.empty((B, h, Lq), device=q.device, dtype=torch.float32) if need_lse else None
     att = torch.empty((B, h, Lq, Lk), device=q.device, dtype=torch.float32) if need_att else None
-    mask, sb, sh, sq = _mask_strides(mask, B, h, Lq, Lk)
     if scale is None:
         scale = 1.0 / math.sqrt(d_k)
+    # prefix-LM structure hint (harness.m4c.mmt_mask): per-key row + causal tail instead of the dense (B,1,L,L) tensor
+    hint = getattr(mask, "_ovqa_prefix_lm", None)
+    if hint is not None and q.dtype == torch.bfloat16 and geo is None and not need_att:
+        key_row, tail, value = hint
+        rc = L.lib().ovqa_sdpa_fwd_prefix_lm(_p(q), _p(k), _p(v), _p(out), B, h, Lq, Lk, d_k, d_v, q.stride(1), k.stride(1), v.stride(1),
+                                             out.stride(1), _p(key_row), key_row.stride(0) if key_row.shape[0] > 1 else 0, int(tail),
+                                             float(value), float(scale), _DT[q.dtype], _p(lse), _stream())
+        if rc == 0:
+            return out, lse, att
+        if rc != L.ERR_BAD_SHAPE:
+            L.check(rc, "ovqa_sdpa_fwd_prefix_lm")                 # (BAD_SHAPE: this shape has no structured kernel -> dense mask below)
+    mask, sb, sh, sq = _mask_strides(mask, B, h, Lq, Lk)
     g = geo
     L.call("ovqa_sdpa_fwd", _p(q), _p(k), _p(v), _p(out), B, h, Lq, Lk, d_k, d_v,
            q.stride(1), k.stride(1), v.stride(1), out.stride(1), _p(mask), sb, sh, sq,

@@ -82,3 +82,33 @@ def test_tc5_core_forward_backward(shape, masked, monkeypatch):
         # reference's own softmax carries the same noise; it only shows where the exact gradient is ~0 (Lk == 1)
         floor = 0.5 * dout.float().abs().max().item() if masked else 1e-3
         assert err <= 3e-2 * max(want.abs().max().item(), floor), f"{name}: {err:.3e} vs scale {want.abs().max().item():.3e}"
+
+
+@pytest.mark.parametrize("Lq_rows", [None, 62])
+def test_prefix_lm_mask_structured_vs_dense(Lq_rows):
+    """M4C's (B,1,L,L) mask (mmf_m4c.py:310-343) given as per-key row + causal tail (ovqa_sdpa_fwd_prefix_lm) against the dense tensor
+    through the generic entry point, both against an fp32 torch reference; also the row-pruned last layer (queries = the last 62 rows)."""
+    from openvivqa_b200.harness.m4c import MMF_M4C
+    dev = torch.device("cuda:0")
+    B, h, L, T, d = 9, 8, 182, 12, 96
+    g = torch.Generator().manual_seed(3)
+    valid = [torch.randint(5, n + 1, (B,), generator=g) for n in (20, 100, 50)]
+    pads = [((torch.arange(n)[None, :] >= v[:, None]).float() * -10e4).view(B, 1, 1, n).to(dev) for n, v in zip((20, 100, 50), valid)]
+    dense = MMF_M4C.mmt_mask(pads[0], pads[1], pads[2], T)
+    assert getattr(dense, "_ovqa_prefix_lm", None) is not None and dense.shape == (B, 1, L, L)
+    x = torch.randn((B, L, 3 * h * d), generator=g).to(dev).bfloat16()
+    q, k, v = x[..., :h * d], x[..., h * d:2 * h * d], x[..., 2 * h * d:]
+    mask = dense
+    if Lq_rows is not None:
+        q = q[:, -Lq_rows:].contiguous()
+        mask = dense[:, :, -Lq_rows:]
+        mask._ovqa_prefix_lm = dense._ovqa_prefix_lm
+    ref, _ = _ref(q.float(), k.float(), v.float(), mask, h, d)
+    out_s, lse_s, _ = ops.sdpa_fwd(q, k, v, h=h, d_k=d, d_v=d, mask=mask, need_lse=True)                 # structured (hint attached)
+    plain = mask.clone()                                                                                  # same values, no hint -> dense path
+    out_d, lse_d, _ = ops.sdpa_fwd(q, k, v, h=h, d_k=d, d_v=d, mask=plain, need_lse=True)
+    torch.cuda.synchronize()
+    scale = max(1.0, ref.abs().max().item())
+    assert (out_s.float() - ref).abs().max().item() <= 2e-2 * scale
+    assert (out_d.float() - ref).abs().max().item() <= 2e-2 * scale
+    assert (lse_s - lse_d).abs().max().item() <= 2e-2
