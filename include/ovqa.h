@@ -165,6 +165,12 @@ int ovqa_layernorm_bwd(const float* dy, const float* x, const float* mean, const
  * Element-wise helpers of the path.
  * ------------------------------------------------------------------------------------------------- */
 /* y(bf16) = x(fp32), n elements — staging of GEMM operands (weights once per optimiser step). */
+/* FeatureEmbedding front-end (vision_embeddings.py:19-25, models/utils.py:44-57): one pass over fp32 features [rows, K]
+ * (row pitch ldx) writes the contiguous bf16 GEMM operand y [rows, K] and the padding mask[rows] (mask_value where the row sums to 0, else 0;
+ * NULL to skip).  K % 8 == 0. */
+int ovqa_cast_rows_padmask(const float* x, void* y_bf16, float* mask, int64_t rows, int64_t K, int64_t ldx, float mask_value, void* stream);
+/* y_bf16[i] = a[i] * b[i]   (a fp32, b fp32 or bf16): gradient of a fused activation from its saved derivative */
+int ovqa_mul_to_bf16(const float* a, const void* b, int b_dtype, void* y_bf16, int64_t n, void* stream);
 int ovqa_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream);
 int ovqa_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream);
 /* out[n] (+)= sum_m x[m, n]  — bias gradients.  x dtype f32/bf16, out fp32, accumulate!=0 adds. */

@@ -2,12 +2,13 @@
 
 Public surface:
   * modules:   ScaledDotProductAttention, AugmentedGeometryScaledDotProductAttention, MultiHeadAttention,
-               PositionWiseFeedForward, OcrPtrNet, DynamicPointerNetwork, META_ATTENTION, build_attention
+               PositionWiseFeedForward, OcrPtrNet, DynamicPointerNetwork, FeatureEmbedding (vision front-end), META_ATTENTION,
+               build_attention
   * install(): patch a reference checkout's registry / imported symbols so every model and YAML picks them up
   * ops / functional: the C-ABI wrappers and autograd blocks
 The CUDA library (openvivqa_b200/libovqa_b200.so) is required; there is no CPU or PyTorch fallback.
 """
-from .modules import (AugmentedGeometryScaledDotProductAttention, DynamicPointerNetwork, META_ATTENTION,  # noqa: F401
+from .modules import (AugmentedGeometryScaledDotProductAttention, DynamicPointerNetwork, FeatureEmbedding, META_ATTENTION,  # noqa: F401
                       MultiHeadAttention, OcrPtrNet, PositionWiseFeedForward, ScaledDotProductAttention,
                       StatefulModule, build_attention, get_compute_dtype, set_compute_dtype)
 from .install import install, uninstall  # noqa: F401

@@ -29,6 +29,8 @@ _PROTOS = {
     "ovqa_gemm": [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _f32, _f32, _vp, _i32,
                   _vp, _vp, _i64, _vp, _i64, _vp, _i64, _f32, _u64, _u64, _vp, _vp, _i32, _vp],
     "ovqa_gemm_bf16_simt": [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _f32, _vp, _i32, _vp],
+    "ovqa_cast_rows_padmask": [_vp, _vp, _vp, _i64, _i64, _i64, _f32, _vp],
+    "ovqa_mul_to_bf16": [_vp, _vp, _i32, _vp, _i64, _vp],
     "ovqa_sdpa_fwd_prefix_lm": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _f32, _f32, _i32,
                                 _vp, _vp],
     "ovqa_sdpa_fwd": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64,

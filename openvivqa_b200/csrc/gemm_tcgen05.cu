@@ -711,6 +711,8 @@ int launch(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, int64_t m, i
         else if (kFwd && feat == (F_BIAS | F_DROP | F_RES)) OVQA_GO(float, EPI_FULL, (kFwd ? F_BIAS | F_DROP | F_RES : F_RUNTIME));     // fc_o / fc2, training
         else if (kFwd && feat == (F_BIAS | F_RES)) OVQA_GO(float, EPI_FULL, (kFwd ? F_BIAS | F_RES : F_RUNTIME));                       // fc_o / fc2, eval
         else if (kDgrad && feat == F_RES) OVQA_GO(float, EPI_FULL, (kDgrad ? F_RES : F_RUNTIME));                                       // dx = dy W + other branch's gradient
+        else if (kFwd && feat == (F_BIAS | F_GELU | F_SAVE_D | F_DROP)) OVQA_GO(float, EPI_FULL, (kFwd ? F_BIAS | F_GELU | F_SAVE_D | F_DROP : F_RUNTIME));   // FeatureEmbedding, training
+        else if (kFwd && feat == (F_BIAS | F_GELU)) OVQA_GO(float, EPI_FULL, (kFwd ? F_BIAS | F_GELU : F_RUNTIME));                                           // FeatureEmbedding, eval
         else OVQA_GO(float, EPI_FULL, F_RUNTIME);
     } else {
         if (mode == EPI_PLAIN) OVQA_GO(__nv_bfloat16, EPI_PLAIN, F_RUNTIME);

@@ -290,6 +290,45 @@ __global__ void dropout_mask_kernel(float* out, int64_t n, float p, uint64_t see
 }
 __global__ void advance_u64_kernel(uint64_t* word, uint64_t delta) { *word += delta; }
 
+// FeatureEmbedding front-end (vision_embeddings.py:19-25 + models/utils.py:44-57): ONE pass over the fp32 region features writes the
+// bf16 GEMM operand AND the padding mask (a row whose features sum to 0 is padding: additive mask_value there, 0 elsewhere).  Warp per row,
+// 16-byte loads; the reference reads the features twice (torch.sum for the mask, then the Linear) plus a cast under autocast.
+__global__ void __launch_bounds__(256) cast_rows_padmask_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, float* __restrict__ mask,
+                                                                int64_t rows, int64_t K, int64_t ldx, float mask_value) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
+    if (row >= rows) return;
+    const float* xr = x + row * ldx;
+    __nv_bfloat16* yr = y + row * K;
+    float s = 0.f;
+    const int64_t nv = K / 8;                                    // 8 elements per lane and iteration: two 16-byte loads, one 16-byte store
+    for (int64_t c = lane; c < nv; c += 32) {
+        const float4 a = ld4(xr + 8 * c), b = ld4(xr + 8 * c + 4);
+        s += ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
+        *reinterpret_cast<uint4*>(yr + 8 * c) = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+    }
+    for (int64_t c = nv * 8 + lane; c < K; c += 32) { const float v = xr[c]; s += v; yr[c] = __float2bfloat16_rn(v); }
+    s = warp_sum(s);
+    if (lane == 0 && mask) mask[row] = s == 0.0f ? mask_value : 0.0f;
+}
+
+// out_bf16 = a (fp32) * b (fp32 | bf16): the gradient of a fused activation from its saved derivative
+template <typename TB>
+__global__ void mul_to_bf16_kernel(const float* __restrict__ a, const TB* __restrict__ b, __nv_bfloat16* __restrict__ y, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+        if (i + 4 <= n) {
+            const float4 av = ld4(a + i);
+            float b0, b1, b2, b3;
+            if constexpr (sizeof(TB) == 4) { const float4 bv = ld4(reinterpret_cast<const float*>(b) + i); b0 = bv.x; b1 = bv.y; b2 = bv.z; b3 = bv.w; }
+            else { const uint2 u = *reinterpret_cast<const uint2*>(b + i); const float2 p0 = unpack_bf16x2(u.x), p1 = unpack_bf16x2(u.y); b0 = p0.x; b1 = p0.y; b2 = p1.x; b3 = p1.y; }
+            *reinterpret_cast<uint2*>(y + i) = make_uint2(pack_bf16x2(av.x * b0, av.y * b1), pack_bf16x2(av.z * b2, av.w * b3));
+        } else {
+            for (int64_t j = i; j < n; ++j) y[j] = __float2bfloat16_rn(a[j] * to_f32<TB>(b[j]));
+        }
+    }
+}
+
 // many (src fp32 -> dst fp32|bf16) contiguous copies in one launch: blockIdx.y = descriptor, blockIdx.x strides over it
 __global__ void stage_many_kernel(const ovqa_stage_desc* __restrict__ descs) {
     const ovqa_stage_desc d = descs[blockIdx.y];
@@ -454,6 +493,25 @@ extern "C" int ovqa_dropout_mask(float* out, int64_t n, float p, uint64_t seed, 
     if (!out || n < 0) return OVQA_ERR_BAD_ARG;
     if (n == 0) return OVQA_OK;
     dropout_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, n, p, seed, offset, offset_base);
+    OVQA_LAUNCH_OK();
+    return OVQA_OK;
+}
+
+extern "C" int ovqa_cast_rows_padmask(const float* x, void* y_bf16, float* mask, int64_t rows, int64_t K, int64_t ldx, float mask_value, void* stream) {
+    if (!x || !y_bf16 || rows < 0 || K <= 0 || ldx < K) return OVQA_ERR_BAD_ARG;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y_bf16) & 15) || (ldx % 4) || (K % 8)) return OVQA_ERR_ALIGNMENT;
+    if (rows == 0) return OVQA_OK;
+    cast_rows_padmask_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y_bf16, mask, rows, K, ldx, mask_value);
+    OVQA_LAUNCH_OK();
+    return OVQA_OK;
+}
+extern "C" int ovqa_mul_to_bf16(const float* a, const void* b, int b_dtype, void* y_bf16, int64_t n, void* stream) {
+    if (!a || !b || !y_bf16 || n < 0) return OVQA_ERR_BAD_ARG;
+    if ((reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15) || (reinterpret_cast<uintptr_t>(y_bf16) & 7)) return OVQA_ERR_ALIGNMENT;
+    if (n == 0) return OVQA_OK;
+    if (b_dtype == OVQA_F32) mul_to_bf16_kernel<float><<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(a, (const float*)b, (__nv_bfloat16*)y_bf16, n);
+    else if (b_dtype == OVQA_BF16) mul_to_bf16_kernel<__nv_bfloat16><<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(a, (const __nv_bfloat16*)b, (__nv_bfloat16*)y_bf16, n);
+    else return OVQA_ERR_BAD_ARG;
     OVQA_LAUNCH_OK();
     return OVQA_OK;
 }

@@ -442,6 +442,47 @@ def pwff_block(x, *, w1, b1, w2, b2, gamma, beta, mode="fp32", dropout=0.0, trai
     return y
 
 
+# ----------------------------------------------------------------------------- FeatureEmbedding front-end
+class _FeatureEmbeddingFn(torch.autograd.Function):
+    """``dropout(gelu(x W^T + b))`` and the zero-row padding mask of ``x`` (vision_embeddings.py:19-25), bf16 path: one pass over the fp32
+    features (bf16 operand + mask), one GEMM with the whole activation fused (its saved derivative makes backward one multiply)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, cfg):
+        ctx.set_materialize_grads(False)
+        p = cfg["dropout"] if cfg["training"] else 0.0
+        K, D = x.shape[-1], w.shape[0]
+        x16, mask = ops.cast_rows_padmask(x.reshape(-1, K), cfg["mask_value"])
+        need_grad = cfg["grad"] and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
+        aux = torch.empty((x16.shape[0], D), device=x.device, dtype=torch.float32) if need_grad else None
+        seed, off = dropout_stream.next(x16.shape[0] * D) if p > 0.0 else (0, 0)
+        y = ops.gemm(x16, weights.get([w], torch.bfloat16), bias=weights.get([b], torch.float32), out_dtype=torch.float32, gelu=True,
+                     aux_out=aux, save_dgelu=need_grad, dropout_p=p, seed=seed, offset=off,
+                     offset_base=dropout_stream.base(x.device) if p > 0.0 else None)
+        if need_grad:
+            ctx.save_for_backward(x16, aux)
+        ctx.mark_non_differentiable(mask)
+        return y.view(*x.shape[:-1], D), mask.view(x.shape[0], 1, 1, -1) if x.dim() == 3 else mask
+
+    @staticmethod
+    def backward(ctx, dy, _dmask):
+        if dy is None:
+            return None, None, None, None
+        x16, aux = ctx.saved_tensors
+        D = aux.shape[1]
+        dpre = ops.mul_to_bf16(dy.reshape(-1, D).float(), aux)             # grad of the pre-activation: dy * GELU'(pre) * dropout scale
+        dw, db = _zero_slab(dy.device, (D, x16.shape[1]), (D,))
+        _wgrad(dpre, x16, out=dw)
+        ops.colsum(dpre, out=db, accumulate=True)
+        return None, dw, db, None
+
+
+def feature_embedding(features, w, b, *, dropout=0.0, training=False, mask_value=-10e4):
+    """(B, N, K) fp32 region features -> ((B, N, D) fp32, (B,1,1,N) additive padding mask); bf16 tensor-core path only."""
+    cfg = dict(grad=torch.is_grad_enabled(), dropout=float(dropout), training=bool(training), mask_value=float(mask_value))
+    return _FeatureEmbeddingFn.apply(features, w, b, cfg)
+
+
 # ----------------------------------------------------------------------------- stand-alone pieces (direct core calls)
 class _SdpaFn(torch.autograd.Function):
     @staticmethod

@@ -33,9 +33,12 @@ def attention_cfg(d_model=512, head=8, d_key=None, d_value=None, d_ff=2048, drop
     return c
 
 
-def _embeddings(d_model, d_feature, dropout):
+def _embeddings(d_model, d_feature, dropout, compute_dtype=None):
+    vis = NS(ARCHITECTURE="FeatureEmbedding", D_FEATURE=d_feature, D_MODEL=d_model, DROPOUT=dropout)
+    if compute_dtype is not None:
+        vis.COMPUTE_DTYPE = compute_dtype
     return dict(
-        VISION_EMBEDDING=NS(ARCHITECTURE="FeatureEmbedding", D_FEATURE=d_feature, D_MODEL=d_model, DROPOUT=dropout),
+        VISION_EMBEDDING=vis,
         TEXT_EMBEDDING=NS(ARCHITECTURE="LSTMTextEmbedding", D_MODEL=d_model, D_EMBEDDING=300, DROPOUT=dropout,
                           WORD_EMBEDDING=None, WORD_EMBEDDING_CACHE=None),
         VISION_ATTR_REDUCE=NS(D_MODEL=d_model, DROPOUT=dropout), TEXT_ATTR_REDUCE=NS(D_MODEL=d_model, DROPOUT=dropout))
@@ -47,7 +50,7 @@ def mcan_cfg(d_model=512, d_feature=2048, layers=6, head=8, d_ff=2048, dropout=0
               SELF_ENCODER=NS(ARCHITECTURE="Encoder", D_MODEL=d_model, LAYERS=layers, SELF_ATTENTION=att()),
               GUIDED_ENCODER=NS(ARCHITECTURE="GuidedAttentionEncoder", D_MODEL=d_model, LAYERS=layers,
                                 SELF_ATTENTION=att(), GUIDED_ATTENTION=att()),
-              **_embeddings(d_model, d_feature, dropout))
+              **_embeddings(d_model, d_feature, dropout, compute_dtype))
 
 
 def xmt_cfg(kind="cross", d_model=512, d_feature=2048, layers=2, head=8, d_ff=2048, dropout=0.1, geometry=False,
@@ -61,7 +64,7 @@ def xmt_cfg(kind="cross", d_model=512, d_feature=2048, layers=2, head=8, d_ff=20
              VISION_SELF_ATTENTION=att("AugmentedGeometryScaledDotProductAttention" if geometry else "ScaledDotProductAttention"),
              LANGUAGE_SELF_ATTENTION=att())
     return NS(ARCHITECTURE="CrossModalityTransformer", NAME="xmt", DEVICE="cuda", D_MODEL=d_model, ENCODER=enc,
-              USE_BOXES=geometry, **_embeddings(d_model, d_feature, dropout))
+              USE_BOXES=geometry, **_embeddings(d_model, d_feature, dropout, compute_dtype))
 
 
 def m4c_cfg(hidden=768, heads=8, mmt_layers=4, text_layers=3, d_obj=1024, d_ocr=812, ptr_qk=None, compute_dtype=None):

@@ -193,18 +193,7 @@ def build_encoder(config):
     return ENCODERS[config.ARCHITECTURE](config)
 
 
-class FeatureEmbedding(nn.Module):
-    """vision_embeddings.py:10-25."""
-
-    def __init__(self, config):
-        super().__init__()
-        self.proj = nn.Linear(config.D_FEATURE, config.D_MODEL)
-        self.gelu = nn.GELU()
-        self.dropout = nn.Dropout(config.DROPOUT)
-
-    def forward(self, features):
-        masks = generate_padding_mask(features, padding_idx=0)
-        return self.dropout(self.gelu(self.proj(features))), masks
+from ..modules import FeatureEmbedding      # noqa: E402  vision_embeddings.py:10-25 — the drop-in (bf16: fused cast + mask + GEMM epilogue)
 
 
 class LSTMTextEmbedding(nn.Module):

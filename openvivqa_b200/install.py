@@ -47,6 +47,13 @@ def install(compute_dtype: str | None = None, verbose: bool = False):
     classes = {"MultiHeadAttention": mha, "PositionWiseFeedForward": M.PositionWiseFeedForward, "OcrPtrNet": M.OcrPtrNet,
                "ScaledDotProductAttention": M.ScaledDotProductAttention,
                "AugmentedGeometryScaledDotProductAttention": M.AugmentedGeometryScaledDotProductAttention}
+    # vision front-end: registered in META_VISION_EMBEDDING (vision_embeddings.py:10)
+    vis_builder = _maybe("builders.vision_embedding_builder")
+    if vis_builder is not None:
+        vreg = vis_builder.META_VISION_EMBEDDING
+        _saved.setdefault(("vision_registry", "FeatureEmbedding"), vreg._obj_map.get("FeatureEmbedding"))
+        vreg._obj_map["FeatureEmbedding"] = M.FeatureEmbedding
+        classes["FeatureEmbedding"] = M.FeatureEmbedding
     for name, mods in _REBIND.items():
         for modname in mods:
             mod = _maybe(modname)
@@ -61,7 +68,13 @@ def install(compute_dtype: str | None = None, verbose: bool = False):
 def uninstall():
     """Undo :func:`install` (used by the tests that compare with/without the drop-ins in one process)."""
     for (where, name), obj in list(_saved.items()):
-        if where == "registry":
+        if where == "vision_registry":
+            vreg = sys.modules["builders.vision_embedding_builder"].META_VISION_EMBEDDING
+            if obj is None:
+                vreg._obj_map.pop(name, None)
+            else:
+                vreg._obj_map[name] = obj
+        elif where == "registry":
             reg = sys.modules["builders.attention_builder"].META_ATTENTION
             if obj is None:
                 reg._obj_map.pop(name, None)

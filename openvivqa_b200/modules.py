@@ -40,6 +40,9 @@ def get_compute_dtype() -> str:
     return _default_mode
 
 
+MASK_VALUE = -10e4          # models/utils.py:56
+
+
 def _mode_of(module) -> str:
     return module.compute_dtype or _default_mode
 
@@ -305,6 +308,30 @@ class PositionWiseFeedForward(nn.Module):
         return Fn.pwff_block(input, w1=self.fc1.weight, b1=self.fc1.bias, w2=self.fc2.weight, b2=self.fc2.bias,
                              gamma=self.layer_norm.weight, beta=self.layer_norm.bias, mode=_mode_of(self),
                              dropout=self.dropout_1.p, training=self.training, eps=self.layer_norm.eps)
+
+
+class FeatureEmbedding(nn.Module):
+    """vision_embeddings.py:10-25 (``META_VISION_EMBEDDING``): ``dropout(gelu(proj(features)))`` and the padding mask
+    of the all-zero region rows (models/utils.py:44-57).  Same parameter names (``proj.weight`` / ``proj.bias``) and config keys
+    (``D_FEATURE``, ``D_MODEL``, ``DROPOUT``).  bf16 mode: one pass over the fp32 features (bf16 operand + mask) and one tensor-core GEMM
+    with bias + GELU + dropout fused; fp32 mode (the 1e-4 parity path): the library's fp32 GEMM, then the reference's own element-wise ops."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.proj = nn.Linear(config.D_FEATURE, config.D_MODEL)
+        self.gelu = nn.GELU()
+        self.dropout = nn.Dropout(config.DROPOUT)
+        self.compute_dtype = getattr(config, "COMPUTE_DTYPE", None)
+
+    def forward(self, features):
+        mode = _mode_of(self)
+        if mode == "bf16" and features.dim() == 3 and features.dtype == torch.float32 and features.shape[-1] % 8 == 0:
+            return Fn.feature_embedding(features, self.proj.weight, self.proj.bias, dropout=self.dropout.p, training=self.training,
+                                        mask_value=MASK_VALUE)
+        masks = (torch.sum(features, dim=-1) == 0).long() * MASK_VALUE
+        masks = masks.unsqueeze(1).unsqueeze(1).to(features.dtype)
+        y = Fn.linear(features, self.proj.weight, self.proj.bias, "fp32")
+        return self.dropout(self.gelu(y)), masks
 
 
 class OcrPtrNet(nn.Module):

@@ -263,6 +263,29 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, *, dx_add=None, want_bf16: bool = Fa
     return out + (dbias,) if want_dbias else out
 
 
+def cast_rows_padmask(x: torch.Tensor, mask_value: float):
+    """fp32 (rows, K) -> (bf16 copy (rows, K), additive padding mask (rows,) fp32: ``mask_value`` where the row sums to 0) in one pass."""
+    _need_cuda(x)
+    x = _rowmajor2d(x, "x")
+    if x.dtype != torch.float32 or x.shape[1] % 8 != 0:
+        raise ValueError("cast_rows_padmask: x must be fp32 with a width that is a multiple of 8")
+    y = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    mask = torch.empty((x.shape[0],), device=x.device, dtype=torch.float32)
+    L.call("ovqa_cast_rows_padmask", _p(x), _p(y), _p(mask), x.shape[0], x.shape[1], _ld(x), float(mask_value), _stream())
+    return y, mask
+
+
+def mul_to_bf16(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """bf16(a * b), a fp32, b fp32 or bf16 (same shape, contiguous)."""
+    _need_cuda(a, b)
+    a, b = a.contiguous(), b.contiguous()
+    if a.dtype != torch.float32 or b.dtype not in _DT or a.shape != b.shape:
+        raise ValueError("mul_to_bf16: a fp32, b fp32/bf16, equal shapes")
+    y = torch.empty(a.shape, device=a.device, dtype=torch.bfloat16)
+    L.call("ovqa_mul_to_bf16", _p(a), _p(b), _DT[b.dtype], _p(y), a.numel(), _stream())
+    return y
+
+
 def to_bf16(x: torch.Tensor) -> torch.Tensor:
     _need_cuda(x)
     if x.dtype == torch.bfloat16:

@@ -336,6 +336,36 @@ def test_pwff_gradients(dev, mode):
     grad_check([(n, p.grad) for n, p in m.named_parameters()], gp, tol)
 
 
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_feature_embedding_front_end(dev, mode):
+    """FeatureEmbedding (vision_embeddings.py:10-25) against the restated oracle: output, padding mask of the all-zero
+    rows, gradients of proj.weight / proj.bias; and the fused dropout of the bf16 path."""
+    B, N, K, D = 5, 37, 256, 128
+    feats = S.padded_features(B, N, K, 41, min_valid=5, relu_like=True)
+    params = {"proj.weight": torch.randn((D, K), generator=S._gen(7, "fw")) * 0.05, "proj.bias": torch.randn((D,), generator=S._gen(7, "fb")) * 0.1}
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    ref, ref_mask = R.feature_embedding(p, feats)
+    w = torch.randn(ref.shape, generator=torch.Generator().manual_seed(5))
+    (ref * w).sum().backward()
+    m = ovqa.FeatureEmbedding(H.NS(D_FEATURE=K, D_MODEL=D, DROPOUT=0.0, COMPUTE_DTYPE=mode))
+    m.load_state_dict(params)
+    m = m.to(dev).train()
+    y, mask = m(feats.to(dev))
+    assert mask.shape == ref_mask.shape and torch.equal(mask.cpu(), ref_mask.to(mask.dtype))
+    check(y, ref, mode, "FeatureEmbedding")
+    (y * w.to(dev)).sum().backward()
+    tol = 2e-4 if mode == "fp32" else 4e-2
+    grad_check([(n, q.grad) for n, q in m.named_parameters()], {k: v.grad for k, v in p.items()}, tol)
+    if mode == "bf16":                                   # fused dropout: zero pattern with the right rate, kept values scaled by 1 / (1 - p)
+        m.dropout.p = 0.25
+        yd, _ = m(feats.to(dev))
+        live = y.detach().abs() > 1e-3
+        kept = (yd.detach() != 0) & live
+        frac = kept.sum().item() / live.sum().item()
+        assert 0.70 < frac < 0.80, frac
+        assert (yd.detach()[kept] - y.detach()[kept] / 0.75).abs().max().item() <= 2e-2 * y.detach().abs().max().item()
+
+
 def test_geometry_gradients(dev):
     D, h = 128, 4
     B, N = 2, 13
