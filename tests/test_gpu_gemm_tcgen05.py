@@ -198,12 +198,14 @@ def test_tanhfit_gelu_matches_erf_gelu(dev):
 
 
 @pytest.mark.parametrize("a_op,b_op", [("N", "N"), ("N", "T"), ("T", "T"), ("T", "N")])
-@pytest.mark.parametrize("m,n,k", [(40000, 512, 512), (20008, 768, 256), (38000 + 77, 256, 1024), (40000, 2048, 512)])
+@pytest.mark.parametrize("m,n,k", [(40000, 512, 512), (20008, 768, 256), (38000 + 77, 256, 1024), (40000, 2048, 512), (30000, 1100, 128)])
 def test_cta_pair_matches_single_cta(dev, monkeypatch, a_op, b_op, m, n, k):
     """cta_group::2 (a CTA pair per 256-row tile, B split across the pair) against the single-CTA kernel: same K order, so
     the results must be bit-identical, ragged last pair tiles included."""
     if a_op == "T":
         m = (m + 7) // 8 * 8
+    if b_op == "T":
+        n = (n + 7) // 8 * 8       # TMA: the contiguous dimension's pitch must be a multiple of 16 bytes
     a, b, ref = _mk(m, n, k, a_op, b_op, dev)
     bias = torch.randn(n, device=dev)
     res = torch.randn((m, n), device=dev)

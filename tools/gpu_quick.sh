@@ -2,5 +2,6 @@
 # quick GPU iteration: full GPU suite + MCAN bench (no CPU baseline)
 mkdir -p gpurun_out; : > gpurun_out/summary.txt
 timeout 1500 python -m pytest tests -q -m gpu --timeout 300 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/summary.txt
+timeout 600 python -c "import __graft_entry__ as g; g.build(); g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/summary.txt; tail -3 gpurun_out/smoke.log
 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/summary.txt
 cat gpurun_out/summary.txt; tail -15 gpurun_out/pytest_gpu.log | cut -c1-250; cut -c1-300 gpurun_out/bench.log; tail -5 gpurun_out/bench.err

@@ -140,8 +140,24 @@ def bench_ln():
              bwd_us=t_b, bwd_gbs=y_b / t_b / 1e3, bwd_frac_hbm=y_b / t_b / 1e3 / PEAKS["hbm_gbs"])
 
 
+def _torch_mha(q, kv, mask, w, h):
+    """The reference block's arithmetic in plain PyTorch ops (attentions.py:46-60, 319-339, eval): what the unmodified module launches."""
+    import torch.nn.functional as F
+    B, Lq, D = q.shape
+    Lk, d = kv.shape[1], D // h
+    Q = F.linear(q, w["q"][0], w["q"][1]).view(B, Lq, h, d).permute(0, 2, 1, 3)
+    K = F.linear(kv, w["k"][0], w["k"][1]).view(B, Lk, h, d).permute(0, 2, 3, 1)
+    V = F.linear(kv, w["v"][0], w["v"][1]).view(B, Lk, h, d).permute(0, 2, 1, 3)
+    att = torch.matmul(Q, K) / math.sqrt(d)
+    att = torch.softmax(att + mask, dim=-1)
+    out = torch.matmul(att, V).permute(0, 2, 1, 3).contiguous().view(B, Lq, D)
+    out = F.linear(out, w["o"][0], w["o"][1])
+    return F.layer_norm(q + out, (D,), w["ln"][0], w["ln"][1])
+
+
 def bench_mha():
-    """BASELINE configs[4]: fused MHA block, eval, k=v!=q, padding mask with 20% trailing keys masked."""
+    """BASELINE configs[4]: fused MHA block, eval, k=v!=q, padding mask with 20% trailing keys masked; next to the same block in plain
+    PyTorch ops on the same GPU (fp32 eager = the reference as shipped, and bf16 autocast)."""
     ovqa.set_compute_dtype("bf16")
     for D, dk in [(512, 64), (768, 96)]:
         m = ovqa.MultiHeadAttention(H.attention_cfg(D, 8, dk, dk, dropout=0.0, compute_dtype="bf16")).to(dev).eval()
@@ -154,13 +170,22 @@ def bench_mha():
                 kv = torch.randn((B, Lk, D), device=dev)
                 mask = torch.zeros((B, 1, 1, Lk), device=dev)
                 mask[:, :, :, int(Lk * 0.8):] = -10e4
+                a = m.attention
+                w = {"q": (a.fc_q.weight, a.fc_q.bias), "k": (a.fc_k.weight, a.fc_k.bias), "v": (a.fc_v.weight, a.fc_v.bias),
+                     "o": (a.fc_o.weight, a.fc_o.bias), "ln": (m.layer_norm.weight, m.layer_norm.bias)}
                 with torch.no_grad():
                     t = timeit(lambda: m(q, kv, kv, mask), iters=10, warmup=2)
+                    t32 = t16 = None
+                    if B * Lk * 8 * Lq * 4 < 3e9:        # the reference materialises (B, h, Lq, Lk) fp32 three times
+                        t32 = timeit(lambda: _torch_mha(q, kv, mask, w, 8), iters=5, warmup=1)
+                        with torch.autocast("cuda", dtype=torch.bfloat16):
+                            t16 = timeit(lambda: _torch_mha(q, kv, mask, w, 8), iters=5, warmup=1)
                 F_mha = 4.0 * D * D * (Lq + Lk) + 4.0 * Lq * Lk * D
                 Y_mha = 4 * D * (Lq + Lk + Lq) + 4 * Lk            # fp32 activations in/out as the module sees them
                 t_roof = max(B * F_mha / (PEAKS["bf16_tflops"] * 1e12), B * Y_mha / (PEAKS["hbm_gbs"] * 1e9)) * 1e6
                 emit(kind="mha_block", D=D, B=B, Lq=Lq, Lk=Lk, us=t, samples_per_s=B / t * 1e6, tflops=B * F_mha / t / 1e6,
-                     roofline_us=t_roof, frac_of_roofline=t_roof / t)
+                     roofline_us=t_roof, frac_of_roofline=t_roof / t, torch_fp32_us=t32, torch_bf16_autocast_us=t16,
+                     speedup_vs_torch_fp32=(t32 / t if t32 else None), speedup_vs_torch_bf16=(t16 / t if t16 else None))
     ovqa.set_compute_dtype("fp32")
 
 
