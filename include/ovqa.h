@@ -234,6 +234,40 @@ int ovqa_greedy_step(const float* scores, int64_t* prev_inds, int64_t* last_ids,
                      int32_t* all_eos, int64_t B, int64_t T, int64_t W, int64_t step, int64_t eos_idx,
                      void* stream);
 
+/* -------------------------------------------------------------------------------------------------
+ * Incremental decoding: ONE MultiHeadAttention block of a decode step over a cache of PROJECTED keys / values.
+ *   replaces: MultiHeadAttention.forward inside `statefulness()` (attentions.py:319-331 with :321-325's torch.cat of the raw
+ *             running_keys / running_values and the full re-projection at :48-50), as driven by Decoder / DecoderLayer
+ *             (decoders.py:21-26, :53-71) from BeamSearch.iter (beam_search.py:41-58).  Eval mode (dropout off).
+ *   x_f32   [B*Lq, D] fp32: the block input (query rows AND residual).   x_op: the same rows in the compute dtype (bf16), or NULL (cast here).
+ *   self_attention != 0: keys / values are the query rows (Lnew == Lq): one GEMM over the fused weight.
+ *   self_attention == 0: kv_src_op [B*Lnew, D] (compute dtype) are the rows to append, or NULL with Lnew == 0 (attend over the cache as is:
+ *                        encoder attention, whose keys were projected once).
+ *   w_qkv [(2*h*dk + h*dv), D] = [Wq; Wk; Wv] row-major in the compute dtype, b_qkv fp32 [2*h*dk + h*dv];  w_o [D, h*dv], b_o [D].
+ *   kv_cache [B, cap, h*dk + h*dv] compute dtype: row (b, j) = [K_j | V_j]; `len` positions are valid on entry; the call files the Lnew new
+ *            rows at positions len .. len+Lnew-1 (the caller then advances len) and attends over all len+Lnew positions.
+ *   mask: additive fp32, element (b, head, lq, j) at b*mask_sb + head*mask_sh + lq*mask_sq + j, j < len+Lnew; NULL = none.
+ *   y_f32 [B*Lq, D] = LayerNorm(x + fc_o(attention));  y_op: optional second copy in bf16 (bf16 mode only).
+ *   workspace: >= ovqa_mha_decode_workspace_bytes(...) bytes, 16-byte aligned, caller-owned; launches: (cast) + 1-2 GEMM + attention + GEMM + LN.
+ * ------------------------------------------------------------------------------------------------- */
+int64_t ovqa_mha_decode_workspace_bytes(int64_t B, int64_t Lq, int64_t Lnew, int64_t D, int64_t h, int64_t dk, int64_t dv, int dtype);
+int ovqa_mha_decode_step(const float* x_f32, const void* x_op, const void* kv_src_op, int self_attention,
+                         int64_t B, int64_t Lq, int64_t Lnew, int64_t D, int64_t h, int64_t dk, int64_t dv,
+                         const void* w_qkv, const float* b_qkv, const void* w_o, const float* b_o,
+                         const float* gamma, const float* beta, float eps,
+                         void* kv_cache, int64_t cap, int64_t len,
+                         const float* mask, int64_t mask_sb, int64_t mask_sh, int64_t mask_sq,
+                         float scale, int dtype, void* workspace, int64_t workspace_bytes,
+                         float* y_f32, void* y_op, void* stream);
+
+/* PositionWiseFeedForward in eval mode from one call (positionwise_feed_forward.py:23-27, dropout off):
+ *   y = LayerNorm(x + fc2(gelu(fc1 x)));  x_f32 [rows, D], x_op as above;  w1 [d_ff, D], w2 [D, d_ff] compute dtype; biases fp32. */
+int64_t ovqa_pwff_infer_workspace_bytes(int64_t rows, int64_t D, int64_t d_ff, int dtype);
+int ovqa_pwff_infer(const float* x_f32, const void* x_op, int64_t rows, int64_t D, int64_t d_ff,
+                    const void* w1, const float* b1, const void* w2, const float* b2,
+                    const float* gamma, const float* beta, float eps, int dtype,
+                    void* workspace, int64_t workspace_bytes, float* y_f32, void* y_op, void* stream);
+
 /* Verification twin of ovqa_gemm's bf16 path on CUDA cores (same operand forms, bias/GELU epilogue): lets the
  * GPU tests cross-check the tcgen05 kernel on device.  Not on the product path. */
 int ovqa_gemm_bf16_simt(const void* A, const void* B, void* C, int64_t m, int64_t n, int64_t k,

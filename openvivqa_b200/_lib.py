@@ -30,6 +30,11 @@ _PROTOS = {
                   _vp, _vp, _i64, _vp, _i64, _vp, _i64, _f32, _u64, _u64, _vp, _vp, _i32, _vp],
     "ovqa_gemm_bf16_simt": [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _f32, _vp, _i32, _vp],
     "ovqa_cast_rows_padmask": [_vp, _vp, _vp, _i64, _i64, _i64, _f32, _vp],
+    "ovqa_mha_decode_step": [_vp, _vp, _vp, _i32, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _i64, _i64,
+                             _vp, _i64, _i64, _i64, _f32, _i32, _vp, _i64, _vp, _vp, _vp],
+    "ovqa_mha_decode_workspace_bytes": [_i64] * 7 + [_i32],
+    "ovqa_pwff_infer_workspace_bytes": [_i64, _i64, _i64, _i32],
+    "ovqa_pwff_infer": [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i32, _vp, _i64, _vp, _vp, _vp],
     "ovqa_mul_to_bf16": [_vp, _vp, _i32, _vp, _i64, _vp],
     "ovqa_sdpa_fwd_prefix_lm": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _f32, _f32, _i32,
                                 _vp, _vp],
@@ -53,7 +58,8 @@ _PROTOS = {
     "ovqa_greedy_step": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp],
     "ovqa_dropout_mask": [_vp, _i64, _f32, _u64, _u64, _vp, _vp],
 }
-_RESTYPES = {"ovqa_error_string": C.c_char_p, "ovqa_launch_count": C.c_uint64}
+_RESTYPES = {"ovqa_error_string": C.c_char_p, "ovqa_launch_count": C.c_uint64, "ovqa_mha_decode_workspace_bytes": C.c_int64,
+             "ovqa_pwff_infer_workspace_bytes": C.c_int64}
 
 _lib = None
 _lock = threading.Lock()

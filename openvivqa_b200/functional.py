@@ -347,7 +347,7 @@ class _MHAFn(torch.autograd.Function):
                      geo_db=gdb, scale=cfg["scale"])
         dkeys = dvalues = None
         if self_att:
-            d2 = dqkv.view(B * Lq, -1)
+            d2 = dqkv.view(B * Lq, dqkv.shape[-1])
             dW = _wgrad(d2, xq, out=dWs[0])
             ops.colsum(d2[:, :hk], out=dbq, accumulate=True)
             dwq, dwk, dwv = dW[:hk], dW[hk:2 * hk], dW[2 * hk:]
@@ -358,7 +358,7 @@ class _MHAFn(torch.autograd.Function):
             ops.colsum(dq2, out=dbq, accumulate=True)
             dqueries = ops.gemm(dq2, weights.get([wq], cdt), b_op="T", out_dtype=torch.float32, residual=ds.view(B * Lq, D)).view(B, Lq, D)
             if kv_same:
-                d2 = dkvb.view(B * Lk, -1)
+                d2 = dkvb.view(B * Lk, dkvb.shape[-1])
                 dW = _wgrad(d2, xk, out=dWs[1])
                 dwk, dwv = dW[:hk], dW[hk:]
                 dkeys = ops.gemm(d2, weights.get([wk, wv], cdt), b_op="T", out_dtype=torch.float32).view(B, Lk, D)
@@ -376,6 +376,91 @@ def mha_block(queries, keys, values, mask, *, wq, bq, wk, bk, wv, bv, wo, bo, ga
                geo_trig=bool(geo_trig), scale=(1.0 / math.sqrt(d_k)) if scale is None else float(scale))
     y, y16 = _MHAFn.apply(queries, keys, values, mask, boxes, wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta, geo_w, geo_b, cfg)
     _attach_shadow(y, y16 if mode == "bf16" else None)
+    return y
+
+
+# ----------------------------------------------------------------------------- incremental decode (projected K/V cache)
+def project_kv_fused(keys, values, *, wk, bk, wv, bv, mode="fp32"):
+    """[K | V] = [fc_k(keys) | fc_v(values)] as one (B, L, h*d_k + h*d_v) buffer in the compute dtype (the layout of the decode cache)."""
+    cdt = _cdt(mode)
+    B, Lk = keys.shape[0], keys.shape[1]
+    hk, hv = wk.shape[0], wv.shape[0]
+    fb = lambda *bs: weights.get(list(bs), torch.float32)
+    with torch.no_grad():
+        xk = _operand(keys, mode)
+        if values is keys:
+            return ops.gemm(xk, weights.get([wk, wv], cdt), bias=fb(bk, bv), out_dtype=cdt).view(B, Lk, hk + hv)
+        kv = torch.empty((B * Lk, hk + hv), device=keys.device, dtype=cdt)
+        ops.gemm(xk, weights.get([wk], cdt), bias=fb(bk), out=kv[:, :hk])
+        ops.gemm(_operand(values, mode), weights.get([wv], cdt), bias=fb(bv), out=kv[:, hk:])
+        return kv.view(B, Lk, hk + hv)
+
+
+def _f32c(x):
+    return x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous()
+
+
+def _shadow_of(x, mode):
+    sh = getattr(x, "_ovqa_bf16", None) if mode == "bf16" else None
+    return sh[1] if (sh is not None and sh[0] == x._version and sh[1].shape == x.shape and sh[1].is_contiguous()) else None
+
+
+class InferPlan:
+    """Staged operands of one block resolved ONCE (fused / bf16 weight copies, fp32 biases, LayerNorm affine) and their device
+    pointers, so a decode step does no cache lookups: at beam-search batch sizes the step is bounded by host dispatch, not by the GPU.
+    ``valid()`` re-checks the parameters' version counters / storage and the optimiser-step epoch (a handful of attribute reads)."""
+    __slots__ = ("params", "stamp", "keep", "ptrs", "dt", "mode")
+
+    def __init__(self, mode, groups, affine):
+        """``groups``: list of (parameter list, "w" | "b") -> one staged operand each (weights in the compute dtype, biases fp32);
+        ``affine``: (gamma, beta) passed as they are."""
+        cdt = _cdt(mode)
+        self.mode, self.dt = mode, (0 if mode == "fp32" else 1)
+        self.params = [p for g, _ in groups for p in g] + list(affine)
+        self.keep = [weights.get(list(g), cdt if kind == "w" else torch.float32) for g, kind in groups] + [a.detach() for a in affine]
+        for t in self.keep:
+            if not t.is_contiguous():
+                raise ValueError("InferPlan: staged operands must be contiguous")
+        self.ptrs = tuple(t.data_ptr() for t in self.keep)
+        self.stamp = self._stamp()
+
+    def _stamp(self):
+        return (weights.epoch,) + tuple((p._version, p.data_ptr()) for p in self.params)
+
+    def valid(self):
+        return self.stamp == self._stamp()
+
+
+def mha_decode_plan(*, wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta, mode="fp32") -> InferPlan:
+    return InferPlan(mode, [((wq, wk, wv), "w"), ((bq, bk, bv), "b"), ((wo,), "w"), ((bo,), "b")], (gamma, beta))
+
+
+def pwff_plan(*, w1, b1, w2, b2, gamma, beta, mode="fp32") -> InferPlan:
+    return InferPlan(mode, [((w1,), "w"), ((b1,), "b"), ((w2,), "w"), ((b2,), "b")], (gamma, beta))
+
+
+def mha_decode_block(plan: InferPlan, queries, kv_src, self_attention, kv_cache, length, mask, *, h, d_k, d_v, eps=1e-5, scale=None):
+    """Inference-only MHA block of a decode step over the projected-K/V cache (ONE library call, see csrc/decode.cu): fc_q (fused with
+    fc_k / fc_v of the new rows) -> attention over cache + new rows (which it files into the cache) -> fc_o + residual -> LayerNorm.
+    Same arithmetic as ``mha_block`` in eval mode (attentions.py:319-331); no autograd graph.  ``kv_src``: (B, Lnew, D) rows to append
+    (None: none), ignored when ``self_attention`` (the query rows are appended)."""
+    mode = plan.mode
+    x = _f32c(queries)
+    src = None
+    if kv_src is not None and not self_attention:
+        src = _operand(kv_src, mode).view(kv_src.shape)
+    y, y16 = ops.mha_decode_step(x, _shadow_of(queries, mode), src, self_attention, plan.ptrs, dt=plan.dt, eps=eps, h=h, d_k=d_k, d_v=d_v,
+                                 kv_cache=kv_cache, length=length, mask=mask, scale=(1.0 / math.sqrt(d_k)) if scale is None else scale)
+    if y16 is not None:
+        y._ovqa_bf16 = (y._version, y16)
+    return y
+
+
+def pwff_infer_block(plan: InferPlan, x, *, d_ff, eps=1e-5):
+    """Inference-only feed-forward block from ONE library call (positionwise_feed_forward.py:23-27 with dropout off)."""
+    y, y16 = ops.pwff_infer(_f32c(x), _shadow_of(x, plan.mode), plan.ptrs, dt=plan.dt, d_ff=d_ff, eps=eps)
+    if y16 is not None:
+        y._ovqa_bf16 = (y._version, y16)
     return y
 
 

@@ -19,7 +19,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .. import functional as Fn
-from ..modules import MultiHeadAttention, PositionWiseFeedForward
+from ..modules import MultiHeadAttention, PositionWiseFeedForward, StatefulModule
 
 MASK_VALUE = -10e4
 
@@ -187,6 +187,22 @@ class CrossModalityEncoder(nn.Module):
 
 ENCODERS = {"Encoder": Encoder, "GuidedAttentionEncoder": GuidedAttentionEncoder,
             "CoAttentionEncoder": CoAttentionEncoder, "CrossModalityEncoder": CrossModalityEncoder}
+
+
+class DecoderLayer(StatefulModule):
+    """decoders.py:13-26 (call pattern only): stateful self-attention -> encoder attention -> feed-forward.  Derives from the
+    stateful container so ``statefulness(batch)`` / ``apply_to_states(fn)`` reach both attention blocks (containers.py:19-31)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.self_attn = MultiHeadAttention(config.SELF_ATTENTION)
+        self.enc_attn = MultiHeadAttention(config.ENC_ATTENTION)
+        self.pwff = PositionWiseFeedForward(config.ENC_ATTENTION)
+
+    def forward(self, queries, keys, values, self_attention_mask, enc_attention_mask, **kwargs):
+        self_att = self.self_attn(queries, queries, queries, attention_mask=self_attention_mask, **kwargs)
+        enc_att = self.enc_attn(self_att, keys, values, attention_mask=enc_attention_mask, **kwargs)
+        return self.pwff(enc_att)
 
 
 def build_encoder(config):

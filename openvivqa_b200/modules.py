@@ -41,6 +41,7 @@ def get_compute_dtype() -> str:
 
 
 MASK_VALUE = -10e4          # models/utils.py:56
+DECODE_KV_CACHE = True      # inference-time stateful decode keeps projected keys / values (False: the reference's bookkeeping, for A/B timing)
 
 
 def _mode_of(module) -> str:
@@ -250,7 +251,77 @@ def make_multi_head_attention(base=StatefulModule, builder=None):
             if self.can_be_stateful:
                 self.register_state("running_keys", torch.zeros((0, d_model)))
                 self.register_state("running_values", torch.zeros((0, d_model)))
+                if isinstance(self.attention, ScaledDotProductAttention):
+                    # decode-time cache of the PROJECTED keys / values, (B, capacity, h*d_k + h*d_v) with ``_kv_len`` valid positions
+                    # (inference fast path below).  Registered as a state so that beam search re-gathers it with the rest
+                    # (beam_search.py:19-33), but kept out of the state_dict: the reference's checkpoints do not have it.
+                    core = self.attention
+                    self.register_state("running_kv_proj", torch.zeros((0, core.h * (core.d_k + core.d_v))))
+                    self._non_persistent_buffers_set.add("running_kv_proj")
+            self._kv_len = 0
+            self._enc_kv = None          # (tag, [K|V], keys, values): encoder keys / values projected once per stateful session
+            self._session = None         # per-session decode plan: None = not decided yet, False = reference bookkeeping
             self.compute_dtype = getattr(config, "COMPUTE_DTYPE", None)
+
+        def enable_statefulness(self, batch_size):
+            super().enable_statefulness(batch_size)
+            self._kv_len, self._enc_kv, self._session = 0, None, None
+
+        def disable_statefulness(self):
+            super().disable_statefulness()
+            self._kv_len, self._enc_kv, self._session = 0, None, None
+
+        def _open_session(self, core):
+            self._session = self._open_decode_session(core)
+            return self._session is not False
+
+        def _open_decode_session(self, core):
+            """Decide once per ``statefulness()`` session whether the inference fast path applies, and resolve its operands."""
+            ok = (DECODE_KV_CACHE and type(core) is ScaledDotProductAttention and (not self.training or self.dropout.p == 0.0)
+                  and (not self.can_be_stateful or self.running_keys.shape[1] == 0))
+            if not ok:
+                return False
+            mode = self.compute_dtype or core.compute_dtype or get_compute_dtype()
+            kv = dict(wk=core.fc_k.weight, bk=core.fc_k.bias, wv=core.fc_v.weight, bv=core.fc_v.bias, mode=mode)
+            plan = Fn.mha_decode_plan(wq=core.fc_q.weight, bq=core.fc_q.bias, wo=core.fc_o.weight, bo=core.fc_o.bias,
+                                      gamma=self.layer_norm.weight, beta=self.layer_norm.bias, **kv)
+            return dict(plan=plan, kv=kv, mode=mode, h=core.h, d_k=core.d_k, d_v=core.d_v, eps=float(self.layer_norm.eps),
+                        stateful=bool(self.can_be_stateful), cdt=torch.float32 if mode == "fp32" else torch.bfloat16)
+
+        def _decode_fast_path(self, sess, queries, keys, values, attention_mask):
+            """Inference-time incremental decoding.  The reference re-projects the WHOLE running key / value
+            sequence at every step (attentions.py:321-325 then :48-50) and re-projects the unchanged encoder output in every
+            cross-attention call; here only the new rows go through fc_k / fc_v and the projected rows are kept — in a buffer with spare
+            capacity, so nothing is concatenated either — and the whole block is enqueued by one library call (csrc/decode.cu).  A T-step
+            decode does O(T) instead of O(T^2) projection work.  Same outputs: fc_k / fc_v act row by row."""
+            kv_src, self_att = None, False
+            if sess["stateful"]:
+                need = self._kv_len + keys.shape[1]
+                cache = self._buffers["running_kv_proj"]
+                if cache.shape[1] < need or cache.dtype != sess["cdt"]:              # grow geometrically: amortised O(1) copies per step
+                    grown = torch.empty((queries.shape[0], max(32, 2 * need), cache.shape[2]), device=queries.device, dtype=sess["cdt"])
+                    if self._kv_len:
+                        grown[:, :self._kv_len] = cache[:, :self._kv_len]
+                    self._buffers["running_kv_proj"] = cache = grown
+                elif not cache.is_contiguous():
+                    self._buffers["running_kv_proj"] = cache = cache.contiguous()
+                self_att = keys is queries and values is queries
+                length = self._kv_len
+                if not self_att:
+                    if values is keys:
+                        kv_src = keys
+                    else:                                                            # distinct key / value sources: project, then file
+                        cache[:, length:need] = Fn.project_kv_fused(keys, values, **sess["kv"])
+                        length = need
+                self._kv_len = need
+            else:
+                tag = (keys.data_ptr(), keys._version, keys.shape, values.data_ptr(), values._version)
+                enc = self._enc_kv
+                if enc is None or enc[0] != tag:
+                    self._enc_kv = enc = (tag, Fn.project_kv_fused(keys, values, **sess["kv"]), keys, values)   # (tensors held: the tag stays unique)
+                cache, length = enc[1], keys.shape[1]
+            return Fn.mha_decode_block(sess["plan"], queries, kv_src, self_att, cache, length, attention_mask, h=sess["h"], d_k=sess["d_k"],
+                                       d_v=sess["d_v"], eps=sess["eps"])
 
         def forward(self, queries, keys, values, attention_mask, **kwargs):
             core = self.attention
@@ -258,8 +329,13 @@ def make_multi_head_attention(base=StatefulModule, builder=None):
                 # a core we do not accelerate (memory / adaptive variants): reference composition, their own math
                 out, _ = core(queries, keys, values, attention_mask, **kwargs)
                 out = self.layer_norm(queries + self.dropout(out))
+            elif self._is_stateful and self._session is not False and not torch.is_grad_enabled() and (
+                    self._session is not None or self._open_session(core)):
+                out = self._decode_fast_path(self._session, queries, keys, values, attention_mask)
             else:
                 if self.can_be_stateful and self._is_stateful:
+                    if self._kv_len != 0:
+                        raise RuntimeError("MultiHeadAttention: a stateful decode may not switch between no_grad and grad mode half-way")
                     self.running_keys = torch.cat([self.running_keys, keys], 1)
                     keys = self.running_keys
                     self.running_values = torch.cat([self.running_values, values], 1)
@@ -305,6 +381,13 @@ class PositionWiseFeedForward(nn.Module):
         self.compute_dtype = getattr(config, "COMPUTE_DTYPE", None)
 
     def forward(self, input):
+        if not torch.is_grad_enabled() and not self.training:                  # inference: the block from one library call
+            plan = self.__dict__.get("_plan")
+            if plan is None or not plan[0].valid() or plan[0].mode != _mode_of(self):
+                plan = (Fn.pwff_plan(w1=self.fc1.weight, b1=self.fc1.bias, w2=self.fc2.weight, b2=self.fc2.bias, gamma=self.layer_norm.weight,
+                                     beta=self.layer_norm.bias, mode=_mode_of(self)), self.fc1.weight.shape[0], float(self.layer_norm.eps))
+                self.__dict__["_plan"] = plan
+            return Fn.pwff_infer_block(plan[0], input, d_ff=plan[1], eps=plan[2])
         return Fn.pwff_block(input, w1=self.fc1.weight, b1=self.fc1.bias, w2=self.fc2.weight, b2=self.fc2.bias,
                              gamma=self.layer_norm.weight, beta=self.layer_norm.bias, mode=_mode_of(self),
                              dropout=self.dropout_1.p, training=self.training, eps=self.layer_norm.eps)

@@ -90,6 +90,12 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_op: str = "N", b_op: str = "N", 
     flags = (L.EPI_GELU if gelu else 0) | ((L.EPI_MUL_AUX if mul_aux is not None else L.EPI_DGELU) if dgelu_aux is not None else 0) | \
         (L.EPI_SAVE_DGELU if save_dgelu else 0)
     aux = dgelu_aux if dgelu_aux is not None else aux_out
+    if m == 0 or n == 0:                     # empty batch: nothing to launch (an empty tensor has no device pointer to validate)
+        return out
+    if k == 0 and flags == 0 and residual is None and c2 is None and colsum is None:
+        # empty reduction (a weight gradient over zero rows): the product is exactly zero
+        out.zero_() if beta == 0.0 else out.mul_(beta)
+        return out if bias is None else out.add_(bias.to(out.dtype))
     L.call("ovqa_gemm", _p(a), _p(b), _p(out), m, n, k, _ld(a), _ld(b), _ld(out),
            L.OP_N if a_op == "N" else L.OP_T, L.OP_N if b_op == "N" else L.OP_T, _DT[a.dtype], _DT[out.dtype],
            float(alpha), float(beta), _p(bias), flags, _p(dgelu_aux), _p(aux_out), _ld(aux) if aux is not None else 0,
@@ -164,6 +170,8 @@ def sdpa_fwd(q, k, v, *, h: int, d_k: int, d_v: int, mask=None, geo: Optional[Ge
     att = torch.empty((B, h, Lq, Lk), device=q.device, dtype=torch.float32) if need_att else None
     if scale is None:
         scale = 1.0 / math.sqrt(d_k)
+    if B == 0 or Lq == 0:
+        return out, lse, att
     # prefix-LM structure hint (harness.m4c.mmt_mask): per-key row + causal tail instead of the dense (B,1,L,L) tensor
     hint = getattr(mask, "_ovqa_prefix_lm", None)
     if hint is not None and q.dtype == torch.bfloat16 and geo is None and not need_att:
@@ -196,6 +204,10 @@ def sdpa_bwd(q, k, v, out, dout, lse, dq, dk, dv, *, h: int, d_k: int, d_v: int,
     if scale is None:
         scale = 1.0 / math.sqrt(d_k)
     g = geo
+    if B == 0 or Lq == 0:                    # no query rows: every gradient is zero
+        for t in (dq, dk, dv):
+            t.zero_()
+        return
     L.call("ovqa_sdpa_bwd", _p(q), _p(k), _p(v), _p(out), _p(dout), _p(dq), _p(dk), _p(dv), B, h, Lq, Lk, d_k, d_v,
            q.stride(1), k.stride(1), v.stride(1), out.stride(1), dout.stride(1), dq.stride(1), dk.stride(1), dv.stride(1),
            _p(mask), sb, sh, sq,
@@ -226,8 +238,9 @@ def layernorm_fwd(x, gamma, beta, *, residual=None, post_add=None, eps: float = 
     s = torch.empty_like(x2) if save_sum else None
     mean = torch.empty((rows,), device=x.device, dtype=torch.float32) if save_stats else None
     rstd = torch.empty((rows,), device=x.device, dtype=torch.float32) if save_stats else None
-    L.call("ovqa_layernorm_fwd", _p(x2), _p(r2), _p(gamma), _p(beta), _p(pa), pa_rows, _p(y), _p(y16), _p(s), _p(mean),
-           _p(rstd), rows, D, float(eps), _stream())
+    if rows > 0:
+        L.call("ovqa_layernorm_fwd", _p(x2), _p(r2), _p(gamma), _p(beta), _p(pa), pa_rows, _p(y), _p(y16), _p(s), _p(mean),
+               _p(rstd), rows, D, float(eps), _stream())
     shp = x.shape
     return (None if y is None else y.view(shp), None if y16 is None else y16.view(shp),
             None if s is None else s.view(shp), mean, rstd)
@@ -256,9 +269,10 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, *, dx_add=None, want_bf16: bool = Fa
         if dbeta is None:
             dbeta = torch.zeros((D,), device=x.device, dtype=torch.float32)
         dbias = (dbias_given if dbias_given is not None else torch.zeros((D,), device=x.device, dtype=torch.float32)) if want_dbias else None
-    L.call("ovqa_layernorm_bwd", _p(dy2), _p(x2), _p(mean), _p(rstd), _p(gamma),
-           None if dx_add is None else _p(dx_add.reshape(-1, D).contiguous()), _p(dx), _p(dx16), _p(dgamma), _p(dbeta), _p(dbias),
-           rows, D, float(dropout_p), int(seed), int(offset), _p(offset_base), _stream())
+    if rows > 0:
+        L.call("ovqa_layernorm_bwd", _p(dy2), _p(x2), _p(mean), _p(rstd), _p(gamma),
+               None if dx_add is None else _p(dx_add.reshape(-1, D).contiguous()), _p(dx), _p(dx16), _p(dgamma), _p(dbeta), _p(dbias),
+               rows, D, float(dropout_p), int(seed), int(offset), _p(offset_base), _stream())
     out = (dx.view(x.shape), (None if dx16 is None else dx16.view(x.shape)), dgamma, dbeta)
     return out + (dbias,) if want_dbias else out
 
@@ -271,6 +285,8 @@ def cast_rows_padmask(x: torch.Tensor, mask_value: float):
         raise ValueError("cast_rows_padmask: x must be fp32 with a width that is a multiple of 8")
     y = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
     mask = torch.empty((x.shape[0],), device=x.device, dtype=torch.float32)
+    if x.shape[0] == 0:
+        return y, mask
     L.call("ovqa_cast_rows_padmask", _p(x), _p(y), _p(mask), x.shape[0], x.shape[1], _ld(x), float(mask_value), _stream())
     return y, mask
 
@@ -282,6 +298,8 @@ def mul_to_bf16(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     if a.dtype != torch.float32 or b.dtype not in _DT or a.shape != b.shape:
         raise ValueError("mul_to_bf16: a fp32, b fp32/bf16, equal shapes")
     y = torch.empty(a.shape, device=a.device, dtype=torch.bfloat16)
+    if a.numel() == 0:
+        return y
     L.call("ovqa_mul_to_bf16", _p(a), _p(b), _DT[b.dtype], _p(y), a.numel(), _stream())
     return y
 
@@ -292,6 +310,8 @@ def to_bf16(x: torch.Tensor) -> torch.Tensor:
         return x
     x = x.contiguous()
     y = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    if x.numel() == 0:
+        return y
     L.call("ovqa_cast_f32_to_bf16", _p(x), _p(y), x.numel(), _stream())
     return y
 
@@ -302,6 +322,8 @@ def to_f32(x: torch.Tensor) -> torch.Tensor:
         return x
     x = x.contiguous()
     y = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+    if x.numel() == 0:
+        return y
     L.call("ovqa_cast_bf16_to_f32", _p(x), _p(y), x.numel(), _stream())
     return y
 
@@ -312,6 +334,8 @@ def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool
     if out is None:
         out = torch.empty((x.shape[1],), device=x.device, dtype=torch.float32)
         accumulate = False
+    if x.shape[0] == 0 or x.shape[1] == 0:
+        return out if accumulate else out.zero_()
     L.call("ovqa_colsum", _p(x), _p(out), x.shape[0], x.shape[1], _ld(x), _DT[x.dtype], int(accumulate), _stream())
     return out
 
@@ -320,6 +344,8 @@ def add(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     _need_cuda(a, b)
     a, b = a.contiguous(), b.contiguous()
     y = torch.empty_like(a)
+    if a.numel() == 0:
+        return y
     L.call("ovqa_add_f32", _p(a), _p(b), _p(y), a.numel(), _stream())
     return y
 
@@ -329,12 +355,16 @@ def dropout_apply(x: torch.Tensor, p: float, seed: int, offset: int, out_dtype=t
     _need_cuda(x)
     x = x.contiguous()
     y = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    if x.numel() == 0:
+        return y
     L.call("ovqa_dropout_apply", _p(x), _p(y), x.numel(), float(p), int(seed), int(offset), _p(offset_base), _DT[out_dtype], _stream())
     return y
 
 
 def dropout_keep_mask(n: int, p: float, seed: int, offset: int, device, offset_base=None) -> torch.Tensor:
     out = torch.empty((n,), device=device, dtype=torch.float32)
+    if n == 0:
+        return out
     L.call("ovqa_dropout_mask", _p(out), n, float(p), int(seed), int(offset), _p(offset_base), _stream())
     return out
 
@@ -398,3 +428,92 @@ def greedy_step(scores, prev_inds, last_ids, argmax_out, all_eos, step: int, eos
     B, T, W = scores.shape
     L.call("ovqa_greedy_step", _p(scores.contiguous()), _p(prev_inds), _p(last_ids), _p(argmax_out), _p(all_eos), B, T, W,
            int(step), int(eos_idx), _stream())
+
+
+# ----------------------------------------------------------------------------- inference blocks enqueued by one call (decode.cu)
+_WS = {}
+_HOSTPROF = False      # tools only: lets a host-overhead profile run the wrappers on CPU tensors against a stubbed library
+
+
+def _workspace(device, nbytes: int) -> torch.Tensor:
+    """Grow-only scratch buffer per (device, stream): kernels of one stream run in order, so consecutive calls may reuse it."""
+    if torch.cuda.is_current_stream_capturing():          # a captured graph keeps its own buffer (its memory pool keeps it alive)
+        return torch.empty((nbytes,), device=device, dtype=torch.uint8)
+    key = (device, _stream())
+    ws = _WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty((max(nbytes, 1 << 20),), device=device, dtype=torch.uint8)
+        _WS[key] = ws
+    return ws
+
+
+def _mask_args(mask, B: int, h: int, Lq: int, Lk: int):
+    """(tensor kept alive, pointer, sb, sh, sq) of an additive mask; the common (·,·,·,Lk) fp32 layout without building views."""
+    if mask is None:
+        return None, None, 0, 0, 0
+    if mask.dtype is torch.float32 and mask.dim() == 4:
+        shp, st = mask.shape, mask.stride()
+        if shp[3] == Lk and (st[3] == 1 or Lk == 1) and shp[0] in (1, B) and shp[1] in (1, h) and shp[2] in (1, Lq):
+            return mask, mask.data_ptr(), (0 if shp[0] == 1 else st[0]), (0 if shp[1] == 1 else st[1]), (0 if shp[2] == 1 else st[2])
+    m, sb, sh, sq = _mask_strides(mask, B, h, Lq, Lk)
+    return m, m.data_ptr(), sb, sh, sq
+
+
+def mha_decode_step(x, x_op, kv_src, self_attention: bool, wptrs, *, dt: int, eps: float, h: int, d_k: int, d_v: int, kv_cache, length: int,
+                    mask=None, scale: float):
+    """One MultiHeadAttention block of an inference decode step over the projected-K/V cache ``kv_cache`` (B, cap, h*d_k + h*d_v), of which
+    ``length`` positions are valid; appends the new rows in place (the caller advances its length).  x (B,Lq,D) fp32 contiguous, ``x_op``
+    the same rows in bf16 or None; ``wptrs`` = device pointers (w_qkv, b_qkv, w_o, b_o, gamma, beta) of tensors the caller keeps alive,
+    ``dt`` their compute dtype code.  Returns (y fp32, y bf16 | None).  Kept lean on purpose: at beam-search batch sizes the step is
+    bounded by host dispatch."""
+    B, Lq, D = x.shape
+    Lnew = Lq if self_attention else (0 if kv_src is None else kv_src.shape[1])
+    cshape = kv_cache.shape
+    if (not x.is_cuda and not _HOSTPROF) or x.dtype is not torch.float32 or not x.is_contiguous() or not kv_cache.is_contiguous() or _DT.get(kv_cache.dtype) != dt:
+        raise ValueError("mha_decode_step: x must be a contiguous fp32 CUDA tensor, the cache contiguous in the compute dtype")
+    if cshape[0] != B or cshape[2] != h * (d_k + d_v) or length + Lnew > cshape[1]:
+        raise ValueError(f"mha_decode_step: cache {tuple(cshape)} cannot take {length}+{Lnew} positions of batch {B}")
+    if kv_src is not None and not self_attention and (not kv_src.is_contiguous() or _DT.get(kv_src.dtype) != dt or kv_src.shape[0] != B):
+        raise ValueError("mha_decode_step: kv_src must be contiguous (B, Lnew, D) in the compute dtype")
+    mkeep, mptr, sb, sh, sq = _mask_args(mask, B, h, Lq, length + Lnew)
+    y = torch.empty_like(x)
+    y16 = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if dt == L.BF16 else None
+    if B == 0 or Lq == 0:
+        return y, y16
+    l = L.lib()
+    st = _stream()
+    nws = l.ovqa_mha_decode_workspace_bytes(B, Lq, Lnew, D, h, d_k, d_v, dt)
+    ws = _WS.get((x.device, st))
+    if ws is None or ws.numel() < nws or torch.cuda.is_current_stream_capturing():
+        ws = _workspace(x.device, nws)
+    rc = l.ovqa_mha_decode_step(x.data_ptr(), None if x_op is None else x_op.data_ptr(), None if kv_src is None else kv_src.data_ptr(),
+                                1 if self_attention else 0, B, Lq, Lnew, D, h, d_k, d_v, wptrs[0], wptrs[1], wptrs[2], wptrs[3], wptrs[4],
+                                wptrs[5], eps, kv_cache.data_ptr(), cshape[1], length, mptr, sb, sh, sq, scale, dt, ws.data_ptr(), ws.numel(),
+                                y.data_ptr(), None if y16 is None else y16.data_ptr(), st)
+    if rc:
+        L.check(rc, "ovqa_mha_decode_step")
+    return y, y16
+
+
+def pwff_infer(x, x_op, wptrs, *, dt: int, d_ff: int, eps: float):
+    """LN(x + fc2(gelu(fc1 x))) in eval mode from one call.  x (…, D) fp32 contiguous; ``wptrs`` = device pointers (w1, b1, w2, b2, gamma,
+    beta) of tensors the caller keeps alive.  Returns (y fp32, y bf16 | None)."""
+    D = x.shape[-1]
+    rows = x.numel() // D
+    if (not x.is_cuda and not _HOSTPROF) or x.dtype is not torch.float32 or not x.is_contiguous():
+        raise ValueError("pwff_infer: x must be a contiguous fp32 CUDA tensor")
+    y = torch.empty_like(x)
+    y16 = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if dt == L.BF16 else None
+    if rows == 0:
+        return y, y16
+    l = L.lib()
+    st = _stream()
+    nws = l.ovqa_pwff_infer_workspace_bytes(rows, D, d_ff, dt)
+    ws = _WS.get((x.device, st))
+    if ws is None or ws.numel() < nws or torch.cuda.is_current_stream_capturing():
+        ws = _workspace(x.device, nws)
+    rc = l.ovqa_pwff_infer(x.data_ptr(), None if x_op is None else x_op.data_ptr(), rows, D, d_ff, wptrs[0], wptrs[1], wptrs[2], wptrs[3],
+                           wptrs[4], wptrs[5], eps, dt, ws.data_ptr(), ws.numel(), y.data_ptr(), None if y16 is None else y16.data_ptr(), st)
+    if rc:
+        L.check(rc, "ovqa_pwff_infer")
+    return y, y16

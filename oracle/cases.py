@@ -115,3 +115,43 @@ def m4c_inputs(c, seed: int = 5):
         ocr_fasttext_features=torch.randn((B, c["Nocr"], 300), generator=g) * valid,
         ocr_boxes=S.boxes(B, c["Nocr"], seed + 4, scale=1.0),
     )
+
+
+# ----------------------------------------------------------------------------- decoder layer, stateless and stepwise (decoders.py:13-26)
+DEC_CASE = dict(B=3, T=7, N=11, D=128, h=4, d_ff=256, regather_at=3, perm=(2, 0, 1))
+
+
+def dec_spec(D: int, h: int, d_ff: int):
+    """state_dict layout of the reference DecoderLayer (running_keys / running_values buffers of the stateful self-attention incl.)."""
+    spec = []
+    for blk, stateful in (("self_attn", True), ("enc_attn", False)):
+        if stateful:                                                     # a module's own buffers precede its children's entries
+            spec += [(f"{blk}.running_keys", (0, D)), (f"{blk}.running_values", (0, D))]
+        spec += [(f"{blk}.{k}", sh) for k, sh in att_spec(D, h, D // h, D // h)]
+    return spec + [(f"pwff.{k}", sh) for k, sh in pwff_spec(D, d_ff)]
+
+
+def dec_inputs(seed: int = 41):
+    c = DEC_CASE
+    g = S._gen(seed, "decoder")
+    x = torch.randn((c["B"], c["T"], c["D"]), generator=g)
+    tok_pad = torch.zeros((c["B"], c["T"]), dtype=torch.bool)
+    tok_pad[1, 4:] = True                                               # sample 1 ends after 4 tokens: later positions are padding
+    enc = S.padded_features(c["B"], c["N"], c["D"], seed + 1, min_valid=4, relu_like=False)
+    enc_mask = R.padding_mask(enc, 0)
+    pad_mask = (tok_pad.long() * -10e4).float().view(c["B"], 1, 1, c["T"])                 # models/utils.py:44-60 form
+    full_mask = R.self_attention_masks(pad_mask, R.sequential_mask(c["T"]))
+    step_masks = [pad_mask[..., t:t + 1] for t in range(c["T"])]
+    return dict(x=x, enc=enc, enc_mask=enc_mask, full_mask=full_mask, step_masks=step_masks)
+
+
+def dec_stepwise_inputs(x):
+    """Per-step (x_t, mask_t, enc, enc_mask) of the golden stepwise run: after step ``regather_at`` the batch rows change places
+    (make_golden.gen_decoder), as they do when beam search re-gathers the surviving beams."""
+    c = DEC_CASE
+    perm, cur, per_step = torch.tensor(c["perm"]), torch.arange(c["B"]), []
+    for t in range(c["T"]):
+        per_step.append((x["x"][cur, t:t + 1], x["step_masks"][t][cur], x["enc"][cur], x["enc_mask"][cur]))
+        if t == c["regather_at"]:
+            cur = cur[perm]
+    return per_step, perm

@@ -193,12 +193,50 @@ def gen_m4c():
     print("m4c.pt decode prev_inds:\n", out["decode"]["prev_inds"])
 
 
+def gen_decoder():
+    """DecoderLayer (decoders.py:13-26) run stateless over the whole sequence and one token at a time inside ``statefulness()``
+    with a beam-style re-gather of the states half-way (containers.py:26-31, beam_search.py:19-33)."""
+    import models.modules.decoders as Dm
+    from models.utils import generate_sequential_mask, generate_self_attention_masks
+
+    c = C.DEC_CASE
+    att = lambda st: RL.attention_cfg(c["D"], c["h"], c["D"] // c["h"], c["D"] // c["h"], d_ff=c["d_ff"], stateful=st)
+    layer = Dm.DecoderLayer(RL.NS(SELF_ATTENTION=att(True), ENC_ATTENTION=att(False))).eval()
+    spec = _load(layer)
+    assert spec == C.dec_spec(c["D"], c["h"], c["d_ff"]), spec
+    x = C.dec_inputs()
+    out = dict(spec=spec)
+    with torch.no_grad():
+        pad = x["full_mask"].new_zeros(()) + torch.stack([m for m in x["step_masks"]], -1).view(c["B"], 1, 1, c["T"])
+        full_mask = generate_self_attention_masks(pad, generate_sequential_mask(c["T"]))
+        assert torch.equal(full_mask.float(), x["full_mask"].float())
+        out["full"] = layer(x["x"], x["enc"], x["enc"], full_mask, x["enc_mask"])
+        steps = []
+        perm = torch.tensor(c["perm"])
+        xs, enc, enc_mask, masks = x["x"], x["enc"], x["enc_mask"], x["step_masks"]
+        with layer.statefulness(c["B"]):
+            running_mask = torch.zeros((c["B"], 1, 1, 0))
+            for t in range(c["T"]):
+                running_mask = torch.cat([running_mask, masks[t]], -1)                       # decoders.py:53-55
+                steps.append(layer(xs[:, t:t + 1], enc, enc, running_mask, enc_mask))
+                if t == c["regather_at"]:                                                    # the batch rows change places, states follow
+                    layer.apply_to_states(lambda s_: s_[perm])
+                    running_mask = running_mask[perm]
+                    xs, enc, enc_mask = xs[perm], enc[perm], enc_mask[perm]
+                    masks = [m[perm] for m in masks]
+            assert layer.self_attn.running_keys.shape == (c["B"], c["T"], c["D"])
+        out["steps"] = torch.cat(steps, 1)
+    torch.save(out, os.path.join(OUT, "decoder.pt"))
+    print("decoder.pt: stepwise-vs-full max abs before the re-gather",
+          (out["steps"][:, :c["regather_at"] + 1] - out["full"][:, :c["regather_at"] + 1]).abs().max().item())
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     RL.load()
     torch.manual_seed(0)
     torch.set_num_threads(min(8, os.cpu_count() or 1))
-    which = sys.argv[1:] or ["attention", "geometry", "masks", "encoders", "mcan", "m4c"]
+    which = sys.argv[1:] or ["attention", "geometry", "masks", "encoders", "mcan", "m4c", "decoder"]
     for w in which:
         globals()["gen_" + w]()
 

@@ -183,6 +183,35 @@ def pwff(p: Params, x, *, dropout: float = 0.0, training: bool = False, eps: flo
     return _ln(p, "layer_norm", x + out, eps)
 
 
+# --------------------------------------------------------------------------- decoder layer (models/modules/decoders.py)
+def decoder_layer(p: Params, queries, keys, values, self_mask, enc_mask, cfg):
+    """DecoderLayer.forward — decoders.py:21-26: self-attention -> encoder attention -> feed-forward."""
+    self_att = mha(sub(p, "self_attn"), queries, queries, queries, self_mask, **_acfg(cfg))
+    enc_att = mha(sub(p, "enc_attn"), self_att, keys, values, enc_mask, **_acfg(cfg))
+    return pwff(sub(p, "pwff"), enc_att, dropout=cfg.get("dropout", 0.0), training=cfg.get("training", False))
+
+
+def decoder_layer_stateful(p: Params, steps, keys, values, step_masks, enc_mask, cfg, regather=None):
+    """The same layer driven one token at a time inside ``statefulness()`` (beam search, base_transformer.py:50-52): the
+    self-attention block appends each step's keys / values to ``running_keys`` / ``running_values`` and attends over all of them
+    (attentions.py:321-325); the caller accumulates the self-attention mask the same way (decoders.py:53-55).  ``steps``: list of
+    (B,1,D) inputs; ``step_masks``: list of (B,1,1,1) additive masks; ``regather``: {t: batch index tensor} applied to the states
+    after step t (what beam_search.py:19-33 does through ``apply_to_states``).  Returns the list of (B,1,D) outputs."""
+    running_k = running_v = running_mask = None
+    outs = []
+    for t, (x, m) in enumerate(zip(steps, step_masks)):
+        running_k = x if running_k is None else torch.cat([running_k, x], 1)                  # attentions.py:322-325
+        running_v = x if running_v is None else torch.cat([running_v, x], 1)
+        running_mask = m if running_mask is None else torch.cat([running_mask, m], -1)       # decoders.py:54
+        self_att = mha(sub(p, "self_attn"), x, running_k, running_v, running_mask, **_acfg(cfg))
+        enc_att = mha(sub(p, "enc_attn"), self_att, keys, values, enc_mask, **_acfg(cfg))
+        outs.append(pwff(sub(p, "pwff"), enc_att))
+        if regather is not None and t in regather:
+            idx = regather[t]
+            running_k, running_v, running_mask = running_k[idx], running_v[idx], running_mask[idx]
+    return outs
+
+
 # --------------------------------------------------------------------------- encoders (models/modules/encoders.py)
 def _acfg(cfg) -> dict:
     return dict(h=cfg["h"], d_k=cfg["d_k"], d_v=cfg["d_v"], dropout=cfg.get("dropout", 0.0),

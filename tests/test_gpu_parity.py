@@ -627,3 +627,149 @@ def test_weight_cache_follows_optimizer_updates(dev):
         y2 = ref(x, x, x, None)
     assert (y1 - y0).abs().max() > 1e-3          # the step changed the output ...
     assert torch.equal(y1, y2)                   # ... exactly as a freshly built module with the new weights sees it
+
+
+# ------------------------------------------------------------------------------------------------ stateful decode
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_decoder_layer_stepwise_with_kv_cache(dev, golden, mode):
+    """DecoderLayer (decoders.py:13-26) over the whole sequence and one token at a time inside ``statefulness()``: the inference
+    path keeps PROJECTED keys / values (self-attention: appended per step and re-gathered with the beams; encoder attention:
+    projected once) and must reproduce the reference, which re-projects everything at every step."""
+    c, g = C.DEC_CASE, golden("decoder")
+    att = lambda st: H.attention_cfg(c["D"], c["h"], d_ff=c["d_ff"], stateful=st, compute_dtype=mode)
+    layer = load(H.DecoderLayer(H.NS(SELF_ATTENTION=att(True), ENC_ATTENTION=att(False))), S.synth_params(g["spec"], 0), dev)
+    x = C.dec_inputs()
+    d = lambda t: t.to(dev)
+    with torch.no_grad():
+        check(layer(d(x["x"]), d(x["enc"]), d(x["enc"]), d(x["full_mask"]), d(x["enc_mask"])), g["full"], mode, "decoder layer, whole sequence")
+    per_step, perm = C.dec_stepwise_inputs(x)
+
+    def run(grad):
+        outs = []
+        with torch.set_grad_enabled(grad), layer.statefulness(c["B"]):
+            running_mask, enc_prev = torch.zeros((c["B"], 1, 1, 0), device=dev), None
+            for t, (xt, mt, enc, enc_mask) in enumerate(per_step):
+                running_mask = torch.cat([running_mask, d(mt)], -1)
+                if enc_prev is None or not torch.equal(enc_prev[0].cpu(), enc):       # (the same tensor object across steps, as beam search passes it)
+                    enc_prev = (d(enc), d(enc_mask))
+                outs.append(layer(d(xt), enc_prev[0], enc_prev[0], running_mask, enc_prev[1]))
+                if t == c["regather_at"]:
+                    layer.apply_to_states(lambda s_: s_[d(perm)])
+                    running_mask = running_mask[d(perm)]
+            sa = layer.self_attn
+            if grad:      # reference bookkeeping: raw keys accumulate, nothing cached
+                assert sa.running_keys.shape == (c["B"], c["T"], c["D"]) and sa._kv_len == 0 and layer.enc_attn._enc_kv is None
+            else:         # inference: projected rows accumulate, encoder keys projected once per tensor
+                assert sa._kv_len == c["T"] and sa.running_kv_proj.shape[0] == c["B"] and sa.running_keys.shape[1] == 0
+                assert layer.enc_attn._enc_kv is not None
+        assert layer.self_attn.running_kv_proj.shape == (0, 2 * c["D"]) and layer.self_attn._kv_len == 0 and layer.enc_attn._enc_kv is None
+        return torch.cat(outs, 1)
+
+    cached, recomputed = run(False), run(True)
+    check(cached, g["steps"], mode, "stepwise decode, projected K/V cache")
+    check(recomputed, g["steps"], mode, "stepwise decode, reference bookkeeping")
+    # the two paths run the same kernels on the same rows; only the GEMM batch differs
+    assert abs_err(cached, recomputed) <= (1e-5 if mode == "fp32" else 2e-2)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("D,h", [(128, 4), (192, 2)])
+def test_mha_decode_step_call(dev, mode, D, h):
+    """ovqa_mha_decode_step on its own: multi-row prefixes, single rows, appended rows from another source, per-query masks — each
+    step against the oracle block over the concatenated RAW inputs (what the reference computes, attentions.py:321-331)."""
+    dk = D // h
+    p = S.synth_params(C.att_spec(D, h, dk, dk), 3)
+    P = {k: v.to(dev) for k, v in p.items()}
+    W = dict(wq=P["attention.fc_q.weight"], bq=P["attention.fc_q.bias"], wk=P["attention.fc_k.weight"], bk=P["attention.fc_k.bias"],
+             wv=P["attention.fc_v.weight"], bv=P["attention.fc_v.bias"], wo=P["attention.fc_o.weight"], bo=P["attention.fc_o.bias"],
+             gamma=P["layer_norm.weight"], beta=P["layer_norm.bias"], mode=mode)
+    plan = Fn.mha_decode_plan(**W)
+    g = S._gen(5, f"decode{D}")
+    B, cap = 3, 16
+    cache = torch.full((B, cap, 2 * D), float("nan"), device=dev, dtype=torch.float32 if mode == "fp32" else torch.bfloat16)
+    raw, length = [], 0
+    schedule = [("self", 3), ("self", 1), ("cross", 2), ("self", 2), ("none", 1)]
+    for kind, n in schedule:
+        q = torch.randn((B, n if kind == "self" else 2, D), generator=g)
+        src = q if kind == "self" else (torch.randn((B, n, D), generator=g) if kind == "cross" else None)
+        if src is not None:
+            raw.append(src)
+        keys = torch.cat(raw, 1)
+        Lk = keys.shape[1]
+        mask = (torch.rand((B, 1, q.shape[1], Lk), generator=g) < 0.25).float() * -10e4
+        mask[..., 0] = 0.0
+        ref = R.mha(p, q, keys, keys, mask, h=h, d_k=dk, d_v=dk)
+        y = Fn.mha_decode_block(plan, q.to(dev), None if src is None else src.to(dev), kind == "self", cache, length, mask.to(dev),
+                                h=h, d_k=dk, d_v=dk)
+        length = Lk
+        check(y, ref, mode, f"decode step {kind}/{n} at length {Lk}")
+    assert torch.isfinite(cache[:, :length].float()).all() and torch.isnan(cache[:, length:].float()).all()     # filed exactly the valid rows
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_pwff_inference_call_matches_the_block(dev, mode):
+    torch.manual_seed(0)
+    m = ovqa.PositionWiseFeedForward(H.attention_cfg(128, 4, d_ff=256, dropout=0.1, compute_dtype=mode)).to(dev).eval()
+    x = torch.randn((3, 5, 128), device=dev)
+    with torch.no_grad():
+        y_call = m(x)                                    # one library call
+    y_block = m(x)                                       # grad mode: the autograd block (same kernels)
+    assert abs_err(y_call, y_block) <= 1e-6
+    m.train()
+    with torch.no_grad():
+        assert abs_err(m(x), y_block) > 1e-3             # training-mode dropout still applies under no_grad
+
+
+def test_encoder_kv_cache_follows_in_place_updates(dev):
+    """The once-per-session projection of the encoder keys is keyed on the tensor's identity AND version."""
+    torch.manual_seed(0)
+    m = ovqa.MultiHeadAttention(H.attention_cfg(128, 4, compute_dtype="bf16")).to(dev).eval()
+    q, enc = torch.randn((2, 1, 128), device=dev), torch.randn((2, 9, 128), device=dev)
+    with torch.no_grad():
+        ref0 = m(q, enc, enc, None)
+        with m.statefulness(2):
+            y0 = m(q, enc, enc, None)
+            tag0 = m._enc_kv[0]
+            y0b = m(q, enc, enc, None)
+            assert m._enc_kv[0] == tag0                        # second step: cache hit
+            enc.mul_(-1.0)                                     # same storage, new contents
+            y1 = m(q, enc, enc, None)
+            assert m._enc_kv[0] != tag0
+        ref1 = m(q, enc, enc, None)
+    # (the one-call decode path scores with fp32 probabilities, the block's tensor-core kernel rounds them to bf16)
+    assert torch.equal(y0, y0b) and abs_err(y0, ref0) <= BF16_ABS and abs_err(y1, ref1) <= BF16_ABS
+    assert abs_err(y1, y0) > 10 * BF16_ABS
+
+
+# ------------------------------------------------------------------------------------------------ empty inputs
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_empty_inputs(dev, dt):
+    """A batch of zero rows goes through every wrapper and returns correctly shaped empty results (what torch's own ops do)."""
+    a, w = torch.empty((0, 64), device=dev, dtype=dt), torch.randn((32, 64), device=dev).to(dt)      # w: Linear layout (n, k)
+    assert ops.gemm(a, w).shape == (0, 32)
+    assert ops.gemm(w, a).shape == (32, 0)
+    dw = ops.gemm(torch.empty((0, 32), device=dev, dtype=dt), a, a_op="T", b_op="T", out_dtype=torch.float32)   # weight gradient over zero rows
+    assert dw.shape == (32, 64) and float(dw.abs().sum()) == 0.0
+    q = torch.empty((0, 5, 64), device=dev, dtype=dt)
+    out, lse, _ = ops.sdpa_fwd(q, q, q, h=4, d_k=16, d_v=16, need_lse=True)
+    assert out.shape == (0, 5, 64) and lse.shape == (0, 4, 5)
+    x = torch.empty((0, 7, 64), device=dev)
+    g, b = torch.ones(64, device=dev), torch.zeros(64, device=dev)
+    y, y16, _, mean, rstd = ops.layernorm_fwd(x, g, b, want_bf16=True, save_stats=True)
+    assert y.shape == x.shape and y16.shape == x.shape and mean.numel() == 0
+    dx, _, dg, db = ops.layernorm_bwd(x, x, mean, rstd, g)
+    assert dx.shape == x.shape and float(dg.abs().sum()) == 0.0 and float(db.abs().sum()) == 0.0
+    assert float(ops.colsum(torch.empty((0, 64), device=dev)).abs().sum()) == 0.0
+    assert ops.to_bf16(torch.empty((0, 8), device=dev)).shape == (0, 8)
+    yb, m = ops.cast_rows_padmask(torch.empty((0, 64), device=dev), -1e4)
+    assert yb.shape == (0, 64) and m.shape == (0,)
+    # the module level: an empty batch through a training-mode block, forward and backward
+    torch.manual_seed(0)
+    mha = ovqa.MultiHeadAttention(H.attention_cfg(64, 4, dropout=0.1, compute_dtype="bf16" if dt == torch.bfloat16 else "fp32")).to(dev).train()
+    xe = torch.empty((0, 5, 64), device=dev, requires_grad=True)
+    ye = mha(xe, xe, xe, None)
+    assert ye.shape == (0, 5, 64)
+    ye.sum().backward()
+    assert xe.grad.shape == xe.shape
+    for p in mha.parameters():
+        assert p.grad is None or float(p.grad.abs().sum()) == 0.0

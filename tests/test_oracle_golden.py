@@ -137,3 +137,35 @@ def test_m4c_step_parts_and_greedy_decode(golden):
     scores, prev_inds, n = R.m4c_greedy_decode(p, x, max_iter=c["T"], **kw)
     assert torch.equal(prev_inds, g["decode"]["prev_inds"])
     _close(scores, g["decode"]["scores"], atol=1e-2, rtol=1e-5)
+
+
+def _dec_case():
+    c = C.DEC_CASE
+    cfg = dict(h=c["h"], d_k=c["D"] // c["h"], d_v=c["D"] // c["h"])
+    p = {k: v for k, v in S.synth_params(C.dec_spec(c["D"], c["h"], c["d_ff"]), 0).items() if "running_" not in k}
+    return c, cfg, p, C.dec_inputs()
+
+
+def test_decoder_layer_stateless_and_stepwise(golden):
+    """decoders.py:13-26 over a whole sequence, and token by token with running keys / values + a beam-style state re-gather."""
+    c, cfg, p, x = _dec_case()
+    g = golden("decoder")
+    assert g["spec"] == C.dec_spec(c["D"], c["h"], c["d_ff"])
+    _close(R.decoder_layer(p, x["x"], x["enc"], x["enc"], x["full_mask"], x["enc_mask"], cfg), g["full"])
+    per_step, perm = C.dec_stepwise_inputs(x)
+    # the encoder side changes rows at the re-gather too, so drive the oracle in two segments that share its running state
+    outs = []
+    running_k = running_m = None
+    for t, (xt, mt, enc, enc_mask) in enumerate(per_step):
+        running_k = xt if running_k is None else torch.cat([running_k, xt], 1)
+        running_m = mt if running_m is None else torch.cat([running_m, mt], -1)
+        sa = R.mha(R.sub(p, "self_attn"), xt, running_k, running_k, running_m, **cfg)
+        ea = R.mha(R.sub(p, "enc_attn"), sa, enc, enc, enc_mask, **cfg)
+        outs.append(R.pwff(R.sub(p, "pwff"), ea))
+        if t == c["regather_at"]:
+            running_k, running_m = running_k[perm], running_m[perm]
+    _close(torch.cat(outs, 1), g["steps"])
+    # and the packaged stepwise oracle (no encoder-side permutation: compare the steps before the re-gather)
+    k = c["regather_at"] + 1
+    st = R.decoder_layer_stateful(p, [x["x"][:, t:t + 1] for t in range(k)], x["enc"], x["enc"], x["step_masks"][:k], x["enc_mask"], cfg)
+    _close(torch.cat(st, 1), g["steps"][:, :k])

@@ -189,6 +189,77 @@ def bench_mha():
     ovqa.set_compute_dtype("fp32")
 
 
+def bench_decode():
+    """T-step incremental decode through 3 decoder layers (decoders.py:13-26) at batch x beam = 320 rows, 100
+    encoder regions.  (a) projected-K/V cache (the inference path), (b) the same kernels with the reference's bookkeeping (re-project
+    the running sequence and the encoder output at every step), (c) the reference arithmetic in plain PyTorch ops, fp32 and bf16 autocast."""
+    import torch.nn.functional as F
+    from openvivqa_b200 import modules as M
+    B, T, N, D, h, dff, nl = 320, 20, 100, 512, 8, 2048, 3
+    att = lambda st: H.attention_cfg(D, h, d_ff=dff, dropout=0.0, stateful=st, compute_dtype="bf16")
+    layers = [H.DecoderLayer(H.NS(SELF_ATTENTION=att(True), ENC_ATTENTION=att(False))).to(dev).eval() for _ in range(nl)]
+    xs = [torch.randn((B, 1, D), device=dev) for _ in range(T)]
+    enc = torch.randn((B, N, D), device=dev)
+    enc_mask = torch.zeros((B, 1, 1, N), device=dev)
+    enc_mask[..., 80:] = -10e4
+
+    def ours():
+        for l in layers:
+            l.enable_statefulness(B)
+        mask = torch.zeros((B, 1, 1, 0), device=dev)
+        for t in range(T):
+            mask = torch.cat([mask, torch.zeros((B, 1, 1, 1), device=dev)], -1)
+            y = xs[t]
+            for l in layers:
+                y = l(y, enc, enc, mask, enc_mask)
+        for l in layers:
+            l.disable_statefulness()
+        return y
+
+    def wts(m):
+        a = m.attention
+        return {"q": (a.fc_q.weight, a.fc_q.bias), "k": (a.fc_k.weight, a.fc_k.bias), "v": (a.fc_v.weight, a.fc_v.bias),
+                "o": (a.fc_o.weight, a.fc_o.bias), "ln": (m.layer_norm.weight, m.layer_norm.bias)}
+    W = [(wts(l.self_attn), wts(l.enc_attn), l.pwff) for l in layers]
+
+    def torch_ref():
+        running = [None] * nl
+        mask = torch.zeros((B, 1, 1, 0), device=dev)
+        for t in range(T):
+            mask = torch.cat([mask, torch.zeros((B, 1, 1, 1), device=dev)], -1)
+            y = xs[t]
+            for i, (ws, we, ff) in enumerate(W):
+                running[i] = y if running[i] is None else torch.cat([running[i], y], 1)         # attentions.py:321-325
+                y = _torch_mha(y, running[i], mask, ws, h)
+                y = _torch_mha(y, enc, enc_mask, we, h)
+                o = F.linear(F.gelu(F.linear(y, ff.fc1.weight, ff.fc1.bias)), ff.fc2.weight, ff.fc2.bias)
+                y = F.layer_norm(y + o, (D,), ff.layer_norm.weight, ff.layer_norm.bias)
+        return y
+
+    with torch.no_grad():
+        t_cache = timeit(ours, iters=5, warmup=2)
+        M.DECODE_KV_CACHE = False
+        t_nocache = timeit(ours, iters=5, warmup=2)
+        M.DECODE_KV_CACHE = True
+        # the same 20 steps captured into ONE CUDA graph (every step's shapes are known in advance): what the GPU alone needs
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            ours()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            y_graph = ours()
+        t_graph = timeit(graph.replay, iters=5, warmup=2)
+        t32 = timeit(torch_ref, iters=3, warmup=1)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            t16 = timeit(torch_ref, iters=3, warmup=1)
+        a, b = ours(), torch_ref()
+    emit(kind="decode_3_layers", rows=B, steps=T, regions=N, D=D, cached_us=t_cache, cached_one_graph_us=t_graph, recompute_us=t_nocache, torch_fp32_us=t32,
+         torch_bf16_autocast_us=t16, rows_per_s_cached=B / t_cache * 1e6, speedup_vs_recompute=t_nocache / t_cache,
+         speedup_vs_torch_fp32=t32 / t_cache, speedup_vs_torch_bf16=t16 / t_cache, max_abs_diff_vs_torch_fp32=(a - b).abs().max().item())
+
+
 def bench_gemm_epilogues():
     """The fused epilogues of the training step at the vision-branch shapes (B*L = 25600)."""
     M, D, F_ = 25600, 512, 2048
@@ -221,4 +292,4 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "epi", "sdpa", "ln", "mha"]
     emit(kind="meta", gpu=torch.cuda.get_device_name(0), peaks=PEAKS)
     for w in which:
-        {"gemm": bench_gemm, "wgrad": bench_wgrad_split, "epi": bench_gemm_epilogues, "sdpa": bench_sdpa, "ln": bench_ln, "mha": bench_mha}[w]()
+        {"gemm": bench_gemm, "wgrad": bench_wgrad_split, "epi": bench_gemm_epilogues, "sdpa": bench_sdpa, "ln": bench_ln, "mha": bench_mha, "decode": bench_decode}[w]()
