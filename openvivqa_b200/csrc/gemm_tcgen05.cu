@@ -28,12 +28,16 @@ using namespace tc5;
 constexpr int BM = 128;          // UMMA M (cta_group::1)
 constexpr int BK = 64;           // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int kEpiWarps = 16;
-constexpr int kThreads = 64 + kEpiWarps * 32;
-constexpr int kRegBoundThreads = 640;   // __launch_bounds__ figure: 65536/640 -> <= 96 registers per thread, which is what 5 warps per SM
-                                        // sub-partition (18 warps over 4 partitions) can actually be given
+// Epilogue warps per CTA (template parameter EPW): 16 warps leave <= 96 registers per thread (18 warps over 4 sub-partitions put 5 on
+// one: 16384 / (5 * 32)), 8 warps leave 168 (10 warps: 3 per sub-partition).  Measured on the MCAN step (profiles/README, run L): the
+// fp32-result epilogues (residual, dropout, split-K atomics) and the plain ones run faster with 8 warps and two passes' worth of
+// independent instruction streams each; the bf16 epilogues that multiply by a saved operand or evaluate GELU want the 16 warps.
+constexpr int kMaxEpiWarps = 16;
+constexpr int epw_for(int mode, int feat) {
+    return (mode == 1 /*EPI_FULL*/ && (feat < 0 || (feat & 8 /*F_MULAUX*/) || ((feat & 2 /*F_GELU*/) && !(feat & 4 /*F_SAVE_D*/)))) ? 16 : 8;
+}
 constexpr int kAccStages = 2;
-constexpr int kScratchBytes = kEpiWarps * 32 * 32 * 4;   // one 32x32 fp32 chunk per epilogue warp
+constexpr int kScratchBytes = kMaxEpiWarps * 32 * 32 * 4;   // one 32x32 fp32 chunk per epilogue warp
 
 // CTAS = 1: one CTA per 128 x BN tile.  CTAS = 2: a CTA pair (cluster of 2, cta_group::2) per 256 x BN tile — each CTA stages its
 // own 128 rows of A and HALF of B (the MMA reads the other half from the peer's shared memory): 32 KB instead of 48 KB of L2 -> smem
@@ -133,8 +137,8 @@ __device__ __noinline__ void epilogue_scalar(const Epilogue& epi, float acc, int
 }
 
 // ----------------------------------------------------------------------------- kernel
-template <int BN, bool A_MN, bool B_MN, typename TC, int MODE, int FEAT, int CTAS>
-__global__ void __launch_bounds__(kRegBoundThreads, 1)
+template <int BN, bool A_MN, bool B_MN, typename TC, int MODE, int FEAT, int CTAS, int EPW>
+__global__ void __launch_bounds__(EPW == 16 ? 640 : 384, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, TC* __restrict__ C,
                     int64_t m, int64_t n, int64_t k, int64_t ldc, Epilogue epi, int split_k) {
     using cfg = Cfg<BN, CTAS>;
@@ -163,7 +167,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
         // full: the leader's own arrive.expect_tx (+ the peer's remote arrive); tmem_empty: the epilogue warps of every CTA of the pair
         for (int i = 0; i < cfg::kStages; ++i) { mbar_init(full_bar + i, CTAS); mbar_init(empty_bar + i, 1); }
-        for (int i = 0; i < kAccStages; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, kEpiWarps * CTAS); }
+        for (int i = 0; i < kAccStages; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, EPW * CTAS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -316,7 +320,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                     constexpr int kLinesPerRow = BN * kElt / 128;
                     const char* base = (FEAT & F_RES) ? reinterpret_cast<const char*>(residual) : reinterpret_cast<const char*>(aux_in);
                     const int64_t ld_b = ((FEAT & F_RES) ? ld_res : ld_aux) * kElt;
-                    for (int idx = (warp - 2) * 32 + lane; idx < BM * kLinesPerRow; idx += kEpiWarps * 32) {
+                    for (int idx = (warp - 2) * 32 + lane; idx < BM * kLinesPerRow; idx += EPW * 32) {
                         const int64_t r = (int64_t)mt2 * TM + (int64_t)cta_rank * BM + idx / kLinesPerRow;
                         const int64_t cbyte = ((int64_t)nt2 * BN) * kElt + (idx % kLinesPerRow) * 128;
                         if (r < m && cbyte < n * kElt) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + r * ld_b + cbyte));
@@ -328,7 +332,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             const int64_t row_base = (int64_t)mt * TM + (int64_t)cta_rank * BM + quad * 32 + rr;          // + 8 * pass
             const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-            for (int c0 = slot * 32; c0 < BN; c0 += 128) {
+            for (int c0 = slot * 32; c0 < BN; c0 += (EPW / 4) * 32) {
                 const int64_t col0 = (int64_t)nt * BN + c0;
                 if (col0 >= n) break;                                     // warp-uniform
                 const int64_t col = col0 + (kSplit ? c8 * 4 : c8 * 8);
@@ -677,7 +681,8 @@ int launch(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, int64_t m, i
     }
 #define OVQA_GO(TC_, MODE_, FEAT_)                                                                                              \
     do {                                                                                                                       \
-        auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, TC_, MODE_, FEAT_, CTAS>;                                               \
+        constexpr int kEpw = epw_for(MODE_, FEAT_), kThreads = 64 + kEpw * 32;                                                  \
+        auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, TC_, MODE_, FEAT_, CTAS, kEpw>;                                               \
         static bool attr_set = false;                                                                                          \
         if (!attr_set) { OVQA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::kSmemBytes)); attr_set = true; } \
         if constexpr (CTAS == 1) {                                                                                             \
