@@ -32,24 +32,25 @@ constexpr int UMMA_K = 16;
 // one: 16384 / (5 * 32)), 8 warps leave 168 (10 warps: 3 per sub-partition).  Measured on the MCAN step (profiles/README, run L): the
 // fp32-result epilogues (residual, dropout, split-K atomics) and the plain ones run faster with 8 warps and two passes' worth of
 // independent instruction streams each; the bf16 epilogues that multiply by a saved operand or evaluate GELU want the 16 warps.
-constexpr int kMaxEpiWarps = 16;
 constexpr int epw_for(int mode, int feat) {
     return (mode == 1 /*EPI_FULL*/ && (feat < 0 || (feat & 8 /*F_MULAUX*/) || ((feat & 2 /*F_GELU*/) && !(feat & 4 /*F_SAVE_D*/)))) ? 16 : 8;
 }
 constexpr int kAccStages = 2;
-constexpr int kScratchBytes = kMaxEpiWarps * 32 * 32 * 4;   // one 32x32 fp32 chunk per epilogue warp
 
 // CTAS = 1: one CTA per 128 x BN tile.  CTAS = 2: a CTA pair (cluster of 2, cta_group::2) per 256 x BN tile — each CTA stages its
 // own 128 rows of A and HALF of B (the MMA reads the other half from the peer's shared memory): 32 KB instead of 48 KB of L2 -> smem
 // traffic per SM and k-block at BN = 256, and room for 5 pipeline stages instead of 3 (profiles/r01d: the single-CTA 128 x 256 tile
 // is bound by the L2 -> SM path, not by the tensor pipe).
-template <int BN, int CTAS> struct Cfg {
-    static constexpr int kStages = CTAS == 2 ? 5 : (BN == 256 ? 3 : 5);
+template <int BN, int CTAS, int EPW> struct Cfg {
+    static constexpr int kScratchBytes = EPW * 32 * 32 * 4;   // one 32x32 fp32 chunk per epilogue warp
+    // pipeline depth: what fits beside the scratch (8 epilogue warps free 32 KB: one more stage)
+    static constexpr int kStages = (CTAS == 2 ? 5 : (BN == 256 ? 3 : 5)) + (EPW == 8 ? 1 : 0);
     static constexpr int kABytes = BM * BK * 2;
     static constexpr int kBBytes = (BN / CTAS) * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kTmemCols = kAccStages * BN;  // 256 or 512: power of two
     static constexpr int kSmemBytes = kStages * kStageBytes + kScratchBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
 // ----------------------------------------------------------------------------- epilogue pieces
@@ -141,13 +142,13 @@ template <int BN, bool A_MN, bool B_MN, typename TC, int MODE, int FEAT, int CTA
 __global__ void __launch_bounds__(EPW == 16 ? 640 : 384, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, TC* __restrict__ C,
                     int64_t m, int64_t n, int64_t k, int64_t ldc, Epilogue epi, int split_k) {
-    using cfg = Cfg<BN, CTAS>;
+    using cfg = Cfg<BN, CTAS, EPW>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + cfg::kStages * cfg::kABytes;
     float4* scratch = reinterpret_cast<float4*>(smem + cfg::kStages * cfg::kStageBytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + cfg::kStages * cfg::kStageBytes + kScratchBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + cfg::kStages * cfg::kStageBytes + cfg::kScratchBytes);
     uint64_t* full_bar = bars;                              // [kStages]   TMA -> MMA
     uint64_t* empty_bar = bars + cfg::kStages;              // [kStages]   MMA -> TMA
     uint64_t* tmem_full = bars + 2 * cfg::kStages;          // [2]         MMA -> epilogue
@@ -657,7 +658,6 @@ inline int make_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t 
 template <int BN, bool A_MN, bool B_MN, int CTAS>
 int launch(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb,
            int64_t ldc, const Epilogue& epi, int split_k, cudaStream_t st) {
-    using cfg = Cfg<BN, CTAS>;
     CUtensorMap ma, mb;
     int rc;
     // K-major: tensor [rows, k] box {64 k, ROWS};  MN-major: tensor [k, rows] box {64 rows, 64 k}.  A CTA of a pair loads half of B's rows.
@@ -682,6 +682,7 @@ int launch(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, int64_t m, i
 #define OVQA_GO(TC_, MODE_, FEAT_)                                                                                              \
     do {                                                                                                                       \
         constexpr int kEpw = epw_for(MODE_, FEAT_), kThreads = 64 + kEpw * 32;                                                  \
+        using cfg = Cfg<BN, CTAS, kEpw>;                                                                                        \
         auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, TC_, MODE_, FEAT_, CTAS, kEpw>;                                               \
         static bool attr_set = false;                                                                                          \
         if (!attr_set) { OVQA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::kSmemBytes)); attr_set = true; } \
