@@ -432,7 +432,6 @@ def greedy_step(scores, prev_inds, last_ids, argmax_out, all_eos, step: int, eos
 
 # ----------------------------------------------------------------------------- inference blocks enqueued by one call (decode.cu)
 _WS = {}
-_HOSTPROF = False      # tools only: lets a host-overhead profile run the wrappers on CPU tensors against a stubbed library
 
 
 def _workspace(device, nbytes: int) -> torch.Tensor:
@@ -469,12 +468,14 @@ def mha_decode_step(x, x_op, kv_src, self_attention: bool, wptrs, *, dt: int, ep
     B, Lq, D = x.shape
     Lnew = Lq if self_attention else (0 if kv_src is None else kv_src.shape[1])
     cshape = kv_cache.shape
-    if (not x.is_cuda and not _HOSTPROF) or x.dtype is not torch.float32 or not x.is_contiguous() or not kv_cache.is_contiguous() or _DT.get(kv_cache.dtype) != dt:
+    if not x.is_cuda or not kv_cache.is_cuda or x.dtype is not torch.float32 or not x.is_contiguous() or not kv_cache.is_contiguous() or _DT.get(kv_cache.dtype) != dt:
         raise ValueError("mha_decode_step: x must be a contiguous fp32 CUDA tensor, the cache contiguous in the compute dtype")
     if cshape[0] != B or cshape[2] != h * (d_k + d_v) or length + Lnew > cshape[1]:
         raise ValueError(f"mha_decode_step: cache {tuple(cshape)} cannot take {length}+{Lnew} positions of batch {B}")
-    if kv_src is not None and not self_attention and (not kv_src.is_contiguous() or _DT.get(kv_src.dtype) != dt or kv_src.shape[0] != B):
-        raise ValueError("mha_decode_step: kv_src must be contiguous (B, Lnew, D) in the compute dtype")
+    if kv_src is not None and not self_attention and (not kv_src.is_cuda or not kv_src.is_contiguous() or _DT.get(kv_src.dtype) != dt
+                                                      or kv_src.shape[0] != B):
+        raise ValueError("mha_decode_step: kv_src must be a contiguous CUDA tensor (B, Lnew, D) in the compute dtype")
+    _need_cuda(x_op, mask)
     mkeep, mptr, sb, sh, sq = _mask_args(mask, B, h, Lq, length + Lnew)
     y = torch.empty_like(x)
     y16 = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if dt == L.BF16 else None
@@ -500,8 +501,9 @@ def pwff_infer(x, x_op, wptrs, *, dt: int, d_ff: int, eps: float):
     beta) of tensors the caller keeps alive.  Returns (y fp32, y bf16 | None)."""
     D = x.shape[-1]
     rows = x.numel() // D
-    if (not x.is_cuda and not _HOSTPROF) or x.dtype is not torch.float32 or not x.is_contiguous():
+    if not x.is_cuda or x.dtype is not torch.float32 or not x.is_contiguous():
         raise ValueError("pwff_infer: x must be a contiguous fp32 CUDA tensor")
+    _need_cuda(x_op)
     y = torch.empty_like(x)
     y16 = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if dt == L.BF16 else None
     if rows == 0:

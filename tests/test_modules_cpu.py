@@ -76,6 +76,19 @@ def test_decode_cache_states_stay_out_of_the_state_dict():
         assert layer.self_attn._is_stateful and layer.enc_attn._is_stateful and not layer.enc_attn.can_be_stateful
 
 
+def test_one_call_inference_wrappers_refuse_cpu_tensors():
+    """No CPU fallback and no bypass: the lean decode / feed-forward wrappers hand raw pointers to the library, so anything that is
+    not a CUDA tensor must be rejected before the call (north_star: CPU tensors -> error)."""
+    from openvivqa_b200 import ops
+    assert not hasattr(ops, "_HOSTPROF")
+    x = torch.zeros((2, 1, 64))
+    cache = torch.zeros((2, 4, 128))
+    with pytest.raises(ValueError):
+        ops.mha_decode_step(x, None, None, True, (0,) * 6, dt=0, eps=1e-5, h=4, d_k=16, d_v=16, kv_cache=cache, length=0, scale=0.25)
+    with pytest.raises(ValueError):
+        ops.pwff_infer(x, None, (0,) * 6, dt=0, d_ff=256, eps=1e-5)
+
+
 def test_compute_dtype_selection():
     assert ovqa.get_compute_dtype() in ("fp32", "bf16")
     with pytest.raises(ValueError):
