@@ -2,7 +2,7 @@
 
 Public surface:
   * modules:   ScaledDotProductAttention, AugmentedGeometryScaledDotProductAttention, MultiHeadAttention,
-               PositionWiseFeedForward, OcrPtrNet, DynamicPointerNetwork, FeatureEmbedding (vision front-end), META_ATTENTION,
+               PositionWiseFeedForward, OcrPtrNet, DynamicPointerNetwork, FeatureEmbedding (vision front-end), beam_select, META_ATTENTION,
                build_attention
   * install(): patch a reference checkout's registry / imported symbols so every model and YAML picks them up
   * ops / functional: the C-ABI wrappers and autograd blocks
@@ -10,7 +10,7 @@ The CUDA library (openvivqa_b200/libovqa_b200.so) is required; there is no CPU o
 """
 from .modules import (AugmentedGeometryScaledDotProductAttention, DynamicPointerNetwork, FeatureEmbedding, META_ATTENTION,  # noqa: F401
                       MultiHeadAttention, OcrPtrNet, PositionWiseFeedForward, ScaledDotProductAttention,
-                      StatefulModule, build_attention, get_compute_dtype, set_compute_dtype)
+                      StatefulModule, beam_select, build_attention, get_compute_dtype, set_compute_dtype)
 from .install import install, uninstall  # noqa: F401
 
 __version__ = "0.1.0"

@@ -178,6 +178,123 @@ static int launch_decode_attn(const DecodeAttn& a, cudaStream_t st) {
     return OVQA_OK;
 }
 
+// ----------------------------------------------------------------------------- beam selection: the k largest entries of every row
+// BeamSearch.select (beam_search.py:35-38) sorts all beam x vocabulary candidates of every sample and keeps the first `beam_size`.
+// Here: grid (chunks, rows); every thread keeps the k best of its strided share in registers (sorted insertion), the block merges the
+// 256 sorted lists by k rounds of a block-wide arg-max over the list heads; a second tiny launch merges the chunks' results the same way.
+// Order: descending value, NaN greatest (as torch.sort), equal values by ascending index (torch's order among ties is unspecified).
+constexpr int kTopkMax = 16, kTopkThreads = 256;
+
+__device__ __forceinline__ bool topk_before(float a, int64_t ia, float b, int64_t ib) {      // does (a, ia) come before (b, ib)?
+    const bool na = a != a, nb = b != b;
+    if (na != nb) return na;
+    if (!na && a != b) return a > b;
+    return ia < ib;
+}
+
+// block-wide selection of the k best among the threads' sorted lists (v[], ix[] of length k, sentinel index -1 = empty slot)
+template <int K>
+__device__ void topk_block_merge(float (&v)[K], int64_t (&ix)[K], int k, float* out_v, int64_t* out_i) {
+    __shared__ float s_v[kTopkThreads / 32];
+    __shared__ int64_t s_i[kTopkThreads / 32];
+    __shared__ int s_t[kTopkThreads / 32];
+    __shared__ int s_win;
+    int head = 0;
+    for (int r = 0; r < k; ++r) {
+        // candidate of this thread: its list head
+        float cv = 0.f; int64_t ci = -1; int ct = threadIdx.x;
+        if (head < k) {
+#pragma unroll
+            for (int j = 0; j < K; ++j) if (j == head) { cv = v[j]; ci = ix[j]; }
+        }
+        // warp arg-best
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, cv, o);
+            const int64_t oi = __shfl_xor_sync(0xffffffffu, ci, o);
+            const int ot = __shfl_xor_sync(0xffffffffu, ct, o);
+            const bool take = oi >= 0 && (ci < 0 || topk_before(ov, oi, cv, ci));
+            if (take) { cv = ov; ci = oi; ct = ot; }
+        }
+        if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = cv; s_i[threadIdx.x >> 5] = ci; s_t[threadIdx.x >> 5] = ct; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float bv = s_v[0]; int64_t bi = s_i[0]; int bt = s_t[0];
+            for (int w = 1; w < kTopkThreads / 32; ++w)
+                if (s_i[w] >= 0 && (bi < 0 || topk_before(s_v[w], s_i[w], bv, bi))) { bv = s_v[w]; bi = s_i[w]; bt = s_t[w]; }
+            out_v[r] = bv; out_i[r] = bi; s_win = bi >= 0 ? bt : -1;
+        }
+        __syncthreads();
+        if (s_win == (int)threadIdx.x) ++head;
+        __syncthreads();
+    }
+}
+
+template <int K>
+__device__ __forceinline__ void topk_insert(float (&v)[K], int64_t (&ix)[K], int k, float x, int64_t i) {
+    if (ix[k - 1] >= 0 && !topk_before(x, i, v[k - 1], ix[k - 1])) return;      // not better than the current k-th
+    // bubble up from the end (k is small)
+    float cv = x; int64_t ci = i;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        if (j < k) {
+            const bool first = ix[j] < 0 || topk_before(cv, ci, v[j], ix[j]);
+            if (first) { const float tv = v[j]; const int64_t ti = ix[j]; v[j] = cv; ix[j] = ci; cv = tv; ci = ti; }
+            if (ci < 0) break;
+        }
+    }
+}
+
+// phase 1: x [rows, n] (row pitch ldx); partial results [rows, chunks, k]
+template <int K>
+__global__ void __launch_bounds__(kTopkThreads) topk_partial_kernel(const float* __restrict__ x, int64_t n, int64_t ldx, int k, int chunks,
+                                                                    float* __restrict__ pv, int64_t* __restrict__ pi) {
+    const int64_t row = blockIdx.y;
+    const int chunk = blockIdx.x;
+    const int64_t per = (n + chunks - 1) / chunks, lo = chunk * per, hi = min(n, lo + per);
+    float v[K]; int64_t ix[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) { v[j] = 0.f; ix[j] = -1; }
+    const float* xr = x + row * ldx;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += kTopkThreads) topk_insert<K>(v, ix, k, __ldg(xr + i), i);
+    __shared__ float o_v[kTopkMax];
+    __shared__ int64_t o_i[kTopkMax];
+    topk_block_merge<K>(v, ix, k, o_v, o_i);
+    if ((int)threadIdx.x < k) {
+        pv[(row * chunks + chunk) * k + threadIdx.x] = o_v[threadIdx.x];
+        pi[(row * chunks + chunk) * k + threadIdx.x] = o_i[threadIdx.x];
+    }
+}
+
+// phase 2: merge the chunks' lists of a row (chunks * k <= kTopkThreads * K candidates)
+template <int K>
+__global__ void __launch_bounds__(kTopkThreads) topk_merge_kernel(const float* __restrict__ pv, const int64_t* __restrict__ pi, int k, int chunks,
+                                                                  float* __restrict__ out_v, int64_t* __restrict__ out_i) {
+    const int64_t row = blockIdx.x;
+    float v[K]; int64_t ix[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) { v[j] = 0.f; ix[j] = -1; }
+    const int total = chunks * k;
+    for (int c = threadIdx.x; c < total; c += kTopkThreads) {
+        const int64_t i = pi[row * total + c];
+        if (i >= 0) topk_insert<K>(v, ix, k, pv[row * total + c], i);
+    }
+    __shared__ float o_v[kTopkMax];
+    __shared__ int64_t o_i[kTopkMax];
+    topk_block_merge<K>(v, ix, k, o_v, o_i);
+    if ((int)threadIdx.x < k) { out_v[row * k + threadIdx.x] = o_v[threadIdx.x]; out_i[row * k + threadIdx.x] = o_i[threadIdx.x]; }
+}
+
+static inline int topk_chunks(int64_t rows, int64_t n) {
+    // enough blocks to fill the SMs, at least ~4 elements per thread and chunk
+    int64_t c = (2 * (int64_t)sm_count() + rows - 1) / (rows > 0 ? rows : 1);
+    const int64_t cmax = (n + 4 * kTopkThreads - 1) / (4 * kTopkThreads);
+    if (c > cmax) c = cmax;
+    if (c < 1) c = 1;
+    if (c > 64) c = 64;
+    return (int)c;
+}
+
 static inline int64_t up256(int64_t v) { return (v + 255) / 256 * 256; }
 
 }  // namespace ovqa
@@ -278,4 +395,29 @@ extern "C" int ovqa_pwff_infer(const float* x_f32, const void* x_op, int64_t row
     if ((rc = plain_gemm(ws_h, w2, ws_s, rows, D, d_ff, d_ff, d_ff, D, dtype, OVQA_F32, b2, 0, x_f32, D, stream))) return rc;
     return ovqa_layernorm_fwd(ws_s, nullptr, gamma, beta, nullptr, 0, y_f32, dtype == OVQA_BF16 ? y_op : nullptr, nullptr, nullptr, nullptr, rows,
                               D, eps, stream);
+}
+
+extern "C" int64_t ovqa_topk_rows_workspace_bytes(int64_t rows, int64_t n, int k) {
+    if (rows <= 0 || n <= 0 || k <= 0) return 0;
+    return up256(rows * topk_chunks(rows, n) * k * 4) + up256(rows * topk_chunks(rows, n) * k * 8);
+}
+
+extern "C" int ovqa_topk_rows(const float* x, int64_t rows, int64_t n, int64_t ldx, int k, float* out_val, int64_t* out_idx, void* workspace,
+                              int64_t workspace_bytes, void* stream) {
+    if (!x || !out_val || !out_idx || rows < 0 || n <= 0 || ldx < n || k <= 0) return OVQA_ERR_BAD_ARG;
+    if (k > kTopkMax || k > n) return OVQA_ERR_BAD_SHAPE;
+    if (rows == 0) return OVQA_OK;
+    if (!workspace || workspace_bytes < ovqa_topk_rows_workspace_bytes(rows, n, k)) return OVQA_ERR_BAD_ARG;
+    const int chunks = topk_chunks(rows, n);
+    float* pv = reinterpret_cast<float*>(workspace);
+    int64_t* pi = reinterpret_cast<int64_t*>(reinterpret_cast<char*>(workspace) + up256(rows * chunks * k * 4));
+    cudaStream_t st = (cudaStream_t)stream;
+    const dim3 grid((unsigned)chunks, (unsigned)rows);
+    if (k <= 8) topk_partial_kernel<8><<<grid, kTopkThreads, 0, st>>>(x, n, ldx, k, chunks, pv, pi);
+    else topk_partial_kernel<16><<<grid, kTopkThreads, 0, st>>>(x, n, ldx, k, chunks, pv, pi);
+    OVQA_LAUNCH_OK();
+    if (k <= 8) topk_merge_kernel<8><<<(unsigned)rows, kTopkThreads, 0, st>>>(pv, pi, k, chunks, out_val, out_idx);
+    else topk_merge_kernel<16><<<(unsigned)rows, kTopkThreads, 0, st>>>(pv, pi, k, chunks, out_val, out_idx);
+    OVQA_LAUNCH_OK();
+    return OVQA_OK;
 }

@@ -54,6 +54,12 @@ def install(compute_dtype: str | None = None, verbose: bool = False):
         _saved.setdefault(("vision_registry", "FeatureEmbedding"), vreg._obj_map.get("FeatureEmbedding"))
         vreg._obj_map["FeatureEmbedding"] = M.FeatureEmbedding
         classes["FeatureEmbedding"] = M.FeatureEmbedding
+    # beam selection: BeamSearch.select's full sort -> row-wise top-k (beam_search.py:35-38)
+    beam_mod = _maybe("models.modules.beam_search")
+    if beam_mod is not None and hasattr(beam_mod, "BeamSearch"):
+        _saved.setdefault(("beam_select", "select"), beam_mod.BeamSearch.select)
+        beam_mod.BeamSearch.select = M._beam_search_select
+        classes["BeamSearch.select"] = M._beam_search_select
     for name, mods in _REBIND.items():
         for modname in mods:
             mod = _maybe(modname)
@@ -74,6 +80,8 @@ def uninstall():
                 vreg._obj_map.pop(name, None)
             else:
                 vreg._obj_map[name] = obj
+        elif where == "beam_select":
+            sys.modules["models.modules.beam_search"].BeamSearch.select = obj
         elif where == "registry":
             reg = sys.modules["builders.attention_builder"].META_ATTENTION
             if obj is None:

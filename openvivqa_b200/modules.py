@@ -393,6 +393,23 @@ class PositionWiseFeedForward(nn.Module):
                              dropout=self.dropout_1.p, training=self.training, eps=self.layer_norm.eps)
 
 
+def beam_select(candidate_logprob: torch.Tensor, b_s: int, beam_size: int):
+    """``BeamSearch.select`` (beam_search.py:35-38) without the full sort: the ``beam_size`` best of the beam x vocabulary candidates of
+    every sample from the row-wise top-k kernel (csrc/decode.cu).  Returns (flat candidate indices (b_s, beam_size) int64, their
+    log-probabilities), as the reference does.  Under autograd (self-critical training calls beam search with gradients enabled) the
+    values are gathered from the input so they stay differentiable."""
+    flat = candidate_logprob.reshape(b_s, -1)
+    val, idx = ops.topk_rows(flat.detach().float(), beam_size)
+    if torch.is_grad_enabled() and flat.requires_grad:
+        val = torch.gather(flat, 1, idx)
+    return idx, val.to(candidate_logprob.dtype)
+
+
+def _beam_search_select(self, candidate_logprob):
+    """Bound over the reference's ``BeamSearch.select`` by ``install()``."""
+    return beam_select(candidate_logprob, self.b_s, self.beam_size)
+
+
 class FeatureEmbedding(nn.Module):
     """vision_embeddings.py:10-25 (``META_VISION_EMBEDDING``): ``dropout(gelu(proj(features)))`` and the padding mask
     of the all-zero region rows (models/utils.py:44-57).  Same parameter names (``proj.weight`` / ``proj.bias``) and config keys

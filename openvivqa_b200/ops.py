@@ -519,3 +519,23 @@ def pwff_infer(x, x_op, wptrs, *, dt: int, d_ff: int, eps: float):
     if rc:
         L.check(rc, "ovqa_pwff_infer")
     return y, y16
+
+
+def topk_rows(x: torch.Tensor, k: int):
+    """The k largest entries of every row of x (rows, n) fp32, descending: (values (rows, k) fp32, indices (rows, k) int64).
+    NaN sorts first (as torch.sort(descending=True)); equal values come in ascending index order."""
+    _need_cuda(x)
+    x = _rowmajor2d(x, "x")
+    if x.dtype != torch.float32:
+        raise ValueError("topk_rows: x must be fp32")
+    rows, n = x.shape
+    if not (1 <= k <= min(16, n)):
+        raise ValueError(f"topk_rows: k must be in 1..min(16, {n})")
+    val = torch.empty((rows, k), device=x.device, dtype=torch.float32)
+    idx = torch.empty((rows, k), device=x.device, dtype=torch.int64)
+    if rows == 0:
+        return val, idx
+    l = L.lib()
+    ws = _workspace(x.device, l.ovqa_topk_rows_workspace_bytes(rows, n, k))
+    L.check(l.ovqa_topk_rows(_p(x), rows, n, _ld(x), k, _p(val), _p(idx), _p(ws), ws.numel(), _stream()), "ovqa_topk_rows")
+    return val, idx

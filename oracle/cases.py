@@ -155,3 +155,16 @@ def dec_stepwise_inputs(x):
         if t == c["regather_at"]:
             cur = cur[perm]
     return per_step, perm
+
+
+# ----------------------------------------------------------------------------- beam selection (beam_search.py:35-38)
+BEAM_CASES = {"first_step": (3, 1, 37, 4), "later_step": (3, 4, 37, 4), "wide": (2, 5, 3000, 5)}     # (b_s, current beams, vocab, beam_size)
+
+
+def beam_inputs(name: str, seed: int = 53):
+    b_s, cur, V, beam = BEAM_CASES[name]
+    x = torch.log_softmax(torch.randn((b_s, cur, V), generator=S._gen(seed, name)) * 3.0, -1)
+    x = x + torch.randn((b_s, cur, 1), generator=S._gen(seed + 1, name))                  # running sequence log-probabilities
+    if cur > 1:
+        x[0, 1, 1:] = -999.0                                                              # a finished beam: beam_search.py:54-56
+    return x

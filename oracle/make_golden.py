@@ -231,12 +231,25 @@ def gen_decoder():
           (out["steps"][:, :c["regather_at"] + 1] - out["full"][:, :c["regather_at"] + 1]).abs().max().item())
 
 
+def gen_beam():
+    """BeamSearch.select (beam_search.py:35-38) on seeded candidate tables, incl. one with a finished beam's -999 entries."""
+    from models.modules.beam_search import BeamSearch
+
+    out = {}
+    for name, (b_s, cur, V, beam) in C.BEAM_CASES.items():
+        bs = BeamSearch(model=None, b_s=b_s, max_len=4, eos_idx=2, beam_size=beam, device="cpu")
+        idx, logprob = bs.select(C.beam_inputs(name))
+        out[name] = dict(idx=idx, logprob=logprob)
+    torch.save(out, os.path.join(OUT, "beam.pt"))
+    print("beam.pt", {k: tuple(v["idx"].shape) for k, v in out.items()})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     RL.load()
     torch.manual_seed(0)
     torch.set_num_threads(min(8, os.cpu_count() or 1))
-    which = sys.argv[1:] or ["attention", "geometry", "masks", "encoders", "mcan", "m4c", "decoder"]
+    which = sys.argv[1:] or ["attention", "geometry", "masks", "encoders", "mcan", "m4c", "decoder", "beam"]
     for w in which:
         globals()["gen_" + w]()
 

@@ -212,6 +212,13 @@ def decoder_layer_stateful(p: Params, steps, keys, values, step_masks, enc_mask,
     return outs
 
 
+def beam_select(candidate_logprob: torch.Tensor, b_s: int, beam_size: int):
+    """BeamSearch.select — beam_search.py:35-38: all candidates of a sample sorted by descending log-probability, the first
+    ``beam_size`` kept.  Returns (flat candidate indices, their log-probabilities), both (b_s, beam_size)."""
+    logprob, idx = torch.sort(candidate_logprob.view(b_s, -1), -1, descending=True)
+    return idx[:, :beam_size], logprob[:, :beam_size]
+
+
 # --------------------------------------------------------------------------- encoders (models/modules/encoders.py)
 def _acfg(cfg) -> dict:
     return dict(h=cfg["h"], d_k=cfg["d_k"], d_v=cfg["d_v"], dropout=cfg.get("dropout", 0.0),

@@ -741,6 +741,32 @@ def test_encoder_kv_cache_follows_in_place_updates(dev):
     assert abs_err(y1, y0) > 10 * BF16_ABS
 
 
+# ------------------------------------------------------------------------------------------------ beam selection
+@pytest.mark.parametrize("name", list(C.BEAM_CASES))
+def test_beam_select_matches_reference(dev, golden, name):
+    """BeamSearch.select (beam_search.py:35-38): identical candidate indices and log-probabilities (index work: bit-exact)."""
+    b_s, cur, V, beam = C.BEAM_CASES[name]
+    idx, logprob = ovqa.beam_select(C.beam_inputs(name).to(dev), b_s, beam)
+    g = golden("beam")[name]
+    assert torch.equal(idx.cpu(), g["idx"]) and torch.equal(logprob.cpu(), g["logprob"])
+
+
+@pytest.mark.parametrize("rows,n,k", [(1, 5, 5), (7, 1000, 1), (64, 50000, 5), (3, 200000, 16), (300, 33, 8)])
+def test_topk_rows_against_sort(dev, rows, n, k):
+    torch.manual_seed(rows * 1000 + k)
+    x = torch.randn((rows, n), device=dev)
+    x[0, n // 2] = float("nan")                          # NaN sorts first, as torch.sort(descending=True)
+    x[-1, : min(n, 3)] = 7.5                             # ties: ascending index
+    val, idx = ops.topk_rows(x, k)
+    ref_val, ref_idx = torch.sort(x, dim=-1, descending=True, stable=True)
+    assert torch.equal(idx, ref_idx[:, :k])
+    assert torch.equal(torch.nan_to_num(val, nan=123.0), torch.nan_to_num(ref_val[:, :k], nan=123.0))
+    # a strided view (row pitch larger than n)
+    big = torch.randn((rows, n + 8), device=dev)
+    v2, i2 = ops.topk_rows(big[:, :n], k)
+    assert torch.equal(i2, torch.sort(big[:, :n], dim=-1, descending=True, stable=True)[1][:, :k])
+
+
 # ------------------------------------------------------------------------------------------------ empty inputs
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
 def test_empty_inputs(dev, dt):

@@ -105,8 +105,11 @@ def test_install_into_the_reference_checkout_and_reference_state_dict_loads():
     from builders.attention_builder import META_ATTENTION
 
     ref_mha = A.MultiHeadAttention(RL.attention_cfg())
+    import models.modules.beam_search as BS
+    ref_select = BS.BeamSearch.select
     try:
         ovqa.install()
+        assert BS.BeamSearch.select is not ref_select and BS.BeamSearch.select.__module__.startswith("openvivqa_b200")
         assert META_ATTENTION.get("ScaledDotProductAttention") is ovqa.ScaledDotProductAttention
         assert E.MultiHeadAttention.__module__.startswith("openvivqa_b200")
         enc = E.Encoder(RL.NS(D_MODEL=512, LAYERS=1, SELF_ATTENTION=RL.attention_cfg()))   # the reference's own Encoder
@@ -121,6 +124,7 @@ def test_install_into_the_reference_checkout_and_reference_state_dict_loads():
     finally:
         ovqa.uninstall()
     assert E.MultiHeadAttention is A.MultiHeadAttention
+    assert BS.BeamSearch.select is ref_select
     assert META_ATTENTION.get("ScaledDotProductAttention").__module__ == "models.modules.attentions"
 
 

@@ -169,3 +169,11 @@ def test_decoder_layer_stateless_and_stepwise(golden):
     k = c["regather_at"] + 1
     st = R.decoder_layer_stateful(p, [x["x"][:, t:t + 1] for t in range(k)], x["enc"], x["enc"], x["step_masks"][:k], x["enc_mask"], cfg)
     _close(torch.cat(st, 1), g["steps"][:, :k])
+
+
+@pytest.mark.parametrize("name", list(C.BEAM_CASES))
+def test_beam_select(golden, name):
+    b_s, cur, V, beam = C.BEAM_CASES[name]
+    idx, logprob = R.beam_select(C.beam_inputs(name), b_s, beam)
+    g = golden("beam")[name]
+    assert torch.equal(idx, g["idx"]) and torch.equal(logprob, g["logprob"])
