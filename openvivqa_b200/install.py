@@ -60,6 +60,9 @@ def install(compute_dtype: str | None = None, verbose: bool = False):
         _saved.setdefault(("beam_select", "select"), beam_mod.BeamSearch.select)
         beam_mod.BeamSearch.select = M._beam_search_select
         classes["BeamSearch.select"] = M._beam_search_select
+        # the re-gather closure records its input -> output tensors, so encoder attention can keep its projected keys across beams
+        _saved.setdefault(("beam_expand", "_expand_state"), beam_mod.BeamSearch._expand_state)
+        beam_mod.BeamSearch._expand_state = M._beam_search_expand_state(_saved[("beam_expand", "_expand_state")])
     for name, mods in _REBIND.items():
         for modname in mods:
             mod = _maybe(modname)
@@ -82,6 +85,8 @@ def uninstall():
                 vreg._obj_map[name] = obj
         elif where == "beam_select":
             sys.modules["models.modules.beam_search"].BeamSearch.select = obj
+        elif where == "beam_expand":
+            sys.modules["models.modules.beam_search"].BeamSearch._expand_state = obj
         elif where == "registry":
             reg = sys.modules["builders.attention_builder"].META_ATTENTION
             if obj is None:

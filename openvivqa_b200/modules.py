@@ -48,6 +48,29 @@ def _mode_of(module) -> str:
     return module.compute_dtype or _default_mode
 
 
+DECODE_MAX_QUERY_ROWS = 16   # the one-warp-per-(row, head) decode kernel is for a handful of query rows; longer blocks use the tiled cores
+
+
+def tracked_regather(fn):
+    """Wrap a state re-gather function (``BeamSearch._expand_state``'s closure, beam_search.py:19-33) so that it remembers which
+    output tensor it produced from which input tensor during one ``apply_to_states`` sweep.  The sweep transforms the model's own
+    states (e.g. ``encoder_features``, base_transformer.py:17) and, with the SAME function, the projected-K/V caches of the attention
+    blocks below it; the record lets a block prove at its next call that the keys it is handed ARE ``fn(previous keys)`` — so its
+    re-gathered projection is still theirs — by object identity, without comparing contents."""
+    if hasattr(fn, "_ovqa_memo"):
+        return fn
+    memo = {}
+
+    def tracked(s):
+        out = fn(s)
+        if isinstance(s, torch.Tensor) and isinstance(out, torch.Tensor):
+            memo[id(s)] = (s, out)                     # (the input is held so that its id stays unique while the record lives)
+        return out
+
+    tracked._ovqa_memo = memo
+    return tracked
+
+
 class StatefulModule(nn.Module):
     """Minimal stand-in for the reference's ``containers.Module`` (models/modules/containers.py:4-70): buffers
     registered as decode "states" that ``statefulness(batch_size)`` expands per batch and resets afterwards.
@@ -75,6 +98,7 @@ class StatefulModule(nn.Module):
             yield from m.states()
 
     def apply_to_states(self, fn):
+        fn = tracked_regather(fn)
         for n in self._state_names:
             self._buffers[n] = fn(self._buffers[n])
         for m in self._children_stateful():
@@ -258,18 +282,52 @@ def make_multi_head_attention(base=StatefulModule, builder=None):
                     core = self.attention
                     self.register_state("running_kv_proj", torch.zeros((0, core.h * (core.d_k + core.d_v))))
                     self._non_persistent_buffers_set.add("running_kv_proj")
+            elif isinstance(self.attention, ScaledDotProductAttention):
+                # encoder attention inside a decode session: the encoder keys / values are projected once; the projection is a state too,
+                # so a beam re-gather of the model's ``encoder_features`` (base_transformer.py:17) re-gathers it the same way
+                core = self.attention
+                self.register_state("running_enc_kv_proj", torch.zeros((0, core.h * (core.d_k + core.d_v))))
+                self._non_persistent_buffers_set.add("running_enc_kv_proj")
             self._kv_len = 0
-            self._enc_kv = None          # (tag, [K|V], keys, values): encoder keys / values projected once per stateful session
+            self._enc_kv = None          # (tag, keys, values) of the tensors whose projection ``running_enc_kv_proj`` holds
+            self._regather_memo = None   # record of the last ``apply_to_states`` sweep (tracked_regather)
             self._session = None         # per-session decode plan: None = not decided yet, False = reference bookkeeping
             self.compute_dtype = getattr(config, "COMPUTE_DTYPE", None)
 
         def enable_statefulness(self, batch_size):
             super().enable_statefulness(batch_size)
-            self._kv_len, self._enc_kv, self._session = 0, None, None
+            self._kv_len, self._enc_kv, self._session, self._regather_memo = 0, None, None, None
 
         def disable_statefulness(self):
             super().disable_statefulness()
-            self._kv_len, self._enc_kv, self._session = 0, None, None
+            self._kv_len, self._enc_kv, self._session, self._regather_memo = 0, None, None, None
+
+        def apply_to_states(self, fn):
+            super().apply_to_states(fn)                  # (re-gathers running_kv_proj / running_enc_kv_proj with everything else)
+            if not self.can_be_stateful:
+                self._regather_memo = getattr(fn, "_ovqa_memo", None)
+
+        def _encoder_projection(self, sess, keys, values):
+            """[K | V] of the encoder keys / values, projected once per session.  Still valid when the tensors are the very objects
+            seen last time (and unmodified), or when they are what the last ``apply_to_states`` sweep made of those objects — the
+            sweep re-gathered the projection with the same function.  Anything else: project again."""
+            tag = (keys.data_ptr(), keys._version, keys.shape, values.data_ptr(), values._version)
+            enc, memo = self._enc_kv, self._regather_memo
+            self._regather_memo = None
+            if enc is not None and enc[0] == tag:
+                return self._buffers["running_enc_kv_proj"]
+            if enc is not None and memo is not None:
+                rk, rv = memo.get(id(enc[1])), memo.get(id(enc[2]))
+                if rk is not None and rv is not None and rk[0] is enc[1] and rv[0] is enc[2] and rk[1] is keys and rv[1] is values \
+                        and self._buffers["running_enc_kv_proj"].shape[:2] == keys.shape[:2]:
+                    self._enc_kv = (tag, keys, values)
+                    cache = self._buffers["running_enc_kv_proj"]
+                    if not cache.is_contiguous():
+                        self._buffers["running_enc_kv_proj"] = cache = cache.contiguous()
+                    return cache
+            self._buffers["running_enc_kv_proj"] = cache = Fn.project_kv_fused(keys, values, **sess["kv"]).contiguous()
+            self._enc_kv = (tag, keys, values)               # (the tensors are held so that the tag stays unique)
+            return cache
 
         def _open_session(self, core):
             self._session = self._open_decode_session(core)
@@ -315,11 +373,9 @@ def make_multi_head_attention(base=StatefulModule, builder=None):
                         length = need
                 self._kv_len = need
             else:
-                tag = (keys.data_ptr(), keys._version, keys.shape, values.data_ptr(), values._version)
-                enc = self._enc_kv
-                if enc is None or enc[0] != tag:
-                    self._enc_kv = enc = (tag, Fn.project_kv_fused(keys, values, **sess["kv"]), keys, values)   # (tensors held: the tag stays unique)
-                cache, length = enc[1], keys.shape[1]
+                if queries.shape[1] > DECODE_MAX_QUERY_ROWS:
+                    return None                                                      # a long block (an encoder run inside the session): tiled cores
+                cache, length = self._encoder_projection(sess, keys, values), keys.shape[1]
             return Fn.mha_decode_block(sess["plan"], queries, kv_src, self_att, cache, length, attention_mask, h=sess["h"], d_k=sess["d_k"],
                                        d_v=sess["d_v"], eps=sess["eps"])
 
@@ -333,6 +389,8 @@ def make_multi_head_attention(base=StatefulModule, builder=None):
                     self._session is not None or self._open_session(core)):
                 out = self._decode_fast_path(self._session, queries, keys, values, attention_mask)
             else:
+                out = None
+            if out is None and isinstance(core, ScaledDotProductAttention):
                 if self.can_be_stateful and self._is_stateful:
                     if self._kv_len != 0:
                         raise RuntimeError("MultiHeadAttention: a stateful decode may not switch between no_grad and grad mode half-way")
@@ -403,6 +461,13 @@ def beam_select(candidate_logprob: torch.Tensor, b_s: int, beam_size: int):
     if torch.is_grad_enabled() and flat.requires_grad:
         val = torch.gather(flat, 1, idx)
     return idx, val.to(candidate_logprob.dtype)
+
+
+def _beam_search_expand_state(orig):
+    """``BeamSearch._expand_state`` (beam_search.py:19-33) returning a tracked re-gather function (see ``tracked_regather``)."""
+    def _expand_state(self, selected_beam, cur_beam_size):
+        return tracked_regather(orig(self, selected_beam, cur_beam_size))
+    return _expand_state
 
 
 def _beam_search_select(self, candidate_logprob):

@@ -720,6 +720,61 @@ def test_pwff_inference_call_matches_the_block(dev, mode):
         assert abs_err(m(x), y_block) > 1e-3             # training-mode dropout still applies under no_grad
 
 
+def test_encoder_projection_follows_beam_regather(dev, monkeypatch):
+    """Beam search re-gathers the model's encoder features AND the attention blocks' states with one function per step
+    (beam_search.py:19-33, containers.py:26-31).  The projected encoder keys must be re-gathered, not re-projected — and must be
+    re-projected whenever the keys are NOT provably that function's output."""
+    torch.manual_seed(0)
+    layer = H.DecoderLayer(H.NS(SELF_ATTENTION=H.attention_cfg(128, 4, d_ff=256, stateful=True, compute_dtype="bf16"),
+                                ENC_ATTENTION=H.attention_cfg(128, 4, d_ff=256, compute_dtype="bf16"))).to(dev).eval()
+    calls = []
+    real = Fn.project_kv_fused
+    monkeypatch.setattr(Fn, "project_kv_fused", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+    B, beam, N = 2, 3, 9
+    enc = torch.randn((B, N, 128), device=dev)
+    xs = [torch.randn((B * beam, 1, 128), device=dev) for _ in range(4)]
+
+    class Model(ovqa.StatefulModule):                      # the owner of ``encoder_features``, as base_transformer.py:17
+        def __init__(self):
+            super().__init__()
+            self.layer = layer
+            self.register_state("encoder_features", None)
+
+    model = Model()
+    with torch.no_grad():
+        with model.statefulness(B):
+            model.encoder_features = enc
+            expand = lambda s: s.repeat_interleave(beam, 0)                         # step 0: every sample fans out into its beams
+            perm = torch.tensor([1, 0, 2, 5, 4, 3], device=dev)
+            outs, keys_seen = [], []
+            x0 = torch.randn((B, 1, 128), device=dev)
+            outs.append(layer(x0, model.encoder_features, model.encoder_features, None, None))
+            model.apply_to_states(expand)
+            for t, x in enumerate(xs):
+                keys_seen.append(model.encoder_features)
+                outs.append(layer(x, model.encoder_features, model.encoder_features, None, None))
+                model.apply_to_states(lambda s: s[perm])
+            assert len(calls) == 1                                                    # projected once for the whole search
+            # keys that did NOT come out of the sweep (same shape, other contents): projected again
+            other = torch.randn_like(model.encoder_features)
+            y_other = layer(xs[0], other, other, None, None)
+            assert len(calls) == 2
+        # reference bookkeeping on the same inputs (grad mode: no caches) gives the same numbers
+        ref_layer_out = []
+    with layer.statefulness(B):
+        with torch.enable_grad():
+            r0 = layer(x0, enc, enc, None, None)
+            layer.apply_to_states(expand)
+            e = expand(enc)
+            for t, x in enumerate(xs):
+                ref_layer_out.append(layer(x, e, e, None, None))
+                layer.apply_to_states(lambda s: s[perm])
+                e = e[perm]
+    assert abs_err(outs[0], r0) <= BF16_ABS
+    for a, b in zip(outs[1:], ref_layer_out):
+        assert abs_err(a, b) <= BF16_ABS
+
+
 def test_encoder_kv_cache_follows_in_place_updates(dev):
     """The once-per-session projection of the encoder keys is keyed on the tensor's identity AND version."""
     torch.manual_seed(0)
