@@ -280,13 +280,15 @@ def make_multi_head_attention(base=StatefulModule, builder=None):
                     # (inference fast path below).  Registered as a state so that beam search re-gathers it with the rest
                     # (beam_search.py:19-33), but kept out of the state_dict: the reference's checkpoints do not have it.
                     core = self.attention
-                    self.register_state("running_kv_proj", torch.zeros((0, core.h * (core.d_k + core.d_v))))
+                    # (one placeholder row, not zero: the reference's re-gather closure cannot reshape an EMPTY state — `view(-1, …)`
+                    # of zero elements is ambiguous, beam_search.py:31)
+                    self.register_state("running_kv_proj", torch.zeros((1, core.h * (core.d_k + core.d_v))))
                     self._non_persistent_buffers_set.add("running_kv_proj")
             elif isinstance(self.attention, ScaledDotProductAttention):
                 # encoder attention inside a decode session: the encoder keys / values are projected once; the projection is a state too,
                 # so a beam re-gather of the model's ``encoder_features`` (base_transformer.py:17) re-gathers it the same way
                 core = self.attention
-                self.register_state("running_enc_kv_proj", torch.zeros((0, core.h * (core.d_k + core.d_v))))
+                self.register_state("running_enc_kv_proj", torch.zeros((1, core.h * (core.d_k + core.d_v))))      # (placeholder row, as above)
                 self._non_persistent_buffers_set.add("running_enc_kv_proj")
             self._kv_len = 0
             self._enc_kv = None          # (tag, keys, values) of the tensors whose projection ``running_enc_kv_proj`` holds
@@ -354,6 +356,10 @@ def make_multi_head_attention(base=StatefulModule, builder=None):
             decode does O(T) instead of O(T^2) projection work.  Same outputs: fc_k / fc_v act row by row."""
             kv_src, self_att = None, False
             if sess["stateful"]:
+                if self._kv_len == 0 and self._buffers["running_keys"].shape[1] == 0:
+                    # the raw running keys / values stay unused on this path; give the states one element per row so that the
+                    # reference's re-gather closure (beam_search.py:19-33) can still reshape them
+                    self._buffers["running_keys"] = self._buffers["running_values"] = queries.new_zeros((queries.shape[0], 1, 1))
                 need = self._kv_len + keys.shape[1]
                 cache = self._buffers["running_kv_proj"]
                 if cache.shape[1] < need or cache.dtype != sess["cdt"]:              # grow geometrically: amortised O(1) copies per step

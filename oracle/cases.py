@@ -168,3 +168,13 @@ def beam_inputs(name: str, seed: int = 53):
     if cur > 1:
         x[0, 1, 1:] = -999.0                                                              # a finished beam: beam_search.py:54-56
     return x
+
+
+# ----------------------------------------------------------------------------- beam search over a stateful decoder (base_transformer.py:30-54)
+GEN_CASE = dict(B=3, N=7, D=64, h=4, d_ff=128, layers=2, vocab=23, T=6, beam=3, eos=10)    # eos: a token these weights emit early
+
+
+def gen_inputs(seed: int = 61):
+    c = GEN_CASE
+    enc = S.padded_features(c["B"], c["N"], c["D"], seed, min_valid=3, relu_like=False)
+    return dict(enc=enc, enc_mask=R.padding_mask(enc, 0))

@@ -244,12 +244,48 @@ def gen_beam():
     print("beam.pt", {k: tuple(v["idx"].shape) for k, v in out.items()})
 
 
+def gen_generative():
+    """The reference's own beam search (BaseTransformer.beam_search / step, base_transformer.py:30-54; BeamSearch, beam_search.py;
+    Decoder, decoders.py:28-76) over a small stateful decoder: token sequences and their log-probabilities."""
+    import models.modules.decoders as Dm
+    from models.base_transformer import BaseTransformer
+
+    c = C.GEN_CASE
+    att = lambda st: RL.attention_cfg(c["D"], c["h"], c["D"] // c["h"], c["D"] // c["h"], d_ff=c["d_ff"], stateful=st)
+    cfg = RL.NS(D_MODEL=c["D"], LAYERS=c["layers"], ATTENTION=RL.NS(SELF_ATTENTION=att(True), ENC_ATTENTION=att(False)),
+                TEXT_EMBEDDING=RL.NS(ARCHITECTURE="UsualEmbedding", D_MODEL=c["D"], WORD_EMBEDDING=None, D_EMBEDDING=c["D"], DROPOUT=0.1))
+
+    class Captioner(BaseTransformer):
+        def __init__(self, config, vocab):
+            super().__init__(config, vocab)
+            self.device = "cpu"
+            self.decoder = Dm.Decoder(config, vocab)
+
+        def encoder_forward(self, feats):
+            return feats["enc"], feats["enc_mask"]
+
+    m = Captioner(cfg, RL.StubVocab(c["vocab"], max_answer_length=c["T"])).eval()
+    m.eos_idx = c["eos"]                       # (so that finished beams — beam_search.py:50-56 — occur with these seeded weights)
+    spec = _load(m)
+    x = C.gen_inputs()
+    out = dict(spec=spec)
+    with torch.no_grad():
+        for beam in (1, c["beam"]):
+            tokens, logp = m.beam_search(x, batch_size=c["B"], beam_size=beam, out_size=1)
+            out[f"beam{beam}"] = dict(tokens=tokens, logp=logp)
+        # the decoder as a whole-sequence scorer (training-time call, decoders.py:47-76) on the beam-3 result
+        toks = torch.cat([torch.full((c["B"], 1), 1, dtype=torch.long), out[f"beam{c['beam']}"]["tokens"][:, :-1]], 1)
+        out["teacher_forced"] = m.decoder(toks, x["enc"], x["enc_mask"])
+    torch.save(out, os.path.join(OUT, "generative.pt"))
+    print("generative.pt", out["beam1"]["tokens"].tolist(), out[f"beam{c['beam']}"]["tokens"].tolist())
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     RL.load()
     torch.manual_seed(0)
     torch.set_num_threads(min(8, os.cpu_count() or 1))
-    which = sys.argv[1:] or ["attention", "geometry", "masks", "encoders", "mcan", "m4c", "decoder", "beam"]
+    which = sys.argv[1:] or ["attention", "geometry", "masks", "encoders", "mcan", "m4c", "decoder", "beam", "generative"]
     for w in which:
         globals()["gen_" + w]()
 

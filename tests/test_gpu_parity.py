@@ -660,9 +660,10 @@ def test_decoder_layer_stepwise_with_kv_cache(dev, golden, mode):
             if grad:      # reference bookkeeping: raw keys accumulate, nothing cached
                 assert sa.running_keys.shape == (c["B"], c["T"], c["D"]) and sa._kv_len == 0 and layer.enc_attn._enc_kv is None
             else:         # inference: projected rows accumulate, encoder keys projected once per tensor
-                assert sa._kv_len == c["T"] and sa.running_kv_proj.shape[0] == c["B"] and sa.running_keys.shape[1] == 0
+                assert sa._kv_len == c["T"] and sa.running_kv_proj.shape[0] == c["B"] and sa.running_keys.shape[1:] == (1, 1)
                 assert layer.enc_attn._enc_kv is not None
-        assert layer.self_attn.running_kv_proj.shape == (0, 2 * c["D"]) and layer.self_attn._kv_len == 0 and layer.enc_attn._enc_kv is None
+        assert layer.self_attn.running_kv_proj.shape == (1, 2 * c["D"]) and layer.self_attn._kv_len == 0 and layer.enc_attn._enc_kv is None
+        assert layer.self_attn.running_keys.shape == (0, c["D"])
         return torch.cat(outs, 1)
 
     cached, recomputed = run(False), run(True)
@@ -820,6 +821,59 @@ def test_topk_rows_against_sort(dev, rows, n, k):
     big = torch.randn((rows, n + 8), device=dev)
     v2, i2 = ops.topk_rows(big[:, :n], k)
     assert torch.equal(i2, torch.sort(big[:, :n], dim=-1, descending=True, stable=True)[1][:, :k])
+
+
+# ------------------------------------------------------------------------------------------------ beam search end to end
+def _captioner(mode, dev, g):
+    c = C.GEN_CASE
+    att = lambda st: H.attention_cfg(c["D"], c["h"], d_ff=c["d_ff"], stateful=st, compute_dtype=mode)
+    cfg = H.NS(D_MODEL=c["D"], LAYERS=c["layers"], ATTENTION=H.NS(SELF_ATTENTION=att(True), ENC_ATTENTION=att(False)))
+    m = H.Captioner(cfg, H.StubVocab(c["vocab"], max_answer_length=c["T"]))
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items() if v.dtype.is_floating_point] == g["spec"]
+    m.load_state_dict(S.synth_params(g["spec"], 0), strict=False)
+    m.eos_idx = c["eos"]
+    return m.to(dev).eval()
+
+
+@pytest.mark.parametrize("beam", [1, C.GEN_CASE["beam"]])
+def test_beam_search_token_sequences_match_the_reference(dev, golden, beam, monkeypatch):
+    """The reference's beam search over a stateful decoder (base_transformer.py:30-54, beam_search.py, decoders.py:28-76; golden
+    vectors made by running it on CPU) against the same search through the decode path: projected-K/V caches, one-call blocks,
+    top-k selection, provenance-tracked re-gathers.  fp32: IDENTICAL token sequences, log-probabilities to 1e-4."""
+    g, c = golden("generative"), C.GEN_CASE
+    x = {k: v.to(dev) for k, v in C.gen_inputs().items()}
+    m = _captioner("fp32", dev, g)
+    calls = []
+    real = Fn.project_kv_fused
+    monkeypatch.setattr(Fn, "project_kv_fused", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+    with torch.no_grad():
+        tokens, logp = m.beam_search(x["enc"], x["enc_mask"], c["B"], beam)
+    assert torch.equal(tokens.cpu(), g[f"beam{beam}"]["tokens"])
+    assert rel_err(logp, g[f"beam{beam}"]["logp"]) <= FP32_REL
+    assert len(calls) == c["layers"]                       # the encoder output was projected once per layer for the whole search
+    # with gradients enabled (self-critical training) the reference's bookkeeping runs instead: same sequences
+    tokens_g, logp_g = m.beam_search(x["enc"], x["enc_mask"], c["B"], beam)
+    assert torch.equal(tokens_g.cpu(), g[f"beam{beam}"]["tokens"]) and logp_g.requires_grad
+    assert rel_err(logp_g, g[f"beam{beam}"]["logp"]) <= FP32_REL
+    # bf16: same machinery; the sequences may legitimately differ where two continuations are within bf16 noise, the scores may not drift
+    mb = _captioner("bf16", dev, g)
+    with torch.no_grad():
+        tb, lb = mb.beam_search(x["enc"], x["enc_mask"], c["B"], beam)
+    same = (tb.cpu() == g[f"beam{beam}"]["tokens"]).all(-1)
+    assert tb.shape == (c["B"], c["T"]) and torch.isfinite(lb).all()
+    if same.any():
+        assert abs_err(lb.cpu()[same], g[f"beam{beam}"]["logp"][same]) <= 5e-2
+
+
+def test_decoder_whole_sequence_scoring(dev, golden):
+    """decoders.py:47-76 as the training-time scorer (teacher forcing, causal + padding mask) — the stateless twin of the search."""
+    g, c = golden("generative"), C.GEN_CASE
+    x = {k: v.to(dev) for k, v in C.gen_inputs().items()}
+    toks = torch.cat([torch.full((c["B"], 1), 1, dtype=torch.long), g[f"beam{c['beam']}"]["tokens"][:, :-1]], 1).to(dev)
+    for mode in ("fp32", "bf16"):
+        m = _captioner(mode, dev, g)
+        with torch.no_grad():
+            check(m.decoder(toks, x["enc"], x["enc_mask"]), g["teacher_forced"], mode, f"decoder scoring {mode}", bf16_abs=5e-2)
 
 
 # ------------------------------------------------------------------------------------------------ empty inputs

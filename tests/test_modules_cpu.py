@@ -68,9 +68,9 @@ def test_decode_cache_states_stay_out_of_the_state_dict():
     assert set(k for k in m.state_dict() if "running" in k) == {"running_keys", "running_values"}
     assert len(list(m.states())) == 3
     with m.statefulness(2):
-        assert m.running_kv_proj.shape == (2, 0, 1024)
+        assert m.running_kv_proj.shape == (2, 1, 1024)
         m.apply_to_states(lambda s: s[torch.tensor([1, 0])])
-    assert m.running_kv_proj.shape == (0, 1024) and m._enc_kv is None and m._kv_len == 0
+    assert m.running_kv_proj.shape == (1, 1024) and m._enc_kv is None and m._kv_len == 0
     layer = H.DecoderLayer(H.NS(SELF_ATTENTION=H.attention_cfg(stateful=True), ENC_ATTENTION=H.attention_cfg()))
     with layer.statefulness(2):
         assert layer.self_attn._is_stateful and layer.enc_attn._is_stateful and not layer.enc_attn.can_be_stateful

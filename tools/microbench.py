@@ -260,6 +260,32 @@ def bench_decode():
          speedup_vs_torch_fp32=t32 / t_cache, speedup_vs_torch_bf16=t16 / t_cache, max_abs_diff_vs_torch_fp32=(a - b).abs().max().item())
 
 
+def bench_beam_search():
+    """The whole search as the reference drives it (base_transformer.py:30-54 + beam_search.py): 64 samples x 5 beams, 20 steps, 3 decoder
+    layers, 100 encoder regions, 10 000-word vocabulary; decode path on / off (off = the reference's bookkeeping on the same kernels:
+    raw running keys re-projected every step, encoder keys re-projected every step)."""
+    from openvivqa_b200 import modules as M
+    B, beam, T, N, D, V = 64, 5, 20, 100, 512, 10000
+    att = lambda st: H.attention_cfg(D, 8, d_ff=2048, dropout=0.0, stateful=st, compute_dtype="bf16")
+    cfg = H.NS(D_MODEL=D, LAYERS=3, ATTENTION=H.NS(SELF_ATTENTION=att(True), ENC_ATTENTION=att(False)))
+    m = H.Captioner(cfg, H.StubVocab(V, max_answer_length=T)).to(dev).eval()
+    m.eos_idx = -1                                         # never finishes: every step does full work
+    enc = torch.randn((B, N, D), device=dev)
+    mask = torch.zeros((B, 1, 1, N), device=dev)
+    mask[..., 80:] = -10e4
+    run = lambda: m.beam_search(enc, mask, B, beam)
+    with torch.no_grad():
+        t_on = timeit(run, iters=5, warmup=2)
+        M.DECODE_KV_CACHE = False
+        t_off = timeit(run, iters=5, warmup=2)
+        M.DECODE_KV_CACHE = True
+        cand = torch.randn((B, beam * V), device=dev)
+        t_topk = timeit(lambda: ops.topk_rows(cand, beam), iters=20, warmup=3)
+        t_sort = timeit(lambda: torch.sort(cand, -1, descending=True), iters=20, warmup=3)
+    emit(kind="beam_search_3_layers", samples=B, beam=beam, steps=T, regions=N, D=D, vocab=V, decode_path_us=t_on, reference_bookkeeping_us=t_off,
+         speedup=t_off / t_on, samples_per_s=B / t_on * 1e6, select_topk_us=t_topk, select_sort_us=t_sort)
+
+
 def bench_gemm_epilogues():
     """The fused epilogues of the training step at the vision-branch shapes (B*L = 25600)."""
     M, D, F_ = 25600, 512, 2048
@@ -292,4 +318,4 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "epi", "sdpa", "ln", "mha"]
     emit(kind="meta", gpu=torch.cuda.get_device_name(0), peaks=PEAKS)
     for w in which:
-        {"gemm": bench_gemm, "wgrad": bench_wgrad_split, "epi": bench_gemm_epilogues, "sdpa": bench_sdpa, "ln": bench_ln, "mha": bench_mha, "decode": bench_decode}[w]()
+        {"gemm": bench_gemm, "wgrad": bench_wgrad_split, "epi": bench_gemm_epilogues, "sdpa": bench_sdpa, "ln": bench_ln, "mha": bench_mha, "decode": bench_decode, "beam": bench_beam_search}[w]()
