@@ -270,7 +270,8 @@ int ovqa_pwff_infer(const float* x_f32, const void* x_op, int64_t rows, int64_t 
 
 /* Beam selection: the k largest entries of every row, in descending order (NaN greatest, equal values by ascending index).
  *   replaces: BeamSearch.select (beam_search.py:35-38: torch.sort over all beam x vocabulary candidates of a sample, then [:beam_size]).
- *   x fp32 [rows, n] (row pitch ldx);  out_val fp32 [rows, k], out_idx int64 [rows, k];  1 <= k <= min(16, n).
+ *   x fp32 [rows, n] (row pitch ldx);  out_val fp32 [rows, k], out_idx int64 [rows, k];  1 <= k <= min(16, n), rows <= 65535
+ *   (OVQA_ERR_BAD_SHAPE otherwise).
  *   workspace >= ovqa_topk_rows_workspace_bytes(rows, n, k) bytes, caller-owned;  two launches. */
 int64_t ovqa_topk_rows_workspace_bytes(int64_t rows, int64_t n, int k);
 int ovqa_topk_rows(const float* x, int64_t rows, int64_t n, int64_t ldx, int k, float* out_val, int64_t* out_idx,

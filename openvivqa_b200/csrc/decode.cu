@@ -405,7 +405,7 @@ extern "C" int64_t ovqa_topk_rows_workspace_bytes(int64_t rows, int64_t n, int k
 extern "C" int ovqa_topk_rows(const float* x, int64_t rows, int64_t n, int64_t ldx, int k, float* out_val, int64_t* out_idx, void* workspace,
                               int64_t workspace_bytes, void* stream) {
     if (!x || !out_val || !out_idx || rows < 0 || n <= 0 || ldx < n || k <= 0) return OVQA_ERR_BAD_ARG;
-    if (k > kTopkMax || k > n) return OVQA_ERR_BAD_SHAPE;
+    if (k > kTopkMax || k > n || rows > 65535) return OVQA_ERR_BAD_SHAPE;      // (rows ride on gridDim.y)
     if (rows == 0) return OVQA_OK;
     if (!workspace || workspace_bytes < ovqa_topk_rows_workspace_bytes(rows, n, k)) return OVQA_ERR_BAD_ARG;
     const int chunks = topk_chunks(rows, n);
