@@ -89,6 +89,51 @@ def test_one_call_inference_wrappers_refuse_cpu_tensors():
         ops.pwff_infer(x, None, (0,) * 6, dt=0, d_ff=256, eps=1e-5)
 
 
+def test_encoder_projection_bookkeeping_across_regathers(monkeypatch):
+    """Host logic of the decode session (no kernels: the three library-backed calls are stubbed): the encoder projection is reused when
+    the keys are the same objects or provably what the last ``apply_to_states`` sweep made of them, and rebuilt otherwise."""
+    from openvivqa_b200 import functional as Fn
+    calls = []
+    monkeypatch.setattr(Fn, "project_kv_fused", lambda keys, values, **k: (calls.append(1), torch.zeros(keys.shape[0], keys.shape[1], 256))[1])
+    monkeypatch.setattr(Fn, "mha_decode_block", lambda plan, q, *a, **k: torch.zeros_like(q))
+    monkeypatch.setattr(Fn, "mha_decode_plan", lambda **k: None)
+    mha = ovqa.MultiHeadAttention(H.attention_cfg(128, 4)).eval()
+
+    class Model(ovqa.StatefulModule):                       # owner of ``encoder_features`` (base_transformer.py:17)
+        def __init__(self):
+            super().__init__()
+            self.m = mha
+            self.register_state("encoder_features", None)
+
+    model, perm = Model(), torch.tensor([1, 0, 2, 5, 4, 3])
+    with torch.no_grad(), model.statefulness(2):
+        model.encoder_features = torch.randn(2, 9, 128)
+        mha(torch.randn(2, 1, 128), model.encoder_features, model.encoder_features, None)
+        assert len(calls) == 1 and mha.running_enc_kv_proj.shape == (2, 9, 256)
+        mha(torch.randn(2, 1, 128), model.encoder_features, model.encoder_features, None)
+        assert len(calls) == 1                                                        # same objects: reused
+        model.apply_to_states(lambda s: s.repeat_interleave(3, 0))                    # fan out into beams
+        q = torch.randn(6, 1, 128)
+        for _ in range(3):
+            mha(q, model.encoder_features, model.encoder_features, None)
+            model.apply_to_states(lambda s: s[perm])
+        assert len(calls) == 1 and mha.running_enc_kv_proj.shape == (6, 9, 256)       # re-gathered with the states, never re-projected
+        other = torch.randn_like(model.encoder_features)
+        mha(q, other, other, None)
+        assert len(calls) == 2                                                        # foreign tensors of the same shape: projected again
+        mha(q, model.encoder_features, model.encoder_features, None)
+        n = len(calls)
+        model.apply_to_states(lambda s: s[perm])
+        model.apply_to_states(lambda s: s[perm])                                      # two sweeps between calls: provenance chain broken
+        mha(q, model.encoder_features, model.encoder_features, None)
+        assert len(calls) == n + 1
+        model.encoder_features.mul_(2.0)                                              # edited in place: version counter moved
+        mha(q, model.encoder_features, model.encoder_features, None)
+        assert len(calls) == n + 2
+        assert mha._decode_fast_path(mha._session, torch.randn(6, 40, 128), other, other, None) is None   # long query block: tiled cores
+    assert mha.running_enc_kv_proj.shape == (1, 256) and mha._enc_kv is None and mha._regather_memo is None
+
+
 def test_compute_dtype_selection():
     assert ovqa.get_compute_dtype() in ("fp32", "bf16")
     with pytest.raises(ValueError):
