@@ -5,6 +5,7 @@ import torch
 import openvivqa_b200 as ovqa
 from openvivqa_b200 import harness as H
 from oracle import cases as C
+from oracle import synth as S
 from oracle import ref_loader as RL
 
 
@@ -196,3 +197,80 @@ def test_m4c_mirror_state_dict_matches_reference_generated_spec(golden):
     m = H.MMF_M4C(H.m4c_cfg(c["hidden"], c["heads"], c["mmt_layers"], c["text_layers"], c["d_obj"]),
                   H.StubVocab(c["vocab"], max_answer_length=c["T"]))
     assert _spec(m) == [tuple(t) for t in golden("m4c")["spec"]]
+
+
+@pytest.mark.skipif(not RL.available(), reason="/root/reference not mounted")
+def test_reference_beam_search_runs_on_the_installed_drop_ins(monkeypatch, golden):
+    """The REAL drop-in scenario, bookkeeping level: the reference's own BaseTransformer / Decoder / BeamSearch classes with
+    ``install()`` applied — its containers.Module state recursion, its re-gather closure (wrapped), its ``select`` (rebound) — must
+    reproduce the golden token sequences.  No GPU here: the four library-backed calls are replaced by plain torch restatements, so
+    what is tested is every piece of host logic between them (sessions, caches with spare capacity, placeholder rows, provenance)."""
+    import math
+    import torch.nn.functional as F
+    from openvivqa_b200 import functional as Fn, ops
+
+    def mha_decode_block(plan, queries, kv_src, self_att, cache, length, mask, *, h, d_k, d_v, eps=1e-5, scale=None):
+        w_qkv, b_qkv, w_o, b_o, gamma, beta = plan.keep
+        hk = h * d_k
+        B, Lq, D = queries.shape
+        q = F.linear(queries, w_qkv[:hk], b_qkv[:hk])
+        src = queries if self_att else kv_src
+        if src is not None:
+            cache[:, length:length + src.shape[1]] = F.linear(src, w_qkv[hk:], b_qkv[hk:])
+            length += src.shape[1]
+        k, v = cache[:, :length, :hk], cache[:, :length, hk:]
+        att = q.view(B, Lq, h, d_k).permute(0, 2, 1, 3) @ k.reshape(B, length, h, d_k).permute(0, 2, 3, 1) / math.sqrt(d_k)
+        att = torch.softmax(att if mask is None else att + mask, -1)
+        ctx = (att @ v.reshape(B, length, h, d_v).permute(0, 2, 1, 3)).permute(0, 2, 1, 3).reshape(B, Lq, h * d_v)
+        return F.layer_norm(queries + F.linear(ctx, w_o, b_o), (D,), gamma, beta, eps)
+
+    def pwff_infer_block(plan, x, *, d_ff, eps=1e-5):
+        w1, b1, w2, b2, g, b = plan.keep
+        return F.layer_norm(x + F.linear(F.gelu(F.linear(x, w1, b1)), w2, b2), (x.shape[-1],), g, b, eps)
+
+    def topk_rows(x, k):
+        v, i = torch.sort(x, dim=-1, descending=True, stable=True)
+        return v[:, :k].contiguous(), i[:, :k].contiguous()
+
+    projections = []
+    monkeypatch.setattr(Fn, "mha_decode_block", mha_decode_block)
+    monkeypatch.setattr(Fn, "pwff_infer_block", pwff_infer_block)
+    monkeypatch.setattr(Fn, "project_kv_fused", lambda keys, values, *, wk, bk, wv, bv, mode="fp32":
+                        (projections.append(1), torch.cat([F.linear(keys, wk, bk), F.linear(values, wv, bv)], -1))[1])
+    monkeypatch.setattr(ops, "topk_rows", topk_rows)
+
+    RL.load()
+    import models.modules.decoders as Dm
+    from models.base_transformer import BaseTransformer
+    c, g = C.GEN_CASE, golden("generative")
+    try:
+        ovqa.install(compute_dtype="fp32")
+        assert Dm.MultiHeadAttention.__module__.startswith("openvivqa_b200")
+        att = lambda st: RL.attention_cfg(c["D"], c["h"], c["D"] // c["h"], c["D"] // c["h"], d_ff=c["d_ff"], stateful=st)
+        cfg = RL.NS(D_MODEL=c["D"], LAYERS=c["layers"], ATTENTION=RL.NS(SELF_ATTENTION=att(True), ENC_ATTENTION=att(False)),
+                    TEXT_EMBEDDING=RL.NS(ARCHITECTURE="UsualEmbedding", D_MODEL=c["D"], WORD_EMBEDDING=None, D_EMBEDDING=c["D"], DROPOUT=0.1))
+
+        class Captioner(BaseTransformer):                       # as oracle/make_golden.py::gen_generative
+            def __init__(self, config, vocab):
+                super().__init__(config, vocab)
+                self.device = "cpu"
+                self.decoder = Dm.Decoder(config, vocab)        # the reference's Decoder, now built from the drop-ins
+
+            def encoder_forward(self, feats):
+                return feats["enc"], feats["enc_mask"]
+
+        m = Captioner(cfg, RL.StubVocab(c["vocab"], max_answer_length=c["T"])).eval()
+        assert S.spec_of(m.state_dict()) == g["spec"]           # reference checkpoint layout unchanged by the extra (non-persistent) states
+        m.load_state_dict(S.synth_params(g["spec"], 0), strict=False)
+        m.eos_idx = c["eos"]
+        x = C.gen_inputs()
+        with torch.no_grad():
+            for beam in (1, c["beam"]):
+                projections.clear()
+                tokens, logp = m.beam_search(x, batch_size=c["B"], beam_size=beam, out_size=1)
+                assert torch.equal(tokens, g[f"beam{beam}"]["tokens"])
+                torch.testing.assert_close(logp, g[f"beam{beam}"]["logp"], rtol=1e-4, atol=1e-5)
+                assert len(projections) == c["layers"]          # encoder keys projected once per layer for the whole search
+    finally:
+        ovqa.uninstall()
+        ovqa.set_compute_dtype("fp32")
