@@ -11,5 +11,5 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05_kernel --launch-skip 52 -c 1 -f -o gpurun_out/gemm_fc2_full python tools/microbench.py gemm > gpurun_out/ncu_gemm.log 2>&1; echo "ncu_fc2 rc=$?" >> gpurun_out/summary.txt
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"sdpa_fwd_tc5_kernel|sdpa_bwd_tc5_kernel" --launch-skip 8 -c 2 -f -o gpurun_out/tc5_full python tools/microbench.py sdpa > gpurun_out/ncu_tc5.log 2>&1; echo "ncu_tc5 rc=$?" >> gpurun_out/summary.txt
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"layernorm_bwd" --launch-skip 5 -c 1 -f -o gpurun_out/ln_full python tools/microbench.py ln > gpurun_out/ncu_ln.log 2>&1; echo "ncu_ln rc=$?" >> gpurun_out/summary.txt
-timeout 900 python tools/microbench.py gemm epi sdpa ln mha decode > gpurun_out/microbench.jsonl 2> gpurun_out/microbench.err; echo "microbench rc=$?" >> gpurun_out/summary.txt
+timeout 900 python tools/microbench.py gemm epi sdpa ln mha decode beam > gpurun_out/microbench.jsonl 2> gpurun_out/microbench.err; echo "microbench rc=$?" >> gpurun_out/summary.txt
 cat gpurun_out/summary.txt; tail -4 gpurun_out/pytest_gpu.log; tail -3 gpurun_out/smoke.log; cut -c1-400 gpurun_out/bench.log; cut -c1-400 gpurun_out/bench_m4c.log; cut -c1-300 gpurun_out/bench_ref.log
