@@ -112,16 +112,26 @@ class StatefulModule(nn.Module):
             if d is None:
                 self._buffers[n] = None
             else:
-                t = d.clone().detach().to(self._buffers[n].device).unsqueeze(0)
+                t = self._default_on(d, self._buffers[n].device).unsqueeze(0)
                 self._buffers[n] = t.expand([batch_size] + list(t.shape[1:])).contiguous()
         self._is_stateful = True
+
+    @staticmethod
+    def _default_on(d, device):
+        """A state's default on ``device``.  All-zero defaults (every one the path registers) are made by a fill on the device: no
+        host-to-device copy, so a decode session may be opened inside a CUDA-graph capture."""
+        if d.device == device:
+            return d.clone().detach()
+        if d.numel() == 0 or not bool(d.any()):
+            return torch.zeros(d.shape, dtype=d.dtype, device=device)
+        return d.clone().detach().to(device)
 
     def disable_statefulness(self):
         for m in self._children_stateful():
             m.disable_statefulness()
         for n in self._state_names:
             d = self._state_defaults[n]
-            self._buffers[n] = None if d is None else d.clone().detach().to(self._buffers[n].device)
+            self._buffers[n] = None if d is None else self._default_on(d, self._buffers[n].device)
         self._is_stateful = False
 
     @contextmanager
