@@ -243,6 +243,7 @@ def test_reference_beam_search_runs_on_the_installed_drop_ins(monkeypatch, golde
     import models.modules.decoders as Dm
     from models.base_transformer import BaseTransformer
     c, g = C.GEN_CASE, golden("generative")
+    previous_dtype = ovqa.get_compute_dtype()
     try:
         ovqa.install(compute_dtype="fp32")
         assert Dm.MultiHeadAttention.__module__.startswith("openvivqa_b200")
@@ -273,4 +274,4 @@ def test_reference_beam_search_runs_on_the_installed_drop_ins(monkeypatch, golde
                 assert len(projections) == c["layers"]          # encoder keys projected once per layer for the whole search
     finally:
         ovqa.uninstall()
-        ovqa.set_compute_dtype("fp32")
+        ovqa.set_compute_dtype(previous_dtype)
