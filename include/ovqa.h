@@ -125,7 +125,10 @@ int ovqa_sdpa_fwd_prefix_lm(const void* q, const void* k, const void* v, void* o
 /* Backward of the core (recomputes the probabilities from q,k,mask,lse):
  *   dq, dk, dv have the layouts of q, k, v (lddq/lddk/lddv).  `delta` [B,h,Lq] fp32 is caller-provided
  *   scratch (rowsum(dout*out)).  Geometry bias participates in the recomputation; its weight gradient
- *   (geo_dw [h,d_g], geo_db [h], fp32, ACCUMULATED into) is produced when non-NULL. */
+ *   (geo_dw [h,d_g], geo_db [h], fp32, ACCUMULATED into) is produced when non-NULL.
+ *   `att` / `datt` [B,h,Lq,Lk] fp32 (both or neither; NULL from MultiHeadAttention): the probabilities ovqa_sdpa_fwd returned and the
+ *   gradient arriving THROUGH them — a direct caller of the core may consume `att` itself (mmf_lorra.py:118-146 builds its
+ *   features from the attention weights), so dP = dout v^T + datt. */
 int ovqa_sdpa_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout,
                   void* dq, void* dk, void* dv,
                   int64_t B, int64_t h, int64_t Lq, int64_t Lk, int64_t dk_, int64_t dv_,
@@ -135,7 +138,8 @@ int ovqa_sdpa_bwd(const void* q, const void* k, const void* v, const void* out, 
                   const float* boxes, const float* geo_w, const float* geo_b, const float* geo_freq,
                   int64_t d_g, int geo_trig,
                   float* geo_dw, float* geo_db,
-                  float scale, int dtype, const float* lse, float* delta, void* stream);
+                  float scale, int dtype, const float* lse, float* delta,
+                  const float* att, const float* datt, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * LayerNorm over the last dimension with optional fused residual add.
@@ -214,6 +218,15 @@ int ovqa_ptr_scores(const void* q, const void* k, const void* mask, float* score
                     int64_t B, int64_t T, int64_t L, int64_t d, int64_t ldq, int64_t ldk,
                     int64_t ld_scores, int64_t col_offset, float scale, int dtype, int mask_is_bool,
                     void* stream);
+
+/* Backward of ovqa_ptr_scores (autograd of mmf_m4c.py:394-396; the M4C training path):
+ *   dq[b,t,:] = scale * sum_j dscores[b,t,j] k[b,j,:],   dk[b,j,:] = scale * sum_t dscores[b,t,j] q[b,t,:];
+ *   dscores fp32 rows of pitch ld_dscores (the gradient of the pointer columns, e.g. a slice of d(scores)); the additive mask is a
+ *   constant, `bool_mask` (uint8 [B,L], or NULL) marks the keys ovqa_ptr_scores filled with -inf: they carry no gradient. */
+int ovqa_ptr_scores_bwd(const float* dscores, const void* q, const void* k, const void* bool_mask,
+                        void* dq, void* dk, int64_t B, int64_t T, int64_t L, int64_t d,
+                        int64_t ld_dscores, int64_t ldq, int64_t ldk, int64_t lddq, int64_t lddk,
+                        float scale, int dtype, void* stream);
 
 /* PrevPredEmbeddings: out[b,t,:] = LN_src(table_row(prev_inds[b,t])) + LN_emb(pos_emb[t] + type_emb[is_ocr])
  *   where table_row(i) = ans_emb[i] (i < V, LayerNorm ans_*) else ocr_emb[b, i-V] (LayerNorm ocr_*).

@@ -44,7 +44,7 @@ _PROTOS = {
                       _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _i32, _vp, _vp, _vp],
     "ovqa_sdpa_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64,
                       _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
-                      _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _f32, _i32, _vp, _vp, _vp],
+                      _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _f32, _i32, _vp, _vp, _vp, _vp, _vp],
     "ovqa_layernorm_fwd": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, _vp],
     "ovqa_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, _u64, _u64, _vp, _vp],
     "ovqa_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
@@ -56,6 +56,7 @@ _PROTOS = {
     "ovqa_stage_many": [_vp, _i64, _vp],
     "ovqa_box_geometry_bias": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp],
     "ovqa_ptr_scores": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _i32, _i32, _vp],
+    "ovqa_ptr_scores_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _i32, _vp],
     "ovqa_prev_pred_embed": [_vp] * 12 + [_i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _vp],
     "ovqa_greedy_step": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp],
     "ovqa_dropout_mask": [_vp, _i64, _f32, _u64, _u64, _vp, _vp],

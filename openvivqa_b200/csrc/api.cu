@@ -9,17 +9,17 @@ thread_local int g_last_cuda_error = 0;
 unsigned long long g_launch_count = 0;
 
 int sm_count() {
-    static int n = [] {
-        int dev = 0, v = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return kNumSMsB200;
-        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return kNumSMsB200;
-        return v;
-    }();
-    return n;
+    static int cache[64] = {};
+    const int dev = current_device() & 63;
+    int v = __atomic_load_n(&cache[dev], __ATOMIC_RELAXED);
+    if (v > 0) return v;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = kNumSMsB200;
+    __atomic_store_n(&cache[dev], v, __ATOMIC_RELAXED);
+    return v;
 }
 
 template <typename T> int sdpa_fwd_simt_launch(const SdpaArgs&, cudaStream_t);
-template <typename T> int sdpa_bwd_simt_launch(const SdpaArgs&, const void*, void*, void*, void*, int64_t, int64_t, int64_t, int64_t, float*, float*, float*, cudaStream_t);
+template <typename T> int sdpa_bwd_simt_launch(const SdpaArgs&, const void*, void*, void*, void*, int64_t, int64_t, int64_t, int64_t, float*, float*, float*, const float*, const float*, cudaStream_t);
 int box_geometry_bias_launch(const GeoArg&, float*, int64_t, int64_t, int64_t, cudaStream_t);
 int sdpa_fwd_mma_bf16(const SdpaArgs&, cudaStream_t);   // attention_mma.cu
 bool sdpa_fwd_mma_supported(const SdpaArgs&);
@@ -75,6 +75,10 @@ extern "C" int ovqa_gemm(const void* A, const void* B, void* C, int64_t m, int64
     // debugging aid only: OVQA_BF16_GEMM=simt routes bf16 GEMMs to the CUDA-core twin (to bisect a tensor-core bug)
     static const bool force_simt = [] { const char* e = getenv("OVQA_BF16_GEMM"); return e && e[0] == 's'; }();
     if (force_simt) return gemm_simt_bf16((const __nv_bfloat16*)A, (const __nv_bfloat16*)B, C, m, n, k, lda, ldb, ldc, a_op, b_op, e, split_k, st);
+    // TMA needs 16-byte aligned bases and row pitches; operands that are not (a width that is no multiple of 8, an odd column slice)
+    // go to the CUDA-core twin — same operand forms and epilogue — instead of failing (split_k == 0 "auto" means 1 there)
+    if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) || (lda % 8) || (ldb % 8))
+        return gemm_simt_bf16((const __nv_bfloat16*)A, (const __nv_bfloat16*)B, C, m, n, k, lda, ldb, ldc, a_op, b_op, e, split_k, st);
     return gemm_tcgen05_bf16((const __nv_bfloat16*)A, (const __nv_bfloat16*)B, C, m, n, k, lda, ldb, ldc, a_op, b_op, e, split_k, st);
 }
 
@@ -141,24 +145,27 @@ extern "C" int ovqa_sdpa_bwd(const void* q, const void* k, const void* v, const 
                              int64_t ldk, int64_t ldv, int64_t ldo, int64_t lddo, int64_t lddq, int64_t lddk, int64_t lddv,
                              const float* mask, int64_t mask_sb, int64_t mask_sh, int64_t mask_sq, const float* boxes,
                              const float* geo_w, const float* geo_b, const float* geo_freq, int64_t d_g, int geo_trig,
-                             float* geo_dw, float* geo_db, float scale, int dtype, const float* lse, float* delta, void* stream) {
+                             float* geo_dw, float* geo_db, float scale, int dtype, const float* lse, float* delta, const float* att,
+                             const float* datt, void* stream) {
     int rc = check_sdpa(q, k, v, B, h, Lq, Lk, dk_, dv_, boxes, geo_w, geo_b, d_g, geo_trig, dtype);
     if (rc) return rc;
     if (!out || !dout || !dq || !dk || !dv || !lse) return OVQA_ERR_BAD_ARG;
     if ((geo_dw == nullptr) != (geo_db == nullptr)) return OVQA_ERR_BAD_ARG;
+    if (datt && !att) return OVQA_ERR_BAD_ARG;
     if (B == 0 || Lq == 0) return OVQA_OK;
     SdpaArgs a{q, k, v, const_cast<void*>(out), B, h, Lq, Lk, dk_, dv_, ldq, ldk, ldv, ldo, {mask, mask_sb, mask_sh, mask_sq},
                {boxes, geo_w, geo_b, geo_freq, (int)d_g, geo_trig}, scale, const_cast<float*>(lse), nullptr};
     cudaStream_t st = (cudaStream_t)stream;
     // debugging aid only: OVQA_SDPA_BWD=simt keeps the bf16 backward on the CUDA-core kernels
     static const bool force_simt = [] { const char* e = getenv("OVQA_SDPA_BWD"); return e && e[0] == 's'; }();
-    if (dtype == OVQA_BF16 && !force_simt && sdpa_bwd_tc5_supported(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv))
+    // a gradient THROUGH the probabilities (datt) is folded into dP by the CUDA-core kernels only
+    if (dtype == OVQA_BF16 && !force_simt && !datt && sdpa_bwd_tc5_supported(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv))
         return sdpa_bwd_tc5_bf16(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv, st);
-    if (dtype == OVQA_BF16 && !force_simt && sdpa_bwd_mma_supported(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv))
+    if (dtype == OVQA_BF16 && !force_simt && !datt && sdpa_bwd_mma_supported(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv))
         return sdpa_bwd_mma_bf16(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv, st);
     if (!delta) return OVQA_ERR_BAD_ARG;
-    if (dtype == OVQA_F32) return sdpa_bwd_simt_launch<float>(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv, delta, geo_dw, geo_db, st);
-    return sdpa_bwd_simt_launch<__nv_bfloat16>(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv, delta, geo_dw, geo_db, st);
+    if (dtype == OVQA_F32) return sdpa_bwd_simt_launch<float>(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv, delta, geo_dw, geo_db, att, datt, st);
+    return sdpa_bwd_simt_launch<__nv_bfloat16>(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv, delta, geo_dw, geo_db, att, datt, st);
 }
 
 extern "C" int ovqa_box_geometry_bias(const float* boxes, const float* geo_w, const float* geo_b, const float* geo_freq, float* out,

@@ -134,9 +134,11 @@ struct SdpaBwdArgs {
     float* delta;        // [B,h,Lq]
     float* geo_dw;       // [h,d_g] accumulated
     float* geo_db;       // [h]
+    const float* att;    // [B,h,Lq,Lk] forward probabilities, with datt: the caller differentiates THROUGH the returned probabilities
+    const float* datt;   // [B,h,Lq,Lk] their upstream gradient (mmf_lorra.py:127-146 builds features from `att`), or NULL
 };
 
-// delta[b,h,i] = sum_d dout[b,i,h,d] * out[b,i,h,d]     (warp per row)
+// delta[b,h,i] = sum_d dout[b,i,h,d] * out[b,i,h,d]  (+ sum_j att[b,h,i,j] * datt[b,h,i,j])     (warp per row)
 template <typename T>
 __global__ void sdpa_delta_kernel(SdpaBwdArgs a) {
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;  // over B*Lq*h
@@ -148,8 +150,14 @@ __global__ void sdpa_delta_kernel(SdpaBwdArgs a) {
     const T* d_o = reinterpret_cast<const T*>(a.dout) + bi * a.lddo + (int64_t)hd * a.f.dv;
     float s = 0.0f;
     for (int d = lane; d < a.f.dv; d += 32) s = fmaf(to_f32<T>(o[d]), to_f32<T>(d_o[d]), s);
+    const int64_t stat = ((bi / a.f.Lq) * a.f.h + hd) * a.f.Lq + bi % a.f.Lq;
+    if (a.datt) {
+        const float* pr = a.att + stat * a.f.Lk;
+        const float* dr = a.datt + stat * a.f.Lk;
+        for (int j = lane; j < a.f.Lk; j += 32) s = fmaf(__ldg(pr + j), __ldg(dr + j), s);
+    }
     s = warp_sum(s);
-    if (lane == 0) a.delta[((bi / a.f.Lq) * a.f.h + hd) * a.f.Lq + bi % a.f.Lq] = s;
+    if (lane == 0) a.delta[stat] = s;
 }
 
 // score recomputation for one (row, key) pair; identical arithmetic to the forward
@@ -215,6 +223,7 @@ __global__ void __launch_bounds__(NW * 32) sdpa_bwd_dq_simt(SdpaBwdArgs a) {
                 const float* dor = sdO + r * dv;
                 const float* vr = sV + lane * (dv + 1);
                 for (int d = 0; d < dv; ++d) dp = fmaf(dor[d], vr[d], dp);
+                if (a.datt) dp += __ldg(a.datt + (stat0 + r) * Lk + k0 + lane);
                 ds = p * (dp - a.delta[stat0 + r]);
                 if (geo && a.geo_dw && raw > 1e-6f) {
                     // d log(clamp(relu(raw))) / d raw = 1/raw when raw > 1e-6; chain into w_h, b_h (attentions.py:116-132)
@@ -312,6 +321,7 @@ __global__ void __launch_bounds__(NW * 32) sdpa_bwd_dkv_simt(SdpaBwdArgs a) {
                 const float* dor = sdO + lane * (dv + 1);
                 const float* vr = sV + jr * dv;
                 for (int d = 0; d < dv; ++d) dp = fmaf(dor[d], vr[d], dp);
+                if (a.datt) dp += __ldg(a.datt + (stat0 + i0 + lane) * Lk + j0 + jr);
                 ds = p * (dp - a.delta[stat0 + i0 + lane]);
             }
             sP[jr * KC + lane] = p;
@@ -374,8 +384,9 @@ template int sdpa_fwd_simt_launch<__nv_bfloat16>(const SdpaArgs&, cudaStream_t);
 
 template <typename T>
 int sdpa_bwd_simt_launch(const SdpaArgs& f, const void* dout, void* dq, void* dk, void* dv, int64_t lddo, int64_t lddq,
-                         int64_t lddk, int64_t lddv, float* delta, float* geo_dw, float* geo_db, cudaStream_t st) {
-    SdpaBwdArgs a{f, dout, dq, dk, dv, lddo, lddq, lddk, lddv, delta, geo_dw, geo_db};
+                         int64_t lddk, int64_t lddv, float* delta, float* geo_dw, float* geo_db, const float* att, const float* datt,
+                         cudaStream_t st) {
+    SdpaBwdArgs a{f, dout, dq, dk, dv, lddo, lddq, lddk, lddv, delta, geo_dw, geo_db, att, datt};
     const int64_t rows = f.B * f.Lq * f.h;
     sdpa_delta_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(a);
     OVQA_LAUNCH_OK();
@@ -394,8 +405,8 @@ int sdpa_bwd_simt_launch(const SdpaArgs& f, const void* dout, void* dq, void* dk
     OVQA_LAUNCH_OK();
     return OVQA_OK;
 }
-template int sdpa_bwd_simt_launch<float>(const SdpaArgs&, const void*, void*, void*, void*, int64_t, int64_t, int64_t, int64_t, float*, float*, float*, cudaStream_t);
-template int sdpa_bwd_simt_launch<__nv_bfloat16>(const SdpaArgs&, const void*, void*, void*, void*, int64_t, int64_t, int64_t, int64_t, float*, float*, float*, cudaStream_t);
+template int sdpa_bwd_simt_launch<float>(const SdpaArgs&, const void*, void*, void*, void*, int64_t, int64_t, int64_t, int64_t, float*, float*, float*, const float*, const float*, cudaStream_t);
+template int sdpa_bwd_simt_launch<__nv_bfloat16>(const SdpaArgs&, const void*, void*, void*, void*, int64_t, int64_t, int64_t, int64_t, float*, float*, float*, const float*, const float*, cudaStream_t);
 
 // ------------------------------------------------------------------------------------------------ materialised geometry bias
 __global__ void box_geometry_bias_kernel(GeoArg g, float* out, int64_t B, int64_t N, int64_t h) {

@@ -792,8 +792,8 @@ int sdpa_fwd_tc5_bf16(const SdpaArgs& a, cudaStream_t st) {
     if ((rc = make_tma_map_bf16(&mq, a.q, cols, (uint64_t)(a.B * a.Lq), (uint64_t)a.ldq, kD, (uint32_t)a.Lq))) return rc;
     if ((rc = make_tma_map_bf16(&mk, a.k, cols, (uint64_t)(a.B * a.Lk), (uint64_t)a.ldk, kD, (uint32_t)args.nk16))) return rc;
     if ((rc = make_tma_map_bf16(&mv, a.v, cols, (uint64_t)(a.B * a.Lk), (uint64_t)a.ldv, kD, (uint32_t)args.nk16))) return rc;
-    static bool attr_set = false;
-    if (!attr_set) { OVQA_CUDA_OK(cudaFuncSetAttribute(sdpa_fwd_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem)); attr_set = true; }
+    static OncePerDevice attr_set;
+    if (attr_set.pending()) { OVQA_CUDA_OK(cudaFuncSetAttribute(sdpa_fwd_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem)); attr_set.mark(); }
     const int64_t items = a.B * a.h;
     const int64_t slots = 2 * (int64_t)sm_count();            // two CTAs per SM
     const int grid = (int)(items < slots ? items : slots);
@@ -864,8 +864,8 @@ int sdpa_bwd_tc5_bf16(const SdpaArgs& a, const void* dout, void* dq, void* dk, v
     if ((rc = make_tma_map_bf16(&mdo, dout, cols, (uint64_t)(a.B * a.Lq), (uint64_t)lddo, kD, (uint32_t)args.nq16))) return rc;
     if ((rc = make_tma_map_bf16(&mk, a.k, cols, (uint64_t)(a.B * a.Lk), (uint64_t)a.ldk, kD, (uint32_t)args.nk16))) return rc;
     if ((rc = make_tma_map_bf16(&mv, a.v, cols, (uint64_t)(a.B * a.Lk), (uint64_t)a.ldv, kD, (uint32_t)args.nk16))) return rc;
-    static bool attr_set = false;
-    if (!attr_set) { OVQA_CUDA_OK(cudaFuncSetAttribute(sdpa_bwd_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem)); attr_set = true; }
+    static OncePerDevice attr_set;
+    if (attr_set.pending()) { OVQA_CUDA_OK(cudaFuncSetAttribute(sdpa_bwd_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem)); attr_set.mark(); }
     const int64_t items = a.B * a.h;
     const int grid = (int)(items < sm_count() ? items : sm_count());
     sdpa_bwd_tc5_kernel<<<grid, kBwdThreads, kBwdSmem, st>>>(mq, mdo, mk, mv, args);

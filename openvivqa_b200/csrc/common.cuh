@@ -28,7 +28,17 @@ extern unsigned long long g_launch_count;
     } while (0)
 
 constexpr int kNumSMsB200 = 148;
-int sm_count();
+int sm_count();                  // of the CURRENT device (cached per device)
+
+// "once per device" latch for per-function attributes (cudaFuncSetAttribute applies to the current device only: a process that
+// drives several GPUs must opt every one of them into > 48 KB of dynamic shared memory)
+inline int current_device() { int d = 0; return cudaGetDevice(&d) == cudaSuccess ? d : 0; }
+struct OncePerDevice {
+    unsigned long long done = 0;
+    unsigned long long bit() const { return 1ull << (current_device() & 63); }
+    bool pending() const { return (__atomic_load_n(&done, __ATOMIC_RELAXED) & bit()) == 0; }
+    void mark() { __atomic_fetch_or(&done, bit(), __ATOMIC_RELAXED); }
+};
 
 // ----------------------------------------------------------------------------- element access
 template <typename T> __device__ __forceinline__ float to_f32(T v);

@@ -684,8 +684,8 @@ int launch(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, int64_t m, i
         constexpr int kEpw = epw_for(MODE_, FEAT_), kThreads = 64 + kEpw * 32;                                                  \
         using cfg = Cfg<BN, CTAS, kEpw>;                                                                                        \
         auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, TC_, MODE_, FEAT_, CTAS, kEpw>;                                               \
-        static bool attr_set = false;                                                                                          \
-        if (!attr_set) { OVQA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::kSmemBytes)); attr_set = true; } \
+        static OncePerDevice attr_set;                                                                                          \
+        if (attr_set.pending()) { OVQA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::kSmemBytes)); attr_set.mark(); } \
         if constexpr (CTAS == 1) {                                                                                             \
             kern<<<grid, kThreads, cfg::kSmemBytes, st>>>(ma, mb, (TC_*)C, m, n, k, ldc, epi, split_k);                        \
         } else {                                                                                                               \

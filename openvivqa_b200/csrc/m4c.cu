@@ -76,6 +76,58 @@ __global__ void __launch_bounds__(256) ptr_scores_vec_kernel(const __nv_bfloat16
     }
 }
 
+// Backward of the pointer scores (autograd of mmf_m4c.py:394-396):  dq[b,t,:] = scale * sum_j dS[b,t,j] k[b,j,:],
+// dk[b,j,:] = scale * sum_t dS[b,t,j] q[b,t,:].  The additive mask is a constant; positions a boolean mask filled with -inf carry no
+// gradient.  CTA = (sample, 128-column slab of d): dS of the sample sits in shared memory, every thread owns one column and keeps 16
+// accumulators (rows of dq, then rows of dk, 16 at a time); q / k column reads are coalesced across the CTA.
+constexpr int kPtrBwdThreads = 128, kPtrBwdAcc = 16;
+template <typename T>
+__global__ void __launch_bounds__(kPtrBwdThreads) ptr_scores_bwd_kernel(const float* __restrict__ ds, const T* __restrict__ q, const T* __restrict__ k,
+                                                                       const uint8_t* __restrict__ bool_mask, T* __restrict__ dq, T* __restrict__ dk,
+                                                                       int Tn, int L, int d, int64_t ld_ds, int64_t ldq, int64_t ldk, int64_t lddq,
+                                                                       int64_t lddk, float scale) {
+    extern __shared__ float sds[];                       // [Tn][L]
+    const int64_t b = blockIdx.x;
+    for (int i = threadIdx.x; i < Tn * L; i += blockDim.x) {
+        const int t = i / L, j = i % L;
+        float v = ds[(b * Tn + t) * ld_ds + j];
+        if (bool_mask && bool_mask[b * L + j]) v = 0.f;
+        sds[i] = v;
+    }
+    __syncthreads();
+    const int c = blockIdx.y * blockDim.x + threadIdx.x;
+    if (c >= d) return;
+    const T* qb = q + b * Tn * ldq + c;
+    const T* kb = k + b * L * ldk + c;
+    float acc[kPtrBwdAcc];
+    for (int t0 = 0; t0 < Tn; t0 += kPtrBwdAcc) {
+#pragma unroll
+        for (int i = 0; i < kPtrBwdAcc; ++i) acc[i] = 0.f;
+        for (int j = 0; j < L; ++j) {
+            const float kv = to_f32<T>(kb[(int64_t)j * ldk]);
+#pragma unroll
+            for (int i = 0; i < kPtrBwdAcc; ++i)
+                if (t0 + i < Tn) acc[i] = fmaf(sds[(t0 + i) * L + j], kv, acc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < kPtrBwdAcc; ++i)
+            if (t0 + i < Tn) dq[(b * Tn + t0 + i) * lddq + c] = from_f32<T>(acc[i] * scale);
+    }
+    for (int j0 = 0; j0 < L; j0 += kPtrBwdAcc) {
+#pragma unroll
+        for (int i = 0; i < kPtrBwdAcc; ++i) acc[i] = 0.f;
+        for (int t = 0; t < Tn; ++t) {
+            const float qv = to_f32<T>(qb[(int64_t)t * ldq]);
+#pragma unroll
+            for (int i = 0; i < kPtrBwdAcc; ++i)
+                if (j0 + i < L) acc[i] = fmaf(sds[t * L + j0 + i], qv, acc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < kPtrBwdAcc; ++i)
+            if (j0 + i < L) dk[(b * L + j0 + i) * lddk + c] = from_f32<T>(acc[i] * scale);
+    }
+}
+
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
 // LayerNorm of a register-resident row (float4 per lane), fp32 two-pass
@@ -194,6 +246,27 @@ extern "C" int ovqa_ptr_scores(const void* q, const void* k, const void* mask, f
     if (dtype == OVQA_F32) ptr_scores_kernel<float><<<grid, 256, 0, st>>>((const float*)q, (const float*)k, mask, scores, B, T, L, d, ldq, ldk, ld_scores, col_offset, scale, mask_is_bool);
     else if (dtype == OVQA_BF16) ptr_scores_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, mask, scores, B, T, L, d, ldq, ldk, ld_scores, col_offset, scale, mask_is_bool);
     else return OVQA_ERR_BAD_ARG;
+    OVQA_LAUNCH_OK();
+    return OVQA_OK;
+}
+
+extern "C" int ovqa_ptr_scores_bwd(const float* dscores, const void* q, const void* k, const void* bool_mask, void* dq, void* dk, int64_t B,
+                                   int64_t T, int64_t L, int64_t d, int64_t ld_dscores, int64_t ldq, int64_t ldk, int64_t lddq, int64_t lddk,
+                                   float scale, int dtype, void* stream) {
+    if (!dscores || !q || !k || !dq || !dk || B < 0 || T < 0 || L < 0 || d <= 0) return OVQA_ERR_BAD_ARG;
+    if (dtype != OVQA_F32 && dtype != OVQA_BF16) return OVQA_ERR_BAD_ARG;
+    if (B == 0 || T == 0 || L == 0) return OVQA_OK;                 // (the caller zero-fills whichever of dq / dk has rows then)
+    const size_t smem = (size_t)T * (size_t)L * sizeof(float);
+    if (smem > 48 * 1024 || B > 0x7fffffff) return OVQA_ERR_BAD_SHAPE;
+    dim3 grid((unsigned)B, (unsigned)((d + kPtrBwdThreads - 1) / kPtrBwdThreads));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == OVQA_F32)
+        ptr_scores_bwd_kernel<float><<<grid, kPtrBwdThreads, smem, st>>>(dscores, (const float*)q, (const float*)k, (const uint8_t*)bool_mask, (float*)dq,
+                                                                         (float*)dk, (int)T, (int)L, (int)d, ld_dscores, ldq, ldk, lddq, lddk, scale);
+    else
+        ptr_scores_bwd_kernel<__nv_bfloat16><<<grid, kPtrBwdThreads, smem, st>>>(dscores, (const __nv_bfloat16*)q, (const __nv_bfloat16*)k,
+                                                                                 (const uint8_t*)bool_mask, (__nv_bfloat16*)dq, (__nv_bfloat16*)dk, (int)T,
+                                                                                 (int)L, (int)d, ld_dscores, ldq, ldk, lddq, lddk, scale);
     OVQA_LAUNCH_OK();
     return OVQA_OK;
 }

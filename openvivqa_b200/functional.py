@@ -38,7 +38,7 @@ class _DropoutStream:
         """Device word added to every offset inside the kernels (``offset_base`` of the C ABI).  Zero unless a
         CUDA-graph user advances it between replays with :meth:`advance_on_device` — the launch parameters
         (seed, offset) are frozen inside a captured graph, this word is what makes each replay draw new masks."""
-        key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+        key = (device.type, device.index if (device.index is not None or device.type != "cuda") else torch.cuda.current_device())
         t = self._base.get(key)
         if t is None:
             t = self._base[key] = torch.zeros((1,), dtype=torch.int64, device=device)
@@ -471,16 +471,17 @@ class _PWFFFn(torch.autograd.Function):
         ctx.set_materialize_grads(False)
         mode = cfg["mode"]
         p = cfg["dropout"] if cfg["training"] else 0.0
+        p1 = cfg["dropout_inner"] if cfg["training"] else 0.0               # after the activation (0 for an HF BertIntermediate)
         cdt = _cdt(mode)
         D = x.shape[-1]
         x2 = _operand(x, mode)
         M, dff = x2.shape[0], w1.shape[0]
         need_grad = cfg["grad"] and any(ctx.needs_input_grad)
         pre = torch.empty((M, dff), device=x.device, dtype=cdt) if need_grad else None
-        s1, o1 = dropout_stream.next(M * dff) if p > 0.0 else (0, 0)
-        rng_base = dropout_stream.base(x.device) if p > 0.0 else None
+        s1, o1 = dropout_stream.next(M * dff) if p1 > 0.0 else (0, 0)
+        rng_base = dropout_stream.base(x.device) if (p > 0.0 or p1 > 0.0) else None
         hact = ops.gemm(x2, weights.get([w1], cdt), bias=weights.get([b1], torch.float32), out_dtype=cdt, gelu=True,
-                        aux_out=pre, save_dgelu=need_grad, dropout_p=p, seed=s1, offset=o1, offset_base=rng_base)   # pre := GELU'(fc1 x) * dropout scale
+                        aux_out=pre, save_dgelu=need_grad, dropout_p=p1, seed=s1, offset=o1, offset_base=rng_base)   # pre := GELU'(fc1 x) * dropout scale
         s2, o2 = dropout_stream.next(M * D) if p > 0.0 else (0, 0)
         x_res = x.reshape(-1, D)
         x_res = x_res if (x_res.dtype == torch.float32 and x_res.is_contiguous()) else x_res.float().contiguous()
@@ -520,8 +521,10 @@ class _PWFFFn(torch.autograd.Function):
         return dx, dw1, db1, dw2, db2, dgamma, dbeta, None
 
 
-def pwff_block(x, *, w1, b1, w2, b2, gamma, beta, mode="fp32", dropout=0.0, training=False, eps=1e-5):
-    cfg = dict(grad=torch.is_grad_enabled(), mode=mode, dropout=float(dropout), training=bool(training), eps=float(eps))
+def pwff_block(x, *, w1, b1, w2, b2, gamma, beta, mode="fp32", dropout=0.0, training=False, eps=1e-5, dropout_hidden=True):
+    """``dropout_hidden=False``: no dropout after the activation (HF ``BertIntermediate``; the reference's own block drops there too)."""
+    cfg = dict(grad=torch.is_grad_enabled(), mode=mode, dropout=float(dropout), dropout_inner=float(dropout) if dropout_hidden else 0.0,
+               training=bool(training), eps=float(eps))
     y, y16 = _PWFFFn.apply(x, w1, b1, w2, b2, gamma, beta, cfg)
     _attach_shadow(y, y16 if mode == "bf16" else None)
     return y
@@ -570,41 +573,72 @@ def feature_embedding(features, w, b, *, dropout=0.0, training=False, mask_value
 
 # ----------------------------------------------------------------------------- stand-alone pieces (direct core calls)
 class _SdpaFn(torch.autograd.Function):
+    """The attention core as a differentiable function of q, k, v, the geometry weights AND through both outputs: a direct caller may
+    consume the probabilities (``MMF_LoRRA`` builds its features from them, mmf_lorra.py:127-146), so ``att`` carries a gradient too:
+    dP = dout v^T + datt inside the same backward kernels."""
+
     @staticmethod
-    def forward(ctx, q, k, v, mask, cfg):
+    def forward(ctx, q, k, v, mask, boxes, geo_w, geo_b, cfg):
         ctx.set_materialize_grads(False)
         h, dk, dv = cfg["h"], cfg["d_k"], cfg["d_v"]
         need_grad = cfg["grad"] and any(ctx.needs_input_grad)
-        out, lse, att = ops.sdpa_fwd(q, k, v, h=h, d_k=dk, d_v=dv, mask=mask, geo=cfg.get("geo"), scale=cfg["scale"],
+        geo = ops.GeoParams(boxes, geo_w.detach(), geo_b.detach(), cfg["geo_trig"]) if boxes is not None else None
+        out, lse, att = ops.sdpa_fwd(q, k, v, h=h, d_k=dk, d_v=dv, mask=mask, geo=geo, scale=cfg["scale"],
                                      need_lse=need_grad, need_att=cfg["need_att"])
         if need_grad:
-            ctx.save_for_backward(q, k, v, mask, out, lse)
+            ctx.save_for_backward(q, k, v, mask, out, lse, att, boxes, geo_w, geo_b)
             ctx.cfg = cfg
-        if att is not None:
-            ctx.mark_non_differentiable(att)
-            return out, att
-        return out, torch.empty(0, device=q.device)
+        return out, (att if att is not None else torch.empty(0, device=q.device))
 
     @staticmethod
-    def backward(ctx, dout, _datt):
-        if dout is None:
-            return (None,) * 5
-        q, k, v, mask, out, lse = ctx.saved_tensors
+    def backward(ctx, dout, datt):
+        if dout is None and datt is None:
+            return (None,) * 8
+        q, k, v, mask, out, lse, att, boxes, geo_w, geo_b = ctx.saved_tensors
         cfg = ctx.cfg
+        if att is None:
+            datt = None
+        dout = torch.zeros_like(out) if dout is None else dout.to(out.dtype).contiguous()
         dq, dk_, dv_ = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-        ops.sdpa_bwd(q, k, v, out, dout.contiguous(), lse, dq, dk_, dv_, h=cfg["h"], d_k=cfg["d_k"], d_v=cfg["d_v"],
-                     mask=mask, geo=cfg.get("geo"), scale=cfg["scale"])
-        return dq, dk_, dv_, None, None
+        geo = ops.GeoParams(boxes, geo_w.detach(), geo_b.detach(), cfg["geo_trig"]) if boxes is not None else None
+        want_geo = geo is not None and (ctx.needs_input_grad[5] or ctx.needs_input_grad[6])
+        gdw = torch.zeros_like(geo_w, dtype=torch.float32) if want_geo else None
+        gdb = torch.zeros_like(geo_b, dtype=torch.float32) if want_geo else None
+        ops.sdpa_bwd(q, k, v, out, dout, lse, dq, dk_, dv_, h=cfg["h"], d_k=cfg["d_k"], d_v=cfg["d_v"], mask=mask, geo=geo,
+                     geo_dw=gdw, geo_db=gdb, scale=cfg["scale"], att=att, datt=datt)
+        return dq, dk_, dv_, None, None, gdw, gdb, None
 
 
-def sdpa(q, k, v, mask, *, h, d_k, d_v, scale=None, need_att=False, geo=None):
-    """Attention core on already projected (B,L,h*d) tensors (fp32 or bf16).  Returns (out, att|None).
-    Gradients flow to q,k,v (not through the returned probabilities, nor to the geometry weights: use
-    :func:`mha_block` for that)."""
+def sdpa(q, k, v, mask, *, h, d_k, d_v, scale=None, need_att=False, boxes=None, geo_w=None, geo_b=None, geo_trig=True):
+    """Attention core on already projected (B,L,h*d) tensors (fp32 or bf16).  Returns (out, att|None).  Gradients flow to q, k, v and to
+    the geometry weights ``geo_w`` (h,d_g) / ``geo_b`` (h) — through ``out`` and, when requested, through the probabilities ``att``."""
     cfg = dict(grad=torch.is_grad_enabled(), h=h, d_k=d_k, d_v=d_v, scale=(1.0 / math.sqrt(d_k)) if scale is None else float(scale), need_att=need_att,
-               geo=geo)
-    out, att = _SdpaFn.apply(q.contiguous(), k.contiguous(), v.contiguous(), mask, cfg)
+               geo_trig=bool(geo_trig))
+    out, att = _SdpaFn.apply(q.contiguous(), k.contiguous(), v.contiguous(), mask, boxes, geo_w, geo_b, cfg)
     return out, (att if need_att else None)
+
+
+class _PtrScoresFn(torch.autograd.Function):
+    """Pointer-network scores ``q k^T * scale + mask`` (mmf_m4c.py:394-396 / m4c.py:27-33) with their backward."""
+
+    @staticmethod
+    def forward(ctx, q, k, mask, scale, mask_is_bool):
+        scores = torch.empty((q.shape[0], q.shape[1], k.shape[1]), device=q.device, dtype=torch.float32)
+        ops.ptr_scores(q, k, mask, scores, 0, scale, mask_is_bool=mask_is_bool)
+        ctx.save_for_backward(q, k, mask if mask_is_bool else None)
+        ctx.scale = scale
+        return scores
+
+    @staticmethod
+    def backward(ctx, ds):
+        q, k, bool_mask = ctx.saved_tensors
+        dq, dk = ops.ptr_scores_bwd(ds.float(), q, k, ctx.scale, bool_mask=bool_mask)
+        return dq, dk, None, None, None
+
+
+def ptr_scores(q, k, mask, scale, mask_is_bool=False):
+    """Differentiable pointer scores (B,T,L) fp32 of projected q (B,T,d) and k (B,L,d)."""
+    return _PtrScoresFn.apply(q, k, mask, float(scale), bool(mask_is_bool))
 
 
 class _LayerNormFn(torch.autograd.Function):

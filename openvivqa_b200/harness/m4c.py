@@ -1,37 +1,21 @@
 """Host-side mirror of ``MMF_M4C`` (models/mmf_m4c.py:24-459) wired to the B200 kernels — BASELINE config 3.
 
 Same ``state_dict()`` names as the reference module (HF ``BertEncoder`` naming for ``text_bert`` / ``mmt.encoder``), so
-reference checkpoints and the oracle's parameter dicts load with ``strict=True``.
-
-B200-first restructuring of the greedy decode loop (mmf_m4c.py:236-256) — results identical to the reference's:
-
-* the BERT layers (third-party arithmetic) run through the SAME fused blocks as the repo's own
-  attention (``functional.mha_block`` / ``pwff_block`` with eps 1e-12 and d_ff 3072): one fused QKV GEMM, the
-  tensor-core attention core with the (B,1,L,L) prefix-LM mask, output projection + residual + LayerNorm;
-* everything that does not depend on ``prev_inds`` is computed ONCE per batch instead of once per step: the
-  object / OCR input encodings, the masks, and the TextBert pass + ``text_bert_out_linear`` (the reference re-runs
-  TextBert in every one of the 12 iterations, mmf_m4c.py:203-206; in eval mode it is a pure function of the tokens);
-* the joint ``(B, L, D)`` encoder input is one persistent buffer: text / object / OCR rows are written once, the
-  decoder rows are written in place each step by ``ovqa_prev_pred_embed`` (no ``(B, V+Locr, D)`` table, no cat);
-* scores live in one ``(B, T, V+Locr)`` buffer: the classifier GEMM writes columns ``[0, V)``, the pointer kernel
-  writes ``[V, V+Locr)`` (no ``torch.cat``, mmf_m4c.py:227);
-* argmax / shift / EOS latch are one kernel pair; the host reads the all-EOS flag only when ``early_exit`` is on.
-
-MMT must be re-run every step: encoder rows attend to the (unmasked) decoder columns (mmf_m4c.py:310-314), so
-there is no prefix to cache.
+reference checkpoints and the oracle's parameter dicts load with ``strict=True``.  The classes below are parameter containers;
+ALL arithmetic — the HF-BERT layers through the fused blocks, ``PrevPredEmbeddings``, the prefix-LM mask, the pointer scores and the
+restructured greedy loop — lives in :mod:`openvivqa_b200.m4c`, the same functions ``install()`` binds over the reference's own classes.
+This mirror exists because the GPU box has no reference checkout.
 """
 from __future__ import annotations
-
-import math
 
 import torch
 import torch.nn.functional as F
 from torch import nn
 
 from .. import functional as Fn
-from .. import ops
+from .. import m4c as M4
 from ..modules import OcrPtrNet, get_compute_dtype
-from .models import MASK_VALUE, generate_padding_mask, generate_sequential_mask
+from .models import generate_padding_mask
 
 
 class _BertSelf(nn.Module):
@@ -61,48 +45,27 @@ class _BertIntermediate(nn.Module):
 
 
 class BertLayer(nn.Module):
-    """HF ``BertLayer`` (eval): ``LN(dense(softmax(QK^T d^-1/2 + mask) V) + x)`` then ``LN(dense(gelu(dense ·)) + ·)``,
-    eps 1e-12 — computed by the fused MHA / PWFF blocks of the hot path."""
+    """HF ``BertLayer`` parameters (no dropout modules: the mirror is the inference model of BASELINE config 3)."""
 
     def __init__(self, d, heads, d_ff=3072, eps=1e-12):
         super().__init__()
         self.attention = _BertAttention(d, eps)
         self.intermediate = _BertIntermediate(d, d_ff)
         self.output = _BertDenseLN(d_ff, d, eps)
-        self.heads, self.d_head, self.eps = heads, d // heads, eps
+        self.heads = heads
 
     def forward(self, x, mask, mode, q_rows=None):
-        """``q_rows`` (slice): compute the layer only for those query rows (keys/values: all rows) — used for the LAST
-        layer of the decode step, whose other rows nobody reads."""
-        if self.training:
-            raise RuntimeError("harness BertLayer is inference-only (BASELINE config 3 is M4C *decode*)")
-        a, s = self.attention, self.attention.self
-        xq, mq = x, mask
-        if q_rows is not None:
-            xq = x[:, q_rows].contiguous()
-            mq = mask[:, :, q_rows] if (mask is not None and mask.shape[2] > 1) else mask
-            hint = getattr(mask, "_ovqa_prefix_lm", None)
-            if hint is not None and mq is not mask and q_rows.stop in (None, mask.shape[2]) and mq.shape[2] >= hint[1]:
-                mq._ovqa_prefix_lm = hint                     # the row slice still ends with the causal tail
-        att = Fn.mha_block(xq, x, x, mq, wq=s.query.weight, bq=s.query.bias, wk=s.key.weight, bk=s.key.bias,
-                           wv=s.value.weight, bv=s.value.bias, wo=a.output.dense.weight, bo=a.output.dense.bias,
-                           gamma=a.output.LayerNorm.weight, beta=a.output.LayerNorm.bias, h=self.heads, d_k=self.d_head,
-                           d_v=self.d_head, mode=mode, eps=self.eps)
-        return Fn.pwff_block(att, w1=self.intermediate.dense.weight, b1=self.intermediate.dense.bias,
-                             w2=self.output.dense.weight, b2=self.output.dense.bias, gamma=self.output.LayerNorm.weight,
-                             beta=self.output.LayerNorm.bias, mode=mode, eps=self.eps)
+        return M4.bert_layer(self, x, mask, mode, heads=self.heads, q_rows=q_rows, training=self.training)
 
 
 class BertEncoder(nn.Module):
     def __init__(self, d, heads, layers, d_ff=3072, eps=1e-12):
         super().__init__()
         self.layer = nn.ModuleList([BertLayer(d, heads, d_ff, eps) for _ in range(layers)])
+        self.heads = heads
 
     def forward(self, x, mask, mode, last_q_rows=None):
-        n = len(self.layer)
-        for i, layer in enumerate(self.layer):
-            x = layer(x, mask, mode, q_rows=last_q_rows if i == n - 1 else None)
-        return x
+        return M4.bert_encoder(self, x, mask, mode, heads=self.heads, last_q_rows=last_q_rows, training=self.training)
 
 
 class _BertEmbeddings(nn.Module):
@@ -114,10 +77,7 @@ class _BertEmbeddings(nn.Module):
         self.LayerNorm = nn.LayerNorm(d, eps=eps)
 
     def forward(self, ids):
-        L = ids.shape[1]
-        pos_type = self.position_embeddings.weight[:L] + self.token_type_embeddings.weight[0]
-        e = self.word_embeddings(ids)                                   # gather: library op off the hot path
-        return Fn.layer_norm(e + pos_type, self.LayerNorm.weight, self.LayerNorm.bias, self.LayerNorm.eps)
+        return M4.bert_embeddings(self, ids)
 
 
 class TextBert(nn.Module):
@@ -127,13 +87,14 @@ class TextBert(nn.Module):
         super().__init__()
         self.embeddings = _BertEmbeddings(d, vocab_size)
         self.encoder = BertEncoder(d, heads, layers)
+        self.heads = heads
 
     def forward(self, txt_inds, txt_mask, mode):
-        return self.encoder(self.embeddings(txt_inds), txt_mask, mode)
+        return M4.text_bert(self, txt_inds, txt_mask, mode, heads=self.heads)
 
 
 class PrevPredEmbeddings(nn.Module):
-    """mmf_m4c.py:399-445 — parameters only; the arithmetic is ``ovqa_prev_pred_embed``."""
+    """mmf_m4c.py:399-445 — parameters; the arithmetic is ``m4c.prev_pred_embeddings`` (``ovqa_prev_pred_embed``)."""
 
     def __init__(self, d, eps=1e-12, max_dec_length=100, max_type_num=5):
         super().__init__()
@@ -142,21 +103,23 @@ class PrevPredEmbeddings(nn.Module):
         self.ans_layer_norm = nn.LayerNorm(d, eps=eps)
         self.ocr_layer_norm = nn.LayerNorm(d, eps=eps)
         self.emb_layer_norm = nn.LayerNorm(d, eps=eps)
-        self.eps = eps
 
-    def write(self, ans_emb, ocr_emb, prev_inds, out):
-        ln = lambda m: (m.weight, m.bias)
-        return ops.prev_pred_embed(ans_emb, ocr_emb, prev_inds, self.position_embeddings.weight, self.token_type_embeddings.weight,
-                                   ln(self.ans_layer_norm), ln(self.ocr_layer_norm), ln(self.emb_layer_norm), self.eps, out=out)
+    def forward(self, ans_emb, ocr_emb, prev_inds):
+        return M4.prev_pred_embeddings(self, ans_emb, ocr_emb, prev_inds)
 
 
 class MMT(nn.Module):
-    """mmf_m4c.py:283-364 (parameters; the forward is driven by :class:`MMF_M4C`)."""
+    """mmf_m4c.py:283-364."""
 
     def __init__(self, d, heads, layers):
         super().__init__()
         self.prev_pred_embeddings = PrevPredEmbeddings(d)
         self.encoder = BertEncoder(d, heads, layers)
+        self.heads = heads
+
+    def forward(self, txt_emb, txt_mask, obj_emb, obj_mask, ocr_emb, ocr_mask, fixed_ans_emb, prev_inds, mode="fp32"):
+        return M4.mmt_forward(self, txt_emb, txt_mask, obj_emb, obj_mask, ocr_emb, ocr_mask, fixed_ans_emb, prev_inds, heads=self.heads,
+                              mode=mode, training=self.training)
 
 
 class MMF_M4C(nn.Module):
@@ -184,8 +147,7 @@ class MMF_M4C(nn.Module):
         self.ocr_ptr_net = OcrPtrNet(config.OCR_PTR_NET.HIDDEN_SIZE, config.OCR_PTR_NET.QUERY_KEY_SIZE)
         self.classifier = nn.Linear(d, len(vocab))
         self.compute_dtype = getattr(config, "COMPUTE_DTYPE", None)
-        self.ocr_ptr_net.compute_dtype = self.compute_dtype          # the pointer network follows the model's compute dtype (it fell back
-                                                                     # to the global default: two fp32 CUDA-core GEMMs per decode step, 20 % of the decode)
+        self.ocr_ptr_net.compute_dtype = self.compute_dtype          # the pointer network follows the model's compute dtype
         self.prune_last_layer = True
 
     # ------------------------------------------------------------------ step-invariant part (once per batch)
@@ -205,7 +167,7 @@ class MMF_M4C(nn.Module):
         return Fn.layer_norm(y, ln.weight, ln.bias, ln.eps, post_add=post_add)
 
     def encode_inputs(self, items, mode):
-        """_forward_{txt,obj,ocr}_encoding (mmf_m4c.py:128-200) + the TextBert pass hoisted out of the loop."""
+        """_forward_{txt,obj,ocr}_encoding (mmf_m4c.py:128-200): masks and the object / OCR inputs of MMT."""
         txt_mask = generate_padding_mask(items.question_tokens, self.padding_idx)
         obj_box = self._lin_ln(self.linear_obj_bbox_to_mmt_in, self.obj_bbox_layer_norm, items.region_boxes, mode)
         obj = self._lin_ln(self.linear_obj_feat_to_mmt_in, self.obj_feat_layer_norm, items.region_features, mode, post_add=None) + obj_box
@@ -215,73 +177,21 @@ class MMF_M4C(nn.Module):
         ocr_box = self._lin_ln(self.linear_ocr_bbox_to_mmt_in, self.ocr_bbox_layer_norm, items.ocr_boxes, mode)
         ocr = self._lin_ln(self.linear_ocr_feat_to_mmt_in, self.ocr_feat_layer_norm, ocr_feat, mode) + ocr_box
         ocr_mask = generate_padding_mask(ocr_feat, 0)
-        txt = self.text_bert(items.question_tokens, txt_mask, mode)
-        if not isinstance(self.text_bert_out_linear, nn.Identity):
-            txt = Fn.linear(txt, self.text_bert_out_linear.weight, self.text_bert_out_linear.bias, mode)
-        return txt, txt_mask, obj, obj_mask, ocr, ocr_mask
+        return txt_mask, obj, obj_mask, ocr, ocr_mask
 
-    @staticmethod
-    def mmt_mask(txt_mask, obj_mask, ocr_mask, T):
-        """(B,1,L,L) prefix-LM mask of MMT.forward (mmf_m4c.py:310-343), decoder columns open for encoder rows."""
-        B, dev = txt_mask.shape[0], txt_mask.device
-        am = torch.cat([txt_mask, obj_mask, ocr_mask, torch.zeros((B, 1, 1, T), device=dev)], dim=-1).float()
-        L = am.shape[-1]
-        ext = am.repeat(1, 1, L, 1)
-        ext[:, :, -T:, -T:] = generate_sequential_mask(T, dev)
-        ext = ext.contiguous()
-        # structure hint for the attention core: the dense tensor is a per-key row plus a causal T x T tail, which the
-        # tensor-memory kernel evaluates without reading (B, L, L) floats per launch (ops.sdpa_fwd; dense mask otherwise)
-        ext._ovqa_prefix_lm = (am.contiguous(), T, float(MASK_VALUE))
-        return ext
+    mmt_mask = staticmethod(M4.mmt_mask)
 
     # ------------------------------------------------------------------ decode
-    class State:
-        pass
-
     def prepare(self, items):
-        """Allocate the persistent decode buffers for a batch and run the step-invariant part."""
+        """Allocate the persistent decode buffers for a batch and run the step-invariant part (incl. the hoisted TextBert pass)."""
         mode = self._mode()
-        txt, txt_mask, obj, obj_mask, ocr, ocr_mask = self.encode_inputs(items, mode)
-        B, dev = txt.shape[0], txt.device
-        T, D = self.max_iter, self.d
-        Lt, No, Nc = txt.shape[1], obj.shape[1], ocr.shape[1]
-        st = self.State()
-        st.mode, st.B, st.T, st.Lt, st.No, st.Nc = mode, B, T, Lt, No, Nc
-        st.L = Lt + No + Nc + T
-        st.x = torch.empty((B, st.L, D), device=dev, dtype=torch.float32)
-        st.x[:, :Lt], st.x[:, Lt:Lt + No], st.x[:, Lt + No:Lt + No + Nc] = txt, obj, ocr
-        st.ocr_in = ocr.contiguous()
-        st.ocr_mask = ocr_mask
-        st.mask = self.mmt_mask(txt_mask, obj_mask, ocr_mask, T)
-        st.V = self.classifier.weight.shape[0]
-        st.W = st.V + Nc
-        st.Wp = (st.W + 3) // 4 * 4                                        # row pitch of the score buffer: 16-byte rows
-        st.scores = torch.full((B, T, st.Wp), float("-inf"), device=dev, dtype=torch.float32)
-        st.prev_inds = torch.zeros((B, T), dtype=torch.long, device=dev)
-        st.prev_inds[:, 0] = self.bos_idx
-        st.last_ids = torch.zeros((B,), dtype=torch.long, device=dev)
-        st.argmax = torch.empty((B, T), dtype=torch.long, device=dev)
-        st.all_eos = torch.zeros((1,), dtype=torch.int32, device=dev)
-        st.rows = slice(Lt + No, st.L)                                     # OCR + decoder rows: all the last layer must produce
-        return st
+        txt_mask, obj, obj_mask, ocr, ocr_mask = self.encode_inputs(items, mode)
+        txt = M4.encode_text(self, items.question_tokens, txt_mask, mode)
+        return M4.prepare_decode(self, txt, txt_mask, obj, obj_mask, ocr, ocr_mask, mode)
 
     def step(self, st, ith):
         """One _forward_mmt + _forward_output + greedy update (mmf_m4c.py:202-229,247-253)."""
-        mode = st.mode
-        self.mmt.prev_pred_embeddings.write(self.classifier.weight, st.ocr_in, st.prev_inds, st.x[:, -st.T:])
-        st.x._ovqa_bf16 = None                                             # the buffer changed in place: drop any shadow
-        if self.prune_last_layer:
-            y = self.mmt.encoder(st.x, st.mask, mode, last_q_rows=st.rows)  # (B, Nc+T, D)
-            ocr_out, dec_out = y[:, :st.Nc], y[:, st.Nc:]
-        else:
-            y = self.mmt.encoder(st.x, st.mask, mode)
-            ocr_out, dec_out = y[:, st.Lt + st.No:st.Lt + st.No + st.Nc], y[:, -st.T:]
-        s2 = st.scores.view(st.B * st.T, st.Wp)
-        dec2 = Fn._operand(dec_out.contiguous(), mode)
-        ops.gemm(dec2, Fn.weights.get([self.classifier.weight], Fn._cdt(mode)), bias=Fn.weights.get([self.classifier.bias], torch.float32),
-                 out=s2[:, :st.V])
-        self.ocr_ptr_net(dec_out.contiguous(), ocr_out.contiguous(), st.ocr_mask, scores_out=st.scores, col_offset=st.V)
-        ops.greedy_step(st.scores, st.prev_inds, st.last_ids, st.argmax, st.all_eos, ith, self.eos_idx)
+        M4.decode_step(self, st, ith, self.prune_last_layer)
 
     @torch.no_grad()
     def forward(self, items, early_exit=True):

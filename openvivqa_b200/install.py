@@ -10,16 +10,23 @@ from __future__ import annotations
 import importlib
 import sys
 
+from . import m4c as M4
 from . import modules as M
 
 _saved = {}
+
+# reference modules that define the M4C classes (mmf_m4c.py:259-459) or verbatim-equivalent copies of them (mmf_sal.py:207-375), with
+# the model class whose greedy loop (mmf_m4c.py:231-256 / mmf_sal.py:179-205) is rebound and whether that model owns a TextBert.
+# Classes other modules import FROM these (mmf_regional_m4c, mmf_iterative_*, mmf_language_adaptive_m4c: `from .mmf_m4c import OcrPtrNet,
+# MMT, PrevPredEmbeddings`) are the same class objects, so patching the methods in place reaches them too.  The variants that use
+# binary masks (mmf_improved_decoding_m4c.py, experimental_mmf_m4c.py) are different arithmetic and stay untouched.
+_M4C_MODULES = {"models.mmf_m4c": ("MMF_M4C", True), "models.mmf_sal": ("MMF_SAL", False)}
 
 _REBIND = {
     "MultiHeadAttention": ("models.modules.attentions", "models.modules.encoders", "models.modules.decoders",
                            "models.modules.SCP"),
     "PositionWiseFeedForward": ("models.modules.positionwise_feed_forward", "models.modules.encoders",
                                 "models.modules.decoders", "models.iterative_mcan"),
-    "OcrPtrNet": ("models.mmf_m4c",),
 }
 
 
@@ -44,7 +51,7 @@ def install(compute_dtype: str | None = None, verbose: bool = False):
     containers = _maybe("models.modules.containers")
     base = containers.Module if containers is not None else M.StatefulModule
     mha = M.make_multi_head_attention(base=base, builder=att_builder.build_attention)
-    classes = {"MultiHeadAttention": mha, "PositionWiseFeedForward": M.PositionWiseFeedForward, "OcrPtrNet": M.OcrPtrNet,
+    classes = {"MultiHeadAttention": mha, "PositionWiseFeedForward": M.PositionWiseFeedForward,
                "ScaledDotProductAttention": M.ScaledDotProductAttention,
                "AugmentedGeometryScaledDotProductAttention": M.AugmentedGeometryScaledDotProductAttention}
     # vision front-end: registered in META_VISION_EMBEDDING (vision_embeddings.py:10)
@@ -63,6 +70,21 @@ def install(compute_dtype: str | None = None, verbose: bool = False):
         # the re-gather closure records its input -> output tensors, so encoder attention can keep its projected keys across beams
         _saved.setdefault(("beam_expand", "_expand_state"), beam_mod.BeamSearch._expand_state)
         beam_mod.BeamSearch._expand_state = M._beam_search_expand_state(_saved[("beam_expand", "_expand_state")])
+    # M4C family: methods of the reference's own classes are rebound in place (state_dict, constructors and HF initialisation stay theirs)
+    for modname, (model_name, with_text_bert) in _M4C_MODULES.items():
+        mod = _maybe(modname)
+        if mod is None:
+            continue
+        bindings = M4.make_reference_bindings(mod, with_text_bert)
+        if hasattr(mod, model_name):
+            bindings[(model_name, "_forward_mmt_and_output")] = M4.make_model_binding(getattr(mod, model_name), with_text_bert)
+        for (owner, attr), fn in bindings.items():
+            target = mod if owner is None else getattr(mod, owner)
+            _saved.setdefault(("m4c", modname, owner, attr), getattr(target, attr))
+            setattr(target, attr, fn)
+            classes[f"{modname}.{owner + '.' if owner else ''}{attr}"] = fn
+            if verbose:
+                print(f"openvivqa_b200: {modname}.{owner + '.' if owner else ''}{attr} -> B200 path")
     for name, mods in _REBIND.items():
         for modname in mods:
             mod = _maybe(modname)
@@ -76,7 +98,13 @@ def install(compute_dtype: str | None = None, verbose: bool = False):
 
 def uninstall():
     """Undo :func:`install` (used by the tests that compare with/without the drop-ins in one process)."""
-    for (where, name), obj in list(_saved.items()):
+    for key, obj in list(_saved.items()):
+        if key[0] == "m4c":
+            _, modname, owner, attr = key
+            mod = sys.modules[modname]
+            setattr(mod if owner is None else getattr(mod, owner), attr, obj)
+            continue
+        where, name = key
         if where == "vision_registry":
             vreg = sys.modules["builders.vision_embedding_builder"].META_VISION_EMBEDDING
             if obj is None:

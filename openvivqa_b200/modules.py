@@ -48,6 +48,7 @@ def _mode_of(module) -> str:
     return module.compute_dtype or _default_mode
 
 
+DECODE_MAX_KEYS = 200 * 1024 // (4 * 4)   # sdpa_decode_kernel keeps one fp32 score row per warp in shared memory (csrc/decode.cu: 4 warps, 200 KB)
 DECODE_MAX_QUERY_ROWS = 16   # the one-warp-per-(row, head) decode kernel is for a handful of query rows; longer blocks use the tiled cores
 
 
@@ -171,7 +172,7 @@ class ScaledDotProductAttention(nn.Module):
         _init_core_linears(self)
 
     def _geo(self, boxes):
-        return None
+        return {}
 
     def forward(self, queries, keys, values, attention_mask=None, **kwargs):
         mode = _mode_of(self)
@@ -179,8 +180,8 @@ class ScaledDotProductAttention(nn.Module):
         q = Fn.linear(queries, self.fc_q.weight, self.fc_q.bias, mode, odt)
         k = Fn.linear(keys, self.fc_k.weight, self.fc_k.bias, mode, odt)
         v = Fn.linear(values, self.fc_v.weight, self.fc_v.bias, mode, odt)
-        ctx, att = Fn.sdpa(q, k, v, attention_mask, h=self.h, d_k=self.d_k, d_v=self.d_v, need_att=True,
-                           geo=self._geo(kwargs.get("boxes")))
+        # `att` is differentiable: direct callers build features from the weights alone (mmf_lorra.py:127-146)
+        ctx, att = Fn.sdpa(q, k, v, attention_mask, h=self.h, d_k=self.d_k, d_v=self.d_v, need_att=True, **self._geo(kwargs.get("boxes")))
         out = Fn.linear(ctx, self.fc_o.weight, self.fc_o.bias, mode)
         return out, att
 
@@ -224,8 +225,8 @@ class AugmentedGeometryScaledDotProductAttention(ScaledDotProductAttention):
     def _geo(self, boxes):
         if boxes is None:
             raise ValueError("AugmentedGeometryScaledDotProductAttention needs `boxes` (B,N,4)")
-        w, b = self.geo_weights()
-        return ops.GeoParams(boxes, w.detach(), b.detach(), self.trignometric_embedding)
+        w, b = self.geo_weights()                       # (cat of the h Linear(d_g, 1): autograd routes the gradient back to each)
+        return dict(boxes=boxes, geo_w=w, geo_b=b, geo_trig=self.trignometric_embedding)
 
     def forward(self, queries, keys, values, boxes=None, attention_mask=None, **kwargs):
         return super().forward(queries, keys, values, attention_mask, boxes=boxes)
@@ -349,9 +350,11 @@ def make_multi_head_attention(base=StatefulModule, builder=None):
             """Decide once per ``statefulness()`` session whether the inference fast path applies, and resolve its operands."""
             ok = (DECODE_KV_CACHE and type(core) is ScaledDotProductAttention and (not self.training or self.dropout.p == 0.0)
                   and (not self.can_be_stateful or self.running_keys.shape[1] == 0))
-            if not ok:
-                return False
             mode = self.compute_dtype or core.compute_dtype or get_compute_dtype()
+            vec = 4 if mode == "fp32" else 8                    # elements per 16-byte vector: the decode kernel's row granularity and width limit
+            ok = ok and all(d % vec == 0 and d <= 32 * vec for d in (core.d_k, core.d_v))
+            if not ok:
+                return False                                    # shapes outside the one-call kernel's range: the tiled blocks (reference bookkeeping)
             kv = dict(wk=core.fc_k.weight, bk=core.fc_k.bias, wv=core.fc_v.weight, bv=core.fc_v.bias, mode=mode)
             plan = Fn.mha_decode_plan(wq=core.fc_q.weight, bq=core.fc_q.bias, wo=core.fc_o.weight, bo=core.fc_o.bias,
                                       gamma=self.layer_norm.weight, beta=self.layer_norm.bias, **kv)
@@ -365,6 +368,12 @@ def make_multi_head_attention(base=StatefulModule, builder=None):
             capacity, so nothing is concatenated either — and the whole block is enqueued by one library call (csrc/decode.cu).  A T-step
             decode does O(T) instead of O(T^2) projection work.  Same outputs: fc_k / fc_v act row by row."""
             kv_src, self_att = None, False
+            if (self._kv_len if sess["stateful"] else 0) + keys.shape[1] > DECODE_MAX_KEYS:
+                if sess["stateful"] and self._kv_len:
+                    raise RuntimeError(f"MultiHeadAttention: the projected-K/V decode cache holds at most {DECODE_MAX_KEYS} positions")
+                if sess["stateful"]:
+                    self._session = False                        # nothing cached yet: this session keeps the reference's bookkeeping
+                return None
             if sess["stateful"]:
                 if self._kv_len == 0 and self._buffers["running_keys"].shape[1] == 0:
                     # the raw running keys / values stay unused on this path; give the states one element per row so that the
@@ -398,7 +407,13 @@ def make_multi_head_attention(base=StatefulModule, builder=None):
         def forward(self, queries, keys, values, attention_mask, **kwargs):
             core = self.attention
             if not isinstance(core, ScaledDotProductAttention):
-                # a core we do not accelerate (memory / adaptive variants): reference composition, their own math
+                # a core we do not accelerate (memory / adaptive variants): reference composition, their own math — including the
+                # running keys / values of a stateful decode, which the reference concatenates for EVERY core (attentions.py:320-325)
+                if self.can_be_stateful and self._is_stateful:
+                    self.running_keys = torch.cat([self.running_keys, keys], 1)
+                    keys = self.running_keys
+                    self.running_values = torch.cat([self.running_values, values], 1)
+                    values = self.running_values
                 out, _ = core(queries, keys, values, attention_mask, **kwargs)
                 out = self.layer_norm(queries + self.dropout(out))
             elif self._is_stateful and self._session is not False and not torch.is_grad_enabled() and (
@@ -467,12 +482,19 @@ class PositionWiseFeedForward(nn.Module):
                              dropout=self.dropout_1.p, training=self.training, eps=self.layer_norm.eps)
 
 
+TOPK_MAX = 16       # kTopkMax of csrc/decode.cu
+
+
 def beam_select(candidate_logprob: torch.Tensor, b_s: int, beam_size: int):
     """``BeamSearch.select`` (beam_search.py:35-38) without the full sort: the ``beam_size`` best of the beam x vocabulary candidates of
     every sample from the row-wise top-k kernel (csrc/decode.cu).  Returns (flat candidate indices (b_s, beam_size) int64, their
     log-probabilities), as the reference does.  Under autograd (self-critical training calls beam search with gradients enabled) the
     values are gathered from the input so they stay differentiable."""
     flat = candidate_logprob.reshape(b_s, -1)
+    if not flat.is_cuda or beam_size > TOPK_MAX or b_s > 65535 or beam_size > flat.shape[1]:
+        # outside the top-k kernel's range (or a CPU run of the reference): the reference's own selection, beam_search.py:36-38
+        logprob, idx = torch.sort(flat, -1, descending=True)
+        return idx[:, :beam_size], logprob[:, :beam_size]
     val, idx = ops.topk_rows(flat.detach().float(), beam_size)
     if torch.is_grad_enabled() and flat.requires_grad:
         val = torch.gather(flat, 1, idx)
@@ -529,7 +551,7 @@ class OcrPtrNet(nn.Module):
     def forward(self, query_inputs, key_inputs, attention_mask, scores_out=None, col_offset=0):
         """``scores_out`` (B,T,W) fp32 + ``col_offset``: write the pointer scores straight into the joint score
         tensor (replaces the ``torch.cat`` at mmf_m4c.py:227).  Inference-only fast path; returns (B,T,Locr)."""
-        mode = _mode_of(self)
+        mode = getattr(self, "compute_dtype", None) or _default_mode          # (also bound over the reference's own class: no such attribute there)
         squeeze = query_inputs.dim() == 2
         if squeeze:
             query_inputs = query_inputs.unsqueeze(1)
@@ -537,10 +559,16 @@ class OcrPtrNet(nn.Module):
         q = Fn.linear(query_inputs, self.query.weight, self.query.bias, mode, odt)
         k = Fn.linear(key_inputs, self.key.weight, self.key.bias, mode, odt)
         B, T, L = q.shape[0], q.shape[1], k.shape[1]
-        if scores_out is None:
-            scores_out, col_offset = torch.empty((B, T, L), device=q.device, dtype=torch.float32), 0
-        ops.ptr_scores(q.detach(), k.detach(), attention_mask, scores_out, col_offset, 1.0 / math.sqrt(self.query_key_size))
-        res = scores_out[..., col_offset:col_offset + L]
+        scale = 1.0 / math.sqrt(self.query_key_size)
+        if torch.is_grad_enabled() and (q.requires_grad or k.requires_grad):
+            if scores_out is not None:
+                raise ValueError("OcrPtrNet: `scores_out` (in-place scores) is an inference-only fast path; call it under torch.no_grad()")
+            res = Fn.ptr_scores(q, k, attention_mask, scale)                # differentiable (mmf_m4c.py:379-396 trains through it)
+        else:
+            if scores_out is None:
+                scores_out, col_offset = torch.empty((B, T, L), device=q.device, dtype=torch.float32), 0
+            ops.ptr_scores(q, k, attention_mask, scores_out, col_offset, scale)
+            res = scores_out[..., col_offset:col_offset + L]
         return res.squeeze(1) if squeeze else res
 
 
@@ -559,5 +587,4 @@ class DynamicPointerNetwork(nn.Module):
         odt = torch.float32 if mode == "fp32" else torch.bfloat16
         q = Fn.linear(query_inputs, self.fc_q.weight, self.fc_q.bias, mode, odt)
         k = Fn.linear(key_inputs, self.fc_k.weight, self.fc_k.bias, mode, odt)
-        scores = torch.empty((q.shape[0], q.shape[1], k.shape[1]), device=q.device, dtype=torch.float32)
-        return ops.ptr_scores(q.detach(), k.detach(), attention_mask, scores, 0, 1.0 / math.sqrt(self.d_model), mask_is_bool=True)
+        return Fn.ptr_scores(q, k, attention_mask, 1.0 / math.sqrt(self.d_model), mask_is_bool=True)

@@ -194,8 +194,14 @@ def sdpa_fwd(q, k, v, *, h: int, d_k: int, d_v: int, mask=None, geo: Optional[Ge
 
 
 def sdpa_bwd(q, k, v, out, dout, lse, dq, dk, dv, *, h: int, d_k: int, d_v: int, mask=None,
-             geo: Optional[GeoParams] = None, geo_dw=None, geo_db=None, scale: Optional[float] = None):
-    _need_cuda(q, k, v, out, dout, lse, dq, dk, dv)
+             geo: Optional[GeoParams] = None, geo_dw=None, geo_db=None, scale: Optional[float] = None, att=None, datt=None):
+    """``att`` / ``datt`` (B,h,Lq,Lk) fp32: the probabilities the forward returned and the gradient arriving through them (a direct
+    caller of the core consumed ``att``, mmf_lorra.py:127-146); both or neither."""
+    _need_cuda(q, k, v, out, dout, lse, dq, dk, dv, att, datt)
+    if datt is not None:
+        if att is None or att.shape != datt.shape or att.dtype != torch.float32:
+            raise ValueError("sdpa_bwd: datt needs the saved fp32 probabilities `att` of the same shape")
+        att, datt = att.contiguous(), datt.float().contiguous()
     B, Lq, Lk = q.shape[0], q.shape[1], k.shape[1]
     mask, sb, sh, sq = _mask_strides(mask, B, h, Lq, Lk)
     if dout.stride(2) != 1:
@@ -213,7 +219,7 @@ def sdpa_bwd(q, k, v, out, dout, lse, dq, dk, dv, *, h: int, d_k: int, d_v: int,
            _p(mask), sb, sh, sq,
            _p(g.boxes) if g else None, _p(g.w) if g else None, _p(g.b) if g else None,
            _p(g.freq) if (g and g.freq is not None) else None, g.d_g if g else 0, int(g.trig) if g else 0,
-           _p(geo_dw), _p(geo_db), float(scale), _DT[q.dtype], _p(lse), _p(delta), _stream())
+           _p(geo_dw), _p(geo_db), float(scale), _DT[q.dtype], _p(lse), _p(delta), _p(att) if datt is not None else None, _p(datt), _stream())
 
 
 def layernorm_fwd(x, gamma, beta, *, residual=None, post_add=None, eps: float = 1e-5, want_f32: bool = True,
@@ -392,12 +398,20 @@ def box_geometry_bias(geo: GeoParams, h: int) -> torch.Tensor:
     return out
 
 
+def _dense_rows(t: torch.Tensor) -> torch.Tensor:
+    """(B, L, d) with unit last stride and batch stride L * row pitch (what the pointer kernels address), else a contiguous copy."""
+    if t.stride(2) != 1 or (t.shape[0] > 1 and t.stride(0) != t.shape[1] * t.stride(1)):
+        return t.contiguous()
+    return t
+
+
 def ptr_scores(q, k, mask, scores, col_offset: int, scale: float, mask_is_bool: bool = False):
     """Writes ``scores[:, :, col_offset:col_offset+L]`` in place (scores: fp32 (B,T,W) contiguous)."""
     _need_cuda(q, k, mask, scores)
     B, T, d = q.shape
     Lk = k.shape[1]
-    if q.stride(2) != 1 or k.stride(2) != 1 or not scores.is_contiguous() or scores.dtype != torch.float32:
+    q, k = _dense_rows(q), _dense_rows(k)
+    if not scores.is_contiguous() or scores.dtype != torch.float32:
         raise ValueError("ptr_scores: bad layout")
     if mask is not None:
         mask = mask.reshape(B, Lk).contiguous()
@@ -405,6 +419,27 @@ def ptr_scores(q, k, mask, scores, col_offset: int, scale: float, mask_is_bool: 
     L.call("ovqa_ptr_scores", _p(q), _p(k), _p(mask), _p(scores), B, T, Lk, d, q.stride(1), k.stride(1), scores.shape[-1],
            col_offset, float(scale), _DT[q.dtype], int(mask_is_bool), _stream())
     return scores
+
+
+def ptr_scores_bwd(dscores, q, k, scale: float, bool_mask=None):
+    """(dq, dk) of ``ptr_scores``: dq = scale * dS k, dk = scale * dS^T q (dscores: fp32 (B,T,L) view with unit last stride; keys a boolean
+    mask filled with -inf carry no gradient)."""
+    _need_cuda(dscores, q, k, bool_mask)
+    B, T, d = q.shape
+    Lk = k.shape[1]
+    if dscores.dtype != torch.float32 or dscores.shape != (B, T, Lk):
+        raise ValueError("ptr_scores_bwd: dscores must be fp32 (B,T,L)")
+    if dscores.stride(2) != 1 or (B > 1 and dscores.stride(0) != T * dscores.stride(1)):
+        dscores = dscores.contiguous()
+    q, k = _dense_rows(q), _dense_rows(k)
+    dq, dk = torch.empty((B, T, d), device=q.device, dtype=q.dtype), torch.empty((B, Lk, d), device=k.device, dtype=k.dtype)
+    if B * T * Lk == 0:
+        return dq.zero_(), dk.zero_()
+    if bool_mask is not None:
+        bool_mask = bool_mask.reshape(B, Lk).to(torch.uint8).contiguous()
+    L.call("ovqa_ptr_scores_bwd", _p(dscores), _p(q), _p(k), _p(bool_mask), _p(dq), _p(dk), B, T, Lk, d, dscores.stride(1), q.stride(1), k.stride(1),
+           d, d, float(scale), _DT[q.dtype], _stream())
+    return dq, dk
 
 
 def prev_pred_embed(ans_emb, ocr_emb, prev_inds, pos_emb, type_emb, ans_ln, ocr_ln, emb_ln, eps: float, out=None):

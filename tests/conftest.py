@@ -7,6 +7,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+if os.path.join(ROOT, "tests") not in sys.path:
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
@@ -26,3 +29,12 @@ def golden():
         return cache[name]
 
     return load
+
+
+@pytest.fixture
+def cpu_ops(monkeypatch):
+    """Every library-backed call replaced by its plain-torch CPU restatement (tests/cpu_ops.py): host logic under test, no kernels."""
+    import cpu_ops as E
+
+    E.install(monkeypatch)
+    return E
