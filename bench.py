@@ -347,6 +347,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()                                   # fail loudly if the CUDA library is missing
     ovqa.set_compute_dtype("bf16")
+    H.bench_library_math().__enter__()           # numerical setup shared with tests/test_gpu_bench_configs.py (TF32 library ops around the path, no autocast)
     torch.manual_seed(0)
     model = H.MCAN(H.mcan_cfg(wl["d_model"], wl["d_feature"], wl["layers"], wl["h"], wl["d_ff"], dropout=wl["dropout"], compute_dtype="bf16"),
                    H.StubVocab(wl["vocab"], wl["answers"])).to(dev).train()
@@ -369,8 +370,7 @@ def run_ours(args):
         """One training step on the static input buffers: fwd + NLL + bwd + Adam.  Capturable."""
         Fn.dropout_stream.advance_on_device(dev)                          # fresh dropout masks every replay (device-side offset)
         feats, toks, ans = static
-        with torch.autocast("cuda", dtype=torch.bfloat16):              # library ops around the hot path (LSTM, embedding Linear, head)
-            logp = net(H.Batch(region_features=feats, question_tokens=toks))
+        logp = H.bench_forward(net, H.Batch(region_features=feats, question_tokens=toks))
         loss = F.nll_loss(logp.float(), ans)
         opt.zero_grad(set_to_none=True)
         loss.backward()

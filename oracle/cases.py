@@ -93,6 +93,11 @@ M4C_SMALL = dict(B=3, Lt=7, Nobj=9, Nocr=5, d_obj=32, hidden=96, heads=4, mmt_la
                  vocab=60, T=6)
 
 
+# BASELINE config 3 at its own shape (what bench.py's m4c_decode workload runs): 20 + 100 + 50 + 12 = 182 positions, hidden 768, 8 heads of
+# 96, 4 MMT + 3 TextBert layers, vocabulary 3000 -> 3050 score columns, 12 greedy steps.  Batch 4 keeps the CPU reference run short.
+M4C_FULL = dict(B=4, Lt=20, Nobj=100, Nocr=50, d_obj=1024, hidden=768, heads=8, mmt_layers=4, text_layers=3, vocab=3000, T=12)
+
+
 def mcan_inputs(c, seed: int = 1):
     return dict(region_features=S.padded_features(c["B"], c["Nv"], c["d_feature"], seed, min_valid=36),
                 question_tokens=S.padded_tokens(c["B"], c["Lt"], c["vocab"], seed, min_len=5))

@@ -193,6 +193,46 @@ def gen_m4c():
     print("m4c.pt decode prev_inds:\n", out["decode"]["prev_inds"])
 
 
+def gen_m4c_full():
+    """The reference MMF_M4C at BASELINE config 3's own shape (cases.M4C_FULL): greedy token sequences (early exit as upstream) and a
+    sample of the scores.  78 M parameters regenerated from seeds; only outputs are stored."""
+    RL.load_m4c()
+    import models.mmf_m4c as M4
+
+    c = C.M4C_FULL
+    cfg = RL.NS(
+        DEVICE="cpu",
+        MMT=RL.NS(HIDDEN_SIZE=c["hidden"], NUM_HIDDEN_LAYERS=c["mmt_layers"], NUM_ATTENTION_HEADS=c["heads"]),
+        TEXT_BERT=RL.NS(HIDDEN_SIZE=c["hidden"], NUM_HIDDEN_LAYERS=c["text_layers"], LOAD_PRETRAINED=False, PRETRAINED_NAME=None),
+        OBJECT_EMBEDDING=RL.NS(D_FEATURE=c["d_obj"], DROPOUT=0.1), OCR_EMBEDDING=RL.NS(D_FEATURE=812, DROPOUT=0.1),
+        OCR_PTR_NET=RL.NS(HIDDEN_SIZE=c["hidden"], QUERY_KEY_SIZE=c["hidden"]),
+    )
+    m = M4.MMF_M4C(cfg, RL.StubVocab(c["vocab"], max_answer_length=c["T"])).eval()
+    spec = _load(m)
+
+    class Items(dict):
+        __getattr__ = dict.__getitem__
+
+    items = Items(batch_size=c["B"], **C.m4c_inputs(c))
+    with torch.no_grad():
+        fwd = {}
+        m._forward_txt_encoding(items, fwd)
+        m._forward_obj_encoding(items, fwd)
+        m._forward_ocr_encoding(items, fwd)
+        # first iteration alone (prev_inds = [bos, 0, ...]): the scores a bf16 run is compared against before any argmax feedback
+        fwd["prev_inds"] = torch.zeros((c["B"], c["T"]), dtype=torch.long)
+        fwd["prev_inds"][:, 0] = 1
+        m._forward_mmt(items, fwd)
+        m._forward_output(items, fwd)
+        first = fwd["scores"].clone()
+        m._forward_mmt_and_output(items, fwd)
+    top2 = fwd["scores"].topk(2, dim=-1).values
+    out = dict(spec=spec, prev_inds=fwd["prev_inds"], first_step_scores=first[:, 0].contiguous(), scores_sample=fwd["scores"][:, :, ::7].contiguous(),
+               top2_margin=(top2[..., 0] - top2[..., 1]).contiguous())
+    torch.save(out, os.path.join(OUT, "m4c_full.pt"))
+    print("m4c_full.pt prev_inds:\n", out["prev_inds"], "\nmin top-2 margin", float(out["top2_margin"].min()))
+
+
 def gen_decoder():
     """DecoderLayer (decoders.py:13-26) run stateless over the whole sequence and one token at a time inside ``statefulness()``
     with a beam-style re-gather of the states half-way (containers.py:26-31, beam_search.py:19-33)."""
@@ -285,7 +325,7 @@ def main():
     RL.load()
     torch.manual_seed(0)
     torch.set_num_threads(min(8, os.cpu_count() or 1))
-    which = sys.argv[1:] or ["attention", "geometry", "masks", "encoders", "mcan", "m4c", "decoder", "beam", "generative"]
+    which = sys.argv[1:] or ["attention", "geometry", "masks", "encoders", "mcan", "m4c", "m4c_full", "decoder", "beam", "generative"]
     for w in which:
         globals()["gen_" + w]()
 

@@ -177,3 +177,16 @@ def test_beam_select(golden, name):
     idx, logprob = R.beam_select(C.beam_inputs(name), b_s, beam)
     g = golden("beam")[name]
     assert torch.equal(idx, g["idx"]) and torch.equal(logprob, g["logprob"])
+
+
+def test_m4c_full_config_greedy_decode_matches_the_reference(golden):
+    """BASELINE config 3 at its own shape (cases.M4C_FULL): the restated decode loop reproduces the REFERENCE's token sequences and scores."""
+    c, g = C.M4C_FULL, golden("m4c_full")
+    p = S.synth_params(g["spec"], 0)
+    x = C.m4c_inputs(c)
+    with torch.no_grad():
+        scores, prev_inds, n = R.m4c_greedy_decode(p, x, max_iter=c["T"], mmt_layers=c["mmt_layers"], text_layers=c["text_layers"],
+                                                   heads=c["heads"], ptr_qk=c["hidden"])
+    assert torch.equal(prev_inds, g["prev_inds"])
+    valid = g["scores_sample"] > -1e4
+    torch.testing.assert_close(scores[:, :, ::7][valid], g["scores_sample"][valid], rtol=1e-4, atol=1e-4)
