@@ -128,7 +128,9 @@ int ovqa_sdpa_fwd_prefix_lm(const void* q, const void* k, const void* v, void* o
  *   (geo_dw [h,d_g], geo_db [h], fp32, ACCUMULATED into) is produced when non-NULL.
  *   `att` / `datt` [B,h,Lq,Lk] fp32 (both or neither; NULL from MultiHeadAttention): the probabilities ovqa_sdpa_fwd returned and the
  *   gradient arriving THROUGH them — a direct caller of the core may consume `att` itself (mmf_lorra.py:118-146 builds its
- *   features from the attention weights), so dP = dout v^T + datt. */
+ *   features from the attention weights), so dP = dout v^T + datt.
+ *   `dbias` [B,h,Lq,Lk] fp32 or NULL: receives dS = P (dP - delta), the gradient of an additive per-(b,h,q,k) term that was passed as
+ *   `mask` — how the box-geometry bias trains its weights (ovqa_geo_bias_fwd / _bwd).  bf16 only (OVQA_ERR_BAD_SHAPE otherwise). */
 int ovqa_sdpa_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout,
                   void* dq, void* dk, void* dv,
                   int64_t B, int64_t h, int64_t Lq, int64_t Lk, int64_t dk_, int64_t dv_,
@@ -139,7 +141,7 @@ int ovqa_sdpa_bwd(const void* q, const void* k, const void* v, const void* out, 
                   int64_t d_g, int geo_trig,
                   float* geo_dw, float* geo_db,
                   float scale, int dtype, const float* lse, float* delta,
-                  const float* att, const float* datt, void* stream);
+                  const float* att, const float* datt, float* dbias, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * LayerNorm over the last dimension with optional fused residual add.
@@ -206,6 +208,18 @@ int ovqa_add_f32(const float* a, const float* b, float* y, int64_t n, void* stre
  * ------------------------------------------------------------------------------------------------- */
 int ovqa_box_geometry_bias(const float* boxes, const float* geo_w, const float* geo_b, const float* geo_freq,
                            float* out, int64_t B, int64_t N, int64_t h, int64_t d_g, int geo_trig, void* stream);
+
+/* Box-geometry attention bias as a tensor (the tensor-core route of AugmentedGeometryScaledDotProductAttention, attentions.py:113-134):
+ *   out[b,hd,i,j] = log(clamp(relu(geo_w[hd] . emb(box_i, box_j) + geo_b[hd]), 1e-6)) [+ key_mask[b*key_mask_sb + j]]      fp32 [B,h,N,N]
+ *   with emb = box_relational_embedding (models/utils.py:102-162), evaluated once per pair for all heads.  The result is passed to
+ *   ovqa_sdpa_fwd / ovqa_sdpa_bwd as `mask` with strides (h*N*N, N*N, N).  ovqa_geo_bias_bwd turns the attention backward's `dbias`
+ *   into the weight gradients: geo_dw [h,d_g], geo_db [h] (fp32, ACCUMULATED into).  h <= 16, d_g <= 64. */
+int ovqa_geo_bias_fwd(const float* boxes, const float* geo_w, const float* geo_b, const float* geo_freq,
+                      const float* key_mask, int64_t key_mask_sb, float* out,
+                      int64_t B, int64_t N, int64_t h, int64_t d_g, int geo_trig, void* stream);
+int ovqa_geo_bias_bwd(const float* boxes, const float* geo_w, const float* geo_b, const float* geo_freq,
+                      const float* dbias, float* geo_dw, float* geo_db,
+                      int64_t B, int64_t N, int64_t h, int64_t d_g, int geo_trig, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * M4C dynamic pointer network and greedy decode step.

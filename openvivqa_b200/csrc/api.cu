@@ -29,7 +29,7 @@ int sdpa_fwd_tc5w_bf16(const SdpaArgs&, cudaStream_t);  // attention_tc5.cu, wid
 bool sdpa_fwd_tc5w_supported(const SdpaArgs&);
 int sdpa_bwd_tc5_bf16(const SdpaArgs&, const void*, void*, void*, void*, int64_t, int64_t, int64_t, int64_t, cudaStream_t);
 bool sdpa_bwd_tc5_supported(const SdpaArgs&, const void*, const void*, const void*, const void*, int64_t, int64_t, int64_t, int64_t);
-int sdpa_bwd_mma_bf16(const SdpaArgs&, const void*, void*, void*, void*, int64_t, int64_t, int64_t, int64_t, cudaStream_t);
+int sdpa_bwd_mma_bf16(const SdpaArgs&, const void*, void*, void*, void*, int64_t, int64_t, int64_t, int64_t, float*, cudaStream_t);
 bool sdpa_bwd_mma_supported(const SdpaArgs&, const void*, const void*, const void*, const void*, int64_t, int64_t, int64_t, int64_t);
 
 }  // namespace ovqa
@@ -146,7 +146,7 @@ extern "C" int ovqa_sdpa_bwd(const void* q, const void* k, const void* v, const 
                              const float* mask, int64_t mask_sb, int64_t mask_sh, int64_t mask_sq, const float* boxes,
                              const float* geo_w, const float* geo_b, const float* geo_freq, int64_t d_g, int geo_trig,
                              float* geo_dw, float* geo_db, float scale, int dtype, const float* lse, float* delta, const float* att,
-                             const float* datt, void* stream) {
+                             const float* datt, float* dbias, void* stream) {
     int rc = check_sdpa(q, k, v, B, h, Lq, Lk, dk_, dv_, boxes, geo_w, geo_b, d_g, geo_trig, dtype);
     if (rc) return rc;
     if (!out || !dout || !dq || !dk || !dv || !lse) return OVQA_ERR_BAD_ARG;
@@ -159,10 +159,11 @@ extern "C" int ovqa_sdpa_bwd(const void* q, const void* k, const void* v, const 
     // debugging aid only: OVQA_SDPA_BWD=simt keeps the bf16 backward on the CUDA-core kernels
     static const bool force_simt = [] { const char* e = getenv("OVQA_SDPA_BWD"); return e && e[0] == 's'; }();
     // a gradient THROUGH the probabilities (datt) is folded into dP by the CUDA-core kernels only
-    if (dtype == OVQA_BF16 && !force_simt && !datt && sdpa_bwd_tc5_supported(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv))
+    if (dtype == OVQA_BF16 && !force_simt && !datt && !dbias && sdpa_bwd_tc5_supported(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv))
         return sdpa_bwd_tc5_bf16(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv, st);
-    if (dtype == OVQA_BF16 && !force_simt && !datt && sdpa_bwd_mma_supported(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv))
-        return sdpa_bwd_mma_bf16(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv, st);
+    if (dtype == OVQA_BF16 && (!force_simt || dbias) && !datt && sdpa_bwd_mma_supported(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv))
+        return sdpa_bwd_mma_bf16(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv, dbias, st);
+    if (dbias) return OVQA_ERR_BAD_SHAPE;          // dS is returned by the warp-tile bf16 kernel only (d in {32, 64, 96}, 16-byte aligned rows)
     if (!delta) return OVQA_ERR_BAD_ARG;
     if (dtype == OVQA_F32) return sdpa_bwd_simt_launch<float>(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv, delta, geo_dw, geo_db, att, datt, st);
     return sdpa_bwd_simt_launch<__nv_bfloat16>(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv, delta, geo_dw, geo_db, att, datt, st);

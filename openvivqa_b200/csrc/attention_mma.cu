@@ -233,6 +233,7 @@ struct SdpaBwdMmaArgs {
     const void* dout;
     void *dq, *dk, *dv;
     int64_t lddo, lddq, lddk, lddv;
+    float* dbias;        // [B,h,Lq,Lk] fp32 or NULL: dS, the gradient of an additive (b,h,q,k) bias such as the box-geometry term
 };
 
 // Register budget: the register file is per SM sub-partition (16K), so 12 resident warps (3 per sub-partition) may use
@@ -334,6 +335,11 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) sdpa_bwd_mma_kernel(SdpaBwd
                         }
                         s[nt][e] = p_lo * (dp[nt][e] - dl_lo);
                         s[nt][2 + e] = p_hi * (dp[nt][2 + e] - dl_hi);
+                        if (a.dbias && j < Lk) {
+                            float* db = a.dbias + (((int64_t)b * f.h + hd) * Lq) * Lk + j;
+                            if (i_lo < Lq) db[(int64_t)i_lo * Lk] = s[nt][e];
+                            if (i_hi < Lq) db[(int64_t)i_hi * Lk] = s[nt][2 + e];
+                        }
                     }
                 }
                 mma_p_rows<D, BCH>(acc, s, sK + k0 * P, lane);
@@ -495,8 +501,8 @@ bool sdpa_bwd_mma_supported(const SdpaArgs& a, const void* dout, const void* dq,
 }
 
 int sdpa_bwd_mma_bf16(const SdpaArgs& f, const void* dout, void* dq, void* dk, void* dv, int64_t lddo, int64_t lddq, int64_t lddk,
-                      int64_t lddv, cudaStream_t st) {
-    SdpaBwdMmaArgs a{f, dout, dq, dk, dv, lddo, lddq, lddk, lddv};
+                      int64_t lddv, float* dbias, cudaStream_t st) {
+    SdpaBwdMmaArgs a{f, dout, dq, dk, dv, lddo, lddq, lddk, lddv, dbias};
     switch ((int)f.dk) {
         case 32: return launch_bwd<32>(a, st);
         case 64: return launch_bwd<64>(a, st);

@@ -53,11 +53,25 @@ def freeze_unused(model: torch.nn.Module) -> List[str]:
     return names
 
 
-def data_parallel(model: torch.nn.Module, device_ids: Iterable[int] | None = None, bucket_cap_mb: int = 25):
+def data_parallel(model: torch.nn.Module, device_ids: Iterable[int] | None = None, bucket_cap_mb: int = 25, grad_dtype: str = "fp32"):
     """Wrap for data-parallel training: gradient all-reduce in ``bucket_cap_mb`` buckets launched from autograd hooks
-    (overlaps the rest of backward); gradients are bucket views (no extra copy).  No-op for world size 1."""
+    (overlaps the rest of backward); gradients are bucket views (no extra copy).  No-op for world size 1.
+
+    ``grad_dtype="bf16"``: every bucket crosses NVLink as bf16 (cast, all-reduce, cast back and average — the stock
+    ``bf16_compress_hook``): half the bytes, and half the time the collective's CTAs compete with the backward kernels for SMs and HBM
+    ("bf16 grads halve it").  Parameters and optimiser state stay fp32."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return model
     freeze_unused(model)
-    return torch.nn.parallel.DistributedDataParallel(model, device_ids=list(device_ids) if device_ids is not None else None,
-                                                     gradient_as_bucket_view=True, bucket_cap_mb=bucket_cap_mb)
+    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=list(device_ids) if device_ids is not None else None,
+                                                    gradient_as_bucket_view=True, bucket_cap_mb=bucket_cap_mb)
+    net._ovqa_grad_dtype = "fp32"
+    if grad_dtype == "bf16" and next(model.parameters()).is_cuda:
+        from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+        net.register_comm_hook(None, default_hooks.bf16_compress_hook)
+        net._ovqa_grad_dtype = "bf16"
+    return net
+
+
+def grad_dtype_of(net) -> str:
+    return getattr(net, "_ovqa_grad_dtype", "fp32")

@@ -271,6 +271,13 @@ class _MHAFn(torch.autograd.Function):
             proj = (q, k, v)
         geo = ops.GeoParams(boxes, geo_w.detach(), geo_b.detach(), cfg["geo_trig"]) if boxes is not None else None
         need_grad = cfg["grad"] and any(ctx.needs_input_grad)     # (grad mode is always off INSIDE forward: flag taken outside)
+        geo_as_bias = geo is not None and mode == "bf16"
+        if geo_as_bias:
+            # tensor-core route of the geometry core: the box bias (pair embedding evaluated once for all heads) + the padding mask become
+            # one additive (B,h,N,N) tensor for the bf16 attention kernels; backward gets dS back and reduces the fc_g gradients from it
+            per_key = mask is None or (mask.dim() == 4 and mask.shape[1] == 1 and mask.shape[2] == 1)
+            mask = ops.geo_bias(geo, h, key_mask=mask if per_key else None) if per_key else ops.geo_bias(geo, h) + mask
+            geo = None
         att_ctx, lse, _ = ops.sdpa_fwd(q, k, v, h=h, d_k=dk, d_v=dv, mask=mask, geo=geo, scale=cfg["scale"], need_lse=need_grad)
         seed, off = dropout_stream.next(B * Lq * D) if p > 0.0 else (0, 0)
         rng_base = dropout_stream.base(queries.device) if p > 0.0 else None
@@ -287,6 +294,7 @@ class _MHAFn(torch.autograd.Function):
             ctx.n_proj = len(proj)
             ctx.cfg, ctx.p, ctx.seed, ctx.off, ctx.rng_base = cfg, p, seed, off, rng_base
             ctx.flags = (self_att, kv_same)
+            ctx.geo_as_bias = geo_as_bias
             ctx.shapes = (B, Lq, Lk, D)
         y16 = y16.view(B, Lq, D) if y16 is not None else y.new_empty(0)
         ctx.mark_non_differentiable(y16)
@@ -343,8 +351,13 @@ class _MHAFn(torch.autograd.Function):
         else:
             q, k, v = proj
             dq, dk_, dv_ = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-        ops.sdpa_bwd(q, k, v, att_ctx, dctx, lse, dq, dk_, dv_, h=h, d_k=dk, d_v=dv, mask=mask, geo=geo, geo_dw=gdw,
-                     geo_db=gdb, scale=cfg["scale"])
+        if ctx.geo_as_bias:                                      # `mask` is the saved (B,h,N,N) bias: get dS back, reduce the fc_g gradients from it
+            dbias = torch.empty_like(mask)
+            ops.sdpa_bwd(q, k, v, att_ctx, dctx, lse, dq, dk_, dv_, h=h, d_k=dk, d_v=dv, mask=mask, scale=cfg["scale"], dbias=dbias)
+            ops.geo_bias_bwd(geo, h, dbias, gdw, gdb)
+        else:
+            ops.sdpa_bwd(q, k, v, att_ctx, dctx, lse, dq, dk_, dv_, h=h, d_k=dk, d_v=dv, mask=mask, geo=geo, geo_dw=gdw,
+                         geo_db=gdb, scale=cfg["scale"])
         dkeys = dvalues = None
         if self_att:
             d2 = dqkv.view(B * Lq, dqkv.shape[-1])

@@ -194,10 +194,12 @@ def sdpa_fwd(q, k, v, *, h: int, d_k: int, d_v: int, mask=None, geo: Optional[Ge
 
 
 def sdpa_bwd(q, k, v, out, dout, lse, dq, dk, dv, *, h: int, d_k: int, d_v: int, mask=None,
-             geo: Optional[GeoParams] = None, geo_dw=None, geo_db=None, scale: Optional[float] = None, att=None, datt=None):
+             geo: Optional[GeoParams] = None, geo_dw=None, geo_db=None, scale: Optional[float] = None, att=None, datt=None, dbias=None):
     """``att`` / ``datt`` (B,h,Lq,Lk) fp32: the probabilities the forward returned and the gradient arriving through them (a direct
     caller of the core consumed ``att``, mmf_lorra.py:127-146); both or neither."""
-    _need_cuda(q, k, v, out, dout, lse, dq, dk, dv, att, datt)
+    _need_cuda(q, k, v, out, dout, lse, dq, dk, dv, att, datt, dbias)
+    if dbias is not None and (dbias.dtype != torch.float32 or not dbias.is_contiguous() or dbias.shape != (q.shape[0], h, q.shape[1], k.shape[1])):
+        raise ValueError("sdpa_bwd: dbias must be a contiguous fp32 (B,h,Lq,Lk) tensor")
     if datt is not None:
         if att is None or att.shape != datt.shape or att.dtype != torch.float32:
             raise ValueError("sdpa_bwd: datt needs the saved fp32 probabilities `att` of the same shape")
@@ -219,7 +221,7 @@ def sdpa_bwd(q, k, v, out, dout, lse, dq, dk, dv, *, h: int, d_k: int, d_v: int,
            _p(mask), sb, sh, sq,
            _p(g.boxes) if g else None, _p(g.w) if g else None, _p(g.b) if g else None,
            _p(g.freq) if (g and g.freq is not None) else None, g.d_g if g else 0, int(g.trig) if g else 0,
-           _p(geo_dw), _p(geo_db), float(scale), _DT[q.dtype], _p(lse), _p(delta), _p(att) if datt is not None else None, _p(datt), _stream())
+           _p(geo_dw), _p(geo_db), float(scale), _DT[q.dtype], _p(lse), _p(delta), _p(att) if datt is not None else None, _p(datt), _p(dbias), _stream())
 
 
 def layernorm_fwd(x, gamma, beta, *, residual=None, post_add=None, eps: float = 1e-5, want_f32: bool = True,
@@ -419,6 +421,37 @@ def ptr_scores(q, k, mask, scores, col_offset: int, scale: float, mask_is_bool: 
     L.call("ovqa_ptr_scores", _p(q), _p(k), _p(mask), _p(scores), B, T, Lk, d, q.stride(1), k.stride(1), scores.shape[-1],
            col_offset, float(scale), _DT[q.dtype], int(mask_is_bool), _stream())
     return scores
+
+
+def geo_bias(geo: GeoParams, h: int, key_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(B,h,N,N) fp32 additive attention bias ``log(clamp(relu(w_h . emb(box_i, box_j) + b_h), 1e-6)) [+ key_mask[b, j]]`` — the pair
+    embedding is evaluated once for all heads.  ``key_mask``: additive per-key mask (B,1,1,N) / (B,N) / (1,..,N) or None."""
+    _need_cuda(geo.boxes, key_mask)
+    B, N = geo.boxes.shape[:2]
+    out = torch.empty((B, h, N, N), device=geo.boxes.device, dtype=torch.float32)
+    if B * N == 0:
+        return out
+    km, sb = None, 0
+    if key_mask is not None:
+        km = key_mask.reshape(-1, N).float().contiguous()
+        if km.shape[0] not in (1, B):
+            raise ValueError("geo_bias: key_mask must be a per-key mask broadcastable over heads and queries")
+        sb = N if km.shape[0] == B else 0
+    L.call("ovqa_geo_bias_fwd", _p(geo.boxes), _p(geo.w), _p(geo.b), _p(geo.freq) if geo.freq is not None else None, _p(km), sb, _p(out),
+           B, N, h, geo.d_g, int(geo.trig), _stream())
+    return out
+
+
+def geo_bias_bwd(geo: GeoParams, h: int, dbias: torch.Tensor, geo_dw: torch.Tensor, geo_db: torch.Tensor):
+    """Accumulates the geometry weight gradients (geo_dw (h,d_g), geo_db (h), fp32) from ``dbias`` = d loss / d bias (B,h,N,N)."""
+    _need_cuda(geo.boxes, dbias, geo_dw, geo_db)
+    B, N = geo.boxes.shape[:2]
+    if dbias.shape != (B, h, N, N) or dbias.dtype != torch.float32 or not dbias.is_contiguous():
+        raise ValueError("geo_bias_bwd: dbias must be contiguous fp32 (B,h,N,N)")
+    if B * N == 0:
+        return
+    L.call("ovqa_geo_bias_bwd", _p(geo.boxes), _p(geo.w), _p(geo.b), _p(geo.freq) if geo.freq is not None else None, _p(dbias), _p(geo_dw), _p(geo_db),
+           B, N, h, geo.d_g, int(geo.trig), _stream())
 
 
 def ptr_scores_bwd(dscores, q, k, scale: float, bool_mask=None):

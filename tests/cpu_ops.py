@@ -115,6 +115,20 @@ def box_geometry_bias(geo, h):
     return geo_log_bias(geo, h)
 
 
+def geo_bias(geo, h, key_mask=None):
+    out = geo_log_bias(geo, h)
+    if key_mask is not None:
+        out = out + key_mask.reshape(-1, 1, 1, geo.boxes.shape[1]).float()
+    return out.contiguous()
+
+
+def geo_bias_bwd(geo, h, dbias, geo_dw, geo_db):
+    raw, emb = geo_raw(geo, h)
+    coef = torch.where(raw > 1e-6, dbias / raw, torch.zeros_like(dbias))
+    geo_dw += torch.einsum("bhij,bijg->hg", coef, emb)
+    geo_db += coef.sum(dim=(0, 2, 3))
+
+
 def sdpa_fwd(q, k, v, *, h, d_k, d_v, mask=None, geo=None, scale=None, need_lse=False, need_att=False, out=None):
     B, Lq, Lk = q.shape[0], q.shape[1], k.shape[1]
     scale = 1.0 / math.sqrt(d_k) if scale is None else scale
@@ -129,7 +143,7 @@ def sdpa_fwd(q, k, v, *, h, d_k, d_v, mask=None, geo=None, scale=None, need_lse=
 
 
 def sdpa_bwd(q, k, v, out, dout, lse, dq, dk, dv, *, h, d_k, d_v, mask=None, geo=None, geo_dw=None, geo_db=None, scale=None,
-             att=None, datt=None):
+             att=None, datt=None, dbias=None):
     B, Lq, Lk = q.shape[0], q.shape[1], k.shape[1]
     scale = 1.0 / math.sqrt(d_k) if scale is None else scale
     s = _scores(q, k, h, d_k, mask, geo, scale)
@@ -142,6 +156,8 @@ def sdpa_bwd(q, k, v, out, dout, lse, dq, dk, dv, *, h, d_k, d_v, mask=None, geo
     if datt is not None:
         dp = dp + datt.float()
     ds = p * (dp - (p * dp).sum(-1, keepdim=True))
+    if dbias is not None:
+        dbias.copy_(ds)
     dv.copy_((p.transpose(-1, -2) @ do).permute(0, 2, 1, 3).reshape(B, Lk, h * d_v).to(dv.dtype))
     dq.copy_(((ds @ kh) * scale).permute(0, 2, 1, 3).reshape(B, Lq, h * d_k).to(dq.dtype))
     dk.copy_(((ds.transpose(-1, -2) @ qh) * scale).permute(0, 2, 1, 3).reshape(B, Lk, h * d_k).to(dk.dtype))
@@ -313,7 +329,7 @@ def pwff_infer_block(plan, x, *, d_ff, eps=1e-5):
 
 
 OPS = ("gemm", "sdpa_fwd", "sdpa_bwd", "layernorm_fwd", "layernorm_bwd", "cast_rows_padmask", "mul_to_bf16", "to_bf16", "to_f32", "colsum",
-       "add", "dropout_apply", "dropout_keep_mask", "stage_many", "advance_u64", "box_geometry_bias", "ptr_scores", "ptr_scores_bwd",
+       "add", "dropout_apply", "dropout_keep_mask", "stage_many", "advance_u64", "box_geometry_bias", "geo_bias", "geo_bias_bwd", "ptr_scores", "ptr_scores_bwd",
        "prev_pred_embed", "greedy_step", "topk_rows", "mha_decode_step", "pwff_infer")
 
 

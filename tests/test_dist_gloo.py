@@ -73,7 +73,8 @@ def test_gloo_world2_host_logic():
 
 
 def test_reference_arm_rank0_only_prints():
-    env = dict(os.environ, WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29999", OMP_NUM_THREADS="4")
+    env = dict(os.environ, WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29999", OMP_NUM_THREADS="4",
+               OVQA_REFERENCE_ARM_BATCH="8", OVQA_REFERENCE_ARM_M4C_BATCH="1")        # (bounded: the arm's default is the workload's batch of 256)
     outs = []
     for rank in (0, 1):
         r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
@@ -83,4 +84,5 @@ def test_reference_arm_rank0_only_prints():
     assert len(outs[0]) == 1 and outs[1] == []
     line = json.loads(outs[0][0])
     assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] == 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["unit"] == "samples/s"
+    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["unit"] == "samples/s"
+    assert line["m4c_decode"]["value"] > 0

@@ -228,3 +228,30 @@ def test_stateful_decode_of_a_foreign_core_keeps_the_running_keys(cpu_ops):
         for _ in range(3):
             m(torch.randn(2, 1, D), torch.randn(2, 1, D), torch.randn(2, 1, D), None)
     assert seen == [1, 2, 3]
+
+
+@pytest.mark.parametrize("masked", [False, True])
+def test_geometry_block_bf16_route_returns_the_geometry_gradients(cpu_ops, masked):
+    """bf16 mode sends the box-geometry term to the attention kernels as an additive (B,h,N,N) bias and reduces the fc_g gradients from
+    the dS the backward kernel returns; host logic of that route (bias + padding mask combination, saved tensors, gradient plumbing)."""
+    D, h, B, N = 64, 4, 2, 9
+    params = S.synth_params(C.att_spec(D, h, D // h, D // h, geometry_dg=D // h), 4)
+    x = S.padded_features(B, N, D, 3, min_valid=4, relu_like=False)
+    boxes = S.boxes(B, N, 5)
+    mask = R.padding_mask(x, 0) if masked else None
+    pr = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    xr = x.clone().requires_grad_(True)
+    ref = R.mha(pr, xr, xr, xr, mask, h=h, d_k=D // h, d_v=D // h, boxes=boxes, d_g=D // h, trig=True)
+    w = torch.randn(ref.shape, generator=torch.Generator().manual_seed(5))
+    (ref * w).sum().backward()
+    m = ovqa.MultiHeadAttention(H.attention_cfg(D, h, dropout=0.0, arch="AugmentedGeometryScaledDotProductAttention", compute_dtype="bf16")).train()
+    m.load_state_dict(params, strict=True)
+    xi = x.clone().requires_grad_(True)
+    y = m(xi, xi, xi, mask, boxes=boxes)
+    (y * w).sum().backward()
+    _close(y.detach(), ref.detach(), 3e-2)                               # (the emulated library rounds operands to bf16 in this mode)
+    for i in range(h):
+        g, gr = m.attention.fc_gs[i].weight.grad, pr[f"attention.fc_gs.{i}.weight"].grad
+        assert g is not None and float((g - gr).norm() / gr.norm().clamp_min(1e-9)) < 0.1, i
+        gb, gbr = m.attention.fc_gs[i].bias.grad, pr[f"attention.fc_gs.{i}.bias"].grad
+        assert float((gb - gbr).abs().max()) <= 0.1 * float(gbr.abs().max()) + 1e-4

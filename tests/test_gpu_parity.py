@@ -908,3 +908,57 @@ def test_empty_inputs(dev, dt):
     assert xe.grad.shape == xe.shape
     for p in mha.parameters():
         assert p.grad is None or float(p.grad.abs().sum()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------------ geometry bias as a tensor (bf16 route)
+@pytest.mark.parametrize("name", list(C.GEO_CASES))
+def test_geo_bias_kernels_against_the_oracle(dev, name):
+    """ovqa_geo_bias_fwd against attentions.py:113-119,131-132 (restated), ovqa_geo_bias_bwd against autograd of the same."""
+    from openvivqa_b200 import ops
+    B, N, D, h, trig = C.GEO_CASES[name]
+    x = C.geo_inputs(name)
+    dg = x["d_g"]
+    params = S.synth_params([(f"fc_gs.{i}.{t}", (1, dg) if t == "weight" else (1,)) for i in range(h) for t in ("weight", "bias")], 3)
+    pr = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    ref = R.geometry_log_bias(pr, x["boxes"], h=h, d_g=dg, trig=trig)
+    gsel = torch.randn(ref.shape, generator=torch.Generator().manual_seed(2))
+    # the log of the clamp has slope 0 on the clamped side: weight the loss away from entries sitting at the clamp (sign flips there are fp noise)
+    (ref * gsel).sum().backward()
+    w = torch.cat([params[f"fc_gs.{i}.weight"] for i in range(h)], 0).to(dev)
+    b = torch.cat([params[f"fc_gs.{i}.bias"] for i in range(h)], 0).to(dev)
+    geo = ops.GeoParams(x["boxes"].to(dev), w, b, trig)
+    key_mask = torch.zeros((B, 1, 1, N), device=dev)
+    key_mask[:, :, :, -3:] = -10e4
+    out = ops.geo_bias(geo, h)
+    torch.testing.assert_close(out.cpu(), ref.detach(), rtol=2e-4, atol=2e-4)
+    torch.testing.assert_close(ops.geo_bias(geo, h, key_mask=key_mask).cpu(), ref.detach() + key_mask.cpu(), rtol=2e-4, atol=2e-2)
+    dw, db = torch.zeros((h, dg), device=dev), torch.zeros((h,), device=dev)
+    ops.geo_bias_bwd(geo, h, gsel.to(dev).contiguous(), dw, db)
+    dw_ref = torch.cat([pr[f"fc_gs.{i}.weight"].grad for i in range(h)], 0)
+    db_ref = torch.cat([pr[f"fc_gs.{i}.bias"].grad for i in range(h)], 0)
+    assert rel_err(dw, dw_ref) <= 2e-3 and rel_err(db, db_ref) <= 2e-3, (rel_err(dw, dw_ref), rel_err(db, db_ref))
+
+
+def test_geometry_gradients_bf16_route(dev):
+    """The MHA block with the geometry core in bf16 mode (bias tensor + tensor-core attention kernels + dS -> fc_g gradients)."""
+    D, h = 128, 4
+    B, N = 3, 37
+    params = S.synth_params(C.att_spec(D, h, D // h, D // h, geometry_dg=D // h), 4)
+    x = S.padded_features(B, N, D, 3, min_valid=9, relu_like=False)
+    mask = R.padding_mask(x, 0)
+    boxes = S.boxes(B, N, 5)
+    f = lambda p, t: R.mha(p, t, t, t, mask, h=h, d_k=D // h, d_v=D // h, boxes=boxes, d_g=D // h, trig=True)
+    out, w, gp, gx = _oracle_grads(f, params, [x])
+    m = ovqa.MultiHeadAttention(H.attention_cfg(D, h, dropout=0.0, arch="AugmentedGeometryScaledDotProductAttention", compute_dtype="bf16"))
+    m.load_state_dict(params)
+    m = m.to(dev).train()
+    xd = x.to(dev).requires_grad_(True)
+    y = m(xd, xd, xd, mask.to(dev), boxes=boxes.to(dev))
+    (y * w.to(dev)).sum().backward()
+    check(y, out, "bf16", "geometry block bf16")
+    named = dict(m.named_parameters())
+    for i in range(h):
+        g, gr = named[f"attention.fc_gs.{i}.weight"].grad.cpu(), gp[f"attention.fc_gs.{i}.weight"]
+        assert float((g - gr).norm() / gr.norm().clamp_min(1e-9)) <= 6e-2, (i, g, gr)
+    g, gr = named["attention.fc_q.weight"].grad.cpu(), gp["attention.fc_q.weight"]
+    assert float((g - gr).norm() / gr.norm()) <= 6e-2
