@@ -384,7 +384,10 @@ class GemmMeter:
                      to_bf16=y_io("to_bf16"), to_f32=y_io("to_f32"), add=y_io("add"), dropout_apply=y_io("dropout_apply"),
                      ptr_scores=lambda a, kw, out: (nbytes(a[0], a[1]) + 4.0 * a[0].shape[0] * a[0].shape[1] * a[1].shape[1], "ptr_scores"),
                      prev_pred_embed=lambda a, kw, out: (nbytes(out if torch.is_tensor(out) else None) * 2, "prev_pred_embed"),
-                     greedy_step=lambda a, kw, out: (nbytes(a[0]), "greedy_step"))
+                     greedy_step=lambda a, kw, out: (nbytes(a[0]), "greedy_step"),
+                     # geometry bias: boxes in, (B,h,N,N) fp32 out (forward) / in (backward)
+                     geo_bias=lambda a, kw, out: (nbytes(a[0].boxes) + nbytes(out if torch.is_tensor(out) else None), f"geo_bias {tuple(out.shape)}"),
+                     geo_bias_bwd=lambda a, kw, out: (nbytes(a[0].boxes) + nbytes(a[2]), f"geo_bias_bwd {tuple(a[2].shape)}"))
         for name, fn_bytes in table.items():
             if not hasattr(ops, name):
                 continue
@@ -439,9 +442,11 @@ METER = GemmMeter()
 def meter_step(meter, body, use_graph, prepare=None):
     """Run ``body`` once more with an event pair around every library launch; returns (ms of the instrumented step, how, graph).
     With graphs: a second, instrumented capture (event-record nodes), replayed twice; otherwise eager events."""
+    from openvivqa_b200 import functional as Fn
     meter.reset()
     meter.enabled = True
     g2 = None
+    one_call, Fn.ONE_CALL_INFERENCE = Fn.ONE_CALL_INFERENCE, False      # the same kernels, enqueued op by op so that each launch can be bracketed
     try:
         if not use_graph:
             raise RuntimeError("graphs disabled")
@@ -471,6 +476,7 @@ def meter_step(meter, body, use_graph, prepare=None):
         ms, how = e_a.elapsed_time(e_b), ("CUDA events around every library launch during 1 eager step after the timed regions (host launch gaps "
                                           f"included; graph metering unavailable: {repr(e)[:80]})")
     meter.enabled = False
+    Fn.ONE_CALL_INFERENCE = one_call
     return ms, how, g2
 
 

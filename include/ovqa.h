@@ -287,6 +287,24 @@ int ovqa_mha_decode_step(const float* x_f32, const void* x_op, const void* kv_sr
                          float scale, int dtype, void* workspace, int64_t workspace_bytes,
                          float* y_f32, void* y_op, void* stream);
 
+/* MultiHeadAttention block, inference, ONE call (attentions.py:319-331 + :46-60 in eval mode): projection GEMM(s) over the fused
+ *   [Wq; Wk; Wv] operand -> attention core -> fc_o + bias + residual -> LayerNorm.  Same arithmetic as the per-op entry points above; what it
+ *   removes is host dispatch (one FFI call instead of six), which bounds the block below batch ~256.
+ *   kind 0: self-attention (xk / xv ignored, Lk == Lq);  1: keys == values (xk [B*Lk, D]);  2: three inputs.
+ *   x*_f32: fp32 rows (xq_f32 is also the residual); x*_op: the same rows in the compute dtype (bf16) or NULL (cast into the workspace);
+ *           for dtype fp32 the *_op pointers are ignored and xk / xv are fp32.
+ *   w_qkv [(2*h*dk + h*dv), D] = [Wq; Wk; Wv] row-major in the compute dtype, b_qkv fp32;  w_o [D, h*dv], b_o [D];  gamma / beta [D].
+ *   mask: additive fp32 with element strides (0 = broadcast) or NULL.  prefix_*: optional structured description of the SAME mask (per-key
+ *           row + causal tail, see ovqa_sdpa_fwd_prefix_lm): used when that kernel supports the shape, the dense mask otherwise.
+ *   y_f32 [B*Lq, D] fp32, y_op: optional bf16 copy.  Workspace: ovqa_mha_block_infer_workspace_bytes. */
+int64_t ovqa_mha_block_infer_workspace_bytes(int64_t B, int64_t Lq, int64_t Lk, int64_t D, int64_t h, int64_t dk, int64_t dv, int kind, int dtype);
+int ovqa_mha_block_infer(const float* xq_f32, const void* xq_op, const void* xk, const void* xk_op, const void* xv, const void* xv_op,
+                         int kind, int64_t B, int64_t Lq, int64_t Lk, int64_t D, int64_t h, int64_t dk, int64_t dv,
+                         const void* w_qkv, const float* b_qkv, const void* w_o, const float* b_o, const float* gamma, const float* beta, float eps,
+                         const float* mask, int64_t mask_sb, int64_t mask_sh, int64_t mask_sq,
+                         const float* prefix_key_mask, int64_t prefix_sb, int64_t prefix_tail, float prefix_value,
+                         float scale, int dtype, void* workspace, int64_t workspace_bytes, float* y_f32, void* y_op, void* stream);
+
 /* PositionWiseFeedForward in eval mode from one call (positionwise_feed_forward.py:23-27, dropout off):
  *   y = LayerNorm(x + fc2(gelu(fc1 x)));  x_f32 [rows, D], x_op as above;  w1 [d_ff, D], w2 [D, d_ff] compute dtype; biases fp32. */
 int64_t ovqa_pwff_infer_workspace_bytes(int64_t rows, int64_t D, int64_t d_ff, int dtype);

@@ -33,6 +33,9 @@ _PROTOS = {
     "ovqa_mha_decode_step": [_vp, _vp, _vp, _i32, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _i64, _i64,
                              _vp, _i64, _i64, _i64, _f32, _i32, _vp, _i64, _vp, _vp, _vp],
     "ovqa_mha_decode_workspace_bytes": [_i64] * 7 + [_i32],
+    "ovqa_mha_block_infer_workspace_bytes": [_i64] * 7 + [_i32, _i32],
+    "ovqa_mha_block_infer": [_vp] * 6 + [_i32] + [_i64] * 7 + [_vp] * 6 + [_f32, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _f32, _f32, _i32, _vp, _i64,
+                             _vp, _vp, _vp],
     "ovqa_pwff_infer_workspace_bytes": [_i64, _i64, _i64, _i32],
     "ovqa_topk_rows_workspace_bytes": [_i64, _i64, _i32],
     "ovqa_topk_rows": [_vp, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _i64, _vp],
@@ -64,7 +67,7 @@ _PROTOS = {
     "ovqa_dropout_mask": [_vp, _i64, _f32, _u64, _u64, _vp, _vp],
 }
 _RESTYPES = {"ovqa_error_string": C.c_char_p, "ovqa_launch_count": C.c_uint64, "ovqa_mha_decode_workspace_bytes": C.c_int64,
-             "ovqa_pwff_infer_workspace_bytes": C.c_int64, "ovqa_topk_rows_workspace_bytes": C.c_int64}
+             "ovqa_pwff_infer_workspace_bytes": C.c_int64, "ovqa_topk_rows_workspace_bytes": C.c_int64, "ovqa_mha_block_infer_workspace_bytes": C.c_int64}
 
 _lib = None
 _lock = threading.Lock()

@@ -367,6 +367,93 @@ extern "C" int ovqa_mha_decode_step(const float* x_f32, const void* x_op, const 
                               D, eps, stream);
 }
 
+// ----------------------------------------------------------------------------- whole MHA block, inference, one call
+// MultiHeadAttention.forward in eval mode (attentions.py:319-331 with :46-60): projection GEMM(s) over the fused [Wq; Wk; Wv] operand ->
+// attention core -> fc_o + bias + residual -> LayerNorm, enqueued back to back from C.  The Python block (functional.mha_block) costs
+// ~190 us of host dispatch (six library calls, each through ctypes, with their allocations): at batch 16-64 that is more than the GPU
+// work and made the drop-in slower than eager PyTorch (profiles/r01l_microbench.jsonl); this entry leaves one ctypes call.
+//   kind 0: self-attention (keys = values = queries): one GEMM over the whole fused weight
+//   kind 1: keys = values != queries: fc_q over the query rows, [fc_k | fc_v] over the key rows in one GEMM
+//   kind 2: three different inputs: three GEMMs
+extern "C" int64_t ovqa_mha_block_infer_workspace_bytes(int64_t B, int64_t Lq, int64_t Lk, int64_t D, int64_t h, int64_t dk, int64_t dv, int kind,
+                                                        int dtype) {
+    const int64_t e = dtype == OVQA_BF16 ? 2 : 4, hk = h * dk, hv = h * dv, rq = B * Lq, rk = B * Lk;
+    int64_t n = up256(rq * D * e) + up256(rq * hv * e) + up256(rq * D * 4);                      // query operand, context, fc_o + residual sum
+    if (kind == 0) n += up256(rq * (2 * hk + hv) * e);
+    else n += up256(rq * hk * e) + up256(rk * (hk + hv) * e) + (kind == 1 ? 1 : 2) * up256(rk * D * e);
+    return n;
+}
+
+extern "C" int ovqa_mha_block_infer(const float* xq_f32, const void* xq_op, const void* xk, const void* xk_op, const void* xv, const void* xv_op,
+                                    int kind, int64_t B, int64_t Lq, int64_t Lk, int64_t D, int64_t h, int64_t dk, int64_t dv, const void* w_qkv,
+                                    const float* b_qkv, const void* w_o, const float* b_o, const float* gamma, const float* beta, float eps,
+                                    const float* mask, int64_t mask_sb, int64_t mask_sh, int64_t mask_sq, const float* prefix_key_mask,
+                                    int64_t prefix_sb, int64_t prefix_tail, float prefix_value, float scale, int dtype, void* workspace,
+                                    int64_t workspace_bytes, float* y_f32, void* y_op, void* stream) {
+    if (!xq_f32 || !w_qkv || !b_qkv || !w_o || !b_o || !gamma || !beta || !y_f32) return OVQA_ERR_BAD_ARG;
+    if (B < 0 || Lq < 0 || Lk <= 0 || D <= 0 || h <= 0 || dk <= 0 || dv <= 0 || kind < 0 || kind > 2) return OVQA_ERR_BAD_ARG;
+    if (dtype != OVQA_F32 && dtype != OVQA_BF16) return OVQA_ERR_BAD_ARG;
+    if ((kind == 0 && Lk != Lq) || (kind >= 1 && !xk) || (kind == 2 && !xv)) return OVQA_ERR_BAD_ARG;
+    if (B == 0 || Lq == 0) return OVQA_OK;
+    if (!workspace || workspace_bytes < ovqa_mha_block_infer_workspace_bytes(B, Lq, Lk, D, h, dk, dv, kind, dtype)) return OVQA_ERR_BAD_ARG;
+    const int64_t e = dtype == OVQA_BF16 ? 2 : 4, hk = h * dk, hv = h * dv, rq = B * Lq, rk = B * Lk;
+    char* ws = reinterpret_cast<char*>(workspace);
+    void* ws_xq = ws;        ws += up256(rq * D * e);
+    void* ws_ctx = ws;       ws += up256(rq * hv * e);
+    float* ws_s = reinterpret_cast<float*>(ws);   ws += up256(rq * D * 4);
+    int rc;
+    // operands in the compute dtype: fp32 inputs are used as they are; bf16 takes the caller's shadow copy or casts here
+    auto operand = [&](const void* f32, const void* op, void* scratch, int64_t rows, const void** out) -> int {
+        if (dtype == OVQA_F32) { *out = f32; return OVQA_OK; }
+        if (op) { *out = op; return OVQA_OK; }
+        *out = scratch;
+        return ovqa_cast_f32_to_bf16(reinterpret_cast<const float*>(f32), scratch, rows * D, stream);
+    };
+    const void* q_in;
+    if ((rc = operand(xq_f32, xq_op, ws_xq, rq, &q_in))) return rc;
+    const char* wq = reinterpret_cast<const char*>(w_qkv);
+    const void *q, *k, *v;
+    int64_t ldq, ldk, ldv;
+    if (kind == 0) {
+        void* qkv = ws;      ws += up256(rq * (2 * hk + hv) * e);
+        if ((rc = plain_gemm(q_in, w_qkv, qkv, rq, 2 * hk + hv, D, D, D, 2 * hk + hv, dtype, dtype, b_qkv, 0, nullptr, 0, stream))) return rc;
+        q = qkv; k = reinterpret_cast<char*>(qkv) + hk * e; v = reinterpret_cast<char*>(qkv) + 2 * hk * e;
+        ldq = ldk = ldv = 2 * hk + hv;
+    } else {
+        void* qb = ws;       ws += up256(rq * hk * e);
+        void* kvb = ws;      ws += up256(rk * (hk + hv) * e);
+        void* ws_xk = ws;    ws += up256(rk * D * e);
+        if ((rc = plain_gemm(q_in, w_qkv, qb, rq, hk, D, D, D, hk, dtype, dtype, b_qkv, 0, nullptr, 0, stream))) return rc;
+        const void* k_in;
+        if ((rc = operand(xk, xk_op, ws_xk, rk, &k_in))) return rc;
+        if (kind == 1) {
+            if ((rc = plain_gemm(k_in, wq + hk * D * e, kvb, rk, hk + hv, D, D, D, hk + hv, dtype, dtype, b_qkv + hk, 0, nullptr, 0, stream))) return rc;
+        } else {
+            void* ws_xv = ws;    ws += up256(rk * D * e);
+            const void* v_in;
+            if ((rc = operand(xv, xv_op, ws_xv, rk, &v_in))) return rc;
+            if ((rc = plain_gemm(k_in, wq + hk * D * e, kvb, rk, hk, D, D, D, hk + hv, dtype, dtype, b_qkv + hk, 0, nullptr, 0, stream))) return rc;
+            if ((rc = plain_gemm(v_in, wq + 2 * hk * D * e, reinterpret_cast<char*>(kvb) + hk * e, rk, hv, D, D, D, hk + hv, dtype, dtype, b_qkv + 2 * hk, 0,
+                                 nullptr, 0, stream))) return rc;
+        }
+        q = qb; k = kvb; v = reinterpret_cast<char*>(kvb) + hk * e;
+        ldq = hk; ldk = ldv = hk + hv;
+    }
+    // attention core: the structured prefix-LM form when the caller described one and this shape has that kernel, else the dense mask
+    rc = OVQA_ERR_BAD_SHAPE;
+    if (prefix_key_mask)
+        rc = ovqa_sdpa_fwd_prefix_lm(q, k, v, ws_ctx, B, h, Lq, Lk, dk, dv, ldq, ldk, ldv, hv, prefix_key_mask, prefix_sb, prefix_tail, prefix_value,
+                                     scale, dtype, nullptr, stream);
+    if (rc == OVQA_ERR_BAD_SHAPE)
+        rc = ovqa_sdpa_fwd(q, k, v, ws_ctx, B, h, Lq, Lk, dk, dv, ldq, ldk, ldv, hv, mask, mask_sb, mask_sh, mask_sq, nullptr, nullptr, nullptr, nullptr, 0,
+                           0, scale, dtype, nullptr, nullptr, stream);
+    if (rc) return rc;
+    // fc_o + bias + residual, then LayerNorm   (attentions.py:58, :330-331 with dropout off)
+    if ((rc = plain_gemm(ws_ctx, w_o, ws_s, rq, D, hv, hv, hv, D, dtype, OVQA_F32, b_o, 0, xq_f32, D, stream))) return rc;
+    return ovqa_layernorm_fwd(ws_s, nullptr, gamma, beta, nullptr, 0, y_f32, dtype == OVQA_BF16 ? y_op : nullptr, nullptr, nullptr, nullptr, rq, D,
+                              eps, stream);
+}
+
 extern "C" int64_t ovqa_pwff_infer_workspace_bytes(int64_t rows, int64_t D, int64_t d_ff, int dtype) {
     const int64_t e = dtype == OVQA_BF16 ? 2 : 4;
     return up256(rows * D * e) + up256(rows * d_ff * e) + up256(rows * D * 4);

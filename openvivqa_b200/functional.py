@@ -383,8 +383,51 @@ class _MHAFn(torch.autograd.Function):
         return (dqueries, dkeys, dvalues, None, None, dwq, dbq, dwk, dbk, dwv, dbv, dwo, dbo, dgamma, dbeta, gdw, gdb, None)
 
 
+ONE_CALL_INFERENCE = True      # eval-mode blocks without autograd go through ONE library call (ovqa_mha_block_infer); bench.py switches it off
+                               # while it meters the individual kernels of a step
+_block_plans = {}
+
+
+def _block_plan(wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta, mode):
+    key = (id(wq), id(wo), mode)
+    e = _block_plans.get(key)
+    if e is not None and e[1]() is wq and e[0].valid():
+        return e[0]
+    plan = mha_decode_plan(wq=wq, bq=bq, wk=wk, bk=bk, wv=wv, bv=bv, wo=wo, bo=bo, gamma=gamma, beta=beta, mode=mode)
+    if len(_block_plans) > 1024:
+        for k in [k for k, v in _block_plans.items() if v[1]() is None]:
+            del _block_plans[k]
+    _block_plans[key] = (plan, weakref.ref(wq))
+    return plan
+
+
+def _mha_block_infer(queries, keys, values, mask, plan, *, h, d_k, d_v, eps, scale):
+    """The block in eval mode from one library call; None when that path does not apply (the caller runs the per-op block)."""
+    if queries.dim() != 3 or not queries.is_cuda:
+        return None
+    mode = plan.mode
+    kind = 0 if (keys is queries and values is queries) else (1 if values is keys else 2)
+    xq = _f32c(queries)
+    xk = None if kind == 0 else _f32c(keys)
+    xv = None if kind != 2 else _f32c(values)
+    sh = lambda t: None if t is None else _shadow_of(t, mode)
+    res = ops.mha_block_infer(xq, sh(queries), xk, None if kind == 0 else sh(keys), xv, None if kind != 2 else sh(values), kind, plan.ptrs, dt=plan.dt,
+                              eps=eps, h=h, d_k=d_k, d_v=d_v, mask=mask, scale=scale)
+    if res is None:
+        return None
+    y, y16 = res
+    if y16 is not None:
+        y._ovqa_bf16 = (y._version, y16)
+    return y
+
+
 def mha_block(queries, keys, values, mask, *, wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta, h, d_k, d_v, mode="fp32",
               dropout=0.0, training=False, eps=1e-5, boxes=None, geo_w=None, geo_b=None, geo_trig=True, scale=None):
+    if ONE_CALL_INFERENCE and boxes is None and not torch.is_grad_enabled() and not (training and dropout > 0.0):
+        y = _mha_block_infer(queries, keys, values, mask, _block_plan(wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta, mode), h=h, d_k=d_k, d_v=d_v,
+                             eps=float(eps), scale=(1.0 / math.sqrt(d_k)) if scale is None else float(scale))
+        if y is not None:
+            return y
     cfg = dict(grad=torch.is_grad_enabled(), mode=mode, h=h, d_k=d_k, d_v=d_v, dropout=float(dropout), training=bool(training), eps=float(eps),
                geo_trig=bool(geo_trig), scale=(1.0 / math.sqrt(d_k)) if scale is None else float(scale))
     y, y16 = _MHAFn.apply(queries, keys, values, mask, boxes, wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta, geo_w, geo_b, cfg)
@@ -536,6 +579,13 @@ class _PWFFFn(torch.autograd.Function):
 
 def pwff_block(x, *, w1, b1, w2, b2, gamma, beta, mode="fp32", dropout=0.0, training=False, eps=1e-5, dropout_hidden=True):
     """``dropout_hidden=False``: no dropout after the activation (HF ``BertIntermediate``; the reference's own block drops there too)."""
+    if ONE_CALL_INFERENCE and not torch.is_grad_enabled() and not (training and dropout > 0.0) and x.is_cuda:
+        key = (id(w1), id(w2), mode)
+        e = _block_plans.get(key)
+        if e is None or e[1]() is not w1 or not e[0].valid():
+            e = (pwff_plan(w1=w1, b1=b1, w2=w2, b2=b2, gamma=gamma, beta=beta, mode=mode), weakref.ref(w1))
+            _block_plans[key] = e
+        return pwff_infer_block(e[0], x, d_ff=w1.shape[0], eps=float(eps))
     cfg = dict(grad=torch.is_grad_enabled(), mode=mode, dropout=float(dropout), dropout_inner=float(dropout) if dropout_hidden else 0.0,
                training=bool(training), eps=float(eps))
     y, y16 = _PWFFFn.apply(x, w1, b1, w2, b2, gamma, beta, cfg)

@@ -564,6 +564,48 @@ def mha_decode_step(x, x_op, kv_src, self_attention: bool, wptrs, *, dt: int, ep
     return y, y16
 
 
+def mha_block_infer(xq, xq_op, xk, xk_op, xv, xv_op, kind: int, wptrs, *, dt: int, eps: float, h: int, d_k: int, d_v: int, mask=None, scale: float,
+                    max_workspace: int = 1 << 30):
+    """One MultiHeadAttention block in eval mode from ONE library call (ovqa_mha_block_infer).  xq (B,Lq,D) fp32 contiguous (queries and
+    residual); xk / xv (B,Lk,D) fp32 contiguous for kind 1 / 2; ``*_op``: the same rows in bf16 or None.  ``wptrs`` = device pointers
+    (w_qkv, b_qkv, w_o, b_o, gamma, beta).  Returns (y fp32, y bf16 | None), or None when the scratch space would exceed ``max_workspace``
+    (huge batches: host dispatch is irrelevant there, the caller takes the per-op path)."""
+    B, Lq, D = xq.shape
+    Lk = Lq if kind == 0 else xk.shape[1]
+    for t in (xq, xk, xv):
+        if t is not None and (not t.is_cuda or t.dtype is not torch.float32 or not t.is_contiguous()):
+            raise ValueError("mha_block_infer: inputs must be contiguous fp32 CUDA tensors")
+    for t in (xq_op, xk_op, xv_op):
+        if t is not None and (not t.is_cuda or t.dtype is not torch.bfloat16 or not t.is_contiguous()):
+            raise ValueError("mha_block_infer: operand shadows must be contiguous bf16 CUDA tensors")
+    _need_cuda(mask)
+    l = L.lib()
+    nws = l.ovqa_mha_block_infer_workspace_bytes(B, Lq, Lk, D, h, d_k, d_v, kind, dt)
+    if nws > max_workspace:
+        return None
+    y = torch.empty_like(xq)
+    y16 = torch.empty(xq.shape, device=xq.device, dtype=torch.bfloat16) if dt == L.BF16 else None
+    if B == 0 or Lq == 0:
+        return y, y16
+    hint = getattr(mask, "_ovqa_prefix_lm", None) if dt == L.BF16 else None
+    mkeep, mptr, sb, sh, sq = _mask_args(mask, B, h, Lq, Lk)
+    pk, psb, ptail, pval = None, 0, 0, 0.0
+    if hint is not None:
+        key_row, ptail, pval = hint
+        pk, psb = key_row.data_ptr(), (key_row.stride(0) if key_row.shape[0] > 1 else 0)
+    st = _stream()
+    ws = _WS.get((xq.device, st))
+    if ws is None or ws.numel() < nws or torch.cuda.is_current_stream_capturing():
+        ws = _workspace(xq.device, nws)
+    p = lambda t: None if t is None else t.data_ptr()
+    rc = l.ovqa_mha_block_infer(xq.data_ptr(), p(xq_op), p(xk), p(xk_op), p(xv), p(xv_op), kind, B, Lq, Lk, D, h, d_k, d_v, wptrs[0], wptrs[1],
+                                wptrs[2], wptrs[3], wptrs[4], wptrs[5], eps, mptr, sb, sh, sq, pk, psb, int(ptail), float(pval), scale, dt,
+                                ws.data_ptr(), ws.numel(), y.data_ptr(), p(y16), st)
+    if rc:
+        L.check(rc, "ovqa_mha_block_infer")
+    return y, y16
+
+
 def pwff_infer(x, x_op, wptrs, *, dt: int, d_ff: int, eps: float):
     """LN(x + fc2(gelu(fc1 x))) in eval mode from one call.  x (…, D) fp32 contiguous; ``wptrs`` = device pointers (w1, b1, w2, b2, gamma,
     beta) of tensors the caller keeps alive.  Returns (y fp32, y bf16 | None)."""

@@ -930,8 +930,13 @@ def test_geo_bias_kernels_against_the_oracle(dev, name):
     key_mask = torch.zeros((B, 1, 1, N), device=dev)
     key_mask[:, :, :, -3:] = -10e4
     out = ops.geo_bias(geo, h)
-    torch.testing.assert_close(out.cpu(), ref.detach(), rtol=2e-4, atol=2e-4)
-    torch.testing.assert_close(ops.geo_bias(geo, h, key_mask=key_mask).cpu(), ref.detach() + key_mask.cpu(), rtol=2e-4, atol=2e-2)
+    # compared as clamp(relu(raw), 1e-6) = exp(bias): the log amplifies the last-bit differences of sin / cos at arguments of several
+    # hundred radians wherever the 64-term sum nearly cancels (raw ~ 1e-3 -> 2e-2 on the log)
+    torch.testing.assert_close(out.cpu().exp(), ref.detach().exp(), rtol=1e-3, atol=5e-5)
+    assert ((out.cpu() - ref.detach()).abs() > 1e-3).float().mean().item() < 1e-3
+    masked = ops.geo_bias(geo, h, key_mask=key_mask).cpu()
+    torch.testing.assert_close(masked[..., :-3], out.cpu()[..., :-3], rtol=0, atol=0)
+    assert (masked[..., -3:] < -9e4).all()
     dw, db = torch.zeros((h, dg), device=dev), torch.zeros((h,), device=dev)
     ops.geo_bias_bwd(geo, h, gsel.to(dev).contiguous(), dw, db)
     dw_ref = torch.cat([pr[f"fc_gs.{i}.weight"].grad for i in range(h)], 0)
@@ -962,3 +967,40 @@ def test_geometry_gradients_bf16_route(dev):
         assert float((g - gr).norm() / gr.norm().clamp_min(1e-9)) <= 6e-2, (i, g, gr)
     g, gr = named["attention.fc_q.weight"].grad.cpu(), gp["attention.fc_q.weight"]
     assert float((g - gr).norm() / gr.norm()) <= 6e-2
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("kind", ["self", "kv_same", "three"])
+def test_one_call_inference_block_matches_the_per_op_block(dev, mode, kind):
+    """ovqa_mha_block_infer (eval mode, no autograd: one library call) against the per-op block it replaces — same kernels, same bits."""
+    from openvivqa_b200 import functional as Fn
+    D, h, B, Lq, Lk = 128, 4, 5, 21, 37
+    m = ovqa.MultiHeadAttention(H.attention_cfg(D, h, dropout=0.1, compute_dtype=mode))
+    m.load_state_dict(S.synth_params(C.att_spec(D, h, D // h, D // h), 2))
+    m = m.to(dev).eval()
+    g = S._gen(4, "onecall")
+    q = torch.randn((B, Lq, D), generator=g).to(dev)
+    k = q if kind == "self" else torch.randn((B, Lk, D), generator=g).to(dev)
+    v = k if kind != "three" else torch.randn((B, Lk, D), generator=g).to(dev)
+    mask = torch.zeros((B, 1, 1, k.shape[1]), device=dev)
+    mask[:, :, :, -5:] = -10e4
+    with torch.no_grad():
+        assert Fn.ONE_CALL_INFERENCE
+        y1 = m(q, k, v, mask)
+        Fn.ONE_CALL_INFERENCE = False
+        try:
+            y0 = m(q, k, v, mask)
+        finally:
+            Fn.ONE_CALL_INFERENCE = True
+    assert torch.equal(y1, y0)
+    if mode == "bf16":
+        assert torch.equal(y1._ovqa_bf16[1], y0._ovqa_bf16[1])
+    pw = ovqa.PositionWiseFeedForward(H.attention_cfg(D, h, d_ff=256, dropout=0.1, compute_dtype=mode)).to(dev).eval()
+    with torch.no_grad():
+        z1 = Fn.pwff_block(y1, w1=pw.fc1.weight, b1=pw.fc1.bias, w2=pw.fc2.weight, b2=pw.fc2.bias, gamma=pw.layer_norm.weight, beta=pw.layer_norm.bias, mode=mode)
+        Fn.ONE_CALL_INFERENCE = False
+        try:
+            z0 = Fn.pwff_block(y0, w1=pw.fc1.weight, b1=pw.fc1.bias, w2=pw.fc2.weight, b2=pw.fc2.bias, gamma=pw.layer_norm.weight, beta=pw.layer_norm.bias, mode=mode)
+        finally:
+            Fn.ONE_CALL_INFERENCE = True
+    assert torch.equal(z1, z0)
