@@ -36,6 +36,7 @@ extern "C" {
 #define OVQA_EPI_DGELU       2      /* multiply by GELU'(aux) (backward of the above)             */
 #define OVQA_EPI_SAVE_DGELU  4      /* with GELU + aux_out: aux_out receives GELU'(v) x dropout scale */
 #define OVQA_EPI_MUL_AUX     8      /* multiply by aux (the derivative saved by the forward pass) */
+#define OVQA_EPI_RELU       16      /* max(v, 0) (the attribute-reduce MLP, models/mcan.py:21-25)    */
 
 #define OVQA_OP_N 0                 /* operand stored with the reduction (K) dimension contiguous */
 #define OVQA_OP_T 1                 /* operand stored with its M/N dimension contiguous           */
@@ -220,6 +221,18 @@ int ovqa_geo_bias_fwd(const float* boxes, const float* geo_w, const float* geo_b
 int ovqa_geo_bias_bwd(const float* boxes, const float* geo_w, const float* geo_b, const float* geo_freq,
                       const float* dbias, float* geo_dw, float* geo_db,
                       int64_t B, int64_t N, int64_t h, int64_t d_g, int geo_trig, void* stream);
+
+/* Attribute-reduce pooling (models/mcan.py:70-77; the same lines in cross_modality_transformer.py / visiolinguistic_transformer.py;
+ * SURVEY §8f rank 3).  hidden [B,N,Dh] = dropout(relu(fc1 x)) (ovqa_gemm with OVQA_EPI_RELU + dropout), x [B,N,D] fp32:
+ *   logits[b,n] = hidden[b,n,:] . w2 + *b2;  probs = softmax over n (no padding mask, as upstream);  pooled[b,:] = sum_n probs[b,n] x[b,n,:].
+ *   probs [B,N] fp32 optional (saved for backward).
+ * Backward: dx [B,N,D] fp32 (optional) = probs dpooled^T;  dpre [B,N,Dh] (hidden's dtype) = the gradient of fc1's PRE-activation,
+ *   dlogit[n] w2[c] / (1 - dropout_p) where hidden[b,n,c] > 0 (the unit was active and kept), else 0;  dw2 [Dh], db2 [1] fp32 ACCUMULATED into. */
+int ovqa_attr_pool_fwd(const void* hidden, const float* w2, const float* b2, const float* x, float* pooled, float* probs,
+                       int64_t B, int64_t N, int64_t Dh, int64_t D, int hidden_dtype, void* stream);
+int ovqa_attr_pool_bwd(const float* dpooled, const void* hidden, const float* w2, const float* x, const float* probs,
+                       float* dx, void* dpre, float* dw2, float* db2,
+                       int64_t B, int64_t N, int64_t Dh, int64_t D, float dropout_p, int hidden_dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * M4C dynamic pointer network and greedy decode step.

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libovqa_b200.so")
 
 F32, BF16 = 0, 1
 OP_N, OP_T = 0, 1
-EPI_GELU, EPI_DGELU, EPI_SAVE_DGELU, EPI_MUL_AUX = 1, 2, 4, 8
+EPI_GELU, EPI_DGELU, EPI_SAVE_DGELU, EPI_MUL_AUX, EPI_RELU = 1, 2, 4, 8, 16
 ERR_BAD_SHAPE = -2
 
 _vp, _i64, _i32, _f32, _u64 = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_uint64
@@ -61,6 +61,8 @@ _PROTOS = {
     "ovqa_stage_many": [_vp, _i64, _vp],
     "ovqa_box_geometry_bias": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp],
     "ovqa_ptr_scores": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _i32, _i32, _vp],
+    "ovqa_attr_pool_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp],
+    "ovqa_attr_pool_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _i32, _vp],
     "ovqa_ptr_scores_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _i32, _vp],
     "ovqa_prev_pred_embed": [_vp] * 12 + [_i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _vp],
     "ovqa_greedy_step": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp],

@@ -225,6 +225,7 @@ __device__ __forceinline__ float epilogue_value(const Epilogue& e, float acc, in
     const float ds = e.dropout_p > 0.0f ? dropout_scale((uint64_t)(row * n_cols + col), e.dropout_p, 1.0f / (1.0f - e.dropout_p), e.seed, effective_offset(e.offset, e.offset_base)) : 1.0f;
     if (e.aux_out) reinterpret_cast<TC*>(e.aux_out)[row * e.ld_aux + col] = from_f32<TC>((e.flags & OVQA_EPI_SAVE_DGELU) ? dgelu_erf(v) * ds : v);
     if (e.flags & OVQA_EPI_GELU) v = gelu_erf(v);
+    if (e.flags & OVQA_EPI_RELU) v = fmaxf(v, 0.0f);
     if (e.flags & OVQA_EPI_DGELU) v *= dgelu_erf(to_f32<TC>(reinterpret_cast<const TC*>(e.aux_in)[row * e.ld_aux + col]));
     if (e.flags & OVQA_EPI_MUL_AUX) v *= to_f32<TC>(reinterpret_cast<const TC*>(e.aux_in)[row * e.ld_aux + col]);
     v *= ds;

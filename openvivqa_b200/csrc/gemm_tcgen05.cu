@@ -294,6 +294,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         const bool f_gelu = MODE == EPI_FULL && (epi.flags & OVQA_EPI_GELU), f_dgelu = MODE == EPI_FULL && (epi.flags & OVQA_EPI_DGELU);
         const bool f_save_d = MODE == EPI_FULL && (epi.flags & OVQA_EPI_SAVE_DGELU) && (epi.flags & OVQA_EPI_GELU) && epi.aux_out;
         const bool f_mul_aux = MODE == EPI_FULL && (epi.flags & OVQA_EPI_MUL_AUX);
+        const bool f_relu = MODE == EPI_FULL && (epi.flags & OVQA_EPI_RELU);
         const bool f_drop = MODE == EPI_FULL && epi.dropout_p > 0.f;
         const float* __restrict__ residual = MODE == EPI_FULL ? epi.residual : nullptr;
         const TC* __restrict__ aux_in = MODE == EPI_FULL ? reinterpret_cast<const TC*>(epi.aux_in) : nullptr;
@@ -530,6 +531,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) v[j] = gelu_fast(v[j]);
                             }
+                            if (f_relu) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+                            }
                         }
                         if (f_dgelu || f_mul_aux) {
                             if (residual) load8<TC, HI>(aux_in + row * ld_aux + col, b8 /*scratch: bias already applied*/);
@@ -674,7 +679,7 @@ int launch(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, int64_t m, i
     const int mode = split_k > 1 ? EPI_SPLITK : full ? EPI_FULL : EPI_PLAIN;
     // compile-time feature set of this launch, if it is one of the specialised combinations (else F_RUNTIME)
     int feat = F_RUNTIME;
-    if (mode == EPI_FULL && !epi.c2 && epi.beta == 0.f && !(epi.flags & OVQA_EPI_DGELU) && !(epi.aux_out && !(epi.flags & OVQA_EPI_SAVE_DGELU))) {
+    if (mode == EPI_FULL && !epi.c2 && epi.beta == 0.f && !(epi.flags & (OVQA_EPI_DGELU | OVQA_EPI_RELU)) && !(epi.aux_out && !(epi.flags & OVQA_EPI_SAVE_DGELU))) {
         feat = (epi.bias ? F_BIAS : 0) | ((epi.flags & OVQA_EPI_GELU) ? F_GELU : 0) | ((epi.flags & OVQA_EPI_SAVE_DGELU) ? F_SAVE_D : 0) |
                ((epi.flags & OVQA_EPI_MUL_AUX) ? F_MULAUX : 0) | (epi.dropout_p > 0.f ? F_DROP : 0) | (epi.residual ? F_RES : 0) |
                (epi.colsum ? F_COLSUM : 0);

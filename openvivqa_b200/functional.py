@@ -634,6 +634,72 @@ def feature_embedding(features, w, b, *, dropout=0.0, training=False, mask_value
     return _FeatureEmbeddingFn.apply(features, w, b, cfg)
 
 
+# ----------------------------------------------------------------------------- attribute-reduce pooling head
+class _AttrReduceFn(torch.autograd.Function):
+    """``(x * softmax(fc2(dropout(relu(fc1 x))), dim=1)).sum(dim=1)`` (models/mcan.py:21-25,70-77): one GEMM with the ReLU + dropout epilogue,
+    one pooling kernel (scores, softmax over the sequence and the weighted sum in one pass per sample); backward: one pooling kernel (dx,
+    fc1's pre-activation gradient, fc2's gradients), the split-K weight gradient, the dgrad GEMM that also adds the pooling's dx."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, cfg):
+        ctx.set_materialize_grads(False)
+        mode = cfg["mode"]
+        p = cfg["dropout"] if cfg["training"] else 0.0
+        cdt = _cdt(mode)
+        B, N, D = x.shape
+        Dh = w1.shape[0]
+        x2 = _operand(x, mode)
+        xf = _f32c(x)
+        seed, off = dropout_stream.next(B * N * Dh) if p > 0.0 else (0, 0)
+        hid = ops.gemm(x2, weights.get([w1], cdt), bias=weights.get([b1], torch.float32), out_dtype=cdt, relu=True, dropout_p=p, seed=seed, offset=off,
+                       offset_base=dropout_stream.base(x.device) if p > 0.0 else None).view(B, N, Dh)
+        need_grad = cfg["grad"] and any(ctx.needs_input_grad)
+        pooled, probs = ops.attr_pool_fwd(hid, w2.detach(), b2.detach(), xf, save_probs=need_grad)
+        if need_grad:
+            ctx.save_for_backward(x2, xf, hid, probs, w1, w2)
+            ctx.cfg, ctx.p = cfg, p
+        return pooled
+
+    @staticmethod
+    def backward(ctx, dpooled):
+        if dpooled is None:
+            return (None,) * 6
+        x2, xf, hid, probs, w1, w2 = ctx.saved_tensors
+        mode = ctx.cfg["mode"]
+        B, N, Dh = hid.shape
+        D = xf.shape[-1]
+        dw1, db1, dw2, db2 = _zero_slab(dpooled.device, (Dh, D), (Dh,), tuple(w2.shape), (1,))
+        dx_pool, dpre = ops.attr_pool_bwd(dpooled, hid, w2.detach(), xf, probs, ctx.p, dw2.view(-1), db2, need_dx=ctx.needs_input_grad[0])
+        dpre2 = dpre.view(B * N, Dh)
+        _wgrad(dpre2, x2, out=dw1)
+        ops.colsum(dpre2, out=db1, accumulate=True)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.gemm(dpre2, weights.get([w1], _cdt(mode)), b_op="T", out_dtype=torch.float32, residual=dx_pool.view(B * N, D)).view(B, N, D)
+        return dx, dw1, db1, dw2, db2, None
+
+
+def attr_reduce_pool(x, *, w1, b1, w2, b2, mode="fp32", dropout=0.0, training=False):
+    """(B,N,D) -> (B,D): the attribute-reduce MLP, the softmax over the sequence and the weighted sum of models/mcan.py:70-77."""
+    cfg = dict(grad=torch.is_grad_enabled(), mode=mode, dropout=float(dropout), training=bool(training))
+    return _AttrReduceFn.apply(x, w1, b1, w2, b2, cfg)
+
+
+def pool_and_classify(model, vision_features, text_features, mode, log_softmax=False):
+    """The classifier tail shared by MCAN / CrossModalityTransformer / VisiolinguisticTransformer (models/mcan.py:70-81): both
+    attribute-reduce poolings, ``layer_norm(vision_proj(.) + text_proj(.))`` and ``classify`` through the library.  ``model`` is any
+    module with the reference's attribute names (``vision_attr_reduce`` / ``text_attr_reduce`` MLPs with fc1 / dropout / fc2,
+    ``vision_proj``, ``text_proj``, ``layer_norm``, ``classify``)."""
+    def pool(mlp, feats):
+        return attr_reduce_pool(feats, w1=mlp.fc1.weight, b1=mlp.fc1.bias, w2=mlp.fc2.weight, b2=mlp.fc2.bias, mode=mode, dropout=mlp.dropout.p,
+                                training=mlp.training)
+    wv, wt = pool(model.vision_attr_reduce, vision_features), pool(model.text_attr_reduce, text_features)
+    s = linear(wv, model.vision_proj.weight, model.vision_proj.bias, mode) + linear(wt, model.text_proj.weight, model.text_proj.bias, mode)
+    out = layer_norm(s, model.layer_norm.weight, model.layer_norm.bias, model.layer_norm.eps)
+    logits = linear(out, model.classify.weight, model.classify.bias, mode)
+    return torch.log_softmax(logits, dim=-1) if log_softmax else logits
+
+
 # ----------------------------------------------------------------------------- stand-alone pieces (direct core calls)
 class _SdpaFn(torch.autograd.Function):
     """The attention core as a differentiable function of q, k, v, the geometry weights AND through both outputs: a direct caller may

@@ -19,7 +19,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .. import functional as Fn
-from ..modules import MultiHeadAttention, PositionWiseFeedForward, StatefulModule
+from ..modules import MultiHeadAttention, PositionWiseFeedForward, StatefulModule, get_compute_dtype
 
 MASK_VALUE = -10e4
 
@@ -245,12 +245,9 @@ class MLP(nn.Module):
 
 class _ClassifierBase(nn.Module):
     def _pool_and_classify(self, vision_features, text_features):
-        av = F.softmax(self.vision_attr_reduce(vision_features), dim=1)
-        at = F.softmax(self.text_attr_reduce(text_features), dim=1)
-        wv = (vision_features * av).sum(dim=1)
-        wt = (text_features * at).sum(dim=1)
-        out = self.layer_norm(self.vision_proj(wv) + self.text_proj(wt))
-        return self.classify(out)
+        """models/mcan.py:70-80: attribute-reduce pooling of both modalities, fusion LayerNorm, classifier — the library's pooling head."""
+        mode = getattr(self.vision_embedding, "compute_dtype", None) or get_compute_dtype()
+        return Fn.pool_and_classify(self, vision_features, text_features, mode)
 
     def _build_head(self, config, vocab):
         self.vision_attr_reduce = MLP(config.VISION_ATTR_REDUCE)

@@ -85,6 +85,12 @@ def install(compute_dtype: str | None = None, verbose: bool = False):
             classes[f"{modname}.{owner + '.' if owner else ''}{attr}"] = fn
             if verbose:
                 print(f"openvivqa_b200: {modname}.{owner + '.' if owner else ''}{attr} -> B200 path")
+    # classifier tail of MCAN (models/mcan.py:70-80): the forward is rebound so that the attribute-reduce pooling runs in the library
+    mcan_mod = _maybe("models.mcan")
+    if mcan_mod is not None and hasattr(mcan_mod, "MCAN"):
+        _saved.setdefault(("m4c", "models.mcan", "MCAN", "forward"), mcan_mod.MCAN.forward)
+        mcan_mod.MCAN.forward = M.mcan_forward
+        classes["models.mcan.MCAN.forward"] = M.mcan_forward
     for name, mods in _REBIND.items():
         for modname in mods:
             mod = _maybe(modname)

@@ -537,6 +537,18 @@ class FeatureEmbedding(nn.Module):
         return self.dropout(self.gelu(y)), masks
 
 
+def mcan_forward(self, input_features):
+    """``MCAN.forward`` (models/mcan.py:49-81) with the classifier tail (:70-80: attribute-reduce pooling, fusion LayerNorm, classifier)
+    through the library's pooling head; bound over the reference's class by ``install()``.  The embeddings and encoders it calls are the
+    reference's own objects (already built from the drop-ins)."""
+    vision_features, vision_padding_mask = self.vision_embedding(input_features.region_features)
+    text_features, (text_padding_mask, _) = self.text_embedding(input_features.question_tokens)
+    text_features = self.self_encoder(features=text_features, padding_mask=text_padding_mask)
+    vision_features = self.guided_encoder(vision_features=vision_features, vision_padding_mask=vision_padding_mask,
+                                          language_features=text_features, language_padding_mask=text_padding_mask)
+    return Fn.pool_and_classify(self, vision_features, text_features, get_compute_dtype(), log_softmax=True)
+
+
 class OcrPtrNet(nn.Module):
     """mmf_m4c.py:367-396: ``(Wq·dec + b)(Wk·ocr + b)ᵀ / √d_qk + mask``."""
 

@@ -47,7 +47,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_op: str = "N", b_op: str = "N", 
          aux_out: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          c2: Optional[torch.Tensor] = None, dropout_p: float = 0.0, seed: int = 0, offset: int = 0,
          offset_base: Optional[torch.Tensor] = None, split_k: int = 1, save_dgelu: bool = False,
-         mul_aux: Optional[torch.Tensor] = None, colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
+         mul_aux: Optional[torch.Tensor] = None, colsum: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
     """``C[m,n] = epilogue(sum_k A[m,k] B[n,k])`` — see ``ovqa_gemm`` in include/ovqa.h.
 
     ``a_op``/``b_op``: "N" = operand stored [rows, k]; "T" = stored [k, rows].
@@ -88,7 +88,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_op: str = "N", b_op: str = "N", 
     if colsum is not None and (colsum.dtype != torch.float32 or colsum.numel() != n or not colsum.is_contiguous()):
         raise ValueError("gemm: colsum must be contiguous fp32 [n]")
     flags = (L.EPI_GELU if gelu else 0) | ((L.EPI_MUL_AUX if mul_aux is not None else L.EPI_DGELU) if dgelu_aux is not None else 0) | \
-        (L.EPI_SAVE_DGELU if save_dgelu else 0)
+        (L.EPI_SAVE_DGELU if save_dgelu else 0) | (L.EPI_RELU if relu else 0)
     aux = dgelu_aux if dgelu_aux is not None else aux_out
     if m == 0 or n == 0:                     # empty batch: nothing to launch (an empty tensor has no device pointer to validate)
         return out
@@ -421,6 +421,40 @@ def ptr_scores(q, k, mask, scores, col_offset: int, scale: float, mask_is_bool: 
     L.call("ovqa_ptr_scores", _p(q), _p(k), _p(mask), _p(scores), B, T, Lk, d, q.stride(1), k.stride(1), scores.shape[-1],
            col_offset, float(scale), _DT[q.dtype], int(mask_is_bool), _stream())
     return scores
+
+
+def attr_pool_fwd(hidden: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, x: torch.Tensor, save_probs: bool = True):
+    """softmax-over-the-sequence pooling of ``x`` (B,N,D) fp32 by the scores ``hidden . w2 + b2`` (hidden (B,N,Dh) fp32 / bf16, the
+    attribute-reduce MLP's first layer).  Returns (pooled (B,D) fp32, probs (B,N) fp32 | None)."""
+    _need_cuda(hidden, w2, b2, x)
+    B, N, Dh = hidden.shape
+    D = x.shape[-1]
+    if hidden.dtype not in _DT or x.dtype != torch.float32 or x.shape[:2] != (B, N) or not hidden.is_contiguous() or not x.is_contiguous():
+        raise ValueError("attr_pool_fwd: hidden (B,N,Dh) fp32/bf16 and x (B,N,D) fp32, both contiguous")
+    w2, b2 = w2.reshape(-1).float().contiguous(), b2.reshape(-1).float().contiguous()
+    if w2.numel() != Dh or b2.numel() != 1:
+        raise ValueError("attr_pool_fwd: w2 must have Dh elements, b2 one")
+    pooled = torch.empty((B, D), device=x.device, dtype=torch.float32)
+    probs = torch.empty((B, N), device=x.device, dtype=torch.float32) if save_probs else None
+    if B > 0:
+        L.call("ovqa_attr_pool_fwd", _p(hidden), _p(w2), _p(b2), _p(x), _p(pooled), _p(probs), B, N, Dh, D, _DT[hidden.dtype], _stream())
+    return pooled, probs
+
+
+def attr_pool_bwd(dpooled, hidden, w2, x, probs, dropout_p: float, dw2: torch.Tensor, db2: torch.Tensor, need_dx: bool = True):
+    """Backward of :func:`attr_pool_fwd`: returns (dx (B,N,D) fp32 | None, dpre (B,N,Dh) in hidden's dtype — the gradient of the MLP's fc1
+    PRE-activation); accumulates into ``dw2`` (Dh) / ``db2`` (1) fp32."""
+    _need_cuda(dpooled, hidden, w2, x, probs, dw2, db2)
+    B, N, Dh = hidden.shape
+    D = x.shape[-1]
+    dpooled = dpooled.float().contiguous()
+    w2 = w2.reshape(-1).float().contiguous()
+    dx = torch.empty((B, N, D), device=x.device, dtype=torch.float32) if need_dx else None
+    dpre = torch.empty_like(hidden)
+    if B > 0:
+        L.call("ovqa_attr_pool_bwd", _p(dpooled), _p(hidden), _p(w2), _p(x), _p(probs), _p(dx), _p(dpre), _p(dw2), _p(db2), B, N, Dh, D, float(dropout_p),
+               _DT[hidden.dtype], _stream())
+    return dx, dpre
 
 
 def geo_bias(geo: GeoParams, h: int, key_mask: Optional[torch.Tensor] = None) -> torch.Tensor:

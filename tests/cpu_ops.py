@@ -29,7 +29,7 @@ def _op(t, op):
 
 def gemm(a, b, *, a_op="N", b_op="N", out=None, out_dtype=None, bias=None, alpha=1.0, beta=0.0, gelu=False, dgelu_aux=None,
          aux_out=None, residual=None, c2=None, dropout_p=0.0, seed=0, offset=0, offset_base=None, split_k=1, save_dgelu=False,
-         mul_aux=None, colsum=None):
+         mul_aux=None, colsum=None, relu=False):
     A, B = _op(a, a_op), _op(b, b_op)
     m, n = A.shape[0], B.shape[0]
     v = (A @ B.t()) * alpha
@@ -50,6 +50,8 @@ def gemm(a, b, *, a_op="N", b_op="N", out=None, out_dtype=None, bias=None, alpha
             aux_out.copy_(v.to(aux_out.dtype))
     if gelu:
         v = F.gelu(v)
+    if relu:
+        v = torch.relu(v)
     if dgelu_aux is not None:
         x = dgelu_aux.float()
         cdf = 0.5 * (1.0 + torch.erf(x / math.sqrt(2.0)))
@@ -113,6 +115,21 @@ def geo_log_bias(geo, h):
 
 def box_geometry_bias(geo, h):
     return geo_log_bias(geo, h)
+
+
+def attr_pool_fwd(hidden, w2, b2, x, save_probs=True):
+    logits = hidden.float() @ w2.reshape(-1).float() + b2.reshape(-1).float()
+    p = torch.softmax(logits, dim=1)
+    return (x * p.unsqueeze(-1)).sum(1), (p if save_probs else None)
+
+
+def attr_pool_bwd(dpooled, hidden, w2, x, probs, dropout_p, dw2, db2, need_dx=True):
+    dp = (x * dpooled.unsqueeze(1)).sum(-1)
+    dl = probs * (dp - (probs * dp).sum(1, keepdim=True))
+    dw2 += (dl.unsqueeze(-1) * hidden.float()).sum((0, 1))
+    db2 += dl.sum()
+    dpre = torch.where(hidden.float() > 0, dl.unsqueeze(-1) * w2.reshape(1, 1, -1).float() / (1.0 - dropout_p), torch.zeros(())).to(hidden.dtype)
+    return (probs.unsqueeze(-1) * dpooled.unsqueeze(1) if need_dx else None), dpre
 
 
 def geo_bias(geo, h, key_mask=None):
@@ -329,7 +346,7 @@ def pwff_infer_block(plan, x, *, d_ff, eps=1e-5):
 
 
 OPS = ("gemm", "sdpa_fwd", "sdpa_bwd", "layernorm_fwd", "layernorm_bwd", "cast_rows_padmask", "mul_to_bf16", "to_bf16", "to_f32", "colsum",
-       "add", "dropout_apply", "dropout_keep_mask", "stage_many", "advance_u64", "box_geometry_bias", "geo_bias", "geo_bias_bwd", "ptr_scores", "ptr_scores_bwd",
+       "add", "dropout_apply", "dropout_keep_mask", "stage_many", "advance_u64", "box_geometry_bias", "geo_bias", "geo_bias_bwd", "attr_pool_fwd", "attr_pool_bwd", "ptr_scores", "ptr_scores_bwd",
        "prev_pred_embed", "greedy_step", "topk_rows", "mha_decode_step", "pwff_infer")
 
 

@@ -255,3 +255,43 @@ def test_geometry_block_bf16_route_returns_the_geometry_gradients(cpu_ops, maske
         assert g is not None and float((g - gr).norm() / gr.norm().clamp_min(1e-9)) < 0.1, i
         gb, gbr = m.attention.fc_gs[i].bias.grad, pr[f"attention.fc_gs.{i}.bias"].grad
         assert float((gb - gbr).abs().max()) <= 0.1 * float(gbr.abs().max()) + 1e-4
+
+
+@pytest.mark.parametrize("p_drop", [0.0, 0.25])
+def test_attribute_reduce_pooling_matches_oracle_autograd(cpu_ops, p_drop):
+    """models/mcan.py:21-25,70-77 through the pooling head: output and every gradient (x, fc1, fc2) against autograd of the composition —
+    with dropout, against the composition that applies the SAME keep-scales."""
+    B, N, D = 3, 11, 32
+    g = torch.Generator().manual_seed(3)
+    params = S.synth_params([("fc1.weight", (D, D)), ("fc1.bias", (D,)), ("fc2.weight", (1, D)), ("fc2.bias", (1,))], 2)
+    x = torch.randn((B, N, D), generator=g)
+    torch.manual_seed(0)
+    Fn.dropout_stream.offset = 0
+    pr = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    xr = x.clone().requires_grad_(True)
+    xi = x.clone().requires_grad_(True)
+    pi = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    y = Fn.attr_reduce_pool(xi, w1=pi["fc1.weight"], b1=pi["fc1.bias"], w2=pi["fc2.weight"], b2=pi["fc2.bias"], mode="fp32", dropout=p_drop, training=True)
+    ks = cpu_ops._keep_scale(B * N * D, p_drop, Fn.dropout_stream.seed, 0).view(B, N, D)
+    hid = torch.relu(torch.nn.functional.linear(xr, pr["fc1.weight"], pr["fc1.bias"])) * ks
+    att = torch.softmax(torch.nn.functional.linear(hid, pr["fc2.weight"], pr["fc2.bias"]), dim=1)
+    ref = (xr * att).sum(dim=1)
+    w = torch.randn(ref.shape, generator=g)
+    (ref * w).sum().backward()
+    (y * w).sum().backward()
+    _close(y.detach(), ref.detach(), 1e-5)
+    _close(xi.grad, xr.grad)
+    for k in params:
+        _close(pi[k].grad, pr[k].grad)
+
+
+def test_harness_mcan_head_goes_through_the_pooling_head(cpu_ops, golden):
+    """MCAN-small end to end on the emulated library (fp32): logits against the reference-generated golden."""
+    c = C.MCAN_SMALL
+    gm = golden("mcan")["small"]
+    m = H.MCAN(H.mcan_cfg(c["d_model"], c["d_feature"], c["layers"], c["h"], c["d_ff"], compute_dtype="fp32"), H.StubVocab(c["vocab"], c["answers"]))
+    m.load_state_dict(S.synth_params(gm["spec"], 0), strict=True)
+    m.eval()
+    with torch.no_grad():
+        logp = m(H.Batch(C.mcan_inputs(c)))
+    _close(logp, gm["logp"], 1e-4)

@@ -1004,3 +1004,36 @@ def test_one_call_inference_block_matches_the_per_op_block(dev, mode, kind):
         finally:
             Fn.ONE_CALL_INFERENCE = True
     assert torch.equal(z1, z0)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("p_drop", [0.0, 0.1])
+def test_attribute_reduce_pooling_head(dev, mode, p_drop):
+    """SURVEY 8f rank 3 (models/mcan.py:21-25,70-77): ReLU + dropout GEMM epilogue and the pooling kernels, forward and backward, against
+    autograd of the reference composition (with dropout: the composition applies the library's own keep mask)."""
+    from openvivqa_b200 import functional as Fn, ops
+    B, N, D = 7, 100, 512
+    g = torch.Generator().manual_seed(3)
+    params = S.synth_params([("fc1.weight", (D, D)), ("fc1.bias", (D,)), ("fc2.weight", (1, D)), ("fc2.bias", (1,))], 2)
+    x = torch.randn((B, N, D), generator=g)
+    torch.manual_seed(0)
+    Fn.dropout_stream.offset = 0
+    pi = {k: v.clone().to(dev).requires_grad_(True) for k, v in params.items()}
+    xi = x.clone().to(dev).requires_grad_(True)
+    y = Fn.attr_reduce_pool(xi, w1=pi["fc1.weight"], b1=pi["fc1.bias"], w2=pi["fc2.weight"], b2=pi["fc2.bias"], mode=mode, dropout=p_drop, training=True)
+    keep = ops.dropout_keep_mask(B * N * D, p_drop, Fn.dropout_stream.seed, 0, dev).view(B, N, D).cpu() if p_drop > 0 else torch.ones(B, N, D)
+    ks = keep / (1.0 - p_drop)
+    pr = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    xr = x.clone().requires_grad_(True)
+    hid = torch.relu(torch.nn.functional.linear(xr, pr["fc1.weight"], pr["fc1.bias"])) * ks
+    att = torch.softmax(torch.nn.functional.linear(hid, pr["fc2.weight"], pr["fc2.bias"]), dim=1)
+    ref = (xr * att).sum(dim=1)
+    w = torch.randn(ref.shape, generator=g)
+    (ref * w).sum().backward()
+    (y * w.to(dev)).sum().backward()
+    check(y, ref, mode, "pooled")
+    tol = 2e-3 if mode == "fp32" else 6e-2
+    assert rel_err(xi.grad, xr.grad) <= tol, rel_err(xi.grad, xr.grad)
+    for k in params:
+        e = float((pi[k].grad.cpu() - pr[k].grad).norm() / pr[k].grad.norm().clamp_min(1e-12))
+        assert e <= tol, (k, e)

@@ -137,3 +137,34 @@ def test_install_covers_the_sal_copies_and_uninstall_restores(cpu_ops):
     finally:
         ovqa.uninstall()
     assert orig == (M4.MMT.forward, M4.OcrPtrNet.forward, SAL.MMT.forward, SAL._batch_gather, M4.MMF_M4C._forward_mmt_and_output)
+
+
+def test_reference_mcan_after_install_matches_the_stock_model(cpu_ops):
+    """The reference's own MCAN (models/mcan.py) built after install(): drop-in attention / feed-forward / vision embedding and the rebound
+    forward whose classifier tail runs the library's pooling head — same log-probabilities as the stock model, reference state_dict loads."""
+    from openvivqa_b200 import harness as H
+    RL.load()
+    import models.mcan as MC
+    from builders.model_builder import META_ARCHITECTURE
+    c = C.MCAN_SMALL
+    vocab = RL.StubVocab(c["vocab"], c["answers"])
+    cfg = RL.mcan_cfg(c["d_model"], c["d_feature"], c["layers"], c["h"], c["d_ff"], device="cpu")
+    torch.manual_seed(0)
+    stock = META_ARCHITECTURE.get("MCAN")(cfg, vocab).eval()
+    x = H.Batch(C.mcan_inputs(c))
+    with torch.no_grad():
+        ref = stock(x)
+    prev = ovqa.get_compute_dtype()
+    try:
+        ovqa.install(compute_dtype="fp32")
+        assert MC.MCAN.forward.__module__.startswith("openvivqa_b200")
+        ours = META_ARCHITECTURE.get("MCAN")(cfg, vocab)
+        ours.load_state_dict(stock.state_dict(), strict=True)
+        ours.eval()
+        with torch.no_grad():
+            got = ours(x)
+    finally:
+        ovqa.uninstall()
+        ovqa.set_compute_dtype(prev)
+    assert not MC.MCAN.forward.__module__.startswith("openvivqa_b200")
+    torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-5)
