@@ -103,6 +103,10 @@ int ovqa_gemm(const void* A, const void* B, void* C,
  *   lse  [B, h, Lq] fp32, optional: row log-sum-exp, saved for backward / for ovqa_sdpa_probs.
  *   att  [B, h, Lq, Lk] fp32, optional: the probabilities (direct callers of the core consume them:
  *         mmf_lorra.py:118-146).
+ *   prob_dropout_*: dropout applied to the PROBABILITIES before they multiply v (HF BertSelfAttention's attention_probs_dropout_prob, the
+ *         layers MMF_M4C trains through: mmf_m4c.py:274-276,349-351); p = 0 for the repo's own cores.  Keep decision of element
+ *         ((b*h + head)*Lq + i)*Lk + j from the library's counter stream (seed, offset [+ *offset_base]); ovqa_sdpa_bwd regenerates it from
+ *         the same triple.  p > 0 runs on the CUDA-core kernels.
  * ------------------------------------------------------------------------------------------------- */
 int ovqa_sdpa_fwd(const void* q, const void* k, const void* v, void* out,
                   int64_t B, int64_t h, int64_t Lq, int64_t Lk, int64_t dk, int64_t dv,
@@ -110,7 +114,9 @@ int ovqa_sdpa_fwd(const void* q, const void* k, const void* v, void* out,
                   const float* mask, int64_t mask_sb, int64_t mask_sh, int64_t mask_sq,
                   const float* boxes, const float* geo_w, const float* geo_b, const float* geo_freq,
                   int64_t d_g, int geo_trig,
-                  float scale, int dtype, float* lse, float* att, void* stream);
+                  float scale, int dtype, float* lse, float* att,
+                  float prob_dropout_p, uint64_t prob_dropout_seed, uint64_t prob_dropout_offset, const uint64_t* prob_dropout_offset_base,
+                  void* stream);
 
 /* Same core under M4C's prefix-LM mask (MMT.forward, mmf_m4c.py:310-343: (B,1,L,L) = per-key padding row repeated over the queries, with
  * the last T x T block — the decoder steps — replaced by a causal pattern) WITHOUT materialising / reading the dense mask:
@@ -142,7 +148,9 @@ int ovqa_sdpa_bwd(const void* q, const void* k, const void* v, const void* out, 
                   int64_t d_g, int geo_trig,
                   float* geo_dw, float* geo_db,
                   float scale, int dtype, const float* lse, float* delta,
-                  const float* att, const float* datt, float* dbias, void* stream);
+                  const float* att, const float* datt, float* dbias,
+                  float prob_dropout_p, uint64_t prob_dropout_seed, uint64_t prob_dropout_offset, const uint64_t* prob_dropout_offset_base,
+                  void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * LayerNorm over the last dimension with optional fused residual add.

@@ -44,10 +44,10 @@ _PROTOS = {
     "ovqa_sdpa_fwd_prefix_lm": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _f32, _f32, _i32,
                                 _vp, _vp],
     "ovqa_sdpa_fwd": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
-                      _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _i32, _vp, _vp, _vp],
+                      _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _i32, _vp, _vp, _f32, _u64, _u64, _vp, _vp],
     "ovqa_sdpa_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64,
                       _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
-                      _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _f32, _i32, _vp, _vp, _vp, _vp, _vp, _vp],
+                      _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _f32, _i32, _vp, _vp, _vp, _vp, _vp, _f32, _u64, _u64, _vp, _vp],
     "ovqa_geo_bias_fwd": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i32, _vp],
     "ovqa_geo_bias_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp],
     "ovqa_layernorm_fwd": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, _vp],

@@ -108,15 +108,18 @@ extern "C" int ovqa_sdpa_fwd(const void* q, const void* k, const void* v, void* 
                              int64_t dk, int64_t dv, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, const float* mask,
                              int64_t mask_sb, int64_t mask_sh, int64_t mask_sq, const float* boxes, const float* geo_w,
                              const float* geo_b, const float* geo_freq, int64_t d_g, int geo_trig, float scale, int dtype,
-                             float* lse, float* att, void* stream) {
+                             float* lse, float* att, float prob_dropout_p, uint64_t prob_dropout_seed, uint64_t prob_dropout_offset,
+                             const uint64_t* prob_dropout_offset_base, void* stream) {
     int rc = check_sdpa(q, k, v, B, h, Lq, Lk, dk, dv, boxes, geo_w, geo_b, d_g, geo_trig, dtype);
     if (rc) return rc;
-    if (!out) return OVQA_ERR_BAD_ARG;
+    if (!out || prob_dropout_p < 0.f || prob_dropout_p >= 1.f) return OVQA_ERR_BAD_ARG;
     if (B == 0 || Lq == 0) return OVQA_OK;
     SdpaArgs a{q, k, v, out, B, h, Lq, Lk, dk, dv, ldq, ldk, ldv, ldo, {mask, mask_sb, mask_sh, mask_sq},
-               {boxes, geo_w, geo_b, geo_freq, (int)d_g, geo_trig}, scale, lse, att};
+               {boxes, geo_w, geo_b, geo_freq, (int)d_g, geo_trig}, scale, lse, att, prob_dropout_p, prob_dropout_seed, prob_dropout_offset,
+               prob_dropout_offset_base};
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == OVQA_F32) return sdpa_fwd_simt_launch<float>(a, st);
+    if (prob_dropout_p > 0.f) return sdpa_fwd_simt_launch<__nv_bfloat16>(a, st);      // probability dropout: CUDA-core kernels (training of HF BERT layers)
     if (sdpa_fwd_tc5_supported(a)) return sdpa_fwd_tc5_bf16(a, st);
     if (sdpa_fwd_tc5w_supported(a)) return sdpa_fwd_tc5w_bf16(a, st);
     if (sdpa_fwd_mma_supported(a)) return sdpa_fwd_mma_bf16(a, st);
@@ -146,22 +149,26 @@ extern "C" int ovqa_sdpa_bwd(const void* q, const void* k, const void* v, const 
                              const float* mask, int64_t mask_sb, int64_t mask_sh, int64_t mask_sq, const float* boxes,
                              const float* geo_w, const float* geo_b, const float* geo_freq, int64_t d_g, int geo_trig,
                              float* geo_dw, float* geo_db, float scale, int dtype, const float* lse, float* delta, const float* att,
-                             const float* datt, float* dbias, void* stream) {
+                             const float* datt, float* dbias, float prob_dropout_p, uint64_t prob_dropout_seed, uint64_t prob_dropout_offset,
+                             const uint64_t* prob_dropout_offset_base, void* stream) {
     int rc = check_sdpa(q, k, v, B, h, Lq, Lk, dk_, dv_, boxes, geo_w, geo_b, d_g, geo_trig, dtype);
     if (rc) return rc;
     if (!out || !dout || !dq || !dk || !dv || !lse) return OVQA_ERR_BAD_ARG;
     if ((geo_dw == nullptr) != (geo_db == nullptr)) return OVQA_ERR_BAD_ARG;
     if (datt && !att) return OVQA_ERR_BAD_ARG;
+    if (prob_dropout_p < 0.f || prob_dropout_p >= 1.f || (prob_dropout_p > 0.f && dbias)) return OVQA_ERR_BAD_ARG;
     if (B == 0 || Lq == 0) return OVQA_OK;
     SdpaArgs a{q, k, v, const_cast<void*>(out), B, h, Lq, Lk, dk_, dv_, ldq, ldk, ldv, ldo, {mask, mask_sb, mask_sh, mask_sq},
-               {boxes, geo_w, geo_b, geo_freq, (int)d_g, geo_trig}, scale, const_cast<float*>(lse), nullptr};
+               {boxes, geo_w, geo_b, geo_freq, (int)d_g, geo_trig}, scale, const_cast<float*>(lse), nullptr, prob_dropout_p, prob_dropout_seed,
+               prob_dropout_offset, prob_dropout_offset_base};
+    const bool tensor_ok = prob_dropout_p == 0.f;         // the tensor-core kernels draw no probability dropout
     cudaStream_t st = (cudaStream_t)stream;
     // debugging aid only: OVQA_SDPA_BWD=simt keeps the bf16 backward on the CUDA-core kernels
     static const bool force_simt = [] { const char* e = getenv("OVQA_SDPA_BWD"); return e && e[0] == 's'; }();
     // a gradient THROUGH the probabilities (datt) is folded into dP by the CUDA-core kernels only
-    if (dtype == OVQA_BF16 && !force_simt && !datt && !dbias && sdpa_bwd_tc5_supported(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv))
+    if (dtype == OVQA_BF16 && tensor_ok && !force_simt && !datt && !dbias && sdpa_bwd_tc5_supported(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv))
         return sdpa_bwd_tc5_bf16(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv, st);
-    if (dtype == OVQA_BF16 && (!force_simt || dbias) && !datt && sdpa_bwd_mma_supported(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv))
+    if (dtype == OVQA_BF16 && tensor_ok && (!force_simt || dbias) && !datt && sdpa_bwd_mma_supported(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv))
         return sdpa_bwd_mma_bf16(a, dout, dq, dk, dv, lddo, lddq, lddk, lddv, dbias, st);
     if (dbias) return OVQA_ERR_BAD_SHAPE;          // dS is returned by the warp-tile bf16 kernel only (d in {32, 64, 96}, 16-byte aligned rows)
     if (!delta) return OVQA_ERR_BAD_ARG;

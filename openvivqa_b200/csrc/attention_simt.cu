@@ -81,7 +81,13 @@ __global__ void __launch_bounds__(NW * 32) sdpa_fwd_simt(SdpaArgs a) {
         sum = warp_sum(sum);
         const float inv = 1.0f / sum;
         float* att = a.att ? a.att + (((int64_t)b * a.h + hd) * a.Lq + q0 + r) * a.Lk : nullptr;
-        for (int j = lane; j < Lk; j += 32) { const float p = row[j] * inv; row[j] = p; if (att) att[j] = p; }
+        const uint64_t row_idx = (uint64_t)((((int64_t)b * a.h + hd) * a.Lq + q0 + r) * a.Lk);
+        for (int j = lane; j < Lk; j += 32) {
+            float p = row[j] * inv;
+            if (a.pdrop > 0.f) p *= dropout_scale(row_idx + j, a.pdrop, 1.0f / (1.0f - a.pdrop), a.pdrop_seed, effective_offset(a.pdrop_offset, a.pdrop_offset_base));
+            row[j] = p;
+            if (att) att[j] = p;
+        }
         if (a.lse && lane == 0) a.lse[((int64_t)b * a.h + hd) * a.Lq + q0 + r] = mx + logf(sum);
     }
     __syncthreads();
@@ -224,6 +230,7 @@ __global__ void __launch_bounds__(NW * 32) sdpa_bwd_dq_simt(SdpaBwdArgs a) {
                 const float* vr = sV + lane * (dv + 1);
                 for (int d = 0; d < dv; ++d) dp = fmaf(dor[d], vr[d], dp);
                 if (a.datt) dp += __ldg(a.datt + (stat0 + r) * Lk + k0 + lane);
+                if (f.pdrop > 0.f) dp *= dropout_scale((uint64_t)((stat0 + r) * Lk + k0 + lane), f.pdrop, 1.0f / (1.0f - f.pdrop), f.pdrop_seed, effective_offset(f.pdrop_offset, f.pdrop_offset_base));
                 ds = p * (dp - a.delta[stat0 + r]);
                 if (geo && a.geo_dw && raw > 1e-6f) {
                     // d log(clamp(relu(raw))) / d raw = 1/raw when raw > 1e-6; chain into w_h, b_h (attentions.py:116-132)
@@ -322,7 +329,11 @@ __global__ void __launch_bounds__(NW * 32) sdpa_bwd_dkv_simt(SdpaBwdArgs a) {
                 const float* vr = sV + jr * dv;
                 for (int d = 0; d < dv; ++d) dp = fmaf(dor[d], vr[d], dp);
                 if (a.datt) dp += __ldg(a.datt + (stat0 + i0 + lane) * Lk + j0 + jr);
+                float keep = 1.f;
+                if (f.pdrop > 0.f) keep = dropout_scale((uint64_t)((stat0 + i0 + lane) * Lk + j0 + jr), f.pdrop, 1.0f / (1.0f - f.pdrop), f.pdrop_seed, effective_offset(f.pdrop_offset, f.pdrop_offset_base));
+                dp *= keep;
                 ds = p * (dp - a.delta[stat0 + i0 + lane]);
+                p *= keep;                                  // dV = (dropped probabilities)^T dO
             }
             sP[jr * KC + lane] = p;
             sdS[jr * KC + lane] = ds;

@@ -32,6 +32,11 @@ struct SdpaArgs {
     float scale;
     float* lse;
     float* att;
+    // dropout on the PROBABILITIES (HF BertSelfAttention: attention_probs_dropout_prob; the repo's own cores have none): element
+    // ((b*h + head)*Lq + i)*Lk + j of the library's counter-based keep stream.  CUDA-core kernels only.
+    float pdrop;
+    uint64_t pdrop_seed, pdrop_offset;
+    const uint64_t* pdrop_offset_base;
 };
 
 // models/utils.py:118-137 per box: centre, and (extent + 1)

@@ -446,7 +446,7 @@ extern "C" int ovqa_mha_block_infer(const float* xq_f32, const void* xq_op, cons
                                      scale, dtype, nullptr, stream);
     if (rc == OVQA_ERR_BAD_SHAPE)
         rc = ovqa_sdpa_fwd(q, k, v, ws_ctx, B, h, Lq, Lk, dk, dv, ldq, ldk, ldv, hv, mask, mask_sb, mask_sh, mask_sq, nullptr, nullptr, nullptr, nullptr, 0,
-                           0, scale, dtype, nullptr, nullptr, stream);
+                           0, scale, dtype, nullptr, nullptr, 0.f, 0, 0, nullptr, stream);
     if (rc) return rc;
     // fc_o + bias + residual, then LayerNorm   (attentions.py:58, :330-331 with dropout off)
     if ((rc = plain_gemm(ws_ctx, w_o, ws_s, rq, D, hv, hv, hv, D, dtype, OVQA_F32, b_o, 0, xq_f32, D, stream))) return rc;

@@ -278,7 +278,12 @@ class _MHAFn(torch.autograd.Function):
             per_key = mask is None or (mask.dim() == 4 and mask.shape[1] == 1 and mask.shape[2] == 1)
             mask = ops.geo_bias(geo, h, key_mask=mask if per_key else None) if per_key else ops.geo_bias(geo, h) + mask
             geo = None
-        att_ctx, lse, _ = ops.sdpa_fwd(q, k, v, h=h, d_k=dk, d_v=dv, mask=mask, geo=geo, scale=cfg["scale"], need_lse=need_grad)
+        pp = cfg.get("prob_dropout", 0.0) if cfg["training"] else 0.0          # dropout on the probabilities (HF BERT layers): its own counter range
+        prob_dropout = None
+        if pp > 0.0:
+            ps, po = dropout_stream.next(B * h * Lq * Lk)
+            prob_dropout = (pp, ps, po, dropout_stream.base(queries.device))
+        att_ctx, lse, _ = ops.sdpa_fwd(q, k, v, h=h, d_k=dk, d_v=dv, mask=mask, geo=geo, scale=cfg["scale"], need_lse=need_grad, prob_dropout=prob_dropout)
         seed, off = dropout_stream.next(B * Lq * D) if p > 0.0 else (0, 0)
         rng_base = dropout_stream.base(queries.device) if p > 0.0 else None
         q_res = queries.reshape(-1, D)
@@ -295,6 +300,7 @@ class _MHAFn(torch.autograd.Function):
             ctx.cfg, ctx.p, ctx.seed, ctx.off, ctx.rng_base = cfg, p, seed, off, rng_base
             ctx.flags = (self_att, kv_same)
             ctx.geo_as_bias = geo_as_bias
+            ctx.prob_dropout = prob_dropout
             ctx.shapes = (B, Lq, Lk, D)
         y16 = y16.view(B, Lq, D) if y16 is not None else y.new_empty(0)
         ctx.mark_non_differentiable(y16)
@@ -357,7 +363,7 @@ class _MHAFn(torch.autograd.Function):
             ops.geo_bias_bwd(geo, h, dbias, gdw, gdb)
         else:
             ops.sdpa_bwd(q, k, v, att_ctx, dctx, lse, dq, dk_, dv_, h=h, d_k=dk, d_v=dv, mask=mask, geo=geo, geo_dw=gdw,
-                         geo_db=gdb, scale=cfg["scale"])
+                         geo_db=gdb, scale=cfg["scale"], prob_dropout=ctx.prob_dropout)
         dkeys = dvalues = None
         if self_att:
             d2 = dqkv.view(B * Lq, dqkv.shape[-1])
@@ -422,13 +428,15 @@ def _mha_block_infer(queries, keys, values, mask, plan, *, h, d_k, d_v, eps, sca
 
 
 def mha_block(queries, keys, values, mask, *, wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta, h, d_k, d_v, mode="fp32",
-              dropout=0.0, training=False, eps=1e-5, boxes=None, geo_w=None, geo_b=None, geo_trig=True, scale=None):
-    if ONE_CALL_INFERENCE and boxes is None and not torch.is_grad_enabled() and not (training and dropout > 0.0):
+              dropout=0.0, training=False, eps=1e-5, boxes=None, geo_w=None, geo_b=None, geo_trig=True, scale=None, prob_dropout=0.0):
+    """``prob_dropout``: dropout on the attention PROBABILITIES (HF ``BertSelfAttention``; the reference's own cores have none)."""
+    if ONE_CALL_INFERENCE and boxes is None and not torch.is_grad_enabled() and not (training and (dropout > 0.0 or prob_dropout > 0.0)):
         y = _mha_block_infer(queries, keys, values, mask, _block_plan(wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta, mode), h=h, d_k=d_k, d_v=d_v,
                              eps=float(eps), scale=(1.0 / math.sqrt(d_k)) if scale is None else float(scale))
         if y is not None:
             return y
-    cfg = dict(grad=torch.is_grad_enabled(), mode=mode, h=h, d_k=d_k, d_v=d_v, dropout=float(dropout), training=bool(training), eps=float(eps),
+    cfg = dict(grad=torch.is_grad_enabled(), mode=mode, h=h, d_k=d_k, d_v=d_v, dropout=float(dropout), prob_dropout=float(prob_dropout),
+               training=bool(training), eps=float(eps),
                geo_trig=bool(geo_trig), scale=(1.0 / math.sqrt(d_k)) if scale is None else float(scale))
     y, y16 = _MHAFn.apply(queries, keys, values, mask, boxes, wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta, geo_w, geo_b, cfg)
     _attach_shadow(y, y16 if mode == "bf16" else None)
@@ -694,9 +702,11 @@ def pool_and_classify(model, vision_features, text_features, mode, log_softmax=F
         return attr_reduce_pool(feats, w1=mlp.fc1.weight, b1=mlp.fc1.bias, w2=mlp.fc2.weight, b2=mlp.fc2.bias, mode=mode, dropout=mlp.dropout.p,
                                 training=mlp.training)
     wv, wt = pool(model.vision_attr_reduce, vision_features), pool(model.text_attr_reduce, text_features)
-    s = linear(wv, model.vision_proj.weight, model.vision_proj.bias, mode) + linear(wt, model.text_proj.weight, model.text_proj.bias, mode)
+    # B rows each: the two fusion projections and the classifier stay on the exact fp32 GEMM in every mode — 0.2 GFLOP per batch, and the
+    # logits are where operand rounding shows (bf16 operands here alone moved MCAN's log-probabilities by 5e-3)
+    s = linear(wv, model.vision_proj.weight, model.vision_proj.bias, "fp32") + linear(wt, model.text_proj.weight, model.text_proj.bias, "fp32")
     out = layer_norm(s, model.layer_norm.weight, model.layer_norm.bias, model.layer_norm.eps)
-    logits = linear(out, model.classify.weight, model.classify.bias, mode)
+    logits = linear(out, model.classify.weight, model.classify.bias, "fp32")
     return torch.log_softmax(logits, dim=-1) if log_softmax else logits
 
 

@@ -47,12 +47,10 @@ def _layer_dropouts(layer):
 
 
 def fused_layers_apply(encoder, training: bool) -> bool:
-    """Whether the fused blocks reproduce this encoder's arithmetic: always in eval mode; in training mode only without dropout on the
-    attention PROBABILITIES (HF applies p = 0.1 there, which the attention kernels do not draw yet) — the caller then keeps the stock
-    HF layers, the reference's own arithmetic, rather than silently training a different model."""
-    if not training:
-        return True
-    return all(_layer_dropouts(layer)[0] == 0.0 for layer in encoder.layer)
+    """Whether the fused blocks reproduce this encoder's arithmetic: always — eval mode, and training with HF's two dropouts (p on the
+    hidden states after each dense, p on the attention PROBABILITIES: ``functional.mha_block(prob_dropout=...)``).  Kept as the single
+    switch the rebound ``MMT`` / ``TextBert`` forwards consult before leaving the reference's own layers."""
+    return True
 
 
 def bert_layer(layer, x, mask, mode, *, heads, q_rows=None, training=False):
@@ -60,7 +58,7 @@ def bert_layer(layer, x, mask, mode, *, heads, q_rows=None, training=False):
     the module (1e-12).  ``q_rows`` (slice): only those query rows (keys / values: all rows) — the last layer of a decode step."""
     a, s = layer.attention, layer.attention.self
     eps = float(a.output.LayerNorm.eps)
-    _, p_hid = _layer_dropouts(layer)
+    p_att, p_hid = _layer_dropouts(layer)
     xq, mq = x, mask
     if q_rows is not None:
         xq = x[:, q_rows].contiguous()
@@ -71,7 +69,7 @@ def bert_layer(layer, x, mask, mode, *, heads, q_rows=None, training=False):
     d = s.query.weight.shape[0] // heads
     att = Fn.mha_block(xq, x, x, mq, wq=s.query.weight, bq=s.query.bias, wk=s.key.weight, bk=s.key.bias, wv=s.value.weight, bv=s.value.bias,
                        wo=a.output.dense.weight, bo=a.output.dense.bias, gamma=a.output.LayerNorm.weight, beta=a.output.LayerNorm.bias,
-                       h=heads, d_k=d, d_v=d, mode=mode, eps=eps, dropout=p_hid, training=training)
+                       h=heads, d_k=d, d_v=d, mode=mode, eps=eps, dropout=p_hid, prob_dropout=p_att, training=training)
     return Fn.pwff_block(att, w1=layer.intermediate.dense.weight, b1=layer.intermediate.dense.bias, w2=layer.output.dense.weight,
                          b2=layer.output.dense.bias, gamma=layer.output.LayerNorm.weight, beta=layer.output.LayerNorm.bias, mode=mode,
                          eps=float(layer.output.LayerNorm.eps), dropout=p_hid, training=training, dropout_hidden=False)

@@ -154,7 +154,7 @@ class GeoParams:
 
 
 def sdpa_fwd(q, k, v, *, h: int, d_k: int, d_v: int, mask=None, geo: Optional[GeoParams] = None,
-             scale: Optional[float] = None, need_lse: bool = False, need_att: bool = False, out=None):
+             scale: Optional[float] = None, need_lse: bool = False, need_att: bool = False, out=None, prob_dropout=None):
     """Attention core on projected tensors.  q:(B,Lq,>=h*d_k) k:(B,Lk,..) v:(B,Lk,..) — last-dim-contiguous views
     (e.g. slices of a fused QKV buffer).  Returns (out (B,Lq,h*d_v), lse|None, att|None)."""
     _need_cuda(q, k, v, mask)
@@ -173,8 +173,9 @@ def sdpa_fwd(q, k, v, *, h: int, d_k: int, d_v: int, mask=None, geo: Optional[Ge
     if B == 0 or Lq == 0:
         return out, lse, att
     # prefix-LM structure hint (harness.m4c.mmt_mask): per-key row + causal tail instead of the dense (B,1,L,L) tensor
+    pd_p, pd_seed, pd_off, pd_base = prob_dropout if prob_dropout is not None else (0.0, 0, 0, None)
     hint = getattr(mask, "_ovqa_prefix_lm", None)
-    if hint is not None and q.dtype == torch.bfloat16 and geo is None and not need_att:
+    if hint is not None and q.dtype == torch.bfloat16 and geo is None and not need_att and pd_p == 0.0:
         key_row, tail, value = hint
         rc = L.lib().ovqa_sdpa_fwd_prefix_lm(_p(q), _p(k), _p(v), _p(out), B, h, Lq, Lk, d_k, d_v, q.stride(1), k.stride(1), v.stride(1),
                                              out.stride(1), _p(key_row), key_row.stride(0) if key_row.shape[0] > 1 else 0, int(tail),
@@ -189,12 +190,13 @@ def sdpa_fwd(q, k, v, *, h: int, d_k: int, d_v: int, mask=None, geo: Optional[Ge
            q.stride(1), k.stride(1), v.stride(1), out.stride(1), _p(mask), sb, sh, sq,
            _p(g.boxes) if g else None, _p(g.w) if g else None, _p(g.b) if g else None,
            _p(g.freq) if (g and g.freq is not None) else None, g.d_g if g else 0, int(g.trig) if g else 0,
-           float(scale), _DT[q.dtype], _p(lse), _p(att), _stream())
+           float(scale), _DT[q.dtype], _p(lse), _p(att), float(pd_p), int(pd_seed), int(pd_off), _p(pd_base), _stream())
     return out, lse, att
 
 
 def sdpa_bwd(q, k, v, out, dout, lse, dq, dk, dv, *, h: int, d_k: int, d_v: int, mask=None,
-             geo: Optional[GeoParams] = None, geo_dw=None, geo_db=None, scale: Optional[float] = None, att=None, datt=None, dbias=None):
+             geo: Optional[GeoParams] = None, geo_dw=None, geo_db=None, scale: Optional[float] = None, att=None, datt=None, dbias=None,
+             prob_dropout=None):
     """``att`` / ``datt`` (B,h,Lq,Lk) fp32: the probabilities the forward returned and the gradient arriving through them (a direct
     caller of the core consumed ``att``, mmf_lorra.py:127-146); both or neither."""
     _need_cuda(q, k, v, out, dout, lse, dq, dk, dv, att, datt, dbias)
@@ -221,7 +223,8 @@ def sdpa_bwd(q, k, v, out, dout, lse, dq, dk, dv, *, h: int, d_k: int, d_v: int,
            _p(mask), sb, sh, sq,
            _p(g.boxes) if g else None, _p(g.w) if g else None, _p(g.b) if g else None,
            _p(g.freq) if (g and g.freq is not None) else None, g.d_g if g else 0, int(g.trig) if g else 0,
-           _p(geo_dw), _p(geo_db), float(scale), _DT[q.dtype], _p(lse), _p(delta), _p(att) if datt is not None else None, _p(datt), _p(dbias), _stream())
+           _p(geo_dw), _p(geo_db), float(scale), _DT[q.dtype], _p(lse), _p(delta), _p(att) if datt is not None else None, _p(datt), _p(dbias),
+           *((float(prob_dropout[0]), int(prob_dropout[1]), int(prob_dropout[2]), _p(prob_dropout[3])) if prob_dropout is not None else (0.0, 0, 0, None)), _stream())
 
 
 def layernorm_fwd(x, gamma, beta, *, residual=None, post_add=None, eps: float = 1e-5, want_f32: bool = True,

@@ -146,11 +146,21 @@ def geo_bias_bwd(geo, h, dbias, geo_dw, geo_db):
     geo_db += coef.sum(dim=(0, 2, 3))
 
 
-def sdpa_fwd(q, k, v, *, h, d_k, d_v, mask=None, geo=None, scale=None, need_lse=False, need_att=False, out=None):
+def _prob_keep(prob_dropout, shape):
+    if prob_dropout is None or prob_dropout[0] <= 0.0:
+        return None
+    p, seed, off, base = prob_dropout
+    return _keep_scale(math.prod(shape), p, seed, off, base).view(shape)
+
+
+def sdpa_fwd(q, k, v, *, h, d_k, d_v, mask=None, geo=None, scale=None, need_lse=False, need_att=False, out=None, prob_dropout=None):
     B, Lq, Lk = q.shape[0], q.shape[1], k.shape[1]
     scale = 1.0 / math.sqrt(d_k) if scale is None else scale
     s = _scores(q, k, h, d_k, mask, geo, scale)
     p = torch.softmax(s, dim=-1)
+    keep = _prob_keep(prob_dropout, p.shape)
+    if keep is not None:
+        p = p * keep
     vh = v[..., :h * d_v].float().reshape(B, Lk, h, d_v).permute(0, 2, 1, 3)
     o = (p @ vh).permute(0, 2, 1, 3).reshape(B, Lq, h * d_v).to(q.dtype)
     if out is not None:
@@ -160,7 +170,7 @@ def sdpa_fwd(q, k, v, *, h, d_k, d_v, mask=None, geo=None, scale=None, need_lse=
 
 
 def sdpa_bwd(q, k, v, out, dout, lse, dq, dk, dv, *, h, d_k, d_v, mask=None, geo=None, geo_dw=None, geo_db=None, scale=None,
-             att=None, datt=None, dbias=None):
+             att=None, datt=None, dbias=None, prob_dropout=None):
     B, Lq, Lk = q.shape[0], q.shape[1], k.shape[1]
     scale = 1.0 / math.sqrt(d_k) if scale is None else scale
     s = _scores(q, k, h, d_k, mask, geo, scale)
@@ -172,9 +182,14 @@ def sdpa_bwd(q, k, v, out, dout, lse, dq, dk, dv, *, h, d_k, d_v, mask=None, geo
     dp = do @ vh.transpose(-1, -2)
     if datt is not None:
         dp = dp + datt.float()
+    keep = _prob_keep(prob_dropout, p.shape)
+    if keep is not None:
+        dp = dp * keep
     ds = p * (dp - (p * dp).sum(-1, keepdim=True))
     if dbias is not None:
         dbias.copy_(ds)
+    if keep is not None:
+        p = p * keep
     dv.copy_((p.transpose(-1, -2) @ do).permute(0, 2, 1, 3).reshape(B, Lk, h * d_v).to(dv.dtype))
     dq.copy_(((ds @ kh) * scale).permute(0, 2, 1, 3).reshape(B, Lq, h * d_k).to(dq.dtype))
     dk.copy_(((ds.transpose(-1, -2) @ qh) * scale).permute(0, 2, 1, 3).reshape(B, Lk, h * d_k).to(dk.dtype))

@@ -295,3 +295,36 @@ def test_harness_mcan_head_goes_through_the_pooling_head(cpu_ops, golden):
     with torch.no_grad():
         logp = m(H.Batch(C.mcan_inputs(c)))
     _close(logp, gm["logp"], 1e-4)
+
+
+def test_probability_dropout_block_matches_the_explicit_composition(cpu_ops):
+    """HF BertSelfAttention drops attention PROBABILITIES (p = 0.1 by default): mha_block(prob_dropout=...) forward and backward against
+    autograd through the explicit composition that applies the SAME keep-scales (mask stream of the call's (seed, offset))."""
+    torch.manual_seed(0)
+    D, h, B, L = 32, 4, 2, 9
+    params = S.synth_params(C.att_spec(D, h, D // h, D // h), 3)
+    x = torch.randn(B, L, D)
+    mask = torch.zeros(B, 1, 1, L)
+    mask[:, :, :, -2:] = R.MASK_VALUE
+    pi = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    xi = x.clone().requires_grad_(True)
+    Fn.dropout_stream.offset = 0
+    y = Fn.mha_block(xi, xi, xi, mask, wq=pi["attention.fc_q.weight"], bq=pi["attention.fc_q.bias"], wk=pi["attention.fc_k.weight"],
+                     bk=pi["attention.fc_k.bias"], wv=pi["attention.fc_v.weight"], bv=pi["attention.fc_v.bias"], wo=pi["attention.fc_o.weight"],
+                     bo=pi["attention.fc_o.bias"], gamma=pi["layer_norm.weight"], beta=pi["layer_norm.bias"], h=h, d_k=D // h, d_v=D // h,
+                     mode="fp32", dropout=0.0, prob_dropout=0.3, training=True)
+    keep = cpu_ops._keep_scale(B * h * L * L, 0.3, Fn.dropout_stream.seed, 0).view(B, h, L, L)
+    pr = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    xr = x.clone().requires_grad_(True)
+    lin = lambda n, t: torch.nn.functional.linear(t, pr[f"attention.{n}.weight"], pr[f"attention.{n}.bias"])
+    sp = lambda t: t.view(B, L, h, D // h).permute(0, 2, 1, 3)
+    att = torch.softmax(sp(lin("fc_q", xr)) @ sp(lin("fc_k", xr)).transpose(-1, -2) / math.sqrt(D // h) + mask, -1) * keep
+    ctx = (att @ sp(lin("fc_v", xr))).permute(0, 2, 1, 3).reshape(B, L, D)
+    ref = torch.nn.functional.layer_norm(xr + lin("fc_o", ctx), (D,), pr["layer_norm.weight"], pr["layer_norm.bias"])
+    w = torch.randn(ref.shape, generator=torch.Generator().manual_seed(1))
+    (ref * w).sum().backward()
+    (y * w).sum().backward()
+    _close(y.detach(), ref.detach(), 1e-5)
+    _close(xi.grad, xr.grad)
+    for k in params:
+        _close(pi[k].grad, pr[k].grad)

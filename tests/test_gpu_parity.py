@@ -1037,3 +1037,34 @@ def test_attribute_reduce_pooling_head(dev, mode, p_drop):
     for k in params:
         e = float((pi[k].grad.cpu() - pr[k].grad).norm() / pr[k].grad.norm().clamp_min(1e-12))
         assert e <= tol, (k, e)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_probability_dropout_in_the_attention_core(dev, mode):
+    """Dropout on the attention probabilities (HF BertSelfAttention, the layers MMF_M4C trains through): forward and backward of the core
+    against autograd of softmax(.) * keep-scale @ v, with the keep-scales read back from the library's own counter stream."""
+    from openvivqa_b200 import functional as Fn, ops
+    B, h, Lq, Lk, d, p = 3, 4, 37, 53, 32, 0.2
+    g = torch.Generator().manual_seed(8)
+    dt = torch.float32 if mode == "fp32" else torch.bfloat16
+    q, k, v = (torch.randn((B, L, h * d), generator=g).to(dt) for L in (Lq, Lk, Lk))
+    mask = torch.zeros((B, 1, 1, Lk))
+    mask[:, :, :, -7:] = -10e4
+    seed, off = 1234, 77
+    pd = (p, seed, off, None)
+    qd, kd, vd = q.to(dev), k.to(dev), v.to(dev)
+    out, lse, _ = ops.sdpa_fwd(qd, kd, vd, h=h, d_k=d, d_v=d, mask=mask.to(dev), need_lse=True, prob_dropout=pd)
+    keep = ops.dropout_keep_mask(B * h * Lq * Lk, p, seed, off, dev).view(B, h, Lq, Lk).cpu() / (1.0 - p)
+    qr, kr, vr = (t.float().clone().requires_grad_(True) for t in (q, k, v))
+    sp = lambda t, L: t.view(B, L, h, d).permute(0, 2, 1, 3)
+    att = torch.softmax(sp(qr, Lq) @ sp(kr, Lk).transpose(-1, -2) / math.sqrt(d) + mask, -1) * keep
+    ref = (att @ sp(vr, Lk)).permute(0, 2, 1, 3).reshape(B, Lq, h * d)
+    w = torch.randn(ref.shape, generator=g)
+    (ref * w).sum().backward()
+    check(out, ref, mode, "core with probability dropout")
+    dq, dk, dv = torch.empty_like(qd), torch.empty_like(kd), torch.empty_like(vd)
+    ops.sdpa_bwd(qd, kd, vd, out, w.to(dev).to(dt), lse, dq, dk, dv, h=h, d_k=d, d_v=d, mask=mask.to(dev), prob_dropout=pd)
+    tol = 1e-3 if mode == "fp32" else 4e-2
+    for got, want, name in ((dq, qr.grad, "dq"), (dk, kr.grad, "dk"), (dv, vr.grad, "dv")):
+        e = float((got.float().cpu() - want).norm() / want.norm())
+        assert e <= tol, (name, e)
