@@ -364,6 +364,9 @@ class _MHAFn(torch.autograd.Function):
         else:
             ops.sdpa_bwd(q, k, v, att_ctx, dctx, lse, dq, dk_, dv_, h=h, d_k=dk, d_v=dv, mask=mask, geo=geo, geo_dw=gdw,
                          geo_db=gdb, scale=cfg["scale"], prob_dropout=ctx.prob_dropout)
+        if ctx.prob_dropout is not None:
+            # dropped probabilities do not sum to 1 over the keys: the value-bias shortcut above does not hold, take the column sums of dV
+            dbv = ops.colsum(dv_.reshape(-1, dv_.shape[-1]) if dv_.is_contiguous() else dv_.view(B * Lk, dv_.shape[-1]))
         dkeys = dvalues = None
         if self_att:
             d2 = dqkv.view(B * Lq, dqkv.shape[-1])
