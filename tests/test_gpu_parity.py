@@ -922,8 +922,9 @@ def test_geo_bias_kernels_against_the_oracle(dev, name):
     pr = {k: v.clone().requires_grad_(True) for k, v in params.items()}
     ref = R.geometry_log_bias(pr, x["boxes"], h=h, d_g=dg, trig=trig)
     gsel = torch.randn(ref.shape, generator=torch.Generator().manual_seed(2))
-    # the log of the clamp has slope 0 on the clamped side: weight the loss away from entries sitting at the clamp (sign flips there are fp noise)
-    (ref * gsel).sum().backward()
+    # d log(raw) / d raw = 1 / raw reaches 1e6 next to the clamp, where raw itself is only known to ~1e-5 (sin / cos at hundreds of radians):
+    # the loss is taken on exp(bias) = clamp(relu(raw), 1e-6), i.e. the kernel is handed dbias = gsel * exp(bias), which keeps it conditioned
+    (ref.exp() * gsel).sum().backward()
     w = torch.cat([params[f"fc_gs.{i}.weight"] for i in range(h)], 0).to(dev)
     b = torch.cat([params[f"fc_gs.{i}.bias"] for i in range(h)], 0).to(dev)
     geo = ops.GeoParams(x["boxes"].to(dev), w, b, trig)
@@ -938,7 +939,7 @@ def test_geo_bias_kernels_against_the_oracle(dev, name):
     torch.testing.assert_close(masked[..., :-3], out.cpu()[..., :-3], rtol=0, atol=0)
     assert (masked[..., -3:] < -9e4).all()
     dw, db = torch.zeros((h, dg), device=dev), torch.zeros((h,), device=dev)
-    ops.geo_bias_bwd(geo, h, gsel.to(dev).contiguous(), dw, db)
+    ops.geo_bias_bwd(geo, h, (gsel * ref.detach().exp()).to(dev).contiguous(), dw, db)
     dw_ref = torch.cat([pr[f"fc_gs.{i}.weight"].grad for i in range(h)], 0)
     db_ref = torch.cat([pr[f"fc_gs.{i}.bias"].grad for i in range(h)], 0)
     assert rel_err(dw, dw_ref) <= 2e-3 and rel_err(db, db_ref) <= 2e-3, (rel_err(dw, dw_ref), rel_err(db, db_ref))
@@ -1035,6 +1036,9 @@ def test_attribute_reduce_pooling_head(dev, mode, p_drop):
     tol = 2e-3 if mode == "fp32" else 6e-2
     assert rel_err(xi.grad, xr.grad) <= tol, rel_err(xi.grad, xr.grad)
     for k in params:
+        if k == "fc2.bias":          # softmax gradients sum to zero over the sequence: the true gradient is 0, both sides hold rounding noise
+            assert float(pi[k].grad.abs().max()) <= 1e-3 * float(w.abs().sum()) / N
+            continue
         e = float((pi[k].grad.cpu() - pr[k].grad).norm() / pr[k].grad.norm().clamp_min(1e-12))
         assert e <= tol, (k, e)
 
