@@ -97,8 +97,10 @@ class ClockSampler:
                     power_w_max=max(pw) if pw else None, reasons=reasons, samples=len(rows), samples_under_load=len(busy))
 
 
-def synth_batches(n, wl, seed=1, boxes=False):
-    """n distinct synthetic ViVQA-shaped batches in pinned host memory: (features, tokens, answers[, boxes])."""
+def synth_batches(n, wl, seed=1, boxes=False, feature_dtype=torch.float32):
+    """n distinct synthetic ViVQA-shaped batches in pinned host memory: (features, tokens, answers[, boxes]).
+    ``feature_dtype=torch.bfloat16``: the region features are STAGED as bf16 (pre-padded pinned bf16 staging buffers) —
+    the vision embedding's GEMM rounds its operand to bf16 anyway, so the step's results are bit-identical and the feed is half the bytes."""
     g = torch.Generator().manual_seed(seed)
     B, Nv, Lt = wl["B"], wl["Nv"], wl["Lt"]
     out = []
@@ -106,6 +108,7 @@ def synth_batches(n, wl, seed=1, boxes=False):
         feats = torch.randn((B, Nv, wl["d_feature"]), generator=g).abs_()
         nv = torch.randint(36, Nv + 1, (B,), generator=g)
         feats[torch.arange(Nv).unsqueeze(0) >= nv.unsqueeze(1)] = 0.0
+        feats = feats.to(feature_dtype)
         toks = torch.randint(4, wl["vocab"], (B, Lt), generator=g)
         nt = torch.randint(5, Lt + 1, (B,), generator=g)
         toks[torch.arange(Lt).unsqueeze(0) >= nt.unsqueeze(1)] = 0
@@ -533,9 +536,10 @@ def run_train(ctx, wl, workload_name, metric, make_model, forward_loss, boxes=Fa
         side0 = torch.cuda.Stream()
         side0.wait_stream(torch.cuda.current_stream())
         torch.cuda.set_stream(side0)
-    net = D.data_parallel(model, device_ids=[ctx.local], bucket_cap_mb=25, grad_dtype=os.environ.get("OVQA_DDP_GRAD_DTYPE", "bf16"))
+    net = D.data_parallel(model, device_ids=[ctx.local], bucket_cap_mb=int(os.environ.get("OVQA_DDP_BUCKET_MB", "25")), grad_dtype=os.environ.get("OVQA_DDP_GRAD_DTYPE", "bf16"))
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.9, 0.98), fused=True, capturable=use_graph)
-    host = synth_batches(3, wl, seed=1 + rank, boxes=boxes)
+    feat_dt = torch.float32 if os.environ.get("OVQA_FEATURE_FEED", "bf16") == "fp32" else torch.bfloat16
+    host = synth_batches(3, wl, seed=1 + rank, boxes=boxes, feature_dtype=feat_dt)
     dev_batches = [tuple(t.to(dev) for t in b) for b in host]
     static = tuple(torch.empty_like(t) for t in dev_batches[0])           # the step's input buffers (graph-stable addresses)
     meter = METER
@@ -702,6 +706,8 @@ def run_train(ctx, wl, workload_name, metric, make_model, forward_loss, boxes=Fa
                    ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
                    config=dict(workload=workload_name, global_batch=wl["B"] * world, parallelism=f"dp{world}",
                                l2=f"inputs larger than L2 ({h2d_bytes / 1e6:.0f} MB per step, 3 rotating batches)", final_loss=final_loss,
+                               feature_feed=("region features staged as bf16 in pinned host memory and in HBM (the vision embedding's GEMM rounds its operand to "
+                                             "bf16 anyway: bit-identical step, half the feed bytes)" if feat_dt == torch.bfloat16 else "fp32 region features"),
                                cuda_graph=graph is not None, cuda_graph_error=graph_err, eager_ms_per_step=eager_ms_per_step,
                                numerics="bf16 operands / fp32 accumulate in the path's blocks; library ops around them fp32 with TF32 allowed (harness.bench_library_math)"),
                    e2e=dict(value=e2e, unit="samples/s", h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=4),

@@ -184,6 +184,9 @@ int ovqa_layernorm_bwd(const float* dy, const float* x, const float* mean, const
  * (row pitch ldx) writes the contiguous bf16 GEMM operand y [rows, K] and the padding mask[rows] (mask_value where the row sums to 0, else 0;
  * NULL to skip).  K % 8 == 0. */
 int ovqa_cast_rows_padmask(const float* x, void* y_bf16, float* mask, int64_t rows, int64_t K, int64_t ldx, float mask_value, void* stream);
+/* The same padding mask for features that ARRIVE as bf16 (an input feed staged as bf16 in pinned host memory halves the host-to-device
+ * bytes; the first GEMM rounds its operand to bf16 anyway, so results are bit-identical): mask[row] = mask_value where the row sums to 0. */
+int ovqa_rows_padmask_bf16(const void* x_bf16, float* mask, int64_t rows, int64_t K, int64_t ldx, float mask_value, void* stream);
 /* y_bf16[i] = a[i] * b[i]   (a fp32, b fp32 or bf16): gradient of a fused activation from its saved derivative */
 int ovqa_mul_to_bf16(const float* a, const void* b, int b_dtype, void* y_bf16, int64_t n, void* stream);
 int ovqa_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream);

@@ -30,6 +30,7 @@ _PROTOS = {
                   _vp, _vp, _i64, _vp, _i64, _vp, _i64, _f32, _u64, _u64, _vp, _vp, _i32, _vp],
     "ovqa_gemm_bf16_simt": [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _f32, _vp, _i32, _vp],
     "ovqa_cast_rows_padmask": [_vp, _vp, _vp, _i64, _i64, _i64, _f32, _vp],
+    "ovqa_rows_padmask_bf16": [_vp, _vp, _i64, _i64, _i64, _f32, _vp],
     "ovqa_mha_decode_step": [_vp, _vp, _vp, _i32, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _i64, _i64,
                              _vp, _i64, _i64, _i64, _f32, _i32, _vp, _i64, _vp, _vp, _vp],
     "ovqa_mha_decode_workspace_bytes": [_i64] * 7 + [_i32],

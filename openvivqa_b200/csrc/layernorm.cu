@@ -312,6 +312,25 @@ __global__ void __launch_bounds__(256) cast_rows_padmask_kernel(const float* __r
     if (lane == 0 && mask) mask[row] = s == 0.0f ? mask_value : 0.0f;
 }
 
+// the padding mask alone, for features that already arrive as bf16 (pinned bf16 staging of the input feed): warp per row
+__global__ void __launch_bounds__(256) rows_padmask_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ mask, int64_t rows, int64_t K,
+                                                                int64_t ldx, float mask_value) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
+    if (row >= rows) return;
+    const __nv_bfloat16* xr = x + row * ldx;
+    float s = 0.f;
+    const int64_t nv = K / 8;
+    for (int64_t c = lane; c < nv; c += 32) {
+        const uint4 u = *reinterpret_cast<const uint4*>(xr + 8 * c);
+        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+        s += ((a.x + a.y) + (b.x + b.y)) + ((c2.x + c2.y) + (d.x + d.y));
+    }
+    for (int64_t c = nv * 8 + lane; c < K; c += 32) s += __bfloat162float(xr[c]);
+    s = warp_sum(s);
+    if (lane == 0) mask[row] = s == 0.0f ? mask_value : 0.0f;
+}
+
 // out_bf16 = a (fp32) * b (fp32 | bf16): the gradient of a fused activation from its saved derivative
 template <typename TB>
 __global__ void mul_to_bf16_kernel(const float* __restrict__ a, const TB* __restrict__ b, __nv_bfloat16* __restrict__ y, int64_t n) {
@@ -502,6 +521,14 @@ extern "C" int ovqa_cast_rows_padmask(const float* x, void* y_bf16, float* mask,
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y_bf16) & 15) || (ldx % 4) || (K % 8)) return OVQA_ERR_ALIGNMENT;
     if (rows == 0) return OVQA_OK;
     cast_rows_padmask_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y_bf16, mask, rows, K, ldx, mask_value);
+    OVQA_LAUNCH_OK();
+    return OVQA_OK;
+}
+extern "C" int ovqa_rows_padmask_bf16(const void* x_bf16, float* mask, int64_t rows, int64_t K, int64_t ldx, float mask_value, void* stream) {
+    if (!x_bf16 || !mask || rows < 0 || K <= 0 || ldx < K) return OVQA_ERR_BAD_ARG;
+    if ((reinterpret_cast<uintptr_t>(x_bf16) & 15) || (ldx % 8)) return OVQA_ERR_ALIGNMENT;
+    if (rows == 0) return OVQA_OK;
+    rows_padmask_bf16_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x_bf16, mask, rows, K, ldx, mask_value);
     OVQA_LAUNCH_OK();
     return OVQA_OK;
 }

@@ -528,7 +528,7 @@ class FeatureEmbedding(nn.Module):
 
     def forward(self, features):
         mode = _mode_of(self)
-        if mode == "bf16" and features.dim() == 3 and features.dtype == torch.float32 and features.shape[-1] % 8 == 0:
+        if mode == "bf16" and features.dim() == 3 and features.dtype in (torch.float32, torch.bfloat16) and features.shape[-1] % 8 == 0:
             return Fn.feature_embedding(features, self.proj.weight, self.proj.bias, dropout=self.dropout.p, training=self.training,
                                         mask_value=MASK_VALUE)
         masks = (torch.sum(features, dim=-1) == 0).long() * MASK_VALUE

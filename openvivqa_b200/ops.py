@@ -292,8 +292,15 @@ def cast_rows_padmask(x: torch.Tensor, mask_value: float):
     """fp32 (rows, K) -> (bf16 copy (rows, K), additive padding mask (rows,) fp32: ``mask_value`` where the row sums to 0) in one pass."""
     _need_cuda(x)
     x = _rowmajor2d(x, "x")
+    if x.dtype == torch.bfloat16 and x.shape[1] % 8 == 0:
+        # features staged as bf16 (input feed in pinned bf16 host buffers): they ARE the GEMM operand, only the mask is computed
+        x = x if _ld(x) % 8 == 0 else x.contiguous()
+        mask = torch.empty((x.shape[0],), device=x.device, dtype=torch.float32)
+        if x.shape[0]:
+            L.call("ovqa_rows_padmask_bf16", _p(x), _p(mask), x.shape[0], x.shape[1], _ld(x), float(mask_value), _stream())
+        return x, mask
     if x.dtype != torch.float32 or x.shape[1] % 8 != 0:
-        raise ValueError("cast_rows_padmask: x must be fp32 with a width that is a multiple of 8")
+        raise ValueError("cast_rows_padmask: x must be fp32 (or bf16) with a width that is a multiple of 8")
     y = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
     mask = torch.empty((x.shape[0],), device=x.device, dtype=torch.float32)
     if x.shape[0] == 0:

@@ -238,7 +238,7 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, *, dx_add=None, want_bf16=False, dro
 
 
 def cast_rows_padmask(x, mask_value):
-    return x.to(torch.bfloat16), (x.sum(-1) == 0).float() * mask_value
+    return x.to(torch.bfloat16), (x.float().sum(-1) == 0).float() * mask_value
 
 
 def mul_to_bf16(a, b):

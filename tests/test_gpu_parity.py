@@ -1072,3 +1072,20 @@ def test_probability_dropout_in_the_attention_core(dev, mode):
     for got, want, name in ((dq, qr.grad, "dq"), (dk, kr.grad, "dk"), (dv, vr.grad, "dv")):
         e = float((got.float().cpu() - want).norm() / want.norm())
         assert e <= tol, (name, e)
+
+
+def test_feature_embedding_accepts_bf16_staged_features(dev):
+    """Region features staged as bf16 (pinned bf16 feed): same outputs, mask and gradients as the fp32 features they were rounded from."""
+    from openvivqa_b200 import functional as Fn
+    B, N, K, D = 3, 40, 256, 128
+    feats = S.padded_features(B, N, K, 3, min_valid=7).to(torch.bfloat16).float()        # exactly representable in bf16
+    m = ovqa.FeatureEmbedding(H.NS(D_FEATURE=K, D_MODEL=D, DROPOUT=0.0, COMPUTE_DTYPE="bf16")).to(dev).train()
+    y32, m32 = m(feats.to(dev))
+    y32.square().sum().backward()
+    g32 = m.proj.weight.grad.clone()
+    m.zero_grad()
+    y16, m16 = m(feats.to(dev).to(torch.bfloat16))
+    y16.square().sum().backward()
+    assert torch.equal(y16, y32) and torch.equal(m16, m32)
+    assert torch.equal(m.proj.weight.grad, g32)
+    assert (m16 != 0).any() and (m16 == 0).any()
