@@ -1022,7 +1022,9 @@ def test_attribute_reduce_pooling_head(dev, mode, p_drop):
     pi = {k: v.clone().to(dev).requires_grad_(True) for k, v in params.items()}
     xi = x.clone().to(dev).requires_grad_(True)
     y = Fn.attr_reduce_pool(xi, w1=pi["fc1.weight"], b1=pi["fc1.bias"], w2=pi["fc2.weight"], b2=pi["fc2.bias"], mode=mode, dropout=p_drop, training=True)
-    keep = ops.dropout_keep_mask(B * N * D, p_drop, Fn.dropout_stream.seed, 0, dev).view(B, N, D).cpu() if p_drop > 0 else torch.ones(B, N, D)
+    # (the device-side offset base may have been advanced by an earlier CUDA-graph test of this process: read the mask with it)
+    keep = ops.dropout_keep_mask(B * N * D, p_drop, Fn.dropout_stream.seed, 0, dev, offset_base=Fn.dropout_stream.base(dev)).view(B, N, D).cpu() \
+        if p_drop > 0 else torch.ones(B, N, D)
     ks = keep / (1.0 - p_drop)
     pr = {k: v.clone().requires_grad_(True) for k, v in params.items()}
     xr = x.clone().requires_grad_(True)
