@@ -1,23 +1,29 @@
 // Exact-fp32 FFMA GEMM: the 1e-4 parity path of ovqa_gemm (and the on-device cross-check of the tcgen05
 // kernel).  Plain smem-tiled 64x64x16 with 4x4 register blocking; operands addressed through generic
 // (row, k) strides so N/T forms share one kernel.  Not the performance path: bf16 goes to gemm_tcgen05.cu.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace ovqa {
 
 namespace {
 
-constexpr int BM = 64, BN = 64, BK = 16, NT = 256;
+constexpr int BK = 16;
 
-template <typename TIn, typename TC>
-__global__ void __launch_bounds__(NT) gemm_simt_kernel(const TIn* __restrict__ A, const TIn* __restrict__ B, TC* __restrict__ C,
+// Tile T x T with (T/4)^2 threads, each a 4 x 4 block of outputs.  T = 64 for ordinary sizes; T = 32 when a 64-wide tiling would leave most
+// SMs idle (the B-row projections and the classifier of the pooling head, 256 x 512 x 512: 32 CTAs with a 32-step serial k loop took
+// 44 us for 0.13 GFLOP) — four times the CTAs, same summation order per output, so results stay deterministic (no split-K atomics).
+template <typename TIn, typename TC, int T>
+__global__ void __launch_bounds__((T / 4) * (T / 4)) gemm_simt_kernel(const TIn* __restrict__ A, const TIn* __restrict__ B, TC* __restrict__ C,
                                                        int64_t m, int64_t n, int64_t k, int64_t sa_m, int64_t sa_k,
                                                        int64_t sb_n, int64_t sb_k, int64_t ldc, Epilogue epi, int split_k) {
+    constexpr int BM = T, BN = T, NT = (T / 4) * (T / 4);
     __shared__ float As[BK][BM + 4];
     __shared__ float Bs[BK][BN + 4];
     const int tid = threadIdx.x;
     const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
-    const int tx = tid % 16, ty = tid / 16;  // 16x16 threads, each 4x4 outputs
+    const int tx = tid % (T / 4), ty = tid / (T / 4);  // (T/4) x (T/4) threads, each 4x4 outputs
 
     // k range of this split
     const int64_t k_per = ((k + split_k - 1) / split_k + BK - 1) / BK * BK;
@@ -25,16 +31,16 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const TIn* __restrict__ A
     const int64_t k_end = min(k, k_begin + k_per);
 
     float acc[4][4] = {};
-    // loader mapping: 1024 elements per tile / 256 threads = 4 each
+    // loader mapping: T*BK elements per operand tile over NT threads; consecutive threads follow the operand's contiguous dimension
     const bool a_kc = (sa_k == 1), b_kc = (sb_k == 1);
     for (int64_t kk = k_begin; kk < k_end; kk += BK) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int e = tid; e < T * BK; e += NT) {
             int r, c;  // r: m (or n) index in tile, c: k index in tile
-            if (a_kc) { r = tid / 4; c = (tid % 4) * 4 + i; } else { c = tid / 16; r = (tid % 16) * 4 + i; }
+            if (a_kc) { r = e / BK; c = e % BK; } else { c = e / T; r = e % T; }
             const int64_t gm = m0 + r, gk = kk + c;
             As[c][r] = (gm < m && gk < k_end) ? to_f32<TIn>(A[gm * sa_m + gk * sa_k]) : 0.0f;
-            if (b_kc) { r = tid / 4; c = (tid % 4) * 4 + i; } else { c = tid / 16; r = (tid % 16) * 4 + i; }
+            if (b_kc) { r = e / BK; c = e % BK; } else { c = e / T; r = e % T; }
             const int64_t gn = n0 + r, gk2 = kk + c;
             Bs[c][r] = (gn < n && gk2 < k_end) ? to_f32<TIn>(B[gn * sb_n + gk2 * sb_k]) : 0.0f;
         }
@@ -79,11 +85,17 @@ int launch(const TIn* A, const TIn* B, void* C, int64_t m, int64_t n, int64_t k,
     const int64_t sb_n = b_op == OVQA_OP_N ? ldb : 1, sb_k = b_op == OVQA_OP_N ? 1 : ldb;
     if (split_k < 1) split_k = 1;
     if (split_k > 1 && epi.c_dtype != OVQA_F32) return OVQA_ERR_BAD_ARG;
-    dim3 grid((unsigned)((n + BN - 1) / BN), (unsigned)((m + BM - 1) / BM), (unsigned)split_k);
-    if (epi.c_dtype == OVQA_F32)
-        gemm_simt_kernel<TIn, float><<<grid, NT, 0, st>>>(A, B, (float*)C, m, n, k, sa_m, sa_k, sb_n, sb_k, ldc, epi, split_k);
-    else
-        gemm_simt_kernel<TIn, __nv_bfloat16><<<grid, NT, 0, st>>>(A, B, (__nv_bfloat16*)C, m, n, k, sa_m, sa_k, sb_n, sb_k, ldc, epi, split_k);
+    const int64_t tiles64 = ((n + 63) / 64) * ((m + 63) / 64) * split_k;
+    const bool small = tiles64 * 2 <= sm_count();
+    auto go = [&](auto tile_tag) {
+        constexpr int T = decltype(tile_tag)::value;
+        dim3 grid((unsigned)((n + T - 1) / T), (unsigned)((m + T - 1) / T), (unsigned)split_k);
+        if (epi.c_dtype == OVQA_F32)
+            gemm_simt_kernel<TIn, float, T><<<grid, (T / 4) * (T / 4), 0, st>>>(A, B, (float*)C, m, n, k, sa_m, sa_k, sb_n, sb_k, ldc, epi, split_k);
+        else
+            gemm_simt_kernel<TIn, __nv_bfloat16, T><<<grid, (T / 4) * (T / 4), 0, st>>>(A, B, (__nv_bfloat16*)C, m, n, k, sa_m, sa_k, sb_n, sb_k, ldc, epi, split_k);
+    };
+    if (small) go(std::integral_constant<int, 32>{}); else go(std::integral_constant<int, 64>{});
     OVQA_LAUNCH_OK();
     return OVQA_OK;
 }

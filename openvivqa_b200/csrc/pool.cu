@@ -52,9 +52,15 @@ __global__ void __launch_bounds__(kPoolThreads) attr_pool_fwd_kernel(const TH* _
     __syncthreads();
     const float* xb = x + b * (int64_t)N * D;
     for (int c = threadIdx.x; c < D; c += kPoolThreads) {          // consecutive threads -> consecutive columns: every row read is coalesced
-        float a = 0.f;
-        for (int n = 0; n < N; ++n) a = fmaf(sp[n], __ldg(xb + (int64_t)n * D + c), a);
-        pooled[b * D + c] = a;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;           // four rows in flight per thread: the loop is latency-bound otherwise
+        int n = 0;
+        for (; n + 4 <= N; n += 4) {
+            const float x0 = __ldg(xb + (int64_t)n * D + c), x1 = __ldg(xb + (int64_t)(n + 1) * D + c), x2 = __ldg(xb + (int64_t)(n + 2) * D + c),
+                        x3 = __ldg(xb + (int64_t)(n + 3) * D + c);
+            a0 = fmaf(sp[n], x0, a0); a1 = fmaf(sp[n + 1], x1, a1); a2 = fmaf(sp[n + 2], x2, a2); a3 = fmaf(sp[n + 3], x3, a3);
+        }
+        for (; n < N; ++n) a0 = fmaf(sp[n], __ldg(xb + (int64_t)n * D + c), a0);
+        pooled[b * D + c] = (a0 + a1) + (a2 + a3);
     }
 }
 
@@ -96,6 +102,7 @@ __global__ void __launch_bounds__(kPoolThreads) attr_pool_bwd_kernel(const float
         float* dxb = dx + b * (int64_t)N * D;
         for (int c = threadIdx.x; c < D; c += kPoolThreads) {
             const float g = __ldg(dpb + c);
+#pragma unroll 8
             for (int n = 0; n < N; ++n) dxb[(int64_t)n * D + c] = __ldg(pb + n) * g;
         }
     }
@@ -105,6 +112,7 @@ __global__ void __launch_bounds__(kPoolThreads) attr_pool_bwd_kernel(const float
     for (int c = threadIdx.x; c < Dh; c += kPoolThreads) {
         const float w = __ldg(w2 + c) * inv_keep;
         float acc = 0.f;
+#pragma unroll 8
         for (int n = 0; n < N; ++n) {
             const float hv = to_f32<TH>(hb[(int64_t)n * Dh + c]), dl = sd[n];
             acc = fmaf(dl, hv, acc);
