@@ -263,7 +263,10 @@ struct Tc5WideArgs {
     SdpaArgs a;
     int nk16, q_rows, n_mt;      // keys rounded to 16; rows of the Q box; row tiles per (sample, head)
 };
-constexpr int kWideThreads = 64 + 2 * 128;
+// Softmax groups have TWO threads per query row (8 warps per group: warps h*4 .. h*4+3 own the 16-key chunks c with c % 2 == h).  With one
+// thread per row the element-wise chain of an item (~3 900 instructions for 192 keys) ran at an IPC of 0.16 per warp with two warps per
+// scheduler: 92 us per launch of the M4C shape against a 22 us HBM bound (profiles/r02_kernels_ncu.md).
+constexpr int kWideThreads = 64 + 2 * 256;
 
 template <int TW>
 __global__ void __launch_bounds__(kWideThreads, 1)
@@ -282,7 +285,8 @@ sdpa_fwd_tc5w_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_co
                    v0_off = k1_off + (uint32_t)nk16 * kRowB, v1_off = v0_off + (uint32_t)nk16 * 128u, stage_bytes = v1_off + (uint32_t)nk16 * kRowB;
     uint8_t* s_load = smem;
     float* s_mask = reinterpret_cast<float*>(smem + 2 * stage_bytes);     // [2 groups][256]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_mask + 2 * 256);
+    float* s_red = s_mask + 2 * 256;                                      // [2 groups][max | sum][2 halves][128 rows]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_red + 2 * 2 * 2 * 128);
     uint64_t* load_full = bars;          // [2]
     uint64_t* load_empty = bars + 2;     // [2]
     uint64_t* s_full = bars + 4;         // [2]
@@ -294,8 +298,8 @@ sdpa_fwd_tc5w_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_co
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(load_full + i, 1); mbar_init(load_empty + i, 1); mbar_init(s_full + i, 1); mbar_init(p_full + i, 128);
-            mbar_init(o_full + i, 1); mbar_init(acc_empty + i, 128);
+            mbar_init(load_full + i, 1); mbar_init(load_empty + i, 1); mbar_init(s_full + i, 1); mbar_init(p_full + i, 256);
+            mbar_init(o_full + i, 1); mbar_init(acc_empty + i, 256);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -373,8 +377,10 @@ sdpa_fwd_tc5w_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_co
             }
         }
     } else {
-        const int g = (warp - 2) / 4, quad = warp % 4, row = quad * 32 + lane, tid_g = (warp - 2) % 4 * 32 + lane;
+        const int g = (warp - 2) / 8, half = ((warp - 2) / 4) % 2, quad = warp % 4, row = quad * 32 + lane, tid_g = (warp - 2) % 8 * 32 + lane;
         float* mrow = s_mask + g * 256;
+        float* red_max = s_red + g * 512;             // [2 halves][128]
+        float* red_sum = red_max + 256;               // [2 halves][128]
         const uint32_t mrow_u32 = smem_u32(mrow);
         const uint32_t p_row = smem_u32(s_load + g * stage_bytes) + (uint32_t)row * 128u, p_x = (uint32_t)(row & 7);   // stage g == group g
         const uint32_t t_s = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * 256);
@@ -388,17 +394,15 @@ sdpa_fwd_tc5w_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_co
             return a.mask.ptr ? __ldg(a.mask.ptr + (int64_t)(bh / H) * a.mask.sb + (int64_t)(bh % H) * a.mask.sh + key) : 0.0f;
         };
         const int first = blockIdx.x + g * gridDim.x;
-        float mv0 = mask_of(first, tid_g), mv1 = mask_of(first, tid_g + 128);
+        float mv = mask_of(first, tid_g);
         int u = 0;
         for (int item = first; item < n_items; item += 2 * gridDim.x, ++u) {
             const int mt = item % n_mt, bh = item / n_mt, b = bh / H, hd = bh % H;
             const uint32_t par = (uint32_t)u & 1u;
-            named_bar_sync(1 + g, 128);
-            mrow[tid_g] = mv0 * kLog2e;
-            mrow[tid_g + 128] = mv1 * kLog2e;
-            mv0 = mask_of(item + 2 * gridDim.x, tid_g);
-            mv1 = mask_of(item + 2 * gridDim.x, tid_g + 128);
-            named_bar_sync(1 + g, 128);
+            named_bar_sync(1 + g, 256);               // the previous item's readers of the mask row / reduction scratch are done
+            mrow[tid_g] = mv * kLog2e;
+            mv = mask_of(item + 2 * gridDim.x, tid_g);
+            named_bar_sync(1 + g, 256);
             mbar_wait(s_full + g, par);
             tcgen05_fence_after();
             // prefix-LM tail: keys beyond `kmax` are in this query's causal future (kmax = INT_MAX for rows outside the tail)
@@ -419,31 +423,38 @@ sdpa_fwd_tc5w_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_co
                     for (int j = 0; j < 16; ++j) v[j] += (16 * ch + j > kmax) ? cval2 : 0.0f;
                 }
             };
+            // this thread's chunks: half, half + 2, ...  (nmine of them; chunk index of the i-th: 2 i + half)
+            const int nmine = (nch - half + 1) / 2;
             uint32_t ra[16], rb[16];
             float mx = -INFINITY;
-            tmem_ld_32x32b_x16(t_s, ra);
+            if (nmine > 0) tmem_ld_32x32b_x16(t_s + (uint32_t)(16 * half), ra);
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                if (c < nch) {
+            for (int i = 0; i < 8; ++i) {
+                if (i < nmine) {
+                    const int c = 2 * i + half;
                     tmem_ld_wait();
-                    if (c + 1 < nch) tmem_ld_32x32b_x16(t_s + (uint32_t)(16 * (c + 1)), (c & 1) ? ra : rb);
+                    if (i + 1 < nmine) tmem_ld_32x32b_x16(t_s + (uint32_t)(16 * (c + 2)), (i & 1) ? ra : rb);
                     float v[16];
-                    scaled((c & 1) ? rb : ra, c, v);
+                    scaled((i & 1) ? rb : ra, c, v);
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) mx = fmaxf(fmaxf(mx, fmaxf(v[j], v[j + 1])), fmaxf(v[j + 2], v[j + 3]));
                 }
             }
+            red_max[half * 128 + row] = mx;
+            named_bar_sync(1 + g, 256);
+            mx = fmaxf(mx, red_max[(half ^ 1) * 128 + row]);
             float l = 0.f;
             const int qi = mt * 128 + row;
             const bool live = qi < Lq;
-            tmem_ld_32x32b_x16(t_s, ra);
+            if (nmine > 0) tmem_ld_32x32b_x16(t_s + (uint32_t)(16 * half), ra);
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                if (c < nch) {
+            for (int i = 0; i < 8; ++i) {
+                if (i < nmine) {
+                    const int c = 2 * i + half;
                     tmem_ld_wait();
-                    if (c + 1 < nch) tmem_ld_32x32b_x16(t_s + (uint32_t)(16 * (c + 1)), (c & 1) ? ra : rb);
+                    if (i + 1 < nmine) tmem_ld_32x32b_x16(t_s + (uint32_t)(16 * (c + 2)), (i & 1) ? ra : rb);
                     float v[16];
-                    scaled((c & 1) ? rb : ra, c, v);
+                    scaled((i & 1) ? rb : ra, c, v);
                     uint32_t pk[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -456,34 +467,39 @@ sdpa_fwd_tc5w_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_co
                     sts128u(blk + ((((uint32_t)(2 * c + 1) & 7u) ^ p_x) << 4), pk[4], pk[5], pk[6], pk[7]);
                 }
             }
+            red_sum[half * 128 + row] = l;            // (visible to the partner after the p_full -> o_full barrier chain: release / acquire)
             fence_proxy_async_smem();
             mbar_arrive(p_full + g);
             mbar_wait(o_full + g, par);
             tcgen05_fence_after();
+            l += red_sum[(half ^ 1) * 128 + row];
             const float inv = 1.0f / l;
             __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.out) + ((int64_t)b * Lq + qi) * a.ldo + (int64_t)hd * D;
+            // O drain: 16-column chunks, alternating between the two threads of a row
+            constexpr int kOch = D / 16;
 #pragma unroll
-            for (int c32 = 0; c32 < D / 32; ++c32) {
-                uint32_t o[32];
-                tmem_ld_32x32b_x32(t_s + (uint32_t)(32 * c32), o);
+            for (int c16 = 0; c16 < kOch; ++c16) {
+                if ((c16 & 1) != half) continue;
+                uint32_t o[16];
+                tmem_ld_32x32b_x16(t_s + (uint32_t)(16 * c16), o);
                 tmem_ld_wait();
-                if (c32 == D / 32 - 1) {
+                if (c16 + 2 >= kOch) {               // this thread's last read of the accumulator
                     tcgen05_fence_before();
                     mbar_arrive(acc_empty + g);
                 }
                 if (live) {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
+                    for (int c = 0; c < 2; ++c) {
                         uint4 w;
                         w.x = pack_bf16x2(__uint_as_float(o[8 * c]) * inv, __uint_as_float(o[8 * c + 1]) * inv);
                         w.y = pack_bf16x2(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv);
                         w.z = pack_bf16x2(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv);
                         w.w = pack_bf16x2(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv);
-                        *reinterpret_cast<uint4*>(op + 32 * c32 + 8 * c) = w;
+                        *reinterpret_cast<uint4*>(op + 16 * c16 + 8 * c) = w;
                     }
                 }
             }
-            if (live && a.lse) a.lse[((int64_t)b * H + hd) * Lq + qi] = fmaf(mx, kLn2, __logf(l));
+            if (live && half == 0 && a.lse) a.lse[((int64_t)b * H + hd) * Lq + qi] = fmaf(mx, kLn2, __logf(l));
         }
     }
     tcgen05_fence_before();
@@ -804,7 +820,7 @@ int sdpa_fwd_tc5_bf16(const SdpaArgs& a, cudaStream_t st) {
 
 // wide heads (d = 96 / 128) and rows longer than one tile: sdpa_fwd_tc5w_kernel
 static size_t tc5w_stage_bytes(int tw, int nk16) { const int rowb = tw == 64 ? 128 : 64; return (size_t)(128 + 2 * nk16) * (128 + rowb); }
-static size_t tc5w_smem_bytes(int tw, int nk16) { return 2 * tc5w_stage_bytes(tw, nk16) + 2 * 256 * 4 + 256 + 1024; }
+static size_t tc5w_smem_bytes(int tw, int nk16) { return 2 * tc5w_stage_bytes(tw, nk16) + 2 * 256 * 4 /*mask rows*/ + 2 * 512 * 4 /*max / sum exchange*/ + 256 + 1024; }
 
 bool sdpa_fwd_tc5w_supported(const SdpaArgs& a) {
     const int mode = tc5_mode("OVQA_SDPA_TC5");
