@@ -28,29 +28,37 @@ using namespace tc5;
 constexpr int BM = 128;          // UMMA M (cta_group::1)
 constexpr int BK = 64;           // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-// Epilogue warps per CTA (template parameter EPW): 16 warps leave <= 96 registers per thread (18 warps over 4 sub-partitions put 5 on
-// one: 16384 / (5 * 32)), 8 warps leave 168 (10 warps: 3 per sub-partition).  Measured on the MCAN step (profiles/README, run L): the
-// fp32-result epilogues (residual, dropout, split-K atomics) and the plain ones run faster with 8 warps and two passes' worth of
-// independent instruction streams each; the bf16 epilogues that multiply by a saved operand or evaluate GELU want the 16 warps.
-constexpr int epw_for(int mode, int feat) {
-    return (mode == 1 /*EPI_FULL*/ && (feat < 0 || (feat & 8 /*F_MULAUX*/) || ((feat & 2 /*F_GELU*/) && !(feat & 4 /*F_SAVE_D*/)))) ? 16 : 8;
-}
+// Epilogue warps per CTA (template parameter EPW).  The specialised epilogues run on 8 warps (<= 168 registers per thread: 10 warps, 3 per
+// sub-partition) and are fed by the TMA unit (below); the run-time-feature epilogue keeps 16 warps (<= 96 registers) to hide the latency of
+// its per-element global accesses.
+constexpr int epw_for(int mode, int feat) { return (mode == 1 /*EPI_FULL*/ && feat < 0) ? 16 : 8; }
 constexpr int kAccStages = 2;
+#ifndef OVQA_EPI_BUFS
+#define OVQA_EPI_BUFS 3
+#endif
 
 // CTAS = 1: one CTA per 128 x BN tile.  CTAS = 2: a CTA pair (cluster of 2, cta_group::2) per 256 x BN tile — each CTA stages its
 // own 128 rows of A and HALF of B (the MMA reads the other half from the peer's shared memory): 32 KB instead of 48 KB of L2 -> smem
-// traffic per SM and k-block at BN = 256, and room for 5 pipeline stages instead of 3 (profiles/r01d: the single-CTA 128 x 256 tile
-// is bound by the L2 -> SM path, not by the tensor pipe).
+// traffic per SM and k-block at BN = 256 (profiles/r01d: the single-CTA 128 x 256 tile is bound by the L2 -> SM path, not by the tensor pipe).
+//
+// TMA-fed epilogue (8-warp kernels): every epilogue warp owns kEpiBufs staging buffers of 4 KB, one per 32 x 32 chunk in flight.  The
+// chunk's input operand (residual rows, fp32; saved derivative, bf16) is brought in by cp.async.bulk.tensor two chunks ahead, the lane
+// that holds accumulator row r (tcgen05.ld 32x32b: row per lane) finishes its 32 columns in registers, overwrites ITS OWN row of the
+// buffer with the result (128B / 64B swizzle: conflict-free), and one lane hands the buffer to the TMA unit (tensor store, or fp32
+// add-reduction for split-K).  No per-element global access, no transposition pass, ragged edges clipped by the tensor map.
 template <int BN, int CTAS, int EPW> struct Cfg {
-    static constexpr int kScratchBytes = EPW * 32 * 32 * 4;   // one 32x32 fp32 chunk per epilogue warp
-    // pipeline depth: what fits beside the scratch (8 epilogue warps free 32 KB: one more stage)
-    static constexpr int kStages = (CTAS == 2 ? 5 : (BN == 256 ? 3 : 5)) + (EPW == 8 ? 1 : 0);
+    static constexpr int kEpiBufs = EPW == 16 ? 1 : ((CTAS == 1 && BN == 256) ? 2 : OVQA_EPI_BUFS);
+    static constexpr int kScratchBytes = EPW * kEpiBufs * 4096;   // 32x32 fp32 chunks
+    static constexpr int kBarBytes = 512;
     static constexpr int kABytes = BM * BK * 2;
     static constexpr int kBBytes = (BN / CTAS) * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kFit = (227 * 1024 - 1024 /*align slack*/ - kBarBytes - kScratchBytes) / kStageBytes;
+    static constexpr int kStages = kFit > 6 ? 6 : kFit;
     static constexpr int kTmemCols = kAccStages * BN;  // 256 or 512: power of two
-    static constexpr int kSmemBytes = kStages * kStageBytes + kScratchBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-    static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+    static constexpr int kSmemBytes = kStages * kStageBytes + kScratchBytes + 1024 + kBarBytes;
+    static_assert(kStages >= 3 && kSmemBytes <= 227 * 1024, "shared memory budget");
+    static_assert((2 * kStages + 2 * kAccStages + EPW * kEpiBufs) * 8 + 8 <= kBarBytes, "barrier region");
 };
 
 // ----------------------------------------------------------------------------- epilogue pieces
@@ -140,8 +148,9 @@ __device__ __noinline__ void epilogue_scalar(const Epilogue& epi, float acc, int
 // ----------------------------------------------------------------------------- kernel
 template <int BN, bool A_MN, bool B_MN, typename TC, int MODE, int FEAT, int CTAS, int EPW>
 __global__ void __launch_bounds__(EPW == 16 ? 640 : 384, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, TC* __restrict__ C,
-                    int64_t m, int64_t n, int64_t k, int64_t ldc, Epilogue epi, int split_k) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_c,
+                    const __grid_constant__ CUtensorMap tma_x, TC* __restrict__ C, int64_t m, int64_t n, int64_t k, int64_t ldc, Epilogue epi,
+                    int split_k, int use_tma) {
     using cfg = Cfg<BN, CTAS, EPW>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -153,7 +162,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     uint64_t* empty_bar = bars + cfg::kStages;              // [kStages]   MMA -> TMA
     uint64_t* tmem_full = bars + 2 * cfg::kStages;          // [2]         MMA -> epilogue
     uint64_t* tmem_empty = tmem_full + kAccStages;          // [2]         epilogue -> MMA
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + kAccStages);
+    uint64_t* epi_bar = tmem_empty + kAccStages;            // [EPW * kEpiBufs]  TMA -> epilogue warp (input operand of a chunk)
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(epi_bar + EPW * cfg::kEpiBufs);
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     constexpr int TM = BM * CTAS;                            // rows of a work tile (a CTA pair shares one 256-row tile)
@@ -166,9 +176,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
+        if (use_tma) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_c)) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_x)) : "memory");
+        }
         // full: the leader's own arrive.expect_tx (+ the peer's remote arrive); tmem_empty: the epilogue warps of every CTA of the pair
         for (int i = 0; i < cfg::kStages; ++i) { mbar_init(full_bar + i, CTAS); mbar_init(empty_bar + i, 1); }
         for (int i = 0; i < kAccStages; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, EPW * CTAS); }
+        for (int i = 0; i < EPW * cfg::kEpiBufs; ++i) mbar_init(epi_bar + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -276,7 +291,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         constexpr bool kSplit = sizeof(TC) == 4;
         constexpr int HI = kSplit ? 16 : 4;               // column distance between a lane's two groups of four
         // scratch: 32 rows x 8 granules of 16 B per warp, granule index XOR (row & 7)  (conflict-free both ways)
-        const uint32_t sc = smem_u32(scratch) + (uint32_t)(warp - 2) * 4096u;
+        const uint32_t sc = smem_u32(scratch) + (uint32_t)(warp - 2) * (uint32_t)(cfg::kEpiBufs * 4096);
         const uint32_t st_row = sc + (uint32_t)lane * 128u, st_x = (uint32_t)(lane & 7);
         const uint32_t g_lo = kSplit ? (uint32_t)c8 : (uint32_t)(2 * c8), g_hi = kSplit ? (uint32_t)(4 + c8) : (uint32_t)(2 * c8 + 1);   // 16-byte granules of the row
         const uint32_t ld_lo = sc + (uint32_t)rr * 128u + ((g_lo ^ (uint32_t)rr) << 4), ld_hi = sc + (uint32_t)rr * 128u + ((g_hi ^ (uint32_t)rr) << 4);
@@ -308,6 +323,194 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         const int64_t ld_res = epi.ld_res, ld_aux = epi.ld_aux, ldc2 = epi.ldc2;
         int acc = 0;
         uint32_t acc_phase = 0;
+        // ------------------------------------------------------------------ TMA-fed epilogue (see Cfg)
+        constexpr int kFe = (MODE == EPI_FULL && FEAT >= 0) ? FEAT : 0;
+        constexpr bool kTmaCapable = EPW == 8 && (MODE != EPI_FULL || (FEAT >= 0 && !((FEAT & F_SAVE_D) && sizeof(TC) == 4)));
+        bool tma_done = false;
+        if constexpr (kTmaCapable) {
+          if (use_tma) {                                                 // warp-uniform (kernel argument)
+            tma_done = true;
+            constexpr bool kGelu = kFe & F_GELU, kSave = kFe & F_SAVE_D, kMul = kFe & F_MULAUX, kDrop = kFe & F_DROP, kRes = kFe & F_RES,
+                           kColsum = kFe & F_COLSUM;
+            constexpr bool kLoad = kRes || kMul;
+            constexpr uint32_t kBoxBytes = 32u * 32u * (uint32_t)sizeof(TC);
+            constexpr int NB = cfg::kEpiBufs;
+            constexpr int kChunkStep = (EPW / 4) * 32;
+            const int ew = warp - 2;
+            const uint32_t bufs = smem_u32(scratch) + (uint32_t)ew * (uint32_t)(NB * 4096);
+            uint64_t* in_bar = epi_bar + ew * NB;
+            const bool bias_vec = al16(bias);
+            const float k_out = kDrop ? inv_keep : 1.0f;                  // dropout keep-scale, folded into the constants below
+            const float a_s = (kGelu ? 1.0f : k_out) * alpha;
+            const float b_s = (kDrop && !kGelu) ? k_out : 1.0f;
+            const GeluK gk(k_out);
+            // this lane's row of a staged chunk: 128-byte rows under SWIZZLE_128B (fp32), 64-byte rows under SWIZZLE_64B (bf16)
+            const uint32_t row_off = kSplit ? (uint32_t)lane * 128u : (uint32_t)lane * 64u;
+            const uint32_t sx = kSplit ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
+            // the chunk sequence of this warp, walked a second time ahead of the math by the loads of the input operand (lane 0)
+            int ld_tile = tile0, ld_c0 = slot * 32;
+            uint32_t ld_cnt = 0, cnt = 0;
+            auto ld_issue = [&]() {
+                while (ld_tile < num_tiles) {
+                    int mt2, nt2, ka, kb_;
+                    decode(ld_tile, mt2, nt2, ka, kb_);
+                    const int64_t c = (int64_t)nt2 * BN + ld_c0;
+                    if (ld_c0 < BN && c < n) {
+                        const uint32_t b = ld_cnt % NB;
+                        mbar_expect_tx(in_bar + b, kBoxBytes);
+                        tma_load_2d_u32(bufs + b * 4096u, &tma_x, in_bar + b, (int)c, mt2 * TM + (int)cta_rank * BM + quad * 32);
+                        ld_c0 += kChunkStep;
+                        ++ld_cnt;
+                        return;
+                    }
+                    ld_tile += tile_step;
+                    ld_c0 = slot * 32;
+                }
+            };
+            if constexpr (kLoad) {
+                if (lane == 0) for (int q = 0; q < NB - 1; ++q) ld_issue();
+            }
+            for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+                int mt, nt, kb0, kb1;
+                decode(tile, mt, nt, kb0, kb1);
+                mbar_wait(tmem_full + acc, acc_phase);
+                tcgen05_fence_after();
+                const int row0 = mt * TM + (int)cta_rank * BM + quad * 32;
+                const int64_t row = (int64_t)row0 + lane;
+                const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+                for (int c0 = slot * 32; c0 < BN; c0 += kChunkStep) {
+                    const int64_t col0 = (int64_t)nt * BN + c0;
+                    if (col0 >= n) break;                                     // warp-uniform
+                    const bool full_cols = col0 + 32 <= n;
+                    const uint32_t b = cnt % NB, buf = bufs + b * 4096u;
+                    const uint32_t my = buf + row_off;
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(t_row + (uint32_t)c0, r);
+                    if constexpr (kLoad) {
+                        mbar_wait(in_bar + b, (cnt / NB) & 1u);              // the operand rows have landed in `buf`
+                    } else {
+                        if (lane == 0) bulk_wait_read<NB - 1>();             // the store that last read `buf` is done with it
+                        __syncwarp();
+                    }
+                    tmem_ld_wait();
+                    float v[32];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        float b4[4] = {0.f, 0.f, 0.f, 0.f};
+                        if (bias) {
+                            if (full_cols && bias_vec) {
+                                const float4 t = __ldg(reinterpret_cast<const float4*>(bias + col0 + 4 * q));
+                                b4[0] = t.x; b4[1] = t.y; b4[2] = t.z; b4[3] = t.w;
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) b4[j] = __ldg(bias + min(col0 + 4 * q + j, n - 1));
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) v[4 * q + j] = fmaf(__uint_as_float(r[4 * q + j]), a_s, b4[j] * b_s);
+                    }
+                    float g[kSave ? 32 : 1];
+                    if constexpr (kGelu) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if constexpr (kSave) v[j] = gelu_and_grad_tanhfit(v[j], gk, g[j]);
+                            else v[j] = gelu_tanhfit(v[j], gk);
+                        }
+                    }
+                    if constexpr (kMul) {                                     // bf16: granule q = columns [8q, 8q + 8)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint32_t w0, w1, w2, w3;
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(my + (((uint32_t)q ^ sx) << 4)) : "memory");
+                            const uint32_t w[4] = {w0, w1, w2, w3};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float2 a = unpack_bf16x2(w[j]);
+                                v[8 * q + 2 * j] *= a.x; v[8 * q + 2 * j + 1] *= a.y;
+                            }
+                        }
+                    }
+                    if constexpr (kDrop) {
+                        // Philox group = 8 consecutive elements of a row (n % 8 == 0, col0 % 32 == 0): four calls per lane and chunk
+                        const uint64_t ctr = rng_offset + (uint64_t)((row * n + col0) >> 3);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint4 rr = philox4x32(ctr + (uint64_t)q, seed);
+                            bool keep[8];
+                            dropout_keep8(keep, rr, thr_hi);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                v[8 * q + j] = keep[j] ? v[8 * q + j] : 0.0f;
+                                if constexpr (kSave) g[8 * q + j] = keep[j] ? g[8 * q + j] : 0.0f;
+                            }
+                        }
+                    }
+                    if constexpr (kSplit) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const uint32_t ga = my + (((uint32_t)q ^ sx) << 4);
+                            if constexpr (kRes) {
+                                float x0, x1, x2, x3;
+                                lds128(ga, x0, x1, x2, x3);
+                                v[4 * q] += x0; v[4 * q + 1] += x1; v[4 * q + 2] += x2; v[4 * q + 3] += x3;
+                            }
+                            sts128(ga, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint32_t ga = my + (((uint32_t)q ^ sx) << 4);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ga), "r"(pack_bf16x2(v[8 * q], v[8 * q + 1])), "r"(pack_bf16x2(v[8 * q + 2], v[8 * q + 3])),
+                                         "r"(pack_bf16x2(v[8 * q + 4], v[8 * q + 5])), "r"(pack_bf16x2(v[8 * q + 6], v[8 * q + 7])) : "memory");
+                            if constexpr (kSave)
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ga + 2048u), "r"(pack_bf16x2(g[8 * q], g[8 * q + 1])), "r"(pack_bf16x2(g[8 * q + 2], g[8 * q + 3])),
+                                             "r"(pack_bf16x2(g[8 * q + 4], g[8 * q + 5])), "r"(pack_bf16x2(g[8 * q + 6], g[8 * q + 7])) : "memory");
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if constexpr (MODE == EPI_SPLITK) tma_reduce_add_2d_u32(&tma_c, buf, (int)col0, row0);
+                        else tma_store_2d_u32(&tma_c, buf, (int)col0, row0);
+                        if constexpr (kSave) tma_store_2d_u32(&tma_x, buf + 2048u, (int)col0, row0);
+                        bulk_commit();
+                        if constexpr (kLoad) {
+                            bulk_wait_read<1>();                              // store(cnt - 1) has read its buffer: the next load may land there
+                            ld_issue();
+                        }
+                    }
+                    if constexpr (kColsum) {
+                        // column sums over the chunk's 32 rows (rows beyond m excluded): transposing butterfly, lane L ends with column L
+                        if (row >= m) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                        }
+#pragma unroll
+                        for (int w = 16; w >= 1; w >>= 1) {
+                            const bool up = lane & w;
+#pragma unroll
+                            for (int j = 0; j < w; ++j) {
+                                const float give = up ? v[j] : v[j + w], keepv = up ? v[j + w] : v[j];
+                                v[j] = keepv + __shfl_xor_sync(0xffffffffu, give, w);
+                            }
+                        }
+                        if (col0 + lane < n) atomicAdd(colsum + col0 + lane, v[0]);
+                    }
+                    ++cnt;
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CTAS == 2 && cta_rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(tmem_empty + acc), 0));
+                    else mbar_arrive(tmem_empty + acc);
+                }
+                if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+            }
+            if (lane == 0) bulk_wait_all();                               // shared memory stays valid until the last store has read it
+          }
+        }
+        if (!tma_done)
         for (int tile = tile0; tile < num_tiles; tile += tile_step) {
             int mt, nt, kb0, kb1;
             decode(tile, mt, nt, kb0, kb1);
@@ -610,28 +813,29 @@ EncodeFn get_encode() {
 }
 
 struct MapKey {
-    const void* ptr; uint64_t inner, outer, ld; uint32_t box_inner, box_outer; int swz;
+    const void* ptr; uint64_t inner, outer, ld; uint32_t box_inner, box_outer; int swz, elt;
     bool operator==(const MapKey& o) const {
-        return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner && box_outer == o.box_outer && swz == o.swz;
+        return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner && box_outer == o.box_outer && swz == o.swz &&
+               elt == o.elt;
     }
 };
 struct MapKeyHash {
     size_t operator()(const MapKey& k) const {
         size_t h = std::hash<const void*>()(k.ptr);
         auto mix = [&](uint64_t v) { h ^= std::hash<uint64_t>()(v) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
-        mix(k.inner); mix(k.outer); mix(k.ld); mix(((uint64_t)k.box_inner << 32) | k.box_outer); mix((uint64_t)k.swz);
+        mix(k.inner); mix(k.outer); mix(k.ld); mix(((uint64_t)k.box_inner << 32) | k.box_outer); mix(((uint64_t)k.elt << 32) | (uint64_t)k.swz);
         return h;
     }
 };
 
 }  // namespace
 
-// 2-D bf16 tensor [outer, inner] with row stride ld (elements); box [box_outer, box_inner]; SWIZZLE_128B; OOB -> 0.
-int tc5::make_tma_map_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer,
-                           int swizzle_bytes) {
+// 2-D tensor [outer, inner] of bf16 (elt_bytes 2) or fp32 (4) with row stride ld (elements); box [box_outer, box_inner]; 128B / 64B swizzle; OOB -> 0.
+int tc5::make_tma_map(CUtensorMap* out, const void* ptr, int elt_bytes, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer,
+                      int swizzle_bytes) {
     static std::mutex mu;
     static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-    const MapKey key{ptr, inner, outer, ld, box_inner, box_outer, swizzle_bytes};
+    const MapKey key{ptr, inner, outer, ld, box_inner, box_outer, swizzle_bytes, elt_bytes};
     {
         std::lock_guard<std::mutex> g(mu);
         auto it = cache.find(key);
@@ -640,10 +844,10 @@ int tc5::make_tma_map_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, ui
     EncodeFn enc = get_encode();
     if (!enc) return OVQA_ERR_NO_DEVICE;
     const cuuint64_t dims[2] = {inner, outer};
-    const cuuint64_t strides[1] = {ld * 2};
+    const cuuint64_t strides[1] = {ld * (uint64_t)elt_bytes};
     const cuuint32_t box[2] = {box_inner, box_outer};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+    const CUresult r = enc(out, elt_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -652,6 +856,10 @@ int tc5::make_tma_map_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, ui
     if (cache.size() > 4096) cache.clear();
     cache.emplace(key, *out);
     return OVQA_OK;
+}
+int tc5::make_tma_map_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer,
+                           int swizzle_bytes) {
+    return make_tma_map(out, ptr, 2, inner, outer, ld, box_inner, box_outer, swizzle_bytes);
 }
 
 namespace {
@@ -672,6 +880,26 @@ int launch(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, int64_t m, i
     if (rc) return rc;
     const int num_k_blocks = (int)((k + BK - 1) / BK);
     if (split_k > num_k_blocks) split_k = num_k_blocks;
+    // epilogue through the TMA unit: 32 x 32 boxes of C and of the specialised epilogue's one extra tensor (residual in, saved derivative in / out)
+    CUtensorMap mc{}, mx{};
+    int use_tma = 0;
+    {
+        static const bool enabled = [] { const char* e = getenv("OVQA_GEMM_TMA_EPILOGUE"); return !(e && e[0] == '0'); }();
+        auto tma_ok = [](const void* p, int64_t ld, int eb) { return p && (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld * eb) % 16 == 0; };
+        const int eb = epi.c_dtype == OVQA_F32 ? 4 : 2;
+        const void* x = nullptr;
+        int64_t ldx = 0;
+        int ebx = eb;
+        if (epi.residual) { x = epi.residual; ldx = epi.ld_res; ebx = 4; }
+        else if (epi.aux_in) { x = epi.aux_in; ldx = epi.ld_aux; }
+        else if (epi.aux_out) { x = epi.aux_out; ldx = epi.ld_aux; }
+        if (enabled && m < (int64_t)1 << 30 && n < (int64_t)1 << 30 && tma_ok(C, ldc, eb) && (!x || tma_ok(x, ldx, ebx)) && (epi.dropout_p <= 0.f || n % 8 == 0) &&
+            (!epi.colsum || (reinterpret_cast<uintptr_t>(epi.colsum) & 3) == 0)) {
+            rc = tc5::make_tma_map(&mc, C, eb, (uint64_t)n, (uint64_t)m, (uint64_t)ldc, 32, 32, eb == 4 ? 128 : 64);
+            if (!rc && x) rc = tc5::make_tma_map(&mx, x, ebx, (uint64_t)n, (uint64_t)m, (uint64_t)ldx, 32, 32, ebx == 4 ? 128 : 64);
+            use_tma = rc == OVQA_OK;
+        }
+    }
     const int64_t tiles = ((m + BM * CTAS - 1) / (BM * CTAS)) * ((n + BN - 1) / BN) * split_k;
     const int64_t units = sm_count() / CTAS;
     const int grid = (int)(tiles < units ? tiles : units) * CTAS;
@@ -692,7 +920,7 @@ int launch(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, int64_t m, i
         static OncePerDevice attr_set;                                                                                          \
         if (attr_set.pending()) { OVQA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::kSmemBytes)); attr_set.mark(); } \
         if constexpr (CTAS == 1) {                                                                                             \
-            kern<<<grid, kThreads, cfg::kSmemBytes, st>>>(ma, mb, (TC_*)C, m, n, k, ldc, epi, split_k);                        \
+            kern<<<grid, kThreads, cfg::kSmemBytes, st>>>(ma, mb, mc, mx, (TC_*)C, m, n, k, ldc, epi, split_k, use_tma);                        \
         } else {                                                                                                               \
             cudaLaunchConfig_t lc{};                                                                                           \
             lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(kThreads); lc.dynamicSmemBytes = cfg::kSmemBytes; lc.stream = st; \
@@ -711,7 +939,7 @@ int launch(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, int64_t m, i
             }                                                                                                                  \
             const int clusters = grid / CTAS < max_clusters ? grid / CTAS : max_clusters;                                      \
             lc.gridDim = dim3((unsigned)(clusters * CTAS));                                                                    \
-            OVQA_CUDA_OK(cudaLaunchKernelEx(&lc, kern, ma, mb, (TC_*)C, m, n, k, ldc, epi, split_k));                          \
+            OVQA_CUDA_OK(cudaLaunchKernelEx(&lc, kern, ma, mb, mc, mx, (TC_*)C, m, n, k, ldc, epi, split_k, use_tma));                          \
         }                                                                                                                      \
     } while (0)
     // the specialised sets exist for the operand forms that launch them: forward y = x W^T is (N,N), dgrad dx = dy W is (N,T)

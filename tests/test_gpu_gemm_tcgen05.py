@@ -129,7 +129,7 @@ def test_fast_gelu_matches_erf_gelu(dev):
     assert (out - want).abs().max().item() <= 1e-6
 
 
-@pytest.mark.parametrize("m,n,k", [(300, 512, 192), (1000, 2048, 512), (257, 768, 2048)])
+@pytest.mark.parametrize("m,n,k", [(300, 512, 192), (1000, 2048, 512), (257, 768, 2048), (300, 520, 192), (77, 72, 64), (5000, 1000, 512)])
 def test_specialised_epilogues(dev, m, n, k):
     """The compile-time feature sets of gemm_tcgen05.cu (fc1 train / eval, dpre, fc_o / fc2 train / eval, dx + residual)
     against torch: erf GELU (the tanh-fit epilogue must stay within bf16 rounding of it), the same Philox keep mask as every
@@ -187,6 +187,13 @@ def test_specialised_epilogues(dev, m, n, k):
     # dx = dy W + the other branch's gradient  (N,T form, fp32 out)
     s = ops.gemm(a, bt, b_op="T", residual=res, out_dtype=torch.float32)
     assert (s - (ref + res)).abs().max() <= 1e-3 * (ref + res).abs().max()
+    # ... accumulated in place (result written over the residual it read), and the saved derivative multiplied in place
+    acc = res.clone()
+    ops.gemm(a, bt, b_op="T", residual=acc, out=acc)
+    assert torch.equal(acc, s)
+    dd = dsave.clone()
+    ops.gemm(a, bt, b_op="T", mul_aux=dd, out=dd)
+    assert torch.equal(dd, d)
 
 
 def test_tanhfit_gelu_matches_erf_gelu(dev):

@@ -82,6 +82,53 @@ def bench_gemm():
              cublas_tflops=fl / t_ref / 1e6, frac_of_peak=fl / t_ours / 1e6 / PEAKS["bf16_tflops"])
 
 
+def bench_gemm_epi():
+    """The fused-epilogue GEMMs of one MCAN training step (vision stream, batch 256): microseconds next to the HBM and tensor floors."""
+    B = 256
+    M = B * 100
+    for tag, m, n, k, bo, odt, feat in [
+            ("fc_o  bias+drop+res  f32 ", M, 512, 512, "N", torch.float32, "bdr"),
+            ("fc2   bias+drop+res  f32 ", M, 512, 2048, "N", torch.float32, "bdr"),
+            ("fc_o  bias+res eval  f32 ", M, 512, 512, "N", torch.float32, "br"),
+            ("fc1   bias+gelu+save+drop", M, 2048, 512, "N", torch.bfloat16, "bgsd"),
+            ("fc1   bias+gelu eval     ", M, 2048, 512, "N", torch.bfloat16, "bg"),
+            ("qkv   bias           bf16", M, 1536, 512, "N", torch.bfloat16, "b"),
+            ("dpre  mulaux         bf16", M, 2048, 512, "T", torch.bfloat16, "m"),
+            ("dpre  mulaux+colsum  bf16", M, 2048, 512, "T", torch.bfloat16, "mc"),
+            ("dctx  colsum         bf16", M, 512, 512, "T", torch.bfloat16, "c"),
+            ("dx    res            f32 ", M, 512, 512, "T", torch.float32, "r"),
+            ("dx    res k=2048     f32 ", M, 512, 2048, "T", torch.float32, "r"),
+            ("plain                bf16", M, 512, 512, "T", torch.bfloat16, ""),
+            ("plain                f32 ", M, 512, 512, "N", torch.float32, ""),
+            ("fc_o text bias+drop+res  ", B * 30, 512, 512, "N", torch.float32, "bdr")]:
+        a = torch.randn((m, k), device=dev).bfloat16()
+        b = torch.randn((n, k) if bo == "N" else (k, n), device=dev).bfloat16()
+        out = torch.empty((m, n), device=dev, dtype=odt)
+        kw = {}
+        bytes_ = m * k * 2 + n * k * 2 + m * n * out.element_size()
+        if "b" in feat:
+            kw["bias"] = torch.randn(n, device=dev)
+        if "d" in feat:
+            kw.update(dropout_p=0.1, seed=3, offset=7)
+        if "r" in feat:
+            kw["residual"] = torch.randn((m, n), device=dev)
+            bytes_ += m * n * 4
+        if "g" in feat:
+            kw["gelu"] = True
+        if "s" in feat:
+            kw.update(aux_out=torch.empty((m, n), device=dev, dtype=odt), save_dgelu=True)
+            bytes_ += m * n * out.element_size()
+        if "m" in feat:
+            kw["mul_aux"] = torch.randn((m, n), device=dev).to(odt)
+            bytes_ += m * n * out.element_size()
+        if "c" in feat:
+            kw["colsum"] = torch.zeros(n, device=dev)
+        t = timeit(lambda: ops.gemm(a, b, b_op=bo, out=out, **kw))
+        fl = 2.0 * m * n * k
+        emit(kind="gemm_epi", tag=tag, m=m, n=n, k=k, us=t, tflops=fl / t / 1e6, hbm_floor_us=bytes_ / PEAKS["hbm_gbs"] / 1e3,
+             tensor_floor_us=fl / PEAKS["bf16_tflops"] / 1e6, gbs=bytes_ / t / 1e3)
+
+
 def bench_wgrad_split():
     """Split-K sweep for the weight-gradient GEMMs (dW = dy^T x, k = B*L rows): atomics per output element grow with the
     split, SM occupancy with the number of work units."""
@@ -286,36 +333,8 @@ def bench_beam_search():
          speedup=t_off / t_on, samples_per_s=B / t_on * 1e6, select_topk_us=t_topk, select_sort_us=t_sort)
 
 
-def bench_gemm_epilogues():
-    """The fused epilogues of the training step at the vision-branch shapes (B*L = 25600)."""
-    M, D, F_ = 25600, 512, 2048
-    x16 = torch.randn((M, D), device=dev).bfloat16()
-    h16 = torch.randn((M, F_), device=dev).bfloat16()
-    w1, w2 = torch.randn((F_, D), device=dev).bfloat16(), torch.randn((D, F_), device=dev).bfloat16()
-    wqkv, wo = torch.randn((3 * D, D), device=dev).bfloat16(), torch.randn((D, D), device=dev).bfloat16()
-    b1, b2, bqkv = torch.randn(F_, device=dev), torch.randn(D, device=dev), torch.randn(3 * D, device=dev)
-    res = torch.randn((M, D), device=dev)
-    pre = torch.empty((M, F_), device=dev, dtype=torch.bfloat16)
-    o_h, o_s, o_qkv = torch.empty((M, F_), device=dev, dtype=torch.bfloat16), torch.empty((M, D), device=dev), torch.empty((M, 3 * D), device=dev, dtype=torch.bfloat16)
-    d2 = torch.randn((M, D), device=dev).bfloat16()
-    cases = [
-        ("qkv: bias -> bf16", 2.0 * M * 3 * D * D, lambda: ops.gemm(x16, wqkv, bias=bqkv, out=o_qkv)),
-        ("fc1: bias+save pre+GELU+dropout -> bf16", 2.0 * M * F_ * D, lambda: ops.gemm(x16, w1, bias=b1, out=o_h, gelu=True, aux_out=pre, dropout_p=0.1, seed=1, offset=0)),
-        ("fc1 eval: bias+GELU -> bf16", 2.0 * M * F_ * D, lambda: ops.gemm(x16, w1, bias=b1, out=o_h, gelu=True)),
-        ("fc2: bias+dropout+residual -> f32", 2.0 * M * F_ * D, lambda: ops.gemm(h16, w2, bias=b2, out=o_s, dropout_p=0.1, seed=1, offset=0, residual=res)),
-        ("fc_o: bias+dropout+residual -> f32", 2.0 * M * D * D, lambda: ops.gemm(x16, wo, bias=b2, out=o_s, dropout_p=0.1, seed=1, offset=0, residual=res)),
-        ("fc1 train: bias+GELU+save GELU'+dropout -> bf16", 2.0 * M * F_ * D, lambda: ops.gemm(x16, w1, bias=b1, out=o_h, gelu=True, aux_out=pre, save_dgelu=True, dropout_p=0.1, seed=1, offset=0)),
-        ("dpre: dgrad fc2 * GELU'(pre) * dropout -> bf16", 2.0 * M * F_ * D, lambda: ops.gemm(d2, w2, b_op="T", out=o_h, dgelu_aux=pre, dropout_p=0.1, seed=1, offset=0)),
-        ("dpre: dgrad fc2 * saved derivative -> bf16", 2.0 * M * F_ * D, lambda: ops.gemm(d2, w2, b_op="T", out=o_h, mul_aux=pre)),
-        ("dx: dgrad fc1 + residual -> f32", 2.0 * M * F_ * D, lambda: ops.gemm(h16, w1, b_op="T", out=o_s, residual=res)),
-    ]
-    for tag, fl, fn in cases:
-        t = timeit(fn)
-        emit(kind="gemm_epilogue", tag=tag, us=t, tflops=fl / t / 1e6, frac_of_peak=fl / t / 1e6 / PEAKS["bf16_tflops"])
-
-
 if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "epi", "sdpa", "ln", "mha"]
     emit(kind="meta", gpu=torch.cuda.get_device_name(0), peaks=PEAKS)
     for w in which:
-        {"gemm": bench_gemm, "wgrad": bench_wgrad_split, "epi": bench_gemm_epilogues, "sdpa": bench_sdpa, "ln": bench_ln, "mha": bench_mha, "decode": bench_decode, "beam": bench_beam_search}[w]()
+        {"gemm": bench_gemm, "wgrad": bench_wgrad_split, "epi": bench_gemm_epi, "sdpa": bench_sdpa, "ln": bench_ln, "mha": bench_mha, "decode": bench_decode, "beam": bench_beam_search}[w]()
