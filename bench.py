@@ -536,7 +536,8 @@ def run_train(ctx, wl, workload_name, metric, make_model, forward_loss, boxes=Fa
         side0 = torch.cuda.Stream()
         side0.wait_stream(torch.cuda.current_stream())
         torch.cuda.set_stream(side0)
-    net = D.data_parallel(model, device_ids=[ctx.local], bucket_cap_mb=int(os.environ.get("OVQA_DDP_BUCKET_MB", "25")), grad_dtype=os.environ.get("OVQA_DDP_GRAD_DTYPE", "bf16"))
+    net = D.data_parallel(model, device_ids=[ctx.local], bucket_cap_mb=int(os.environ.get("OVQA_DDP_BUCKET_MB", "25")), grad_dtype=os.environ.get("OVQA_DDP_GRAD_DTYPE", "bf16"),
+                          sm_reserve=int(os.environ.get("OVQA_DDP_SM_RESERVE", "0")))
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.9, 0.98), fused=True, capturable=use_graph)
     feat_dt = torch.float32 if os.environ.get("OVQA_FEATURE_FEED", "bf16") == "fp32" else torch.bfloat16
     host = synth_batches(3, wl, seed=1 + rank, boxes=boxes, feature_dtype=feat_dt)

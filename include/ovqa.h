@@ -44,7 +44,9 @@ extern "C" {
 int         ovqa_version(void);
 const char* ovqa_error_string(int code);
 int         ovqa_last_cuda_error(void);           /* cudaError_t of the last failing call (thread local) */
-int         ovqa_device_sm_count(void);
+int         ovqa_device_sm_count(void);          /* SMs the persistent kernels size their grids for (device count minus the reserve) */
+int         ovqa_set_sm_reserve(int sms);         /* leave `sms` SMs (rounded up to even) to co-running kernels of other streams (NCCL during a
+                                                     data-parallel backward pass); returns the previous reserve.  Initial value: $OVQA_SM_RESERVE or 0 */
 uint64_t    ovqa_launch_count(void);              /* kernels launched by this library so far (process wide) */
 
 /* ---------------------------------------------------------------------------------------------------

@@ -25,6 +25,7 @@ _PROTOS = {
     "ovqa_error_string": [_i32],
     "ovqa_last_cuda_error": [],
     "ovqa_device_sm_count": [],
+    "ovqa_set_sm_reserve": [_i32],
     "ovqa_launch_count": [],
     "ovqa_gemm": [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _f32, _f32, _vp, _i32,
                   _vp, _vp, _i64, _vp, _i64, _vp, _i64, _f32, _u64, _u64, _vp, _vp, _i32, _vp],

@@ -8,14 +8,21 @@ namespace ovqa {
 thread_local int g_last_cuda_error = 0;
 unsigned long long g_launch_count = 0;
 
+// SMs the persistent kernels size their grids for: the device's count minus a reserve (ovqa_set_sm_reserve) left free for kernels of
+// OTHER streams that must co-run — NCCL's all-reduce during a data-parallel backward pass.  A persistent grid of one CTA per SM whose last
+// CTAs cannot become resident (their SMs hold the collective) runs those CTAs' tiles as a second wave: the whole launch takes ~1.7x
+// (profiles/r02k_ddp_timeline.json).
+static int g_sm_reserve = [] { const char* e = getenv("OVQA_SM_RESERVE"); const int v = e ? atoi(e) : 0; return v < 0 ? 0 : (v + 1) / 2 * 2; }();
 int sm_count() {
     static int cache[64] = {};
     const int dev = current_device() & 63;
     int v = __atomic_load_n(&cache[dev], __ATOMIC_RELAXED);
-    if (v > 0) return v;
-    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = kNumSMsB200;
-    __atomic_store_n(&cache[dev], v, __ATOMIC_RELAXED);
-    return v;
+    if (v <= 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = kNumSMsB200;
+        __atomic_store_n(&cache[dev], v, __ATOMIC_RELAXED);
+    }
+    const int r = __atomic_load_n(&g_sm_reserve, __ATOMIC_RELAXED);
+    return v - r >= 8 ? v - r : v;
 }
 
 template <typename T> int sdpa_fwd_simt_launch(const SdpaArgs&, cudaStream_t);
@@ -51,6 +58,10 @@ extern "C" const char* ovqa_error_string(int code) {
 }
 extern "C" int ovqa_last_cuda_error(void) { return g_last_cuda_error; }
 extern "C" int ovqa_device_sm_count(void) { return sm_count(); }
+extern "C" int ovqa_set_sm_reserve(int sms) {
+    if (sms < 0) sms = 0;
+    return __atomic_exchange_n(&g_sm_reserve, (sms + 1) / 2 * 2, __ATOMIC_RELAXED);
+}
 extern "C" uint64_t ovqa_launch_count(void) { return __atomic_load_n(&g_launch_count, __ATOMIC_RELAXED); }
 
 extern "C" int ovqa_gemm(const void* A, const void* B, void* C, int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb,

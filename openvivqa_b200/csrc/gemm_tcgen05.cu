@@ -33,9 +33,6 @@ constexpr int UMMA_K = 16;
 // its per-element global accesses.
 constexpr int epw_for(int mode, int feat) { return (mode == 1 /*EPI_FULL*/ && feat < 0) ? 16 : 8; }
 constexpr int kAccStages = 2;
-#ifndef OVQA_EPI_BUFS
-#define OVQA_EPI_BUFS 3
-#endif
 
 // CTAS = 1: one CTA per 128 x BN tile.  CTAS = 2: a CTA pair (cluster of 2, cta_group::2) per 256 x BN tile — each CTA stages its
 // own 128 rows of A and HALF of B (the MMA reads the other half from the peer's shared memory): 32 KB instead of 48 KB of L2 -> smem
@@ -46,19 +43,25 @@ constexpr int kAccStages = 2;
 // that holds accumulator row r (tcgen05.ld 32x32b: row per lane) finishes its 32 columns in registers, overwrites ITS OWN row of the
 // buffer with the result (128B / 64B swizzle: conflict-free), and one lane hands the buffer to the TMA unit (tensor store, or fp32
 // add-reduction for split-K).  No per-element global access, no transposition pass, ragged edges clipped by the tensor map.
+// The pipeline depth and the number of staging buffers are chosen per LAUNCH (kernel arguments `stages`, `nb`; shared memory carved
+// at run time): short reductions (K = 512) are bound by the epilogue and want 3 buffers per warp, long ones by the main loop and want
+// the 6-deep operand ring (host: launch()).
 template <int BN, int CTAS, int EPW> struct Cfg {
-    static constexpr int kEpiBufs = EPW == 16 ? 1 : ((CTAS == 1 && BN == 256) ? 2 : OVQA_EPI_BUFS);
-    static constexpr int kScratchBytes = EPW * kEpiBufs * 4096;   // 32x32 fp32 chunks
     static constexpr int kBarBytes = 512;
     static constexpr int kABytes = BM * BK * 2;
     static constexpr int kBBytes = (BN / CTAS) * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kFit = (227 * 1024 - 1024 /*align slack*/ - kBarBytes - kScratchBytes) / kStageBytes;
-    static constexpr int kStages = kFit > 6 ? 6 : kFit;
     static constexpr int kTmemCols = kAccStages * BN;  // 256 or 512: power of two
-    static constexpr int kSmemBytes = kStages * kStageBytes + kScratchBytes + 1024 + kBarBytes;
-    static_assert(kStages >= 3 && kSmemBytes <= 227 * 1024, "shared memory budget");
-    static_assert((2 * kStages + 2 * kAccStages + EPW * kEpiBufs) * 8 + 8 <= kBarBytes, "barrier region");
+    static constexpr int kMaxStages = 6, kMaxEpiBufs = EPW == 16 ? 1 : 3;   // (16-warp kernels: the run-time-feature epilogue, one scratch chunk per warp)
+    static constexpr int kSmemLimit = 227 * 1024;
+    static constexpr int scratch_bytes(int nb) { return EPW * nb * 4096; }                  // 32x32 fp32 chunks
+    static constexpr int stages_for(int nb) {
+        const int fit = (kSmemLimit - 1024 /*align slack*/ - kBarBytes - scratch_bytes(nb)) / kStageBytes;
+        return fit > kMaxStages ? kMaxStages : fit;
+    }
+    static constexpr int smem_bytes(int stages, int nb) { return stages * kStageBytes + scratch_bytes(nb) + 1024 + kBarBytes; }
+    static_assert(stages_for(1) >= 3, "shared memory budget");
+    static_assert((2 * kMaxStages + 2 * kAccStages + EPW * kMaxEpiBufs) * 8 + 8 <= kBarBytes, "barrier region");
 };
 
 // ----------------------------------------------------------------------------- epilogue pieces
@@ -150,20 +153,20 @@ template <int BN, bool A_MN, bool B_MN, typename TC, int MODE, int FEAT, int CTA
 __global__ void __launch_bounds__(EPW == 16 ? 640 : 384, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_c,
                     const __grid_constant__ CUtensorMap tma_x, TC* __restrict__ C, int64_t m, int64_t n, int64_t k, int64_t ldc, Epilogue epi,
-                    int split_k, int use_tma) {
+                    int split_k, int use_tma, int nb, int stages) {
     using cfg = Cfg<BN, CTAS, EPW>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + cfg::kStages * cfg::kABytes;
-    float4* scratch = reinterpret_cast<float4*>(smem + cfg::kStages * cfg::kStageBytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + cfg::kStages * cfg::kStageBytes + cfg::kScratchBytes);
+    uint8_t* smem_b = smem + stages * cfg::kABytes;
+    float4* scratch = reinterpret_cast<float4*>(smem + stages * cfg::kStageBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + stages * cfg::kStageBytes + cfg::scratch_bytes(nb));
     uint64_t* full_bar = bars;                              // [kStages]   TMA -> MMA
-    uint64_t* empty_bar = bars + cfg::kStages;              // [kStages]   MMA -> TMA
-    uint64_t* tmem_full = bars + 2 * cfg::kStages;          // [2]         MMA -> epilogue
+    uint64_t* empty_bar = bars + stages;                    // [stages]    MMA -> TMA
+    uint64_t* tmem_full = bars + 2 * stages;                // [2]         MMA -> epilogue
     uint64_t* tmem_empty = tmem_full + kAccStages;          // [2]         epilogue -> MMA
     uint64_t* epi_bar = tmem_empty + kAccStages;            // [EPW * kEpiBufs]  TMA -> epilogue warp (input operand of a chunk)
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(epi_bar + EPW * cfg::kEpiBufs);
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(epi_bar + EPW * nb);
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     constexpr int TM = BM * CTAS;                            // rows of a work tile (a CTA pair shares one 256-row tile)
@@ -181,9 +184,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_x)) : "memory");
         }
         // full: the leader's own arrive.expect_tx (+ the peer's remote arrive); tmem_empty: the epilogue warps of every CTA of the pair
-        for (int i = 0; i < cfg::kStages; ++i) { mbar_init(full_bar + i, CTAS); mbar_init(empty_bar + i, 1); }
+        for (int i = 0; i < stages; ++i) { mbar_init(full_bar + i, CTAS); mbar_init(empty_bar + i, 1); }
         for (int i = 0; i < kAccStages; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, EPW * CTAS); }
-        for (int i = 0; i < EPW * cfg::kEpiBufs; ++i) mbar_init(epi_bar + i, 1);
+        for (int i = 0; i < EPW * nb; ++i) mbar_init(epi_bar + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -245,7 +248,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 #pragma unroll
                         for (int j = 0; j < BN / CTAS / 64; ++j) load(sb + j * 8192, &tma_b, b_row + j * 64, kb * BK);
                     }
-                    if (++stage == cfg::kStages) { stage = 0; phase ^= 1; }
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -276,7 +279,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                     }
                     // frees the smem slot (in both CTAs of a pair) when these MMAs retire
                     if constexpr (CTAS == 2) tcgen05_commit_2sm(empty_bar + stage); else tcgen05_commit(empty_bar + stage);
-                    if (++stage == cfg::kStages) { stage = 0; phase ^= 1; }
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
                 // accumulator ready for the epilogue warps (of both CTAs)
                 if constexpr (CTAS == 2) tcgen05_commit_2sm(tmem_full + acc); else tcgen05_commit(tmem_full + acc);
@@ -291,7 +294,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         constexpr bool kSplit = sizeof(TC) == 4;
         constexpr int HI = kSplit ? 16 : 4;               // column distance between a lane's two groups of four
         // scratch: 32 rows x 8 granules of 16 B per warp, granule index XOR (row & 7)  (conflict-free both ways)
-        const uint32_t sc = smem_u32(scratch) + (uint32_t)(warp - 2) * (uint32_t)(cfg::kEpiBufs * 4096);
+        const uint32_t sc = smem_u32(scratch) + (uint32_t)(warp - 2) * (uint32_t)(nb * 4096);
         const uint32_t st_row = sc + (uint32_t)lane * 128u, st_x = (uint32_t)(lane & 7);
         const uint32_t g_lo = kSplit ? (uint32_t)c8 : (uint32_t)(2 * c8), g_hi = kSplit ? (uint32_t)(4 + c8) : (uint32_t)(2 * c8 + 1);   // 16-byte granules of the row
         const uint32_t ld_lo = sc + (uint32_t)rr * 128u + ((g_lo ^ (uint32_t)rr) << 4), ld_hi = sc + (uint32_t)rr * 128u + ((g_hi ^ (uint32_t)rr) << 4);
@@ -325,7 +328,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         uint32_t acc_phase = 0;
         // ------------------------------------------------------------------ TMA-fed epilogue (see Cfg)
         constexpr int kFe = (MODE == EPI_FULL && FEAT >= 0) ? FEAT : 0;
-        constexpr bool kTmaCapable = EPW == 8 && (MODE != EPI_FULL || (FEAT >= 0 && !((FEAT & F_SAVE_D) && sizeof(TC) == 4)));
+        // (the GELU epilogues stay on the transposing path below: they are bound by their ~900 instructions per chunk, not by memory
+        // latency, and measured 5-10 % slower here — two stores of 64-byte rows per chunk for fc1's result + saved derivative)
+        constexpr bool kTmaCapable = EPW == 8 && (MODE != EPI_FULL || (FEAT >= 0 && !(FEAT & F_GELU)));
         bool tma_done = false;
         if constexpr (kTmaCapable) {
           if (use_tma) {                                                 // warp-uniform (kernel argument)
@@ -334,12 +339,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                            kColsum = kFe & F_COLSUM;
             constexpr bool kLoad = kRes || kMul;
             constexpr uint32_t kBoxBytes = 32u * 32u * (uint32_t)sizeof(TC);
-            constexpr int NB = cfg::kEpiBufs;
             constexpr int kChunkStep = (EPW / 4) * 32;
             const int ew = warp - 2;
-            const uint32_t bufs = smem_u32(scratch) + (uint32_t)ew * (uint32_t)(NB * 4096);
-            uint64_t* in_bar = epi_bar + ew * NB;
-            const bool bias_vec = al16(bias);
+            const uint32_t bufs = smem_u32(scratch) + (uint32_t)ew * (uint32_t)(nb * 4096);
+            uint64_t* in_bar = epi_bar + ew * nb;
             const float k_out = kDrop ? inv_keep : 1.0f;                  // dropout keep-scale, folded into the constants below
             const float a_s = (kGelu ? 1.0f : k_out) * alpha;
             const float b_s = (kDrop && !kGelu) ? k_out : 1.0f;
@@ -349,18 +352,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             const uint32_t sx = kSplit ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
             // the chunk sequence of this warp, walked a second time ahead of the math by the loads of the input operand (lane 0)
             int ld_tile = tile0, ld_c0 = slot * 32;
-            uint32_t ld_cnt = 0, cnt = 0;
+            uint32_t ld_b = 0, cur_b = 0, cur_par = 0;               // staging buffer of the next load / of the current chunk (+ its barrier parity)
             auto ld_issue = [&]() {
                 while (ld_tile < num_tiles) {
                     int mt2, nt2, ka, kb_;
                     decode(ld_tile, mt2, nt2, ka, kb_);
                     const int64_t c = (int64_t)nt2 * BN + ld_c0;
                     if (ld_c0 < BN && c < n) {
-                        const uint32_t b = ld_cnt % NB;
-                        mbar_expect_tx(in_bar + b, kBoxBytes);
-                        tma_load_2d_u32(bufs + b * 4096u, &tma_x, in_bar + b, (int)c, mt2 * TM + (int)cta_rank * BM + quad * 32);
+                        mbar_expect_tx(in_bar + ld_b, kBoxBytes);
+                        tma_load_2d_u32(bufs + ld_b * 4096u, &tma_x, in_bar + ld_b, (int)c, mt2 * TM + (int)cta_rank * BM + quad * 32);
                         ld_c0 += kChunkStep;
-                        ++ld_cnt;
+                        if (++ld_b == (uint32_t)nb) ld_b = 0;
                         return;
                     }
                     ld_tile += tile_step;
@@ -368,11 +370,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                 }
             };
             if constexpr (kLoad) {
-                if (lane == 0) for (int q = 0; q < NB - 1; ++q) ld_issue();
+                if (lane == 0) for (int q = 0; q < nb - 1; ++q) ld_issue();      // (host: nb >= 2 for the kernels that load)
             }
+            // bias: lane L holds bias[col0 + L] of the chunk about to be processed, requested one chunk ahead (its latency would otherwise sit
+            // between the accumulator read and the first FMA of every chunk) and handed to the row-owning lanes by shuffles
+            float bias_cur = 0.f, bias_nxt = 0.f;
+            int64_t bias_col = -1, bias_nxt_col = -1;
+            auto bias_fetch = [&](int64_t c) { return bias ? __ldg(bias + min(c + lane, n - 1)) : 0.f; };
             for (int tile = tile0; tile < num_tiles; tile += tile_step) {
                 int mt, nt, kb0, kb1;
                 decode(tile, mt, nt, kb0, kb1);
+                if (bias && bias_nxt_col != (int64_t)nt * BN + slot * 32) {      // first tile (or a skipped ragged one): nothing was requested ahead
+                    bias_nxt_col = (int64_t)nt * BN + slot * 32;
+                    bias_nxt = bias_fetch(bias_nxt_col);
+                }
                 mbar_wait(tmem_full + acc, acc_phase);
                 tcgen05_fence_after();
                 const int row0 = mt * TM + (int)cta_rank * BM + quad * 32;
@@ -382,33 +393,41 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                 for (int c0 = slot * 32; c0 < BN; c0 += kChunkStep) {
                     const int64_t col0 = (int64_t)nt * BN + c0;
                     if (col0 >= n) break;                                     // warp-uniform
-                    const bool full_cols = col0 + 32 <= n;
-                    const uint32_t b = cnt % NB, buf = bufs + b * 4096u;
+                    if (bias) {
+                        bias_cur = bias_nxt; bias_col = bias_nxt_col;
+                        if (bias_col != col0) { bias_col = col0; bias_cur = bias_fetch(col0); }     // (not reached on the regular chunk sequence)
+                        // the chunk after this one: next in the tile, else the first of this warp's next tile
+                        if (c0 + kChunkStep < BN && col0 + kChunkStep < n) bias_nxt_col = col0 + kChunkStep;
+                        else {
+                            int mt2 = 0, nt2 = 0, ka, kb_;
+                            if (tile + tile_step < num_tiles) decode(tile + tile_step, mt2, nt2, ka, kb_);
+                            bias_nxt_col = (int64_t)nt2 * BN + slot * 32;
+                        }
+                        bias_nxt = bias_fetch(bias_nxt_col);
+                    }
+                    const uint32_t b = cur_b, buf = bufs + b * 4096u;
                     const uint32_t my = buf + row_off;
                     uint32_t r[32];
                     tmem_ld_32x32b_x32(t_row + (uint32_t)c0, r);
                     if constexpr (kLoad) {
-                        mbar_wait(in_bar + b, (cnt / NB) & 1u);              // the operand rows have landed in `buf`
+                        mbar_wait(in_bar + b, cur_par);                      // the operand rows have landed in `buf`
                     } else {
-                        if (lane == 0) bulk_wait_read<NB - 1>();             // the store that last read `buf` is done with it
+                        if (lane == 0) {                                     // the store that last read `buf` is done with it
+                            if (nb == 3) bulk_wait_read<2>(); else if (nb == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+                        }
                         __syncwarp();
                     }
                     tmem_ld_wait();
                     float v[32];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        float b4[4] = {0.f, 0.f, 0.f, 0.f};
-                        if (bias) {
-                            if (full_cols && bias_vec) {
-                                const float4 t = __ldg(reinterpret_cast<const float4*>(bias + col0 + 4 * q));
-                                b4[0] = t.x; b4[1] = t.y; b4[2] = t.z; b4[3] = t.w;
-                            } else {
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    if (bias) {                                              // warp-uniform
+                        const float bsc = bias_cur * b_s;
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) b4[j] = __ldg(bias + min(col0 + 4 * q + j, n - 1));
-                            }
-                        }
+                        for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], a_s, __shfl_sync(0xffffffffu, bsc, j));
+                    } else {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) v[4 * q + j] = fmaf(__uint_as_float(r[4 * q + j]), a_s, b4[j] * b_s);
+                        for (int j = 0; j < 32; ++j) v[j] *= a_s;
                     }
                     float g[kSave ? 32 : 1];
                     if constexpr (kGelu) {
@@ -497,7 +516,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                         }
                         if (col0 + lane < n) atomicAdd(colsum + col0 + lane, v[0]);
                     }
-                    ++cnt;
+                    if (++cur_b == (uint32_t)nb) { cur_b = 0; cur_par ^= 1u; }
                 }
                 tcgen05_fence_before();
                 __syncwarp();
@@ -900,6 +919,8 @@ int launch(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, int64_t m, i
             use_tma = rc == OVQA_OK;
         }
     }
+    // k-blocks of one work unit: a short main loop (K <= 1024) leaves the epilogue exposed, a long one hides it and wants the deeper operand ring
+    const bool short_k = (num_k_blocks + split_k - 1) / split_k <= 16;
     const int64_t tiles = ((m + BM * CTAS - 1) / (BM * CTAS)) * ((n + BN - 1) / BN) * split_k;
     const int64_t units = sm_count() / CTAS;
     const int grid = (int)(tiles < units ? tiles : units) * CTAS;
@@ -918,12 +939,21 @@ int launch(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, int64_t m, i
         using cfg = Cfg<BN, CTAS, kEpw>;                                                                                        \
         auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, TC_, MODE_, FEAT_, CTAS, kEpw>;                                               \
         static OncePerDevice attr_set;                                                                                          \
-        if (attr_set.pending()) { OVQA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::kSmemBytes)); attr_set.mark(); } \
+        if (attr_set.pending()) { OVQA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::kSmemLimit)); attr_set.mark(); } \
+        /* TMA-fed epilogue: which instantiations have it (mirrors kTmaCapable in the kernel), how many staging buffers per warp */ \
+        constexpr bool kCap = kEpw == 8 && (MODE_ != EPI_FULL || ((FEAT_) >= 0 && !((FEAT_) & F_GELU)));                          \
+        constexpr bool kLoads = MODE_ == EPI_FULL && (FEAT_) >= 0 && ((FEAT_) & (F_RES | F_MULAUX));                              \
+        const int tma = kCap ? use_tma : 0;                                                                                     \
+        int nb = (!tma || MODE_ == EPI_SPLITK) ? 1 : short_k ? (kLoads ? 3 : 2) : (kLoads ? 2 : 1);                                                      \
+        while (nb > 1 && cfg::stages_for(nb) < 3) --nb;                                                                         \
+        if (kLoads && nb < 2) { nb = 1; }                                                                                       \
+        const int tma_f = (kLoads && nb < 2) ? 0 : tma;                                                                         \
+        const int stages = cfg::stages_for(nb), smem_bytes = cfg::smem_bytes(stages, nb);                                       \
         if constexpr (CTAS == 1) {                                                                                             \
-            kern<<<grid, kThreads, cfg::kSmemBytes, st>>>(ma, mb, mc, mx, (TC_*)C, m, n, k, ldc, epi, split_k, use_tma);                        \
+            kern<<<grid, kThreads, smem_bytes, st>>>(ma, mb, mc, mx, (TC_*)C, m, n, k, ldc, epi, split_k, tma_f, nb, stages);   \
         } else {                                                                                                               \
             cudaLaunchConfig_t lc{};                                                                                           \
-            lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(kThreads); lc.dynamicSmemBytes = cfg::kSmemBytes; lc.stream = st; \
+            lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(kThreads); lc.dynamicSmemBytes = smem_bytes; lc.stream = st;  \
             cudaLaunchAttribute at[1];                                                                                         \
             at[0].id = cudaLaunchAttributeClusterDimension;                                                                    \
             at[0].val.clusterDim.x = CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;                             \
@@ -939,7 +969,7 @@ int launch(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, int64_t m, i
             }                                                                                                                  \
             const int clusters = grid / CTAS < max_clusters ? grid / CTAS : max_clusters;                                      \
             lc.gridDim = dim3((unsigned)(clusters * CTAS));                                                                    \
-            OVQA_CUDA_OK(cudaLaunchKernelEx(&lc, kern, ma, mb, mc, mx, (TC_*)C, m, n, k, ldc, epi, split_k, use_tma));                          \
+            OVQA_CUDA_OK(cudaLaunchKernelEx(&lc, kern, ma, mb, mc, mx, (TC_*)C, m, n, k, ldc, epi, split_k, tma_f, nb, stages)); \
         }                                                                                                                      \
     } while (0)
     // the specialised sets exist for the operand forms that launch them: forward y = x W^T is (N,N), dgrad dx = dy W is (N,T)
@@ -991,7 +1021,8 @@ int gemm_tcgen05_bf16(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, i
         const int64_t tm = pair ? 2 * BM : BM, units = pair ? sm_count() / 2 : sm_count();
         const int64_t tiles = ((m + tm - 1) / tm) * ((n + (wide ? 255 : 127)) / (wide ? 256 : 128));
         const int64_t kblocks = (k + BK - 1) / BK;
-        int64_t want = (2 * units + tiles / 2) / tiles;
+        static const int waves = [] { const char* e = getenv("OVQA_WGRAD_WAVES"); const int w = e ? atoi(e) : 2; return w < 1 ? 1 : w; }();
+        int64_t want = (waves * units + tiles / 2) / tiles;
         if (want > kblocks / 8) want = kblocks / 8;
         split_k = (int)(want < 1 ? 1 : want);
     } else {

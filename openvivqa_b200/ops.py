@@ -41,6 +41,11 @@ def _ld(t: torch.Tensor) -> int:
     return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
 
 
+def set_sm_reserve(sms: int) -> int:
+    """Leave ``sms`` SMs free of the library's persistent kernels (for a co-running collective); returns the previous reserve."""
+    return int(L.lib().ovqa_set_sm_reserve(int(sms)))
+
+
 def gemm(a: torch.Tensor, b: torch.Tensor, *, a_op: str = "N", b_op: str = "N", out: Optional[torch.Tensor] = None,
          out_dtype: Optional[torch.dtype] = None, bias: Optional[torch.Tensor] = None, alpha: float = 1.0,
          beta: float = 0.0, gelu: bool = False, dgelu_aux: Optional[torch.Tensor] = None,
