@@ -1,5 +1,6 @@
 // Shared device/host helpers for libovqa_b200 (sm_100a only).
 #pragma once
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -26,6 +27,28 @@ extern unsigned long long g_launch_count;
         __atomic_fetch_add(&::ovqa::g_launch_count, 1ull, __ATOMIC_RELAXED); \
         OVQA_CUDA_OK(cudaPeekAtLastError());                  \
     } while (0)
+
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// The library's kernels are launched with programmaticStreamSerializationAllowed: a kernel's CTAs may be scheduled (and run their set-up)
+// while the previous kernel of the stream is still draining; `pdl_wait()` — the first thing every such kernel does before it touches
+// global memory — blocks until that kernel has completed and its writes are visible, `pdl_trigger()` lets the NEXT kernel be scheduled.
+// Captured CUDA graphs keep the edges as programmatic dependencies.  OVQA_PDL=0 launches everything fully serialised.
+inline bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("OVQA_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = grid; lc.blockDim = block; lc.dynamicSmemBytes = smem; lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&lc, kern, static_cast<KArgs>(args)...);
+}
 
 constexpr int kNumSMsB200 = 148;
 int sm_count();                  // of the CURRENT device (cached per device)

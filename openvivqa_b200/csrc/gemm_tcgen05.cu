@@ -202,6 +202,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
+    // Programmatic dependent launch: everything above (barriers, tensor memory, descriptor prefetch) may run while the previous kernel of
+    // the stream drains; nothing below may touch global memory before that kernel's writes are visible.  (No-op without the launch attribute.)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // ... and the NEXT kernel of the stream may be scheduled from here on (it waits the same way before touching memory): its CTAs
+    // take over SMs as this grid's CTAs retire instead of after the grid has drained.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     // tile -> (m tile, n tile, k split); n fastest so concurrently running CTAs share the A (activation) tile in L2
     auto decode = [&](int tile, int& mt, int& nt, int& kb0, int& kb1) {
@@ -949,15 +955,18 @@ int launch(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, int64_t m, i
         if (kLoads && nb < 2) { nb = 1; }                                                                                       \
         const int tma_f = (kLoads && nb < 2) ? 0 : tma;                                                                         \
         const int stages = cfg::stages_for(nb), smem_bytes = cfg::smem_bytes(stages, nb);                                       \
-        if constexpr (CTAS == 1) {                                                                                             \
-            kern<<<grid, kThreads, smem_bytes, st>>>(ma, mb, mc, mx, (TC_*)C, m, n, k, ldc, epi, split_k, tma_f, nb, stages);   \
-        } else {                                                                                                               \
-            cudaLaunchConfig_t lc{};                                                                                           \
-            lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(kThreads); lc.dynamicSmemBytes = smem_bytes; lc.stream = st;  \
-            cudaLaunchAttribute at[1];                                                                                         \
-            at[0].id = cudaLaunchAttributeClusterDimension;                                                                    \
-            at[0].val.clusterDim.x = CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;                             \
-            lc.attrs = at; lc.numAttrs = 1;                                                                                    \
+        cudaLaunchConfig_t lc{};                                                                                               \
+        lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(kThreads); lc.dynamicSmemBytes = smem_bytes; lc.stream = st;      \
+        cudaLaunchAttribute at[2];                                                                                             \
+        int na = 0;                                                                                                            \
+        if (pdl_enabled()) { at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[na].val.programmaticStreamSerializationAllowed = 1; ++na; } \
+        if constexpr (CTAS == 2) {                                                                                             \
+            at[na].id = cudaLaunchAttributeClusterDimension;                                                                   \
+            at[na].val.clusterDim.x = CTAS; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;                          \
+            ++na;                                                                                                              \
+        }                                                                                                                      \
+        lc.attrs = at; lc.numAttrs = na;                                                                                       \
+        if constexpr (CTAS == 2) {                                                                                             \
             /* persistent kernel: never more clusters than can be co-resident (GPCs with an odd SM count cannot pair them all) */ \
             static int max_clusters = -1;                                                                                      \
             if (max_clusters < 0) {                                                                                            \
@@ -969,8 +978,8 @@ int launch(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, int64_t m, i
             }                                                                                                                  \
             const int clusters = grid / CTAS < max_clusters ? grid / CTAS : max_clusters;                                      \
             lc.gridDim = dim3((unsigned)(clusters * CTAS));                                                                    \
-            OVQA_CUDA_OK(cudaLaunchKernelEx(&lc, kern, ma, mb, mc, mx, (TC_*)C, m, n, k, ldc, epi, split_k, tma_f, nb, stages)); \
         }                                                                                                                      \
+        OVQA_CUDA_OK(cudaLaunchKernelEx(&lc, kern, ma, mb, mc, mx, (TC_*)C, m, n, k, ldc, epi, split_k, tma_f, nb, stages));   \
     } while (0)
     // the specialised sets exist for the operand forms that launch them: forward y = x W^T is (N,N), dgrad dx = dy W is (N,T)
     constexpr bool kFwd = !A_MN && !B_MN, kDgrad = !A_MN && B_MN;
