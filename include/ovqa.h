@@ -247,6 +247,22 @@ int ovqa_attr_pool_bwd(const float* dpooled, const void* hidden, const float* w2
                        float* dx, void* dpre, float* dw2, float* db2,
                        int64_t B, int64_t N, int64_t Dh, int64_t D, float dropout_p, int hidden_dtype, void* stream);
 
+/* Recurrent part of the single-layer, batch-first LSTM of LSTMTextEmbedding (models/modules/text_embeddings.py:234,244: nn.LSTM(d_model, d_model,
+ * batch_first=True) called without an initial state).  Gate order i, f, g, o (PyTorch).  bf16 operands, fp32 accumulate / state.
+ *   xg [B,L,4H] fp32 = x W_ih^T + b_ih for all steps (one ovqa_gemm);  w_hh_bf16 [4H,H];  b_hh [4H] fp32 or NULL.
+ *   y [B,L,H] fp32 = h_t.  Optional outputs (all or none are needed by the backward pass): y_bf16 [B,L,H], hprev_bf16 [B,L,H] = h_{t-1} rows
+ *   (zero at t = 0: the operand of the W_hh weight gradient), gates_bf16 [B,L,4H] = activated i,f,g,o, c_out [B,L,H] fp32 = c_t.
+ * One kernel per direction: a thread-block cluster of H/32 CTAs keeps W_hh in registers for all L steps and exchanges h_t (forward) /
+ * the partial products of dh_{t-1} (backward) through distributed shared memory.  H must be 128, 256 or 512 (ovqa_lstm_supported);
+ * other sizes return OVQA_ERR_BAD_SHAPE (the caller keeps the library LSTM).
+ * Backward: dy [B,L,H] fp32 -> dgates_bf16 [B,L,4H] = gradient of the gate PRE-activations; the caller forms dx = dgates W_ih,
+ * dW_ih = dgates^T x, dW_hh = dgates^T hprev, db_ih = db_hh = column sums of dgates with ovqa_gemm / ovqa_colsum. */
+int ovqa_lstm_supported(int64_t H);
+int ovqa_lstm_fwd(const float* xg, const void* w_hh_bf16, const float* b_hh, float* y, void* y_bf16, void* hprev_bf16, void* gates_bf16,
+                  float* c_out, int64_t B, int64_t L, int64_t H, void* stream);
+int ovqa_lstm_bwd(const float* dy, const void* w_hh_bf16, const void* gates_bf16, const float* c_all, void* dgates_bf16,
+                  int64_t B, int64_t L, int64_t H, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * M4C dynamic pointer network and greedy decode step.
  * ------------------------------------------------------------------------------------------------- */

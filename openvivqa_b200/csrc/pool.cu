@@ -122,6 +122,234 @@ __global__ void __launch_bounds__(kPoolThreads) attr_pool_bwd_kernel(const float
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------- vector kernels
+// The kernels above touch one 2- or 4-byte element per thread and load (profiles/r02_kernels_ncu.md: 80 us for 42 MB, 79 % of the stall
+// samples on outstanding loads, 12 % occupancy — 256 CTAs cannot hide DRAM latency with 4 bytes per request).  These read 16 bytes per
+// request with 4-8 requests in flight per thread; shapes they need: D % 4 == 0, Dh % 8 == 0 (bf16) / % 4 (fp32), 16-byte aligned rows.
+template <typename TH> struct HVec;
+template <> struct HVec<float> {
+    static constexpr int kN = 4;
+    static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    }
+    static __device__ __forceinline__ void store(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct HVec<__nv_bfloat16> {
+    static constexpr int kN = 8;
+    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+        *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    }
+};
+
+__device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nw = kPoolThreads / 32;
+    v = is_max ? warp_max(v) : warp_sum(v);
+    __syncthreads();                                 // `red` may still be read from the previous reduction
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float r = red[0];
+    for (int i = 1; i < nw; ++i) r = is_max ? fmaxf(r, red[i]) : r + red[i];
+    return r;
+}
+
+template <typename TH>
+__global__ void __launch_bounds__(kPoolThreads) attr_pool_fwd_vec_kernel(const TH* __restrict__ hid, const float* __restrict__ w2, const float* __restrict__ b2,
+                                                                         const float* __restrict__ x, float* __restrict__ pooled, float* __restrict__ probs,
+                                                                         int N, int Dh, int D) {
+    extern __shared__ __align__(16) float sp[];      // [N] logits -> probabilities | [kPoolThreads * 4] partial weighted sums
+    __shared__ float red[kPoolThreads / 32];
+    constexpr int HN = HVec<TH>::kN;
+    const int64_t b = blockIdx.x;
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nw = kPoolThreads / 32;
+    const TH* hb = hid + b * (int64_t)N * Dh;
+    float* part = sp + ((N + 3) & ~3);
+    // logits: one warp per row, two rows at a time (their loads are all issued before the first FMA)
+    const int hvecs = Dh / HN;
+    for (int n = warp; n < N; n += 2 * nw) {
+        const int n1 = n + nw;
+        float s0 = 0.f, s1 = 0.f;
+        for (int c = lane; c < hvecs; c += 32) {
+            float h0[HN], h1[HN], w[HN];
+            HVec<TH>::load(hb + (int64_t)n * Dh + c * HN, h0);
+            if (n1 < N) HVec<TH>::load(hb + (int64_t)n1 * Dh + c * HN, h1);
+#pragma unroll
+            for (int j = 0; j < HN; j += 4) {
+                const float4 ww = __ldg(reinterpret_cast<const float4*>(w2 + c * HN + j));
+                w[j] = ww.x; w[j + 1] = ww.y; w[j + 2] = ww.z; w[j + 3] = ww.w;
+            }
+#pragma unroll
+            for (int j = 0; j < HN; ++j) { s0 = fmaf(h0[j], w[j], s0); if (n1 < N) s1 = fmaf(h1[j], w[j], s1); }
+        }
+        s0 = warp_sum(s0); s1 = warp_sum(s1);
+        if (lane == 0) { sp[n] = s0 + __ldg(b2); if (n1 < N) sp[n1] = s1 + __ldg(b2); }
+    }
+    __syncthreads();
+    float mx = -INFINITY;
+    for (int n = threadIdx.x; n < N; n += kPoolThreads) mx = fmaxf(mx, sp[n]);
+    mx = block_reduce(mx, red, true);
+    float sum = 0.f;
+    for (int n = threadIdx.x; n < N; n += kPoolThreads) { const float e = expf(sp[n] - mx); sp[n] = e; sum += e; }
+    sum = block_reduce(sum, red, false);
+    const float inv = 1.f / sum;
+    for (int n = threadIdx.x; n < N; n += kPoolThreads) { const float p = sp[n] * inv; sp[n] = p; if (probs) probs[b * N + n] = p; }
+    __syncthreads();
+    // pooled: thread = (row partition, float4 column group); eight rows in flight per thread, partitions combined through shared memory
+    const float* xb = x + b * (int64_t)N * D;
+    const int dvecs = D / 4;
+    for (int c0 = 0; c0 < dvecs; c0 += kPoolThreads) {
+        const int cols = min(dvecs - c0, kPoolThreads);          // column groups of this pass
+        const int parts = kPoolThreads / cols > 0 ? kPoolThreads / cols : 1;   // row partitions (threads beyond parts * cols idle)
+        const int c = c0 + (int)threadIdx.x % cols, part_id = (int)threadIdx.x / cols;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (part_id < parts) {
+            int n = part_id;
+            for (; n + 3 * parts < N; n += 4 * parts) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(xb + (int64_t)(n + u * parts) * D) + c);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float p = sp[n + u * parts];
+                    acc.x = fmaf(p, v[u].x, acc.x); acc.y = fmaf(p, v[u].y, acc.y); acc.z = fmaf(p, v[u].z, acc.z); acc.w = fmaf(p, v[u].w, acc.w);
+                }
+            }
+            for (; n < N; n += parts) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(xb + (int64_t)n * D) + c);
+                const float p = sp[n];
+                acc.x = fmaf(p, v.x, acc.x); acc.y = fmaf(p, v.y, acc.y); acc.z = fmaf(p, v.z, acc.z); acc.w = fmaf(p, v.w, acc.w);
+            }
+        }
+        __syncthreads();
+        reinterpret_cast<float4*>(part)[threadIdx.x] = acc;
+        __syncthreads();
+        if ((int)threadIdx.x < cols) {
+            float4 t = reinterpret_cast<float4*>(part)[threadIdx.x];
+            for (int q = 1; q < parts; ++q) {
+                const float4 o = reinterpret_cast<float4*>(part)[q * cols + threadIdx.x];
+                t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+            }
+            *reinterpret_cast<float4*>(pooled + b * D + 4 * (c0 + (int)threadIdx.x)) = t;
+        }
+    }
+}
+
+template <typename TH>
+__global__ void __launch_bounds__(kPoolThreads) attr_pool_bwd_vec_kernel(const float* __restrict__ dpooled, const TH* __restrict__ hid, const float* __restrict__ w2,
+                                                                         const float* __restrict__ x, const float* __restrict__ probs, float* __restrict__ dx,
+                                                                         TH* __restrict__ dpre, float* __restrict__ dw2, float* __restrict__ db2, int N, int Dh,
+                                                                         int D, float inv_keep) {
+    extern __shared__ __align__(16) float sd[];      // [N] x.dpooled -> dlogit | [N] p | [kPoolThreads * 8] partial dw2
+    __shared__ float red[kPoolThreads / 32];
+    constexpr int HN = HVec<TH>::kN;
+    const int64_t b = blockIdx.x;
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nw = kPoolThreads / 32;
+    const int Np = (N + 3) & ~3;
+    float* sprob = sd + Np;
+    float* part = sprob + Np;
+    const float* xb = x + b * (int64_t)N * D;
+    const float* dpb = dpooled + b * D;
+    const float* pb = probs + b * N;
+    const int dvecs = D / 4;
+    for (int n = threadIdx.x; n < N; n += kPoolThreads) sprob[n] = __ldg(pb + n);
+    // x . dpooled per row: one warp per row, two rows at a time
+    for (int n = warp; n < N; n += 2 * nw) {
+        const int n1 = n + nw;
+        float s0 = 0.f, s1 = 0.f;
+        for (int c = lane; c < dvecs; c += 32) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(dpb) + c);
+            const float4 a = __ldg(reinterpret_cast<const float4*>(xb + (int64_t)n * D) + c);
+            float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n1 < N) a1 = __ldg(reinterpret_cast<const float4*>(xb + (int64_t)n1 * D) + c);
+            s0 = fmaf(a.x, g.x, fmaf(a.y, g.y, fmaf(a.z, g.z, fmaf(a.w, g.w, s0))));
+            s1 = fmaf(a1.x, g.x, fmaf(a1.y, g.y, fmaf(a1.z, g.z, fmaf(a1.w, g.w, s1))));
+        }
+        s0 = warp_sum(s0); s1 = warp_sum(s1);
+        if (lane == 0) { sd[n] = s0; if (n1 < N) sd[n1] = s1; }
+    }
+    __syncthreads();
+    float dot = 0.f;
+    for (int n = threadIdx.x; n < N; n += kPoolThreads) dot = fmaf(sprob[n], sd[n], dot);
+    dot = block_reduce(dot, red, false);
+    float dl_sum = 0.f;
+    for (int n = threadIdx.x; n < N; n += kPoolThreads) { const float dl = sprob[n] * (sd[n] - dot); sd[n] = dl; dl_sum += dl; }
+    dl_sum = block_reduce(dl_sum, red, false);       // (its barriers also publish sd[] = dlogit)
+    if (threadIdx.x == 0 && db2) atomicAdd(db2, dl_sum);
+    // dx[b,n,:] = p[n] dpooled: 16-byte stores, consecutive threads -> consecutive column groups
+    if (dx) {
+        float* dxb = dx + b * (int64_t)N * D;
+        for (int idx = threadIdx.x; idx < N * dvecs; idx += kPoolThreads) {
+            const int n = idx / dvecs, c = idx % dvecs;
+            const float4 g = __ldg(reinterpret_cast<const float4*>(dpb) + c);
+            const float p = sprob[n];
+            *reinterpret_cast<float4*>(dxb + (int64_t)n * D + 4 * c) = make_float4(p * g.x, p * g.y, p * g.z, p * g.w);
+        }
+    }
+    // d pre-activation and dw2: thread = (row partition, HN-column group), four rows in flight
+    const TH* hb = hid + b * (int64_t)N * Dh;
+    TH* db = dpre + b * (int64_t)N * Dh;
+    const int hvecs = Dh / HN;
+    for (int c0 = 0; c0 < hvecs; c0 += kPoolThreads) {
+        const int cols = min(hvecs - c0, kPoolThreads);
+        const int parts = kPoolThreads / cols > 0 ? kPoolThreads / cols : 1;
+        const int c = c0 + (int)threadIdx.x % cols, part_id = (int)threadIdx.x / cols;
+        float acc[HN], w[HN];
+#pragma unroll
+        for (int j = 0; j < HN; ++j) acc[j] = 0.f;
+        if (part_id < parts) {
+#pragma unroll
+            for (int j = 0; j < HN; j += 4) {
+                const float4 ww = __ldg(reinterpret_cast<const float4*>(w2 + c * HN + j));
+                w[j] = ww.x * inv_keep; w[j + 1] = ww.y * inv_keep; w[j + 2] = ww.z * inv_keep; w[j + 3] = ww.w * inv_keep;
+            }
+            int n = part_id;
+            for (; n + 3 * parts < N; n += 4 * parts) {
+                float h[4][HN];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) HVec<TH>::load(hb + (int64_t)(n + u * parts) * Dh + c * HN, h[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float dl = sd[n + u * parts];
+                    float o[HN];
+#pragma unroll
+                    for (int j = 0; j < HN; ++j) { acc[j] = fmaf(dl, h[u][j], acc[j]); o[j] = h[u][j] > 0.f ? dl * w[j] : 0.f; }
+                    HVec<TH>::store(db + (int64_t)(n + u * parts) * Dh + c * HN, o);
+                }
+            }
+            for (; n < N; n += parts) {
+                float h[HN], o[HN];
+                HVec<TH>::load(hb + (int64_t)n * Dh + c * HN, h);
+                const float dl = sd[n];
+#pragma unroll
+                for (int j = 0; j < HN; ++j) { acc[j] = fmaf(dl, h[j], acc[j]); o[j] = h[j] > 0.f ? dl * w[j] : 0.f; }
+                HVec<TH>::store(db + (int64_t)n * Dh + c * HN, o);
+            }
+        }
+        if (dw2) {
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < HN; ++j) part[j * kPoolThreads + threadIdx.x] = acc[j];
+            __syncthreads();
+            if ((int)threadIdx.x < cols) {
+#pragma unroll
+                for (int j = 0; j < HN; ++j) {
+                    float t = 0.f;
+                    for (int q = 0; q < parts; ++q) t += part[j * kPoolThreads + q * cols + threadIdx.x];
+                    atomicAdd(dw2 + (c0 + (int)threadIdx.x) * HN + j, t);
+                }
+            }
+        }
+    }
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 }  // namespace
 }  // namespace ovqa
 
@@ -133,8 +361,18 @@ extern "C" int ovqa_attr_pool_fwd(const void* hidden, const float* w2, const flo
     if (hidden_dtype != OVQA_F32 && hidden_dtype != OVQA_BF16) return OVQA_ERR_BAD_ARG;
     if (N * sizeof(float) > 48 * 1024 || B > 0x7fffffff) return OVQA_ERR_BAD_SHAPE;
     if (B == 0) return OVQA_OK;
-    const size_t smem = (size_t)N * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
+    const int hn = hidden_dtype == OVQA_F32 ? 4 : 8;
+    const size_t smem_v = (size_t)(((N + 3) & ~3) + kPoolThreads * 4) * sizeof(float);
+    if (D % 4 == 0 && Dh % hn == 0 && al16(hidden) && al16(w2) && al16(x) && al16(pooled) && smem_v <= 48 * 1024) {
+        if (hidden_dtype == OVQA_F32)
+            attr_pool_fwd_vec_kernel<float><<<(unsigned)B, kPoolThreads, smem_v, st>>>((const float*)hidden, w2, b2, x, pooled, probs, (int)N, (int)Dh, (int)D);
+        else
+            attr_pool_fwd_vec_kernel<__nv_bfloat16><<<(unsigned)B, kPoolThreads, smem_v, st>>>((const __nv_bfloat16*)hidden, w2, b2, x, pooled, probs, (int)N, (int)Dh, (int)D);
+        OVQA_LAUNCH_OK();
+        return OVQA_OK;
+    }
+    const size_t smem = (size_t)N * sizeof(float);
     if (hidden_dtype == OVQA_F32)
         attr_pool_fwd_kernel<float><<<(unsigned)B, kPoolThreads, smem, st>>>((const float*)hidden, w2, b2, x, pooled, probs, (int)N, (int)Dh, (int)D);
     else
@@ -153,6 +391,18 @@ extern "C" int ovqa_attr_pool_bwd(const float* dpooled, const void* hidden, cons
     const size_t smem = (size_t)N * sizeof(float);
     const float inv_keep = 1.0f / (1.0f - dropout_p);
     cudaStream_t st = (cudaStream_t)stream;
+    const int hn = hidden_dtype == OVQA_F32 ? 4 : 8;
+    const size_t smem_v = (size_t)(2 * ((N + 3) & ~3) + kPoolThreads * 8) * sizeof(float);
+    if (D % 4 == 0 && Dh % hn == 0 && al16(hidden) && al16(w2) && al16(x) && al16(dpooled) && al16(dpre) && (!dx || al16(dx)) && smem_v <= 48 * 1024) {
+        if (hidden_dtype == OVQA_F32)
+            attr_pool_bwd_vec_kernel<float><<<(unsigned)B, kPoolThreads, smem_v, st>>>(dpooled, (const float*)hidden, w2, x, probs, dx, (float*)dpre, dw2, db2,
+                                                                                     (int)N, (int)Dh, (int)D, inv_keep);
+        else
+            attr_pool_bwd_vec_kernel<__nv_bfloat16><<<(unsigned)B, kPoolThreads, smem_v, st>>>(dpooled, (const __nv_bfloat16*)hidden, w2, x, probs, dx,
+                                                                                             (__nv_bfloat16*)dpre, dw2, db2, (int)N, (int)Dh, (int)D, inv_keep);
+        OVQA_LAUNCH_OK();
+        return OVQA_OK;
+    }
     if (hidden_dtype == OVQA_F32)
         attr_pool_bwd_kernel<float><<<(unsigned)B, kPoolThreads, smem, st>>>(dpooled, (const float*)hidden, w2, x, probs, dx, (float*)dpre, dw2, db2, (int)N,
                                                                              (int)Dh, (int)D, inv_keep);

@@ -713,6 +713,63 @@ def pool_and_classify(model, vision_features, text_features, mode, log_softmax=F
     return torch.log_softmax(logits, dim=-1) if log_softmax else logits
 
 
+# ----------------------------------------------------------------------------- LSTM text embedding
+class _LstmFn(torch.autograd.Function):
+    """``nn.LSTM(batch_first=True)`` of one layer called without an initial state (text_embeddings.py:234,244): the input projection of all
+    steps is one tensor-core GEMM, the recurrence one cluster-resident kernel (``ovqa_lstm_fwd``: W_hh in registers, h exchanged through
+    distributed shared memory); backward: one recurrence kernel producing the gate pre-activation gradients, then the input gradient, both
+    weight gradients (split-K, operands read in place) and the bias gradient as GEMMs / a column sum over all steps."""
+
+    @staticmethod
+    def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, grad):
+        ctx.set_materialize_grads(False)
+        B, T, In = x.shape
+        H = w_hh.shape[1]
+        x2 = _operand(x, "bf16")
+        wih16, whh16 = weights.get([w_ih], torch.bfloat16), weights.get([w_hh], torch.bfloat16)
+        xg = ops.gemm(x2, wih16, bias=weights.get([b_ih], torch.float32) if b_ih is not None else None, out_dtype=torch.float32).view(B, T, 4 * H)
+        need_grad = grad and any(ctx.needs_input_grad)
+        y, y16, hprev16, gates16, c = ops.lstm_fwd(xg, whh16, weights.get([b_hh], torch.float32) if b_hh is not None else None, save=need_grad)
+        _attach_shadow(y, y16)
+        if need_grad:
+            ctx.save_for_backward(x2, wih16, whh16, hprev16, gates16, c)
+            ctx.has_b, ctx.dims = (b_ih is not None, b_hh is not None), (B, T, In, H)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        if dy is None:
+            return (None,) * 6
+        x2, wih16, whh16, hprev16, gates16, c = ctx.saved_tensors
+        B, T, In, H = ctx.dims
+        dg2 = ops.lstm_bwd(dy.float().contiguous(), whh16, gates16, c).view(B * T, 4 * H)
+        dw_ih, dw_hh, db = _zero_slab(dy.device, (4 * H, In), (4 * H, H), (4 * H,))
+        dx = ops.gemm(dg2, wih16, b_op="T", out_dtype=torch.float32).view(B, T, In) if ctx.needs_input_grad[0] else None
+        if ctx.needs_input_grad[1]:
+            _wgrad(dg2, x2, out=dw_ih)
+        if ctx.needs_input_grad[2]:
+            _wgrad(dg2, hprev16.view(B * T, H), out=dw_hh)
+        if (ctx.has_b[0] and ctx.needs_input_grad[3]) or (ctx.has_b[1] and ctx.needs_input_grad[4]):
+            ops.colsum(dg2, out=db, accumulate=True)
+        return (dx, dw_ih if ctx.needs_input_grad[1] else None, dw_hh if ctx.needs_input_grad[2] else None,
+                db if ctx.has_b[0] and ctx.needs_input_grad[3] else None, db.clone() if ctx.has_b[1] and ctx.needs_input_grad[4] else None, None)
+
+
+def lstm_supported(module, x, mode) -> bool:
+    """Whether :func:`lstm` can run ``module`` (an ``nn.LSTM``) on ``x``: bf16 compute mode, CUDA, one unidirectional batch-first layer without
+    projection, hidden size one of the kernel's (``ovqa_lstm_supported``), input width a multiple of 8 (TMA rows of the projection GEMM)."""
+    return (mode == "bf16" and x.is_cuda and x.dim() == 3 and isinstance(module, torch.nn.LSTM) and module.num_layers == 1 and not module.bidirectional
+            and module.batch_first and getattr(module, "proj_size", 0) == 0 and module.input_size % 8 == 0 and ops.lstm_supported(module.hidden_size))
+
+
+def lstm(module, x):
+    """``module(x)[0]`` for a supported ``nn.LSTM`` (see :func:`lstm_supported`), through the library; parameters are read from ``module`` so
+    checkpoints and optimisers see the reference's names (weight_ih_l0, weight_hh_l0, bias_ih_l0, bias_hh_l0)."""
+    b_ih = getattr(module, "bias_ih_l0", None) if module.bias else None
+    b_hh = getattr(module, "bias_hh_l0", None) if module.bias else None
+    return _LstmFn.apply(x, module.weight_ih_l0, module.weight_hh_l0, b_ih, b_hh, torch.is_grad_enabled())
+
+
 # ----------------------------------------------------------------------------- stand-alone pieces (direct core calls)
 class _SdpaFn(torch.autograd.Function):
     """The attention core as a differentiable function of q, k, v, the geometry weights AND through both outputs: a direct caller may

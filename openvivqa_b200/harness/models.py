@@ -227,7 +227,10 @@ class LSTMTextEmbedding(nn.Module):
         padding_masks = generate_padding_mask(tokens, padding_idx=self.padding_idx)
         sequential_masks = generate_sequential_mask(tokens.shape[-1], tokens.device)
         features = self.dropout(self.proj(self.embedding(tokens)))
-        features, _ = self.lstm(features)
+        if Fn.lstm_supported(self.lstm, features, get_compute_dtype()):
+            features = Fn.lstm(self.lstm, features)          # cluster-resident recurrence kernel
+        else:
+            features, _ = self.lstm(features)                # fp32 parity mode / other hidden sizes: the library LSTM (cuDNN)
         return features, (padding_masks, sequential_masks)
 
 

@@ -91,6 +91,12 @@ def install(compute_dtype: str | None = None, verbose: bool = False):
         _saved.setdefault(("m4c", "models.mcan", "MCAN", "forward"), mcan_mod.MCAN.forward)
         mcan_mod.MCAN.forward = M.mcan_forward
         classes["models.mcan.MCAN.forward"] = M.mcan_forward
+    # LSTM text embedding (text_embeddings.py:222-246): the recurrence runs in the library's cluster-resident kernels
+    txt_mod = _maybe("models.modules.text_embeddings")
+    if txt_mod is not None and hasattr(txt_mod, "LSTMTextEmbedding"):
+        _saved.setdefault(("m4c", "models.modules.text_embeddings", "LSTMTextEmbedding", "forward"), txt_mod.LSTMTextEmbedding.forward)
+        txt_mod.LSTMTextEmbedding.forward = M.make_lstm_text_embedding_forward(txt_mod)
+        classes["models.modules.text_embeddings.LSTMTextEmbedding.forward"] = txt_mod.LSTMTextEmbedding.forward
     for name, mods in _REBIND.items():
         for modname in mods:
             mod = _maybe(modname)

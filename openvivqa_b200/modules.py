@@ -549,6 +549,25 @@ def mcan_forward(self, input_features):
     return Fn.pool_and_classify(self, vision_features, text_features, get_compute_dtype(), log_softmax=True)
 
 
+def make_lstm_text_embedding_forward(mod):
+    """``LSTMTextEmbedding.forward`` (models/modules/text_embeddings.py:236-246) with the recurrence through the library's LSTM kernels when
+    the compute dtype is bf16 and the hidden size is one the kernels are built for; bound over the reference's class by
+    ``install()``.  ``mod`` is the reference module (its own mask generators are used); parameters stay the ``nn.LSTM``'s."""
+    gen_pad, gen_seq = mod.generate_padding_mask, mod.generate_sequential_mask
+
+    def forward(self, tokens):
+        padding_masks = gen_pad(tokens, padding_idx=self.padding_idx).to(tokens.device)
+        sequential_masks = gen_seq(tokens.shape[-1]).to(tokens.device)
+        features = self.dropout(self.proj(self.embedding(tokens)))
+        if Fn.lstm_supported(self.lstm, features, get_compute_dtype()):
+            features = Fn.lstm(self.lstm, features)
+        else:
+            features, _ = self.lstm(features)
+        return features, (padding_masks, sequential_masks)
+
+    return forward
+
+
 class OcrPtrNet(nn.Module):
     """mmf_m4c.py:367-396: ``(Wq·dec + b)(Wk·ocr + b)ᵀ / √d_qk + mask``."""
 

@@ -438,6 +438,45 @@ def ptr_scores(q, k, mask, scores, col_offset: int, scale: float, mask_is_bool: 
     return scores
 
 
+def lstm_supported(H: int) -> bool:
+    """Hidden sizes the cluster-resident LSTM kernels are built for (``ovqa_lstm_supported``)."""
+    return bool(L.lib().ovqa_lstm_supported(int(H)))
+
+
+def lstm_fwd(xg: torch.Tensor, w_hh16: torch.Tensor, b_hh: Optional[torch.Tensor], save: bool = True):
+    """Recurrence of a single-layer batch-first LSTM with zero initial state (text_embeddings.py:234,244).  ``xg`` (B,L,4H) fp32 = the input
+    projection of every step (x W_ih^T + b_ih), ``w_hh16`` (4H,H) bf16, ``b_hh`` (4H) fp32 | None.  Returns (y (B,L,H) fp32, y16 (B,L,H) bf16,
+    hprev16 | None, gates16 | None, c | None): the last three are what :func:`lstm_bwd` and the weight-gradient GEMMs need."""
+    _need_cuda(xg, w_hh16, b_hh)
+    B, T, G = xg.shape
+    H = G // 4
+    if xg.dtype != torch.float32 or not xg.is_contiguous() or w_hh16.dtype != torch.bfloat16 or tuple(w_hh16.shape) != (4 * H, H) or not w_hh16.is_contiguous():
+        raise ValueError("lstm_fwd: xg (B,L,4H) fp32 contiguous, w_hh (4H,H) bf16 contiguous")
+    if b_hh is not None and (b_hh.dtype != torch.float32 or b_hh.numel() != 4 * H or not b_hh.is_contiguous()):
+        raise ValueError("lstm_fwd: b_hh must be contiguous fp32 [4H]")
+    dev = xg.device
+    y = torch.empty((B, T, H), device=dev, dtype=torch.float32)
+    y16 = torch.empty((B, T, H), device=dev, dtype=torch.bfloat16)
+    hprev16 = torch.empty((B, T, H), device=dev, dtype=torch.bfloat16) if save else None
+    gates16 = torch.empty((B, T, 4 * H), device=dev, dtype=torch.bfloat16) if save else None
+    c = torch.empty((B, T, H), device=dev, dtype=torch.float32) if save else None
+    if B > 0 and T > 0:
+        L.call("ovqa_lstm_fwd", _p(xg), _p(w_hh16), _p(b_hh), _p(y), _p(y16), _p(hprev16), _p(gates16), _p(c), B, T, H, _stream())
+    return y, y16, hprev16, gates16, c
+
+
+def lstm_bwd(dy: torch.Tensor, w_hh16: torch.Tensor, gates16: torch.Tensor, c: torch.Tensor) -> torch.Tensor:
+    """Backward of the recurrence: ``dy`` (B,L,H) fp32 -> gradient of the gate pre-activations (B,L,4H) bf16."""
+    _need_cuda(dy, w_hh16, gates16, c)
+    B, T, H = dy.shape
+    if dy.dtype != torch.float32 or not dy.is_contiguous() or gates16.shape != (B, T, 4 * H) or c.shape != (B, T, H):
+        raise ValueError("lstm_bwd: dy (B,L,H) fp32 contiguous; gates (B,L,4H) bf16 and c (B,L,H) fp32 as saved by lstm_fwd")
+    dgates16 = torch.empty((B, T, 4 * H), device=dy.device, dtype=torch.bfloat16)
+    if B > 0 and T > 0:
+        L.call("ovqa_lstm_bwd", _p(dy), _p(w_hh16), _p(gates16), _p(c), _p(dgates16), B, T, H, _stream())
+    return dgates16
+
+
 def attr_pool_fwd(hidden: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, x: torch.Tensor, save_probs: bool = True):
     """softmax-over-the-sequence pooling of ``x`` (B,N,D) fp32 by the scores ``hidden . w2 + b2`` (hidden (B,N,Dh) fp32 / bf16, the
     attribute-reduce MLP's first layer).  Returns (pooled (B,D) fp32, probs (B,N) fp32 | None)."""

@@ -117,6 +117,51 @@ def box_geometry_bias(geo, h):
     return geo_log_bias(geo, h)
 
 
+def lstm_supported(H):
+    return H in (128, 256, 512) or H % 4 == 0      # (the CPU restatement has no shape limits; small sizes keep the host-logic tests fast)
+
+
+def lstm_fwd(xg, w_hh16, b_hh, save=True):
+    B, T, G = xg.shape
+    H = G // 4
+    w = w_hh16.float()
+    h = xg.new_zeros(B, H)
+    c = xg.new_zeros(B, H)
+    ys, hp, gs, cs = [], [], [], []
+    for t in range(T):
+        hp.append(h.to(torch.bfloat16))
+        pre = xg[:, t] + h.to(torch.bfloat16).float() @ w.t() + (b_hh if b_hh is not None else 0.0)
+        i, f, g, o = pre.chunk(4, dim=-1)
+        i, f, g, o = torch.sigmoid(i), torch.sigmoid(f), torch.tanh(g), torch.sigmoid(o)
+        c = f * c + i * g
+        h = o * torch.tanh(c)
+        ys.append(h); gs.append(torch.cat((i, f, g, o), -1).to(torch.bfloat16)); cs.append(c)
+    y = torch.stack(ys, 1)
+    if not save:
+        return y, y.to(torch.bfloat16), None, None, None
+    return y, y.to(torch.bfloat16), torch.stack(hp, 1), torch.stack(gs, 1), torch.stack(cs, 1)
+
+
+def lstm_bwd(dy, w_hh16, gates16, c):
+    B, T, H = dy.shape
+    w = w_hh16.float()
+    dc_next = dy.new_zeros(B, H)
+    rec = dy.new_zeros(B, H)
+    out = [None] * T
+    for t in range(T - 1, -1, -1):
+        i, f, g, o = gates16[:, t].float().chunk(4, dim=-1)
+        ct = c[:, t]
+        cp = c[:, t - 1] if t > 0 else torch.zeros_like(ct)
+        dh = dy[:, t] + rec
+        tc = torch.tanh(ct)
+        dc = dc_next + dh * o * (1 - tc * tc)
+        dc_next = dc * f
+        da = torch.cat((dc * g * i * (1 - i), dc * cp * f * (1 - f), dc * i * (1 - g * g), dh * tc * o * (1 - o)), -1).to(torch.bfloat16)
+        out[t] = da
+        rec = da.float() @ w
+    return torch.stack(out, 1)
+
+
 def attr_pool_fwd(hidden, w2, b2, x, save_probs=True):
     logits = hidden.float() @ w2.reshape(-1).float() + b2.reshape(-1).float()
     p = torch.softmax(logits, dim=1)
@@ -361,7 +406,7 @@ def pwff_infer_block(plan, x, *, d_ff, eps=1e-5):
 
 
 OPS = ("gemm", "sdpa_fwd", "sdpa_bwd", "layernorm_fwd", "layernorm_bwd", "cast_rows_padmask", "mul_to_bf16", "to_bf16", "to_f32", "colsum",
-       "add", "dropout_apply", "dropout_keep_mask", "stage_many", "advance_u64", "box_geometry_bias", "geo_bias", "geo_bias_bwd", "attr_pool_fwd", "attr_pool_bwd", "ptr_scores", "ptr_scores_bwd",
+       "add", "dropout_apply", "dropout_keep_mask", "stage_many", "advance_u64", "box_geometry_bias", "geo_bias", "geo_bias_bwd", "attr_pool_fwd", "attr_pool_bwd", "lstm_supported", "lstm_fwd", "lstm_bwd", "ptr_scores", "ptr_scores_bwd",
        "prev_pred_embed", "greedy_step", "topk_rows", "mha_decode_step", "pwff_infer")
 
 

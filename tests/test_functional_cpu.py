@@ -328,3 +328,31 @@ def test_probability_dropout_block_matches_the_explicit_composition(cpu_ops):
     _close(xi.grad, xr.grad)
     for k in params:
         _close(pi[k].grad, pr[k].grad)
+
+
+def test_lstm_function_matches_nn_lstm_autograd(cpu_ops):
+    """SURVEY 8f rank 4 (text_embeddings.py:234,244): the LSTM autograd function on the emulated library — which tensors are saved, the gate
+    pre-activation gradients, dx / dW_ih / dW_hh (h_{t-1} operand) / both bias gradients — against autograd of nn.LSTM itself."""
+    torch.manual_seed(1)
+    B, L, In, Hd = 4, 6, 16, 24
+    ref = torch.nn.LSTM(In, Hd, batch_first=True)
+    m = torch.nn.LSTM(In, Hd, batch_first=True)
+    m.load_state_dict(ref.state_dict())
+    x = torch.randn(B, L, In)
+    xr, xi = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    yr, _ = ref(xr)
+    w = torch.randn(yr.shape, generator=torch.Generator().manual_seed(2))
+    (yr * w).sum().backward()
+    y = Fn.lstm(m, xi)
+    (y * w).sum().backward()
+
+    def rel(a, b):
+        return float((a - b).norm() / b.norm().clamp_min(1e-12))
+    assert rel(y.detach(), yr.detach()) < 2e-2          # bf16 operands (x, W_ih, W_hh, h_{t-1}) with fp32 accumulation and state
+    assert rel(xi.grad, xr.grad) < 3e-2
+    for (k, p), (_, pr) in zip(m.named_parameters(), ref.named_parameters()):
+        assert p.grad is not None, k
+        assert rel(p.grad, pr.grad) < 3e-2, (k, rel(p.grad, pr.grad))
+    assert getattr(y, "_ovqa_bf16", None) is not None      # the bf16 shadow the first encoder block consumes
+    with torch.no_grad():
+        assert torch.equal(Fn.lstm(m, xi), y.detach())
