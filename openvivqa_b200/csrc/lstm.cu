@@ -321,16 +321,30 @@ lstm_bwd_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ 
                         rec[0] += v.x; rec[1] += v.y; rec[2] += v.z; rec[3] += v.w;
                     }
                 }
+                // all of the four cells' operands are requested before the first is used (samples beyond B: clamped, result discarded)
+                float dyv[4], ctv[4], cpv[4];
+                unsigned short gr[4][4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int s = min(b0 + sl + j, B - 1);
+                    const size_t row = (size_t)s * L + t;
+                    dyv[j] = __ldg(dy + row * H + ug);
+                    ctv[j] = __ldg(c_all + row * H + ug);
+                    cpv[j] = t > 0 ? __ldg(c_all + (row - 1) * H + ug) : 0.f;
+                    const unsigned short* gp = reinterpret_cast<const unsigned short*>(gates16) + row * (4 * H) + ug;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) gr[j][g] = __ldg(gp + g * H);
+                }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int s = b0 + sl + j;
                     float dai = 0.f, daf = 0.f, dag = 0.f, dao = 0.f;
                     if (s < B) {
                         const size_t row = (size_t)s * L + t;
-                        const float dh = __ldg(dy + row * H + ug) + rec[j];
-                        const __nv_bfloat16* gp = gates16 + row * (4 * H) + ug;
-                        const float gi = __bfloat162float(gp[0]), gf = __bfloat162float(gp[H]), gg = __bfloat162float(gp[2 * H]), go = __bfloat162float(gp[3 * H]);
-                        const float ct = __ldg(c_all + row * H + ug), cp = t > 0 ? __ldg(c_all + (row - 1) * H + ug) : 0.f;
+                        const float dh = dyv[j] + rec[j];
+                        const float gi = __uint_as_float((uint32_t)gr[j][0] << 16), gf = __uint_as_float((uint32_t)gr[j][1] << 16),
+                                    gg = __uint_as_float((uint32_t)gr[j][2] << 16), go = __uint_as_float((uint32_t)gr[j][3] << 16);
+                        const float ct = ctv[j], cp = cpv[j];
                         const float tc = tanh_f(ct);
                         const float dc = fmaf(dh * go, 1.0f - tc * tc, dc_next[p][j]);
                         dc_next[p][j] = dc * gf;
@@ -363,14 +377,16 @@ lstm_bwd_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ 
                 for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
                     for (int c = 0; c < 4; ++c) acc[mt][nt][c] = 0.f;
+            uint32_t bfr[2][4];
+            const uint32_t bsrc = dgb_u32 + ld_off + (uint32_t)(16 * nh * kGRow * 2);
+            ldmatrix_x4(bsrc, bfr[0][0], bfr[0][1], bfr[0][2], bfr[0][3]);
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
-                uint32_t b0r, b1r, b2r, b3r;
-                ldmatrix_x4(dgb_u32 + ld_off + (uint32_t)(16 * nh * kGRow * 2) + (uint32_t)ks * 32u, b0r, b1r, b2r, b3r);
+                if (ks + 1 < KS) ldmatrix_x4(bsrc + (uint32_t)(ks + 1) * 32u, bfr[(ks + 1) & 1][0], bfr[(ks + 1) & 1][1], bfr[(ks + 1) & 1][2], bfr[(ks + 1) & 1][3]);
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
-                    mma_bf16_16816(acc[mt][0], afr[mt][ks], b0r, b1r);
-                    mma_bf16_16816(acc[mt][1], afr[mt][ks], b2r, b3r);
+                    mma_bf16_16816(acc[mt][0], afr[mt][ks], bfr[ks & 1][0], bfr[ks & 1][1]);
+                    mma_bf16_16816(acc[mt][1], afr[mt][ks], bfr[ks & 1][2], bfr[ks & 1][3]);
                 }
             }
 #pragma unroll
