@@ -31,7 +31,7 @@ constexpr int kTileBytes = 128 * 128;     // 128 rows x 128 B
 constexpr int kStageBytes = 3 * kTileBytes;            // Q, K, V
 constexpr int kPBytes = 2 * kTileBytes;                // P: two 64-key blocks of 128 rows x 128 B (forward: aliased onto the stage's dead Q | K tiles)
 constexpr int kFwdThreads = 64 + 2 * 128;
-constexpr int kFwdSmem = kLoadStages * kStageBytes + 2 * 128 * 4 /*mask rows*/ + 256 /*barriers*/ + 1024 /*align*/;   // 2 CTAs per SM
+constexpr int kFwdSmem = kLoadStages * kStageBytes + 2 * 128 * 4 /*mask rows*/ + 2 * 128 * 4 /*raw mask landing rows*/ + 256 /*barriers*/ + 1024 /*align*/;   // 2 CTAs per SM
 constexpr int kFwdTmemCols = 256;         // group g: S in [128 g, +128), O aliased onto the first 64 of them (S is dead once P is written)
 constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
 
@@ -56,7 +56,8 @@ sdpa_fwd_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* s_load = smem;                                          // [kLoadStages][Q | K | V];  P of the stage's item overwrites Q | K
     float* s_mask = reinterpret_cast<float*>(smem + kLoadStages * kStageBytes);   // [2 groups][128]  (mask * log2 e; -inf beyond Lk)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_mask + 2 * 128);
+    float* s_mraw = s_mask + 2 * 128;                                             // [2 groups][128]  next item's raw mask row (cp.async landing zone)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_mraw + 2 * 128);
     uint64_t* load_full = bars;                     // [kLoadStages]  TMA -> MMA
     uint64_t* load_empty = load_full + kLoadStages; // [kLoadStages]  MMA -> TMA
     uint64_t* s_full = load_empty + kLoadStages;    // [2]            MMA -> softmax group (S ready)
@@ -101,6 +102,14 @@ sdpa_fwd_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 tma_load_2d(st, &map_q, load_full + ls, hd * kD, b * Lq);
                 tma_load_2d(st + kTileBytes, &map_k, load_full + ls, hd * kD, b * Lk);
                 tma_load_2d(st + 2 * kTileBytes, &map_v, load_full + ls, hd * kD, b * Lk);
+                // the stage of the item after this one frees only when ITS predecessor's P V has retired: its tiles travel DRAM -> L2 meanwhile
+                const int nx = item + 2 * (int)gridDim.x;
+                if (nx < n_items) {
+                    const int b2 = nx / H, h2 = nx % H;
+                    tma_prefetch_2d(&map_q, h2 * kD, b2 * Lq);
+                    tma_prefetch_2d(&map_k, h2 * kD, b2 * Lk);
+                    tma_prefetch_2d(&map_v, h2 * kD, b2 * Lk);
+                }
             }
         }
     } else if (warp == 1) {
@@ -151,19 +160,27 @@ sdpa_fwd_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         const float sc2 = a.scale * kLog2e;
         const int nch = nk16 / 16;
         int u = 0;
-        // mask value of key `tid_g` for an item (raw; -inf beyond Lk): fetched one item ahead so its DRAM latency is off the critical path
-        auto mask_of = [&](int item) -> float {
-            if (tid_g >= Lk || item >= n_items) return -INFINITY;
-            return a.mask.ptr ? __ldg(a.mask.ptr + (int64_t)(item / H) * a.mask.sb + (int64_t)(item % H) * a.mask.sh + tid_g) : 0.0f;
+        // mask value of key `tid_g` for an item (raw; -inf beyond Lk): fetched one item ahead so its DRAM latency is off the critical path —
+        // by cp.async into the thread's own slot of a landing row, not into a register (the register was spilled across the item and the
+        // spill store waited for the load: 5 % of the stall samples, profiles/r02_kernels_ncu.md)
+        float* mraw = s_mraw + g * 128 + tid_g;
+        auto mask_fetch = [&](int item) {
+            if (tid_g < Lk && item < n_items && a.mask.ptr)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(mraw)),
+                             "l"(a.mask.ptr + (int64_t)(item / H) * a.mask.sb + (int64_t)(item % H) * a.mask.sh + tid_g) : "memory");
+            else *mraw = (tid_g >= Lk || item >= n_items) ? -INFINITY : 0.0f;
+            asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        float mv_next = mask_of(blockIdx.x + g * gridDim.x);
+        mask_fetch(blockIdx.x + g * gridDim.x);
         for (int item = blockIdx.x + g * gridDim.x; item < n_items; item += 2 * gridDim.x, ++u) {
             const int b = item / H, hd = item % H;
             const uint32_t par = (uint32_t)u & 1u;
             // per-key mask row of this (sample, head), pre-multiplied by log2 e; -inf beyond Lk
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            const float mv_cur = *mraw;
             named_bar_sync(1 + g, 128);               // the previous item's readers are done
-            mrow[tid_g] = mv_next * kLog2e;
-            mv_next = mask_of(item + 2 * gridDim.x);
+            mrow[tid_g] = mv_cur * kLog2e;
+            mask_fetch(item + 2 * gridDim.x);
             named_bar_sync(1 + g, 128);
             mbar_wait(s_full + g, par);
             tcgen05_fence_after();
@@ -222,26 +239,32 @@ sdpa_fwd_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             mbar_arrive(p_full + g);
             mbar_wait(o_full + g, par);
             tcgen05_fence_after();
-            uint32_t o[kD];
-            tmem_ld_32x32b_x32(t_o, o);
-            tmem_ld_32x32b_x32(t_o + 32u, o + 32);
-            tmem_ld_wait();
-            tcgen05_fence_before();
-            mbar_arrive(acc_empty + g);               // S / O columns and the P buffer may be overwritten by item u+1 of this group
-            if (live) {
-                const float inv = 1.0f / l;
-                __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.out) + ((int64_t)b * Lq + row) * a.ldo + (int64_t)hd * kD;
+            // O in two halves of 32 columns (64 accumulator registers at once were the kernel's register peak: it spilled under the 96 that two
+            // resident CTAs leave)
+            const float inv = 1.0f / l;
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.out) + ((int64_t)b * Lq + row) * a.ldo + (int64_t)hd * kD;
 #pragma unroll
-                for (int c = 0; c < kD / 8; ++c) {
-                    uint4 w;
-                    w.x = pack_bf16x2(__uint_as_float(o[8 * c]) * inv, __uint_as_float(o[8 * c + 1]) * inv);
-                    w.y = pack_bf16x2(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv);
-                    w.z = pack_bf16x2(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv);
-                    w.w = pack_bf16x2(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv);
-                    *reinterpret_cast<uint4*>(op + 8 * c) = w;
+            for (int hf = 0; hf < 2; ++hf) {
+                uint32_t o[32];
+                tmem_ld_32x32b_x32(t_o + (uint32_t)(32 * hf), o);
+                tmem_ld_wait();
+                if (hf == 1) {
+                    tcgen05_fence_before();
+                    mbar_arrive(acc_empty + g);       // S / O columns and the P buffer may be overwritten by item u+1 of this group
                 }
-                if (a.lse) a.lse[((int64_t)b * H + hd) * Lq + row] = fmaf(mx, kLn2, __logf(l));
+                if (live) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint4 w;
+                        w.x = pack_bf16x2(__uint_as_float(o[8 * c]) * inv, __uint_as_float(o[8 * c + 1]) * inv);
+                        w.y = pack_bf16x2(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv);
+                        w.z = pack_bf16x2(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv);
+                        w.w = pack_bf16x2(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv);
+                        *reinterpret_cast<uint4*>(op + 32 * hf + 8 * c) = w;
+                    }
+                }
             }
+            if (live && a.lse) a.lse[((int64_t)b * H + hd) * Lq + row] = fmaf(mx, kLn2, __logf(l));
         }
     }
     tcgen05_fence_before();
@@ -329,6 +352,14 @@ sdpa_fwd_tc5w_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_co
                 tma_load_2d(st + k1_off, &map_k1, load_full + ls, c1, krow);
                 tma_load_2d(st + v0_off, &map_v0, load_full + ls, c0, krow);
                 tma_load_2d(st + v1_off, &map_v1, load_full + ls, c1, krow);
+                const int nx = item + 2 * (int)gridDim.x;            // (see sdpa_fwd_tc5_kernel: the item two ahead waits for a stage; pull it into L2)
+                if (nx < n_items) {
+                    const int mt2 = nx % n_mt, bh2 = nx / n_mt, b2 = bh2 / H, h2 = bh2 % H;
+                    const int qrow2 = b2 * Lq + mt2 * 128, krow2 = b2 * Lk, d0 = h2 * D, d1 = h2 * D + 64;
+                    tma_prefetch_2d(&map_q0, d0, qrow2); tma_prefetch_2d(&map_q1, d1, qrow2);
+                    tma_prefetch_2d(&map_k0, d0, krow2); tma_prefetch_2d(&map_k1, d1, krow2);
+                    tma_prefetch_2d(&map_v0, d0, krow2); tma_prefetch_2d(&map_v1, d1, krow2);
+                }
             }
         }
     } else if (warp == 1) {
@@ -427,17 +458,25 @@ sdpa_fwd_tc5w_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_co
             const int nmine = (nch - half + 1) / 2;
             uint32_t ra[16], rb[16];
             float mx = -INFINITY;
+            // (two chunks per trip of a rolled loop: fully unrolled, the two passes were ~5 600 SASS lines and a quarter of the stall samples
+            // were instruction-cache misses — profiles/r02_kernels_ncu.md)
             if (nmine > 0) tmem_ld_32x32b_x16(t_s + (uint32_t)(16 * half), ra);
+            auto max_of = [&](const uint32_t (&r)[16], int c) {
+                float v[16];
+                scaled(r, c, v);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if (i < nmine) {
-                    const int c = 2 * i + half;
+                for (int j = 0; j < 16; j += 4) mx = fmaxf(fmaxf(mx, fmaxf(v[j], v[j + 1])), fmaxf(v[j + 2], v[j + 3]));
+            };
+#pragma unroll 1
+            for (int i = 0; i < nmine; i += 2) {
+                const int c = 2 * i + half;
+                tmem_ld_wait();
+                if (i + 1 < nmine) tmem_ld_32x32b_x16(t_s + (uint32_t)(16 * (c + 2)), rb);
+                max_of(ra, c);
+                if (i + 1 < nmine) {
                     tmem_ld_wait();
-                    if (i + 1 < nmine) tmem_ld_32x32b_x16(t_s + (uint32_t)(16 * (c + 2)), (i & 1) ? ra : rb);
-                    float v[16];
-                    scaled((i & 1) ? rb : ra, c, v);
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4) mx = fmaxf(fmaxf(mx, fmaxf(v[j], v[j + 1])), fmaxf(v[j + 2], v[j + 3]));
+                    if (i + 2 < nmine) tmem_ld_32x32b_x16(t_s + (uint32_t)(16 * (c + 4)), ra);
+                    max_of(rb, c + 2);
                 }
             }
             red_max[half * 128 + row] = mx;
@@ -447,24 +486,30 @@ sdpa_fwd_tc5w_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_co
             const int qi = mt * 128 + row;
             const bool live = qi < Lq;
             if (nmine > 0) tmem_ld_32x32b_x16(t_s + (uint32_t)(16 * half), ra);
+            auto probs_of = [&](const uint32_t (&r)[16], int c) {
+                float v[16];
+                scaled(r, c, v);
+                uint32_t pk[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if (i < nmine) {
-                    const int c = 2 * i + half;
+                for (int j = 0; j < 8; ++j) {
+                    const float p0 = ex2_approx(v[2 * j] - mx), p1 = ex2_approx(v[2 * j + 1] - mx);
+                    l += p0 + p1;
+                    pk[j] = live ? pack_bf16x2(p0, p1) : 0u;
+                }
+                const uint32_t blk = p_row + (uint32_t)(c >> 2) * kTileBytes;
+                sts128u(blk + ((((uint32_t)(2 * c) & 7u) ^ p_x) << 4), pk[0], pk[1], pk[2], pk[3]);
+                sts128u(blk + ((((uint32_t)(2 * c + 1) & 7u) ^ p_x) << 4), pk[4], pk[5], pk[6], pk[7]);
+            };
+#pragma unroll 1
+            for (int i = 0; i < nmine; i += 2) {
+                const int c = 2 * i + half;
+                tmem_ld_wait();
+                if (i + 1 < nmine) tmem_ld_32x32b_x16(t_s + (uint32_t)(16 * (c + 2)), rb);
+                probs_of(ra, c);
+                if (i + 1 < nmine) {
                     tmem_ld_wait();
-                    if (i + 1 < nmine) tmem_ld_32x32b_x16(t_s + (uint32_t)(16 * (c + 2)), (i & 1) ? ra : rb);
-                    float v[16];
-                    scaled((i & 1) ? rb : ra, c, v);
-                    uint32_t pk[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float p0 = ex2_approx(v[2 * j] - mx), p1 = ex2_approx(v[2 * j + 1] - mx);
-                        l += p0 + p1;
-                        pk[j] = live ? pack_bf16x2(p0, p1) : 0u;
-                    }
-                    const uint32_t blk = p_row + (uint32_t)(c >> 2) * kTileBytes;
-                    sts128u(blk + ((((uint32_t)(2 * c) & 7u) ^ p_x) << 4), pk[0], pk[1], pk[2], pk[3]);
-                    sts128u(blk + ((((uint32_t)(2 * c + 1) & 7u) ^ p_x) << 4), pk[4], pk[5], pk[6], pk[7]);
+                    if (i + 2 < nmine) tmem_ld_32x32b_x16(t_s + (uint32_t)(16 * (c + 4)), ra);
+                    probs_of(rb, c + 2);
                 }
             }
             red_sum[half * 128 + row] = l;            // (visible to the partner after the p_full -> o_full barrier chain: release / acquire)
@@ -606,6 +651,12 @@ sdpa_bwd_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 tma_load_2d(st + kTileBytes, &map_do, load_full + ls, hd * kD, b * Lq);
                 tma_load_2d(st + 2 * kTileBytes, &map_k, load_full + ls, hd * kD, b * Lk);
                 tma_load_2d(st + 3 * kTileBytes, &map_v, load_full + ls, hd * kD, b * Lk);
+                const int nx = item + kBwdStages * (int)gridDim.x;   // the item that will wait for this stage: DRAM -> L2 while it waits
+                if (nx < n_items) {
+                    const int b2 = nx / H, h2 = nx % H;
+                    tma_prefetch_2d(&map_q, h2 * kD, b2 * Lq); tma_prefetch_2d(&map_do, h2 * kD, b2 * Lq);
+                    tma_prefetch_2d(&map_k, h2 * kD, b2 * Lk); tma_prefetch_2d(&map_v, h2 * kD, b2 * Lk);
+                }
             }
         }
     } else if (warp == 1) {

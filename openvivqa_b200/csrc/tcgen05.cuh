@@ -49,6 +49,11 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// tile -> L2 only (no shared-memory destination, no barrier): a producer that has to wait for its stage to free pulls the NEXT tile's bytes
+// from DRAM in the meantime, so the load that follows is an L2 hit
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
+}
 // shared -> global tile store / fp32 add-reduction by the TMA unit (bulk async-group completion: commit + wait by the issuing thread)
 // (shared-memory operands as 32-bit shared-window addresses)
 __device__ __forceinline__ void tma_store_2d_u32(const CUtensorMap* map, uint32_t src, int c0, int c1) {
