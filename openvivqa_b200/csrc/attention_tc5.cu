@@ -606,11 +606,14 @@ sdpa_bwd_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_delta + 2 * 2 * 128);
     uint64_t* load_full = bars;                     // [2]  TMA -> MMA (and phase A)
     uint64_t* load_empty = load_full + kBwdStages;  // [2]  MMA -> TMA
-    uint64_t* sdp_full = load_empty + kBwdStages;   // MMA -> phase A: S and dP ready
-    uint64_t* pds_full = sdp_full + 1;              // phase A -> MMA: P and dS in smem, S / dP columns free   (256 arrivals)
-    uint64_t* out_full = pds_full + 1;              // MMA -> phase B (dV, dK, dQ ready) and -> phase A (P / dS tiles no longer read)
-    uint64_t* out_free = out_full + 1;              // phase B -> MMA: dV / dK / dQ columns drained             (128 arrivals)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(out_free + 1);
+    // Tensor memory is two REGIONS of 256 columns; item `it` lives in region it & 1: S | dP while phase A works on it, then dV | dK | dQ on
+    // top of them (dead once P and dS are in shared memory).  So S / dP of item it + 1 are issued — and usually complete — while phase A is
+    // still on item it: phase A never waits for the tensor pipe between items (it did for ~15 % of an item with one S | dP buffer).
+    uint64_t* sdp_full = load_empty + kBwdStages;   // [2] MMA -> phase A: S and dP of the region's item ready
+    uint64_t* pds_full = sdp_full + 2;              // phase A -> MMA: P and dS in smem, S / dP columns free   (256 arrivals)
+    uint64_t* out_full = pds_full + 1;              // [2] MMA -> phase B (dV, dK, dQ ready) and -> phase A (P / dS tiles no longer read)
+    uint64_t* out_free = out_full + 2;              // [2] phase B -> MMA: the region's dV / dK / dQ columns drained   (128 arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(out_free + 2);
 
     const SdpaArgs& a = args.a;
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -624,7 +627,8 @@ sdpa_bwd_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_k)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_v)) : "memory");
         for (int i = 0; i < kBwdStages; ++i) { mbar_init(load_full + i, 1); mbar_init(load_empty + i, 1); }
-        mbar_init(sdp_full, 1); mbar_init(pds_full, kBwdAThreads); mbar_init(out_full, 1); mbar_init(out_free, 128);
+        for (int i = 0; i < 2; ++i) { mbar_init(sdp_full + i, 1); mbar_init(out_full + i, 1); mbar_init(out_free + i, 128); }
+        mbar_init(pds_full, kBwdAThreads);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -635,7 +639,7 @@ sdpa_bwd_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    constexpr uint32_t kColS = 0, kColDP = 128, kColDV = 256, kColDK = 320, kColDQ = 384;
+    constexpr uint32_t kRegion = 256, kColS = 0, kColDP = 128, kColDV = 0, kColDK = 64, kColDQ = 128;      // column offsets inside a region
 
     if (warp == 0) {
         if (lane == 0) {
@@ -666,46 +670,50 @@ sdpa_bwd_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             const uint32_t idesc_q = make_idesc(128, kD, false, true);         // dQ: A K-major, B MN-major
             auto issue_sdp = [&](int it) {
                 const int ls = it % kBwdStages;
+                const uint32_t reg = tmem_base + (uint32_t)(it & 1) * kRegion;
                 mbar_wait(load_full + ls, (uint32_t)(it / kBwdStages) & 1u);
                 tcgen05_fence_after();
                 const uint32_t q_addr = smem_u32(s_load + ls * kBwdStageBytes), do_addr = q_addr + kTileBytes, k_addr = q_addr + 2 * kTileBytes,
                                v_addr = q_addr + 3 * kTileBytes;
 #pragma unroll
                 for (int kk = 0; kk < kD / 16; ++kk)
-                    tcgen05_mma_bf16(tmem_base + kColS, make_smem_desc(q_addr + kk * 32, 16, 1024), make_smem_desc(k_addr + kk * 32, 16, 1024), idesc_s, kk > 0 ? 1u : 0u);
+                    tcgen05_mma_bf16(reg + kColS, make_smem_desc(q_addr + kk * 32, 16, 1024), make_smem_desc(k_addr + kk * 32, 16, 1024), idesc_s, kk > 0 ? 1u : 0u);
 #pragma unroll
                 for (int kk = 0; kk < kD / 16; ++kk)
-                    tcgen05_mma_bf16(tmem_base + kColDP, make_smem_desc(do_addr + kk * 32, 16, 1024), make_smem_desc(v_addr + kk * 32, 16, 1024), idesc_s, kk > 0 ? 1u : 0u);
-                tcgen05_commit(sdp_full);
+                    tcgen05_mma_bf16(reg + kColDP, make_smem_desc(do_addr + kk * 32, 16, 1024), make_smem_desc(v_addr + kk * 32, 16, 1024), idesc_s, kk > 0 ? 1u : 0u);
+                tcgen05_commit(sdp_full + (it & 1));
             };
             if (my_items > 0) issue_sdp(0);
+            if (my_items > 1) issue_sdp(1);
             for (int it = 0; it < my_items; ++it) {
                 const int ls = it % kBwdStages;
-                const uint32_t par = (uint32_t)it & 1u;
-                mbar_wait(pds_full, par);                 // P(it), dS(it) written; S / dP columns consumed
-                if (it + 1 < my_items) issue_sdp(it + 1);
-                mbar_wait(out_free, par ^ 1u);            // dV / dK / dQ of item it-1 drained
+                const uint32_t reg = tmem_base + (uint32_t)(it & 1) * kRegion;
+                mbar_wait(pds_full, (uint32_t)it & 1u);   // P(it), dS(it) written; S / dP columns of the region consumed
                 tcgen05_fence_after();
                 const uint32_t q_addr = smem_u32(s_load + ls * kBwdStageBytes), do_addr = q_addr + kTileBytes, k_addr = q_addr + 2 * kTileBytes;
                 const uint32_t p_addr = smem_u32(s_p), ds_addr = smem_u32(s_ds);
                 // dV[key, d] = sum_q P[q, key] dO[q, d]: A = P^T (MN-major: 64-key blocks kTileBytes apart, 16 queries = 2048 B), B = dO (MN-major)
                 for (int ks = 0; ks < nq16 / 16; ++ks)
-                    tcgen05_mma_bf16(tmem_base + kColDV, make_smem_desc(p_addr + ks * 2048, kTileBytes, 1024), make_smem_desc(do_addr + ks * 2048, 8192, 1024), idesc_t, ks > 0 ? 1u : 0u);
+                    tcgen05_mma_bf16(reg + kColDV, make_smem_desc(p_addr + ks * 2048, kTileBytes, 1024), make_smem_desc(do_addr + ks * 2048, 8192, 1024), idesc_t, ks > 0 ? 1u : 0u);
                 for (int ks = 0; ks < nq16 / 16; ++ks)
-                    tcgen05_mma_bf16(tmem_base + kColDK, make_smem_desc(ds_addr + ks * 2048, kTileBytes, 1024), make_smem_desc(q_addr + ks * 2048, 8192, 1024), idesc_t, ks > 0 ? 1u : 0u);
+                    tcgen05_mma_bf16(reg + kColDK, make_smem_desc(ds_addr + ks * 2048, kTileBytes, 1024), make_smem_desc(q_addr + ks * 2048, 8192, 1024), idesc_t, ks > 0 ? 1u : 0u);
                 // dQ[q, d] = sum_key dS[q, key] K[key, d]: A = dS (K-major), B = K (MN-major)
                 for (int ks = 0; ks < nk16 / 16; ++ks)
-                    tcgen05_mma_bf16(tmem_base + kColDQ, make_smem_desc(ds_addr + (ks >> 2) * kTileBytes + (ks & 3) * 32, 16, 1024),
+                    tcgen05_mma_bf16(reg + kColDQ, make_smem_desc(ds_addr + (ks >> 2) * kTileBytes + (ks & 3) * 32, 16, 1024),
                                      make_smem_desc(k_addr + ks * 2048, 8192, 1024), idesc_q, ks > 0 ? 1u : 0u);
-                tcgen05_commit(out_full);
+                tcgen05_commit(out_full + (it & 1));
                 tcgen05_commit(load_empty + ls);
+                if (it + 2 < my_items) {
+                    mbar_wait(out_free + (it & 1), (uint32_t)(it >> 1) & 1u);     // dV / dK / dQ of item `it` drained: the region takes S | dP of item it + 2
+                    issue_sdp(it + 2);
+                }
             }
         }
     } else if (warp < 2 + kBwdAThreads / 32) {
         // ---------------------------------------------------------------- phase A: two threads per query row
         const int quad = warp % 4, row = quad * 32 + lane, half = (warp - 2) / 4, tid_g = (warp - 2) * 32 + lane;
         const uint32_t mrow_u32 = smem_u32(s_mask);
-        const uint32_t t_s = tmem_base + ((uint32_t)(quad * 32) << 16) + kColS, t_dp = tmem_base + ((uint32_t)(quad * 32) << 16) + kColDP;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
         const uint32_t p_row = smem_u32(s_p) + (uint32_t)row * 128u, ds_row = smem_u32(s_ds) + (uint32_t)row * 128u, p_x = (uint32_t)(row & 7);
         const float sc2 = a.scale * kLog2e;
         const int nch = nk16 / 16;
@@ -719,14 +727,14 @@ sdpa_bwd_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         float mv_next = mask_of(blockIdx.x), lse_next = lse_of(blockIdx.x);
         for (int it = 0; it < my_items; ++it) {
             const int item = blockIdx.x + it * gridDim.x;
-            const uint32_t par = (uint32_t)it & 1u;
             named_bar_sync(1, kBwdAThreads);
             if (tid_g < 128) s_mask[tid_g] = mv_next * kLog2e;
             const float lse2 = lse_next * kLog2e;
             mv_next = mask_of(item + gridDim.x);
             lse_next = lse_of(item + gridDim.x);
             named_bar_sync(1, kBwdAThreads);
-            mbar_wait(sdp_full, par);
+            const uint32_t t_s = t_lane + (uint32_t)(it & 1) * kRegion + kColS, t_dp = t_lane + (uint32_t)(it & 1) * kRegion + kColDP;
+            mbar_wait(sdp_full + (it & 1), (uint32_t)(it >> 1) & 1u);
             tcgen05_fence_after();
             auto probs = [&](const uint32_t (&rs)[16], int ch, float (&pv)[16]) {       // P for keys [16 ch, +16)
 #pragma unroll
@@ -766,7 +774,7 @@ sdpa_bwd_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             named_bar_sync(2, kBwdAThreads);
             delta += dpart[(half ^ 1) * 128 + row];
             // the P / dS tiles are still being read by dV/dK/dQ of the previous item until out_full(it-1) fires
-            if (it > 0) mbar_wait(out_full, par ^ 1u);
+            if (it > 0) mbar_wait(out_full + ((it - 1) & 1), (uint32_t)((it - 1) >> 1) & 1u);
             // pass 2: P and dS = P (dP - delta) -> shared memory (bf16, [query][key], SWIZZLE_128B rows)
 #pragma unroll
             for (int kq = 0; kq < 4; ++kq) {
@@ -799,12 +807,13 @@ sdpa_bwd_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     } else {
         // ---------------------------------------------------------------- phase B: one thread per output row (key for dV, dK; query for dQ)
         const int quad = warp % 4, row = quad * 32 + lane;
-        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
+        const uint32_t t_row0 = tmem_base + ((uint32_t)(quad * 32) << 16);
         for (int it = 0; it < my_items; ++it) {
             const int item = blockIdx.x + it * gridDim.x;
             const int b = item / H, hd = item % H;
-            mbar_wait(out_full, (uint32_t)it & 1u);
+            mbar_wait(out_full + (it & 1), (uint32_t)(it >> 1) & 1u);
             tcgen05_fence_after();
+            const uint32_t t_row = t_row0 + (uint32_t)(it & 1) * kRegion;
             uint32_t r0[kD];
             tmem_ld_32x32b_x32(t_row + kColDV, r0); tmem_ld_32x32b_x32(t_row + kColDV + 32u, r0 + 32);
             tmem_ld_wait();
@@ -815,7 +824,7 @@ sdpa_bwd_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             tmem_ld_32x32b_x32(t_row + kColDQ, r0); tmem_ld_32x32b_x32(t_row + kColDQ + 32u, r0 + 32);
             tmem_ld_wait();
             tcgen05_fence_before();
-            mbar_arrive(out_free);
+            mbar_arrive(out_free + (it & 1));
             if (row < Lq) store_row64(reinterpret_cast<__nv_bfloat16*>(args.dq) + ((int64_t)b * Lq + row) * args.lddq + (int64_t)hd * kD, r0, a.scale);
         }
     }
