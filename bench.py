@@ -390,7 +390,14 @@ class GemmMeter:
                      greedy_step=lambda a, kw, out: (nbytes(a[0]), "greedy_step"),
                      # geometry bias: boxes in, (B,h,N,N) fp32 out (forward) / in (backward)
                      geo_bias=lambda a, kw, out: (nbytes(a[0].boxes) + nbytes(out if torch.is_tensor(out) else None), f"geo_bias {tuple(out.shape)}"),
-                     geo_bias_bwd=lambda a, kw, out: (nbytes(a[0].boxes) + nbytes(a[2]), f"geo_bias_bwd {tuple(a[2].shape)}"))
+                     geo_bias_bwd=lambda a, kw, out: (nbytes(a[0].boxes) + nbytes(a[2]), f"geo_bias_bwd {tuple(a[2].shape)}"),
+                     # LSTM recurrence (latency-bound by its 30 dependent steps, not by bytes: the GB/s column only says how little it moves):
+                     # xg in; y, y16 (+ hprev, gates, c when training) out  /  dy, gates, c in; dgates out
+                     lstm_fwd=lambda a, kw, out: (nbytes(a[0]) + nbytes(*[t for t in out if torch.is_tensor(t)]), f"lstm_fwd {tuple(out[0].shape)}"),
+                     lstm_bwd=lambda a, kw, out: (nbytes(a[0], a[2], a[3]) + nbytes(out), f"lstm_bwd {tuple(a[0].shape)}"),
+                     # attribute-reduce pooling: hidden + x in (pooled out is B x D)  /  + dx, dpre out
+                     attr_pool_fwd=lambda a, kw, out: (nbytes(a[0], a[3]), f"attr_pool_fwd {tuple(a[3].shape)}"),
+                     attr_pool_bwd=lambda a, kw, out: (nbytes(a[1], a[3]) + nbytes(*[t for t in out if torch.is_tensor(t)]), f"attr_pool_bwd {tuple(a[3].shape)}"))
         for name, fn_bytes in table.items():
             if not hasattr(ops, name):
                 continue
@@ -501,7 +508,7 @@ def rooflines(ctx, meter, meter_ms, meter_how, what):
                     peak_source=peaks["source"] + " (cuBLAS bf16 8192^3: `peak` = burst figure — the timed regions last well under a second at max clocks; "
                     "`frac_sustained` uses the seconds-long power-capped figure)",
                     traffic=traffic, launches=gm["launches"], avg_launch_us=gm["avg_us"], share_of_step=gm["total_ms"] / meter_ms,
-                    instrumented_ms_per_step=meter_ms, how=meter_how, by_gemm=gm["table"][:12])
+                    instrumented_ms_per_step=meter_ms, how=meter_how, by_gemm=gm["table"][:40])
     by_kernel, by_op = meter.summary_other(peaks["hbm_gbs"])
     att = None
     if "sdpa_fwd" in by_op:

@@ -3,7 +3,7 @@ import pytest
 import torch
 
 import openvivqa_b200 as ovqa
-from openvivqa_b200 import harness as H
+from openvivqa_b200 import functional as Fn, harness as H
 from oracle import cases as C
 from oracle import synth as S
 from oracle import ref_loader as RL
@@ -275,3 +275,34 @@ def test_reference_beam_search_runs_on_the_installed_drop_ins(monkeypatch, golde
     finally:
         ovqa.uninstall()
         ovqa.set_compute_dtype(previous_dtype)
+
+
+@pytest.mark.skipif(not RL.available(), reason="/root/reference not mounted")
+def test_install_rebinds_the_reference_lstm_text_embedding(cpu_ops, monkeypatch):
+    """``install()`` rebinds ``LSTMTextEmbedding.forward`` (text_embeddings.py:236-246) on the reference's own class; the
+    parameters stay the ``nn.LSTM``'s.  With the library emulated on CPU: fp32 mode keeps the stock LSTM (bit-identical to the reference's
+    forward), bf16 mode goes through ``Fn.lstm`` and stays within the bf16 path's tolerance; ``uninstall()`` restores the method."""
+    RL.load()
+    import models.modules.text_embeddings as T
+    stock = T.LSTMTextEmbedding.forward
+    cfg = RL.NS(D_EMBEDDING=24, D_MODEL=32, DROPOUT=0.0, WORD_EMBEDDING=None)
+    torch.manual_seed(0)
+    emb = T.LSTMTextEmbedding(cfg, H.StubVocab(50, 10)).eval()
+    tokens = torch.randint(1, 50, (3, 7))
+    tokens[0, 5:] = 0
+    ref, (pad_ref, seq_ref) = emb(tokens)
+    try:
+        ovqa.install(compute_dtype="fp32")
+        assert T.LSTMTextEmbedding.forward is not stock
+        out, (pad, seq) = emb(tokens)
+        assert torch.equal(out, ref) and torch.equal(pad, pad_ref) and torch.equal(seq, seq_ref)
+        # bf16 mode: the library path (here: its CPU restatement; `is_cuda` is the only gate that a CPU tensor cannot pass)
+        monkeypatch.setattr(Fn, "lstm_supported", lambda module, x, mode: mode == "bf16")
+        ovqa.set_compute_dtype("bf16")
+        out16, _ = emb(tokens)
+        assert float((out16 - ref).abs().max()) < 2e-2
+        assert set(emb.state_dict()) == {"embedding.weight", "proj.weight", "proj.bias", "lstm.weight_ih_l0", "lstm.weight_hh_l0", "lstm.bias_ih_l0", "lstm.bias_hh_l0"}
+    finally:
+        ovqa.set_compute_dtype("fp32")
+        ovqa.uninstall()
+    assert T.LSTMTextEmbedding.forward is stock
