@@ -210,11 +210,17 @@ lstm_fwd_kernel(const float* __restrict__ xg, const __nv_bfloat16* __restrict__ 
             if (tid == 0) lstm_mbar_expect_tx(hbar + ((t + 1) & 1), (uint32_t)(NB * H * 2));
             const uint32_t nxt = hbuf_u32 + (uint32_t)((t + 1) & 1) * (uint32_t)(NB * HROW * 2) + (uint32_t)(kUnits * r) * 2u;
             const uint32_t bar = hbar_u32 + (uint32_t)((t + 1) & 1) * 8u;
-            for (int idx = tid; idx < NB * 4 * CS; idx += kLstmThreads) {
-                const int ch = idx % (NB * 4), d = idx / (NB * 4), s = ch / 4, u8 = (ch % 4) * 8;
+            // thread = one 16-byte chunk (sample, 8 units) of the slice, read and packed once, stored to its share of the destinations
+            constexpr int CH = NB * 4, GROUPS = kLstmThreads / CH;      // NB = 32: two groups of 128 threads, NB = 48: one group of 192
+            static_assert(GROUPS >= 1, "one thread per chunk");
+            const int ch = tid % CH, grp = tid / CH;
+            if (grp < GROUPS) {
+                const int s = ch / 4, u8 = (ch % 4) * 8;
                 const float4 v0 = *reinterpret_cast<const float4*>(hst + s * kStRow + u8), v1 = *reinterpret_cast<const float4*>(hst + s * kStRow + u8 + 4);
-                st_async_v4(lstm_mapa(nxt + (uint32_t)(s * HROW + u8) * 2u, (uint32_t)d), pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w),
-                            pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w), lstm_mapa(bar, (uint32_t)d));
+                const uint32_t p0 = pack_bf16x2(v0.x, v0.y), p1 = pack_bf16x2(v0.z, v0.w), p2 = pack_bf16x2(v1.x, v1.y), p3 = pack_bf16x2(v1.z, v1.w);
+                const uint32_t dst = nxt + (uint32_t)(s * HROW + u8) * 2u;
+#pragma unroll
+                for (int d = grp; d < CS; d += GROUPS) st_async_v4(lstm_mapa(dst, (uint32_t)d), p0, p1, p2, p3, lstm_mapa(bar, (uint32_t)d));
             }
             load_xg(t + 1);
         }
