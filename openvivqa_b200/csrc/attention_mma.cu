@@ -100,6 +100,8 @@ __device__ __forceinline__ float quad_sum(float v) { v += __shfl_xor_sync(0xffff
 // absent it is staged as one float row with -inf beyond Lk, so the key-range predicate disappears as well.
 template <int D, int NWARPS, bool FULL>
 __global__ void __launch_bounds__(NWARPS * 32) sdpa_fwd_mma_kernel(SdpaArgs a) {
+    pdl_wait();          // programmatic dependent launch (common.cuh): nothing above touches global memory
+    pdl_trigger();
     extern __shared__ __align__(16) uint8_t smem_raw[];
     constexpr int P = D + PAD;
     const int Lq = (int)a.Lq, Lk = (int)a.Lk;
@@ -241,6 +243,8 @@ struct SdpaBwdMmaArgs {
 // from shared memory inside the chunk loops (ldmatrix is cheap) instead of living in registers across them.
 template <int D, int NWARPS, int MINB>
 __global__ void __launch_bounds__(NWARPS * 32, MINB) sdpa_bwd_mma_kernel(SdpaBwdMmaArgs a) {
+    pdl_wait();          // programmatic dependent launch (common.cuh): nothing above touches global memory
+    pdl_trigger();
     extern __shared__ __align__(16) uint8_t smem_raw[];
     constexpr int P = D + PAD;
     const SdpaArgs& f = a.f;
@@ -424,7 +428,7 @@ int launch_bwd(const SdpaBwdMmaArgs& a, cudaStream_t st) {
     auto go = [&](auto kern, int nw) -> int {
         if (smem > 48 * 1024) OVQA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid((unsigned)a.f.h, (unsigned)a.f.B);
-        kern<<<grid, nw * 32, smem, st>>>(a);
+        OVQA_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(nw * 32), (size_t)(smem), st, a));
         OVQA_LAUNCH_OK();
         return OVQA_OK;
     };
@@ -450,10 +454,10 @@ int launch_fwd(const SdpaArgs& a, cudaStream_t st) {
         dim3 grid((unsigned)((Lq + nw * 16 - 1) / (nw * 16)), (unsigned)a.h, (unsigned)a.B);
         if (full) {
             if (smem > 48 * 1024) OVQA_CUDA_OK(cudaFuncSetAttribute(kern_full, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern_full<<<grid, nw * 32, smem, st>>>(a);
+            OVQA_CUDA_OK(launch_pdl(kern_full, dim3(grid), dim3(nw * 32), (size_t)(smem), st, a));
         } else {
             if (smem > 48 * 1024) OVQA_CUDA_OK(cudaFuncSetAttribute(kern_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern_chunk<<<grid, nw * 32, smem, st>>>(a);
+            OVQA_CUDA_OK(launch_pdl(kern_chunk, dim3(grid), dim3(nw * 32), (size_t)(smem), st, a));
         }
         OVQA_LAUNCH_OK();
         return OVQA_OK;

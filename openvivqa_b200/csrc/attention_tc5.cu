@@ -87,6 +87,8 @@ sdpa_fwd_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();          // programmatic dependent launch: the set-up above overlaps the previous kernel's drain; no global access before this
+    pdl_trigger();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -333,7 +335,9 @@ sdpa_fwd_tc5w_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_co
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
-    const uint32_t tmem_base = *tmem_slot;           // group g: S in columns [256 g, +nk16), O aliased onto [256 g, +D)
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();          // programmatic dependent launch: the set-up above overlaps the previous kernel's drain; no global access before this
+    pdl_trigger();           // group g: S in columns [256 g, +nk16), O aliased onto [256 g, +D)
 
     if (warp == 0) {
         if (lane == 0) {
@@ -639,6 +643,8 @@ sdpa_bwd_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();          // programmatic dependent launch: the set-up above overlaps the previous kernel's drain; no global access before this
+    pdl_trigger();
     constexpr uint32_t kRegion = 256, kColS = 0, kColDP = 128, kColDV = 0, kColDK = 64, kColDQ = 128;      // column offsets inside a region
 
     if (warp == 0) {
@@ -873,7 +879,7 @@ int sdpa_fwd_tc5_bf16(const SdpaArgs& a, cudaStream_t st) {
     const int64_t items = a.B * a.h;
     const int64_t slots = 2 * (int64_t)sm_count();            // two CTAs per SM
     const int grid = (int)(items < slots ? items : slots);
-    sdpa_fwd_tc5_kernel<<<grid, kFwdThreads, kFwdSmem, st>>>(mq, mk, mv, args);
+    OVQA_CUDA_OK(launch_pdl(sdpa_fwd_tc5_kernel, dim3(grid), dim3(kFwdThreads), (size_t)(kFwdSmem), st, mq, mk, mv, args));
     OVQA_LAUNCH_OK();
     return OVQA_OK;
 }
@@ -914,7 +920,7 @@ static int launch_tc5w(const SdpaArgs& a, cudaStream_t st) {
     OVQA_CUDA_OK(cudaFuncSetAttribute(sdpa_fwd_tc5w_kernel<TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int64_t items = a.B * a.h * args.n_mt;
     const int grid = (int)(items < sm_count() ? items : sm_count());
-    sdpa_fwd_tc5w_kernel<TW><<<grid, kWideThreads, smem, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], args);
+    OVQA_CUDA_OK(launch_pdl(sdpa_fwd_tc5w_kernel<TW>, dim3(grid), dim3(kWideThreads), (size_t)(smem), st, m[0], m[1], m[2], m[3], m[4], m[5], args));
     OVQA_LAUNCH_OK();
     return OVQA_OK;
 }
@@ -944,7 +950,7 @@ int sdpa_bwd_tc5_bf16(const SdpaArgs& a, const void* dout, void* dq, void* dk, v
     if (attr_set.pending()) { OVQA_CUDA_OK(cudaFuncSetAttribute(sdpa_bwd_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem)); attr_set.mark(); }
     const int64_t items = a.B * a.h;
     const int grid = (int)(items < sm_count() ? items : sm_count());
-    sdpa_bwd_tc5_kernel<<<grid, kBwdThreads, kBwdSmem, st>>>(mq, mdo, mk, mv, args);
+    OVQA_CUDA_OK(launch_pdl(sdpa_bwd_tc5_kernel, dim3(grid), dim3(kBwdThreads), (size_t)(kBwdSmem), st, mq, mdo, mk, mv, args));
     OVQA_LAUNCH_OK();
     return OVQA_OK;
 }

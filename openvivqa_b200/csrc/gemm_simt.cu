@@ -18,6 +18,8 @@ template <typename TIn, typename TC, int T>
 __global__ void __launch_bounds__((T / 4) * (T / 4)) gemm_simt_kernel(const TIn* __restrict__ A, const TIn* __restrict__ B, TC* __restrict__ C,
                                                        int64_t m, int64_t n, int64_t k, int64_t sa_m, int64_t sa_k,
                                                        int64_t sb_n, int64_t sb_k, int64_t ldc, Epilogue epi, int split_k) {
+    pdl_wait();          // programmatic dependent launch (common.cuh): nothing above touches global memory
+    pdl_trigger();
     constexpr int BM = T, BN = T, NT = (T / 4) * (T / 4);
     __shared__ float As[BK][BM + 4];
     __shared__ float Bs[BK][BN + 4];
@@ -85,6 +87,8 @@ template <typename TIn, typename TC>
 __global__ void __launch_bounds__(256) gemm_simt_small_kernel(const TIn* __restrict__ A, const TIn* __restrict__ B, TC* __restrict__ C, int64_t m,
                                                               int64_t n, int64_t k, int64_t sa_m, int64_t sa_k, int64_t sb_n, int64_t sb_k, int64_t ldc,
                                                               Epilogue epi) {
+    pdl_wait();          // programmatic dependent launch (common.cuh): nothing above touches global memory
+    pdl_trigger();
     constexpr int T = 32, KG = 4;
     __shared__ float As[KG][BK][T + 4];
     __shared__ float Bs[KG][BK][T + 4];
@@ -163,9 +167,9 @@ int launch(const TIn* A, const TIn* B, void* C, int64_t m, int64_t n, int64_t k,
     if (small && split_k == 1 && k >= 256) {
         dim3 grid((unsigned)((n + 31) / 32), (unsigned)((m + 31) / 32));
         if (epi.c_dtype == OVQA_F32)
-            gemm_simt_small_kernel<TIn, float><<<grid, 256, 0, st>>>(A, B, (float*)C, m, n, k, sa_m, sa_k, sb_n, sb_k, ldc, epi);
+            OVQA_CUDA_OK(launch_pdl(gemm_simt_small_kernel<TIn, float>, dim3(grid), dim3(256), (size_t)(0), st, A, B, (float*)C, m, n, k, sa_m, sa_k, sb_n, sb_k, ldc, epi));
         else
-            gemm_simt_small_kernel<TIn, __nv_bfloat16><<<grid, 256, 0, st>>>(A, B, (__nv_bfloat16*)C, m, n, k, sa_m, sa_k, sb_n, sb_k, ldc, epi);
+            OVQA_CUDA_OK(launch_pdl(gemm_simt_small_kernel<TIn, __nv_bfloat16>, dim3(grid), dim3(256), (size_t)(0), st, A, B, (__nv_bfloat16*)C, m, n, k, sa_m, sa_k, sb_n, sb_k, ldc, epi));
         OVQA_LAUNCH_OK();
         return OVQA_OK;
     }
@@ -173,9 +177,9 @@ int launch(const TIn* A, const TIn* B, void* C, int64_t m, int64_t n, int64_t k,
         constexpr int T = decltype(tile_tag)::value;
         dim3 grid((unsigned)((n + T - 1) / T), (unsigned)((m + T - 1) / T), (unsigned)split_k);
         if (epi.c_dtype == OVQA_F32)
-            gemm_simt_kernel<TIn, float, T><<<grid, (T / 4) * (T / 4), 0, st>>>(A, B, (float*)C, m, n, k, sa_m, sa_k, sb_n, sb_k, ldc, epi, split_k);
+            OVQA_CUDA_OK(launch_pdl(gemm_simt_kernel<TIn, float, T>, dim3(grid), dim3((T / 4) * (T / 4)), (size_t)(0), st, A, B, (float*)C, m, n, k, sa_m, sa_k, sb_n, sb_k, ldc, epi, split_k));
         else
-            gemm_simt_kernel<TIn, __nv_bfloat16, T><<<grid, (T / 4) * (T / 4), 0, st>>>(A, B, (__nv_bfloat16*)C, m, n, k, sa_m, sa_k, sb_n, sb_k, ldc, epi, split_k);
+            OVQA_CUDA_OK(launch_pdl(gemm_simt_kernel<TIn, __nv_bfloat16, T>, dim3(grid), dim3((T / 4) * (T / 4)), (size_t)(0), st, A, B, (__nv_bfloat16*)C, m, n, k, sa_m, sa_k, sb_n, sb_k, ldc, epi, split_k));
     };
     if (small) go(std::integral_constant<int, 32>{}); else go(std::integral_constant<int, 64>{});
     OVQA_LAUNCH_OK();

@@ -23,6 +23,8 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ resi
                      const float* __restrict__ beta, const float* __restrict__ post_add, int64_t post_rows,
                      float* __restrict__ y, __nv_bfloat16* __restrict__ y16, float* __restrict__ sum_out,
                      float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t rows, int D, float eps) {
+    pdl_wait();          // programmatic dependent launch (common.cuh): nothing above touches global memory
+    pdl_trigger();
     const int64_t row = (int64_t)blockIdx.x * kRowsPerCta + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
     if (row >= rows) return;
@@ -80,6 +82,8 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
                      float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16, float* __restrict__ dgamma, float* __restrict__ dbeta,
                      float* __restrict__ dbias, int64_t rows, int D, float p, float inv_keep, uint64_t seed, uint64_t offset_,
                      const uint64_t* offset_base) {
+    pdl_wait();          // programmatic dependent launch (common.cuh): nothing above touches global memory
+    pdl_trigger();
     extern __shared__ __align__(16) float ln_smem[];       // [kBwdWarps][2 stages][2 (x, dy)][NV*128]; reused for the final reduction
     constexpr int W = NV * 128;
     const uint64_t offset = p > 0.f ? effective_offset(offset_, offset_base) : 0;
@@ -178,6 +182,8 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
 }
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n) {
+    pdl_wait();          // programmatic dependent launch (common.cuh): nothing above touches global memory
+    pdl_trigger();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x * 8;
     for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
         if (i + 8 <= n) {
@@ -189,10 +195,14 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16*
     }
 }
 __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int64_t n) {
+    pdl_wait();          // programmatic dependent launch (common.cuh): nothing above touches global memory
+    pdl_trigger();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = __bfloat162float(x[i]);
 }
 __global__ void add_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, int64_t n) {
+    pdl_wait();          // programmatic dependent launch (common.cuh): nothing above touches global memory
+    pdl_trigger();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
     for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
         if (i + 4 <= n) *reinterpret_cast<float4*>(y + i) = add4(ld4(a + i), ld4(b + i));
@@ -203,6 +213,8 @@ __global__ void add_f32_kernel(const float* __restrict__ a, const float* __restr
 // out[c] += sum over a slab of rows; block (32 cols, 8 row lanes)
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ x, float* __restrict__ out, int64_t m, int64_t n, int64_t ldx, int64_t rows_per_block) {
+    pdl_wait();          // programmatic dependent launch (common.cuh): nothing above touches global memory
+    pdl_trigger();
     __shared__ float red[8][33];
     const int64_t col = (int64_t)blockIdx.x * 32 + threadIdx.x;
     const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(m, r0 + rows_per_block);
@@ -225,6 +237,8 @@ __global__ void colsum_kernel(const T* __restrict__ x, float* __restrict__ out, 
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ x, float* __restrict__ out, int64_t m, int64_t n, int64_t ldx,
                                                          int64_t rows_per_block) {
+    pdl_wait();          // programmatic dependent launch (common.cuh): nothing above touches global memory
+    pdl_trigger();
     __shared__ float4 red[8][64];
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int64_t col = (int64_t)blockIdx.x * 256 + lane * 8;
@@ -274,6 +288,8 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ x
 template <typename TO>
 __global__ void dropout_apply_kernel(const float* __restrict__ x, TO* __restrict__ y, int64_t n, float p, float inv_keep, uint64_t seed, uint64_t offset_,
                                      const uint64_t* offset_base) {
+    pdl_wait();          // programmatic dependent launch (common.cuh): nothing above touches global memory
+    pdl_trigger();
     const uint64_t offset = p > 0.f ? effective_offset(offset_, offset_base) : 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
     for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
@@ -285,16 +301,22 @@ __global__ void dropout_apply_kernel(const float* __restrict__ x, TO* __restrict
 }
 
 __global__ void dropout_mask_kernel(float* out, int64_t n, float p, uint64_t seed, uint64_t offset, const uint64_t* offset_base) {
+    pdl_wait();          // programmatic dependent launch (common.cuh): nothing above touches global memory
+    pdl_trigger();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = dropout_scale((uint64_t)i, p, 1.0f, seed, effective_offset(offset, offset_base));
 }
-__global__ void advance_u64_kernel(uint64_t* word, uint64_t delta) { *word += delta; }
+__global__ void advance_u64_kernel(uint64_t* word, uint64_t delta) {
+    pdl_wait();          // programmatic dependent launch (common.cuh): nothing above touches global memory
+    pdl_trigger(); *word += delta; }
 
 // FeatureEmbedding front-end (vision_embeddings.py:19-25 + models/utils.py:44-57): ONE pass over the fp32 region features writes the
 // bf16 GEMM operand AND the padding mask (a row whose features sum to 0 is padding: additive mask_value there, 0 elsewhere).  Warp per row,
 // 16-byte loads; the reference reads the features twice (torch.sum for the mask, then the Linear) plus a cast under autocast.
 __global__ void __launch_bounds__(256) cast_rows_padmask_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, float* __restrict__ mask,
                                                                 int64_t rows, int64_t K, int64_t ldx, float mask_value) {
+    pdl_wait();          // programmatic dependent launch (common.cuh): nothing above touches global memory
+    pdl_trigger();
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
     if (row >= rows) return;
@@ -315,6 +337,8 @@ __global__ void __launch_bounds__(256) cast_rows_padmask_kernel(const float* __r
 // the padding mask alone, for features that already arrive as bf16 (pinned bf16 staging of the input feed): warp per row
 __global__ void __launch_bounds__(256) rows_padmask_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ mask, int64_t rows, int64_t K,
                                                                 int64_t ldx, float mask_value) {
+    pdl_wait();          // programmatic dependent launch (common.cuh): nothing above touches global memory
+    pdl_trigger();
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
     if (row >= rows) return;
@@ -334,6 +358,8 @@ __global__ void __launch_bounds__(256) rows_padmask_bf16_kernel(const __nv_bfloa
 // out_bf16 = a (fp32) * b (fp32 | bf16): the gradient of a fused activation from its saved derivative
 template <typename TB>
 __global__ void mul_to_bf16_kernel(const float* __restrict__ a, const TB* __restrict__ b, __nv_bfloat16* __restrict__ y, int64_t n) {
+    pdl_wait();          // programmatic dependent launch (common.cuh): nothing above touches global memory
+    pdl_trigger();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
     for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
         if (i + 4 <= n) {
@@ -350,6 +376,8 @@ __global__ void mul_to_bf16_kernel(const float* __restrict__ a, const TB* __rest
 
 // many (src fp32 -> dst fp32|bf16) contiguous copies in one launch: blockIdx.y = descriptor, blockIdx.x strides over it
 __global__ void stage_many_kernel(const ovqa_stage_desc* __restrict__ descs) {
+    pdl_wait();          // programmatic dependent launch (common.cuh): nothing above touches global memory
+    pdl_trigger();
     const ovqa_stage_desc d = descs[blockIdx.y];
     const float* __restrict__ x = d.src;
     const int64_t n = d.n;
@@ -397,8 +425,8 @@ extern "C" int ovqa_layernorm_fwd(const float* x, const float* residual, const f
     if (rows == 0) return OVQA_OK;
     if (post_add && post_add_rows <= 0) return OVQA_ERR_BAD_ARG;
     const int nv = (int)((D + 127) / 128);
-    OVQA_LN_DISPATCH(layernorm_fwd_kernel)<<<(unsigned)((rows + kRowsPerCta - 1) / kRowsPerCta), kRowsPerCta * 32, 0, (cudaStream_t)stream>>>(
-        x, residual, gamma, beta, post_add, post_add ? post_add_rows : 1, y_f32, (__nv_bfloat16*)y_bf16, sum_out, mean, rstd, rows, (int)D, eps);
+    OVQA_CUDA_OK(launch_pdl(OVQA_LN_DISPATCH(layernorm_fwd_kernel), dim3((unsigned)((rows + kRowsPerCta - 1) / kRowsPerCta)), dim3(kRowsPerCta * 32), (size_t)(0), (cudaStream_t)stream, 
+        x, residual, gamma, beta, post_add, post_add ? post_add_rows : 1, y_f32, (__nv_bfloat16*)y_bf16, sum_out, mean, rstd, rows, (int)D, eps));
     OVQA_LAUNCH_OK();
     return OVQA_OK;
 }
@@ -422,9 +450,9 @@ extern "C" int ovqa_layernorm_bwd(const float* dy, const float* x, const float* 
     int64_t g = (rows + kBwdWarps - 1) / kBwdWarps;
     const int64_t cap = (int64_t)sm_count() * per_sm;
     if (g > cap) g = cap;
-    kern<<<(unsigned)g, kBwdWarps * 32, smem, (cudaStream_t)stream>>>(
+    OVQA_CUDA_OK(launch_pdl(kern, dim3((unsigned)g), dim3(kBwdWarps * 32), (size_t)(smem), (cudaStream_t)stream, 
         dy, x, mean, rstd, gamma, dx_add, dx, (__nv_bfloat16*)dx_bf16, dgamma, dbeta, dbias, rows, (int)D, dropout_p,
-        dropout_p > 0.f ? 1.0f / (1.0f - dropout_p) : 1.0f, seed, offset, offset_base);
+        dropout_p > 0.f ? 1.0f / (1.0f - dropout_p) : 1.0f, seed, offset, offset_base));
     OVQA_LAUNCH_OK();
     return OVQA_OK;
 }
@@ -433,14 +461,14 @@ extern "C" int ovqa_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* s
     if (!x || !y || n < 0) return OVQA_ERR_BAD_ARG;
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return OVQA_ERR_ALIGNMENT;
     if (n == 0) return OVQA_OK;
-    cast_f32_bf16_kernel<<<grid_for((n + 7) / 8, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, n);
+    OVQA_CUDA_OK(launch_pdl(cast_f32_bf16_kernel, dim3(grid_for((n + 7) / 8, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, x, (__nv_bfloat16*)y, n));
     OVQA_LAUNCH_OK();
     return OVQA_OK;
 }
 extern "C" int ovqa_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream) {
     if (!x || !y || n < 0) return OVQA_ERR_BAD_ARG;
     if (n == 0) return OVQA_OK;
-    cast_bf16_f32_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, y, n);
+    OVQA_CUDA_OK(launch_pdl(cast_bf16_f32_kernel, dim3(grid_for(n, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const __nv_bfloat16*)x, y, n));
     OVQA_LAUNCH_OK();
     return OVQA_OK;
 }
@@ -448,7 +476,7 @@ extern "C" int ovqa_add_f32(const float* a, const float* b, float* y, int64_t n,
     if (!a || !b || !y || n < 0) return OVQA_ERR_BAD_ARG;
     if ((reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return OVQA_ERR_ALIGNMENT;
     if (n == 0) return OVQA_OK;
-    add_f32_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(a, b, y, n);
+    OVQA_CUDA_OK(launch_pdl(add_f32_kernel, dim3(grid_for((n + 3) / 4, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, a, b, y, n));
     OVQA_LAUNCH_OK();
     return OVQA_OK;
 }
@@ -466,8 +494,8 @@ extern "C" int ovqa_colsum(const void* x, float* out, int64_t m, int64_t n, int6
         if (rb < 1) rb = 1;
         const int64_t rpb_v = ((m + rb - 1) / rb + 7) / 8 * 8;
         dim3 grid_v((unsigned)cb, (unsigned)((m + rpb_v - 1) / rpb_v));
-        if (dtype == OVQA_F32) colsum_vec_kernel<float><<<grid_v, 256, 0, st>>>((const float*)x, out, m, n, ldx, rpb_v);
-        else colsum_vec_kernel<__nv_bfloat16><<<grid_v, 256, 0, st>>>((const __nv_bfloat16*)x, out, m, n, ldx, rpb_v);
+        if (dtype == OVQA_F32) OVQA_CUDA_OK(launch_pdl(colsum_vec_kernel<float>, dim3(grid_v), dim3(256), (size_t)(0), st, (const float*)x, out, m, n, ldx, rpb_v));
+        else OVQA_CUDA_OK(launch_pdl(colsum_vec_kernel<__nv_bfloat16>, dim3(grid_v), dim3(256), (size_t)(0), st, (const __nv_bfloat16*)x, out, m, n, ldx, rpb_v));
         OVQA_LAUNCH_OK();
         return OVQA_OK;
     }
@@ -477,8 +505,8 @@ extern "C" int ovqa_colsum(const void* x, float* out, int64_t m, int64_t n, int6
     if (row_blocks > (m + 63) / 64) row_blocks = (m + 63) / 64;
     const int64_t rpb = (m + row_blocks - 1) / row_blocks;
     dim3 grid((unsigned)col_blocks, (unsigned)row_blocks), block(32, 8);
-    if (dtype == OVQA_F32) colsum_kernel<float><<<grid, block, 0, st>>>((const float*)x, out, m, n, ldx, rpb);
-    else if (dtype == OVQA_BF16) colsum_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, out, m, n, ldx, rpb);
+    if (dtype == OVQA_F32) OVQA_CUDA_OK(launch_pdl(colsum_kernel<float>, dim3(grid), dim3(block), (size_t)(0), st, (const float*)x, out, m, n, ldx, rpb));
+    else if (dtype == OVQA_BF16) OVQA_CUDA_OK(launch_pdl(colsum_kernel<__nv_bfloat16>, dim3(grid), dim3(block), (size_t)(0), st, (const __nv_bfloat16*)x, out, m, n, ldx, rpb));
     else return OVQA_ERR_BAD_ARG;
     OVQA_LAUNCH_OK();
     return OVQA_OK;
@@ -488,15 +516,15 @@ extern "C" int ovqa_dropout_apply(const float* x, void* y, int64_t n, float p, u
     if (!x || !y || n < 0 || p < 0.f || p >= 1.f) return OVQA_ERR_BAD_ARG;
     if (n == 0) return OVQA_OK;
     const float inv = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
-    if (out_dtype == OVQA_F32) dropout_apply_kernel<float><<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, (float*)y, n, p, inv, seed, offset, offset_base);
-    else if (out_dtype == OVQA_BF16) dropout_apply_kernel<__nv_bfloat16><<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, n, p, inv, seed, offset, offset_base);
+    if (out_dtype == OVQA_F32) OVQA_CUDA_OK(launch_pdl(dropout_apply_kernel<float>, dim3(grid_for((n + 3) / 4, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, x, (float*)y, n, p, inv, seed, offset, offset_base));
+    else if (out_dtype == OVQA_BF16) OVQA_CUDA_OK(launch_pdl(dropout_apply_kernel<__nv_bfloat16>, dim3(grid_for((n + 3) / 4, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, x, (__nv_bfloat16*)y, n, p, inv, seed, offset, offset_base));
     else return OVQA_ERR_BAD_ARG;
     OVQA_LAUNCH_OK();
     return OVQA_OK;
 }
 extern "C" int ovqa_advance_u64(uint64_t* word, uint64_t delta, void* stream) {
     if (!word) return OVQA_ERR_BAD_ARG;
-    advance_u64_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(word, delta);
+    OVQA_CUDA_OK(launch_pdl(advance_u64_kernel, dim3(1), dim3(1), (size_t)(0), (cudaStream_t)stream, word, delta));
     OVQA_LAUNCH_OK();
     return OVQA_OK;
 }
@@ -504,14 +532,14 @@ extern "C" int ovqa_stage_many(const ovqa_stage_desc* descs, int64_t n_desc, voi
     if (n_desc < 0 || (n_desc > 0 && !descs)) return OVQA_ERR_BAD_ARG;
     if (n_desc == 0) return OVQA_OK;
     if (n_desc > 65535) return OVQA_ERR_BAD_SHAPE;
-    stage_many_kernel<<<dim3(32, (unsigned)n_desc), 256, 0, (cudaStream_t)stream>>>(descs);
+    OVQA_CUDA_OK(launch_pdl(stage_many_kernel, dim3(dim3(32, (unsigned)n_desc)), dim3(256), (size_t)(0), (cudaStream_t)stream, descs));
     OVQA_LAUNCH_OK();
     return OVQA_OK;
 }
 extern "C" int ovqa_dropout_mask(float* out, int64_t n, float p, uint64_t seed, uint64_t offset, const uint64_t* offset_base, void* stream) {
     if (!out || n < 0) return OVQA_ERR_BAD_ARG;
     if (n == 0) return OVQA_OK;
-    dropout_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, n, p, seed, offset, offset_base);
+    OVQA_CUDA_OK(launch_pdl(dropout_mask_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, out, n, p, seed, offset, offset_base));
     OVQA_LAUNCH_OK();
     return OVQA_OK;
 }
@@ -520,7 +548,7 @@ extern "C" int ovqa_cast_rows_padmask(const float* x, void* y_bf16, float* mask,
     if (!x || !y_bf16 || rows < 0 || K <= 0 || ldx < K) return OVQA_ERR_BAD_ARG;
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y_bf16) & 15) || (ldx % 4) || (K % 8)) return OVQA_ERR_ALIGNMENT;
     if (rows == 0) return OVQA_OK;
-    cast_rows_padmask_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y_bf16, mask, rows, K, ldx, mask_value);
+    OVQA_CUDA_OK(launch_pdl(cast_rows_padmask_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), (size_t)(0), (cudaStream_t)stream, x, (__nv_bfloat16*)y_bf16, mask, rows, K, ldx, mask_value));
     OVQA_LAUNCH_OK();
     return OVQA_OK;
 }
@@ -528,7 +556,7 @@ extern "C" int ovqa_rows_padmask_bf16(const void* x_bf16, float* mask, int64_t r
     if (!x_bf16 || !mask || rows < 0 || K <= 0 || ldx < K) return OVQA_ERR_BAD_ARG;
     if ((reinterpret_cast<uintptr_t>(x_bf16) & 15) || (ldx % 8)) return OVQA_ERR_ALIGNMENT;
     if (rows == 0) return OVQA_OK;
-    rows_padmask_bf16_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x_bf16, mask, rows, K, ldx, mask_value);
+    OVQA_CUDA_OK(launch_pdl(rows_padmask_bf16_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const __nv_bfloat16*)x_bf16, mask, rows, K, ldx, mask_value));
     OVQA_LAUNCH_OK();
     return OVQA_OK;
 }
@@ -536,8 +564,8 @@ extern "C" int ovqa_mul_to_bf16(const float* a, const void* b, int b_dtype, void
     if (!a || !b || !y_bf16 || n < 0) return OVQA_ERR_BAD_ARG;
     if ((reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15) || (reinterpret_cast<uintptr_t>(y_bf16) & 7)) return OVQA_ERR_ALIGNMENT;
     if (n == 0) return OVQA_OK;
-    if (b_dtype == OVQA_F32) mul_to_bf16_kernel<float><<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(a, (const float*)b, (__nv_bfloat16*)y_bf16, n);
-    else if (b_dtype == OVQA_BF16) mul_to_bf16_kernel<__nv_bfloat16><<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(a, (const __nv_bfloat16*)b, (__nv_bfloat16*)y_bf16, n);
+    if (b_dtype == OVQA_F32) OVQA_CUDA_OK(launch_pdl(mul_to_bf16_kernel<float>, dim3(grid_for((n + 3) / 4, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, a, (const float*)b, (__nv_bfloat16*)y_bf16, n));
+    else if (b_dtype == OVQA_BF16) OVQA_CUDA_OK(launch_pdl(mul_to_bf16_kernel<__nv_bfloat16>, dim3(grid_for((n + 3) / 4, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, a, (const __nv_bfloat16*)b, (__nv_bfloat16*)y_bf16, n));
     else return OVQA_ERR_BAD_ARG;
     OVQA_LAUNCH_OK();
     return OVQA_OK;

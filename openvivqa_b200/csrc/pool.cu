@@ -19,6 +19,8 @@ template <typename TH>
 __global__ void __launch_bounds__(kPoolThreads) attr_pool_fwd_kernel(const TH* __restrict__ hid, const float* __restrict__ w2, const float* __restrict__ b2,
                                                                      const float* __restrict__ x, float* __restrict__ pooled, float* __restrict__ probs,
                                                                      int N, int Dh, int D) {
+    pdl_wait();          // programmatic dependent launch (common.cuh): nothing above touches global memory
+    pdl_trigger();
     extern __shared__ float sp[];                   // [N] logits -> probabilities
     __shared__ float red[kPoolThreads / 32];
     const int64_t b = blockIdx.x;
@@ -69,6 +71,8 @@ __global__ void __launch_bounds__(kPoolThreads) attr_pool_bwd_kernel(const float
                                                                      const float* __restrict__ x, const float* __restrict__ probs, float* __restrict__ dx,
                                                                      TH* __restrict__ dpre, float* __restrict__ dw2, float* __restrict__ db2, int N, int Dh,
                                                                      int D, float inv_keep) {
+    pdl_wait();          // programmatic dependent launch (common.cuh): nothing above touches global memory
+    pdl_trigger();
     extern __shared__ float sd[];                   // [N] x.dpooled -> dlogit
     __shared__ float red[kPoolThreads / 32];
     const int64_t b = blockIdx.x;
@@ -163,6 +167,8 @@ template <typename TH>
 __global__ void __launch_bounds__(kPoolThreads) attr_pool_fwd_vec_kernel(const TH* __restrict__ hid, const float* __restrict__ w2, const float* __restrict__ b2,
                                                                          const float* __restrict__ x, float* __restrict__ pooled, float* __restrict__ probs,
                                                                          int N, int Dh, int D) {
+    pdl_wait();          // programmatic dependent launch (common.cuh): nothing above touches global memory
+    pdl_trigger();
     extern __shared__ __align__(16) float sp[];      // [N] logits -> probabilities | [kPoolThreads * 4] partial weighted sums
     __shared__ float red[kPoolThreads / 32];
     constexpr int HN = HVec<TH>::kN;
@@ -245,6 +251,8 @@ __global__ void __launch_bounds__(kPoolThreads) attr_pool_bwd_vec_kernel(const f
                                                                          const float* __restrict__ x, const float* __restrict__ probs, float* __restrict__ dx,
                                                                          TH* __restrict__ dpre, float* __restrict__ dw2, float* __restrict__ db2, int N, int Dh,
                                                                          int D, float inv_keep) {
+    pdl_wait();          // programmatic dependent launch (common.cuh): nothing above touches global memory
+    pdl_trigger();
     extern __shared__ __align__(16) float sd[];      // [N] x.dpooled -> dlogit | [N] p | [kPoolThreads * 8] partial dw2
     __shared__ float red[kPoolThreads / 32];
     constexpr int HN = HVec<TH>::kN;
@@ -366,17 +374,17 @@ extern "C" int ovqa_attr_pool_fwd(const void* hidden, const float* w2, const flo
     const size_t smem_v = (size_t)(((N + 3) & ~3) + kPoolThreads * 4) * sizeof(float);
     if (D % 4 == 0 && Dh % hn == 0 && al16(hidden) && al16(w2) && al16(x) && al16(pooled) && smem_v <= 48 * 1024) {
         if (hidden_dtype == OVQA_F32)
-            attr_pool_fwd_vec_kernel<float><<<(unsigned)B, kPoolThreads, smem_v, st>>>((const float*)hidden, w2, b2, x, pooled, probs, (int)N, (int)Dh, (int)D);
+            OVQA_CUDA_OK(launch_pdl(attr_pool_fwd_vec_kernel<float>, dim3((unsigned)B), dim3(kPoolThreads), (size_t)(smem_v), st, (const float*)hidden, w2, b2, x, pooled, probs, (int)N, (int)Dh, (int)D));
         else
-            attr_pool_fwd_vec_kernel<__nv_bfloat16><<<(unsigned)B, kPoolThreads, smem_v, st>>>((const __nv_bfloat16*)hidden, w2, b2, x, pooled, probs, (int)N, (int)Dh, (int)D);
+            OVQA_CUDA_OK(launch_pdl(attr_pool_fwd_vec_kernel<__nv_bfloat16>, dim3((unsigned)B), dim3(kPoolThreads), (size_t)(smem_v), st, (const __nv_bfloat16*)hidden, w2, b2, x, pooled, probs, (int)N, (int)Dh, (int)D));
         OVQA_LAUNCH_OK();
         return OVQA_OK;
     }
     const size_t smem = (size_t)N * sizeof(float);
     if (hidden_dtype == OVQA_F32)
-        attr_pool_fwd_kernel<float><<<(unsigned)B, kPoolThreads, smem, st>>>((const float*)hidden, w2, b2, x, pooled, probs, (int)N, (int)Dh, (int)D);
+        OVQA_CUDA_OK(launch_pdl(attr_pool_fwd_kernel<float>, dim3((unsigned)B), dim3(kPoolThreads), (size_t)(smem), st, (const float*)hidden, w2, b2, x, pooled, probs, (int)N, (int)Dh, (int)D));
     else
-        attr_pool_fwd_kernel<__nv_bfloat16><<<(unsigned)B, kPoolThreads, smem, st>>>((const __nv_bfloat16*)hidden, w2, b2, x, pooled, probs, (int)N, (int)Dh, (int)D);
+        OVQA_CUDA_OK(launch_pdl(attr_pool_fwd_kernel<__nv_bfloat16>, dim3((unsigned)B), dim3(kPoolThreads), (size_t)(smem), st, (const __nv_bfloat16*)hidden, w2, b2, x, pooled, probs, (int)N, (int)Dh, (int)D));
     OVQA_LAUNCH_OK();
     return OVQA_OK;
 }
@@ -395,20 +403,20 @@ extern "C" int ovqa_attr_pool_bwd(const float* dpooled, const void* hidden, cons
     const size_t smem_v = (size_t)(2 * ((N + 3) & ~3) + kPoolThreads * 8) * sizeof(float);
     if (D % 4 == 0 && Dh % hn == 0 && al16(hidden) && al16(w2) && al16(x) && al16(dpooled) && al16(dpre) && (!dx || al16(dx)) && smem_v <= 48 * 1024) {
         if (hidden_dtype == OVQA_F32)
-            attr_pool_bwd_vec_kernel<float><<<(unsigned)B, kPoolThreads, smem_v, st>>>(dpooled, (const float*)hidden, w2, x, probs, dx, (float*)dpre, dw2, db2,
-                                                                                     (int)N, (int)Dh, (int)D, inv_keep);
+            OVQA_CUDA_OK(launch_pdl(attr_pool_bwd_vec_kernel<float>, dim3((unsigned)B), dim3(kPoolThreads), (size_t)(smem_v), st, dpooled, (const float*)hidden, w2, x, probs, dx, (float*)dpre, dw2, db2,
+                                                                                     (int)N, (int)Dh, (int)D, inv_keep));
         else
-            attr_pool_bwd_vec_kernel<__nv_bfloat16><<<(unsigned)B, kPoolThreads, smem_v, st>>>(dpooled, (const __nv_bfloat16*)hidden, w2, x, probs, dx,
-                                                                                             (__nv_bfloat16*)dpre, dw2, db2, (int)N, (int)Dh, (int)D, inv_keep);
+            OVQA_CUDA_OK(launch_pdl(attr_pool_bwd_vec_kernel<__nv_bfloat16>, dim3((unsigned)B), dim3(kPoolThreads), (size_t)(smem_v), st, dpooled, (const __nv_bfloat16*)hidden, w2, x, probs, dx,
+                                                                                             (__nv_bfloat16*)dpre, dw2, db2, (int)N, (int)Dh, (int)D, inv_keep));
         OVQA_LAUNCH_OK();
         return OVQA_OK;
     }
     if (hidden_dtype == OVQA_F32)
-        attr_pool_bwd_kernel<float><<<(unsigned)B, kPoolThreads, smem, st>>>(dpooled, (const float*)hidden, w2, x, probs, dx, (float*)dpre, dw2, db2, (int)N,
-                                                                             (int)Dh, (int)D, inv_keep);
+        OVQA_CUDA_OK(launch_pdl(attr_pool_bwd_kernel<float>, dim3((unsigned)B), dim3(kPoolThreads), (size_t)(smem), st, dpooled, (const float*)hidden, w2, x, probs, dx, (float*)dpre, dw2, db2, (int)N,
+                                                                             (int)Dh, (int)D, inv_keep));
     else
-        attr_pool_bwd_kernel<__nv_bfloat16><<<(unsigned)B, kPoolThreads, smem, st>>>(dpooled, (const __nv_bfloat16*)hidden, w2, x, probs, dx,
-                                                                                     (__nv_bfloat16*)dpre, dw2, db2, (int)N, (int)Dh, (int)D, inv_keep);
+        OVQA_CUDA_OK(launch_pdl(attr_pool_bwd_kernel<__nv_bfloat16>, dim3((unsigned)B), dim3(kPoolThreads), (size_t)(smem), st, dpooled, (const __nv_bfloat16*)hidden, w2, x, probs, dx,
+                                                                                     (__nv_bfloat16*)dpre, dw2, db2, (int)N, (int)Dh, (int)D, inv_keep));
     OVQA_LAUNCH_OK();
     return OVQA_OK;
 }
