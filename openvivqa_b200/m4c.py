@@ -199,6 +199,9 @@ def prepare_decode(model, txt, txt_mask, obj, obj_mask, ocr, ocr_mask, mode):
     st.L = Lt + No + Nc + T
     st.x = torch.empty((B, st.L, D), device=dev, dtype=torch.float32)
     st.x[:, :Lt], st.x[:, Lt:Lt + No], st.x[:, Lt + No:Lt + No + Nc] = txt, obj, ocr
+    # bf16 operand copy of the encoder input: the 170 prefix rows are step-invariant, so they are cast ONCE per batch; a step refreshes only
+    # its decoder rows (the whole-buffer cast per step was 12 x 22 us of a 22 ms decode)
+    st.x16 = ops.to_bf16(st.x) if mode == "bf16" else None
     st.ocr_in = ocr.float().contiguous()
     st.ocr_mask = ocr_mask
     st.mask = mmt_mask(txt_mask, obj_mask, ocr_mask, T)
@@ -229,7 +232,11 @@ def decode_step(model, st, ith, prune_last_layer=True):
     """One ``_forward_mmt`` + ``_forward_output`` + greedy update (mmf_m4c.py:202-229,247-253)."""
     mode = st.mode
     prev_pred_embeddings(model.mmt.prev_pred_embeddings, model.classifier.weight, st.ocr_in, st.prev_inds, out=st.x[:, -st.T:])
-    st.x._ovqa_bf16 = None                                             # the buffer changed in place: drop any shadow
+    if st.x16 is not None:                                             # the buffer changed in place: refresh the decoder rows of its bf16 copy
+        st.x16[:, -st.T:].copy_(st.x[:, -st.T:])
+        st.x._ovqa_bf16 = (st.x._version, st.x16)
+    else:
+        st.x._ovqa_bf16 = None
     if prune_last_layer:
         y = bert_encoder(model.mmt.encoder, st.x, st.mask, mode, heads=st.heads, last_q_rows=st.rows)      # (B, Nc+T, D)
         ocr_out, dec_out = y[:, :st.Nc], y[:, st.Nc:]
