@@ -52,13 +52,15 @@ __global__ void __launch_bounds__(256) ptr_scores_vec_kernel(const __nv_bfloat16
     for (int c = lane; c < nv; c += 32) {
         const uint4 kv = __ldg(kr + c);
         const float2 k0 = unpack_bf16x2(kv.x), k1 = unpack_bf16x2(kv.y), k2 = unpack_bf16x2(kv.z), k3 = unpack_bf16x2(kv.w);
+        // every query row's vector is requested before the first is used (rows beyond Tn: row 0 again, result unused): requested one by
+        // one inside the predicated loop they were 13 serial L2 round trips per vector — 46 us for 128 x 12 x 50 scores (gpurun_out/r02x_ptr)
+        uint4 qv[kPtrMaxT];
+#pragma unroll
+        for (int t = 0; t < kPtrMaxT; ++t) qv[t] = __ldg(reinterpret_cast<const uint4*>(q + (b * Tn + (t < Tn ? t : 0)) * ldq) + c);
 #pragma unroll
         for (int t = 0; t < kPtrMaxT; ++t) {
-            if (t < Tn) {
-                const uint4 qv = __ldg(reinterpret_cast<const uint4*>(q + (b * Tn + t) * ldq) + c);
-                const float2 q0 = unpack_bf16x2(qv.x), q1 = unpack_bf16x2(qv.y), q2 = unpack_bf16x2(qv.z), q3 = unpack_bf16x2(qv.w);
-                acc[t] += (q0.x * k0.x + q0.y * k0.y) + (q1.x * k1.x + q1.y * k1.y) + (q2.x * k2.x + q2.y * k2.y) + (q3.x * k3.x + q3.y * k3.y);
-            }
+            const float2 q0 = unpack_bf16x2(qv[t].x), q1 = unpack_bf16x2(qv[t].y), q2 = unpack_bf16x2(qv[t].z), q3 = unpack_bf16x2(qv[t].w);
+            acc[t] += (q0.x * k0.x + q0.y * k0.y) + (q1.x * k1.x + q1.y * k1.y) + (q2.x * k2.x + q2.y * k2.y) + (q3.x * k3.x + q3.y * k3.y);
         }
     }
     float add = 0.f;
@@ -197,8 +199,16 @@ __global__ void argmax_rows_kernel(const float* __restrict__ scores, int64_t* __
     const float* r = scores + w * W;
     float best = -INFINITY;
     int64_t bi = W;  // sentinel larger than any index
-    for (int64_t c = lane; c < W; c += 32) {
-        const float v = r[c];
+    int64_t c = lane;
+    for (; c + 96 < W; c += 128) {                    // four loads in flight per lane; compared in ascending column order
+        const float v0 = __ldg(r + c), v1 = __ldg(r + c + 32), v2 = __ldg(r + c + 64), v3 = __ldg(r + c + 96);
+        if (bi == W || v0 > best) { best = v0; bi = c; }
+        if (v1 > best) { best = v1; bi = c + 32; }
+        if (v2 > best) { best = v2; bi = c + 64; }
+        if (v3 > best) { best = v3; bi = c + 96; }
+    }
+    for (; c < W; c += 32) {
+        const float v = __ldg(r + c);
         if (bi == W || v > best) { best = v; bi = c; }  // c ascends per lane: strict > keeps the first maximum
     }
 #pragma unroll
