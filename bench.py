@@ -349,6 +349,21 @@ class GemmMeter:
             return out
 
         ops.gemm = gemm
+        orig_ln = ops.gemm_ln
+
+        def gemm_ln(a, w, *rest, **kw):          # the fused fc_o / fc2 + LayerNorm kernel: a GEMM launch like the others (2 m n k flops)
+            if not meter.enabled:
+                return orig_ln(a, w, *rest, **kw)
+            e0, e1 = meter._pair()
+            e0.record()
+            out = orig_ln(a, w, *rest, **kw)
+            e1.record()
+            m, k, n = a.shape[0], a.shape[1], w.shape[0]
+            tag = f"NN m={m} n={n} k={k} bias{'+drop' if kw.get('dropout_p', 0.0) > 0 else ''}+res+layernorm -> float32"
+            meter.records.append((e0, e1, 2.0 * m * n * k, tag))
+            return out
+
+        ops.gemm_ln = gemm_ln
 
         def nbytes(*ts):
             return float(sum(t.numel() * t.element_size() for t in ts if t is not None))

@@ -247,6 +247,16 @@ int ovqa_attr_pool_bwd(const float* dpooled, const void* hidden, const float* w2
                        float* dx, void* dpre, float* dw2, float* db2,
                        int64_t B, int64_t N, int64_t Dh, int64_t D, float dropout_p, int hidden_dtype, void* stream);
 
+/* Output projection + bias + dropout + residual + LayerNorm in ONE kernel for d_model = 512 (attentions.py:58,331 fc_o -> layer_norm;
+ * positionwise_feed_forward.py:25-26 fc2 -> layer_norm):  s = dropout(A W^T + bias) + residual;  y = LayerNorm(s) * gamma + beta.
+ * A [M,K] bf16 (row pitch lda), W [N,K] bf16 (ldw), N must be 512 (a 128-row tile keeps its full fp32 rows in tensor memory; other widths
+ * return OVQA_ERR_BAD_SHAPE and the caller runs ovqa_gemm + ovqa_layernorm_fwd); residual, s_out, y [M,N] fp32 contiguous; y_bf16 [M,N].
+ * s_out (LayerNorm input, saved for the backward pass), y_bf16, mean / rstd [M] may be NULL.  Dropout: the library's counter stream
+ * (element row*N + col, as ovqa_gemm), so ovqa_layernorm_bwd regenerates the same mask. */
+int ovqa_gemm_ln(const void* A, const void* W, const float* bias, const float* residual, const float* gamma, const float* beta,
+                 float* s_out, float* y, void* y_bf16, float* mean, float* rstd, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldw,
+                 float eps, float dropout_p, uint64_t seed, uint64_t offset, const uint64_t* offset_base, void* stream);
+
 /* Recurrent part of the single-layer, batch-first LSTM of LSTMTextEmbedding (models/modules/text_embeddings.py:234,244: nn.LSTM(d_model, d_model,
  * batch_first=True) called without an initial state).  Gate order i, f, g, o (PyTorch).  bf16 operands, fp32 accumulate / state.
  *   xg [B,L,4H] fp32 = x W_ih^T + b_ih for all steps (one ovqa_gemm);  w_hh_bf16 [4H,H];  b_hh [4H] fp32 or NULL.

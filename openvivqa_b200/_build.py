@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libovqa_b200.so")
 OBJ_DIR = os.path.join(os.path.dirname(HERE), "build", "obj")
-SOURCES = ["api", "gemm_simt", "gemm_tcgen05", "attention_simt", "attention_mma", "attention_tc5", "geometry", "layernorm", "m4c", "decode", "pool", "lstm"]
+SOURCES = ["api", "gemm_simt", "gemm_tcgen05", "attention_simt", "attention_mma", "attention_tc5", "geometry", "layernorm", "m4c", "decode", "pool", "lstm", "gemm_ln"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -63,6 +63,7 @@ _PROTOS = {
     "ovqa_stage_many": [_vp, _i64, _vp],
     "ovqa_box_geometry_bias": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp],
     "ovqa_ptr_scores": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _i32, _i32, _vp],
+    "ovqa_gemm_ln": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _f32, _f32, _u64, _u64, _vp, _vp],
     "ovqa_lstm_supported": [_i64],
     "ovqa_lstm_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp],
     "ovqa_lstm_bwd": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp],

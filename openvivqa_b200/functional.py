@@ -210,6 +210,18 @@ def _masked_operand(ds: torch.Tensor, ds16: Optional[torch.Tensor], mode: str, p
     return d2 if p == 0.0 else ops.dropout_apply(d2, p, seed, off, offset_base=rng_base)
 
 
+def _proj_residual_ln(a2, w_c, bias, residual, gamma, beta, *, eps, p, seed, off, rng_base, mode, need_grad):
+    """``LayerNorm(dropout(a2 w_c^T + bias) + residual)``: the tail of both blocks (attentions.py:58,331; positionwise_feed_forward.py:25-26).
+    The GEMM with the fused bias / dropout / residual epilogue followed by the LayerNorm kernel; or, opt-in (``OVQA_GEMM_LN=1``, see
+    ``ops.gemm_ln_enabled``: parity-green but currently slower), ONE kernel when the width is the fused kernel's (bf16 operands, 512 columns).  Returns (s, y, y16, mean, rstd); s / mean / rstd only when ``need_grad``."""
+    if mode == "bf16" and ops.gemm_ln_enabled() and ops.gemm_ln_supported(a2, w_c):
+        return ops.gemm_ln(a2, w_c, bias, residual, gamma, beta, eps=eps, dropout_p=p, seed=seed, offset=off, offset_base=rng_base,
+                           save=need_grad, want_bf16=True)
+    s = ops.gemm(a2, w_c, bias=bias, out_dtype=torch.float32, dropout_p=p, seed=seed, offset=off, offset_base=rng_base, residual=residual)
+    y, y16, _, mean, rstd = ops.layernorm_fwd(s, gamma, beta, eps=eps, want_bf16=(mode == "bf16"), save_stats=need_grad)
+    return s, y, y16, mean, rstd
+
+
 # ----------------------------------------------------------------------------- generic Linear (AoA gate, pointer net, ...)
 class _LinearFn(torch.autograd.Function):
     @staticmethod
@@ -288,10 +300,8 @@ class _MHAFn(torch.autograd.Function):
         rng_base = dropout_stream.base(queries.device) if p > 0.0 else None
         q_res = queries.reshape(-1, D)
         q_res = q_res if (q_res.dtype == torch.float32 and q_res.is_contiguous()) else q_res.float().contiguous()
-        s = ops.gemm(att_ctx.view(B * Lq, hv), weights.get([wo], cdt), bias=fb(bo), out_dtype=torch.float32,
-                     dropout_p=p, seed=seed, offset=off, offset_base=rng_base, residual=q_res)
-        y, y16, _, mean, rstd = ops.layernorm_fwd(s, gamma.detach(), beta.detach(), eps=cfg["eps"], want_bf16=(mode == "bf16"),
-                                                  save_stats=need_grad)
+        s, y, y16, mean, rstd = _proj_residual_ln(att_ctx.view(B * Lq, hv), weights.get([wo], cdt), fb(bo), q_res, gamma.detach(), beta.detach(),
+                                                  eps=cfg["eps"], p=p, seed=seed, off=off, rng_base=rng_base, mode=mode, need_grad=need_grad)
         y = y.view(B, Lq, D)
         if need_grad:
             ctx.save_for_backward(xq, xk, xv, mask, *proj, att_ctx, lse, s, mean, rstd, gamma, wq, wk, wv, wo,
@@ -552,10 +562,8 @@ class _PWFFFn(torch.autograd.Function):
         s2, o2 = dropout_stream.next(M * D) if p > 0.0 else (0, 0)
         x_res = x.reshape(-1, D)
         x_res = x_res if (x_res.dtype == torch.float32 and x_res.is_contiguous()) else x_res.float().contiguous()
-        s = ops.gemm(hact, weights.get([w2], cdt), bias=weights.get([b2], torch.float32), out_dtype=torch.float32,
-                     dropout_p=p, seed=s2, offset=o2, offset_base=rng_base, residual=x_res)
-        y, y16, _, mean, rstd = ops.layernorm_fwd(s, gamma.detach(), beta.detach(), eps=cfg["eps"], want_bf16=(mode == "bf16"),
-                                                  save_stats=need_grad)
+        s, y, y16, mean, rstd = _proj_residual_ln(hact, weights.get([w2], cdt), weights.get([b2], torch.float32), x_res, gamma.detach(), beta.detach(),
+                                                  eps=cfg["eps"], p=p, seed=s2, off=o2, rng_base=rng_base, mode=mode, need_grad=need_grad)
         if need_grad:
             ctx.save_for_backward(x2, pre, hact, s, mean, rstd, gamma, w1, w2)
             ctx.cfg, ctx.p, ctx.rng, ctx.rng_base = cfg, p, (s1, o1, s2, o2), rng_base

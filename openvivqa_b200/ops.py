@@ -5,6 +5,8 @@ error (SURVEY.md §8b "Errors": no CPU fallback).
 """
 from __future__ import annotations
 
+import os
+
 import math
 from typing import Optional
 
@@ -436,6 +438,41 @@ def ptr_scores(q, k, mask, scores, col_offset: int, scale: float, mask_is_bool: 
     L.call("ovqa_ptr_scores", _p(q), _p(k), _p(mask), _p(scores), B, T, Lk, d, q.stride(1), k.stride(1), scores.shape[-1],
            col_offset, float(scale), _DT[q.dtype], int(mask_is_bool), _stream())
     return scores
+
+
+def gemm_ln_supported(a: torch.Tensor, w: torch.Tensor) -> bool:
+    """Shapes the fused projection + LayerNorm kernel takes (``ovqa_gemm_ln``): bf16 CUDA operands, 512 output columns, 16-byte aligned rows."""
+    return (a.is_cuda and a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2 and w.shape[0] == 512
+            and a.shape[1] == w.shape[1] and a.stride(1) == 1 and w.stride(1) == 1 and a.stride(0) % 8 == 0 and w.stride(0) % 8 == 0
+            and a.data_ptr() % 16 == 0 and w.data_ptr() % 16 == 0)
+
+
+def gemm_ln_enabled() -> bool:
+    """Whether the blocks route their fc_o / fc2 + LayerNorm tail through :func:`gemm_ln`.  OFF by default: the kernel is parity-green
+    (tests/test_gpu_gemm_ln.py) but measured SLOWER than the two-kernel form it would replace (MCAN step 11.00 vs 10.65 ms: its epilogue's
+    per-chunk TMA round trips are serialised and, with all of tensor memory taken by one accumulator, do not overlap the next tile's main
+    loop — DESIGN.md §9).  ``OVQA_GEMM_LN=1`` turns it on."""
+    return os.environ.get("OVQA_GEMM_LN", "0") == "1"
+
+
+def gemm_ln(a, w, bias, residual, gamma, beta, *, eps: float = 1e-5, dropout_p: float = 0.0, seed: int = 0, offset: int = 0, offset_base=None,
+            save: bool = True, want_bf16: bool = True):
+    """``s = dropout(a w^T + bias) + residual;  y = LayerNorm(s) * gamma + beta`` in one kernel (N = 512).  Returns (s | None, y, y16 | None,
+    mean | None, rstd | None): ``s``, ``mean``, ``rstd`` (what :func:`layernorm_bwd` needs) only when ``save``."""
+    _need_cuda(a, w, bias, residual, gamma, beta)
+    m, n = a.shape[0], w.shape[0]
+    if residual.dtype != torch.float32 or tuple(residual.shape) != (m, n) or not residual.is_contiguous():
+        raise ValueError("gemm_ln: residual must be contiguous fp32 [m, n]")
+    dev = a.device
+    y = torch.empty((m, n), device=dev, dtype=torch.float32)
+    y16 = torch.empty((m, n), device=dev, dtype=torch.bfloat16) if want_bf16 else None
+    s = torch.empty((m, n), device=dev, dtype=torch.float32) if save else None
+    mean = torch.empty((m,), device=dev, dtype=torch.float32) if save else None
+    rstd = torch.empty((m,), device=dev, dtype=torch.float32) if save else None
+    if m > 0:
+        L.call("ovqa_gemm_ln", _p(a), _p(w), _p(bias), _p(residual), _p(gamma), _p(beta), _p(s), _p(y), _p(y16), _p(mean), _p(rstd), m, n, a.shape[1],
+               a.stride(0), w.stride(0), float(eps), float(dropout_p), int(seed), int(offset), _p(offset_base), _stream())
+    return s, y, y16, mean, rstd
 
 
 def lstm_supported(H: int) -> bool:

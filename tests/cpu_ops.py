@@ -117,6 +117,14 @@ def box_geometry_bias(geo, h):
     return geo_log_bias(geo, h)
 
 
+def gemm_ln_supported(a, w):
+    return False          # the CPU restatement of the blocks keeps the two-step form (gemm + layernorm_fwd)
+
+
+def gemm_ln_enabled():
+    return False
+
+
 def lstm_supported(H):
     return H in (128, 256, 512) or H % 4 == 0      # (the CPU restatement has no shape limits; small sizes keep the host-logic tests fast)
 
@@ -406,7 +414,7 @@ def pwff_infer_block(plan, x, *, d_ff, eps=1e-5):
 
 
 OPS = ("gemm", "sdpa_fwd", "sdpa_bwd", "layernorm_fwd", "layernorm_bwd", "cast_rows_padmask", "mul_to_bf16", "to_bf16", "to_f32", "colsum",
-       "add", "dropout_apply", "dropout_keep_mask", "stage_many", "advance_u64", "box_geometry_bias", "geo_bias", "geo_bias_bwd", "attr_pool_fwd", "attr_pool_bwd", "lstm_supported", "lstm_fwd", "lstm_bwd", "ptr_scores", "ptr_scores_bwd",
+       "add", "dropout_apply", "dropout_keep_mask", "stage_many", "advance_u64", "box_geometry_bias", "geo_bias", "geo_bias_bwd", "attr_pool_fwd", "attr_pool_bwd", "lstm_supported", "lstm_fwd", "lstm_bwd", "gemm_ln_supported", "gemm_ln_enabled", "ptr_scores", "ptr_scores_bwd",
        "prev_pred_embed", "greedy_step", "topk_rows", "mha_decode_step", "pwff_infer")
 
 
